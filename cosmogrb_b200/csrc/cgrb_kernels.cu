@@ -1,0 +1,1331 @@
+// cgrb_kernels.cu -- sm_100a kernels + C ABI of the photon-event engine.
+//
+// One translation unit; see include/cosmogrb_b200.h for the boundary and DESIGN.md for the
+// data layout and the roofline of each kernel.  Reference lines are relative to the cosmogrb
+// repository root.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "cgrb_device.cuh"
+
+using namespace cgrb;
+
+// ==========================================================================================
+// error plumbing
+// ==========================================================================================
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+static int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return CGRB_E_CUDA;
+    }
+    return CGRB_OK;
+}
+
+#define NT 256            // threads per CTA of the event kernels
+#define NW (NT / 32)
+
+// ==========================================================================================
+// shared helpers
+// ==========================================================================================
+
+// inclusive block scan of doubles over NT threads; s_w holds NW doubles.  Returns the inclusive
+// value, *total = sum over the block.  Contains two __syncthreads and one trailing barrier.
+__device__ __forceinline__ double block_incl_scan(double v, double *s_w, double *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_incl_scan(v, lane);
+    if (lane == 31)
+        s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double w = (lane < NW) ? s_w[lane] : 0.0;
+        w = warp_incl_scan(w, lane);
+        if (lane < NW)
+            s_w[lane] = w;
+    }
+    __syncthreads();
+    double prefix = (wid > 0) ? s_w[wid - 1] : 0.0;
+    *total = s_w[NW - 1];
+    double r = prefix + v;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ int block_incl_scan_i(int v, int *s_w, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_incl_scan_i(v, lane);
+    if (lane == 31)
+        s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < NW) ? s_w[lane] : 0;
+        w = warp_incl_scan_i(w, lane);
+        if (lane < NW)
+            s_w[lane] = w;
+    }
+    __syncthreads();
+    int prefix = (wid > 0) ? s_w[wid - 1] : 0;
+    *total = s_w[NW - 1];
+    int r = prefix + v;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ long long block_sum_ll(long long v, long long *s_w)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0)
+        s_w[wid] = v;
+    __syncthreads();
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++)
+        t += s_w[w];
+    __syncthreads();
+    return t;
+}
+
+// thinning uniforms of candidate k: u1 -> gap, u2 -> acceptance (source) / unused (background)
+struct ThinDraw {
+    double u1, u2;
+    bool exhausted;
+};
+__device__ __forceinline__ ThinDraw thin_draw(const cgrb_rng_t &rng, int unit, uint32_t stream_id,
+                                              uint32_t stage, int64_t k)
+{
+    ThinDraw d;
+    d.exhausted = false;
+    if (rng.mode == 0) {
+        Philox4 p = philox_at(make_key(rng.seed), stream_id, stage, (uint64_t)k, 0u);
+        d.u1 = u53(p.x, p.y);
+        d.u2 = u53(p.z, p.w);
+    } else {
+        int64_t off = rng.d_off ? rng.d_off[unit] : 0;
+        int64_t len = rng.d_len ? rng.d_len[unit] : ((int64_t)1 << 62);
+        if (2 * k + 1 < len) {
+            d.u1 = rng.d_u[off + 2 * k];
+            d.u2 = rng.d_u[off + 2 * k + 1];
+        } else if (2 * k < len) {   // the reference's stream ends on an odd count (Appendix A)
+            d.u1 = rng.d_u[off + 2 * k];
+            d.u2 = 0.5;
+        } else {
+            d.u1 = 0.0;             // -log(0) = +inf: terminates the unit
+            d.u2 = 0.5;
+            d.exhausted = true;
+        }
+    }
+    return d;
+}
+
+// per-unit tables for lambda(t): lambda = norm * ec^-alpha * sum_m c_m exp(-x_m / ec)
+struct LambdaTab {
+    double c[CGRB_NE_LAMBDA];
+    double x[CGRB_NE_LAMBDA];
+};
+
+// builds the table cooperatively; caller syncs afterwards
+__device__ __forceinline__ void build_lambda_tab(LambdaTab *tab, const double *dt, const cgrb_unit_t &u)
+{
+    const double *E = dt + CGRB_DT_G75_E;
+    const double *A = dt + CGRB_DT_G75_A;
+    const double opz = 1.0 + u.z;
+    for (int m = threadIdx.x; m < CGRB_NE_LAMBDA; m += blockDim.x) {
+        // np.trapz weights of cpl_functions.py:325
+        double w;
+        if (m == 0)
+            w = 0.5 * (E[1] - E[0]);
+        else if (m == CGRB_NE_LAMBDA - 1)
+            w = 0.5 * (E[m] - E[m - 1]);
+        else
+            w = 0.5 * (E[m] - E[m - 1]) + 0.5 * (E[m + 1] - E[m]);
+        double x = E[m] * opz;                       // cpl_functions.py:95
+        tab->x[m] = x;
+        tab->c[m] = w * A[m] * pow(x, u.alpha);
+    }
+}
+
+__device__ __forceinline__ double lambda_at(const LambdaTab *tab, const cgrb_unit_t &u, double t)
+{
+    SpecT s = spec_at(u, t);
+    double acc = 0.0;
+#pragma unroll 5
+    for (int m = 0; m < CGRB_NE_LAMBDA; m++)
+        acc += tab->c[m] * exp(-tab->x[m] * s.inv_ec);
+    return s.norm * exp(-u.alpha * s.log_ec) * acc;
+}
+
+// ==========================================================================================
+// spectral model kernels
+// ==========================================================================================
+
+// SourceFunction.energy_integrated_evolution at arbitrary times
+__global__ void __launch_bounds__(NT) k_lambda(const double *__restrict__ dtab, const cgrb_unit_t *units,
+                                               int unit_index, const double *__restrict__ times,
+                                               int64_t n, double *__restrict__ out)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    if (threadIdx.x == 0)
+        u = units[unit_index];
+    __syncthreads();
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT)
+        out[i] = lambda_at(&tab, u, times[i]);
+}
+
+// SourceFunction.evolution(energy, time): cpl_evolution without the response
+__global__ void __launch_bounds__(NT) k_evolution(const cgrb_unit_t *units, int unit_index,
+                                                  const double *__restrict__ energy, int64_t n_energy,
+                                                  const double *__restrict__ times, int64_t n_time,
+                                                  double *__restrict__ out)
+{
+    __shared__ cgrb_unit_t u;
+    if (threadIdx.x == 0)
+        u = units[unit_index];
+    __syncthreads();
+    const double opz = 1.0 + u.z;
+    for (int64_t it = blockIdx.x; it < n_time; it += gridDim.x) {
+        SpecT s = spec_at(u, times[it]);
+        for (int64_t m = threadIdx.x; m < n_energy; m += NT) {
+            double x = energy[m] * opz;
+            out[it * n_energy + m] = cpl_value(s, u.alpha, x, log(x));
+        }
+    }
+}
+
+// Source._get_energy_integrated_max: one CTA per unit, 50-point time grid (source.py:88-110)
+__global__ void __launch_bounds__(64) k_fmax(const double *__restrict__ dtab, cgrb_unit_t *units, int n_units)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    __shared__ double s_f[64];
+    const int ui = blockIdx.x;
+    if (ui >= n_units)
+        return;
+    if (threadIdx.x == 0)
+        u = units[ui];
+    __syncthreads();
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    __syncthreads();
+    double f = -INFINITY;
+    if (threadIdx.x < CGRB_NT_FMAX) {
+        // np.linspace(tstart, tstop, 50)
+        double step = (u.src_tstop - u.src_tstart) / (double)(CGRB_NT_FMAX - 1);
+        double t = (threadIdx.x == CGRB_NT_FMAX - 1) ? u.src_tstop : u.src_tstart + threadIdx.x * step;
+        f = lambda_at(&tab, u, t);
+    }
+    s_f[threadIdx.x] = f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double best = s_f[0];
+        bool has_nan = isnan(best);
+        for (int i = 1; i < CGRB_NT_FMAX; i++) {
+            has_nan |= isnan(s_f[i]);
+            if (s_f[i] > best)
+                best = s_f[i];
+        }
+        units[ui].fmax = has_nan ? nan("") : best;   // np.max propagates NaN
+    }
+}
+
+// ==========================================================================================
+// thinning pass 1: sum of exponential gaps of each segment, in exactly the association order
+// that pass 3 uses for its running time, so that segment boundaries are exactly consistent.
+// ==========================================================================================
+template <int WHICH>  // 0 = source, 1 = background
+__global__ void __launch_bounds__(NT) k_gap_sums(const cgrb_unit_t *__restrict__ units,
+                                                 const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                 cgrb_rng_t rng, double *__restrict__ segsum,
+                                                 cgrb_counts_t *counts)
+{
+    __shared__ double s_w[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t cap = (WHICH == 0) ? u->src_cap : u->bkg_cap;
+    const double rate = (WHICH == 0) ? u->fmax : u->bkg_rate;
+    const double inv_f = 1.0 / rate;
+    const uint32_t stage = (WHICH == 0) ? ST_SRC_TIME : ST_BKG;
+    const uint32_t sid = u->stream_id;
+    const int64_t n = min((int64_t)CGRB_SEG, cap - wk.start);
+    double carry = 0.0;
+    bool exhausted = false;
+    for (int64_t base = 0; base < n; base += NT) {
+        int64_t k = wk.start + base + threadIdx.x;
+        double gap = 0.0;
+        if (base + threadIdx.x < n) {
+            ThinDraw d = thin_draw(rng, wk.unit, sid, stage, k);
+            gap = -(inv_f * log(d.u1));      // time - (1/fmax) * log(u)  cpl_functions.py:160
+            exhausted |= d.exhausted;
+        }
+        double total;
+        (void)block_incl_scan(gap, s_w, &total);
+        carry = carry + total;   // no early exit: same association order as pass 3
+    }
+    if (threadIdx.x == 0)
+        segsum[w] = carry;
+    if (exhausted)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
+}
+
+// pass 2: sequential (association-exact) scan of the segment sums of each unit: one warp per unit
+template <int WHICH>
+__global__ void __launch_bounds__(128) k_seg_scan(const cgrb_unit_t *__restrict__ units, int n_units,
+                                                  const int64_t *__restrict__ unit_work_begin,
+                                                  const double *__restrict__ segsum,
+                                                  double *__restrict__ segstart, cgrb_counts_t *counts)
+{
+    const int lane = threadIdx.x & 31;
+    const int ui = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ui >= n_units)
+        return;
+    const cgrb_unit_t *u = units + ui;
+    const double tstart = (WHICH == 0) ? u->src_tstart : u->bkg_tstart;
+    const double tstop = (WHICH == 0) ? u->src_tstop : u->bkg_tstop;
+    const int64_t b = unit_work_begin[ui], e = unit_work_begin[ui + 1];
+    double t = tstart;
+    for (int64_t s0 = b; s0 < e; s0 += 32) {
+        double v = (s0 + lane < e) ? segsum[s0 + lane] : 0.0;
+        double mine = 0.0;
+        for (int j = 0; j < 32; j++) {
+            double vj = __shfl_sync(0xffffffffu, v, j);
+            if (lane == j)
+                mine = t;
+            t = t + vj;     // same order on every lane
+        }
+        if (s0 + lane < e)
+            segstart[s0 + lane] = mine;
+    }
+    const uint32_t disabled = (WHICH == 0) ? (u->flags & CGRB_UNIT_NO_SOURCE) : (u->flags & CGRB_UNIT_NO_BACKGROUND);
+    if (lane == 0 && !disabled && !(t > tstop))
+        atomicOr(&counts[ui].status, (WHICH == 0) ? CGRB_ST_SRC_CAPACITY : CGRB_ST_BKG_CAPACITY);
+}
+
+// ==========================================================================================
+// source thinning pass 3 (cpl_functions.py:134-188): candidate times by block scan, lambda(t),
+// acceptance, ordered compaction of accepted times into the segment's staging slots.
+// ==========================================================================================
+__global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ dtab,
+                                                    const cgrb_unit_t *__restrict__ units,
+                                                    const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                    cgrb_rng_t rng, const double *__restrict__ segstart,
+                                                    int32_t *__restrict__ segcount, double *__restrict__ stage,
+                                                    double *__restrict__ cand_times,
+                                                    uint8_t *__restrict__ cand_accept, cgrb_counts_t *counts)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    __shared__ double s_w[NW];
+    __shared__ int s_wi[NW];
+    __shared__ double s_t[NT];
+    __shared__ double s_last;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    if (threadIdx.x == 0)
+        u = units[wk.unit];
+    __syncthreads();
+    const double t0 = segstart[w];
+    if ((u.flags & CGRB_UNIT_NO_SOURCE) || t0 > u.src_tstop) {   // dead segment
+        if (threadIdx.x == 0)
+            segcount[w] = 0;
+        return;
+    }
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    if (threadIdx.x == 0)
+        s_last = t0;
+    __syncthreads();
+
+    const double inv_f = 1.0 / u.fmax;
+    const int64_t n = min((int64_t)CGRB_SEG, u.src_cap - wk.start);
+    double carry = 0.0;
+    int seg_n = 0;        // accepted so far in this segment
+    int n_valid_total = 0;
+    bool exhausted = false;
+    for (int64_t base = 0; base < n; base += NT) {
+        const int64_t k = wk.start + base + threadIdx.x;
+        const bool inrange = base + threadIdx.x < n;
+        double gap = 0.0, u2 = 2.0;
+        if (inrange) {
+            ThinDraw d = thin_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, k);
+            gap = -(inv_f * log(d.u1));
+            u2 = d.u2;
+            exhausted |= d.exhausted;
+        }
+        double total;
+        double incl = block_incl_scan(gap, s_w, &total);
+        double t = t0 + (carry + incl);
+        carry = carry + total;
+        // enforce non-decreasing times across association orders (1-ulp inversions)
+        s_t[threadIdx.x] = t;
+        __syncthreads();
+        double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
+        t = fmax(t, left);
+        const bool valid = inrange && (t <= u.src_tstop);   // `if time > tstop: break`
+        bool acc = false;
+        if (valid) {
+            double p_test = lambda_at(&tab, u, t) / u.fmax;
+            acc = (u2 <= p_test);                           // `if test <= p_test`
+        }
+        // ordered compaction
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        unsigned bal = __ballot_sync(0xffffffffu, acc);
+        unsigned balv = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0)
+            s_wi[wid] = __popc(bal) | (__popc(balv) << 16);
+        __syncthreads();
+        int before = 0, tile_acc = 0, tile_valid = 0;
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            int c = s_wi[q] & 0xffff, v = s_wi[q] >> 16;
+            if (q < wid)
+                before += c;
+            tile_acc += c;
+            tile_valid += v;
+        }
+        if (acc) {
+            int rank = before + __popc(bal & ((1u << lane) - 1u));
+            stage[u.src_off + wk.start + seg_n + rank] = t;
+        }
+        if (valid && cand_times) {
+            cand_times[u.src_off + k] = t;
+            cand_accept[u.src_off + k] = acc ? 1 : 0;
+        }
+        seg_n += tile_acc;
+        n_valid_total += tile_valid;
+        if (threadIdx.x == NT - 1)
+            s_last = t;
+        __syncthreads();
+        if (tile_valid < (int)min((int64_t)NT, n - base))
+            break;      // crossed tstop: everything later is beyond it
+    }
+    if (threadIdx.x == 0) {
+        segcount[w] = seg_n;
+        if (n_valid_total)
+            atomicAdd((unsigned long long *)&counts[wk.unit].n_candidates, (unsigned long long)n_valid_total);
+    }
+    if (exhausted)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
+}
+
+// pass 5: gather the per-segment accepted times into the unit's contiguous list; entry 0 is the
+// spurious tstart event of cpl_functions.py:153-154.
+__global__ void __launch_bounds__(NT) k_source_gather(const cgrb_unit_t *__restrict__ units,
+                                                      const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                      const int64_t *__restrict__ unit_work_begin,
+                                                      const int32_t *__restrict__ segcount,
+                                                      const double *__restrict__ stage,
+                                                      double *__restrict__ times_src, cgrb_counts_t *counts)
+{
+    __shared__ long long s_w[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t b = unit_work_begin[wk.unit], e = unit_work_begin[wk.unit + 1];
+    long long part = 0;
+    for (int64_t s = b + threadIdx.x; s < w; s += NT)
+        part += segcount[s];
+    const long long off = block_sum_ll(part, s_w);
+    const int cnt = segcount[w];
+    const double *src = stage + u->src_off + wk.start;
+    double *dst = times_src + u->src_off + 1 + off;
+    for (int j = threadIdx.x; j < cnt; j += NT)
+        dst[j] = src[j];
+    if (threadIdx.x == 0) {
+        if (w == b)
+            times_src[u->src_off] = u->src_tstart;
+        if (w == e - 1)
+            counts[wk.unit].n_src = (u->flags & CGRB_UNIT_NO_SOURCE) ? 0 : 1 + off + cnt;
+    }
+}
+
+// ==========================================================================================
+// background (background.py:13-44 + numpy choice :93): every candidate is an event; event j of
+// the unit is candidate j-1, event 0 is the spurious tstart event.
+// ==========================================================================================
+__global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dtab,
+                                                   const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   cgrb_rng_t rng, cgrb_rng_t rng_chan,
+                                                   const double *__restrict__ segstart,
+                                                   double *__restrict__ times_bkg, uint8_t *__restrict__ pha_bkg,
+                                                   cgrb_counts_t *counts)
+{
+    __shared__ double s_cdf[CGRB_NCHAN];
+    __shared__ double s_w[NW];
+    __shared__ int s_wi[NW];
+    __shared__ double s_t[NT];
+    __shared__ double s_last;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    if (u->flags & CGRB_UNIT_NO_BACKGROUND)
+        return;
+    const double t0 = segstart[w];
+    const double tstop = u->bkg_tstop;
+    const int64_t off = u->bkg_off;
+    const uint32_t sid = u->stream_id;
+    const double *cdf_g = dtab + (size_t)u->det * CGRB_DT_SIZE + CGRB_DT_BKG_CDF;
+    if (threadIdx.x < CGRB_NCHAN)
+        s_cdf[threadIdx.x] = cdf_g[threadIdx.x];
+    if (threadIdx.x == 0)
+        s_last = t0;
+    __syncthreads();
+
+    if (wk.start == 0 && threadIdx.x == 0) {
+        // event 0: tstart, with its own channel draw (sample_channel(size=len(times)))
+        double uc;
+        if (rng.mode == 0) {
+            Philox4 p = philox_at(make_key(rng.seed), sid, ST_BKG, 0xFFFFFFFFFFull, 0u);
+            uc = u53(p.z, p.w);
+        } else {
+            int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
+            uc = rng_chan.d_u[o];
+        }
+        times_bkg[off] = u->bkg_tstart;
+        pha_bkg[off] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, uc), CGRB_NCHAN - 1);
+        atomicAdd((unsigned long long *)&counts[wk.unit].n_bkg, 1ull);
+    }
+    if (t0 > tstop)
+        return;
+
+    const double inv_f = 1.0 / u->bkg_rate;
+    const int64_t n = min((int64_t)CGRB_SEG, u->bkg_cap - wk.start);
+    double carry = 0.0;
+    int n_valid_total = 0;
+    bool exhausted = false;
+    for (int64_t base = 0; base < n; base += NT) {
+        const int64_t k = wk.start + base + threadIdx.x;
+        const bool inrange = base + threadIdx.x < n;
+        double gap = 0.0, uc = 0.0;
+        if (inrange) {
+            ThinDraw d = thin_draw(rng, wk.unit, sid, ST_BKG, k);
+            gap = -(inv_f * log(d.u1));
+            uc = d.u2;
+            exhausted |= d.exhausted;
+        }
+        double total;
+        double incl = block_incl_scan(gap, s_w, &total);
+        double t = t0 + (carry + incl);
+        carry = carry + total;
+        s_t[threadIdx.x] = t;
+        __syncthreads();
+        double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
+        t = fmax(t, left);
+        const bool valid = inrange && (t <= tstop);
+        if (valid) {
+            if (rng.mode != 0) {
+                int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
+                int64_t len = rng_chan.d_len ? rng_chan.d_len[wk.unit] : ((int64_t)1 << 62);
+                if (k + 1 < len)
+                    uc = rng_chan.d_u[o + k + 1];
+                else {
+                    uc = 0.5;
+                    exhausted = true;
+                }
+            }
+            times_bkg[off + k + 1] = t;
+            pha_bkg[off + k + 1] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, uc), CGRB_NCHAN - 1);
+        }
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        unsigned balv = __ballot_sync(0xffffffffu, valid);
+        if (lane == 0)
+            s_wi[wid] = __popc(balv);
+        __syncthreads();
+        int tile_valid = 0;
+#pragma unroll
+        for (int q = 0; q < NW; q++)
+            tile_valid += s_wi[q];
+        n_valid_total += tile_valid;
+        if (threadIdx.x == NT - 1)
+            s_last = t;
+        __syncthreads();
+        if (tile_valid < (int)min((int64_t)NT, n - base))
+            break;
+    }
+    if (threadIdx.x == 0 && n_valid_total)
+        atomicAdd((unsigned long long *)&counts[wk.unit].n_bkg, (unsigned long long)n_valid_total);
+    if (exhausted)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
+}
+
+// ==========================================================================================
+// photon energies (cpl_functions.py:191-286): one warp per photon.  The 500-point envelope
+// maximum is found on log f (monotone in f, no exp); the rejection loop runs 32 trials per round,
+// one per lane, and the lowest accepted trial wins, which is the serial loop's result.
+// ==========================================================================================
+struct EnergyTab {
+    double gx[CGRB_NE_ENVELOPE];   // x_m = E_m (1+z)
+    double gl[CGRB_NE_ENVELOPE];   // log(A_m) + alpha log(x_m)   (-inf where A_m <= 0)
+    double eax[CGRB_NBINS];
+    double eay[CGRB_NBINS];
+};
+
+__global__ void __launch_bounds__(NT) k_sample_energy(const double *__restrict__ dtab,
+                                                      const cgrb_unit_t *__restrict__ units,
+                                                      const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                      int interp_extrap, cgrb_rng_t rng, int64_t max_trials,
+                                                      const double *__restrict__ times_src,
+                                                      double *__restrict__ energy_src,
+                                                      int32_t *__restrict__ trials_out, cgrb_counts_t *counts)
+{
+    __shared__ EnergyTab tab;
+    __shared__ cgrb_unit_t u;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const int64_t n_src = counts[wk.unit].n_src;
+    if (wk.start >= n_src)
+        return;
+    if (threadIdx.x == 0)
+        u = units[wk.unit];
+    __syncthreads();
+    const double *dt = dtab + (size_t)u.det * CGRB_DT_SIZE;
+    const double opz = 1.0 + u.z;
+    const double alpha = u.alpha;
+    for (int m = threadIdx.x; m < CGRB_NE_ENVELOPE; m += NT) {
+        double x = dt[CGRB_DT_G500_E + m] * opz;
+        double A = dt[CGRB_DT_G500_A + m];
+        tab.gx[m] = x;
+        tab.gl[m] = (A > 0.0) ? log(A) + alpha * log(x) : -INFINITY;
+    }
+    for (int m = threadIdx.x; m < CGRB_NBINS; m += NT) {
+        tab.eax[m] = dt[CGRB_DT_EA_X + m];
+        tab.eay[m] = dt[CGRB_DT_EA_Y + m];
+    }
+    __syncthreads();
+
+    const double emin = dt[CGRB_DT_EDGES], emax = dt[CGRB_DT_EDGES + CGRB_NBINS];
+    // power-law proposal constants (cpl_functions.py:254-258)
+    const double ap1 = alpha + 1.0;
+    const double q_lo = pow(emin, ap1);
+    const double p_span = pow(emax, ap1) - q_lo;
+    const double inv_ap1 = 1.0 / ap1;
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // chunk end: next work entry of the same unit starts where this chunk ends
+    int64_t chunk_end = n_src;
+    if (w + 1 < n_work && work[w + 1].unit == wk.unit)
+        chunk_end = min(n_src, work[w + 1].start);
+
+    long long my_trials = 0;
+    bool exhausted = false, capped = false;
+    for (int64_t i = wk.start + wid; i < chunk_end; i += NW) {
+        const double t = times_src[u.src_off + i];
+        const SpecT s = spec_at(u, t);
+        // argmax of the folded spectrum on the 500-point grid (first maximum), via log f
+        double best = -INFINITY;
+        int bidx = CGRB_NE_ENVELOPE;
+        for (int m = lane; m < CGRB_NE_ENVELOPE; m += 32) {
+            double g = tab.gl[m] - tab.gx[m] * s.inv_ec;
+            if (g > best) {
+                best = g;
+                bidx = m;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, d);
+            int oi = __shfl_xor_sync(0xffffffffu, bidx, d);
+            if (ob > best || (ob == best && oi < bidx)) {
+                best = ob;
+                bidx = oi;
+            }
+        }
+        int idx = (bidx < CGRB_NE_ENVELOPE) ? bidx : 0;
+        // literal tmp[idx] = interp(E_idx) * cpl(E_idx (1+z))
+        double A_idx = dt[CGRB_DT_G500_A + idx];
+        double f_idx = A_idx * cpl_value(s, alpha, tab.gx[idx], log(tab.gx[idx]));
+        if (!(f_idx > 0.0)) {       // all-zero (K = 0 before the pulse) or degenerate: np.argmax -> 0
+            idx = 0;
+            A_idx = dt[CGRB_DT_G500_A];
+            f_idx = A_idx * cpl_value(s, alpha, tab.gx[0], log(tab.gx[0]));
+        }
+        const double C = f_idx * 5.0;                         // :241
+        const double e_idx = dt[CGRB_DT_G500_E + idx];
+
+        int64_t base_pos = 0;
+        if (rng.mode != 0)
+            base_pos = rng.d_off[u.src_off + i];
+        const int64_t u_len = (rng.mode != 0 && rng.d_len) ? rng.d_len[0] : ((int64_t)1 << 62);
+
+        double x_acc = nan("");
+        int64_t ntr = 0;
+        for (int64_t round = 0;; round++) {
+            const int64_t j = round * 32 + lane;
+            double u1, u2;
+            bool ok = true;
+            if (rng.mode == 0) {
+                Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, (uint32_t)j);
+                u1 = u53(p.x, p.y);
+                u2 = u53(p.z, p.w);
+            } else {
+                int64_t pos = base_pos + 2 * j;
+                if (pos + 1 < u_len) {
+                    u1 = rng.d_u[pos];
+                    u2 = rng.d_u[pos + 1];
+                } else {
+                    u1 = 0.5;
+                    u2 = 0.0;
+                    ok = false;
+                }
+            }
+            double x = pow(p_span * u1 + q_lo, inv_ap1);                       // :253-258
+            double y = u2 * C * pow(x / e_idx, alpha);                         // :260
+            double xr = x * opz;
+            double fx = interp1(tab.eax, tab.eay, CGRB_NBINS, x, interp_extrap) *
+                        cpl_value(s, alpha, xr, log(xr));
+            bool accept = (y <= fx) || !ok;
+            unsigned bal = __ballot_sync(0xffffffffu, accept);
+            if (bal) {
+                int win = __ffs(bal) - 1;
+                x_acc = __shfl_sync(0xffffffffu, x, win);
+                bool ok_w = __shfl_sync(0xffffffffu, (int)ok, win);
+                if (!ok_w) {
+                    exhausted = true;
+                    x_acc = nan("");
+                }
+                ntr = round * 32 + win + 1;
+                break;
+            }
+            if (max_trials > 0 && (round + 1) * 32 >= max_trials) {
+                capped = true;
+                ntr = (round + 1) * 32;
+                break;
+            }
+        }
+        if (lane == 0) {
+            energy_src[u.src_off + i] = x_acc;
+            if (trials_out)
+                trials_out[u.src_off + i] = (int32_t)ntr;
+            my_trials += ntr;
+        }
+    }
+    if (lane == 0 && my_trials)
+        atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)my_trials);
+    if (lane == 0 && (exhausted || capped))
+        atomicOr(&counts[wk.unit].status,
+                 (exhausted ? CGRB_ST_UNIFORMS_EXHAUSTED : 0u) | (capped ? CGRB_ST_TRIAL_CAP : 0u));
+}
+
+// ==========================================================================================
+// digitize (response.py:10-25): photon bin by searchsorted on the edges, then the NEAREST value
+// of the row-cumulative matrix (argmin |cum - r|, first index on ties), found by binary search.
+// The detector's 140x128 cumulative matrix (143,360 B) is staged into shared memory with one
+// mbarrier-tracked bulk-async (TMA) copy per CTA when the chunk is large enough to amortise it.
+// ==========================================================================================
+__device__ __forceinline__ int nearest_cdf(const double *row, double r)
+{
+    // j = first index with row[j] >= r
+    int lo = 0, hi = CGRB_NCHAN;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (row[mid] < r)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    int jhi = min(lo, CGRB_NCHAN - 1);
+    int jlo = max(lo - 1, 0);
+    double dlo = fabs(row[jlo] - r), dhi = fabs(row[jhi] - r);
+    int pick = (dhi < dlo) ? jhi : jlo;            // tie -> lower index
+    double v = row[pick];
+    // first index holding that value
+    lo = 0;
+    hi = pick;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (row[mid] < v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+#define CUM_BYTES (CGRB_NBINS * CGRB_NCHAN * 8)
+#define DIGITIZE_STAGE_MIN 1024
+
+__global__ void __launch_bounds__(NT) k_digitize(const double *__restrict__ dtab,
+                                                 const cgrb_unit_t *__restrict__ units,
+                                                 const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                 cgrb_rng_t rng, const double *__restrict__ energy_src,
+                                                 uint8_t *__restrict__ pha_src, const cgrb_counts_t *counts)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_cum = reinterpret_cast<double *>(smem_raw);                       // [140*128]
+    double *s_edges = reinterpret_cast<double *>(smem_raw + CUM_BYTES);          // [141] (+pad)
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + CUM_BYTES + 144 * 8);
+
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const int64_t n_src = counts[wk.unit].n_src;
+    if (wk.start >= n_src)
+        return;
+    int64_t chunk_end = n_src;
+    if (w + 1 < n_work && work[w + 1].unit == wk.unit)
+        chunk_end = min(n_src, work[w + 1].start);
+    const cgrb_unit_t *u = units + wk.unit;
+    const double *dt = dtab + (size_t)u->det * CGRB_DT_SIZE;
+    const bool staged = (chunk_end - wk.start) >= DIGITIZE_STAGE_MIN;
+
+    if (staged && threadIdx.x == 0) {
+        unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
+        unsigned dst = (unsigned)__cvta_generic_to_shared(s_cum);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)CUM_BYTES)
+                     : "memory");
+        const char *src = reinterpret_cast<const char *>(dt + CGRB_DT_CUM);
+        const unsigned piece = CUM_BYTES / 8;      // 17,920 B, multiple of 16
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    dst + c * piece),
+                "l"(src + (size_t)c * piece), "r"(piece), "r"(bar)
+                : "memory");
+    }
+    for (int m = threadIdx.x; m <= CGRB_NBINS; m += NT)
+        s_edges[m] = dt[CGRB_DT_EDGES + m];
+    __syncthreads();
+    if (staged) {
+        unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(done)
+                : "r"(bar), "r"(0u)
+                : "memory");
+        }
+    }
+    const double *cum = staged ? s_cum : dt + CGRB_DT_CUM;
+
+    for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += NT) {
+        const double e = energy_src[u->src_off + i];
+        int idx = searchsorted_left(s_edges, CGRB_NBINS + 1, e) - 1;      // response.py:14
+        if (idx < 0)
+            idx += CGRB_NBINS;                                            // python negative index
+        if (idx > CGRB_NBINS - 1)
+            idx = CGRB_NBINS - 1;
+        double r;
+        if (rng.mode == 0) {
+            Philox4 p = philox_at(make_key(rng.seed), u->stream_id, ST_SRC_CHAN, (uint64_t)i, 0u);
+            r = u53(p.x, p.y);
+        } else {
+            int64_t o = rng.d_off ? rng.d_off[wk.unit] : 0;
+            r = rng.d_u[o + i];
+        }
+        pha_src[u->src_off + i] = (uint8_t)nearest_cdf(cum + (size_t)idx * CGRB_NCHAN, r);
+    }
+}
+
+// ==========================================================================================
+// combine (lightcurve.py:131-151): merge-path tiles; inside a tile each element finds its rank
+// by a binary search in the other list's slice held in shared memory.
+// ==========================================================================================
+__global__ void __launch_bounds__(NT) k_combine(const cgrb_unit_t *__restrict__ units,
+                                                const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                const double *__restrict__ times_bkg,
+                                                const uint8_t *__restrict__ pha_bkg,
+                                                const double *__restrict__ times_src,
+                                                const uint8_t *__restrict__ pha_src,
+                                                double *__restrict__ times_tot, uint8_t *__restrict__ pha_tot,
+                                                cgrb_counts_t *counts)
+{
+    __shared__ double s_t[CGRB_MERGE_TILE];
+    __shared__ uint8_t s_p[CGRB_MERGE_TILE];
+    __shared__ int64_t s_split[2];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
+    const int64_t total = nA + nB;
+    if (wk.start == 0 && threadIdx.x == 0)
+        counts[wk.unit].n_total = total;
+    if (wk.start >= total)
+        return;
+    const double *A = times_bkg + u->bkg_off;
+    const double *B = times_src + u->src_off;
+    const int64_t d0 = wk.start, d1 = min(d0 + (int64_t)CGRB_MERGE_TILE, total);
+    if (threadIdx.x < 2) {
+        const int64_t d = threadIdx.x ? d1 : d0;
+        int64_t lo = max((int64_t)0, d - nB), hi = min(d, nA);
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (A[mid] <= B[d - 1 - mid])     // ties: background first
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        s_split[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const int64_t i0 = s_split[0], i1 = s_split[1];
+    const int64_t j0 = d0 - i0, j1 = d1 - i1;
+    const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+    for (int k = threadIdx.x; k < na; k += NT) {
+        s_t[k] = A[i0 + k];
+        s_p[k] = pha_bkg[u->bkg_off + i0 + k];
+    }
+    for (int k = threadIdx.x; k < nb; k += NT) {
+        s_t[na + k] = B[j0 + k];
+        s_p[na + k] = pha_src[u->src_off + j0 + k];
+    }
+    __syncthreads();
+    double *out_t = times_tot + u->tot_off + d0;
+    uint8_t *out_p = pha_tot + u->tot_off + d0;
+    for (int k = threadIdx.x; k < na + nb; k += NT) {
+        const double t = s_t[k];
+        int rank;
+        if (k < na) {
+            // number of source events strictly earlier
+            int lo = 0, hi = nb;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (s_t[na + mid] < t)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            rank = k + lo;
+        } else {
+            // number of background events earlier or equal
+            int lo = 0, hi = na;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (t < s_t[mid])
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            rank = (k - na) + lo;
+        }
+        out_t[rank] = t;
+        out_p[rank] = s_p[k];
+    }
+}
+
+// ==========================================================================================
+// GBM dead time, literal reference semantics (gbm_lightcurve.py:80-115).
+//   event 0 is kept and opens a window (10.6 us if overflow channel, else 2.6 us);
+//   afterwards an event is kept iff t > t_end, and ONLY a kept overflow event moves t_end.
+// The chain of dependence runs only through overflow events closer than 10.6 us to each other,
+// so each event resolves its keep flag from a short local look-back (exact for any input).
+// ==========================================================================================
+#define DT_TAU 10.6e-6
+#define DT_NORMAL 2.6e-6
+
+__device__ __forceinline__ double dt_pe(const double *t, const uint8_t *p, int64_t j)
+{
+    return t[j] + ((j == 0 && p[0] != 127) ? DT_NORMAL : DT_TAU);
+}
+
+__device__ __forceinline__ bool dt_keep(const double *__restrict__ t, const uint8_t *__restrict__ p, int64_t i)
+{
+    if (i == 0)
+        return true;
+    const double ti = t[i];
+    // nearest earlier chain element (overflow event or event 0) whose window could cover ti
+    int64_t found = -1;
+    for (int64_t j = i - 1; j >= 0; j--) {
+        if (t[j] + DT_TAU < ti)
+            break;
+        if (p[j] == 127 || j == 0) {
+            found = j;
+            break;
+        }
+    }
+    if (found < 0)
+        return true;
+    // walk back to a chain element that is certainly kept
+    int64_t head = found;
+    while (head > 0) {
+        const double th = t[head];
+        int64_t q = -1;
+        for (int64_t j = head - 1; j >= 0; j--) {
+            if (t[j] + DT_TAU < th)
+                break;
+            if (p[j] == 127 || j == 0) {
+                q = j;
+                break;
+            }
+        }
+        if (q < 0 || dt_pe(t, p, q) < th)
+            break;          // nothing before `head` can veto it
+        head = q;
+    }
+    // replay the reference loop from the head
+    double t_end = dt_pe(t, p, head);
+    for (int64_t j = head + 1; j < i; j++) {
+        if (p[j] == 127) {
+            const double tj = t[j];
+            if (tj > t_end)
+                t_end = tj + DT_TAU;
+        }
+    }
+    return ti > t_end;
+}
+
+__global__ void __launch_bounds__(NT) k_deadtime_count(const cgrb_unit_t *__restrict__ units,
+                                                       const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                       const double *__restrict__ times_tot,
+                                                       const uint8_t *__restrict__ pha_tot,
+                                                       int32_t *__restrict__ tile_count,
+                                                       const cgrb_counts_t *counts)
+{
+    __shared__ int s_wi[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t n = counts[wk.unit].n_total;
+    int cnt = 0;
+    if (wk.start < n) {
+        const double *t = times_tot + u->tot_off;
+        const uint8_t *p = pha_tot + u->tot_off;
+        const int64_t end = min(wk.start + (int64_t)CGRB_DT_TILE, n);
+        for (int64_t i = wk.start + threadIdx.x; i < end; i += NT)
+            cnt += dt_keep(t, p, i) ? 1 : 0;
+    }
+    int total;
+    (void)block_incl_scan_i(cnt, s_wi, &total);
+    if (threadIdx.x == 0)
+        tile_count[w] = total;
+}
+
+__global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__restrict__ units,
+                                                       const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                       const int64_t *__restrict__ unit_work_begin,
+                                                       const double *__restrict__ times_tot,
+                                                       const uint8_t *__restrict__ pha_tot,
+                                                       const int32_t *__restrict__ tile_count,
+                                                       double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
+                                                       uint8_t *__restrict__ selection, cgrb_counts_t *counts)
+{
+    __shared__ long long s_wl[NW];
+    __shared__ int s_wi[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t n = counts[wk.unit].n_total;
+    const int64_t b = unit_work_begin[wk.unit], e = unit_work_begin[wk.unit + 1];
+    long long part = 0;
+    for (int64_t s = b + threadIdx.x; s < w; s += NT)
+        part += tile_count[s];
+    long long off = block_sum_ll(part, s_wl);
+    if (w == e - 1 && threadIdx.x == 0)
+        counts[wk.unit].n_kept = off + tile_count[w];
+    if (wk.start >= n)
+        return;
+    const double *t = times_tot + u->tot_off;
+    const uint8_t *p = pha_tot + u->tot_off;
+    double *ot = times_out + u->tot_off;
+    uint8_t *op = pha_out + u->tot_off;
+    const int64_t end = min(wk.start + (int64_t)CGRB_DT_TILE, n);
+    for (int64_t base = wk.start; base < end; base += NT) {
+        const int64_t i = base + threadIdx.x;
+        bool keep = false;
+        double ti = 0.0;
+        uint8_t pi = 0;
+        if (i < end) {
+            keep = dt_keep(t, p, i);
+            ti = t[i];
+            pi = p[i];
+            if (selection)
+                selection[u->tot_off + i] = keep ? 1 : 0;
+        }
+        int total;
+        int incl = block_incl_scan_i(keep ? 1 : 0, s_wi, &total);
+        if (keep) {
+            ot[off + incl - 1] = ti;
+            op[off + incl - 1] = pi;
+        }
+        off += total;
+    }
+}
+
+__global__ void k_counts_reset(cgrb_counts_t *counts, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        cgrb_counts_t z;
+        memset(&z, 0, sizeof(z));
+        counts[i] = z;
+    }
+}
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+int cgrb_abi_version(void) { return CGRB_ABI_VERSION; }
+
+const char *cgrb_last_error(void) { return g_err; }
+
+int cgrb_device_info(int device, int *out4)
+{
+    if (!out4)
+        return fail(CGRB_E_BADARG, "cgrb_device_info: null output%s");
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess)
+        return fail(CGRB_E_CUDA, "cgrb_device_info: %s", cudaGetErrorString(e));
+    out4[0] = p.multiProcessorCount;
+    out4[1] = p.major;
+    out4[2] = p.minor;
+    out4[3] = (int)p.sharedMemPerBlockOptin;
+    return CGRB_OK;
+}
+
+int64_t cgrb_build_work(const cgrb_unit_t *h_units, int n_units, int which, int64_t chunk,
+                        cgrb_work_t *h_work, int64_t work_cap)
+{
+    if (!h_units || n_units < 0 || chunk <= 0 || which < 0 || which > 3)
+        return fail(CGRB_E_BADARG, "cgrb_build_work: bad argument%s");
+    int64_t n = 0;
+    for (int i = 0; i < n_units; i++) {
+        int64_t cap = which == 0   ? h_units[i].src_cap
+                      : which == 1 ? h_units[i].bkg_cap
+                      : which == 2 ? h_units[i].src_cap + h_units[i].bkg_cap + 2
+                                   : h_units[i].src_cap + 1;
+        int64_t nseg = (cap + chunk - 1) / chunk;
+        if (nseg < 1)
+            nseg = 1;   // every unit owns at least one entry (it carries the per-unit epilogue)
+        for (int64_t s = 0; s < nseg; s++) {
+            if (h_work) {
+                if (n >= work_cap)
+                    return fail(CGRB_E_BADARG, "cgrb_build_work: work_cap too small%s");
+                h_work[n].unit = i;
+                h_work[n].seg = (int32_t)s;
+                h_work[n].start = s * chunk;
+            }
+            n++;
+        }
+    }
+    return n;
+}
+
+int cgrb_counts_reset(cgrb_counts_t *d_counts, int n_units, void *stream)
+{
+    if (!d_counts || n_units <= 0)
+        return fail(CGRB_E_BADARG, "cgrb_counts_reset: bad argument%s");
+    k_counts_reset<<<(n_units + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_counts, n_units);
+    return check_launch("cgrb_counts_reset");
+}
+
+int cgrb_energy_integrated_evolution(const double *d_dtab, const cgrb_unit_t *d_units, int unit_index,
+                                     int interp_extrap, const double *d_times, int64_t n, double *d_out,
+                                     void *stream)
+{
+    (void)interp_extrap;   // the grid effective areas in d_dtab were interpolated on the host
+    if (!d_dtab || !d_units || !d_times || !d_out || n < 0 || unit_index < 0)
+        return fail(CGRB_E_BADARG, "cgrb_energy_integrated_evolution: bad argument%s");
+    if (n == 0)
+        return CGRB_OK;
+    int grid = (int)min((int64_t)4096, (n + NT - 1) / NT);
+    k_lambda<<<grid, NT, 0, (cudaStream_t)stream>>>(d_dtab, d_units, unit_index, d_times, n, d_out);
+    return check_launch("cgrb_energy_integrated_evolution");
+}
+
+int cgrb_evolution(const cgrb_unit_t *d_units, int unit_index, const double *d_energy, int64_t n_energy,
+                   const double *d_times, int64_t n_time, double *d_out, void *stream)
+{
+    if (!d_units || !d_energy || !d_times || !d_out || n_energy < 0 || n_time < 0 || unit_index < 0)
+        return fail(CGRB_E_BADARG, "cgrb_evolution: bad argument%s");
+    if (n_energy == 0 || n_time == 0)
+        return CGRB_OK;
+    int grid = (int)min((int64_t)4096, n_time);
+    k_evolution<<<grid, NT, 0, (cudaStream_t)stream>>>(d_units, unit_index, d_energy, n_energy, d_times,
+                                                       n_time, d_out);
+    return check_launch("cgrb_evolution");
+}
+
+int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int interp_extrap, void *stream)
+{
+    (void)interp_extrap;
+    if (!d_dtab || !d_units || n_units <= 0)
+        return fail(CGRB_E_BADARG, "cgrb_fmax: bad argument%s");
+    k_fmax<<<n_units, 64, 0, (cudaStream_t)stream>>>(d_dtab, d_units, n_units);
+    return check_launch("cgrb_fmax");
+}
+
+static int check_rng(const cgrb_rng_t *rng, const char *who)
+{
+    if (!rng)
+        return fail(CGRB_E_BADARG, "%s: null rng", who);
+    if (rng->mode != 0 && rng->mode != 1)
+        return fail(CGRB_E_BADARG, "%s: rng mode must be 0 (philox) or 1 (injected)", who);
+    if (rng->mode == 1 && !rng->d_u)
+        return fail(CGRB_E_BADARG, "%s: injected rng without uniform buffer", who);
+    return CGRB_OK;
+}
+
+int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                       const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
+                       int interp_extrap, const cgrb_rng_t *rng, double *d_segsum, double *d_segstart,
+                       int32_t *d_segcount, double *d_stage, double *d_times_src, double *d_cand_times,
+                       uint8_t *d_cand_accept, cgrb_counts_t *d_counts, void *stream)
+{
+    (void)interp_extrap;
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_segsum ||
+        !d_segstart || !d_segcount || !d_stage || !d_times_src || !d_counts)
+        return fail(CGRB_E_BADARG, "cgrb_sample_events: bad argument%s");
+    if ((d_cand_times == nullptr) != (d_cand_accept == nullptr))
+        return fail(CGRB_E_BADARG, "cgrb_sample_events: cand_times and cand_accept go together%s");
+    int rc = check_rng(rng, "cgrb_sample_events");
+    if (rc)
+        return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_gap_sums<0><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng, d_segsum, d_counts);
+    k_seg_scan<0><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
+                                                           d_segstart, d_counts);
+    k_source_thin<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng, d_segstart,
+                                                  d_segcount, d_stage, d_cand_times, d_cand_accept, d_counts);
+    k_source_gather<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_segcount,
+                                                    d_stage, d_times_src, d_counts);
+    return check_launch("cgrb_sample_events");
+}
+
+int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                       const cgrb_work_t *d_work, int64_t n_work, int interp_extrap, const cgrb_rng_t *rng,
+                       int64_t max_trials, const double *d_times_src, double *d_energy_src, int32_t *d_trials,
+                       cgrb_counts_t *d_counts, void *stream)
+{
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_src || !d_energy_src ||
+        !d_counts)
+        return fail(CGRB_E_BADARG, "cgrb_sample_energy: bad argument%s");
+    if (interp_extrap != 0 && interp_extrap != 1)
+        return fail(CGRB_E_BADARG, "cgrb_sample_energy: interp_extrap must be 0 (linear) or 1 (clamp)%s");
+    int rc = check_rng(rng, "cgrb_sample_energy");
+    if (rc)
+        return rc;
+    if (rng->mode == 1 && !rng->d_off)
+        return fail(CGRB_E_BADARG, "cgrb_sample_energy: injected mode needs per-photon offsets%s");
+    k_sample_energy<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(
+        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, d_times_src, d_energy_src, d_trials,
+        d_counts);
+    return check_launch("cgrb_sample_energy");
+}
+
+int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work,
+                  int64_t n_work, const cgrb_rng_t *rng, const double *d_energy_src, uint8_t *d_pha_src,
+                  const cgrb_counts_t *d_counts, void *stream)
+{
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_energy_src || !d_pha_src ||
+        !d_counts)
+        return fail(CGRB_E_BADARG, "cgrb_digitize: bad argument%s");
+    int rc = check_rng(rng, "cgrb_digitize");
+    if (rc)
+        return rc;
+    const int smem = CUM_BYTES + 144 * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_digitize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess)
+            return fail(CGRB_E_CUDA, "cgrb_digitize: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    k_digitize<<<(unsigned)n_work, NT, smem, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
+                                                                     d_energy_src, d_pha_src, d_counts);
+    return check_launch("cgrb_digitize");
+}
+
+int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                           const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
+                           const cgrb_rng_t *rng_time, const cgrb_rng_t *rng_chan, double *d_segsum,
+                           double *d_segstart, double *d_times_bkg, uint8_t *d_pha_bkg,
+                           cgrb_counts_t *d_counts, void *stream)
+{
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_segsum ||
+        !d_segstart || !d_times_bkg || !d_pha_bkg || !d_counts)
+        return fail(CGRB_E_BADARG, "cgrb_sample_background: bad argument%s");
+    int rc = check_rng(rng_time, "cgrb_sample_background");
+    if (rc)
+        return rc;
+    cgrb_rng_t chan = *rng_time;
+    if (rng_time->mode == 1) {
+        rc = check_rng(rng_chan, "cgrb_sample_background(chan)");
+        if (rc)
+            return rc;
+        if (rng_chan->mode != 1)
+            return fail(CGRB_E_BADARG, "cgrb_sample_background: channel rng must be injected too%s");
+        chan = *rng_chan;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    k_gap_sums<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_counts);
+    k_seg_scan<1><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
+                                                           d_segstart, d_counts);
+    k_background<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng_time, chan, d_segstart,
+                                                 d_times_bkg, d_pha_bkg, d_counts);
+    return check_launch("cgrb_sample_background");
+}
+
+int cgrb_combine(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
+                 const double *d_times_bkg, const uint8_t *d_pha_bkg, const double *d_times_src,
+                 const uint8_t *d_pha_src, double *d_times_tot, uint8_t *d_pha_tot, cgrb_counts_t *d_counts,
+                 void *stream)
+{
+    if (!d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_bkg || !d_pha_bkg || !d_times_src ||
+        !d_pha_src || !d_times_tot || !d_pha_tot || !d_counts)
+        return fail(CGRB_E_BADARG, "cgrb_combine: bad argument%s");
+    k_combine<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(d_units, d_work, n_work, d_times_bkg,
+                                                                 d_pha_bkg, d_times_src, d_pha_src, d_times_tot,
+                                                                 d_pha_tot, d_counts);
+    return check_launch("cgrb_combine");
+}
+
+int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
+                       const int64_t *d_unit_work_begin, const double *d_times_tot, const uint8_t *d_pha_tot,
+                       int32_t *d_tile_count, double *d_times_out, uint8_t *d_pha_out, uint8_t *d_selection,
+                       cgrb_counts_t *d_counts, void *stream)
+{
+    if (!d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_times_tot ||
+        !d_pha_tot || !d_tile_count || !d_times_out || !d_pha_out || !d_counts)
+        return fail(CGRB_E_BADARG, "cgrb_gbm_dead_time: bad argument%s");
+    cudaStream_t s = (cudaStream_t)stream;
+    k_deadtime_count<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_times_tot, d_pha_tot,
+                                                     d_tile_count, d_counts);
+    k_deadtime_write<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_times_tot,
+                                                     d_pha_tot, d_tile_count, d_times_out, d_pha_out,
+                                                     d_selection, d_counts);
+    return check_launch("cgrb_gbm_dead_time");
+}
+
+}  // extern "C"

@@ -1,0 +1,518 @@
+"""Host side of the photon-event engine: device buffers (torch tensors), work lists, launches.
+
+PyTorch is used only for device memory, streams and host<->device copies; all arithmetic of the
+hot path happens in the CUDA kernels behind the C ABI (include/cosmogrb_b200.h).  There is no
+CPU fallback: without a CUDA device or without the shared library every call raises.
+
+Vocabulary: a *unit* is one (GRB, detector) pair -- one ``LightCurve.process()`` of the reference
+(lightcurve/lightcurve.py:167-200).  A *batch* is a set of units processed by one sequence of
+launches; each unit owns a slice (``*_off`` .. ``*_off + n``) of the flat event arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import threading
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import COUNTS_DTYPE, UNIT_DTYPE, WORK_DTYPE, RngDesc
+
+DEFAULT_SEED = 0x00C0560612B
+ENERGY_CHUNK = 1024          # photons per CTA work item of the energy / digitize kernels
+DEFAULT_MAX_TRIALS = 1 << 22
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+# ----------------------------------------------------------------------------------------------
+# uniform sources
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Philox:
+    """Counter-based Philox4x32-10 stream keyed by (seed, unit stream id, stage, index)."""
+
+    seed: int = DEFAULT_SEED
+
+
+@dataclass
+class Injected:
+    """Replay of explicit uniform streams (parity mode).  All arrays are host numpy arrays;
+    ``thin``/``bkg_time`` hold (u1, u2) pairs per candidate, ``digitize``/``bkg_chan`` one uniform
+    per event, ``energy`` is consumed from per-photon start positions ``energy_off``.
+
+    Each of ``thin``, ``digitize``, ``bkg_time``, ``bkg_chan`` is a list with one array per unit.
+    ``energy`` is one flat array and ``energy_off`` a list (one int64 array per unit) of absolute
+    start positions in it, one per source photon.
+    """
+
+    thin: Optional[list] = None
+    energy: Optional[np.ndarray] = None
+    energy_off: Optional[list] = None
+    digitize: Optional[list] = None
+    bkg_time: Optional[list] = None
+    bkg_chan: Optional[list] = None
+
+
+def make_units(n):
+    u = np.zeros(n, dtype=UNIT_DTYPE)
+    return u
+
+
+def fill_gamma_constants(units):
+    """Per-GRB constants of a = 2 + alpha used by the device igamc (host libm)."""
+    for i in range(len(units)):
+        a = 2.0 + float(units["alpha"][i])
+        if a > 0:
+            units["gamma_a"][i] = math.gamma(a)
+            units["lgamma_a"][i] = math.lgamma(a)
+            units["lgamma_1pa"][i] = math.lgamma(1.0 + a)
+        else:
+            units["gamma_a"][i] = np.nan
+            units["lgamma_a"][i] = np.nan
+            units["lgamma_1pa"][i] = np.nan
+    return units
+
+
+def capacity(rate, span):
+    """Candidate capacity: Poisson mean + 8 sigma + slack.  The candidate count of thinning at
+    rate ``rate`` over ``span`` seconds is Poisson(rate*span); P(N > mean + 8 sigma) < 1e-15."""
+    mean = np.maximum(np.nan_to_num(np.asarray(rate, dtype="f8") * span, nan=0.0, posinf=0.0), 0.0)
+    return (np.ceil(mean + 8.0 * np.sqrt(mean)) + 64).astype(np.int64)
+
+
+def _unit_work_begin(work, n_units):
+    return np.searchsorted(work["unit"], np.arange(n_units + 1), side="left").astype(np.int64)
+
+
+class Batch(object):
+    """Device-resident state of one batch of units.  All event arrays are flat torch tensors on
+    the engine's device; ``units``/``counts`` are the host copies of the per-unit structs."""
+
+    def __init__(self, engine, units, dtab, interp_extrap):
+        self.engine = engine
+        self.units = units
+        self.n_units = len(units)
+        self.dtab = dtab
+        self.interp_extrap = interp_extrap
+        self.counts = None          # host copy after fetch_counts()
+        self.d_units = None
+        self.d_counts = None
+        self.t = {}                 # name -> torch tensor
+        self.work = {}              # which -> (host work, device work, device unit_work_begin)
+        self._keep = []             # keeps injected uniform tensors alive
+
+    # -- per-unit views (host numpy) ------------------------------------------------------------
+    def view(self, name, ui, kind):
+        """Host copy of unit ``ui``'s slice of event array ``name``; kind in src|bkg|tot|kept."""
+        u, c = self.units[ui], self.counts[ui]
+        off, n = {
+            "src": (u["src_off"], c["n_src"]),
+            "bkg": (u["bkg_off"], c["n_bkg"]),
+            "tot": (u["tot_off"], c["n_total"]),
+            "kept": (u["tot_off"], c["n_kept"]),
+        }[kind]
+        return self.t[name][int(off):int(off) + int(n)].cpu().numpy()
+
+
+class Engine(object):
+    """One engine per process and device."""
+
+    def __init__(self, device=None, seed=DEFAULT_SEED, interp_extrap="linear"):
+        torch = _torch()
+        self.lib = _capi.load()
+        if not torch.cuda.is_available():
+            raise _capi.EngineUnavailable(
+                "no CUDA device: the cosmogrb_b200 photon-event engine has no CPU fallback"
+            )
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        info = (C.c_int * 4)()
+        _capi.check(self.lib.cgrb_device_info(self.device.index or 0, info), "cgrb_device_info")
+        self.sm_count, self.cc = info[0], (info[1], info[2])
+        self.seed = int(seed)
+        self.interp_extrap = interp_extrap
+        self._call_counter = 0
+        self._dtab_cache = {}
+        self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
+
+    # -- small helpers --------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def next_seed(self):
+        """A fresh Philox seed per sampler call (the reference reseeds from OS entropy before every
+        call -- sampler/source.py:129; here the sequence is reproducible for a fixed engine seed)."""
+        self._call_counter += 1
+        return (self.seed + 0x9E3779B97F4A7C15 * self._call_counter) & 0xFFFFFFFFFFFFFFFF
+
+    def to_device(self, arr):
+        torch = _torch()
+        a = np.ascontiguousarray(arr)
+        if a.dtype.fields is not None:
+            a = a.view(np.uint8)
+        return torch.from_numpy(a).to(self.device, non_blocking=False)
+
+    def empty(self, n, dtype):
+        torch = _torch()
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
+
+    def upload_tables(self, tables):
+        """tables: list of float64 blocks (Response.device_table) -> one device tensor."""
+        key = tuple(id(t) for t in tables)
+        hit = self._dtab_cache.get(key)
+        if hit is not None and all(a is b for a, b in zip(hit[0], tables)):
+            return hit[1]
+        block = np.concatenate([np.asarray(t, dtype="f8").reshape(-1) for t in tables])
+        assert block.size == len(tables) * _capi.DT_SIZE
+        d = self.to_device(block)
+        if len(self._dtab_cache) > 64:
+            self._dtab_cache.clear()
+        self._dtab_cache[key] = (list(tables), d)
+        return d
+
+    def _extrap_code(self, interp_extrap):
+        return {"linear": 0, "clamp": 1}[interp_extrap or self.interp_extrap]
+
+    def _rng_desc(self, rng, batch, kind):
+        """Build the C rng descriptor for one stage (kind in thin|energy|digitize|bkg_time|bkg_chan)."""
+        d = RngDesc()
+        if isinstance(rng, Philox):
+            d.mode = 0
+            d.seed = rng.seed & 0xFFFFFFFFFFFFFFFF
+            return d
+        if not isinstance(rng, Injected):
+            raise TypeError("rng must be Philox or Injected")
+        d.mode = 1
+        d.seed = 0
+        if kind == "energy":
+            if rng.energy is None or rng.energy_off is None:
+                raise ValueError("Injected.energy / energy_off required")
+            u = self.to_device(np.asarray(rng.energy, dtype="f8"))
+            total = int(batch.units["src_off"][-1] + batch.units["src_cap"][-1] + 1)
+            off = np.zeros(total, dtype=np.int64)
+            for ui in range(batch.n_units):
+                o = np.asarray(rng.energy_off[ui], dtype=np.int64)
+                s = int(batch.units["src_off"][ui])
+                off[s:s + len(o)] = o
+            d_off = self.to_device(off)
+            d_len = self.to_device(np.array([len(rng.energy)], dtype=np.int64))
+        else:
+            streams = getattr(rng, kind)
+            if streams is None:
+                raise ValueError(f"Injected.{kind} required")
+            if len(streams) != batch.n_units:
+                raise ValueError(f"Injected.{kind} needs one stream per unit")
+            lens = np.array([len(s) for s in streams], dtype=np.int64)
+            offs = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
+            flat = np.concatenate([np.asarray(s, dtype="f8") for s in streams]) if lens.sum() else np.zeros(1)
+            u = self.to_device(flat)
+            d_off = self.to_device(offs)
+            d_len = self.to_device(lens)
+        batch._keep += [u, d_off, d_len]
+        d.d_u, d.d_off, d.d_len = u.data_ptr(), d_off.data_ptr(), d_len.data_ptr()
+        return d
+
+    # -- batch construction ---------------------------------------------------------------------
+    def new_batch(self, units, tables, interp_extrap=None, compute_fmax=True):
+        """Upload units and detector tables, compute fmax on the device (unless given), size the
+        per-unit capacities and offsets."""
+        torch = _torch()
+        units = np.array(units, dtype=UNIT_DTYPE, copy=True)
+        fill_gamma_constants(units)
+        dtab = self.upload_tables(tables) if isinstance(tables, (list, tuple)) else tables
+        b = Batch(self, units, dtab, interp_extrap or self.interp_extrap)
+        b.d_units = self.to_device(units)
+        if compute_fmax:
+            _capi.check(self.lib.cgrb_fmax(dtab.data_ptr(), b.d_units.data_ptr(), b.n_units,
+                                           self._extrap_code(b.interp_extrap), self.stream), "cgrb_fmax")
+            self.launches += 1
+            host = b.d_units.cpu().numpy().view(UNIT_DTYPE)
+            units["fmax"] = host["fmax"]
+        self.finalize_layout(b)
+        return b
+
+    def finalize_layout(self, b):
+        units = b.units
+        no_src = (units["flags"] & _capi.UNIT_NO_SOURCE) != 0
+        no_bkg = (units["flags"] & _capi.UNIT_NO_BACKGROUND) != 0
+        src_cap = capacity(units["fmax"], units["src_tstop"] - units["src_tstart"])
+        bkg_cap = capacity(units["bkg_rate"], units["bkg_tstop"] - units["bkg_tstart"])
+        src_cap[no_src] = 0
+        bkg_cap[no_bkg] = 0
+        keep_src = units["src_cap"] > 0
+        keep_bkg = units["bkg_cap"] > 0
+        units["src_cap"] = np.where(keep_src, units["src_cap"], src_cap)   # caller may pre-size
+        units["bkg_cap"] = np.where(keep_bkg, units["bkg_cap"], bkg_cap)
+        units["src_off"] = np.concatenate(([0], np.cumsum(units["src_cap"] + 1)[:-1]))
+        units["bkg_off"] = np.concatenate(([0], np.cumsum(units["bkg_cap"] + 1)[:-1]))
+        units["tot_off"] = np.concatenate(([0], np.cumsum(units["src_cap"] + units["bkg_cap"] + 2)[:-1]))
+        b.n_src_slots = int(np.sum(units["src_cap"] + 1))
+        b.n_bkg_slots = int(np.sum(units["bkg_cap"] + 1))
+        b.n_tot_slots = b.n_src_slots + b.n_bkg_slots
+        b.d_units = self.to_device(units)
+        torch = _torch()
+        b.d_counts = torch.zeros(b.n_units * COUNTS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+
+    def _work(self, b, which, chunk):
+        key = (which, chunk)
+        if key not in b.work:
+            w = _capi.build_work(b.units, which, chunk)
+            b.work[key] = (w, self.to_device(w), self.to_device(_unit_work_begin(w, b.n_units)))
+        return b.work[key]
+
+    def set_counts(self, b, **cols):
+        """Overwrite per-unit counters from the host (stage-level entry points)."""
+        c = np.zeros(b.n_units, dtype=COUNTS_DTYPE)
+        if b.counts is not None:
+            c[:] = b.counts
+        for k, v in cols.items():
+            c[k] = v
+        b.counts = c
+        b.d_counts = self.to_device(c)
+
+    def fetch_counts(self, b):
+        b.counts = b.d_counts.cpu().numpy().view(COUNTS_DTYPE).copy()
+        return b.counts
+
+    # -- stages ---------------------------------------------------------------------------------
+    def sample_events(self, b, rng, want_candidates=False):
+        torch = _torch()
+        w, dw, dwb = self._work(b, 0, _capi.SEG)
+        nw = len(w)
+        t = b.t
+        t["segsum"] = self.empty(nw, torch.float64)
+        t["segstart"] = self.empty(nw, torch.float64)
+        t["segcount"] = self.empty(nw, torch.int32)
+        t["stage"] = self.empty(b.n_src_slots, torch.float64)
+        t["times_src"] = self.empty(b.n_src_slots, torch.float64)
+        cand_t = cand_a = None
+        if want_candidates:
+            t["cand_times"] = cand_t = self.empty(b.n_src_slots, torch.float64)
+            t["cand_accept"] = cand_a = torch.zeros(max(b.n_src_slots, 1), dtype=torch.uint8, device=self.device)
+        desc = self._rng_desc(rng, b, "thin")
+        _capi.check(
+            self.lib.cgrb_sample_events(
+                b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), nw, dwb.data_ptr(),
+                self._extrap_code(b.interp_extrap), C.byref(desc), t["segsum"].data_ptr(),
+                t["segstart"].data_ptr(), t["segcount"].data_ptr(), t["stage"].data_ptr(),
+                t["times_src"].data_ptr(), cand_t.data_ptr() if want_candidates else None,
+                cand_a.data_ptr() if want_candidates else None, b.d_counts.data_ptr(), self.stream),
+            "cgrb_sample_events")
+        self.launches += 4
+
+    def sample_energy(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, want_trials=False):
+        torch = _torch()
+        w, dw, _ = self._work(b, 3, ENERGY_CHUNK)
+        t = b.t
+        t["energy_src"] = self.empty(b.n_src_slots, torch.float64)
+        tr = None
+        if want_trials:
+            t["trials"] = tr = torch.zeros(max(b.n_src_slots, 1), dtype=torch.int32, device=self.device)
+        desc = self._rng_desc(rng, b, "energy")
+        _capi.check(
+            self.lib.cgrb_sample_energy(
+                b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
+                self._extrap_code(b.interp_extrap), C.byref(desc), int(max_trials),
+                t["times_src"].data_ptr(), t["energy_src"].data_ptr(),
+                tr.data_ptr() if want_trials else None, b.d_counts.data_ptr(), self.stream),
+            "cgrb_sample_energy")
+        self.launches += 1
+
+    def digitize_batch(self, b, rng):
+        torch = _torch()
+        w, dw, _ = self._work(b, 3, ENERGY_CHUNK)
+        t = b.t
+        t["pha_src"] = self.empty(b.n_src_slots, torch.uint8)
+        desc = self._rng_desc(rng, b, "digitize")
+        _capi.check(
+            self.lib.cgrb_digitize(
+                b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), C.byref(desc),
+                t["energy_src"].data_ptr(), t["pha_src"].data_ptr(), b.d_counts.data_ptr(), self.stream),
+            "cgrb_digitize")
+        self.launches += 1
+
+    def sample_background(self, b, rng):
+        torch = _torch()
+        w, dw, dwb = self._work(b, 1, _capi.SEG)
+        nw = len(w)
+        t = b.t
+        t["bsegsum"] = self.empty(nw, torch.float64)
+        t["bsegstart"] = self.empty(nw, torch.float64)
+        t["times_bkg"] = self.empty(b.n_bkg_slots, torch.float64)
+        t["pha_bkg"] = self.empty(b.n_bkg_slots, torch.uint8)
+        d_time = self._rng_desc(rng, b, "bkg_time")
+        d_chan = self._rng_desc(rng, b, "bkg_chan") if isinstance(rng, Injected) else d_time
+        _capi.check(
+            self.lib.cgrb_sample_background(
+                b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), nw, dwb.data_ptr(),
+                C.byref(d_time), C.byref(d_chan), t["bsegsum"].data_ptr(), t["bsegstart"].data_ptr(),
+                t["times_bkg"].data_ptr(), t["pha_bkg"].data_ptr(), b.d_counts.data_ptr(), self.stream),
+            "cgrb_sample_background")
+        self.launches += 3
+
+    def combine(self, b):
+        torch = _torch()
+        w, dw, _ = self._work(b, 2, _capi.MERGE_TILE)
+        t = b.t
+        t["times_tot"] = self.empty(b.n_tot_slots, torch.float64)
+        t["pha_tot"] = self.empty(b.n_tot_slots, torch.uint8)
+        _capi.check(
+            self.lib.cgrb_combine(
+                b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), t["times_bkg"].data_ptr(),
+                t["pha_bkg"].data_ptr(), t["times_src"].data_ptr(), t["pha_src"].data_ptr(),
+                t["times_tot"].data_ptr(), t["pha_tot"].data_ptr(), b.d_counts.data_ptr(), self.stream),
+            "cgrb_combine")
+        self.launches += 1
+
+    def dead_time(self, b, want_selection=False):
+        torch = _torch()
+        w, dw, dwb = self._work(b, 2, _capi.DT_TILE)
+        t = b.t
+        t["tile_count"] = self.empty(len(w), torch.int32)
+        t["times_out"] = self.empty(b.n_tot_slots, torch.float64)
+        t["pha_out"] = self.empty(b.n_tot_slots, torch.uint8)
+        sel = None
+        if want_selection:
+            t["selection"] = sel = torch.zeros(max(b.n_tot_slots, 1), dtype=torch.uint8, device=self.device)
+        _capi.check(
+            self.lib.cgrb_gbm_dead_time(
+                b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), dwb.data_ptr(),
+                t["times_tot"].data_ptr(), t["pha_tot"].data_ptr(), t["tile_count"].data_ptr(),
+                t["times_out"].data_ptr(), t["pha_out"].data_ptr(),
+                sel.data_ptr() if want_selection else None, b.d_counts.data_ptr(), self.stream),
+            "cgrb_gbm_dead_time")
+        self.launches += 2
+
+    def process(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, diagnostics=False):
+        """LightCurve.process() for every unit of the batch (lightcurve.py:167-200): source times,
+        energies, channels; background times, channels; combine; dead time."""
+        self.sample_events(b, rng, want_candidates=diagnostics)
+        self.sample_energy(b, rng, max_trials=max_trials, want_trials=diagnostics)
+        self.digitize_batch(b, rng)
+        self.sample_background(b, rng)
+        self.combine(b)
+        self.dead_time(b, want_selection=diagnostics)
+        return b
+
+    def check_status(self, b):
+        c = b.counts if b.counts is not None else self.fetch_counts(b)
+        bad = np.nonzero(c["status"])[0]
+        if len(bad):
+            names = {1: "source capacity", 2: "background capacity", 4: "injected uniforms exhausted",
+                     8: "trial cap", 16: "output capacity"}
+            ui = int(bad[0])
+            st = int(c["status"][ui])
+            what = ", ".join(v for k, v in names.items() if st & k)
+            raise _capi.EngineError(f"{len(bad)} unit(s) failed, first: unit {ui}: {what}")
+
+    # -- single-array conveniences used by the class shims ---------------------------------------
+    def _single_unit(self, response, bkg_weights=None, interp_extrap=None, **fields):
+        u = make_units(1)
+        for k, v in fields.items():
+            u[k] = v
+        tab = response.device_table(bkg_weights, interp_extrap or self.interp_extrap)
+        return u, [tab]
+
+    def energy_integrated_evolution(self, unit, tables, times, interp_extrap=None):
+        torch = _torch()
+        units = np.array(unit, dtype=UNIT_DTYPE, copy=True)
+        fill_gamma_constants(units)
+        dtab = self.upload_tables(tables)
+        du = self.to_device(units)
+        times = np.atleast_1d(np.asarray(times, dtype="f8"))
+        dt = self.to_device(times)
+        out = self.empty(len(times), torch.float64)
+        _capi.check(
+            self.lib.cgrb_energy_integrated_evolution(
+                dtab.data_ptr(), du.data_ptr(), 0, self._extrap_code(interp_extrap), dt.data_ptr(),
+                len(times), out.data_ptr(), self.stream),
+            "cgrb_energy_integrated_evolution")
+        self.launches += 1
+        return out[:len(times)].cpu().numpy()
+
+    def evolution(self, unit, energy, times):
+        torch = _torch()
+        units = np.array(unit, dtype=UNIT_DTYPE, copy=True)
+        fill_gamma_constants(units)
+        du = self.to_device(units)
+        energy = np.atleast_1d(np.asarray(energy, dtype="f8"))
+        times = np.atleast_1d(np.asarray(times, dtype="f8"))
+        de, dt = self.to_device(energy), self.to_device(times)
+        out = self.empty(len(times) * len(energy), torch.float64)
+        _capi.check(
+            self.lib.cgrb_evolution(du.data_ptr(), 0, de.data_ptr(), len(energy), dt.data_ptr(), len(times),
+                                    out.data_ptr(), self.stream),
+            "cgrb_evolution")
+        self.launches += 1
+        return out[:len(times) * len(energy)].cpu().numpy().reshape(len(times), len(energy))
+
+    def digitize(self, response, energies, rng=None):
+        """Response.digitize for a plain array of photon energies."""
+        torch = _torch()
+        energies = np.atleast_1d(np.asarray(energies, dtype="f8"))
+        n = len(energies)
+        if n == 0:
+            return np.zeros(0)
+        u, tabs = self._single_unit(response, src_cap=n, flags=_capi.UNIT_NO_BACKGROUND)
+        b = Batch(self, u, self.upload_tables(tabs), self.interp_extrap)
+        u["src_off"], u["bkg_off"], u["tot_off"] = 0, 0, 0
+        b.n_src_slots, b.n_bkg_slots, b.n_tot_slots = n + 1, 1, n + 2
+        b.d_units = self.to_device(u)
+        self.set_counts(b, n_src=n)
+        b.t["energy_src"] = self.to_device(np.concatenate((energies, [0.0])))
+        self.digitize_batch(b, rng or Philox(self.next_seed()))
+        return b.t["pha_src"][:n].cpu().numpy().astype("f8")
+
+    def gbm_dead_time(self, times, pha):
+        """_gbm_dead_time for one time-sorted event list; returns the boolean selection."""
+        torch = _torch()
+        times = np.ascontiguousarray(times, dtype="f8")
+        n = len(times)
+        if n == 0:
+            return np.zeros(0, dtype=bool)
+        pha8 = np.ascontiguousarray(np.asarray(pha).astype(np.int64).clip(0, 255).astype(np.uint8))
+        u = make_units(1)
+        u["src_cap"], u["bkg_cap"] = n, 0
+        u["flags"] = _capi.UNIT_NO_BACKGROUND
+        b = Batch(self, u, None, self.interp_extrap)
+        b.n_src_slots, b.n_bkg_slots, b.n_tot_slots = n + 1, 1, n + 2
+        b.d_units = self.to_device(u)
+        self.set_counts(b, n_total=n)
+        b.t["times_tot"] = self.to_device(np.concatenate((times, [0.0, 0.0])))
+        b.t["pha_tot"] = self.to_device(np.concatenate((pha8, np.zeros(2, np.uint8))))
+        self.dead_time(b, want_selection=True)
+        return b.t["selection"][:n].cpu().numpy().astype(bool)
+
+
+_engine = None
+_engine_lock = threading.Lock()
+
+
+def get_engine(**kw):
+    """Process-wide engine on the current CUDA device."""
+    global _engine
+    with _engine_lock:
+        if _engine is None:
+            from .config import cosmogrb_config
+
+            opts = dict(seed=cosmogrb_config["engine"]["seed"],
+                        interp_extrap=cosmogrb_config["engine"]["interp_extrap"])
+            opts.update(kw)
+            _engine = Engine(**opts)
+        return _engine
+
+
+def reset_engine():
+    global _engine
+    with _engine_lock:
+        _engine = None

@@ -1,0 +1,234 @@
+/*
+ * cosmogrb_b200.h -- C ABI of the B200-native photon-event engine (libcosmogrb_b200.so).
+ *
+ * Drop-in boundary for ONE path of grburgess/cosmogrb: the per-photon hot path
+ *   NHPP thinning -> CPL energy draw -> DRM fold -> GBM dead time, batched over
+ *   (GRB x detector) "units".
+ * The reference has no FFI of its own (it is Python + numba); every entry point below names
+ * the reference callable it replaces (file:line relative to the cosmogrb repo root).  The
+ * ctypes binding a maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every pointer named d_* is DEVICE memory allocated by the caller (the Python host uses
+ *     torch tensors purely as device buffers); h_* is host memory.  The library never frees
+ *     or keeps caller memory; it allocates nothing on the device.
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream).  Calls return without synchronising unless stated.
+ *   - return value: 0 = ok, <0 = error (CGRB_E_*); cgrb_last_error() gives a message.
+ *     Data-dependent failures (capacity exceeded, injected stream exhausted, trial cap hit)
+ *     are reported asynchronously through the per-unit status word in cgrb_counts_t.
+ *   - units are independent; results do not depend on how units are split over launches,
+ *     processes or GPUs (Philox counters are functions of (seed, unit stream id, stage, index)).
+ */
+#ifndef COSMOGRB_B200_H
+#define COSMOGRB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGRB_ABI_VERSION 1
+
+/* error codes */
+#define CGRB_OK 0
+#define CGRB_E_BADARG (-1)
+#define CGRB_E_CUDA (-2)
+#define CGRB_E_UNSUPPORTED (-3)
+
+/* per-unit asynchronous status bits (cgrb_counts_t.status) */
+#define CGRB_ST_SRC_CAPACITY 1u      /* candidate capacity reached before tstop             */
+#define CGRB_ST_BKG_CAPACITY 2u      /* background capacity reached before tstop            */
+#define CGRB_ST_UNIFORMS_EXHAUSTED 4u /* injected uniform stream too short                   */
+#define CGRB_ST_TRIAL_CAP 8u         /* energy rejection hit max_trials                     */
+#define CGRB_ST_OUT_CAPACITY 16u     /* an output buffer was too small                      */
+
+/* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
+#define CGRB_NBINS 140
+#define CGRB_NCHAN 128
+#define CGRB_NE_LAMBDA 75   /* sampler/cpl_functions.py:303 */
+#define CGRB_NE_ENVELOPE 500 /* sampler/cpl_functions.py:208 */
+#define CGRB_NT_FMAX 50     /* sampler/source.py:100 */
+
+/* candidates per segment: the unit of work of the thinning kernels and the granularity of
+ * the floating-point summation order of arrival times (fixed so results are reproducible) */
+#define CGRB_SEG 8192
+
+/*
+ * Detector table block: one per detector, contiguous doubles in device memory, built on the
+ * host (numpy, bit-identical to response/response.py:74-154) by
+ * cosmogrb_b200.response.Response.  Offsets in doubles:
+ */
+#define CGRB_DT_EDGES 0        /* [141] photon energy edges (Response.energy_edges)                   */
+#define CGRB_DT_EA_X 144       /* [140] effective_area_packed[0] (bin means)                          */
+#define CGRB_DT_EA_Y 288       /* [140] effective_area_packed[1] (row sums, zeros -> 1e-99)           */
+#define CGRB_DT_BKG_CDF 432    /* [128] background channel cdf (background.py:93 via numpy choice)    */
+#define CGRB_DT_G75_E 560      /* [75]  10**linspace(log10 emin, log10 emax, 75)                      */
+#define CGRB_DT_G75_A 640      /* [75]  interp(ea_x, ea_y, G75_E)                                     */
+#define CGRB_DT_G500_E 720     /* [500] 10**linspace(log10 emin, log10 emax, 500)                     */
+#define CGRB_DT_G500_A 1220    /* [500] interp(ea_x, ea_y, G500_E)                                    */
+#define CGRB_DT_CUM 1720       /* [140*128] row-normalised cumulative matrix (16-byte aligned: 13760 B) */
+#define CGRB_DT_SIZE (1720 + 140 * 128) /* 19640 doubles = 157120 B per detector                     */
+
+/* one (GRB, detector) work unit; 192 bytes, device array uploaded by the caller */
+typedef struct {
+    int32_t kind;          /* 0 = CPLSourceFunction (cpl_functions.py), 1 = ConstantCPL (cpl_constant_functions.py) */
+    int32_t det;           /* detector table index into d_dtab                                     */
+    uint32_t stream_id;    /* Philox stream id (grb_id * 16 + detector)                            */
+    uint32_t flags;        /* bit0: source disabled, bit1: background disabled                     */
+    double peak_flux;
+    double ep_start;       /* kind 1: ep                                                           */
+    double ep_tau;
+    double alpha;
+    double trise;
+    double tdecay;
+    double z;
+    double src_tstart;     /* Source(tstart=0, tstop=duration) gbm_grb.py:61-67                    */
+    double src_tstop;
+    double bkg_tstart;     /* GBMGRB._background_start/_stop gbm_grb.py:20-21                      */
+    double bkg_tstop;
+    double bkg_rate;       /* Background._background_rate background.py:125                       */
+    double fmax;           /* Source._fmax (source.py:88-110); written by cgrb_fmax                */
+    double gamma_a;        /* Gamma(2+alpha)      (host, libm)                                     */
+    double lgamma_a;       /* log Gamma(2+alpha)                                                   */
+    double lgamma_1pa;     /* log Gamma(3+alpha)                                                   */
+    int64_t src_cap;       /* candidate capacity of this unit (host: fmax*T + 8 sigma)             */
+    int64_t bkg_cap;       /* background candidate capacity                                        */
+    int64_t src_off;       /* offset of this unit in the per-source-event arrays                   */
+    int64_t bkg_off;       /* offset of this unit in the per-background-event arrays               */
+    int64_t tot_off;       /* offset of this unit in the merged / filtered arrays                  */
+    int64_t reserved;
+} cgrb_unit_t;
+
+#define CGRB_UNIT_NO_SOURCE 1u
+#define CGRB_UNIT_NO_BACKGROUND 2u
+
+/* per-unit counters written by the kernels (device array, zeroed by cgrb_counts_reset) */
+typedef struct {
+    int64_t n_candidates;  /* thinning proposals with t <= tstop                                   */
+    int64_t n_src;         /* len(times_source) incl. the spurious tstart event                    */
+    int64_t n_bkg;         /* len(times_background) incl. the spurious tstart event                */
+    int64_t n_total;       /* merged events entering dead time                                     */
+    int64_t n_kept;        /* events surviving dead time                                           */
+    int64_t n_trials;      /* energy rejection trials                                              */
+    uint32_t status;       /* CGRB_ST_* bits                                                       */
+    uint32_t pad;
+} cgrb_counts_t;
+
+/* work list entry: a chunk of a unit's index space (built on the host by cgrb_build_work) */
+typedef struct {
+    int32_t unit;
+    int32_t seg;           /* chunk number inside the unit                                         */
+    int64_t start;         /* first index of the chunk                                             */
+} cgrb_work_t;
+
+/* uniform source */
+typedef struct {
+    int32_t mode;          /* 0 = Philox4x32-10 (seed, unit stream id, stage, index), 1 = injected  */
+    int32_t pad;
+    uint64_t seed;
+    const double *d_u;     /* injected: uniform buffer                                             */
+    const int64_t *d_off;  /* injected: per unit (thin/bkg/digitize) or per photon (energy) start  */
+    const int64_t *d_len;  /* injected: per unit number of uniforms available after d_off (may be NULL) */
+} cgrb_rng_t;
+
+int cgrb_abi_version(void);
+const char *cgrb_last_error(void);
+/* number of SMs etc. of the current device: out[0]=sm count, out[1]=cc major, out[2]=cc minor, out[3]=max smem optin */
+int cgrb_device_info(int device, int *out4);
+
+/* host helper: split [0, cap_u) of each unit into chunks of `chunk` indices.
+ * h_work may be NULL to query the count.  cap_u = h_units[i].src_cap (which=0, thinning
+ * candidates), bkg_cap (which=1), src_cap+bkg_cap+2 (which=2, merged events) or src_cap+1
+ * (which=3, source events).  Every unit owns at least one entry.  Returns the number of entries. */
+int64_t cgrb_build_work(const cgrb_unit_t *h_units, int n_units, int which, int64_t chunk,
+                        cgrb_work_t *h_work, int64_t work_cap);
+
+int cgrb_counts_reset(cgrb_counts_t *d_counts, int n_units, void *stream);
+
+/* ---- spectral model --------------------------------------------------------------------- */
+
+/* SourceFunction.energy_integrated_evolution(time) (cpl_source.py:81-96, constant_cpl.py:64-78;
+ * numba cpl_functions.py:289-325) for unit `unit_index` at n times. */
+int cgrb_energy_integrated_evolution(const double *d_dtab, const cgrb_unit_t *d_units, int unit_index,
+                                     int interp_extrap, const double *d_times, int64_t n,
+                                     double *d_out, void *stream);
+
+/* SourceFunction.evolution(energy, time) -> [n_time, n_energy] row-major
+ * (cpl_source.py:45-60; numba cpl_functions.py:47-100 / cpl_constant_functions.py:11-44). */
+int cgrb_evolution(const cgrb_unit_t *d_units, int unit_index, const double *d_energy, int64_t n_energy,
+                   const double *d_times, int64_t n_time, double *d_out, void *stream);
+
+/* Source._get_energy_integrated_max (source.py:88-110): fills d_units[i].fmax for every unit. */
+int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int interp_extrap, void *stream);
+
+/* ---- samplers --------------------------------------------------------------------------- */
+
+/* SourceFunction.sample_events (cpl_source.py:98-114; numba cpl_functions.py:134-188,
+ * cpl_constant_functions.py:65-105).  Work list: which=0, chunk=CGRB_SEG.
+ *   d_segsum/d_segstart [n_work] doubles, d_segcount [n_work] int32: workspace
+ *   d_stage   [sum src_cap] doubles: workspace (accepted times per segment)
+ *   d_times_src [sum (src_cap+1)]: output, unit u at src_off; entry 0 is tstart
+ *   d_cand_times / d_cand_accept: optional (may be NULL) per-candidate outputs at src_off
+ * counts: n_candidates, n_src, status. */
+int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                       const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
+                       int interp_extrap, const cgrb_rng_t *rng,
+                       double *d_segsum, double *d_segstart, int32_t *d_segcount, double *d_stage,
+                       double *d_times_src, double *d_cand_times, uint8_t *d_cand_accept,
+                       cgrb_counts_t *d_counts, void *stream);
+
+/* SourceFunction.sample_energy (cpl_source.py:116-132; numba cpl_functions.py:191-286).
+ * Work list: which=3 with any chunk size (photon index space, bounded by counts.n_src).
+ * d_trials may be NULL.  Injected mode: rng->d_off is per photon (absolute positions in d_u),
+ * rng->d_len[0] is the total length of d_u. */
+int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                       const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
+                       const cgrb_rng_t *rng, int64_t max_trials, const double *d_times_src,
+                       double *d_energy_src, int32_t *d_trials, cgrb_counts_t *d_counts, void *stream);
+
+/* Response.digitize (response.py:156-174; numba _digitize :10-25): nearest-CDF channel.
+ * Work list as for cgrb_sample_energy. */
+int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                  const cgrb_work_t *d_work, int64_t n_work, const cgrb_rng_t *rng,
+                  const double *d_energy_src, uint8_t *d_pha_src, const cgrb_counts_t *d_counts,
+                  void *stream);
+
+/* Background.sample_times + sample_channel (background.py:136-174; numba :13-44; numpy choice :93).
+ * Work list: which=1, chunk=CGRB_SEG.  rng_chan is used for the channel draw in injected mode
+ * (one uniform per event, incl. event 0); in Philox mode both come from one counter.
+ * counts: n_bkg, status. */
+int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                           const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
+                           const cgrb_rng_t *rng_time, const cgrb_rng_t *rng_chan,
+                           double *d_segsum, double *d_segstart,
+                           double *d_times_bkg, uint8_t *d_pha_bkg, cgrb_counts_t *d_counts,
+                           void *stream);
+
+/* ---- combine + dead time ---------------------------------------------------------------- */
+
+/* LightCurve._combine (lightcurve.py:131-151): two-way merge of the (ascending) background and
+ * source lists, background first on ties.  Work list: which=2, chunk=CGRB_MERGE_TILE. */
+#define CGRB_MERGE_TILE 2048
+int cgrb_combine(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
+                 const double *d_times_bkg, const uint8_t *d_pha_bkg,
+                 const double *d_times_src, const uint8_t *d_pha_src,
+                 double *d_times_tot, uint8_t *d_pha_tot, cgrb_counts_t *d_counts, void *stream);
+
+/* GBMLightCurve._filter_deadtime (gbm_lightcurve.py:42-56; numba _gbm_dead_time :80-115), literal
+ * reference semantics.  Work list: which=2, chunk=CGRB_DT_TILE; d_tile_count [n_work] int32 is
+ * workspace.  d_selection (optional) receives the per-event keep flag.  Output is compacted at
+ * tot_off; counts.n_kept. */
+#define CGRB_DT_TILE 2048
+int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
+                       const int64_t *d_unit_work_begin,
+                       const double *d_times_tot, const uint8_t *d_pha_tot, int32_t *d_tile_count,
+                       double *d_times_out, uint8_t *d_pha_out, uint8_t *d_selection,
+                       cgrb_counts_t *d_counts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSMOGRB_B200_H */
