@@ -1,0 +1,223 @@
+"""GPU parity: every CUDA stage against the CPU oracle on the same injected uniform streams.
+
+Bars (BASELINE.json north_star): accept/reject decisions, channel indices and dead-time survivor
+sets bit-exact; event times and energies within 1e-6 relative (fp64; measured agreement is ~1e-13).
+All calls go through the C ABI (cosmogrb_b200._capi -> libcosmogrb_b200.so).
+"""
+import numpy as np
+import pytest
+
+from tests import helpers as h
+from oracle import oracle as orc
+from cosmogrb_b200 import _capi
+from cosmogrb_b200.engine import Injected, Philox
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6          # north-star tolerance for fp64 times / energies
+TIGHT = 1e-10        # what we actually expect
+
+
+def _batch(engine, params, det="n0", kind=0, interp_extrap="linear", **kw):
+    rsp = h.response(det)
+    u = h.unit(kind=kind, **params, **kw)
+    b = engine.new_batch(u, [rsp.device_table(h.bkg_weights(det), interp_extrap)], interp_extrap=interp_extrap)
+    return rsp, b
+
+
+@pytest.mark.parametrize("params,kind", [(h.README_DEMO, 0), (h.CONFTEST_BRIGHT, 0), (h.BRIGHT_LONG, 0),
+                                         (dict(z=1.0, peak_flux=5e-9, alpha=-0.66, ep=500.0, duration=2.0), 1)])
+@pytest.mark.parametrize("extrap", ["linear", "clamp"])
+def test_lambda_and_fmax(engine, params, kind, extrap):
+    rsp = h.response("n0")
+    s = h.oracle_source(rsp, kind=kind, interp_extrap=extrap, **params)
+    u = h.unit(kind=kind, **params)
+    tab = rsp.device_table(h.bkg_weights("n0"), extrap)
+    times = np.linspace(0.0, params["duration"], 257)
+    want = orc.energy_integrated_evolution(s, rsp.effective_area_packed, times)
+    got = engine.energy_integrated_evolution(u, [tab], times, interp_extrap=extrap)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-300)
+    b = engine.new_batch(u, [tab], interp_extrap=extrap)
+    want_fmax = orc.fmax(s, rsp.effective_area_packed, 0.0, params["duration"])
+    assert b.units["fmax"][0] == pytest.approx(want_fmax, rel=1e-11)
+
+
+def test_evolution(engine):
+    rsp = h.response("n0")
+    s = h.oracle_source(rsp, **h.README_DEMO)
+    u = h.unit(**h.README_DEMO)
+    e = np.logspace(1, 4, 40)
+    t = np.linspace(0, 20, 11)
+    want = orc.cpl_evolution(s, e, t)
+    got = engine.evolution(u, e, t)
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-300)
+
+
+@pytest.mark.parametrize("params", [h.README_DEMO, h.CONFTEST_BRIGHT])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_sample_events_injected(engine, params, seed):
+    rsp, b = _batch(engine, params)
+    s = h.oracle_source(rsp, **params)
+    fmax = float(b.units["fmax"][0])
+    cap = int(b.units["src_cap"][0])
+    u = np.random.RandomState(seed).random_sample(2 * cap + 2)
+    want_t, want_nc, want_ct, want_acc = orc.sample_events(s, rsp.effective_area_packed, 0.0, params["duration"],
+                                                            fmax, orc.Rng(u=u), want_candidates=True)
+    engine.sample_events(b, Injected(thin=[u]), want_candidates=True)
+    c = engine.fetch_counts(b)
+    assert c["status"][0] == 0
+    assert c["n_candidates"][0] == want_nc
+    got_acc = b.t["cand_accept"][:want_nc].cpu().numpy().astype(bool)
+    got_ct = b.t["cand_times"][:want_nc].cpu().numpy()
+    np.testing.assert_allclose(got_ct, want_ct, rtol=TIGHT)
+    mism = np.nonzero(got_acc != want_acc)[0]
+    assert len(mism) == 0, f"{len(mism)} accept/reject mismatches, first at candidate {mism[:5]}"
+    assert c["n_src"][0] == len(want_t)
+    got_t = b.view("times_src", 0, "src")
+    assert got_t[0] == 0.0                      # the spurious tstart event
+    np.testing.assert_allclose(got_t, want_t, rtol=TIGHT)
+    assert np.all(np.diff(got_t) >= 0)
+
+
+def test_sample_energy_injected_serial_replay(engine):
+    """Strict serial replay: per-photon offsets are the positions the reference's serial stream
+    reaches (cumulative 2 x trials), so the GPU consumes exactly the reference's uniforms."""
+    params = h.CONFTEST_BRIGHT
+    rsp, b = _batch(engine, params)
+    s = h.oracle_source(rsp, **params)
+    rs = np.random.RandomState(5)
+    times = np.sort(rs.uniform(0.05, 2.0, 600))
+    u = rs.random_sample(600 * 2 * 400)
+    want_e, want_tr = orc.sample_energy(s, rsp.effective_area_packed, times, orc.Rng(u=u))
+    off = np.concatenate(([0], np.cumsum(2 * want_tr.astype(np.int64))[:-1]))
+    n = len(times)
+    assert n <= b.units["src_cap"][0]
+    engine.set_counts(b, n_src=n)
+    import torch
+    ts = np.zeros(b.n_src_slots)
+    ts[:n] = times
+    b.t["times_src"] = engine.to_device(ts)
+    engine.sample_energy(b, Injected(energy=u, energy_off=[off]), want_trials=True)
+    c = engine.fetch_counts(b)
+    assert c["status"][0] == 0
+    got_e = b.t["energy_src"][:n].cpu().numpy()
+    got_tr = b.t["trials"][:n].cpu().numpy()
+    assert np.array_equal(got_tr, want_tr)
+    np.testing.assert_allclose(got_e, want_e, rtol=TIGHT)
+    assert c["n_trials"][0] == want_tr.sum()
+
+
+@pytest.mark.parametrize("det", ["n0", "n5", "b0"])
+def test_digitize_bit_exact(engine, det):
+    rsp = h.response(det)
+    rs = np.random.RandomState(11)
+    n = 200_000
+    e = np.exp(rs.uniform(np.log(rsp.emin), np.log(rsp.emax), n))
+    edges = rsp.energy_edges
+    e[:141] = edges                     # exact-edge energies, incl. E == emin (wraps to the last row)
+    e[141:300] = rs.uniform(edges[0], edges[3], 159)   # zero-probability rows
+    u = rs.random_sample(n)
+    u[300:310] = 0.0
+    want = orc.digitize(e, edges, rsp.cumulative_matrix, orc.Rng(u=u))
+    got = engine.digitize(rsp, e, rng=Injected(digitize=[u]))
+    assert got.dtype == np.float64
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("seed", [0, 3])
+def test_background_injected(engine, seed):
+    rsp, b = _batch(engine, h.README_DEMO, flags=_capi.UNIT_NO_SOURCE)
+    cap = int(b.units["bkg_cap"][0])
+    rs = np.random.RandomState(seed)
+    u_t = rs.random_sample(2 * cap + 2)
+    u_c = rs.random_sample(cap + 2)
+    want_t = orc.background_times(-100.0, 300.0, 500.0, orc.Rng(u=u_t))
+    want_c = orc.background_channels(h.bkg_weights("n0"), len(want_t), orc.Rng(u=u_c))
+    engine.sample_background(b, Injected(bkg_time=[u_t], bkg_chan=[u_c]))
+    c = engine.fetch_counts(b)
+    assert c["status"][0] == 0
+    assert c["n_bkg"][0] == len(want_t)
+    got_t = b.view("times_bkg", 0, "bkg")
+    got_c = b.view("pha_bkg", 0, "bkg")
+    np.testing.assert_allclose(got_t, want_t, rtol=TIGHT, atol=1e-9)
+    assert np.all(np.diff(got_t) >= 0)
+    assert np.array_equal(got_c.astype(np.int64), want_c)
+
+
+def test_dead_time_crafted(engine):
+    # the 10-event probe case of SURVEY.md §8c (v)
+    t = np.array([0, 1, 3, 4, 10, 15, 20.5, 20.7, 31.2, 32]) * 1e-6
+    pha = np.array([5, 6, 7, 8, 127, 9, 10, 11, 127, 12])
+    want = np.array([1, 0, 1, 1, 1, 0, 0, 1, 1, 0], dtype=bool)
+    assert np.array_equal(orc.gbm_dead_time(t, pha), want)
+    assert np.array_equal(engine.gbm_dead_time(t, pha), want)
+    # first event in the overflow channel
+    pha2 = pha.copy()
+    pha2[0] = 127
+    assert np.array_equal(engine.gbm_dead_time(t, pha2), orc.gbm_dead_time(t, pha2))
+    # single event / two events
+    assert np.array_equal(engine.gbm_dead_time(t[:1], pha[:1]), [True])
+    assert np.array_equal(engine.gbm_dead_time(t[:2], pha[:2]), [True, False])
+
+
+@pytest.mark.parametrize("rate,frac127", [(500.0, 0.05), (2e5, 0.05), (2e6, 0.3), (5e6, 1.0)])
+def test_dead_time_random(engine, rate, frac127):
+    rs = np.random.RandomState(7)
+    n = 1_000_000
+    t = np.cumsum(rs.exponential(1.0 / rate, n))
+    pha = rs.randint(0, 127, n)
+    pha[rs.random_sample(n) < frac127] = 127
+    want = orc.gbm_dead_time(t, pha)
+    got = engine.gbm_dead_time(t, pha)
+    assert np.array_equal(got, want)
+
+
+def test_combine_and_dead_time_pipeline(engine):
+    """Full unit under Philox; the oracle re-does combine + dead time from the GPU's component lists."""
+    params = h.CONFTEST_BRIGHT
+    rsp, b = _batch(engine, params)
+    engine.process(b, Philox(1234), diagnostics=True)
+    c = engine.fetch_counts(b)
+    engine.check_status(b)
+    t_src, p_src = b.view("times_src", 0, "src"), b.view("pha_src", 0, "src")
+    t_bkg, p_bkg = b.view("times_bkg", 0, "bkg"), b.view("pha_bkg", 0, "bkg")
+    assert c["n_total"][0] == len(t_src) + len(t_bkg)
+    want_t, want_p = orc.combine(t_bkg, p_bkg, t_src, p_src)
+    got_t, got_p = b.view("times_tot", 0, "tot"), b.view("pha_tot", 0, "tot")
+    assert np.array_equal(got_t, want_t)
+    assert np.array_equal(got_p.astype("f8"), want_p)
+    sel = orc.gbm_dead_time(want_t, want_p)
+    got_sel = b.view("selection", 0, "tot").astype(bool)
+    assert np.array_equal(got_sel, sel)
+    assert c["n_kept"][0] == sel.sum()
+    assert np.array_equal(b.view("times_out", 0, "kept"), want_t[sel])
+    assert np.array_equal(b.view("pha_out", 0, "kept").astype("f8"), want_p[sel])
+    # energies inside the response range, channels valid
+    e = b.view("energy_src", 0, "src")
+    assert np.all((e >= rsp.emin) & (e <= rsp.emax))
+    # re-derive the source channels with the oracle from the same Philox uniforms is not possible
+    # (device counters), so check determinism instead: same seed -> identical output
+    rsp2, b2 = _batch(engine, params)
+    engine.process(b2, Philox(1234))
+    engine.fetch_counts(b2)
+    assert np.array_equal(b2.view("times_out", 0, "kept"), want_t[sel])
+
+
+def test_multi_unit_batch_independent_of_batching(engine):
+    """14 detectors in one batch == each detector alone (Philox counters depend only on the unit)."""
+    params = h.CONFTEST_BRIGHT
+    dets = h.GBM_DETECTORS
+    tabs = [h.response(d).device_table(h.bkg_weights(d), "linear") for d in dets]
+    units = np.concatenate([h.unit(det_index=i, stream_id=16 * 7 + i, **params) for i in range(len(dets))])
+    b = engine.new_batch(units, tabs)
+    engine.process(b, Philox(99))
+    c = engine.fetch_counts(b)
+    engine.check_status(b)
+    for i in (0, 5, 13):
+        bi = engine.new_batch(units[i:i + 1].copy(), tabs)
+        engine.process(bi, Philox(99))
+        ci = engine.fetch_counts(bi)
+        for k in ("n_src", "n_bkg", "n_total", "n_kept", "n_candidates", "n_trials"):
+            assert ci[k][0] == c[k][i], k
+        assert np.array_equal(bi.view("times_out", 0, "kept"), b.view("times_out", i, "kept"))
+        assert np.array_equal(bi.view("pha_out", 0, "kept"), b.view("pha_out", i, "kept"))
