@@ -93,6 +93,9 @@ EXPORTS = (
     "cgrb_abi_version",
     "cgrb_last_error",
     "cgrb_device_info",
+    "cgrb_profile_enable",
+    "cgrb_profile_read",
+    "cgrb_launch_count",
     "cgrb_build_work",
     "cgrb_counts_reset",
     "cgrb_energy_integrated_evolution",
@@ -124,6 +127,9 @@ def load():
     lib.cgrb_abi_version.restype = i32
     lib.cgrb_last_error.restype = C.c_char_p
     lib.cgrb_device_info.argtypes = [i32, C.POINTER(C.c_int)]
+    lib.cgrb_profile_enable.argtypes = [i32]
+    lib.cgrb_profile_read.argtypes = [vp, vp, i32]
+    lib.cgrb_launch_count.restype = C.c_longlong
     lib.cgrb_build_work.restype = i64
     lib.cgrb_build_work.argtypes = [vp, i32, i32, i64, vp, i64]
     lib.cgrb_counts_reset.argtypes = [vp, i32, vp]
@@ -139,7 +145,7 @@ def load():
     lib.cgrb_gbm_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cgrb_last_error", "cgrb_build_work"):
+        if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count"):
             fn.restype = i32
     if lib.cgrb_abi_version() != ABI_VERSION:
         raise EngineUnavailable(
@@ -171,3 +177,22 @@ def build_work(units: np.ndarray, which: int, chunk: int) -> np.ndarray:
     if n2 != n:
         check(int(n2) if n2 < 0 else -1, "cgrb_build_work")
     return work
+
+
+def profile_enable(on=True):
+    check(load().cgrb_profile_enable(1 if on else 0), "cgrb_profile_enable")
+
+
+def profile_read(cap=65536):
+    """-> list of (kernel name, milliseconds) for every launch since profile_enable()."""
+    names = C.create_string_buffer(cap * 32)
+    ms = (C.c_float * cap)()
+    n = load().cgrb_profile_read(names, ms, cap)
+    if n < 0:
+        check(n, "cgrb_profile_read")
+    raw = names.raw
+    return [(raw[i * 32:(i + 1) * 32].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n)]
+
+
+def launch_count():
+    return int(load().cgrb_launch_count())

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "cgrb_device.cuh"
 
 using namespace cgrb;
@@ -30,6 +32,42 @@ static int check_launch(const char *what)
     }
     return CGRB_OK;
 }
+
+// ==========================================================================================
+// optional per-launch timing (cgrb_profile_enable / cgrb_profile_read): CUDA events recorded on
+// the launching stream around every kernel, so bench.py can report each kernel's live duration.
+// ==========================================================================================
+struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static long long g_launches = 0;
+
+static inline void prof_begin(const char *name, cudaStream_t s)
+{
+    g_launches++;
+    if (!g_prof)
+        return;
+    ProfRec r;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    g_recs.push_back(r);
+}
+static inline void prof_end(cudaStream_t s)
+{
+    if (g_prof)
+        cudaEventRecord(g_recs.back().b, s);
+}
+#define LAUNCH(name, stream, ...)   \
+    do {                            \
+        prof_begin(name, stream);   \
+        __VA_ARGS__;                \
+        prof_end(stream);           \
+    } while (0)
 
 #define NT 256            // threads per CTA of the event kernels
 #define NW (NT / 32)
@@ -1097,6 +1135,39 @@ extern "C" {
 
 int cgrb_abi_version(void) { return CGRB_ABI_VERSION; }
 
+int cgrb_profile_enable(int on)
+{
+    for (auto &r : g_recs) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_recs.clear();
+    g_prof = on != 0;
+    return CGRB_OK;
+}
+
+int cgrb_profile_read(char *names, float *ms, int cap)
+{
+    int n = 0;
+    for (auto &r : g_recs) {
+        if (n >= cap)
+            break;
+        if (cudaEventSynchronize(r.b) != cudaSuccess)
+            return fail(CGRB_E_CUDA, "cgrb_profile_read: event sync failed%s");
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms[n] = t;
+        if (names) {
+            strncpy(names + (size_t)n * 32, r.name, 31);
+            names[(size_t)n * 32 + 31] = 0;
+        }
+        n++;
+    }
+    return n;
+}
+
+long long cgrb_launch_count(void) { return g_launches; }
+
 const char *cgrb_last_error(void) { return g_err; }
 
 int cgrb_device_info(int device, int *out4)
@@ -1146,7 +1217,7 @@ int cgrb_counts_reset(cgrb_counts_t *d_counts, int n_units, void *stream)
 {
     if (!d_counts || n_units <= 0)
         return fail(CGRB_E_BADARG, "cgrb_counts_reset: bad argument%s");
-    k_counts_reset<<<(n_units + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_counts, n_units);
+    LAUNCH("k_counts_reset", (cudaStream_t)stream, k_counts_reset<<<(n_units + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_counts, n_units));
     return check_launch("cgrb_counts_reset");
 }
 
@@ -1160,7 +1231,7 @@ int cgrb_energy_integrated_evolution(const double *d_dtab, const cgrb_unit_t *d_
     if (n == 0)
         return CGRB_OK;
     int grid = (int)min((int64_t)4096, (n + NT - 1) / NT);
-    k_lambda<<<grid, NT, 0, (cudaStream_t)stream>>>(d_dtab, d_units, unit_index, d_times, n, d_out);
+    LAUNCH("k_lambda", (cudaStream_t)stream, k_lambda<<<grid, NT, 0, (cudaStream_t)stream>>>(d_dtab, d_units, unit_index, d_times, n, d_out));
     return check_launch("cgrb_energy_integrated_evolution");
 }
 
@@ -1172,8 +1243,8 @@ int cgrb_evolution(const cgrb_unit_t *d_units, int unit_index, const double *d_e
     if (n_energy == 0 || n_time == 0)
         return CGRB_OK;
     int grid = (int)min((int64_t)4096, n_time);
-    k_evolution<<<grid, NT, 0, (cudaStream_t)stream>>>(d_units, unit_index, d_energy, n_energy, d_times,
-                                                       n_time, d_out);
+    LAUNCH("k_evolution", (cudaStream_t)stream, k_evolution<<<grid, NT, 0, (cudaStream_t)stream>>>(d_units, unit_index, d_energy, n_energy, d_times,
+                                                       n_time, d_out));
     return check_launch("cgrb_evolution");
 }
 
@@ -1182,7 +1253,7 @@ int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int inter
     (void)interp_extrap;
     if (!d_dtab || !d_units || n_units <= 0)
         return fail(CGRB_E_BADARG, "cgrb_fmax: bad argument%s");
-    k_fmax<<<n_units, 64, 0, (cudaStream_t)stream>>>(d_dtab, d_units, n_units);
+    LAUNCH("k_fmax", (cudaStream_t)stream, k_fmax<<<n_units, 64, 0, (cudaStream_t)stream>>>(d_dtab, d_units, n_units));
     return check_launch("cgrb_fmax");
 }
 
@@ -1213,13 +1284,13 @@ int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
     if (rc)
         return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    k_gap_sums<0><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng, d_segsum, d_counts);
-    k_seg_scan<0><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
-                                                           d_segstart, d_counts);
-    k_source_thin<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng, d_segstart,
-                                                  d_segcount, d_stage, d_cand_times, d_cand_accept, d_counts);
-    k_source_gather<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_segcount,
-                                                    d_stage, d_times_src, d_counts);
+    LAUNCH("k_gap_sums<0>", s, k_gap_sums<0><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng, d_segsum, d_counts));
+    LAUNCH("k_seg_scan<0>", s, k_seg_scan<0><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
+                                                           d_segstart, d_counts));
+    LAUNCH("k_source_thin", s, k_source_thin<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng, d_segstart,
+                                                  d_segcount, d_stage, d_cand_times, d_cand_accept, d_counts));
+    LAUNCH("k_source_gather", s, k_source_gather<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_segcount,
+                                                    d_stage, d_times_src, d_counts));
     return check_launch("cgrb_sample_events");
 }
 
@@ -1238,9 +1309,9 @@ int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
         return rc;
     if (rng->mode == 1 && !rng->d_off)
         return fail(CGRB_E_BADARG, "cgrb_sample_energy: injected mode needs per-photon offsets%s");
-    k_sample_energy<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(
+    LAUNCH("k_sample_energy", (cudaStream_t)stream, k_sample_energy<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(
         d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, d_times_src, d_energy_src, d_trials,
-        d_counts);
+        d_counts));
     return check_launch("cgrb_sample_energy");
 }
 
@@ -1262,8 +1333,8 @@ int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
             return fail(CGRB_E_CUDA, "cgrb_digitize: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    k_digitize<<<(unsigned)n_work, NT, smem, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
-                                                                     d_energy_src, d_pha_src, d_counts);
+    LAUNCH("k_digitize", (cudaStream_t)stream, k_digitize<<<(unsigned)n_work, NT, smem, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
+                                                                     d_energy_src, d_pha_src, d_counts));
     return check_launch("cgrb_digitize");
 }
 
@@ -1289,11 +1360,11 @@ int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int
         chan = *rng_chan;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    k_gap_sums<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_counts);
-    k_seg_scan<1><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
-                                                           d_segstart, d_counts);
-    k_background<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng_time, chan, d_segstart,
-                                                 d_times_bkg, d_pha_bkg, d_counts);
+    LAUNCH("k_gap_sums<1>", s, k_gap_sums<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_counts));
+    LAUNCH("k_seg_scan<1>", s, k_seg_scan<1><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
+                                                           d_segstart, d_counts));
+    LAUNCH("k_background", s, k_background<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng_time, chan, d_segstart,
+                                                 d_times_bkg, d_pha_bkg, d_counts));
     return check_launch("cgrb_sample_background");
 }
 
@@ -1305,9 +1376,9 @@ int cgrb_combine(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_w
     if (!d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_bkg || !d_pha_bkg || !d_times_src ||
         !d_pha_src || !d_times_tot || !d_pha_tot || !d_counts)
         return fail(CGRB_E_BADARG, "cgrb_combine: bad argument%s");
-    k_combine<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(d_units, d_work, n_work, d_times_bkg,
+    LAUNCH("k_combine", (cudaStream_t)stream, k_combine<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(d_units, d_work, n_work, d_times_bkg,
                                                                  d_pha_bkg, d_times_src, d_pha_src, d_times_tot,
-                                                                 d_pha_tot, d_counts);
+                                                                 d_pha_tot, d_counts));
     return check_launch("cgrb_combine");
 }
 
@@ -1320,11 +1391,11 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
         !d_pha_tot || !d_tile_count || !d_times_out || !d_pha_out || !d_counts)
         return fail(CGRB_E_BADARG, "cgrb_gbm_dead_time: bad argument%s");
     cudaStream_t s = (cudaStream_t)stream;
-    k_deadtime_count<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_times_tot, d_pha_tot,
-                                                     d_tile_count, d_counts);
-    k_deadtime_write<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_times_tot,
+    LAUNCH("k_deadtime_count", s, k_deadtime_count<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_times_tot, d_pha_tot,
+                                                     d_tile_count, d_counts));
+    LAUNCH("k_deadtime_write", s, k_deadtime_write<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_times_tot,
                                                      d_pha_tot, d_tile_count, d_times_out, d_pha_out,
-                                                     d_selection, d_counts);
+                                                     d_selection, d_counts));
     return check_launch("cgrb_gbm_dead_time");
 }
 

@@ -280,6 +280,47 @@ class Engine(object):
         b.counts = c
         b.d_counts = self.to_device(c)
 
+    def reset_counts(self, b):
+        _capi.check(self.lib.cgrb_counts_reset(b.d_counts.data_ptr(), b.n_units, self.stream), "cgrb_counts_reset")
+        self.launches += 1
+        b.counts = None
+
+    # the six event lists of LightCurveStorage (light_curve_storage.py:16-80): name, slice kind
+    HOST_ARRAYS = (("times_out", "kept"), ("pha_out", "kept"), ("times_src", "src"), ("pha_src", "src"),
+                   ("times_bkg", "bkg"), ("pha_bkg", "bkg"))
+
+    def to_host(self, b, pinned=None, extra=()):
+        """Copy every unit's event lists to (pinned) host memory, compacted: returns a dict with
+        one host array per list plus per-unit offsets.  ``pinned`` is a cache of pinned staging
+        buffers that is reused (and grown) across calls."""
+        torch = _torch()
+        c = self.fetch_counts(b)
+        self.check_status(b)
+        pinned = {} if pinned is None else pinned
+        n_of = {"kept": c["n_kept"], "src": c["n_src"], "bkg": c["n_bkg"], "tot": c["n_total"]}
+        off_of = {"kept": b.units["tot_off"], "src": b.units["src_off"], "bkg": b.units["bkg_off"],
+                  "tot": b.units["tot_off"]}
+        out = {"counts": c, "d2h_bytes": int(c.nbytes), "events": int(c["n_src"].sum() + c["n_bkg"].sum())}
+        for name, kind in tuple(self.HOST_ARRAYS) + tuple(extra):
+            src = b.t[name]
+            n = n_of[kind].astype(np.int64)
+            starts = np.concatenate(([0], np.cumsum(n)))
+            total = int(starts[-1])
+            buf = pinned.get(name)
+            if buf is None or buf.numel() < total or buf.dtype != src.dtype:
+                buf = torch.empty(max(int(total * 1.1) + 1024, 1), dtype=src.dtype, pin_memory=True)
+                pinned[name] = buf
+            for ui in range(b.n_units):
+                k = int(n[ui])
+                if k:
+                    o = int(off_of[kind][ui])
+                    buf[int(starts[ui]):int(starts[ui]) + k].copy_(src[o:o + k], non_blocking=True)
+            out[name] = buf[:total]
+            out[name + "_offsets"] = starts
+            out["d2h_bytes"] += total * src.element_size()
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
     def fetch_counts(self, b):
         b.counts = b.d_counts.cpu().numpy().view(COUNTS_DTYPE).copy()
         return b.counts

@@ -139,6 +139,15 @@ const char *cgrb_last_error(void);
 /* number of SMs etc. of the current device: out[0]=sm count, out[1]=cc major, out[2]=cc minor, out[3]=max smem optin */
 int cgrb_device_info(int device, int *out4);
 
+/* Optional per-launch timing for benchmarks (no reference counterpart).  While enabled every
+ * kernel launch is bracketed by CUDA events on the launching stream.  cgrb_profile_enable(on)
+ * clears the records; cgrb_profile_read synchronises on the recorded events and returns the
+ * number of records copied (names: cap x 32 chars, may be NULL; ms: cap floats).
+ * cgrb_launch_count() = kernels launched by this library since load. */
+int cgrb_profile_enable(int on);
+int cgrb_profile_read(char *names, float *ms, int cap);
+long long cgrb_launch_count(void);
+
 /* host helper: split [0, cap_u) of each unit into chunks of `chunk` indices.
  * h_work may be NULL to query the count.  cap_u = h_units[i].src_cap (which=0, thinning
  * candidates), bkg_cap (which=1), src_cap+bkg_cap+2 (which=2, merged events) or src_cap+1

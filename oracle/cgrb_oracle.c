@@ -557,7 +557,7 @@ int64_t co_gbm_dead_time(const double *time, const double *pha, int64_t n, uint8
 int64_t co_process_detector(const co_source_t *s, const double *edges, int n_edges,
                             const double *ea_x, const double *ea_y, const double *cum, int n_chan,
                             const double *bkg_weights, double src_tstart, double src_tstop,
-                            double bkg_tstart, double bkg_tstop, double bkg_rate,
+                            double bkg_tstart, double bkg_tstop, double bkg_rate, double fmax_in,
                             uint32_t seed_numba, uint32_t seed_numpy, int64_t max_src_events,
                             int64_t *counters)
 {
@@ -568,7 +568,9 @@ int64_t co_process_detector(const co_source_t *s, const double *edges, int n_edg
     for (int k = 0; k < 6; k++)
         counters[k] = 0;
 
-    double fmax = co_fmax(s, ea_x, ea_y, n_ea, src_tstart, src_tstop);
+    /* fmax_in > 0: a window of a longer source interval, thinned with the full interval's fmax
+     * (bounded-sample CPU baseline); otherwise Source.__init__'s own 50-point maximum */
+    double fmax = (fmax_in > 0) ? fmax_in : co_fmax(s, ea_x, ea_y, n_ea, src_tstart, src_tstop);
 
     int64_t cap_src = (int64_t)(fmax * (src_tstop - src_tstart) * 1.2) + 1024;
     double *t_src = (double *)malloc(sizeof(double) * (size_t)cap_src);

@@ -109,12 +109,13 @@ void co_combine(const double *t_bkg, const double *pha_bkg, int64_t n_bkg,
 int64_t co_gbm_dead_time(const double *time, const double *pha, int64_t n, uint8_t *selection);
 
 /* lightcurve/lightcurve.py:167-200 for one detector, MT19937-seeded, used as the CPU baseline.
+ * fmax_in > 0 overrides Source._fmax (used to time a window of a longer burst).
  * Returns number of (source + background) events before dead time; counters[0..5] =
  * n_src, n_bkg, n_total_after_deadtime, n_candidates, n_trials, status. */
 int64_t co_process_detector(const co_source_t *s, const double *edges, int n_edges,
                             const double *ea_x, const double *ea_y, const double *cum, int n_chan,
                             const double *bkg_weights, double src_tstart, double src_tstop,
-                            double bkg_tstart, double bkg_tstop, double bkg_rate,
+                            double bkg_tstart, double bkg_tstop, double bkg_rate, double fmax_in,
                             uint32_t seed_numba, uint32_t seed_numpy, int64_t max_src_events,
                             int64_t *counters);
 

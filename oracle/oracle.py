@@ -101,7 +101,7 @@ def lib():
     L.co_combine.restype = None
     L.co_gbm_dead_time.argtypes = [vp, vp, i64, vp]
     L.co_gbm_dead_time.restype = i64
-    L.co_process_detector.argtypes = [sp, vp, i32, vp, vp, vp, i32, vp, d, d, d, d, d,
+    L.co_process_detector.argtypes = [sp, vp, i32, vp, vp, vp, i32, vp, d, d, d, d, d, d,
                                       C.c_uint32, C.c_uint32, i64, vp]
     L.co_process_detector.restype = i64
     _lib = L
@@ -275,13 +275,13 @@ def gbm_dead_time(times, pha):
 
 
 def process_detector(s, edges, ea, cum, bkg_weights, src_tstart, src_tstop, bkg_tstart, bkg_tstop, bkg_rate,
-                     seed_numba=1, seed_numpy=2, max_src_events=0):
+                     seed_numba=1, seed_numpy=2, max_src_events=0, fmax=0.0):
     """One LightCurve.process() (MT19937 streams). -> (n_events_pre_deadtime, counters[6])"""
     edges, cum, w = _f8(edges), _f8(cum), _f8(bkg_weights)
     ea_x, ea_y = _f8(ea[0]), _f8(ea[1])
     counters = np.zeros(6, np.int64)
     n = lib().co_process_detector(C.byref(s), edges.ctypes.data, len(edges), ea_x.ctypes.data, ea_y.ctypes.data,
                                   cum.ctypes.data, cum.shape[1], w.ctypes.data, src_tstart, src_tstop,
-                                  bkg_tstart, bkg_tstop, bkg_rate, seed_numba, seed_numpy, max_src_events,
+                                  bkg_tstart, bkg_tstop, bkg_rate, float(fmax), seed_numba, seed_numpy, max_src_events,
                                   counters.ctypes.data)
     return int(n), counters
