@@ -319,11 +319,11 @@ def run_gpu(args):
         return [t.copy() for t in tabs]              # defeat the engine's table cache: real H2D every step
 
     h2d = units.nbytes + sum(t.nbytes for t in tabs)
-    for k in range(max(1, min(args.warmup, 2))):
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))
+    for k in range(0 if args.no_e2e else max(1, min(args.warmup, 2))):
         step_e2e(k)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2e_steps = max(1, min(args.steps, 3))
     d2h, ev_e2e = 0, 0
     e0.record()
     for k in range(e2e_steps):
@@ -332,6 +332,7 @@ def run_gpu(args):
         ev_e2e += out["events"]
     e1.record()
     sync_all()
+    e2e_steps = max(e2e_steps, 1)
     ms_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     ev_e2e_t = torch.tensor([ev_e2e], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -383,6 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
