@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads and exports every symbol include/cosmogrb_b200.h declares; the host
+work-list helper (no device needed) behaves; the product path fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cosmogrb_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cosmogrb_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgrb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+
+    ge.build()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+    assert set(names) == set(_capi.EXPORTS)
+    assert _capi.load().cgrb_abi_version() == _capi.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    assert _capi.UNIT_DTYPE.itemsize == 192 and _capi.COUNTS_DTYPE.itemsize == 56 and _capi.WORK_DTYPE.itemsize == 16
+    src = open(os.path.join(ROOT, "include", "cosmogrb_b200.h")).read()
+    for name in ("EDGES", "EA_X", "EA_Y", "BKG_CDF", "G75_E", "G75_A", "G500_E", "G500_A", "CUM"):
+        m = re.search(rf"#define CGRB_DT_{name} (\d+)", src)
+        assert int(m.group(1)) == getattr(_capi, f"DT_{name}")
+
+
+def test_build_work():
+    u = np.zeros(3, dtype=_capi.UNIT_DTYPE)
+    u["src_cap"] = [0, 8192, 20000]
+    u["bkg_cap"] = [5, 0, 100]
+    w = _capi.build_work(u, 0, 8192)
+    assert list(w["unit"]) == [0, 1, 2, 2, 2]            # every unit owns at least one entry
+    assert list(w["start"]) == [0, 0, 0, 8192, 16384]
+    w2 = _capi.build_work(u, 2, 2048)
+    assert (w2["unit"] == 2).sum() == (20000 + 100 + 2 + 2047) // 2048
+
+
+def test_bad_arguments_are_reported():
+    lib = _capi.load()
+    assert lib.cgrb_counts_reset(None, 1, None) == -1
+    assert b"bad argument" in lib.cgrb_last_error()
+    with pytest.raises(_capi.EngineError):
+        _capi.check(-1, "x")
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from cosmogrb_b200.engine import Engine
+
+    with pytest.raises(_capi.EngineUnavailable):
+        Engine()
