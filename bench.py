@@ -220,7 +220,7 @@ def run_gpu(args):
         """the event-offset gather: per-unit (n_src, n_bkg, n_kept) of all ranks -> global offsets"""
         if dist is None:
             return None
-        c = counts_dev.view(torch.int64).view(len(units), -1)[:, [1, 2, 4]].contiguous()
+        c = counts_dev.view(torch.int64).view(len(units), -1)[:, [1, 2, 4]].contiguous()   # n_src, n_bkg, n_kept
         out = torch.empty((world,) + tuple(c.shape), dtype=c.dtype, device=dev)
         dist.all_gather_into_tensor(out, c)
         return torch.cumsum(out.view(-1, 3), dim=0)
@@ -361,6 +361,7 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "units_per_step_per_gpu": len(units),
                        "events_per_step_per_gpu": ev_step, "source_events": n_src, "background_events": n_bkg,
                        "candidates": int(counts["n_candidates"].sum()), "rejection_trials": int(counts["n_trials"].sum()),
+                       "exact_lambda_evaluations": int(counts["n_exact"].sum()),
                        "kept_after_dead_time": int(counts["n_kept"].sum()), "rng": "philox4x32-10",
                        "l2": "no flush needed: each step streams > 2 GB of event buffers (L2 is 126 MB)",
                        "parallelism": f"{world} x (1 GRB = 14 units per GPU per step)"},

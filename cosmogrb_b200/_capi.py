@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NBINS = 140
 NCHAN = 128
 NE_LAMBDA = 75
@@ -60,19 +60,19 @@ UNIT_DTYPE = np.dtype(
         ("bkg_tstart", "<f8"), ("bkg_tstop", "<f8"), ("bkg_rate", "<f8"),
         ("fmax", "<f8"), ("gamma_a", "<f8"), ("lgamma_a", "<f8"), ("lgamma_1pa", "<f8"),
         ("src_cap", "<i8"), ("bkg_cap", "<i8"), ("src_off", "<i8"), ("bkg_off", "<i8"),
-        ("tot_off", "<i8"), ("reserved", "<i8"),
+        ("tot_off", "<i8"), ("tab_off", "<i8"), ("tab_n", "<i8"), ("ea_scale", "<f8"),
     ],
     align=False,
 )
-assert UNIT_DTYPE.itemsize == 192
+assert UNIT_DTYPE.itemsize == 208
 
 COUNTS_DTYPE = np.dtype(
     [
         ("n_candidates", "<i8"), ("n_src", "<i8"), ("n_bkg", "<i8"), ("n_total", "<i8"),
-        ("n_kept", "<i8"), ("n_trials", "<i8"), ("status", "<u4"), ("pad", "<u4"),
+        ("n_kept", "<i8"), ("n_trials", "<i8"), ("n_exact", "<i8"), ("status", "<u4"), ("pad", "<u4"),
     ]
 )
-assert COUNTS_DTYPE.itemsize == 56
+assert COUNTS_DTYPE.itemsize == 64
 
 WORK_DTYPE = np.dtype([("unit", "<i4"), ("seg", "<i4"), ("start", "<i8")])
 assert WORK_DTYPE.itemsize == 16
@@ -101,10 +101,14 @@ EXPORTS = (
     "cgrb_energy_integrated_evolution",
     "cgrb_evolution",
     "cgrb_fmax",
+    "cgrb_thin_tables",
     "cgrb_sample_events",
     "cgrb_sample_energy",
+    "cgrb_energy_workspace_bytes",
+    "cgrb_sample_energy_envelope",
     "cgrb_digitize",
     "cgrb_sample_background",
+    "cgrb_background_channels",
     "cgrb_combine",
     "cgrb_gbm_dead_time",
 )
@@ -137,15 +141,20 @@ def load():
     lib.cgrb_evolution.argtypes = [vp, i32, vp, i64, vp, i64, vp, vp]
     lib.cgrb_fmax.argtypes = [vp, vp, i32, i32, vp]
     rp = C.POINTER(RngDesc)
-    lib.cgrb_sample_events.argtypes = [vp, vp, i32, vp, i64, vp, i32, rp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_thin_tables.argtypes = [vp, vp, i32, vp, i64, vp, vp]
+    lib.cgrb_sample_events.argtypes = [vp, vp, i32, vp, i64, vp, i32, rp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cgrb_sample_energy.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, vp, vp, vp, vp]
+    lib.cgrb_energy_workspace_bytes.argtypes = [i32]
+    lib.cgrb_energy_workspace_bytes.restype = i64
+    lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, vp, vp, vp, vp, vp]
     lib.cgrb_digitize.argtypes = [vp, vp, i32, vp, i64, rp, vp, vp, vp, vp]
     lib.cgrb_sample_background.argtypes = [vp, vp, i32, vp, i64, vp, rp, rp, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_background_channels.argtypes = [vp, i32, C.c_uint32, rp, i64, vp, vp]
     lib.cgrb_combine.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cgrb_gbm_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count"):
+        if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count", "cgrb_energy_workspace_bytes"):
             fn.restype = i32
     if lib.cgrb_abi_version() != ABI_VERSION:
         raise EngineUnavailable(

@@ -39,6 +39,8 @@ _DEFAULTS = {
         "seed": 0x00C0560612B,
         # semantics of interpolation.interp outside the table: "linear" | "clamp"
         "interp_extrap": "linear",
+        # photon-energy sampler under Philox: "envelope" (tight exact envelope) | "literal"
+        "energy_sampler": "envelope",
         # upper bound on CPL rejection trials per photon
         "max_trials": 1 << 22,
     },

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "cgrb_device.cuh"
+#include "cgrb_energy.cuh"
 
 using namespace cgrb;
 
@@ -192,7 +193,7 @@ __device__ __forceinline__ void build_lambda_tab(LambdaTab *tab, const double *d
             w = 0.5 * (E[m] - E[m - 1]) + 0.5 * (E[m + 1] - E[m]);
         double x = E[m] * opz;                       // cpl_functions.py:95
         tab->x[m] = x;
-        tab->c[m] = w * A[m] * pow(x, u.alpha);
+        tab->c[m] = w * (A[m] * u.ea_scale) * pow(x, u.alpha);
     }
 }
 
@@ -282,6 +283,68 @@ __global__ void __launch_bounds__(64) k_fmax(const double *__restrict__ dtab, cg
 }
 
 // ==========================================================================================
+// squeeze table of the thinning acceptance probability p(t) = lambda(t) / fmax (see the header):
+// nodes on a uniform time grid, then per-interval interpolation-error margins from second differences.
+// ==========================================================================================
+__global__ void __launch_bounds__(NT) k_thin_nodes(const double *__restrict__ dtab,
+                                                   const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   double *__restrict__ thin_tab)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    if (threadIdx.x == 0)
+        u = units[wk.unit];
+    __syncthreads();
+    if (u.tab_n < 4 || (u.flags & CGRB_UNIT_NO_SOURCE))
+        return;
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    __syncthreads();
+    const int64_t k = wk.start + threadIdx.x;
+    if (k >= u.tab_n)
+        return;
+    const double h = (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1);
+    const double t = (k == u.tab_n - 1) ? u.src_tstop : u.src_tstart + (double)k * h;
+    thin_tab[2 * (u.tab_off + k)] = lambda_at(&tab, u, t) / u.fmax;
+}
+
+__global__ void __launch_bounds__(NT) k_thin_margins(const cgrb_unit_t *__restrict__ units,
+                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                     double *__restrict__ thin_tab)
+{
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t n = u->tab_n;
+    if (n < 4 || (u->flags & CGRB_UNIT_NO_SOURCE))
+        return;
+    const int64_t k = wk.start + threadIdx.x;      // interval [k, k+1]
+    if (k >= n)
+        return;
+    const double *p = thin_tab + 2 * u->tab_off;
+    // |second differences| at the nodes k-1 .. k+2 (clamped to the interior nodes 1 .. n-2)
+    double m = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int d = -1; d <= 2; d++) {
+        int64_t c = min(max(k + d, (int64_t)1), n - 2);
+        double d2 = fabs(p[2 * (c - 1)] - 2.0 * p[2 * c] + p[2 * (c + 1)]);
+        bad |= !(d2 == d2) || isinf(d2);
+        m = fmax(m, d2);
+    }
+    // linear interpolation error <= h^2/8 sup|p''| ~ d2/8; x4 safety, plus rounding slack
+    double pk = fabs(p[2 * k]);
+    double margin = 0.5 * m + 1e-12 * (pk + 1.0);
+    thin_tab[2 * (u->tab_off + k) + 1] = bad ? INFINITY : margin;
+}
+
+// ==========================================================================================
 // thinning pass 1: sum of exponential gaps of each segment, in exactly the association order
 // that pass 3 uses for its running time, so that segment boundaries are exactly consistent.
 // ==========================================================================================
@@ -366,7 +429,8 @@ __global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ d
                                                     cgrb_rng_t rng, const double *__restrict__ segstart,
                                                     int32_t *__restrict__ segcount, double *__restrict__ stage,
                                                     double *__restrict__ cand_times,
-                                                    uint8_t *__restrict__ cand_accept, cgrb_counts_t *counts)
+                                                    uint8_t *__restrict__ cand_accept,
+                                                    const double *__restrict__ thin_tab, cgrb_counts_t *counts)
 {
     __shared__ LambdaTab tab;
     __shared__ cgrb_unit_t u;
@@ -394,6 +458,12 @@ __global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ d
 
     const double inv_f = 1.0 / u.fmax;
     const int64_t n = min((int64_t)CGRB_SEG, u.src_cap - wk.start);
+    // squeeze table of p(t) = lambda(t)/fmax (cgrb_thin_tables): decides most candidates without
+    // evaluating lambda; the rest take the exact test, so decisions are those of the exact test
+    const bool squeeze = thin_tab != nullptr && u.tab_n >= 4;
+    const double2 *sq = reinterpret_cast<const double2 *>(thin_tab) + (squeeze ? u.tab_off : 0);
+    const double sq_inv_h = squeeze ? (double)(u.tab_n - 1) / (u.src_tstop - u.src_tstart) : 0.0;
+    long long n_exact = 0;
     double carry = 0.0;
     int seg_n = 0;        // accepted so far in this segment
     int n_valid_total = 0;
@@ -420,8 +490,24 @@ __global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ d
         const bool valid = inrange && (t <= u.src_tstop);   // `if time > tstop: break`
         bool acc = false;
         if (valid) {
-            double p_test = lambda_at(&tab, u, t) / u.fmax;
-            acc = (u2 <= p_test);                           // `if test <= p_test`
+            int decided = 0;
+            if (squeeze) {
+                double q = (t - u.src_tstart) * sq_inv_h;
+                int64_t kq = min(max((int64_t)q, (int64_t)0), u.tab_n - 2);
+                double fr = q - (double)kq;
+                double2 n0 = __ldg(sq + kq), n1 = __ldg(sq + kq + 1);
+                double pl = n0.x + (n1.x - n0.x) * fr;
+                if (u2 <= pl - n0.y) {
+                    acc = true;
+                    decided = 1;
+                } else if (u2 > pl + n0.y)
+                    decided = 1;
+            }
+            if (!decided) {
+                double p_test = lambda_at(&tab, u, t) / u.fmax;
+                acc = (u2 <= p_test);                       // `if test <= p_test`
+                n_exact++;
+            }
         }
         // ordered compaction
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -455,10 +541,17 @@ __global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ d
         if (tile_valid < (int)min((int64_t)NT, n - base))
             break;      // crossed tstop: everything later is beyond it
     }
-    if (threadIdx.x == 0) {
-        segcount[w] = seg_n;
-        if (n_valid_total)
-            atomicAdd((unsigned long long *)&counts[wk.unit].n_candidates, (unsigned long long)n_valid_total);
+    {
+        long long *s_ll = reinterpret_cast<long long *>(s_t);      // s_t is free now
+        __syncthreads();
+        const long long tot_exact = block_sum_ll(n_exact, s_ll);
+        if (threadIdx.x == 0) {
+            segcount[w] = seg_n;
+            if (n_valid_total)
+                atomicAdd((unsigned long long *)&counts[wk.unit].n_candidates, (unsigned long long)n_valid_total);
+            if (tot_exact)
+                atomicAdd((unsigned long long *)&counts[wk.unit].n_exact, (unsigned long long)tot_exact);
+        }
     }
     if (exhausted)
         atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
@@ -610,9 +703,9 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
 }
 
 // ==========================================================================================
-// photon energies (cpl_functions.py:191-286): one warp per photon.  The 500-point envelope
-// maximum is found on log f (monotone in f, no exp); the rejection loop runs 32 trials per round,
-// one per lane, and the lowest accepted trial wins, which is the serial loop's result.
+// photon energies (cpl_functions.py:191-286), literal sampler: one warp per photon.  The 500-point
+// envelope maximum is found on log f (monotone in f, no exp); the rejection loop runs 32 trials per
+// round, one per lane, and the lowest accepted trial wins, which is the serial loop's result.
 // ==========================================================================================
 struct EnergyTab {
     double gx[CGRB_NE_ENVELOPE];   // x_m = E_m (1+z)
@@ -620,6 +713,25 @@ struct EnergyTab {
     double eax[CGRB_NBINS];
     double eay[CGRB_NBINS];
 };
+
+__device__ __forceinline__ EaGuess make_ea_guess(const double *eax)
+{
+    EaGuess g;
+    g.log_x0 = log(eax[0]);
+    g.inv_dlog = (double)(CGRB_NBINS - 1) / (log(eax[CGRB_NBINS - 1]) - g.log_x0);
+    return g;
+}
+
+__device__ __forceinline__ PropConst make_prop_const(double emin, double emax, double alpha)
+{
+    // power-law proposal constants (cpl_functions.py:254-258)
+    PropConst pc;
+    const double ap1 = alpha + 1.0;
+    pc.q_lo = pow(emin, ap1);
+    pc.p_span = pow(emax, ap1) - pc.q_lo;
+    pc.inv_ap1 = 1.0 / ap1;
+    return pc;
+}
 
 __global__ void __launch_bounds__(NT) k_sample_energy(const double *__restrict__ dtab,
                                                       const cgrb_unit_t *__restrict__ units,
@@ -656,12 +768,8 @@ __global__ void __launch_bounds__(NT) k_sample_energy(const double *__restrict__
     }
     __syncthreads();
 
-    const double emin = dt[CGRB_DT_EDGES], emax = dt[CGRB_DT_EDGES + CGRB_NBINS];
-    // power-law proposal constants (cpl_functions.py:254-258)
-    const double ap1 = alpha + 1.0;
-    const double q_lo = pow(emin, ap1);
-    const double p_span = pow(emax, ap1) - q_lo;
-    const double inv_ap1 = 1.0 / ap1;
+    const PropConst pc = make_prop_const(dt[CGRB_DT_EDGES], dt[CGRB_DT_EDGES + CGRB_NBINS], alpha);
+    const EaGuess eg = make_ea_guess(tab.eax);
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // chunk end: next work entry of the same unit starts where this chunk ends
@@ -694,16 +802,7 @@ __global__ void __launch_bounds__(NT) k_sample_energy(const double *__restrict__
             }
         }
         int idx = (bidx < CGRB_NE_ENVELOPE) ? bidx : 0;
-        // literal tmp[idx] = interp(E_idx) * cpl(E_idx (1+z))
-        double A_idx = dt[CGRB_DT_G500_A + idx];
-        double f_idx = A_idx * cpl_value(s, alpha, tab.gx[idx], log(tab.gx[idx]));
-        if (!(f_idx > 0.0)) {       // all-zero (K = 0 before the pulse) or degenerate: np.argmax -> 0
-            idx = 0;
-            A_idx = dt[CGRB_DT_G500_A];
-            f_idx = A_idx * cpl_value(s, alpha, tab.gx[0], log(tab.gx[0]));
-        }
-        const double C = f_idx * 5.0;                         // :241
-        const double e_idx = dt[CGRB_DT_G500_E + idx];
+        const PhotonConst ph = literal_photon(u, s, dt, tab.gx, &idx);
 
         int64_t base_pos = 0;
         if (rng.mode != 0)
@@ -731,12 +830,8 @@ __global__ void __launch_bounds__(NT) k_sample_energy(const double *__restrict__
                     ok = false;
                 }
             }
-            double x = pow(p_span * u1 + q_lo, inv_ap1);                       // :253-258
-            double y = u2 * C * pow(x / e_idx, alpha);                         // :260
-            double xr = x * opz;
-            double fx = interp1(tab.eax, tab.eay, CGRB_NBINS, x, interp_extrap) *
-                        cpl_value(s, alpha, xr, log(xr));
-            bool accept = (y <= fx) || !ok;
+            double x;
+            bool accept = literal_trial(pc, ph, tab.eax, tab.eay, eg, interp_extrap, u1, u2, &x) || !ok;
             unsigned bal = __ballot_sync(0xffffffffu, accept);
             if (bal) {
                 int win = __ffs(bal) - 1;
@@ -767,6 +862,197 @@ __global__ void __launch_bounds__(NT) k_sample_energy(const double *__restrict__
     if (lane == 0 && (exhausted || capped))
         atomicOr(&counts[wk.unit].status,
                  (exhausted ? CGRB_ST_UNIFORMS_EXHAUSTED : 0u) | (capped ? CGRB_ST_TRIAL_CAP : 0u));
+}
+
+// ==========================================================================================
+// photon energies, envelope sampler (Philox only): one thread per photon; see cgrb_energy.cuh.
+// Exact rejection sampling of the literal sampler's output density
+//     h(x) ~ x^alpha min(A(x) e^{-x w}, 5 A(E_idx) e^{-E_idx w}),   w = (1+z)/ec(t)
+// with proposal l = log(x w) from the per-unit piecewise envelope of phi(l) = (alpha+1) l - e^l,
+// truncated to the photon's [log(emin w), log(emax w)] by inverse CDF, and A(x) <= Amax.
+// Degenerate photons (pulse amplitude 0: the spurious tstart event) take the literal first trial.
+// ==========================================================================================
+// literal sampler for one photon by one thread (same Philox counters as the warp version); only
+// degenerate photons take this path, so it is kept out of line to spare registers.
+__device__ __noinline__ double literal_photon_serial(const cgrb_unit_t &u, const double *dt, const double *eax,
+                                                     const double *eay, EaGuess eg, int interp_extrap,
+                                                     uint64_t seed, int64_t i, double t, int64_t max_trials,
+                                                     int64_t *ntr_out, bool *capped)
+{
+    const double opz = 1.0 + u.z, alpha = u.alpha;
+    const SpecT sp = spec_at(u, t);
+    const PropConst pc = make_prop_const(dt[CGRB_DT_EDGES], dt[CGRB_DT_EDGES + CGRB_NBINS], alpha);
+    double best = -INFINITY;
+    int idx = 0;
+    for (int m = 0; m < CGRB_NE_ENVELOPE; m++) {
+        double A = dt[CGRB_DT_G500_A + m], xg = dt[CGRB_DT_G500_E + m] * opz;
+        double g = (A > 0.0) ? log(A) + alpha * log(xg) - xg * sp.inv_ec : -INFINITY;
+        if (g > best) {
+            best = g;
+            idx = m;
+        }
+    }
+    double A_idx = dt[CGRB_DT_G500_A + idx], x_idx = dt[CGRB_DT_G500_E + idx] * opz;
+    double f_idx = A_idx * cpl_value(sp, alpha, x_idx, log(x_idx));
+    if (!(f_idx > 0.0)) {       // np.argmax of an all-zero row -> 0
+        idx = 0;
+        A_idx = dt[CGRB_DT_G500_A];
+        x_idx = dt[CGRB_DT_G500_E] * opz;
+        f_idx = A_idx * cpl_value(sp, alpha, x_idx, log(x_idx));
+    }
+    PhotonConst ph;
+    ph.K1 = f_idx * 5.0 * exp(-alpha * log(dt[CGRB_DT_G500_E + idx]));
+    ph.K2 = sp.norm * exp(alpha * (log(opz) - sp.log_ec));
+    ph.w = opz * sp.inv_ec;
+    for (uint32_t j = 0;; j++) {
+        Philox4 p = philox_at(make_key(seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
+        double x;
+        *ntr_out = (int64_t)j + 1;
+        if (literal_trial(pc, ph, eax, eay, eg, interp_extrap, u53(p.x, p.y), u53(p.z, p.w), &x))
+            return x;
+        if (max_trials > 0 && *ntr_out >= max_trials) {
+            *capped = true;
+            return nan("");
+        }
+    }
+}
+
+struct EnvSmem {
+    double cdf[CGRB_ENV_SEGS + 1];
+    double inv_b[CGRB_ENV_SEGS];
+    double lstar[CGRB_ENV_SEGS];
+    double sstar[CGRB_ENV_SEGS];
+    double hull_w[CGRB_NE_ENVELOPE];
+    int hull_m[CGRB_NE_ENVELOPE];
+    double eax[CGRB_NBINS];
+    double eay[CGRB_NBINS];
+};
+
+__global__ void __launch_bounds__(NT) k_sample_energy_env(const double *__restrict__ dtab,
+                                                          const cgrb_unit_t *__restrict__ units,
+                                                          const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                          int interp_extrap, cgrb_rng_t rng, int64_t max_trials,
+                                                          const EnergyUnitTab *__restrict__ etab,
+                                                          const double *__restrict__ times_src,
+                                                          double *__restrict__ energy_src,
+                                                          int32_t *__restrict__ trials_out, cgrb_counts_t *counts)
+{
+    __shared__ EnvSmem sm;
+    __shared__ cgrb_unit_t u;
+    __shared__ long long s_wl[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const int64_t n_src = counts[wk.unit].n_src;
+    if (wk.start >= n_src)
+        return;
+    const EnergyUnitTab *T = etab + wk.unit;
+    if (threadIdx.x == 0)
+        u = units[wk.unit];
+    for (int j = threadIdx.x; j <= CGRB_ENV_SEGS; j += NT)
+        sm.cdf[j] = T->cdf[j];
+    for (int j = threadIdx.x; j < CGRB_ENV_SEGS; j += NT) {
+        sm.inv_b[j] = T->inv_b[j];
+        sm.lstar[j] = T->lstar[j];
+        sm.sstar[j] = T->sstar[j];
+    }
+    const int n_hull = T->n_hull;
+    for (int j = threadIdx.x; j < n_hull; j += NT) {
+        sm.hull_w[j] = T->hull_w[j];
+        sm.hull_m[j] = T->hull_m[j];
+    }
+    __syncthreads();
+    const double *dt = dtab + (size_t)u.det * CGRB_DT_SIZE;
+    for (int m = threadIdx.x; m < CGRB_NBINS; m += NT) {
+        sm.eax[m] = dt[CGRB_DT_EA_X + m];
+        sm.eay[m] = dt[CGRB_DT_EA_Y + m];
+    }
+    __syncthreads();
+    const double opz = 1.0 + u.z, alpha = u.alpha;
+    const double emin = dt[CGRB_DT_EDGES], emax = dt[CGRB_DT_EDGES + CGRB_NBINS];
+    const double l0 = T->l0, dl = T->dl, inv_dl = T->inv_dl, a = T->a, amax = T->amax;
+    const double log_emin = log(emin), log_emax = log(emax);
+    const EaGuess eg = make_ea_guess(sm.eax);
+    const double ec_den = (alpha == -2.0) ? 0.0001 : (2.0 + alpha);
+
+    int64_t chunk_end = n_src;
+    if (w + 1 < n_work && work[w + 1].unit == wk.unit)
+        chunk_end = min(n_src, work[w + 1].start);
+
+    long long my_trials = 0;
+    bool capped = false;
+    for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += NT) {
+        const double t = times_src[u.src_off + i];
+        double x_acc = nan("");
+        int64_t ntr = 0;
+        // pulse amplitude > 0 ?  (norris underflows for t -> 0+; constant CPL is always regular)
+        bool regular = (u.kind != 0) || (t > 0.0 && (u.trise / t + t / u.tdecay) < 700.0 && u.peak_flux > 0.0);
+        const double ep = (u.kind == 0) ? u.ep_start / (1.0 + t / u.ep_tau) : u.ep_start;
+        const double wq = opz * ec_den / ep;            // (1+z) / ec
+        const double logw = log(wq);
+        double l_lo = log_emin + logw, l_hi = log_emax + logw;
+        // piecewise-linear CDF of the envelope at the truncation points
+        double F_lo, F_hi;
+        {
+            double q = (l_lo - l0) * inv_dl;
+            int j = max(0, min((int)q, CGRB_ENV_SEGS - 1));
+            F_lo = sm.cdf[j] + (sm.cdf[j + 1] - sm.cdf[j]) * fmin(fmax(q - j, 0.0), 1.0);
+            q = (l_hi - l0) * inv_dl;
+            j = max(0, min((int)q, CGRB_ENV_SEGS - 1));
+            F_hi = sm.cdf[j] + (sm.cdf[j + 1] - sm.cdf[j]) * fmin(fmax(q - j, 0.0), 1.0);
+        }
+        if (!(F_hi > F_lo))
+            regular = false;
+        if (regular) {
+            const int idx = hull_lookup(sm.hull_m, sm.hull_w, n_hull, ec_den / ep);
+            const double s_idx = dt[CGRB_DT_G500_E + idx] * wq;
+            const double A5 = 5.0 * dt[CGRB_DT_G500_A + idx];
+            const double inv_w = 1.0 / wq;
+            for (uint32_t j = 0;; j++) {
+                Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
+                const double U = u53(p.x, p.y), V = u53(p.z, p.w);
+                const double y = F_lo + U * (F_hi - F_lo);
+                int lo = 0, hi = CGRB_ENV_SEGS;         // segment: cdf[lo] <= y < cdf[lo+1]
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (sm.cdf[mid] <= y)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                double l = l0 + lo * dl + (y - sm.cdf[lo]) * sm.inv_b[lo];
+                l = fmin(fmax(l, l_lo), l_hi);
+                const double s = exp(l);
+                const double x = s * inv_w;
+                const double r1 = exp(a * (l - sm.lstar[lo]) - (s - sm.sstar[lo]));
+                double A = fmax(interp_guess(sm.eax, sm.eay, CGRB_NBINS, x, l - logw, eg, interp_extrap), 0.0);
+                if (!(s >= s_idx && A <= A5))
+                    A = fmin(A, A5 * exp(s - s_idx));   // the literal envelope clips f here
+                ntr = (int64_t)j + 1;
+                if (V * amax <= r1 * A) {
+                    x_acc = x;
+                    break;
+                }
+                if (max_trials > 0 && ntr >= max_trials) {
+                    capped = true;
+                    break;
+                }
+            }
+        } else {
+            x_acc = literal_photon_serial(u, dt, sm.eax, sm.eay, eg, interp_extrap, rng.seed, i, t, max_trials, &ntr,
+                                          &capped);
+        }
+        energy_src[u.src_off + i] = x_acc;
+        if (trials_out)
+            trials_out[u.src_off + i] = (int32_t)ntr;
+        my_trials += ntr;
+    }
+    const long long tot = block_sum_ll(my_trials, s_wl);
+    if (threadIdx.x == 0 && tot)
+        atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)tot);
+    if (capped)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_TRIAL_CAP);
 }
 
 // ==========================================================================================
@@ -1118,6 +1404,27 @@ __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__rest
     }
 }
 
+// BackgroundSpectrumTemplate.sample_channel(size) on its own (background.py:80-93): n draws from the
+// detector's channel cdf; Philox index = event index (stage ST_BKG, sub-stream 1), or injected u[i].
+__global__ void __launch_bounds__(NT) k_background_channels(const double *__restrict__ dtab, int det, uint32_t stream_id,
+                                                            cgrb_rng_t rng, int64_t n, uint8_t *__restrict__ out)
+{
+    __shared__ double s_cdf[CGRB_NCHAN];
+    const double *cdf_g = dtab + (size_t)det * CGRB_DT_SIZE + CGRB_DT_BKG_CDF;
+    if (threadIdx.x < CGRB_NCHAN)
+        s_cdf[threadIdx.x] = cdf_g[threadIdx.x];
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT) {
+        double uc;
+        if (rng.mode == 0) {
+            Philox4 p = philox_at(make_key(rng.seed), stream_id, ST_BKG, (uint64_t)i, 1u);
+            uc = u53(p.x, p.y);
+        } else
+            uc = rng.d_u[i];
+        out[i] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, uc), CGRB_NCHAN - 1);
+    }
+}
+
 __global__ void k_counts_reset(cgrb_counts_t *counts, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1188,14 +1495,15 @@ int cgrb_device_info(int device, int *out4)
 int64_t cgrb_build_work(const cgrb_unit_t *h_units, int n_units, int which, int64_t chunk,
                         cgrb_work_t *h_work, int64_t work_cap)
 {
-    if (!h_units || n_units < 0 || chunk <= 0 || which < 0 || which > 3)
+    if (!h_units || n_units < 0 || chunk <= 0 || which < 0 || which > 4)
         return fail(CGRB_E_BADARG, "cgrb_build_work: bad argument%s");
     int64_t n = 0;
     for (int i = 0; i < n_units; i++) {
         int64_t cap = which == 0   ? h_units[i].src_cap
                       : which == 1 ? h_units[i].bkg_cap
                       : which == 2 ? h_units[i].src_cap + h_units[i].bkg_cap + 2
-                                   : h_units[i].src_cap + 1;
+                      : which == 3 ? h_units[i].src_cap + 1
+                                   : h_units[i].tab_n;
         int64_t nseg = (cap + chunk - 1) / chunk;
         if (nseg < 1)
             nseg = 1;   // every unit owns at least one entry (it carries the per-unit epilogue)
@@ -1257,6 +1565,17 @@ int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int inter
     return check_launch("cgrb_fmax");
 }
 
+int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work,
+                     int64_t n_work, double *d_thin_tab, void *stream)
+{
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_thin_tab)
+        return fail(CGRB_E_BADARG, "cgrb_thin_tables: bad argument%s");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH("k_thin_nodes", s, k_thin_nodes<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, d_thin_tab));
+    LAUNCH("k_thin_margins", s, k_thin_margins<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_thin_tab));
+    return check_launch("cgrb_thin_tables");
+}
+
 static int check_rng(const cgrb_rng_t *rng, const char *who)
 {
     if (!rng)
@@ -1272,7 +1591,7 @@ int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
                        const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
                        int interp_extrap, const cgrb_rng_t *rng, double *d_segsum, double *d_segstart,
                        int32_t *d_segcount, double *d_stage, double *d_times_src, double *d_cand_times,
-                       uint8_t *d_cand_accept, cgrb_counts_t *d_counts, void *stream)
+                       uint8_t *d_cand_accept, const double *d_thin_tab, cgrb_counts_t *d_counts, void *stream)
 {
     (void)interp_extrap;
     if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_segsum ||
@@ -1288,7 +1607,7 @@ int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
     LAUNCH("k_seg_scan<0>", s, k_seg_scan<0><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
                                                            d_segstart, d_counts));
     LAUNCH("k_source_thin", s, k_source_thin<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng, d_segstart,
-                                                  d_segcount, d_stage, d_cand_times, d_cand_accept, d_counts));
+                                                  d_segcount, d_stage, d_cand_times, d_cand_accept, d_thin_tab, d_counts));
     LAUNCH("k_source_gather", s, k_source_gather<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_segcount,
                                                     d_stage, d_times_src, d_counts));
     return check_launch("cgrb_sample_events");
@@ -1313,6 +1632,34 @@ int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
         d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, d_times_src, d_energy_src, d_trials,
         d_counts));
     return check_launch("cgrb_sample_energy");
+}
+
+int64_t cgrb_energy_workspace_bytes(int n_units) { return (int64_t)sizeof(EnergyUnitTab) * (n_units > 0 ? n_units : 0); }
+
+int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                                const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
+                                const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace,
+                                const double *d_times_src, double *d_energy_src, int32_t *d_trials,
+                                cgrb_counts_t *d_counts, void *stream)
+{
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_src || !d_energy_src ||
+        !d_counts || !d_workspace)
+        return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: bad argument%s");
+    if (interp_extrap != 0 && interp_extrap != 1)
+        return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: interp_extrap must be 0 (linear) or 1 (clamp)%s");
+    int rc = check_rng(rng, "cgrb_sample_energy_envelope");
+    if (rc)
+        return rc;
+    if (rng->mode != 0)
+        return fail(CGRB_E_UNSUPPORTED,
+                    "cgrb_sample_energy_envelope: injected uniforms replay the literal sampler; use cgrb_sample_energy%s");
+    cudaStream_t s = (cudaStream_t)stream;
+    EnergyUnitTab *etab = (EnergyUnitTab *)d_workspace;
+    LAUNCH("k_energy_tables", s, k_energy_tables<<<n_units, 256, 0, s>>>(d_dtab, d_units, n_units, interp_extrap, etab));
+    LAUNCH("k_sample_energy_env", s, k_sample_energy_env<<<(unsigned)n_work, NT, 0, s>>>(
+        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, d_times_src, d_energy_src, d_trials,
+        d_counts));
+    return check_launch("cgrb_sample_energy_envelope");
 }
 
 int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work,
@@ -1366,6 +1713,22 @@ int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int
     LAUNCH("k_background", s, k_background<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng_time, chan, d_segstart,
                                                  d_times_bkg, d_pha_bkg, d_counts));
     return check_launch("cgrb_sample_background");
+}
+
+int cgrb_background_channels(const double *d_dtab, int det, uint32_t stream_id, const cgrb_rng_t *rng, int64_t n,
+                             uint8_t *d_out, void *stream)
+{
+    if (!d_dtab || det < 0 || n < 0 || !d_out)
+        return fail(CGRB_E_BADARG, "cgrb_background_channels: bad argument%s");
+    int rc = check_rng(rng, "cgrb_background_channels");
+    if (rc)
+        return rc;
+    if (n == 0)
+        return CGRB_OK;
+    int grid = (int)min((int64_t)(148 * 8), (n + NT - 1) / NT);
+    LAUNCH("k_background_channels", (cudaStream_t)stream,
+           k_background_channels<<<grid, NT, 0, (cudaStream_t)stream>>>(d_dtab, det, stream_id, *rng, n, d_out));
+    return check_launch("cgrb_background_channels");
 }
 
 int cgrb_combine(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,

@@ -63,6 +63,7 @@ class Injected:
 
 def make_units(n):
     u = np.zeros(n, dtype=UNIT_DTYPE)
+    u["ea_scale"] = 1.0
     return u
 
 
@@ -125,7 +126,7 @@ class Batch(object):
 class Engine(object):
     """One engine per process and device."""
 
-    def __init__(self, device=None, seed=DEFAULT_SEED, interp_extrap="linear"):
+    def __init__(self, device=None, seed=DEFAULT_SEED, interp_extrap="linear", energy_sampler="envelope", squeeze=True):
         torch = _torch()
         self.lib = _capi.load()
         if not torch.cuda.is_available():
@@ -140,6 +141,9 @@ class Engine(object):
         self.sm_count, self.cc = info[0], (info[1], info[2])
         self.seed = int(seed)
         self.interp_extrap = interp_extrap
+        self.energy_sampler = energy_sampler
+        self.squeeze = bool(squeeze)
+        self.squeeze_ratio, self.squeeze_min_candidates, self.squeeze_max_nodes = 8, 2048, 1 << 16
         self._call_counter = 0
         self._dtab_cache = {}
         self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
@@ -256,6 +260,15 @@ class Engine(object):
         units["src_off"] = np.concatenate(([0], np.cumsum(units["src_cap"] + 1)[:-1]))
         units["bkg_off"] = np.concatenate(([0], np.cumsum(units["bkg_cap"] + 1)[:-1]))
         units["tot_off"] = np.concatenate(([0], np.cumsum(units["src_cap"] + units["bkg_cap"] + 2)[:-1]))
+        # squeeze table of the thinning acceptance probability: ~1 node per SQUEEZE_RATIO candidates,
+        # none for short units where building it would cost as much as it saves
+        tab_n = np.where(units["src_cap"] >= self.squeeze_min_candidates,
+                         np.clip(units["src_cap"] // self.squeeze_ratio, 64, self.squeeze_max_nodes), 0)
+        if not self.squeeze:
+            tab_n[:] = 0
+        units["tab_n"] = tab_n
+        units["tab_off"] = np.concatenate(([0], np.cumsum(tab_n)[:-1]))
+        b.n_tab_nodes = int(tab_n.sum())
         b.n_src_slots = int(np.sum(units["src_cap"] + 1))
         b.n_bkg_slots = int(np.sum(units["bkg_cap"] + 1))
         b.n_tot_slots = b.n_src_slots + b.n_bkg_slots
@@ -341,18 +354,36 @@ class Engine(object):
             t["cand_times"] = cand_t = self.empty(b.n_src_slots, torch.float64)
             t["cand_accept"] = cand_a = torch.zeros(max(b.n_src_slots, 1), dtype=torch.uint8, device=self.device)
         desc = self._rng_desc(rng, b, "thin")
+        thin_tab = None
+        if b.n_tab_nodes > 0:
+            # rebuilt on every call (it is part of the sampling work, ~1/8 of a lambda per candidate)
+            w4, dw4, _ = self._work(b, 4, 256)
+            t["thin_tab"] = thin_tab = self.empty(2 * b.n_tab_nodes, torch.float64)
+            _capi.check(self.lib.cgrb_thin_tables(b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units,
+                                                  dw4.data_ptr(), len(w4), thin_tab.data_ptr(), self.stream),
+                        "cgrb_thin_tables")
+            self.launches += 2
         _capi.check(
             self.lib.cgrb_sample_events(
                 b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), nw, dwb.data_ptr(),
                 self._extrap_code(b.interp_extrap), C.byref(desc), t["segsum"].data_ptr(),
                 t["segstart"].data_ptr(), t["segcount"].data_ptr(), t["stage"].data_ptr(),
                 t["times_src"].data_ptr(), cand_t.data_ptr() if want_candidates else None,
-                cand_a.data_ptr() if want_candidates else None, b.d_counts.data_ptr(), self.stream),
+                cand_a.data_ptr() if want_candidates else None,
+                thin_tab.data_ptr() if thin_tab is not None else None, b.d_counts.data_ptr(), self.stream),
             "cgrb_sample_events")
         self.launches += 4
 
-    def sample_energy(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, want_trials=False):
+    def sample_energy(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, want_trials=False, sampler=None):
+        """``sampler``: "literal" (the reference's rejection loop, trial for trial; always used under
+        injected uniforms) or "envelope" (same output distribution from a tight envelope, Philox
+        only; the default under Philox)."""
         torch = _torch()
+        sampler = sampler or self.energy_sampler
+        if isinstance(rng, Injected):
+            sampler = "literal"
+        if sampler not in ("literal", "envelope"):
+            raise ValueError("sampler must be 'literal' or 'envelope'")
         w, dw, _ = self._work(b, 3, ENERGY_CHUNK)
         t = b.t
         t["energy_src"] = self.empty(b.n_src_slots, torch.float64)
@@ -360,6 +391,18 @@ class Engine(object):
         if want_trials:
             t["trials"] = tr = torch.zeros(max(b.n_src_slots, 1), dtype=torch.int32, device=self.device)
         desc = self._rng_desc(rng, b, "energy")
+        if sampler == "envelope":
+            if "etab" not in t:
+                t["etab"] = self.empty(self.lib.cgrb_energy_workspace_bytes(b.n_units), torch.uint8)
+            _capi.check(
+                self.lib.cgrb_sample_energy_envelope(
+                    b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
+                    self._extrap_code(b.interp_extrap), C.byref(desc), int(max_trials), t["etab"].data_ptr(),
+                    t["times_src"].data_ptr(), t["energy_src"].data_ptr(),
+                    tr.data_ptr() if want_trials else None, b.d_counts.data_ptr(), self.stream),
+                "cgrb_sample_energy_envelope")
+            self.launches += 2
+            return
         _capi.check(
             self.lib.cgrb_sample_energy(
                 b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
@@ -434,11 +477,11 @@ class Engine(object):
             "cgrb_gbm_dead_time")
         self.launches += 2
 
-    def process(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, diagnostics=False):
+    def process(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, diagnostics=False, energy_sampler=None):
         """LightCurve.process() for every unit of the batch (lightcurve.py:167-200): source times,
         energies, channels; background times, channels; combine; dead time."""
         self.sample_events(b, rng, want_candidates=diagnostics)
-        self.sample_energy(b, rng, max_trials=max_trials, want_trials=diagnostics)
+        self.sample_energy(b, rng, max_trials=max_trials, want_trials=diagnostics, sampler=energy_sampler)
         self.digitize_batch(b, rng)
         self.sample_background(b, rng)
         self.combine(b)
@@ -514,6 +557,49 @@ class Engine(object):
         self.digitize_batch(b, rng or Philox(self.next_seed()))
         return b.t["pha_src"][:n].cpu().numpy().astype("f8")
 
+    def sample_background_times(self, tstart, tstop, rate):
+        """Background.sample_times: homogeneous Poisson arrival times, tstart prepended."""
+        u = make_units(1)
+        u["bkg_tstart"], u["bkg_tstop"], u["bkg_rate"] = tstart, tstop, rate
+        u["flags"] = _capi.UNIT_NO_SOURCE
+        b = self.new_batch(u, self._uniform_table(), compute_fmax=False)
+        self.sample_background(b, Philox(self.next_seed()))
+        self.fetch_counts(b)
+        self.check_status(b)
+        return b.view("times_bkg", 0, "bkg")
+
+    def _uniform_table(self):
+        if getattr(self, "_utab", None) is None:
+            t = np.zeros(_capi.DT_SIZE)
+            t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + _capi.NCHAN] = np.arange(1, _capi.NCHAN + 1) / _capi.NCHAN
+            self._utab = [t]
+        return self._utab
+
+    def sample_background_channels(self, weights, n, rng=None):
+        """BackgroundSpectrumTemplate.sample_channel(size=n): int64 channel indices."""
+        torch = _torch()
+        w = np.asarray(weights)
+        if len(w) != _capi.NCHAN:
+            raise ValueError(f"the engine is compiled for {_capi.NCHAN} channels")
+        t = np.zeros(_capi.DT_SIZE)
+        cdf = w.astype("f8").cumsum()
+        cdf /= cdf[-1]
+        t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + _capi.NCHAN] = cdf
+        dtab = self.to_device(t)
+        out = self.empty(n, torch.uint8)
+        rng = rng or Philox(self.next_seed())
+        d = RngDesc()
+        keep = None
+        if isinstance(rng, Philox):
+            d.mode, d.seed = 0, rng.seed & 0xFFFFFFFFFFFFFFFF
+        else:
+            keep = self.to_device(np.asarray(rng.bkg_chan[0], dtype="f8"))
+            d.mode, d.d_u = 1, keep.data_ptr()
+        _capi.check(self.lib.cgrb_background_channels(dtab.data_ptr(), 0, 0, C.byref(d), int(n), out.data_ptr(),
+                                                      self.stream), "cgrb_background_channels")
+        self.launches += 1
+        return out[:n].cpu().numpy().astype(np.int64)
+
     def gbm_dead_time(self, times, pha):
         """_gbm_dead_time for one time-sorted event list; returns the boolean selection."""
         torch = _torch()
@@ -547,7 +633,8 @@ def get_engine(**kw):
             from .config import cosmogrb_config
 
             opts = dict(seed=cosmogrb_config["engine"]["seed"],
-                        interp_extrap=cosmogrb_config["engine"]["interp_extrap"])
+                        interp_extrap=cosmogrb_config["engine"]["interp_extrap"],
+                        energy_sampler=cosmogrb_config["engine"]["energy_sampler"])
             opts.update(kw)
             _engine = Engine(**opts)
         return _engine

@@ -1,0 +1,32 @@
+"""``GBMLightCurve`` (cosmogrb/instruments/gbm/gbm_lightcurve.py:11-115): a LightCurve whose merged
+event list goes through the GBM dead-time filter (literal reference semantics, on the GPU)."""
+import numpy as np
+
+from ...engine import get_engine
+from ...lightcurve.lightcurve import LightCurve
+
+
+class GBMLightCurve(LightCurve):
+    _deadtime = True
+
+    def __init__(self, source, background, response, name, grb_name, tstart, tstop):
+        super(GBMLightCurve, self).__init__(source=source, background=background, response=response, name=name,
+                                            grb_name=grb_name, tstart=tstart, tstop=tstop, instrument="GBM")
+        self._extra_info["angle"] = self._response.separation_angle          # gbm_lightcurve.py:40
+
+    def _filter_deadtime(self):
+        """stand-alone filter on ``self._times`` / ``self._pha`` (gbm_lightcurve.py:42-56)."""
+        sel = get_engine().gbm_dead_time(self._times, self._pha)
+        self._times = np.asarray(self._times)[sel]
+        self._pha = np.asarray(self._pha)[sel]
+
+    def write_tte(self):
+        raise NotImplementedError("TTE FITS output is outside the photon-event hot path (SURVEY.md §8 f3)")
+
+
+def gbm_dead_time(time, pha):
+    """``_gbm_dead_time`` (gbm_lightcurve.py:80-115) on the GPU: returns (filtered_time, filtered_pha,
+    selection) with the reference's conventions (zeros where an event is dropped)."""
+    time, pha = np.asarray(time, dtype="f8"), np.asarray(pha, dtype="f8")
+    sel = get_engine().gbm_dead_time(time, pha)
+    return np.where(sel, time, 0.0), np.where(sel, pha, 0.0), sel.astype("f8")

@@ -1,0 +1,212 @@
+"""GBM population runs (cosmogrb/instruments/gbm/gbm_universe.py:7-175).
+
+``GBM_CPL_Universe`` maps the population columns to GRB keyword arguments exactly like the
+reference (:19-29: ep -> ep_start, fluxes.latent -> peak_flux, tau -> ep_tau) and simulates the
+bursts in batches of (GRB x 14 detector) units.  The 14 detector tables are shared by all bursts
+(synthetic DRM = base matrix x viewing-angle factor, carried per unit in ``ea_scale``).
+"""
+import numpy as np
+
+from ... import _capi
+from ...engine import Philox, get_engine, make_units
+from ...io.grb_save import write_grb_file
+from ...lightcurve.light_curve_storage import LightCurveStorage
+from ...universe.universe import GRBWrapper, ParameterServer, Universe, dist_info, gather_event_counts, shard_by_cost
+from .gbm_background import gbm_background_template
+from .gbm_grb import GBMGRB, GBMGRB_CPL, GBMGRB_CPL_Constant
+from .synthetic_response import GBM_DETECTORS, angle_factor, base_response, separation_angles
+
+N_DET = len(GBM_DETECTORS)
+BYTES_PER_SLOT = 8 + 8 + 8 + 1 + 8 + 1 + 8 + 1 + 1      # stage/times/energy/pha + merged + filtered + flags
+
+
+class _GBMBatchedUniverse(Universe):
+    """Shared batched dispatch of the two GBM universes."""
+
+    _kind = 0
+
+    def _unit_columns(self, idx):
+        raise NotImplementedError()
+
+    def base_tables(self, interp_extrap):
+        return [base_response(d).device_table(gbm_background_template(d).weights, interp_extrap)
+                for d in GBM_DETECTORS]
+
+    def build_units(self, idx, rate_seed=0):
+        """Unit records of the GRBs ``idx`` (14 per GRB, GRB-major)."""
+        idx = np.asarray(idx, dtype=np.int64)
+        n = len(idx)
+        u = make_units(n * N_DET)
+        cols = self._unit_columns(idx)
+        for k, v in cols.items():
+            u[k] = np.repeat(np.asarray(v, dtype="f8"), N_DET)
+        u["kind"] = self._kind
+        u["z"] = np.repeat(self._z[idx], N_DET)
+        u["det"] = np.tile(np.arange(N_DET), n)
+        u["stream_id"] = (np.repeat(idx, N_DET) * 16 + np.tile(np.arange(N_DET), n)).astype(np.uint32)
+        u["src_tstart"] = 0.0
+        u["src_tstop"] = np.repeat(self._duration[idx], N_DET)
+        u["bkg_tstart"], u["bkg_tstop"] = GBMGRB._background_start, GBMGRB._background_stop
+        # Background._background_rate ~ N(500, 10) per detector (background.py:125, gbm_grb.py:120),
+        # drawn from a generator keyed by the GRB index so that sharding does not change it
+        rates = np.empty((n, N_DET))
+        for j, g in enumerate(idx):
+            rates[j] = np.random.default_rng([rate_seed, int(g)]).normal(500.0, 10.0, N_DET)
+        u["bkg_rate"] = rates.reshape(-1)
+        ang = separation_angles(self._ra[idx], self._dec[idx])              # [n, 14]
+        fac = np.stack([angle_factor(d, ang[:, j]) for j, d in enumerate(GBM_DETECTORS)], axis=1)
+        u["ea_scale"] = fac.reshape(-1)
+        return u, ang
+
+    def cost_estimate(self):
+        """relative cost of each GRB for the LPT deal: background events + a flux-weighted source term"""
+        pf = np.asarray(self._local_parameters["peak_flux"])
+        return 2e5 * N_DET + 2e10 * pf * self._duration
+
+    def _run_batched(self, grbs_per_batch=None, save=True, seed=None, memory_budget=48e9):
+        eng = get_engine()
+        rank, world = dist_info()
+        mine = shard_by_cost(self.cost_estimate(), world)[rank]
+        tabs = self.base_tables(eng.interp_extrap)
+        seed = eng.seed if seed is None else seed
+        local_counts = np.zeros((len(mine), N_DET, 3), dtype=np.int64)
+        pinned = {}
+        pos = 0
+        self.n_batches = 0
+        while pos < len(mine):
+            # size the batch from the capacities (needs fmax): grow until the memory budget is hit
+            step = grbs_per_batch or 256
+            idx = mine[pos:pos + step]
+            units, ang = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
+            b = eng.new_batch(units, tabs, compute_fmax=True)
+            if grbs_per_batch is None:
+                per_grb = (b.n_tot_slots * BYTES_PER_SLOT) / max(len(idx), 1)
+                fit = max(1, int(memory_budget / max(per_grb, 1.0)))
+                if fit < len(idx):
+                    idx = idx[:fit]
+                    units, ang = units[:fit * N_DET], ang[:fit]
+                    b = eng.new_batch(units, tabs, compute_fmax=True)
+            eng.process(b, Philox(seed))
+            if save:
+                arrays = eng.to_host(b, pinned)
+                c = arrays["counts"]
+                self._save_chunk(idx, b, arrays, ang)
+            else:
+                c = eng.fetch_counts(b)
+                eng.check_status(b)
+            local_counts[pos:pos + len(idx), :, 0] = c["n_src"].reshape(-1, N_DET)
+            local_counts[pos:pos + len(idx), :, 1] = c["n_bkg"].reshape(-1, N_DET)
+            local_counts[pos:pos + len(idx), :, 2] = c["n_kept"].reshape(-1, N_DET)
+            pos += len(idx)
+            self.n_batches += 1
+        # the one exchange of the population run: per-unit event counts of every rank
+        gathered = gather_event_counts(local_counts.reshape(-1, 3))
+        shards = shard_by_cost(self.cost_estimate(), world)
+        full = np.zeros((self._n_grbs, N_DET, 3), dtype=np.int64)
+        for r in range(world):
+            full[shards[r]] = gathered[r].reshape(-1, N_DET, 3)
+        self.event_counts = full
+        self.local_grbs = mine
+
+    def _save_chunk(self, idx, b, arrays, ang):
+        def sl(name, i):
+            o = arrays[name + "_offsets"]
+            return arrays[name][int(o[i]):int(o[i + 1])].numpy().copy()
+
+        for j, g in enumerate(idx):
+            ps = self._parameter_servers[int(g)]
+            storages, responses = [], []
+            for d, det in enumerate(GBM_DETECTORS):
+                i = j * N_DET + d
+                rsp = base_response(det)
+                storages.append(LightCurveStorage(
+                    name=det, tstart=GBMGRB._background_start, tstop=GBMGRB._background_stop, time_adjustment=0.0,
+                    pha=sl("pha_out", i), times=sl("times_out", i), pha_source=sl("pha_src", i).astype("f8"),
+                    times_source=sl("times_src", i), pha_background=sl("pha_bkg", i).astype(np.int64),
+                    times_background=sl("times_bkg", i), channels=rsp.channels, ebounds=rsp.channel_edges, T0=0.0,
+                    instrument="GBM", extra_info={"angle": float(np.rad2deg(ang[j, d])),
+                                                  "ea_scale": float(b.units["ea_scale"][i])}))
+                responses.append(rsp)
+            p = dict(ps.parameters)
+            source_params = {k: p[k] for k in p if k not in ("name", "ra", "dec", "z", "duration", "T0")}
+            write_grb_file(ps.file_path, name=p["name"], T0=p["T0"], z=p["z"], duration=p["duration"], ra=p["ra"],
+                           dec=p["dec"], source_params=source_params, extra_info={}, storages=storages,
+                           responses=responses)
+
+
+class GBM_CPL_Universe(_GBMBatchedUniverse):
+    _kind = 0
+
+    def __init__(self, population, save_path="."):
+        super(GBM_CPL_Universe, self).__init__(population, save_path=save_path)
+
+    def _grb_wrapper(self, parameter_server, serial=False):
+        return GBM_CPL_Wrapper(parameter_server, serial=serial)
+
+    def _process_populations(self):
+        super(GBM_CPL_Universe, self)._process_populations()
+        self._local_parameters["ep_start"] = self._population.ep             # gbm_universe.py:24-29
+        self._local_parameters["alpha"] = self._population.alpha
+        self._local_parameters["peak_flux"] = self._population.fluxes.latent
+        self._local_parameters["trise"] = self._population.trise
+        self._local_parameters["tdecay"] = self._population.tdecay
+        self._local_parameters["ep_tau"] = self._population.tau
+
+    def _unit_columns(self, idx):
+        lp = self._local_parameters
+        return {k: np.asarray(lp[k])[idx] for k in ("ep_start", "alpha", "peak_flux", "trise", "tdecay", "ep_tau")}
+
+    def _parameter_server_type(self, **kwargs):
+        return GBM_CPL_ParameterServer(**kwargs)
+
+
+class GBM_CPL_Wrapper(GRBWrapper):
+    def _grb_type(self, **kwargs):
+        return GBMGRB_CPL(**kwargs)
+
+
+class GBM_CPL_ParameterServer(ParameterServer):
+    def __init__(self, name, ra, dec, z, duration, T0, peak_flux, alpha, ep_start, ep_tau, trise, tdecay):
+        super(GBM_CPL_ParameterServer, self).__init__(
+            name=name, ra=ra, dec=dec, z=z, duration=duration, T0=T0, peak_flux=peak_flux, alpha=alpha,
+            ep_start=ep_start, ep_tau=ep_tau, trise=trise, tdecay=tdecay)
+
+
+class GBM_CPL_Constant_Universe(_GBMBatchedUniverse):
+    _kind = 1
+
+    def __init__(self, population, save_path="."):
+        super(GBM_CPL_Constant_Universe, self).__init__(population, save_path=save_path)
+
+    def _grb_wrapper(self, parameter_server, serial=False):
+        return GBM_CPL_Constant_Wrapper(parameter_server, serial=serial)
+
+    def _process_populations(self):
+        super(GBM_CPL_Constant_Universe, self)._process_populations()
+        self._local_parameters["ep"] = self._population.ep
+        self._local_parameters["alpha"] = self._population.alpha
+        self._local_parameters["peak_flux"] = self._population.fluxes.latent
+
+    def _unit_columns(self, idx):
+        lp = self._local_parameters
+        n = len(idx)
+        return dict(ep_start=np.asarray(lp["ep"])[idx], alpha=np.asarray(lp["alpha"])[idx],
+                    peak_flux=np.asarray(lp["peak_flux"])[idx], trise=np.ones(n), tdecay=np.ones(n), ep_tau=np.ones(n))
+
+    def _parameter_server_type(self, **kwargs):
+        return GBM_CPL_Constant_ParameterServer(**kwargs)
+
+
+class GBM_CPL_Constant_Wrapper(GRBWrapper):
+    def _grb_type(self, **kwargs):
+        return GBMGRB_CPL_Constant(**kwargs)
+
+
+class GBM_CPL_Constant_ParameterServer(ParameterServer):
+    def __init__(self, name, ra, dec, z, duration, T0, peak_flux, alpha, ep):
+        super(GBM_CPL_Constant_ParameterServer, self).__init__(
+            name=name, ra=ra, dec=dec, z=z, duration=duration, T0=T0, peak_flux=peak_flux, alpha=alpha, ep=ep)
+
+
+__all__ = ["GBM_CPL_Universe", "GBM_CPL_Constant_Universe", "GBM_CPL_Wrapper", "GBM_CPL_Constant_Wrapper",
+           "GBM_CPL_ParameterServer", "GBM_CPL_Constant_ParameterServer"]

@@ -60,8 +60,26 @@ def separation_angle(det, ra, dec):
     return float(np.arccos(np.clip(np.dot(src, bore), -1.0, 1.0)))
 
 
-def synthetic_matrix(det, angle, n_zero_rows=2):
-    """-> (matrix[140,128] cm^2, energy_edges[141], channel_edges[129])."""
+def angle_factor(det, angle):
+    """Viewing-angle factor of the synthetic effective area (vectorised over ``angle`` [rad])."""
+    angle = np.asarray(angle, dtype="f8")
+    if det[0] == "b":
+        return np.maximum(np.abs(np.sin(angle)), 0.3)
+    return np.maximum(np.abs(np.cos(angle)), 0.05)
+
+
+def separation_angles(ra, dec):
+    """[n, 14] separation angles [rad] of n sky positions from the 14 boresights."""
+    ra, dec = np.deg2rad(np.atleast_1d(ra)), np.deg2rad(np.atleast_1d(dec))
+    zen = 0.5 * np.pi - dec
+    src = np.stack([np.sin(zen) * np.cos(ra), np.sin(zen) * np.sin(ra), np.cos(zen)], axis=1)
+    bore = np.stack([_unit_vector(*_BORESIGHT[d]) for d in GBM_DETECTORS], axis=0)
+    return np.arccos(np.clip(src @ bore.T, -1.0, 1.0))
+
+
+def synthetic_matrix(det, angle, n_zero_rows=2, factor=None):
+    """-> (matrix[140,128] cm^2, energy_edges[141], channel_edges[129]).  ``factor`` overrides the
+    viewing-angle factor (1.0 = the base, face-on matrix shared by population runs)."""
     tabs = gbm_tables()
     di = GBM_DETECTORS.index(det)
     cedges = np.asarray(tabs["channel_edges"][di], dtype="f8")
@@ -92,11 +110,24 @@ def synthetic_matrix(det, angle, n_zero_rows=2):
     shape = shape * (1.0 + 0.02 * rng.standard_normal(shape.shape)).clip(0.9, 1.1)
     rs = shape.sum(axis=1, keepdims=True)
     shape = np.where(rs > 0, shape / np.maximum(rs, 1e-300), 0.0)
-    cosfac = max(abs(np.cos(angle)), 0.05) if not bgo else max(abs(np.sin(angle)), 0.3)
+    cosfac = float(angle_factor(det, angle)) if factor is None else float(factor)
     ea = a0 * np.exp(-0.5 * ((np.log10(emean) - centre) / 0.8) ** 2) * cosfac
     matrix = shape * ea[:, None]
     matrix[:n_zero_rows, :] = 0.0
     return matrix, eedges, cedges
+
+
+_base = {}
+
+
+def base_response(det):
+    """Face-on (viewing-angle factor 1) response of a detector: the shared table of population runs,
+    where the per-GRB factor travels in ``cgrb_unit_t.ea_scale``."""
+    if det not in _base:
+        matrix, eedges, cedges = synthetic_matrix(det, 0.0, factor=1.0)
+        _base[det] = Response(matrix=matrix, geometric_area=np.pi * 6.35 ** 2, energy_edges=eedges,
+                              channel_edges=cedges)
+    return _base[det]
 
 
 class SyntheticGBMResponse(Response):
@@ -155,4 +186,4 @@ class BGOResponse(SyntheticGBMResponse):
 
 
 __all__ = ["GBM_DETECTORS", "gbm_tables", "synthetic_matrix", "NaIResponse", "BGOResponse",
-           "SyntheticGBMResponse", "separation_angle"]
+           "SyntheticGBMResponse", "separation_angle", "separation_angles", "angle_factor", "base_response"]

@@ -1,0 +1,204 @@
+"""``Universe``: a population of GRBs (cosmogrb/universe/universe.py:14-271).
+
+The reference maps one dask task per GRB (``GRBWrapper``: construct, ``go``, ``save``).  Here the
+population is cut into chunks of GRBs; every chunk is ONE batch of (GRB x detector) units on the
+GPU.  With ``torch.distributed`` initialised (one process per GPU) the GRBs are dealt round-robin in
+cost order over the ranks -- units never exchange data -- and the only collective is a small
+all_gather of per-unit event counts (-> global event offsets), see ``gather_event_counts``.
+"""
+import abc
+from pathlib import Path
+
+import numpy as np
+
+from ..utils.logging import setup_logger
+from .population import Population
+
+logger = setup_logger(__name__)
+
+
+class ParameterServer(object):
+    def __init__(self, name, ra, dec, z, duration, T0, **kwargs):
+        self._parameters = dict(name=name, ra=ra, dec=dec, z=z, duration=duration, T0=T0)
+        self._parameters.update(kwargs)
+        self._file_path = None
+
+    @property
+    def parameters(self):
+        return self._parameters
+
+    def set_file_path(self, file_path):
+        self._file_path = file_path
+
+    @property
+    def file_path(self):
+        return self._file_path
+
+    def __repr__(self):
+        return "\n".join(f"{k}: {v}" for k, v in self._parameters.items())
+
+
+class GRBWrapper(object, metaclass=abc.ABCMeta):
+    """construct -> go -> save for ONE burst (universe.py:245-271); the batched path of
+    ``Universe.go`` does the same for many bursts per launch."""
+
+    def __init__(self, parameter_server, serial=False):
+        grb = self._grb_type(**parameter_server.parameters)
+        grb.go(client=None, serial=serial)
+        grb.save(parameter_server.file_path, clean_up=True)
+        del grb
+
+    @abc.abstractmethod
+    def _grb_type(self, **kwargs):
+        raise NotImplementedError()
+
+
+def dist_info():
+    """(rank, world_size) of torch.distributed if initialised, else (0, 1)."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def shard_by_cost(cost, world):
+    """Longest-processing-time-first deal of work items over ``world`` ranks: returns a list of index
+    arrays, one per rank (each in ascending index order).  Deterministic."""
+    cost = np.asarray(cost, dtype="f8")
+    order = np.argsort(-cost, kind="stable")
+    load = np.zeros(world)
+    owner = np.empty(len(cost), dtype=np.int64)
+    if world == 1:
+        owner[:] = 0
+    else:
+        for i in order:
+            r = int(np.argmin(load))
+            owner[i] = r
+            load[r] += cost[i]
+    return [np.nonzero(owner == r)[0] for r in range(world)]
+
+
+def gather_event_counts(local_counts, device=None):
+    """The population run's only exchange: all_gather of int64 [n_local, 3] (n_source, n_background,
+    n_total_after_dead_time) -> list of per-rank arrays.  Ranks may hold different numbers of units."""
+    rank, world = dist_info()
+    local_counts = np.ascontiguousarray(local_counts, dtype=np.int64).reshape(-1, 3)
+    if world == 1:
+        return [local_counts]
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend()
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if backend == "nccl" else torch.device("cpu"))
+    n = torch.tensor([local_counts.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    nmax = int(max(int(x.item()) for x in ns))
+    pad = torch.zeros((nmax, 3), dtype=torch.int64, device=dev)
+    pad[:local_counts.shape[0]] = torch.from_numpy(local_counts).to(dev)
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return [o[:int(k.item())].cpu().numpy() for o, k in zip(out, ns)]
+
+
+class Universe(object, metaclass=abc.ABCMeta):
+    """Generate a Universe of GRBs from a population file."""
+
+    def __init__(self, population_file, grb_base_name="SynthGRB", save_path="."):
+        if isinstance(population_file, Population):
+            self._population_file = None
+            self._population = population_file
+        else:
+            self._population_file = Path(population_file).absolute()
+            self._population = Population.from_file(population_file).to_sub_population()
+        self._is_processed = False
+        self._grb_base_name = grb_base_name
+        self._save_path = Path(save_path) if save_path is not None else None
+        assert sum(self._population.selection) == len(self._population.selection), \
+            "The population seems to have had a prior selection on it. This is not good"
+        self._n_grbs = len(self._population.selection)
+        self._name = [f"{self._grb_base_name}_{i}" for i in range(self._n_grbs)]
+        self._local_parameters = {}
+        self._parameter_servers = []
+        self._process_populations()
+        self._contstruct_parameter_servers()
+        self.event_counts = None        # [n_grbs, n_det, 3] after go()
+
+    @property
+    def n_grbs(self):
+        return self._n_grbs
+
+    @property
+    def parameter_servers(self):
+        return self._parameter_servers
+
+    def _get_sky_coord(self):
+        self._ra = self._population.ra
+        self._dec = self._population.dec
+
+    def _get_redshift(self):
+        self._z = self._population.distances
+
+    def _get_duration(self):
+        try:
+            self._duration = self._population.duration
+        except Exception:
+            raise RuntimeError("The population must contain a duration value")
+
+    def _process_populations(self):
+        self._get_sky_coord()
+        self._get_redshift()
+        self._get_duration()
+
+    def _contstruct_parameter_servers(self):          # (sic) the reference's spelling
+        for i in range(self._n_grbs):
+            param_dict = dict(z=self._z[i], ra=self._ra[i], dec=self._dec[i], name=self._name[i],
+                              duration=self._duration[i], T0=0.0)
+            for k, v in self._local_parameters.items():
+                param_dict[k] = v[i]
+            ps = self._parameter_server_type(**param_dict)
+            if self._save_path is not None:
+                ps.set_file_path(self._save_path / f"{self._name[i]}_store.h5")
+            self._parameter_servers.append(ps)
+
+    # -- dispatch ---------------------------------------------------------------------------------
+    def go(self, client=None, grbs_per_batch=None, save=True, seed=None):
+        """Simulate the whole population (universe.py:123-149).  ``client`` is accepted for signature
+        compatibility (the dask map is replaced by batched GPU launches + rank sharding)."""
+        self._run_batched(grbs_per_batch=grbs_per_batch, save=save and self._save_path is not None, seed=seed)
+        self._is_processed = True
+
+    @abc.abstractmethod
+    def _run_batched(self, grbs_per_batch=None, save=True, seed=None):
+        raise NotImplementedError()
+
+    def save(self, file_name):
+        """Index of the run: the GRB files and the population file (the reference writes a ``Survey``,
+        universe.py:151-179; survey bookkeeping itself is outside the hot path)."""
+        if not self._is_processed:
+            return
+        from ..io import store
+
+        t = store.Tree()
+        t.attrs("/").update(n_grbs=self._n_grbs, population_file=str(self._population_file),
+                            grb_base_name=self._grb_base_name)
+        if self._save_path is not None:
+            files = [str((self._save_path / f"{self._grb_base_name}_{i}_store.h5").absolute())
+                     for i in range(self._n_grbs)]
+            t.dataset("grb_save_files", np.array(files))
+        if self.event_counts is not None:
+            t.dataset("event_counts", np.asarray(self.event_counts))
+        t.write(file_name)
+
+    @abc.abstractmethod
+    def _grb_wrapper(self, parameter_server, serial=False):
+        raise NotImplementedError()
+
+    @abc.abstractmethod
+    def _parameter_server_type(self, **kwargs):
+        raise NotImplementedError()

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CGRB_ABI_VERSION 1
+#define CGRB_ABI_VERSION 2
 
 /* error codes */
 #define CGRB_OK 0
@@ -72,7 +72,7 @@ extern "C" {
 #define CGRB_DT_CUM 1720       /* [140*128] row-normalised cumulative matrix (16-byte aligned: 13760 B) */
 #define CGRB_DT_SIZE (1720 + 140 * 128) /* 19640 doubles = 157120 B per detector                     */
 
-/* one (GRB, detector) work unit; 192 bytes, device array uploaded by the caller */
+/* one (GRB, detector) work unit; 208 bytes, device array uploaded by the caller */
 typedef struct {
     int32_t kind;          /* 0 = CPLSourceFunction (cpl_functions.py), 1 = ConstantCPL (cpl_constant_functions.py) */
     int32_t det;           /* detector table index into d_dtab                                     */
@@ -99,7 +99,10 @@ typedef struct {
     int64_t src_off;       /* offset of this unit in the per-source-event arrays                   */
     int64_t bkg_off;       /* offset of this unit in the per-background-event arrays               */
     int64_t tot_off;       /* offset of this unit in the merged / filtered arrays                  */
-    int64_t reserved;
+    int64_t tab_off;       /* offset (in nodes) of this unit in the thinning squeeze table           */
+    int64_t tab_n;         /* nodes of the squeeze table on [src_tstart, src_tstop]; 0 = no squeeze  */
+    double ea_scale;       /* multiplies the detector table's effective area (per-GRB viewing-angle
+                              factor on a shared base DRM); 1.0 = use the table as is              */
 } cgrb_unit_t;
 
 #define CGRB_UNIT_NO_SOURCE 1u
@@ -113,6 +116,7 @@ typedef struct {
     int64_t n_total;       /* merged events entering dead time                                     */
     int64_t n_kept;        /* events surviving dead time                                           */
     int64_t n_trials;      /* energy rejection trials                                              */
+    int64_t n_exact;       /* thinning candidates that needed the exact lambda(t) (all, without squeeze) */
     uint32_t status;       /* CGRB_ST_* bits                                                       */
     uint32_t pad;
 } cgrb_counts_t;
@@ -151,7 +155,7 @@ long long cgrb_launch_count(void);
 /* host helper: split [0, cap_u) of each unit into chunks of `chunk` indices.
  * h_work may be NULL to query the count.  cap_u = h_units[i].src_cap (which=0, thinning
  * candidates), bkg_cap (which=1), src_cap+bkg_cap+2 (which=2, merged events) or src_cap+1
- * (which=3, source events).  Every unit owns at least one entry.  Returns the number of entries. */
+ * (which=3, source events) or tab_n (which=4, squeeze-table nodes).  Every unit owns at least one entry.  Returns the number of entries. */
 int64_t cgrb_build_work(const cgrb_unit_t *h_units, int n_units, int which, int64_t chunk,
                         cgrb_work_t *h_work, int64_t work_cap);
 
@@ -175,19 +179,31 @@ int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int inter
 
 /* ---- samplers --------------------------------------------------------------------------- */
 
+/* Squeeze table for the thinning acceptance test (no reference counterpart; it changes no decision).
+ * For every unit with tab_n >= 4 nodes: p_k = lambda(t_k) / fmax on the uniform grid
+ * t_k = src_tstart + k (src_tstop - src_tstart) / (tab_n - 1), and a margin m_k bounding the error of
+ * linear interpolation on [t_k, t_k+1] (from second differences, x4 safety).  cgrb_sample_events
+ * accepts a candidate outright if u2 <= p_lin - m, rejects it if u2 > p_lin + m, and evaluates
+ * lambda(t) exactly (the reference's 75-point trapezoid) only in between, so the accept/reject
+ * decisions are those of the exact test.  d_thin_tab: 2 doubles per node (p, m), sum(tab_n) nodes.
+ * Work list: which=4, chunk=256. */
+int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                     const cgrb_work_t *d_work, int64_t n_work, double *d_thin_tab, void *stream);
+
 /* SourceFunction.sample_events (cpl_source.py:98-114; numba cpl_functions.py:134-188,
  * cpl_constant_functions.py:65-105).  Work list: which=0, chunk=CGRB_SEG.
  *   d_segsum/d_segstart [n_work] doubles, d_segcount [n_work] int32: workspace
  *   d_stage   [sum src_cap] doubles: workspace (accepted times per segment)
  *   d_times_src [sum (src_cap+1)]: output, unit u at src_off; entry 0 is tstart
  *   d_cand_times / d_cand_accept: optional (may be NULL) per-candidate outputs at src_off
+ *   d_thin_tab: squeeze table from cgrb_thin_tables, or NULL (every candidate evaluated exactly)
  * counts: n_candidates, n_src, status. */
 int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                        const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
                        int interp_extrap, const cgrb_rng_t *rng,
                        double *d_segsum, double *d_segstart, int32_t *d_segcount, double *d_stage,
                        double *d_times_src, double *d_cand_times, uint8_t *d_cand_accept,
-                       cgrb_counts_t *d_counts, void *stream);
+                       const double *d_thin_tab, cgrb_counts_t *d_counts, void *stream);
 
 /* SourceFunction.sample_energy (cpl_source.py:116-132; numba cpl_functions.py:191-286).
  * Work list: which=3 with any chunk size (photon index space, bounded by counts.n_src).
@@ -197,6 +213,18 @@ int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
                        const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
                        const cgrb_rng_t *rng, int64_t max_trials, const double *d_times_src,
                        double *d_energy_src, int32_t *d_trials, cgrb_counts_t *d_counts, void *stream);
+
+/* Same contract and the same output DISTRIBUTION as cgrb_sample_energy, Philox only: exact
+ * rejection sampling of the literal sampler's output density from a tight per-unit envelope
+ * (csrc/cgrb_energy.cuh) -- a few trials per photon instead of tens to hundreds.  d_workspace:
+ * cgrb_energy_workspace_bytes(n_units) bytes of device memory.  Injected uniforms replay the
+ * reference's stream and therefore must use cgrb_sample_energy (returns CGRB_E_UNSUPPORTED). */
+int64_t cgrb_energy_workspace_bytes(int n_units);
+int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                                const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
+                                const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace,
+                                const double *d_times_src, double *d_energy_src, int32_t *d_trials,
+                                cgrb_counts_t *d_counts, void *stream);
 
 /* Response.digitize (response.py:156-174; numba _digitize :10-25): nearest-CDF channel.
  * Work list as for cgrb_sample_energy. */
@@ -215,6 +243,11 @@ int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int
                            double *d_segsum, double *d_segstart,
                            double *d_times_bkg, uint8_t *d_pha_bkg, cgrb_counts_t *d_counts,
                            void *stream);
+
+/* BackgroundSpectrumTemplate.sample_channel(size=n) alone (background.py:80-93): n channel draws
+ * from detector table `det`'s background cdf.  Injected mode reads rng->d_u[0..n). */
+int cgrb_background_channels(const double *d_dtab, int det, uint32_t stream_id, const cgrb_rng_t *rng,
+                             int64_t n, uint8_t *d_out, void *stream);
 
 /* ---- combine + dead time ---------------------------------------------------------------- */
 

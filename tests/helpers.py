@@ -36,6 +36,7 @@ def bkg_weights(det="n0"):
 
 def unit(kind=0, det_index=0, stream_id=0, flags=0, bkg=(-100.0, 300.0, 500.0), **p):
     u = np.zeros(1, dtype=_capi.UNIT_DTYPE)
+    u["ea_scale"] = 1.0
     u["kind"], u["det"], u["stream_id"], u["flags"] = kind, det_index, stream_id, flags
     u["peak_flux"], u["alpha"], u["z"] = p["peak_flux"], p["alpha"], p["z"]
     u["ep_start"] = p.get("ep", p.get("ep_start"))

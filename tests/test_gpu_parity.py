@@ -221,3 +221,25 @@ def test_multi_unit_batch_independent_of_batching(engine):
             assert ci[k][0] == c[k][i], k
         assert np.array_equal(bi.view("times_out", 0, "kept"), b.view("times_out", i, "kept"))
         assert np.array_equal(bi.view("pha_out", 0, "kept"), b.view("pha_out", i, "kept"))
+
+
+@pytest.mark.parametrize("params", [h.README_DEMO, h.BRIGHT_LONG])
+def test_squeeze_changes_no_decision(params):
+    """Full-size property test: the squeeze table only short-cuts the acceptance test; the accepted
+    set with and without it is identical (BRIGHT_LONG: ~2e7 candidates per detector)."""
+    from cosmogrb_b200.engine import Engine
+
+    out = {}
+    for squeeze in (True, False):
+        eng = Engine(squeeze=squeeze)
+        rsp = h.response("n0")
+        b = eng.new_batch(h.unit(**params), [rsp.device_table(h.bkg_weights("n0"), "linear")])
+        assert (b.units["tab_n"][0] > 0) == squeeze
+        eng.sample_events(b, Philox(31337))
+        c = eng.fetch_counts(b)
+        assert c["status"][0] == 0
+        out[squeeze] = (int(c["n_candidates"][0]), int(c["n_exact"][0]), b.view("times_src", 0, "src"))
+    assert out[True][0] == out[False][0]
+    assert out[False][1] == out[False][0]                 # without the table every candidate is exact
+    assert out[True][1] < 0.05 * out[True][0], f"squeeze left {out[True][1]} of {out[True][0]} exact"
+    assert np.array_equal(out[True][2], out[False][2])

@@ -1,0 +1,150 @@
+"""GPU, native Philox: distributions against the CPU oracle's MT19937 path (the reference's numba
+path restated) with KS / chi-square agreement at p > 0.01 (BASELINE.json north_star), and the
+envelope energy sampler against the literal one."""
+import numpy as np
+import pytest
+
+from tests import helpers as h
+from oracle import oracle as orc
+from cosmogrb_b200 import _capi
+from cosmogrb_b200.engine import Philox
+
+pytestmark = pytest.mark.gpu
+stats = pytest.importorskip("scipy.stats")
+
+P_MIN = 0.01
+
+
+def _energies(engine, params, times, sampler, seed, kind=0, extrap="linear", det="n0"):
+    rsp = h.response(det)
+    u = h.unit(kind=kind, **params)
+    u["src_cap"] = len(times) + 8
+    b = engine.new_batch(u, [rsp.device_table(h.bkg_weights(det), extrap)], interp_extrap=extrap)
+    engine.set_counts(b, n_src=len(times))
+    ts = np.zeros(b.n_src_slots)
+    ts[:len(times)] = times
+    b.t["times_src"] = engine.to_device(ts)
+    engine.sample_energy(b, Philox(seed), want_trials=True, sampler=sampler)
+    c = engine.fetch_counts(b)
+    assert c["status"][0] == 0
+    n = len(times)
+    return b.t["energy_src"][:n].cpu().numpy(), b.t["trials"][:n].cpu().numpy()
+
+
+@pytest.mark.parametrize("params,tgrid", [(h.CONFTEST_BRIGHT, (0.05, 0.3, 1.0, 1.9)),
+                                          (h.BRIGHT_LONG, (2.0, 20.0, 100.0, 290.0)),
+                                          (h.README_DEMO, (0.5, 5.0, 40.0))])
+@pytest.mark.parametrize("extrap", ["linear", "clamp"])
+def test_envelope_sampler_matches_literal(engine, params, tgrid, extrap):
+    """Same output distribution, photon time by photon time (two-sample KS), far fewer trials."""
+    n = 20000
+    for k, t0 in enumerate(tgrid):
+        times = np.full(n, t0)
+        e_lit, tr_lit = _energies(engine, params, times, "literal", 100 + k, extrap=extrap)
+        e_env, tr_env = _energies(engine, params, times, "envelope", 200 + k, extrap=extrap)
+        rsp = h.response("n0")
+        assert np.all((e_env >= rsp.emin * (1 - 1e-12)) & (e_env <= rsp.emax * (1 + 1e-12)))
+        p = stats.ks_2samp(e_lit, e_env).pvalue
+        assert p > P_MIN, f"t={t0}: KS p={p}"
+        assert tr_env.mean() < 12.0, f"t={t0}: envelope sampler needs {tr_env.mean():.1f} trials/photon"
+        assert tr_env.mean() < tr_lit.mean()
+
+
+def test_envelope_sampler_constant_cpl(engine):
+    params = dict(z=1.0, peak_flux=5e-9, alpha=-0.66, ep=500.0, duration=2.0)
+    times = np.linspace(0.0, 2.0, 20000)
+    e_lit, _ = _energies(engine, params, times, "literal", 1, kind=1)
+    e_env, tr = _energies(engine, params, times, "envelope", 2, kind=1)
+    assert stats.ks_2samp(e_lit, e_env).pvalue > P_MIN
+    assert tr.mean() < 12.0
+
+
+@pytest.mark.parametrize("alpha", [-1.4, -1.0001, -0.3])
+def test_envelope_sampler_alpha_range(engine, alpha):
+    params = dict(h.CONFTEST_BRIGHT, alpha=alpha)
+    times = np.full(20000, 0.5)
+    e_lit, _ = _energies(engine, params, times, "literal", 5)
+    e_env, _ = _energies(engine, params, times, "envelope", 6)
+    assert stats.ks_2samp(e_lit, e_env).pvalue > P_MIN
+
+
+def test_spurious_tstart_event_is_the_literal_first_trial(engine):
+    """t = 0: pulse amplitude 0 -> the reference accepts the first power-law proposal; both samplers
+    must return exactly the same energy for the same Philox counters."""
+    times = np.zeros(64)
+    e_lit, tr_lit = _energies(engine, h.CONFTEST_BRIGHT, times, "literal", 9)
+    e_env, tr_env = _energies(engine, h.CONFTEST_BRIGHT, times, "envelope", 9)
+    assert np.all(tr_lit == 1) and np.all(tr_env == 1)
+    assert np.array_equal(e_lit, e_env)
+
+
+def test_energies_against_oracle_mt_path(engine):
+    """GPU Philox (both samplers) vs the oracle's MT19937 replay of the reference's rejection loop."""
+    params = h.CONFTEST_BRIGHT
+    rsp = h.response("n0")
+    s = h.oracle_source(rsp, **params)
+    for t0, seed in ((0.2, 1), (1.5, 2)):
+        times = np.full(6000, t0)
+        want, _ = orc.sample_energy(s, rsp.effective_area_packed, times, orc.Rng(seed=seed))
+        for sampler in ("literal", "envelope"):
+            got, _ = _energies(engine, params, np.full(20000, t0), sampler, 77 + seed)
+            p = stats.ks_2samp(want, got).pvalue
+            assert p > P_MIN, f"{sampler} t={t0}: KS p={p}"
+
+
+def test_light_curve_and_count_spectrum_against_oracle(engine):
+    """Whole detector under Philox vs the oracle's MT path: binned light curve (chi-square on the
+    source counts per time bin), count spectrum (chi-square on PHA channels), background times (KS
+    against uniform) and background channels (chi-square against the template)."""
+    params = h.CONFTEST_BRIGHT
+    rsp = h.response("n0")
+    s = h.oracle_source(rsp, **params)
+    ea = rsp.effective_area_packed
+    fmax = orc.fmax(s, ea, 0.0, params["duration"])
+    # oracle: a few independent realisations pooled
+    t_all, p_all = [], []
+    for seed in range(6):
+        rng = orc.Rng(seed=1000 + seed)
+        ts, _ = orc.sample_events(s, ea, 0.0, params["duration"], fmax, rng)
+        es, _ = orc.sample_energy(s, ea, ts[1:], rng)
+        ps = orc.digitize(es, rsp.energy_edges, rsp.cumulative_matrix, rng)
+        t_all.append(ts[1:])
+        p_all.append(ps)
+    t_ref, p_ref = np.concatenate(t_all), np.concatenate(p_all)
+    # engine: 14 realisations of the same detector in one batch
+    tabs = [rsp.device_table(h.bkg_weights("n0"), "linear")]
+    units = np.concatenate([h.unit(det_index=0, stream_id=100 + i, **params) for i in range(14)])
+    b = engine.new_batch(units, tabs)
+    engine.process(b, Philox(4242))
+    engine.fetch_counts(b)
+    engine.check_status(b)
+    t_gpu = np.concatenate([b.view("times_src", i, "src")[1:] for i in range(14)])
+    p_gpu = np.concatenate([b.view("pha_src", i, "src")[1:] for i in range(14)])
+    # light curve
+    assert stats.ks_2samp(t_ref, t_gpu).pvalue > P_MIN
+    bins = np.linspace(0, params["duration"], 21)
+    a, _ = np.histogram(t_ref, bins)
+    g, _ = np.histogram(t_gpu, bins)
+    ok = (a + g) >= 10
+    tab = np.vstack([a[ok], g[ok]])
+    assert stats.chi2_contingency(tab)[1] > P_MIN
+    # count spectrum
+    a = np.bincount(p_ref.astype(int), minlength=128)
+    g = np.bincount(p_gpu.astype(int), minlength=128)
+    ok = (a + g) >= 10
+    assert stats.chi2_contingency(np.vstack([a[ok], g[ok]]))[1] > P_MIN
+    # total counts: Poisson-consistent
+    n_ref, n_gpu = len(t_ref) / 6.0, len(t_gpu) / 14.0
+    assert abs(n_ref - n_gpu) < 5.0 * np.sqrt(n_ref / 6.0 + n_gpu / 14.0)
+    # background
+    tb = b.view("times_bkg", 0, "bkg")[1:]
+    assert stats.kstest((tb + 100.0) / 400.0, "uniform").pvalue > P_MIN
+    pb = np.concatenate([b.view("pha_bkg", i, "bkg") for i in range(14)])
+    w = h.bkg_weights("n0").astype("f8")
+    obs = np.bincount(pb.astype(int), minlength=128)
+    exp = w / w.sum() * obs.sum()
+    ok = exp >= 10
+    chi2 = ((obs[ok] - exp[ok]) ** 2 / exp[ok]).sum()
+    assert stats.chi2.sf(chi2, ok.sum() - 1) > P_MIN
+    gaps = np.diff(b.view("times_bkg", 1, "bkg")[1:])
+    assert stats.kstest(gaps, "expon", args=(0, 1.0 / 500.0)).pvalue > P_MIN
