@@ -172,6 +172,7 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 KERNEL_BYTES = {
+    "k_sample_energy_env": 16.0,  # reads time, writes energy per source event
     # algorithmic HBM bytes per EVENT of each kernel's own product
     "k_background": 9.0,        # writes f64 time + u8 channel per background event
     "k_combine": 18.0,          # reads 9 B, writes 9 B per merged event
@@ -207,7 +208,10 @@ def run_gpu(args):
     from cosmogrb_b200.engine import Engine, Philox
 
     dev = torch.device("cuda", local if world > 1 else 0)
-    eng = Engine(device=dev)
+    from cosmogrb_b200.engine import get_engine
+
+    eng = get_engine()              # the process-wide engine the public API uses
+    assert eng.device == dev, (eng.device, dev)
     units, tabs = build_inputs(grb_index=rank)
     seed = 0x00C0560612B
 
@@ -282,7 +286,8 @@ def run_gpu(args):
     n_src, n_bkg = int(counts["n_src"].sum()), int(counts["n_bkg"].sum())
     n_tot = n_src + n_bkg
     units_of = {"k_background": n_bkg, "k_combine": n_tot, "k_deadtime_count": n_tot, "k_deadtime_write": n_tot,
-                "k_source_thin": n_src, "k_source_gather": n_src, "k_sample_energy": n_src, "k_digitize": n_src}
+                "k_source_thin": n_src, "k_source_gather": n_src, "k_sample_energy": n_src, "k_digitize": n_src,
+                "k_sample_energy_env": n_src}
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -306,17 +311,25 @@ def run_gpu(args):
     hbm_kernels = [hbm_roofline(n) for n in kern if n.split("<")[0] in ("k_background", "k_combine",
                                                                            "k_deadtime_count", "k_deadtime_write")]
 
-    # ---- e2e arm: host buffers in, host buffers out -------------------------------------------
-    pinned = {}
+    # ---- e2e arm: the public API, GBMGRB_CPL(...).go(): host objects in, host arrays out -------------
+    # The burst object is built once (like the reference, construction = responses, backgrounds and
+    # fmax; go() = the hot call).  Every go() uploads the unit records and the 14 detector tables
+    # (the engine's table cache is cleared so the copy really happens) and returns the six event lists
+    # of each of the 14 detectors in pinned host memory.
+    from cosmogrb_b200 import gbm
+
+    p = bright_params()
+    grb = None if args.no_e2e else gbm.GBMGRB_CPL(ra=312.0, dec=-62.0, T0=0.1, name=f"bench_{rank}", **p)
 
     def step_e2e(k):
-        b = eng.new_batch(units, tabs_fresh())       # H2D: unit records + tables; fmax on device
-        eng.process(b, Philox(seed + 1000 + k))
-        gather_counts(b.d_counts)
-        return eng.to_host(b, pinned)
-
-    def tabs_fresh():
-        return [t.copy() for t in tabs]              # defeat the engine's table cache: real H2D every step
+        eng._dtab_cache.clear()
+        grb.go(seed=seed + 1000 + k, stream_base=16 * rank)
+        ev = nb = 0
+        for lc in grb.lightcurves.values():
+            st = lc.lightcurve_storage
+            ev += st.n_counts_source + st.n_counts_background
+            nb += 9 * (st.n_counts + st.n_counts_source + st.n_counts_background)
+        return {"events": ev, "d2h_bytes": nb + 14 * 64}
 
     h2d = units.nbytes + sum(t.nbytes for t in tabs)
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 3))

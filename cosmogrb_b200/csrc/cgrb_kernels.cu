@@ -928,7 +928,7 @@ struct EnvSmem {
     double eay[CGRB_NBINS];
 };
 
-__global__ void __launch_bounds__(NT) k_sample_energy_env(const double *__restrict__ dtab,
+__global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__restrict__ dtab,
                                                           const cgrb_unit_t *__restrict__ units,
                                                           const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                           int interp_extrap, cgrb_rng_t rng, int64_t max_trials,
@@ -971,83 +971,141 @@ __global__ void __launch_bounds__(NT) k_sample_energy_env(const double *__restri
     __syncthreads();
     const double opz = 1.0 + u.z, alpha = u.alpha;
     const double emin = dt[CGRB_DT_EDGES], emax = dt[CGRB_DT_EDGES + CGRB_NBINS];
-    const double l0 = T->l0, dl = T->dl, inv_dl = T->inv_dl, a = T->a, amax = T->amax;
-    const double log_emin = log(emin), log_emax = log(emax);
-    const EaGuess eg = make_ea_guess(sm.eax);
-    const double ec_den = (alpha == -2.0) ? 0.0001 : (2.0 + alpha);
+    // loop constants live in shared memory (broadcast loads) to keep the trial loop's registers free
+    __shared__ double ck[12];
+    if (threadIdx.x == 0) {
+        ck[0] = T->l0;
+        ck[1] = T->dl;
+        ck[2] = T->inv_dl;
+        ck[3] = T->a;
+        ck[4] = T->amax;
+        ck[5] = log(emin);
+        ck[6] = log(emax);
+        ck[7] = (alpha == -2.0) ? 0.0001 : (2.0 + alpha);
+        EaGuess g0 = make_ea_guess(sm.eax);
+        ck[8] = g0.log_x0;
+        ck[9] = g0.inv_dlog;
+    }
+    __syncthreads();
+#define l0 ck[0]
+#define dl ck[1]
+#define inv_dl ck[2]
+#define a ck[3]
+#define amax ck[4]
+#define log_emin ck[5]
+#define log_emax ck[6]
+#define ec_den ck[7]
+    EaGuess eg;
+    eg.log_x0 = ck[8];
+    eg.inv_dlog = ck[9];
 
     int64_t chunk_end = n_src;
     if (w + 1 < n_work && work[w + 1].unit == wk.unit)
         chunk_end = min(n_src, work[w + 1].start);
 
+    // Lane refill: every warp owns a contiguous slice of the chunk; a lane that accepted (about one in
+    // three per round) immediately takes the warp's next photon, so lanes never idle waiting for the
+    // slowest geometric tail of their neighbours.
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t per = (chunk_end - wk.start + NW - 1) / NW;
+    const int64_t wbeg = wk.start + (int64_t)wid * per, wend = min(wbeg + per, chunk_end);
+    int64_t next = wbeg;                 // warp-uniform
     long long my_trials = 0;
-    bool capped = false;
-    for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += NT) {
-        const double t = times_src[u.src_off + i];
-        double x_acc = nan("");
-        int64_t ntr = 0;
-        // pulse amplitude > 0 ?  (norris underflows for t -> 0+; constant CPL is always regular)
-        bool regular = (u.kind != 0) || (t > 0.0 && (u.trise / t + t / u.tdecay) < 700.0 && u.peak_flux > 0.0);
-        const double ep = (u.kind == 0) ? u.ep_start / (1.0 + t / u.ep_tau) : u.ep_start;
-        const double wq = opz * ec_den / ep;            // (1+z) / ec
-        const double logw = log(wq);
-        double l_lo = log_emin + logw, l_hi = log_emax + logw;
-        // piecewise-linear CDF of the envelope at the truncation points
-        double F_lo, F_hi;
-        {
-            double q = (l_lo - l0) * inv_dl;
-            int j = max(0, min((int)q, CGRB_ENV_SEGS - 1));
-            F_lo = sm.cdf[j] + (sm.cdf[j + 1] - sm.cdf[j]) * fmin(fmax(q - j, 0.0), 1.0);
-            q = (l_hi - l0) * inv_dl;
-            j = max(0, min((int)q, CGRB_ENV_SEGS - 1));
-            F_hi = sm.cdf[j] + (sm.cdf[j + 1] - sm.cdf[j]) * fmin(fmax(q - j, 0.0), 1.0);
-        }
-        if (!(F_hi > F_lo))
-            regular = false;
-        if (regular) {
-            const int idx = hull_lookup(sm.hull_m, sm.hull_w, n_hull, ec_den / ep);
-            const double s_idx = dt[CGRB_DT_G500_E + idx] * wq;
-            const double A5 = 5.0 * dt[CGRB_DT_G500_A + idx];
-            const double inv_w = 1.0 / wq;
-            for (uint32_t j = 0;; j++) {
-                Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
-                const double U = u53(p.x, p.y), V = u53(p.z, p.w);
-                const double y = F_lo + U * (F_hi - F_lo);
-                int lo = 0, hi = CGRB_ENV_SEGS;         // segment: cdf[lo] <= y < cdf[lo+1]
-                while (hi - lo > 1) {
-                    int mid = (lo + hi) >> 1;
-                    if (sm.cdf[mid] <= y)
-                        lo = mid;
-                    else
-                        hi = mid;
-                }
-                double l = l0 + lo * dl + (y - sm.cdf[lo]) * sm.inv_b[lo];
-                l = fmin(fmax(l, l_lo), l_hi);
-                const double s = exp(l);
-                const double x = s * inv_w;
-                const double r1 = exp(a * (l - sm.lstar[lo]) - (s - sm.sstar[lo]));
-                double A = fmax(interp_guess(sm.eax, sm.eay, CGRB_NBINS, x, l - logw, eg, interp_extrap), 0.0);
-                if (!(s >= s_idx && A <= A5))
-                    A = fmin(A, A5 * exp(s - s_idx));   // the literal envelope clips f here
-                ntr = (int64_t)j + 1;
-                if (V * amax <= r1 * A) {
-                    x_acc = x;
-                    break;
-                }
-                if (max_trials > 0 && ntr >= max_trials) {
-                    capped = true;
-                    break;
+    bool capped = false, active = false;
+    // per-lane photon state
+    int64_t i = 0;
+    uint32_t j = 0;
+    double logw = 0.0, l_lo = 0.0, l_hi = 0.0, F_lo = 0.0, dF = 0.0, s_idx = 0.0, A5 = 0.0, inv_w = 0.0;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (need) {
+            const int64_t cand = next + __popc(need & ((1u << lane) - 1u));
+            next += __popc(need);
+            if (!active && cand < wend) {
+                i = cand;
+                j = 0;
+                const double t = times_src[u.src_off + i];
+                // pulse amplitude > 0 ?  (norris underflows for t -> 0+; constant CPL is always regular)
+                bool regular = (u.kind != 0) || (t > 0.0 && (u.trise / t + t / u.tdecay) < 700.0 && u.peak_flux > 0.0);
+                const double ep = (u.kind == 0) ? u.ep_start / (1.0 + t / u.ep_tau) : u.ep_start;
+                const double wq = opz * ec_den / ep;            // (1+z) / ec
+                logw = log(wq);
+                l_lo = log_emin + logw;
+                l_hi = log_emax + logw;
+                // piecewise-linear CDF of the envelope at the truncation points
+                double q = (l_lo - l0) * inv_dl;
+                int k = max(0, min((int)q, CGRB_ENV_SEGS - 1));
+                F_lo = sm.cdf[k] + (sm.cdf[k + 1] - sm.cdf[k]) * fmin(fmax(q - k, 0.0), 1.0);
+                q = (l_hi - l0) * inv_dl;
+                k = max(0, min((int)q, CGRB_ENV_SEGS - 1));
+                dF = sm.cdf[k] + (sm.cdf[k + 1] - sm.cdf[k]) * fmin(fmax(q - k, 0.0), 1.0) - F_lo;
+                if (!(dF > 0.0))
+                    regular = false;
+                if (regular) {
+                    const int idx = hull_lookup(sm.hull_m, sm.hull_w, n_hull, ec_den / ep);
+                    s_idx = dt[CGRB_DT_G500_E + idx] * wq;
+                    A5 = 5.0 * dt[CGRB_DT_G500_A + idx];
+                    inv_w = 1.0 / wq;
+                    active = true;
+                } else {
+                    // degenerate photon: the literal loop, right here (rare)
+                    int64_t ntr = 0;
+                    const double x = literal_photon_serial(u, dt, sm.eax, sm.eay, eg, interp_extrap, rng.seed, i, t,
+                                                           max_trials, &ntr, &capped);
+                    energy_src[u.src_off + i] = x;
+                    if (trials_out)
+                        trials_out[u.src_off + i] = (int32_t)ntr;
+                    my_trials += ntr;
                 }
             }
-        } else {
-            x_acc = literal_photon_serial(u, dt, sm.eax, sm.eay, eg, interp_extrap, rng.seed, i, t, max_trials, &ntr,
-                                          &capped);
         }
-        energy_src[u.src_off + i] = x_acc;
-        if (trials_out)
-            trials_out[u.src_off + i] = (int32_t)ntr;
-        my_trials += ntr;
+        if (!__any_sync(0xffffffffu, active)) {
+            if (next >= wend)
+                break;
+            continue;
+        }
+        if (active) {
+            Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
+            const double U = u53(p.x, p.y), V = u53(p.z, p.w);
+            const double y = F_lo + U * dF;
+            int lo = 0, hi = CGRB_ENV_SEGS;         // segment: cdf[lo] <= y < cdf[lo+1]
+#pragma unroll
+            for (int it = 0; it < 8; it++) {        // CGRB_ENV_SEGS = 2^8
+                int mid = (lo + hi) >> 1;
+                if (sm.cdf[mid] <= y)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            double l = l0 + lo * dl + (y - sm.cdf[lo]) * sm.inv_b[lo];
+            l = fmin(fmax(l, l_lo), l_hi);
+            const double s = exp(l);
+            const double x = s * inv_w;
+            const double r1 = exp(a * (l - sm.lstar[lo]) - (s - sm.sstar[lo]));
+            double A = fmax(interp_guess(sm.eax, sm.eay, CGRB_NBINS, x, l - logw, eg, interp_extrap), 0.0);
+            if (!(s >= s_idx && A <= A5))
+                A = fmin(A, A5 * exp(s - s_idx));   // the literal envelope clips f here
+            j++;
+            const bool acc = V * amax <= r1 * A;
+            const bool cap = !acc && max_trials > 0 && (int64_t)j >= max_trials;
+            if (acc || cap) {
+                energy_src[u.src_off + i] = acc ? x : nan("");
+                if (trials_out)
+                    trials_out[u.src_off + i] = (int32_t)j;
+                my_trials += j;
+                capped |= cap;
+                active = false;
+            }
+        }
     }
+#undef l0
+#undef dl
+#undef inv_dl
+#undef a
+#undef amax
+#undef log_emin
+#undef log_emax
+#undef ec_den
     const long long tot = block_sum_ll(my_trials, s_wl);
     if (threadIdx.x == 0 && tot)
         atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)tot);

@@ -22,7 +22,8 @@ from . import _capi
 from ._capi import COUNTS_DTYPE, UNIT_DTYPE, WORK_DTYPE, RngDesc
 
 DEFAULT_SEED = 0x00C0560612B
-ENERGY_CHUNK = 1024          # photons per CTA work item of the energy / digitize kernels
+ENERGY_CHUNK = 1024          # photons per CTA work item of the energy kernels
+DIGITIZE_CHUNK = 8192        # photons per CTA of the digitize kernel (amortises staging the 143 KB matrix)
 DEFAULT_MAX_TRIALS = 1 << 22
 
 
@@ -309,7 +310,8 @@ class Engine(object):
         torch = _torch()
         c = self.fetch_counts(b)
         self.check_status(b)
-        pinned = {} if pinned is None else pinned
+        # pinned=None: fresh pinned buffers per call (torch's caching host allocator recycles them), so
+        # the returned arrays stay valid for as long as the caller keeps them
         n_of = {"kept": c["n_kept"], "src": c["n_src"], "bkg": c["n_bkg"], "tot": c["n_total"]}
         off_of = {"kept": b.units["tot_off"], "src": b.units["src_off"], "bkg": b.units["bkg_off"],
                   "tot": b.units["tot_off"]}
@@ -319,10 +321,12 @@ class Engine(object):
             n = n_of[kind].astype(np.int64)
             starts = np.concatenate(([0], np.cumsum(n)))
             total = int(starts[-1])
-            buf = pinned.get(name)
+            buf = pinned.get(name) if pinned is not None else None
             if buf is None or buf.numel() < total or buf.dtype != src.dtype:
-                buf = torch.empty(max(int(total * 1.1) + 1024, 1), dtype=src.dtype, pin_memory=True)
-                pinned[name] = buf
+                buf = torch.empty(max(int(total * 1.1) + 1024, 1) if pinned is not None else max(total, 1),
+                                  dtype=src.dtype, pin_memory=True)
+                if pinned is not None:
+                    pinned[name] = buf
             for ui in range(b.n_units):
                 k = int(n[ui])
                 if k:
@@ -414,7 +418,7 @@ class Engine(object):
 
     def digitize_batch(self, b, rng):
         torch = _torch()
-        w, dw, _ = self._work(b, 3, ENERGY_CHUNK)
+        w, dw, _ = self._work(b, 3, DIGITIZE_CHUNK)
         t = b.t
         t["pha_src"] = self.empty(b.n_src_slots, torch.uint8)
         desc = self._rng_desc(rng, b, "digitize")

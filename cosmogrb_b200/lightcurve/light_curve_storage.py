@@ -12,13 +12,15 @@ class LightCurveStorage(object):
         self._tstart = tstart
         self._tstop = tstop
         self._time_adjustment = time_adjustment
-        self._pha = np.asarray(pha).astype(int)                      # light_curve_storage.py:58
+        # the event arrays may be views of pinned staging buffers in the engine's compact dtypes
+        # (u8 channels); the reference's dtypes -- pha int (light_curve_storage.py:58), pha_source
+        # float64, pha_background int64 -- are materialised on first access
+        self._raw = dict(pha=pha, pha_source=pha_source, pha_background=pha_background)
+        self._conv = {}
         self._times = np.asarray(times)
         self._n_counts = self._times.shape[0]
-        self._pha_source = np.asarray(pha_source)
         self._times_source = np.asarray(times_source)
         self._n_counts_source = self._times_source.shape[0]
-        self._pha_background = np.asarray(pha_background)
         self._times_background = np.asarray(times_background)
         self._n_counts_background = self._times_background.shape[0]
         self._channels = channels
@@ -38,13 +40,33 @@ class LightCurveStorage(object):
     channels = property(lambda self: self._channels)
     ebounds = property(lambda self: self._ebounds)
     times = property(lambda self: self._times)
-    pha = property(lambda self: self._pha)
-    pha_source = property(lambda self: self._pha_source)
+    pha = property(lambda self: self._get("pha", int))
+    pha_source = property(lambda self: self._get("pha_source", np.float64))
     times_source = property(lambda self: self._times_source)
-    pha_background = property(lambda self: self._pha_background)
+    pha_background = property(lambda self: self._get("pha_background", np.int64))
     times_background = property(lambda self: self._times_background)
     time_adjustment = property(lambda self: self._time_adjustment)
     extra_info = property(lambda self: self._extra_info)
+
+    _REF_DTYPE = dict(pha=int, pha_source=np.float64, pha_background=np.int64)
+
+    def _get(self, name, dtype):
+        if name not in self._conv:
+            a = np.asarray(self._raw[name])
+            self._conv[name] = a if a.dtype == np.dtype(dtype) else a.astype(dtype)
+        return self._conv[name]
+
+    @property
+    def _pha(self):
+        return self.pha
+
+    @property
+    def _pha_source(self):
+        return self.pha_source
+
+    @property
+    def _pha_background(self):
+        return self.pha_background
 
     def _select_channel(self, emin, emax, pha, original_idx=None):
         if original_idx is None:

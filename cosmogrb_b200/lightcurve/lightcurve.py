@@ -51,17 +51,17 @@ class LightCurve(object):
 
     def _storage_from(self, arrays, i):
         def sl(name):
+            # views of the (pinned) staging buffers: no second host copy
             o = arrays[name + "_offsets"]
-            return arrays[name][int(o[i]):int(o[i + 1])].numpy().copy()
+            return arrays[name][int(o[i]):int(o[i + 1])].numpy()
 
         pha, times = sl("pha_out"), sl("times_out")
         if not self._deadtime:
             pha, times = sl("pha_tot"), sl("times_tot")
         return LightCurveStorage(
             name=self._name, tstart=self._tstart, tstop=self._tstop, time_adjustment=self._time_adjustment,
-            pha=pha, times=times,
-            pha_source=sl("pha_src").astype("f8"), times_source=sl("times_src"),      # reference dtypes:
-            pha_background=sl("pha_bkg").astype(np.int64), times_background=sl("times_bkg"),  # f8 / i8
+            pha=pha, times=times, pha_source=sl("pha_src"), times_source=sl("times_src"),
+            pha_background=sl("pha_bkg"), times_background=sl("times_bkg"),
             channels=self._response.channels, ebounds=self._response.channel_edges, T0=self._T0,
             instrument=self._instrument, extra_info=self._extra_info)
 

@@ -1,0 +1,151 @@
+"""GPU: the reference-facing API surface (GBMGRB_CPL(...).go(), Source / Background / Response
+sampler classes, GRB.save + GRBSave.from_file, Universe runs) on the CUDA engine."""
+import numpy as np
+import pytest
+
+from tests import helpers as h
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+stats = pytest.importorskip("scipy.stats")
+
+
+@pytest.fixture(scope="module")
+def grb(engine):
+    from cosmogrb_b200 import gbm
+
+    # test/conftest.py:31-53 (the reference's bright fixture)
+    g = gbm.GBMGRB_CPL(ra=312.0, dec=-62.0, z=1.0, peak_flux=1e-5, alpha=-0.66, ep_start=500.0, ep_tau=2.0,
+                       trise=0.1, tdecay=1.0, duration=2.0, T0=0.1)
+    g.go(seed=2024)
+    return g
+
+
+def test_gbmgrb_cpl_go(grb):
+    names = list(grb.lightcurves.keys())
+    assert names == list(h.GBM_DETECTORS)
+    for name, lc in grb.lightcurves.items():
+        st = lc.lightcurve_storage
+        assert st.name == name and st.instrument == "GBM" and st.tstart == -100 and st.tstop == 300
+        assert st.times_source[0] == 0.0 and st.times_background[0] == -100.0       # the spurious tstart events
+        assert np.all(np.diff(st.times) >= 0) and np.all(np.diff(st.times_source) >= 0)
+        assert st.pha.dtype.kind == "i" and st.pha_source.dtype == np.float64 and st.pha_background.dtype == np.int64
+        assert st.pha.min() >= 0 and st.pha.max() <= 127
+        n_pre = st.n_counts_source + st.n_counts_background
+        assert 0 < n_pre - st.n_counts < 0.01 * n_pre                   # dead time removes a few events
+        assert abs(st.n_counts_background - 1 - 500 * 400) < 6 * np.sqrt(2e5) + 40 * 400    # rate ~ N(500, 10)
+        # the total list is the dead-time filtered merge of the two component lists
+        wt, wp = orc.combine(st.times_background, st.pha_background, st.times_source, st.pha_source)
+        sel = orc.gbm_dead_time(wt, wp)
+        assert np.array_equal(st.times, wt[sel]) and np.array_equal(st.pha, wp[sel].astype(int))
+    # brighter in the detectors with the larger effective area
+    n_src = {k: lc.lightcurve_storage.n_counts_source for k, lc in grb.lightcurves.items()}
+    ea = {k: lc.response.effective_area_packed[1].max() for k, lc in grb.lightcurves.items() if k[0] == "n"}
+    best, worst = max(ea, key=ea.get), min(ea, key=ea.get)
+    assert n_src[best] > n_src[worst]
+
+
+def test_grb_save_and_reload(grb, tmp_path):
+    from cosmogrb_b200 import GRBSave
+
+    fn = tmp_path / "test_grb.h5"
+    grb.save(fn)
+    g = GRBSave.from_file(fn)
+    assert g.name == "SynthGRB" and g.z == 1.0 and g.duration == 2.0 and g.T0 == 0.1
+    assert g.source_params["peak_flux"] == 1e-5
+    for name, lc in grb.lightcurves.items():
+        st, got = lc.lightcurve_storage, g[name]["lightcurve"]
+        assert np.array_equal(got.times, st.times) and np.array_equal(got.pha, st.pha)
+        assert np.array_equal(got.times_source, st.times_source)
+        assert np.array_equal(g[name]["response"].matrix, lc.response.matrix)
+        assert got.extra_info["angle"] == pytest.approx(lc.response.separation_angle)
+
+
+def test_go_is_reproducible_and_seed_dependent(engine):
+    from cosmogrb_b200 import gbm
+
+    np.random.seed(3)
+    kw = dict(ra=10.0, dec=20.0, z=1.0, peak_flux=5e-7, alpha=-0.66, ep_start=500.0, ep_tau=2.0, trise=1.0,
+              tdecay=1.0, duration=20.0, T0=0.1)
+    a = gbm.GBMGRB_CPL(**kw)
+    np.random.seed(3)
+    b = gbm.GBMGRB_CPL(**kw)
+    a.go(seed=1)
+    b.go(seed=1)
+    assert np.array_equal(a.lightcurves["n3"].times, b.lightcurves["n3"].times)
+    b.go(seed=2)
+    assert not np.array_equal(a.lightcurves["n3"].times_source, b.lightcurves["n3"].times_source)
+
+
+def test_constant_cpl_grb(engine):
+    from cosmogrb_b200 import gbm
+
+    g = gbm.GBMGRB_CPL_Constant(ra=312.0, dec=-62.0, z=1.0, peak_flux=5e-9, alpha=-0.66, ep=500.0, duration=2.0, T0=0.1)
+    g.go()
+    st = g.lightcurves["n0"].lightcurve_storage
+    lam = g.lightcurves["n0"]._source.fmax
+    assert abs(st.n_counts_source - 1 - 2.0 * lam) < 6 * np.sqrt(2.0 * lam) + 3
+
+
+def test_sampler_classes_standalone(engine):
+    """Source / CPLSourceFunction / Background / Response used one call at a time, like the
+    reference's LightCurve._sample_source (lightcurve.py:74-129)."""
+    from cosmogrb_b200.instruments.gbm.gbm_background import GBMBackground
+    from cosmogrb_b200.sampler import CPLSourceFunction, Source
+
+    p = h.CONFTEST_BRIGHT
+    rsp = h.response("n0")
+    sf = CPLSourceFunction(response=rsp, peak_flux=p["peak_flux"], trise=p["trise"], tdecay=p["tdecay"],
+                           ep_tau=p["ep_tau"], alpha=p["alpha"], ep_start=p["ep_start"])
+    src = Source(0.0, p["duration"], sf, z=p["z"])
+    s = h.oracle_source(rsp, **p)
+    assert src.fmax == pytest.approx(orc.fmax(s, rsp.effective_area_packed, 0.0, p["duration"]), rel=1e-11)
+    assert sf.energy_integrated_evolution(0.5) == pytest.approx(
+        orc.energy_integrated_evolution(s, rsp.effective_area_packed, [0.5])[0], rel=1e-11)
+    evo = sf.evolution(np.array([10.0, 100.0]), np.array([0.2, 0.5, 1.0]))
+    np.testing.assert_allclose(evo, orc.cpl_evolution(s, [10.0, 100.0], [0.2, 0.5, 1.0]), rtol=1e-11)
+    times = src.sample_times()
+    assert times[0] == 0.0 and np.all(np.diff(times) >= 0) and times[-1] <= p["duration"]
+    ref, _ = orc.sample_events(s, rsp.effective_area_packed, 0.0, p["duration"], src.fmax, orc.Rng(seed=5))
+    assert abs(len(times) - len(ref)) < 6 * np.sqrt(len(ref))
+    assert stats.ks_2samp(times[1:], ref[1:]).pvalue > 0.01
+    photons = src.sample_photons(times)
+    assert photons.shape == times.shape and np.all(photons >= rsp.emin * (1 - 1e-12))
+    pha = src.sample_channel(photons, rsp)
+    assert pha.dtype == np.float64 and pha.min() >= 0 and pha.max() <= 127
+    bkg = GBMBackground(-100, 300, average_rate=500, detector="n0")
+    tb = bkg.sample_times()
+    assert tb[0] == -100 and abs(len(tb) - 400 * bkg.background_rate) < 6 * np.sqrt(2e5)
+    cb = bkg.sample_channel(size=len(tb))
+    assert cb.dtype == np.int64 and len(cb) == len(tb)
+    w = h.bkg_weights("n0").astype("f8")
+    obs = np.bincount(cb, minlength=128)
+    exp = w / w.sum() * len(cb)
+    ok = exp >= 10
+    assert stats.chi2.sf(((obs[ok] - exp[ok]) ** 2 / exp[ok]).sum(), ok.sum() - 1) > 0.01
+
+
+def test_universe_run(engine, tmp_path):
+    from cosmogrb_b200 import GRBSave
+    from cosmogrb_b200.instruments.gbm.gbm_universe import GBM_CPL_Universe
+    from cosmogrb_b200.universe import synthetic_population
+
+    pop = synthetic_population(12, seed=7)
+    fn = tmp_path / "pop.npz"
+    pop.writeto(fn)
+    uni = GBM_CPL_Universe(str(fn), save_path=str(tmp_path))
+    uni.go(seed=11)
+    assert uni.event_counts.shape == (12, 14, 3)
+    assert np.all(uni.event_counts[:, :, 1] > 1.8e5)
+    for i in (0, 11):
+        g = GRBSave.from_file(tmp_path / f"SynthGRB_{i}_store.h5")
+        assert g.name == f"SynthGRB_{i}" and g.z == pytest.approx(pop.distances[i])
+        for d, det in enumerate(h.GBM_DETECTORS):
+            st = g[det]["lightcurve"]
+            assert (st.n_counts_source, st.n_counts_background, st.n_counts) == tuple(uni.event_counts[i, d])
+    uni.save(tmp_path / "survey.h5")
+    # results do not depend on the batching (Philox counters are functions of the unit)
+    uni2 = GBM_CPL_Universe(str(fn), save_path=None)
+    uni2.go(seed=11, grbs_per_batch=5)
+    assert uni2.n_batches == 3
+    assert np.array_equal(uni2.event_counts, uni.event_counts)
