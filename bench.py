@@ -35,6 +35,19 @@ WORKLOAD = "C2 bright long GBMGRB_CPL: peak_flux=1e-4 duration=300s trise=5 tdec
 BYTES_PER_EVENT = 18      # (f64 time + u8 channel) x (component list + total list)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the single JSON line, on the process's original stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def bright_params():
     from tests import helpers as h
 
@@ -164,7 +177,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -384,7 +397,7 @@ def run_gpu(args):
             "roofline": roofline, "roofline_hbm_kernels": hbm_kernels,
             "kernels": kern, "cpu_baseline": cpu_baseline, "clocks": clk,
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -400,6 +413,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
     args = ap.parse_args()
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, torchrun warnings)
+    # write to fd 1 too, so everything else goes to stderr and the line is written to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)
