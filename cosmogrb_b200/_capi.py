@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NBINS = 140
 NCHAN = 128
 NE_LAMBDA = 75
@@ -23,6 +23,7 @@ NT_FMAX = 50
 SEG = 8192
 MERGE_TILE = 2048
 DT_TILE = 2048
+ENV_MAXW = 256
 
 # detector table block layout (doubles) -- must match include/cosmogrb_b200.h
 DT_EDGES = 0
@@ -41,6 +42,7 @@ ST_BKG_CAPACITY = 2
 ST_UNIFORMS_EXHAUSTED = 4
 ST_TRIAL_CAP = 8
 ST_OUT_CAPACITY = 16
+ST_ENVELOPE = 32
 
 UNIT_NO_SOURCE = 1
 UNIT_NO_BACKGROUND = 2
@@ -61,10 +63,11 @@ UNIT_DTYPE = np.dtype(
         ("fmax", "<f8"), ("gamma_a", "<f8"), ("lgamma_a", "<f8"), ("lgamma_1pa", "<f8"),
         ("src_cap", "<i8"), ("bkg_cap", "<i8"), ("src_off", "<i8"), ("bkg_off", "<i8"),
         ("tot_off", "<i8"), ("tab_off", "<i8"), ("tab_n", "<i8"), ("ea_scale", "<f8"),
+        ("etab_off", "<i8"), ("etab_nw", "<i8"),
     ],
     align=False,
 )
-assert UNIT_DTYPE.itemsize == 208
+assert UNIT_DTYPE.itemsize == 224
 
 COUNTS_DTYPE = np.dtype(
     [
@@ -144,9 +147,9 @@ def load():
     lib.cgrb_thin_tables.argtypes = [vp, vp, i32, vp, i64, vp, vp]
     lib.cgrb_sample_events.argtypes = [vp, vp, i32, vp, i64, vp, i32, rp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cgrb_sample_energy.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, vp, vp, vp, vp]
-    lib.cgrb_energy_workspace_bytes.argtypes = [i32]
+    lib.cgrb_energy_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_energy_workspace_bytes.restype = i64
-    lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, i64, vp, vp, vp, vp, vp]
     lib.cgrb_digitize.argtypes = [vp, vp, i32, vp, i64, rp, vp, vp, vp, vp]
     lib.cgrb_sample_background.argtypes = [vp, vp, i32, vp, i64, vp, rp, rp, vp, vp, vp, vp, vp, vp]
     lib.cgrb_background_channels.argtypes = [vp, i32, C.c_uint32, rp, i64, vp, vp]

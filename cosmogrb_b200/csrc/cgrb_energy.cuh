@@ -23,23 +23,24 @@
 namespace cgrb {
 
 #define CGRB_ENV_SEGS 256
+#define CGRB_ENV_MAXW 256
 
 // per-unit tables of the energy samplers, built by k_energy_tables (device memory, one per unit)
 struct EnergyUnitTab {
     // upper hull of the lines y_m(w) = gl[m] - gx[m] w  (w = 1/ec): argmax_m f(E_m, t) as a
     // function of w.  hull_m[k] is the argmax for hull_w[k] <= w < hull_w[k+1].
     int n_hull;
-    int pad;
+    int n_w;                           // rows of the unit's proposal table (grid of w = (1+z)/ec)
     double hull_w[CGRB_NE_ENVELOPE];
     int hull_m[CGRB_NE_ENVELOPE];
-    // envelope of phi(l) = a l - e^l on CGRB_ENV_SEGS equal segments of [l0, l0 + SEGS dl]
-    double l0, dl, inv_dl;
+    // proposal: CGRB_ENV_SEGS equal segments in u = log x on [log emin, log emax]
+    double u0, du;
     double a;                          // alpha + 1
-    double amax;                       // max of max(A, 0) over [emin, emax]
-    double cdf[CGRB_ENV_SEGS + 1];     // cumulative segment weights b_j dl (unnormalised)
-    double inv_b[CGRB_ENV_SEGS];       // 1 / b_j  (0 where b_j = 0)
-    double lstar[CGRB_ENV_SEGS];       // argmax of phi on the segment
-    double sstar[CGRB_ENV_SEGS];       // e^lstar
+    double logw0, inv_dlogw;           // row k covers w in [wk[k], wk[k+1])
+    double xlo[CGRB_ENV_SEGS + 1];     // segment edges in x (xlo[0] = emin, xlo[SEGS] = emax)
+    double logM[CGRB_ENV_SEGS];        // log max over the segment of x^(alpha+1) max(A(x), 0)  (-inf: none)
+    double logAmax[CGRB_ENV_SEGS];     // log max over the segment of max(A(x), 0)
+    double wk[CGRB_ENV_MAXW];          // lower edges of the w rows
 };
 
 // interp(ea_x, ea_y, v) with a log-uniform first guess for the bracket (the bin means of
@@ -76,16 +77,53 @@ __device__ __forceinline__ double interp_guess(const double *xs, const double *y
 }
 
 // ------------------------------------------------------------------------------------------
-// per-unit table build: one CTA per unit
+// per-unit table build: one CTA per unit (256 threads = one thread per proposal segment)
 // ------------------------------------------------------------------------------------------
+
+// max over [xa, xb] of G(x) = x^a max(A(x), 0) and of max(A(x), 0), A = interp(ea_x, ea_y, .) piecewise
+// linear with knots at the table nodes: endpoints of every linear piece plus the interior stationary
+// point x* = -a p / ((a + 1) q) of x^a (p + q x).
+__device__ __forceinline__ void segment_max(const double *eax, const double *eay, int extrap, double a, double xa,
+                                            double xb, double *g_max, double *a_max)
+{
+    double gm = 0.0, am = 0.0;
+    int i = searchsorted_right(eax, CGRB_NBINS, xa);      // first knot > xa
+    double p1 = xa;
+    double r1 = interp1(eax, eay, CGRB_NBINS, p1, extrap);
+    for (;;) {
+        const bool last = !(i < CGRB_NBINS && eax[i] < xb);
+        const double p2 = last ? xb : eax[i];
+        const double r2 = interp1(eax, eay, CGRB_NBINS, p2, extrap);
+        const double c1 = fmax(r1, 0.0), c2 = fmax(r2, 0.0);
+        am = fmax(am, fmax(c1, c2));
+        gm = fmax(gm, fmax(c1 * exp(a * log(p1)), c2 * exp(a * log(p2))));
+        if (p2 > p1) {
+            const double q = (r2 - r1) / (p2 - p1), p = r1 - q * p1;
+            const double den = (a + 1.0) * q;
+            if (den != 0.0) {
+                const double xs = -a * p / den;
+                if (xs > p1 && xs < p2)
+                    gm = fmax(gm, fmax(p + q * xs, 0.0) * exp(a * log(xs)));
+            }
+        }
+        if (last)
+            break;
+        p1 = p2;
+        r1 = r2;
+        i++;
+    }
+    *g_max = gm;
+    *a_max = am;
+}
+
 __global__ void __launch_bounds__(256) k_energy_tables(const double *__restrict__ dtab,
                                                        const cgrb_unit_t *__restrict__ units, int n_units,
                                                        int interp_extrap, EnergyUnitTab *__restrict__ etab)
 {
     __shared__ double s_gl[CGRB_NE_ENVELOPE];
     __shared__ double s_gx[CGRB_NE_ENVELOPE];
-    __shared__ double s_b[CGRB_ENV_SEGS];
-    __shared__ double s_red[256];
+    __shared__ double s_eax[CGRB_NBINS];
+    __shared__ double s_eay[CGRB_NBINS];
     const int ui = blockIdx.x;
     if (ui >= n_units)
         return;
@@ -95,75 +133,59 @@ __global__ void __launch_bounds__(256) k_energy_tables(const double *__restrict_
     const double opz = 1.0 + u.z, alpha = u.alpha;
     for (int m = threadIdx.x; m < CGRB_NE_ENVELOPE; m += blockDim.x) {
         double x = dt[CGRB_DT_G500_E + m] * opz;
-        double A = dt[CGRB_DT_G500_A + m];
+        double A = dt[CGRB_DT_G500_A + m];   // ea_scale is a constant factor: no effect on the energy law
         s_gx[m] = x;
         s_gl[m] = (A > 0.0) ? log(A) + alpha * log(x) : -INFINITY;
     }
-    // Amax over the table nodes and the two domain ends
-    double am = 0.0;
-    for (int m = threadIdx.x; m < CGRB_NBINS; m += blockDim.x)
-        am = fmax(am, dt[CGRB_DT_EA_Y + m]);
-    if (threadIdx.x == 0) {
-        am = fmax(am, interp1(dt + CGRB_DT_EA_X, dt + CGRB_DT_EA_Y, CGRB_NBINS, dt[CGRB_DT_EDGES], interp_extrap));
-        am = fmax(am, interp1(dt + CGRB_DT_EA_X, dt + CGRB_DT_EA_Y, CGRB_NBINS, dt[CGRB_DT_EDGES + CGRB_NBINS],
-                              interp_extrap));
+    for (int m = threadIdx.x; m < CGRB_NBINS; m += blockDim.x) {
+        s_eax[m] = dt[CGRB_DT_EA_X + m];
+        s_eay[m] = dt[CGRB_DT_EA_Y + m];
     }
-    s_red[threadIdx.x] = am;
     __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-        if (threadIdx.x < d)
-            s_red[threadIdx.x] = fmax(s_red[threadIdx.x], s_red[threadIdx.x + d]);
-        __syncthreads();
-    }
-    // range of s = x (1+z) / ec over the unit's photons
     const double emin = dt[CGRB_DT_EDGES], emax = dt[CGRB_DT_EDGES + CGRB_NBINS];
-    double ec0, ec1;
+    const double a = alpha + 1.0;
+    const double u0 = log(emin), du = (log(emax) - u0) / CGRB_ENV_SEGS;
+    if (threadIdx.x < CGRB_ENV_SEGS) {
+        const int j = threadIdx.x;
+        const double xa = (j == 0) ? emin : exp(u0 + j * du);
+        const double xb = (j == CGRB_ENV_SEGS - 1) ? emax : exp(u0 + (j + 1) * du);
+        double gm, am;
+        // bounds taken on a slightly wider interval: x = exp(u) may round one ulp outside the segment
+        segment_max(s_eax, s_eay, interp_extrap, a, xa * (1.0 - 1e-13), xb * (1.0 + 1e-13), &gm, &am);
+        T->xlo[j] = xa;
+        if (j == CGRB_ENV_SEGS - 1)
+            T->xlo[CGRB_ENV_SEGS] = emax;
+        T->logM[j] = (gm > 0.0) ? log(gm) + 1e-9 : -INFINITY;
+        T->logAmax[j] = (am > 0.0) ? log(am) + 1e-9 : -INFINITY;
+    }
+    // grid of w = (1+z)/ec(t) over the unit's photons: row k bounds exp(-x w) by exp(-xlo w_k), w_k <= w
     {
         double ep0 = u.ep_start, ep1 = u.ep_start;
         if (u.kind == 0) {
             ep0 = u.ep_start / (1.0 + u.src_tstart / u.ep_tau);
             ep1 = u.ep_start / (1.0 + u.src_tstop / u.ep_tau);
         }
-        double d = (alpha == -2.0) ? 0.0001 : (2.0 + alpha);
-        ec0 = ep0 / d;
-        ec1 = ep1 / d;
-    }
-    const double w_lo = opz / fmax(ec0, ec1), w_hi = opz / fmin(ec0, ec1);
-    double l_lo = log(emin * w_lo) - 1e-9, l_hi = log(emax * w_hi) + 1e-9;
-    l_hi = fmin(l_hi, log(740.0));           // e^-s underflows beyond: zero weight anyway
-    if (!(l_hi > l_lo + 1e-6))
-        l_hi = l_lo + 1e-6;
-    const double dl = (l_hi - l_lo) / CGRB_ENV_SEGS;
-    const double a = alpha + 1.0;
-    if (threadIdx.x < CGRB_ENV_SEGS) {
-        const int j = threadIdx.x;
-        double la = l_lo + j * dl, lb = l_lo + (j + 1) * dl;
-        double ls;                         // argmax of phi(l) = a l - e^l on [la, lb]
-        if (a > 0.0) {
-            double lpk = log(a);
-            ls = fmin(fmax(lpk, la), lb);
-        } else
-            ls = la;
-        double ss = exp(ls);
-        double b = exp(a * ls - ss);
-        s_b[j] = b;
-        T->inv_b[j] = (b > 0.0) ? 1.0 / b : 0.0;
-        T->lstar[j] = ls;
-        T->sstar[j] = ss;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        T->l0 = l_lo;
-        T->dl = dl;
-        T->inv_dl = 1.0 / dl;
-        T->a = a;
-        T->amax = s_red[0];
-        double acc = 0.0;
-        T->cdf[0] = 0.0;
-        for (int j = 0; j < CGRB_ENV_SEGS; j++) {
-            acc += s_b[j] * dl;
-            T->cdf[j + 1] = acc;
+        const double d = (alpha == -2.0) ? 0.0001 : (2.0 + alpha);
+        const double wa = opz * d / ep0, wb = opz * d / ep1;
+        double lw_lo = log(fmin(wa, wb)) - 1e-9, lw_hi = log(fmax(wa, wb)) + 1e-9;
+        int n_w = (int)min((int64_t)CGRB_ENV_MAXW, max((int64_t)1, u.etab_nw));
+        if (!(lw_hi > lw_lo) || isinf(lw_lo) || isinf(lw_hi)) {     // degenerate spectral evolution
+            n_w = 1;
+            lw_hi = lw_lo + 1.0;
         }
+        const double dlw = (lw_hi - lw_lo) / n_w;
+        for (int k = threadIdx.x; k < CGRB_ENV_MAXW; k += blockDim.x)
+            T->wk[k] = (k < n_w) ? exp(lw_lo + k * dlw) : INFINITY;
+        if (threadIdx.x == 0) {
+            T->n_w = n_w;
+            T->logw0 = lw_lo;
+            T->inv_dlogw = 1.0 / dlw;
+            T->u0 = u0;
+            T->du = du;
+            T->a = a;
+        }
+    }
+    if (threadIdx.x == 0) {
         // upper hull, lines in order of increasing slope (-gx): m = 499 .. 0
         int n = 0;
         for (int m = CGRB_NE_ENVELOPE - 1; m >= 0; m--) {

@@ -917,22 +917,74 @@ __device__ __noinline__ double literal_photon_serial(const cgrb_unit_t &u, const
     }
 }
 
+// rows of the proposal table: row r of the batch belongs to the unit with etab_off <= r < etab_off + n_w;
+// row k of a unit holds the (shifted, unnormalised) cumulative masses of the 256 segments at w = wk[k]:
+//     mass_j = exp(logM[j] - xlo[j] wk[k] - shift),  shift = max_j of the exponent.
+#define ENV_ROW (CGRB_ENV_SEGS + 1)
+__global__ void __launch_bounds__(NT) k_energy_rows(const cgrb_unit_t *__restrict__ units, int n_units,
+                                                    const EnergyUnitTab *__restrict__ etab,
+                                                    double *__restrict__ rows, int64_t n_rows)
+{
+    __shared__ double s_w[NW];
+    __shared__ double s_red[NW];
+    const int64_t r = blockIdx.x;
+    if (r >= n_rows)
+        return;
+    int lo = 0, hi = n_units;               // last unit with etab_off <= r
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (units[mid].etab_off <= r)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const EnergyUnitTab *T = etab + lo;
+    const int k = (int)(r - units[lo].etab_off);
+    const int j = threadIdx.x;               // NT == CGRB_ENV_SEGS
+    double v = -INFINITY;
+    if (k < T->n_w) {
+        const double lm = T->logM[j];
+        if (lm > -INFINITY)
+            v = lm - T->xlo[j] * T->wk[k];
+    }
+    // block max
+    double m = v;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((j & 31) == 0)
+        s_red[j >> 5] = m;
+    __syncthreads();
+    m = s_red[0];
+#pragma unroll
+    for (int q = 1; q < NW; q++)
+        m = fmax(m, s_red[q]);
+    const double e = (v > -INFINITY && m > -INFINITY) ? exp(v - m) : 0.0;
+    double total;
+    const double incl = block_incl_scan(e, s_w, &total);
+    double *row = rows + r * ENV_ROW;
+    row[j] = incl - e;
+    if (j == CGRB_ENV_SEGS - 1)
+        row[CGRB_ENV_SEGS] = incl;
+}
+
 struct EnvSmem {
-    double cdf[CGRB_ENV_SEGS + 1];
-    double inv_b[CGRB_ENV_SEGS];
-    double lstar[CGRB_ENV_SEGS];
-    double sstar[CGRB_ENV_SEGS];
+    double xlo[CGRB_ENV_SEGS];
+    double logM[CGRB_ENV_SEGS];
+    double logAmax[CGRB_ENV_SEGS];
+    double wk[CGRB_ENV_MAXW];
     double hull_w[CGRB_NE_ENVELOPE];
     int hull_m[CGRB_NE_ENVELOPE];
     double eax[CGRB_NBINS];
     double eay[CGRB_NBINS];
 };
 
-__global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__restrict__ dtab,
+__global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__restrict__ dtab,
                                                           const cgrb_unit_t *__restrict__ units,
                                                           const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                           int interp_extrap, cgrb_rng_t rng, int64_t max_trials,
                                                           const EnergyUnitTab *__restrict__ etab,
+                                                          const double *__restrict__ rows,
                                                           const double *__restrict__ times_src,
                                                           double *__restrict__ energy_src,
                                                           int32_t *__restrict__ trials_out, cgrb_counts_t *counts)
@@ -950,13 +1002,14 @@ __global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__res
     const EnergyUnitTab *T = etab + wk.unit;
     if (threadIdx.x == 0)
         u = units[wk.unit];
-    for (int j = threadIdx.x; j <= CGRB_ENV_SEGS; j += NT)
-        sm.cdf[j] = T->cdf[j];
+    const int n_w = T->n_w;
     for (int j = threadIdx.x; j < CGRB_ENV_SEGS; j += NT) {
-        sm.inv_b[j] = T->inv_b[j];
-        sm.lstar[j] = T->lstar[j];
-        sm.sstar[j] = T->sstar[j];
+        sm.xlo[j] = T->xlo[j];
+        sm.logM[j] = T->logM[j];
+        sm.logAmax[j] = T->logAmax[j];
     }
+    for (int j = threadIdx.x; j < n_w; j += NT)
+        sm.wk[j] = T->wk[j];
     const int n_hull = T->n_hull;
     for (int j = threadIdx.x; j < n_hull; j += NT) {
         sm.hull_w[j] = T->hull_w[j];
@@ -968,54 +1021,57 @@ __global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__res
         sm.eax[m] = dt[CGRB_DT_EA_X + m];
         sm.eay[m] = dt[CGRB_DT_EA_Y + m];
     }
-    __syncthreads();
-    const double opz = 1.0 + u.z, alpha = u.alpha;
-    const double emin = dt[CGRB_DT_EDGES], emax = dt[CGRB_DT_EDGES + CGRB_NBINS];
     // loop constants live in shared memory (broadcast loads) to keep the trial loop's registers free
     __shared__ double ck[12];
     if (threadIdx.x == 0) {
-        ck[0] = T->l0;
-        ck[1] = T->dl;
-        ck[2] = T->inv_dl;
-        ck[3] = T->a;
-        ck[4] = T->amax;
-        ck[5] = log(emin);
-        ck[6] = log(emax);
-        ck[7] = (alpha == -2.0) ? 0.0001 : (2.0 + alpha);
+        const double alpha = u.alpha;
+        ck[0] = T->u0;
+        ck[1] = T->du;
+        ck[2] = T->a;
+        ck[3] = T->logw0;
+        ck[4] = T->inv_dlogw;
+        ck[5] = dt[CGRB_DT_EDGES];
+        ck[6] = dt[CGRB_DT_EDGES + CGRB_NBINS];
+        ck[7] = (1.0 + u.z) * ((alpha == -2.0) ? 0.0001 : (2.0 + alpha));     // w = ck[7] / ep
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         EaGuess g0 = make_ea_guess(sm.eax);
         ck[8] = g0.log_x0;
         ck[9] = g0.inv_dlog;
     }
     __syncthreads();
-#define l0 ck[0]
-#define dl ck[1]
-#define inv_dl ck[2]
-#define a ck[3]
-#define amax ck[4]
-#define log_emin ck[5]
-#define log_emax ck[6]
-#define ec_den ck[7]
+#define c_u0 ck[0]
+#define c_du ck[1]
+#define c_a ck[2]
+#define c_logw0 ck[3]
+#define c_inv_dlogw ck[4]
+#define c_emin ck[5]
+#define c_emax ck[6]
+#define c_wnum ck[7]
     EaGuess eg;
     eg.log_x0 = ck[8];
     eg.inv_dlog = ck[9];
+    const double inv_opz = 1.0 / (1.0 + u.z);
+    const double *unit_rows = rows + u.etab_off * ENV_ROW;
 
     int64_t chunk_end = n_src;
     if (w + 1 < n_work && work[w + 1].unit == wk.unit)
         chunk_end = min(n_src, work[w + 1].start);
 
-    // Lane refill: every warp owns a contiguous slice of the chunk; a lane that accepted (about one in
-    // three per round) immediately takes the warp's next photon, so lanes never idle waiting for the
-    // slowest geometric tail of their neighbours.
+    // Lane refill: every warp owns a contiguous slice of the chunk; a lane that accepted immediately takes
+    // the warp's next photon, so no lane idles on a neighbour's geometric tail.
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t per = (chunk_end - wk.start + NW - 1) / NW;
     const int64_t wbeg = wk.start + (int64_t)wid * per, wend = min(wbeg + per, chunk_end);
     int64_t next = wbeg;                 // warp-uniform
     long long my_trials = 0;
-    bool capped = false, active = false;
+    bool capped = false, active = false, violated = false;
     // per-lane photon state
     int64_t i = 0;
     uint32_t j = 0;
-    double logw = 0.0, l_lo = 0.0, l_hi = 0.0, F_lo = 0.0, dF = 0.0, s_idx = 0.0, A5 = 0.0, inv_w = 0.0;
+    const double *row = unit_rows;
+    double wq = 0.0, wkk = 0.0, total = 0.0, s_idx = 0.0, A5 = 0.0, t_clip = 0.0;
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !active);
         if (need) {
@@ -1028,24 +1084,24 @@ __global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__res
                 // pulse amplitude > 0 ?  (norris underflows for t -> 0+; constant CPL is always regular)
                 bool regular = (u.kind != 0) || (t > 0.0 && (u.trise / t + t / u.tdecay) < 700.0 && u.peak_flux > 0.0);
                 const double ep = (u.kind == 0) ? u.ep_start / (1.0 + t / u.ep_tau) : u.ep_start;
-                const double wq = opz * ec_den / ep;            // (1+z) / ec
-                logw = log(wq);
-                l_lo = log_emin + logw;
-                l_hi = log_emax + logw;
-                // piecewise-linear CDF of the envelope at the truncation points
-                double q = (l_lo - l0) * inv_dl;
-                int k = max(0, min((int)q, CGRB_ENV_SEGS - 1));
-                F_lo = sm.cdf[k] + (sm.cdf[k + 1] - sm.cdf[k]) * fmin(fmax(q - k, 0.0), 1.0);
-                q = (l_hi - l0) * inv_dl;
-                k = max(0, min((int)q, CGRB_ENV_SEGS - 1));
-                dF = sm.cdf[k] + (sm.cdf[k + 1] - sm.cdf[k]) * fmin(fmax(q - k, 0.0), 1.0) - F_lo;
-                if (!(dF > 0.0))
+                wq = c_wnum / ep;                               // (1+z) / ec
+                int k = (int)floor((log(wq) - c_logw0) * c_inv_dlogw);
+                k = max(0, min(k, n_w - 1));
+                if (sm.wk[k] > wq)
+                    k--;
+                if (k < 0 || !(sm.wk[max(k, 0)] <= wq))         // w below the unit's grid (or NaN)
+                    regular = false;
+                k = max(k, 0);
+                wkk = sm.wk[k];
+                row = unit_rows + (size_t)k * ENV_ROW;
+                total = __ldg(row + CGRB_ENV_SEGS);
+                if (!(total > 0.0) || isinf(total))
                     regular = false;
                 if (regular) {
-                    const int idx = hull_lookup(sm.hull_m, sm.hull_w, n_hull, ec_den / ep);
+                    const int idx = hull_lookup(sm.hull_m, sm.hull_w, n_hull, wq * inv_opz);
                     s_idx = dt[CGRB_DT_G500_E + idx] * wq;
                     A5 = 5.0 * dt[CGRB_DT_G500_A + idx];
-                    inv_w = 1.0 / wq;
+                    t_clip = log(A5) - s_idx;
                     active = true;
                 } else {
                     // degenerate photon: the literal loop, right here (rare)
@@ -1067,26 +1123,30 @@ __global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__res
         if (active) {
             Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
             const double U = u53(p.x, p.y), V = u53(p.z, p.w);
-            const double y = F_lo + U * dF;
-            int lo = 0, hi = CGRB_ENV_SEGS;         // segment: cdf[lo] <= y < cdf[lo+1]
+            const double y = U * total;
+            int lo = 0, hi = CGRB_ENV_SEGS;         // segment: row[lo] <= y < row[lo+1]
 #pragma unroll
             for (int it = 0; it < 8; it++) {        // CGRB_ENV_SEGS = 2^8
-                int mid = (lo + hi) >> 1;
-                if (sm.cdf[mid] <= y)
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(row + mid) <= y)
                     lo = mid;
                 else
                     hi = mid;
             }
-            double l = l0 + lo * dl + (y - sm.cdf[lo]) * sm.inv_b[lo];
-            l = fmin(fmax(l, l_lo), l_hi);
-            const double s = exp(l);
-            const double x = s * inv_w;
-            const double r1 = exp(a * (l - sm.lstar[lo]) - (s - sm.sstar[lo]));
-            double A = fmax(interp_guess(sm.eax, sm.eay, CGRB_NBINS, x, l - logw, eg, interp_extrap), 0.0);
-            if (!(s >= s_idx && A <= A5))
+            const double c0 = __ldg(row + lo), c1 = __ldg(row + lo + 1);
+            const double fr = fmin(fmax((y - c0) / (c1 - c0), 0.0), 1.0);
+            const double uu = c_u0 + ((double)lo + fr) * c_du;
+            const double x = fmin(fmax(exp(uu), c_emin), c_emax);
+            const double s = x * wq;
+            double A = fmax(interp_guess(sm.eax, sm.eay, CGRB_NBINS, x, uu, eg, interp_extrap), 0.0);
+            const double xl = sm.xlo[lo];
+            if (sm.logAmax[lo] - xl * wq > t_clip)
                 A = fmin(A, A5 * exp(s - s_idx));   // the literal envelope clips f here
+            // target x^(a) A e^{-s}  <=  envelope  M_lo e^{-xlo w_k}
+            const double ratio = A * exp(c_a * uu - s - sm.logM[lo] + xl * wkk);
             j++;
-            const bool acc = V * amax <= r1 * A;
+            violated |= ratio > 1.000001;           // the envelope must dominate the target (self-check)
+            const bool acc = V <= ratio;
             const bool cap = !acc && max_trials > 0 && (int64_t)j >= max_trials;
             if (acc || cap) {
                 energy_src[u.src_off + i] = acc ? x : nan("");
@@ -1098,19 +1158,21 @@ __global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__res
             }
         }
     }
-#undef l0
-#undef dl
-#undef inv_dl
-#undef a
-#undef amax
-#undef log_emin
-#undef log_emax
-#undef ec_den
+#undef c_u0
+#undef c_du
+#undef c_a
+#undef c_logw0
+#undef c_inv_dlogw
+#undef c_emin
+#undef c_emax
+#undef c_wnum
     const long long tot = block_sum_ll(my_trials, s_wl);
     if (threadIdx.x == 0 && tot)
         atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)tot);
     if (capped)
         atomicOr(&counts[wk.unit].status, CGRB_ST_TRIAL_CAP);
+    if (violated)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_ENVELOPE);
 }
 
 // ==========================================================================================
@@ -1119,39 +1181,53 @@ __global__ void __launch_bounds__(NT, 2) k_sample_energy_env(const double *__res
 // The detector's 140x128 cumulative matrix (143,360 B) is staged into shared memory with one
 // mbarrier-tracked bulk-async (TMA) copy per CTA when the chunk is large enough to amortise it.
 // ==========================================================================================
+// lower bound (first index with xs[j] >= v) over n <= 255 ascending entries in a fixed 8 probes:
+// no data-dependent trip count, so a warp never diverges on it
+__device__ __forceinline__ int lower_bound_255(const double *xs, int n, double v)
+{
+    int pos = 0;
+#pragma unroll
+    for (int step = 128; step >= 1; step >>= 1) {
+        const int q = pos + step;
+        if (q <= n && xs[q - 1] < v)
+            pos = q;
+    }
+    return pos;
+}
+
 __device__ __forceinline__ int nearest_cdf(const double *row, double r)
 {
-    // j = first index with row[j] >= r
-    int lo = 0, hi = CGRB_NCHAN;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (row[mid] < r)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    int jhi = min(lo, CGRB_NCHAN - 1);
-    int jlo = max(lo - 1, 0);
-    double dlo = fabs(row[jlo] - r), dhi = fabs(row[jhi] - r);
+    // lo = first index with row[j] >= r  (0 .. 128)
+    int lo = 0;
+#pragma unroll
+    for (int step = 64; step >= 1; step >>= 1)
+        if (row[lo + step - 1] < r)
+            lo += step;
+    if (row[lo] < r)
+        lo++;
+    const int jhi = min(lo, CGRB_NCHAN - 1);
+    const int jlo = max(lo - 1, 0);
+    const double vlo = row[jlo], vhi = row[jhi];
+    const double dlo = fabs(vlo - r), dhi = fabs(vhi - r);
     int pick = (dhi < dlo) ? jhi : jlo;            // tie -> lower index
-    double v = row[pick];
-    // first index holding that value
-    lo = 0;
-    hi = pick;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (row[mid] < v)
-            lo = mid + 1;
-        else
-            hi = mid;
+    const double v = (dhi < dlo) ? vhi : vlo;
+    // np.argmin returns the FIRST index holding the nearest value (plateaus of zero-probability channels)
+    if (pick > 0 && !(row[pick - 1] < v)) {
+        int f = 0;
+#pragma unroll
+        for (int step = 64; step >= 1; step >>= 1)
+            if (row[f + step - 1] < v)
+                f += step;
+        pick = f;
     }
-    return lo;
+    return pick;
 }
 
 #define CUM_BYTES (CGRB_NBINS * CGRB_NCHAN * 8)
-#define DIGITIZE_STAGE_MIN 1024
+#define DIGITIZE_STAGE_MIN 4096
+#define DIGITIZE_NT 1024     // one CTA per SM (the staged matrix takes 143 KB of its shared memory): 32 warps
 
-__global__ void __launch_bounds__(NT) k_digitize(const double *__restrict__ dtab,
+__global__ void __launch_bounds__(DIGITIZE_NT) k_digitize(const double *__restrict__ dtab,
                                                  const cgrb_unit_t *__restrict__ units,
                                                  const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                  cgrb_rng_t rng, const double *__restrict__ energy_src,
@@ -1193,7 +1269,7 @@ __global__ void __launch_bounds__(NT) k_digitize(const double *__restrict__ dtab
                 "l"(src + (size_t)c * piece), "r"(piece), "r"(bar)
                 : "memory");
     }
-    for (int m = threadIdx.x; m <= CGRB_NBINS; m += NT)
+    for (int m = threadIdx.x; m <= CGRB_NBINS; m += DIGITIZE_NT)
         s_edges[m] = dt[CGRB_DT_EDGES + m];
     __syncthreads();
     if (staged) {
@@ -1213,9 +1289,9 @@ __global__ void __launch_bounds__(NT) k_digitize(const double *__restrict__ dtab
     }
     const double *cum = staged ? s_cum : dt + CGRB_DT_CUM;
 
-    for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += NT) {
+    for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += DIGITIZE_NT) {
         const double e = energy_src[u->src_off + i];
-        int idx = searchsorted_left(s_edges, CGRB_NBINS + 1, e) - 1;      // response.py:14
+        int idx = lower_bound_255(s_edges, CGRB_NBINS + 1, e) - 1;        // searchsorted 'left', response.py:14
         if (idx < 0)
             idx += CGRB_NBINS;                                            // python negative index
         if (idx > CGRB_NBINS - 1)
@@ -1692,16 +1768,21 @@ int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
     return check_launch("cgrb_sample_energy");
 }
 
-int64_t cgrb_energy_workspace_bytes(int n_units) { return (int64_t)sizeof(EnergyUnitTab) * (n_units > 0 ? n_units : 0); }
+int64_t cgrb_energy_workspace_bytes(int n_units, int64_t n_rows)
+{
+    int64_t tabs = (int64_t)sizeof(EnergyUnitTab) * (n_units > 0 ? n_units : 0);
+    tabs = (tabs + 255) / 256 * 256;
+    return tabs + (int64_t)sizeof(double) * ENV_ROW * (n_rows > 0 ? n_rows : 0);
+}
 
 int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                                 const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
-                                const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace,
+                                const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
                                 const double *d_times_src, double *d_energy_src, int32_t *d_trials,
                                 cgrb_counts_t *d_counts, void *stream)
 {
     if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_src || !d_energy_src ||
-        !d_counts || !d_workspace)
+        !d_counts || !d_workspace || n_rows < n_units)
         return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: bad argument%s");
     if (interp_extrap != 0 && interp_extrap != 1)
         return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: interp_extrap must be 0 (linear) or 1 (clamp)%s");
@@ -1713,10 +1794,13 @@ int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units
                     "cgrb_sample_energy_envelope: injected uniforms replay the literal sampler; use cgrb_sample_energy%s");
     cudaStream_t s = (cudaStream_t)stream;
     EnergyUnitTab *etab = (EnergyUnitTab *)d_workspace;
+    int64_t tabs = ((int64_t)sizeof(EnergyUnitTab) * n_units + 255) / 256 * 256;
+    double *rows = (double *)((char *)d_workspace + tabs);
     LAUNCH("k_energy_tables", s, k_energy_tables<<<n_units, 256, 0, s>>>(d_dtab, d_units, n_units, interp_extrap, etab));
+    LAUNCH("k_energy_rows", s, k_energy_rows<<<(unsigned)n_rows, NT, 0, s>>>(d_units, n_units, etab, rows, n_rows));
     LAUNCH("k_sample_energy_env", s, k_sample_energy_env<<<(unsigned)n_work, NT, 0, s>>>(
-        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, d_times_src, d_energy_src, d_trials,
-        d_counts));
+        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, rows, d_times_src, d_energy_src,
+        d_trials, d_counts));
     return check_launch("cgrb_sample_energy_envelope");
 }
 
@@ -1738,7 +1822,7 @@ int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
             return fail(CGRB_E_CUDA, "cgrb_digitize: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    LAUNCH("k_digitize", (cudaStream_t)stream, k_digitize<<<(unsigned)n_work, NT, smem, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
+    LAUNCH("k_digitize", (cudaStream_t)stream, k_digitize<<<(unsigned)n_work, DIGITIZE_NT, smem, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
                                                                      d_energy_src, d_pha_src, d_counts));
     return check_launch("cgrb_digitize");
 }

@@ -23,7 +23,7 @@ from ._capi import COUNTS_DTYPE, UNIT_DTYPE, WORK_DTYPE, RngDesc
 
 DEFAULT_SEED = 0x00C0560612B
 ENERGY_CHUNK = 1024          # photons per CTA work item of the energy kernels
-DIGITIZE_CHUNK = 8192        # photons per CTA of the digitize kernel (amortises staging the 143 KB matrix)
+DIGITIZE_CHUNK = 65536       # photons per CTA of the digitize kernel (amortises staging the 143 KB matrix)
 DEFAULT_MAX_TRIALS = 1 << 22
 
 
@@ -145,6 +145,7 @@ class Engine(object):
         self.energy_sampler = energy_sampler
         self.squeeze = bool(squeeze)
         self.squeeze_ratio, self.squeeze_min_candidates, self.squeeze_max_nodes = 8, 2048, 1 << 16
+        self.energy_row_spacing, self.energy_candidates_per_row = 0.02, 256
         self._call_counter = 0
         self._dtab_cache = {}
         self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
@@ -270,6 +271,18 @@ class Engine(object):
         units["tab_n"] = tab_n
         units["tab_off"] = np.concatenate(([0], np.cumsum(tab_n)[:-1]))
         b.n_tab_nodes = int(tab_n.sum())
+        # rows of the energy proposal table: a grid of w = (1+z)/ec(t) over the burst, ~2 % apart for long
+        # units, fewer for short ones (a row costs 256 exps to build, about as much as 100 photons)
+        with np.errstate(all="ignore"):
+            span = np.where(units["kind"] == 0,
+                            np.abs(np.log1p(units["src_tstop"] / units["ep_tau"])
+                                   - np.log1p(units["src_tstart"] / units["ep_tau"])), 0.0)
+        span = np.nan_to_num(span, nan=0.0, posinf=0.0)
+        need = np.ceil(span / self.energy_row_spacing).astype(np.int64) + 1
+        nw = np.clip(np.minimum(need, units["src_cap"] // self.energy_candidates_per_row), 1, _capi.ENV_MAXW)
+        units["etab_nw"] = nw
+        units["etab_off"] = np.concatenate(([0], np.cumsum(nw)[:-1]))
+        b.n_etab_rows = int(nw.sum())
         b.n_src_slots = int(np.sum(units["src_cap"] + 1))
         b.n_bkg_slots = int(np.sum(units["bkg_cap"] + 1))
         b.n_tot_slots = b.n_src_slots + b.n_bkg_slots
@@ -397,15 +410,15 @@ class Engine(object):
         desc = self._rng_desc(rng, b, "energy")
         if sampler == "envelope":
             if "etab" not in t:
-                t["etab"] = self.empty(self.lib.cgrb_energy_workspace_bytes(b.n_units), torch.uint8)
+                t["etab"] = self.empty(self.lib.cgrb_energy_workspace_bytes(b.n_units, b.n_etab_rows), torch.uint8)
             _capi.check(
                 self.lib.cgrb_sample_energy_envelope(
                     b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
                     self._extrap_code(b.interp_extrap), C.byref(desc), int(max_trials), t["etab"].data_ptr(),
-                    t["times_src"].data_ptr(), t["energy_src"].data_ptr(),
+                    b.n_etab_rows, t["times_src"].data_ptr(), t["energy_src"].data_ptr(),
                     tr.data_ptr() if want_trials else None, b.d_counts.data_ptr(), self.stream),
                 "cgrb_sample_energy_envelope")
-            self.launches += 2
+            self.launches += 3
             return
         _capi.check(
             self.lib.cgrb_sample_energy(
@@ -497,7 +510,7 @@ class Engine(object):
         bad = np.nonzero(c["status"])[0]
         if len(bad):
             names = {1: "source capacity", 2: "background capacity", 4: "injected uniforms exhausted",
-                     8: "trial cap", 16: "output capacity"}
+                     8: "trial cap", 16: "output capacity", 32: "energy envelope violated"}
             ui = int(bad[0])
             st = int(c["status"][ui])
             what = ", ".join(v for k, v in names.items() if st & k)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CGRB_ABI_VERSION 2
+#define CGRB_ABI_VERSION 3
 
 /* error codes */
 #define CGRB_OK 0
@@ -44,6 +44,7 @@ extern "C" {
 #define CGRB_ST_UNIFORMS_EXHAUSTED 4u /* injected uniform stream too short                   */
 #define CGRB_ST_TRIAL_CAP 8u         /* energy rejection hit max_trials                     */
 #define CGRB_ST_OUT_CAPACITY 16u     /* an output buffer was too small                      */
+#define CGRB_ST_ENVELOPE 32u         /* energy envelope failed to dominate the target (bug)  */
 
 /* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
 #define CGRB_NBINS 140
@@ -72,7 +73,7 @@ extern "C" {
 #define CGRB_DT_CUM 1720       /* [140*128] row-normalised cumulative matrix (16-byte aligned: 13760 B) */
 #define CGRB_DT_SIZE (1720 + 140 * 128) /* 19640 doubles = 157120 B per detector                     */
 
-/* one (GRB, detector) work unit; 208 bytes, device array uploaded by the caller */
+/* one (GRB, detector) work unit; 224 bytes, device array uploaded by the caller */
 typedef struct {
     int32_t kind;          /* 0 = CPLSourceFunction (cpl_functions.py), 1 = ConstantCPL (cpl_constant_functions.py) */
     int32_t det;           /* detector table index into d_dtab                                     */
@@ -103,6 +104,8 @@ typedef struct {
     int64_t tab_n;         /* nodes of the squeeze table on [src_tstart, src_tstop]; 0 = no squeeze  */
     double ea_scale;       /* multiplies the detector table's effective area (per-GRB viewing-angle
                               factor on a shared base DRM); 1.0 = use the table as is              */
+    int64_t etab_off;      /* first row of this unit in the energy proposal table (cgrb_sample_energy_envelope) */
+    int64_t etab_nw;       /* rows of this unit (grid of (1+z)/ec(t) over the burst), 1 .. 256           */
 } cgrb_unit_t;
 
 #define CGRB_UNIT_NO_SOURCE 1u
@@ -215,14 +218,19 @@ int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
                        double *d_energy_src, int32_t *d_trials, cgrb_counts_t *d_counts, void *stream);
 
 /* Same contract and the same output DISTRIBUTION as cgrb_sample_energy, Philox only: exact
- * rejection sampling of the literal sampler's output density from a tight per-unit envelope
- * (csrc/cgrb_energy.cuh) -- a few trials per photon instead of tens to hundreds.  d_workspace:
- * cgrb_energy_workspace_bytes(n_units) bytes of device memory.  Injected uniforms replay the
+ * rejection sampling of the literal sampler's output density
+ *     h(x) ~ x^alpha min(A(x) e^(-x w), 5 A(E_idx) e^(-E_idx w)),   w = (1+z)/ec(t)
+ * from a per-unit tabulated envelope (csrc/cgrb_energy.cuh): 256 equal segments in log x, each bounded
+ * by max x^(alpha+1) A(x) over the segment (A is piecewise linear: exact) times exp(-x_lo w_k), on a
+ * grid of etab_nw values w_k <= w covering the unit's spectral evolution; one cumulative row per w_k.
+ * ~1.1-1.3 trials per photon instead of tens to hundreds.  Every unit owns etab_nw >= 1 rows starting
+ * at row etab_off (ascending); n_rows = total rows of the batch.  d_workspace:
+ * cgrb_energy_workspace_bytes(n_units, n_rows) bytes of device memory.  Injected uniforms replay the
  * reference's stream and therefore must use cgrb_sample_energy (returns CGRB_E_UNSUPPORTED). */
-int64_t cgrb_energy_workspace_bytes(int n_units);
+int64_t cgrb_energy_workspace_bytes(int n_units, int64_t n_rows);
 int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                                 const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
-                                const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace,
+                                const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
                                 const double *d_times_src, double *d_energy_src, int32_t *d_trials,
                                 cgrb_counts_t *d_counts, void *stream);
 

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert _capi.UNIT_DTYPE.itemsize == 208 and _capi.COUNTS_DTYPE.itemsize == 64 and _capi.WORK_DTYPE.itemsize == 16
+    assert _capi.UNIT_DTYPE.itemsize == 224 and _capi.COUNTS_DTYPE.itemsize == 64 and _capi.WORK_DTYPE.itemsize == 16
     src = open(os.path.join(ROOT, "include", "cosmogrb_b200.h")).read()
     for name in ("EDGES", "EA_X", "EA_Y", "BKG_CDF", "G75_E", "G75_A", "G500_E", "G500_A", "CUM"):
         m = re.search(rf"#define CGRB_DT_{name} (\d+)", src)
