@@ -191,7 +191,8 @@ KERNEL_BYTES = {
     "k_combine": 18.0,          # reads 9 B, writes 9 B per merged event
     "k_deadtime_count": 9.0,    # reads 9 B per merged event
     "k_deadtime_write": 18.0,   # reads 9 B, writes <= 9 B per merged event
-    "k_source_thin": 8.0,       # writes one f64 per accepted source event (per candidate: 0 B)
+    "k_source_thin": 16.0,      # reads the stored running gap sum, writes the accepted time (per source event)
+    "k_gap_prefix": 8.0,        # writes one f64 running gap sum per candidate (counted per event here)
     "k_source_gather": 16.0,    # moves one f64 per source event
     "k_sample_energy": 16.0,    # reads time, writes energy per source event
     "k_digitize": 9.0,          # reads energy, writes channel per source event

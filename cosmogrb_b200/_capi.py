@@ -35,7 +35,8 @@ DT_G75_A = 640
 DT_G500_E = 720
 DT_G500_A = 1220
 DT_CUM = 1720
-DT_SIZE = 1720 + NBINS * NCHAN
+DT_GUIDE = 1720 + NBINS * NCHAN           # NBINS*NCHAN bytes of uint8 search guides
+DT_SIZE = DT_GUIDE + NBINS * NCHAN // 8
 
 ST_SRC_CAPACITY = 1
 ST_BKG_CAPACITY = 2
@@ -149,7 +150,7 @@ def load():
     lib.cgrb_sample_energy.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, vp, vp, vp, vp]
     lib.cgrb_energy_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_energy_workspace_bytes.restype = i64
-    lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, i64, vp, vp, vp, vp, vp]
+    lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.cgrb_digitize.argtypes = [vp, vp, i32, vp, i64, rp, vp, vp, vp, vp]
     lib.cgrb_sample_background.argtypes = [vp, vp, i32, vp, i64, vp, rp, rp, vp, vp, vp, vp, vp, vp]
     lib.cgrb_background_channels.argtypes = [vp, i32, C.c_uint32, rp, i64, vp, vp]

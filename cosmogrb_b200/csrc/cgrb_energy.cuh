@@ -33,14 +33,18 @@ struct EnergyUnitTab {
     int n_w;                           // rows of the unit's proposal table (grid of w = (1+z)/ec)
     double hull_w[CGRB_NE_ENVELOPE];
     int hull_m[CGRB_NE_ENVELOPE];
+    double hull_E[CGRB_NE_ENVELOPE];   // grid energy E_m of hull entry k (observer frame)
+    double hull_lA5[CGRB_NE_ENVELOPE]; // log(5 A(E_m)): the literal envelope's constant C = 5 max f
     // proposal: CGRB_ENV_SEGS equal segments in u = log x on [log emin, log emax]
     double u0, du;
     double a;                          // alpha + 1
     double logw0, inv_dlogw;           // row k covers w in [wk[k], wk[k+1])
     double xlo[CGRB_ENV_SEGS + 1];     // segment edges in x (xlo[0] = emin, xlo[SEGS] = emax)
     double logM[CGRB_ENV_SEGS];        // log max over the segment of x^(alpha+1) max(A(x), 0)  (-inf: none)
+    double invMx[CGRB_ENV_SEGS];       // xlo^(alpha+1) / M: x^(alpha+1) / M = invMx exp((alpha+1) z), x = xlo e^z
     double logAmax[CGRB_ENV_SEGS];     // log max over the segment of max(A(x), 0)
     double wk[CGRB_ENV_MAXW];          // lower edges of the w rows
+    int kn[CGRB_ENV_SEGS];             // first effective-area node above the segment's lower edge
 };
 
 // interp(ea_x, ea_y, v) with a log-uniform first guess for the bracket (the bin means of
@@ -155,7 +159,9 @@ __global__ void __launch_bounds__(256) k_energy_tables(const double *__restrict_
         T->xlo[j] = xa;
         if (j == CGRB_ENV_SEGS - 1)
             T->xlo[CGRB_ENV_SEGS] = emax;
+        T->kn[j] = searchsorted_right(s_eax, CGRB_NBINS, xa);
         T->logM[j] = (gm > 0.0) ? log(gm) + 1e-9 : -INFINITY;
+        T->invMx[j] = (gm > 0.0) ? exp(a * log(xa) - (log(gm) + 1e-9)) : 0.0;
         T->logAmax[j] = (am > 0.0) ? log(am) + 1e-9 : -INFINITY;
     }
     // grid of w = (1+z)/ec(t) over the unit's photons: row k bounds exp(-x w) by exp(-xlo w_k), w_k <= w
@@ -185,29 +191,42 @@ __global__ void __launch_bounds__(256) k_energy_tables(const double *__restrict_
             T->a = a;
         }
     }
+    // upper hull of the 500 lines, built by one thread in shared memory (lines in order of increasing
+    // slope -gx: m = 499 .. 0), then written out by all
+    __shared__ double s_hw[CGRB_NE_ENVELOPE];
+    __shared__ int s_hm[CGRB_NE_ENVELOPE];
+    __shared__ int s_nh;
     if (threadIdx.x == 0) {
-        // upper hull, lines in order of increasing slope (-gx): m = 499 .. 0
         int n = 0;
         for (int m = CGRB_NE_ENVELOPE - 1; m >= 0; m--) {
             if (!(s_gl[m] > -INFINITY))
                 continue;
             double wx = -INFINITY;
             while (n > 0) {
-                int t = T->hull_m[n - 1];
+                int t = s_hm[n - 1];
                 // line m overtakes line t (gx[t] > gx[m]) for w > (gl[t] - gl[m]) / (gx[t] - gx[m])
                 wx = (s_gl[t] - s_gl[m]) / (s_gx[t] - s_gx[m]);
-                if (wx <= T->hull_w[n - 1])
+                if (wx <= s_hw[n - 1])
                     n--;            // t never wins (ties resolve to the lower m, like np.argmax)
                 else
                     break;
             }
             if (n == 0)
                 wx = -INFINITY;
-            T->hull_m[n] = m;
-            T->hull_w[n] = wx;
+            s_hm[n] = m;
+            s_hw[n] = wx;
             n++;
         }
+        s_nh = n;
         T->n_hull = n;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < s_nh; k += blockDim.x) {
+        const int m = s_hm[k];
+        T->hull_m[k] = m;
+        T->hull_w[k] = s_hw[k];
+        T->hull_E[k] = dt[CGRB_DT_G500_E + m];
+        T->hull_lA5[k] = log(5.0 * dt[CGRB_DT_G500_A + m]);
     }
 }
 

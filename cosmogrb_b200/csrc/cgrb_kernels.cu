@@ -138,37 +138,70 @@ __device__ __forceinline__ long long block_sum_ll(long long v, long long *s_w)
     return t;
 }
 
-// thinning uniforms of candidate k: u1 -> gap, u2 -> acceptance (source) / unused (background)
-struct ThinDraw {
-    double u1, u2;
+// exclusive block scan of doubles (sum of the values of the threads before this one, fixed association)
+__device__ __forceinline__ double block_excl_scan(double v, double *s_w, double *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double incl = warp_incl_scan(v, lane);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0)
+        excl = 0.0;
+    if (lane == 31)
+        s_w[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        double w = (lane < NW) ? s_w[lane] : 0.0;
+        w = warp_incl_scan(w, lane);
+        if (lane < NW)
+            s_w[lane] = w;
+    }
+    __syncthreads();
+    const double prefix = (wid > 0) ? s_w[wid - 1] : 0.0;
+    *total = s_w[NW - 1];
+    const double r = prefix + excl;
+    __syncthreads();
+    return r;
+}
+
+// Thinning uniforms.  Candidate k of a unit consumes u1 (gap) and u2 (acceptance test for the source,
+// channel draw for the background).  Under Philox one call serves the candidate PAIR (2m, 2m+1):
+// counter (index m, sub 0) -> (u1 of 2m, u1 of 2m+1), (index m, sub 1) -> (u2 of 2m, u2 of 2m+1), so
+// the gap pass and the decision pass each cost half a Philox call per candidate.  Injected streams
+// keep the reference's order u1, u2, u1, u2, ... (Appendix A of SURVEY.md): candidate k reads
+// u[2k], u[2k+1]; the stream may end on an odd count.
+struct PairDraw {
+    double a, b;        // values for candidates 2m and 2m+1
     bool exhausted;
 };
-__device__ __forceinline__ ThinDraw thin_draw(const cgrb_rng_t &rng, int unit, uint32_t stream_id,
-                                              uint32_t stage, int64_t k)
+__device__ __forceinline__ double injected_thin_uniform(const cgrb_rng_t &rng, int64_t off, int64_t len, int64_t k,
+                                                        int which, bool *exhausted)
 {
-    ThinDraw d;
+    const int64_t pos = 2 * k + which;
+    if (pos < len)
+        return rng.d_u[off + pos];
+    if (which == 1)
+        return 0.5;                 // never consulted: the candidate's u1 was the last uniform or beyond
+    *exhausted = true;
+    return 0.0;                     // -log(0) = +inf: terminates the unit
+}
+__device__ __forceinline__ PairDraw pair_draw(const cgrb_rng_t &rng, int unit, uint32_t stream_id, uint32_t stage,
+                                              int64_t m, int which)
+{
+    PairDraw d;
     d.exhausted = false;
     if (rng.mode == 0) {
-        Philox4 p = philox_at(make_key(rng.seed), stream_id, stage, (uint64_t)k, 0u);
-        d.u1 = u53(p.x, p.y);
-        d.u2 = u53(p.z, p.w);
+        Philox4 p = philox_at(make_key(rng.seed), stream_id, stage, (uint64_t)m, (uint32_t)which);
+        d.a = u53(p.x, p.y);
+        d.b = u53(p.z, p.w);
     } else {
-        int64_t off = rng.d_off ? rng.d_off[unit] : 0;
-        int64_t len = rng.d_len ? rng.d_len[unit] : ((int64_t)1 << 62);
-        if (2 * k + 1 < len) {
-            d.u1 = rng.d_u[off + 2 * k];
-            d.u2 = rng.d_u[off + 2 * k + 1];
-        } else if (2 * k < len) {   // the reference's stream ends on an odd count (Appendix A)
-            d.u1 = rng.d_u[off + 2 * k];
-            d.u2 = 0.5;
-        } else {
-            d.u1 = 0.0;             // -log(0) = +inf: terminates the unit
-            d.u2 = 0.5;
-            d.exhausted = true;
-        }
+        const int64_t off = rng.d_off ? rng.d_off[unit] : 0;
+        const int64_t len = rng.d_len ? rng.d_len[unit] : ((int64_t)1 << 62);
+        d.a = injected_thin_uniform(rng, off, len, 2 * m, which, &d.exhausted);
+        d.b = injected_thin_uniform(rng, off, len, 2 * m + 1, which, &d.exhausted);
     }
     return d;
 }
+#define THIN_TILE (2 * NT)      // candidates per tile: two per thread
 
 // per-unit tables for lambda(t): lambda = norm * ec^-alpha * sum_m c_m exp(-x_m / ec)
 struct LambdaTab {
@@ -345,14 +378,16 @@ __global__ void __launch_bounds__(NT) k_thin_margins(const cgrb_unit_t *__restri
 }
 
 // ==========================================================================================
-// thinning pass 1: sum of exponential gaps of each segment, in exactly the association order
-// that pass 3 uses for its running time, so that segment boundaries are exactly consistent.
+// thinning pass 1: exponential gaps of a segment, their running sum INSIDE the segment (stored: the
+// candidate's arrival time minus the segment's start time) and the segment total.  Pass 2 turns the
+// totals into segment start times, pass 3 adds the start time -- no gap is drawn twice.
+// The summation order is fixed (pairs, tiles of THIN_TILE, segments of CGRB_SEG), so times are reproducible.
 // ==========================================================================================
-template <int WHICH>  // 0 = source, 1 = background
-__global__ void __launch_bounds__(NT) k_gap_sums(const cgrb_unit_t *__restrict__ units,
-                                                 const cgrb_work_t *__restrict__ work, int64_t n_work,
-                                                 cgrb_rng_t rng, double *__restrict__ segsum,
-                                                 cgrb_counts_t *counts)
+template <int WHICH>  // 0 = source (prefix -> stage at src_off), 1 = background (prefix -> times_bkg at bkg_off + 1)
+__global__ void __launch_bounds__(NT) k_gap_prefix(const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   cgrb_rng_t rng, double *__restrict__ segsum,
+                                                   double *__restrict__ prefix_out, cgrb_counts_t *counts)
 {
     __shared__ double s_w[NW];
     const int64_t w = blockIdx.x;
@@ -366,19 +401,27 @@ __global__ void __launch_bounds__(NT) k_gap_sums(const cgrb_unit_t *__restrict__
     const uint32_t stage = (WHICH == 0) ? ST_SRC_TIME : ST_BKG;
     const uint32_t sid = u->stream_id;
     const int64_t n = min((int64_t)CGRB_SEG, cap - wk.start);
+    double *out = prefix_out + ((WHICH == 0) ? u->src_off : u->bkg_off + 1) + wk.start;
     double carry = 0.0;
     bool exhausted = false;
-    for (int64_t base = 0; base < n; base += NT) {
-        int64_t k = wk.start + base + threadIdx.x;
-        double gap = 0.0;
-        if (base + threadIdx.x < n) {
-            ThinDraw d = thin_draw(rng, wk.unit, sid, stage, k);
-            gap = -(inv_f * log(d.u1));      // time - (1/fmax) * log(u)  cpl_functions.py:160
+    for (int64_t base = 0; base < n; base += THIN_TILE) {
+        const int64_t j0 = base + 2 * threadIdx.x;          // wk.start and base are even
+        double g0 = 0.0, g1 = 0.0;
+        if (j0 < n) {
+            PairDraw d = pair_draw(rng, wk.unit, sid, stage, (wk.start + j0) >> 1, 0);
+            g0 = -(inv_f * log(d.a));                        // time - (1/fmax) * log(u)  cpl_functions.py:160
+            if (j0 + 1 < n)
+                g1 = -(inv_f * log(d.b));
             exhausted |= d.exhausted;
         }
         double total;
-        (void)block_incl_scan(gap, s_w, &total);
-        carry = carry + total;   // no early exit: same association order as pass 3
+        const double excl = block_excl_scan(g0 + g1, s_w, &total);
+        const double p0 = (carry + excl) + g0, p1 = p0 + g1;
+        if (j0 < n)
+            out[j0] = p0;
+        if (j0 + 1 < n)
+            out[j0 + 1] = p1;
+        carry = carry + total;
     }
     if (threadIdx.x == 0)
         segsum[w] = carry;
@@ -420,21 +463,46 @@ __global__ void __launch_bounds__(128) k_seg_scan(const cgrb_unit_t *__restrict_
 }
 
 // ==========================================================================================
-// source thinning pass 3 (cpl_functions.py:134-188): candidate times by block scan, lambda(t),
-// acceptance, ordered compaction of accepted times into the segment's staging slots.
+// source thinning pass 3 (cpl_functions.py:134-188): candidate time = segment start + stored running
+// sum, acceptance by the squeeze table or the exact lambda(t), ordered compaction of the accepted
+// times -- in place, into the head of the segment's own slots of `stage`.
 // ==========================================================================================
-__global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ dtab,
+// the exact test is rare under the squeeze table: kept out of line so the common path stays lean
+__device__ __noinline__ double lambda_exact(const LambdaTab *tab, const cgrb_unit_t &u, double t)
+{
+    return lambda_at(tab, u, t);
+}
+
+__device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_unit_t &u, bool squeeze,
+                                            const double2 *__restrict__ sq, double sq_inv_h, double t, double u2,
+                                            long long *n_exact)
+{
+    if (squeeze) {
+        const double q = (t - u.src_tstart) * sq_inv_h;
+        const int64_t kq = min(max((int64_t)q, (int64_t)0), u.tab_n - 2);
+        const double fr = q - (double)kq;
+        const double2 n0 = __ldg(sq + kq), n1 = __ldg(sq + kq + 1);
+        const double pl = n0.x + (n1.x - n0.x) * fr;
+        if (u2 <= pl - n0.y)
+            return true;
+        if (u2 > pl + n0.y)
+            return false;
+    }
+    (*n_exact)++;
+    return u2 <= lambda_exact(tab, u, t) / u.fmax;   // `if test <= p_test`
+}
+
+__global__ void __launch_bounds__(NT, 4) k_source_thin(const double *__restrict__ dtab,
                                                     const cgrb_unit_t *__restrict__ units,
                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                     cgrb_rng_t rng, const double *__restrict__ segstart,
-                                                    int32_t *__restrict__ segcount, double *__restrict__ stage,
+                                                    int32_t *__restrict__ segcount, double *stage,
                                                     double *__restrict__ cand_times,
                                                     uint8_t *__restrict__ cand_accept,
                                                     const double *__restrict__ thin_tab, cgrb_counts_t *counts)
 {
     __shared__ LambdaTab tab;
     __shared__ cgrb_unit_t u;
-    __shared__ double s_w[NW];
     __shared__ int s_wi[NW];
     __shared__ double s_t[NT];
     __shared__ double s_last;
@@ -456,89 +524,73 @@ __global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ d
         s_last = t0;
     __syncthreads();
 
-    const double inv_f = 1.0 / u.fmax;
     const int64_t n = min((int64_t)CGRB_SEG, u.src_cap - wk.start);
     // squeeze table of p(t) = lambda(t)/fmax (cgrb_thin_tables): decides most candidates without
     // evaluating lambda; the rest take the exact test, so decisions are those of the exact test
     const bool squeeze = thin_tab != nullptr && u.tab_n >= 4;
     const double2 *sq = reinterpret_cast<const double2 *>(thin_tab) + (squeeze ? u.tab_off : 0);
     const double sq_inv_h = squeeze ? (double)(u.tab_n - 1) / (u.src_tstop - u.src_tstart) : 0.0;
+    double *seg = stage + u.src_off + wk.start;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     long long n_exact = 0;
-    double carry = 0.0;
     int seg_n = 0;        // accepted so far in this segment
     int n_valid_total = 0;
-    bool exhausted = false;
-    for (int64_t base = 0; base < n; base += NT) {
-        const int64_t k = wk.start + base + threadIdx.x;
-        const bool inrange = base + threadIdx.x < n;
-        double gap = 0.0, u2 = 2.0;
-        if (inrange) {
-            ThinDraw d = thin_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, k);
-            gap = -(inv_f * log(d.u1));
-            u2 = d.u2;
-            exhausted |= d.exhausted;
-        }
-        double total;
-        double incl = block_incl_scan(gap, s_w, &total);
-        double t = t0 + (carry + incl);
-        carry = carry + total;
+    for (int64_t base = 0; base < n; base += THIN_TILE) {
+        const int64_t j0 = base + 2 * threadIdx.x;
+        const bool in0 = j0 < n, in1 = j0 + 1 < n;
+        double ta = in0 ? t0 + seg[j0] : INFINITY;
+        double tb = in1 ? t0 + seg[j0 + 1] : INFINITY;
         // enforce non-decreasing times across association orders (1-ulp inversions)
-        s_t[threadIdx.x] = t;
+        s_t[threadIdx.x] = in1 ? tb : ta;
         __syncthreads();
-        double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
-        t = fmax(t, left);
-        const bool valid = inrange && (t <= u.src_tstop);   // `if time > tstop: break`
-        bool acc = false;
-        if (valid) {
-            int decided = 0;
-            if (squeeze) {
-                double q = (t - u.src_tstart) * sq_inv_h;
-                int64_t kq = min(max((int64_t)q, (int64_t)0), u.tab_n - 2);
-                double fr = q - (double)kq;
-                double2 n0 = __ldg(sq + kq), n1 = __ldg(sq + kq + 1);
-                double pl = n0.x + (n1.x - n0.x) * fr;
-                if (u2 <= pl - n0.y) {
-                    acc = true;
-                    decided = 1;
-                } else if (u2 > pl + n0.y)
-                    decided = 1;
-            }
-            if (!decided) {
-                double p_test = lambda_at(&tab, u, t) / u.fmax;
-                acc = (u2 <= p_test);                       // `if test <= p_test`
-                n_exact++;
-            }
+        const double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
+        ta = fmax(ta, left);
+        tb = fmax(tb, ta);
+        const bool va = in0 && (ta <= u.src_tstop);   // `if time > tstop: break`
+        const bool vb = in1 && (tb <= u.src_tstop);
+        bool aa = false, ab = false;
+        if (va) {
+            PairDraw d = pair_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, (wk.start + j0) >> 1, 1);
+            aa = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact);
+            if (vb)
+                ab = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact);
         }
-        // ordered compaction
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        unsigned bal = __ballot_sync(0xffffffffu, acc);
-        unsigned balv = __ballot_sync(0xffffffffu, valid);
-        if (lane == 0)
-            s_wi[wid] = __popc(bal) | (__popc(balv) << 16);
-        __syncthreads();
-        int before = 0, tile_acc = 0, tile_valid = 0;
+        // ordered compaction: per-thread counts (0..2 accepted, 0..2 valid) packed in one int
+        const int mine = (int)aa + (int)ab + (((int)va + (int)vb) << 16);
+        int incl = warp_incl_scan_i(mine, lane);
+        if (lane == 31)
+            s_wi[wid] = incl;
+        __syncthreads();            // also: every read of this tile's slots is done before any write below
+        int before = 0, tile_tot = 0;
 #pragma unroll
         for (int q = 0; q < NW; q++) {
-            int c = s_wi[q] & 0xffff, v = s_wi[q] >> 16;
+            const int c = s_wi[q];
             if (q < wid)
                 before += c;
-            tile_acc += c;
-            tile_valid += v;
+            tile_tot += c;
         }
-        if (acc) {
-            int rank = before + __popc(bal & ((1u << lane) - 1u));
-            stage[u.src_off + wk.start + seg_n + rank] = t;
+        const int rank = ((before + incl - mine) & 0xffff) + seg_n;
+        if (aa)
+            seg[rank] = ta;
+        if (ab)
+            seg[rank + (int)aa] = tb;
+        if (cand_times) {
+            if (va) {
+                cand_times[u.src_off + wk.start + j0] = ta;
+                cand_accept[u.src_off + wk.start + j0] = aa ? 1 : 0;
+            }
+            if (vb) {
+                cand_times[u.src_off + wk.start + j0 + 1] = tb;
+                cand_accept[u.src_off + wk.start + j0 + 1] = ab ? 1 : 0;
+            }
         }
-        if (valid && cand_times) {
-            cand_times[u.src_off + k] = t;
-            cand_accept[u.src_off + k] = acc ? 1 : 0;
-        }
+        const int tile_acc = tile_tot & 0xffff, tile_valid = tile_tot >> 16;
         seg_n += tile_acc;
         n_valid_total += tile_valid;
         if (threadIdx.x == NT - 1)
-            s_last = t;
+            s_last = in1 ? tb : ta;
         __syncthreads();
-        if (tile_valid < (int)min((int64_t)NT, n - base))
+        if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
             break;      // crossed tstop: everything later is beyond it
     }
     {
@@ -553,8 +605,6 @@ __global__ void __launch_bounds__(NT) k_source_thin(const double *__restrict__ d
                 atomicAdd((unsigned long long *)&counts[wk.unit].n_exact, (unsigned long long)tot_exact);
         }
     }
-    if (exhausted)
-        atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
 }
 
 // pass 5: gather the per-segment accepted times into the unit's contiguous list; entry 0 is the
@@ -592,18 +642,19 @@ __global__ void __launch_bounds__(NT) k_source_gather(const cgrb_unit_t *__restr
 
 // ==========================================================================================
 // background (background.py:13-44 + numpy choice :93): every candidate is an event; event j of
-// the unit is candidate j-1, event 0 is the spurious tstart event.
+// the unit is candidate j-1, event 0 is the spurious tstart event.  Pass 1 (k_gap_prefix<1>) left
+// each candidate's running gap sum in its time slot; this pass adds the segment start, draws the
+// channel from the template's cdf and cuts the list at tstop.
 // ==========================================================================================
 __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dtab,
                                                    const cgrb_unit_t *__restrict__ units,
                                                    const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                    cgrb_rng_t rng, cgrb_rng_t rng_chan,
                                                    const double *__restrict__ segstart,
-                                                   double *__restrict__ times_bkg, uint8_t *__restrict__ pha_bkg,
+                                                   double *times_bkg, uint8_t *__restrict__ pha_bkg,
                                                    cgrb_counts_t *counts)
 {
     __shared__ double s_cdf[CGRB_NCHAN];
-    __shared__ double s_w[NW];
     __shared__ int s_wi[NW];
     __shared__ double s_t[NT];
     __shared__ double s_last;
@@ -629,8 +680,8 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
         // event 0: tstart, with its own channel draw (sample_channel(size=len(times)))
         double uc;
         if (rng.mode == 0) {
-            Philox4 p = philox_at(make_key(rng.seed), sid, ST_BKG, 0xFFFFFFFFFFull, 0u);
-            uc = u53(p.z, p.w);
+            Philox4 p = philox_at(make_key(rng.seed), sid, ST_BKG, 0xFFFFFFFFFFull, 1u);
+            uc = u53(p.x, p.y);
         } else {
             int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
             uc = rng_chan.d_u[o];
@@ -642,48 +693,56 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
     if (t0 > tstop)
         return;
 
-    const double inv_f = 1.0 / u->bkg_rate;
     const int64_t n = min((int64_t)CGRB_SEG, u->bkg_cap - wk.start);
-    double carry = 0.0;
+    double *seg_t = times_bkg + off + 1 + wk.start;
+    uint8_t *seg_p = pha_bkg + off + 1 + wk.start;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int n_valid_total = 0;
     bool exhausted = false;
-    for (int64_t base = 0; base < n; base += NT) {
-        const int64_t k = wk.start + base + threadIdx.x;
-        const bool inrange = base + threadIdx.x < n;
-        double gap = 0.0, uc = 0.0;
-        if (inrange) {
-            ThinDraw d = thin_draw(rng, wk.unit, sid, ST_BKG, k);
-            gap = -(inv_f * log(d.u1));
-            uc = d.u2;
-            exhausted |= d.exhausted;
-        }
-        double total;
-        double incl = block_incl_scan(gap, s_w, &total);
-        double t = t0 + (carry + incl);
-        carry = carry + total;
-        s_t[threadIdx.x] = t;
+    for (int64_t base = 0; base < n; base += THIN_TILE) {
+        const int64_t j0 = base + 2 * threadIdx.x;
+        const bool in0 = j0 < n, in1 = j0 + 1 < n;
+        double ta = in0 ? t0 + seg_t[j0] : INFINITY;
+        double tb = in1 ? t0 + seg_t[j0 + 1] : INFINITY;
+        s_t[threadIdx.x] = in1 ? tb : ta;
         __syncthreads();
-        double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
-        t = fmax(t, left);
-        const bool valid = inrange && (t <= tstop);
-        if (valid) {
-            if (rng.mode != 0) {
-                int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
-                int64_t len = rng_chan.d_len ? rng_chan.d_len[wk.unit] : ((int64_t)1 << 62);
-                if (k + 1 < len)
-                    uc = rng_chan.d_u[o + k + 1];
-                else {
-                    uc = 0.5;
+        const double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
+        ta = fmax(ta, left);
+        tb = fmax(tb, ta);
+        const bool va = in0 && (ta <= tstop);
+        const bool vb = in1 && (tb <= tstop);
+        if (va) {
+            double ua, ub = 0.5;
+            if (rng.mode == 0) {
+                PairDraw d = pair_draw(rng, wk.unit, sid, ST_BKG, (wk.start + j0) >> 1, 1);
+                ua = d.a;
+                ub = d.b;
+            } else {
+                const int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
+                const int64_t len = rng_chan.d_len ? rng_chan.d_len[wk.unit] : ((int64_t)1 << 62);
+                const int64_t e0 = wk.start + j0 + 1;           // event index of candidate j0
+                ua = 0.5;
+                if (e0 < len)
+                    ua = rng_chan.d_u[o + e0];
+                else
                     exhausted = true;
+                if (vb) {
+                    if (e0 + 1 < len)
+                        ub = rng_chan.d_u[o + e0 + 1];
+                    else
+                        exhausted = true;
                 }
             }
-            times_bkg[off + k + 1] = t;
-            pha_bkg[off + k + 1] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, uc), CGRB_NCHAN - 1);
+            seg_t[j0] = ta;
+            seg_p[j0] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, ua), CGRB_NCHAN - 1);
+            if (vb) {
+                seg_t[j0 + 1] = tb;
+                seg_p[j0 + 1] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, ub), CGRB_NCHAN - 1);
+            }
         }
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        unsigned balv = __ballot_sync(0xffffffffu, valid);
+        const unsigned bala = __ballot_sync(0xffffffffu, va), balb = __ballot_sync(0xffffffffu, vb);
         if (lane == 0)
-            s_wi[wid] = __popc(balv);
+            s_wi[wid] = __popc(bala) + __popc(balb);
         __syncthreads();
         int tile_valid = 0;
 #pragma unroll
@@ -691,9 +750,9 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
             tile_valid += s_wi[q];
         n_valid_total += tile_valid;
         if (threadIdx.x == NT - 1)
-            s_last = t;
+            s_last = in1 ? tb : ta;
         __syncthreads();
-        if (tile_valid < (int)min((int64_t)NT, n - base))
+        if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
             break;
     }
     if (threadIdx.x == 0 && n_valid_total)
@@ -923,10 +982,12 @@ __device__ __noinline__ double literal_photon_serial(const cgrb_unit_t &u, const
 #define ENV_ROW (CGRB_ENV_SEGS + 1)
 __global__ void __launch_bounds__(NT) k_energy_rows(const cgrb_unit_t *__restrict__ units, int n_units,
                                                     const EnergyUnitTab *__restrict__ etab,
-                                                    double *__restrict__ rows, int64_t n_rows)
+                                                    double *__restrict__ rows, uint8_t *__restrict__ row_guides,
+                                                    int64_t n_rows)
 {
     __shared__ double s_w[NW];
     __shared__ double s_red[NW];
+    __shared__ double s_row[ENV_ROW];
     const int64_t r = blockIdx.x;
     if (r >= n_rows)
         return;
@@ -964,34 +1025,194 @@ __global__ void __launch_bounds__(NT) k_energy_rows(const cgrb_unit_t *__restric
     const double incl = block_incl_scan(e, s_w, &total);
     double *row = rows + r * ENV_ROW;
     row[j] = incl - e;
-    if (j == CGRB_ENV_SEGS - 1)
+    s_row[j] = incl - e;
+    if (j == CGRB_ENV_SEGS - 1) {
         row[CGRB_ENV_SEGS] = incl;
+        s_row[CGRB_ENV_SEGS] = incl;
+    }
+    __syncthreads();
+    // guide[m] = segment of y = (m/256) total: the search for y' >= y starts there and walks forward
+    const double y = ((double)j / (double)CGRB_ENV_SEGS) * s_row[CGRB_ENV_SEGS];
+    int seg = 0;
+#pragma unroll
+    for (int step = CGRB_ENV_SEGS / 2; step >= 1; step >>= 1)
+        if (s_row[seg + step] <= y)
+            seg += step;
+    row_guides[r * CGRB_ENV_SEGS + j] = (uint8_t)seg;
+}
+
+// lower bound (first index with xs[j] >= v) over n <= 255 ascending entries in a fixed 8 probes:
+// no data-dependent trip count, so a warp never diverges on it
+__device__ __forceinline__ int lower_bound_255(const double *xs, int n, double v)
+{
+    int pos = 0;
+#pragma unroll
+    for (int step = 128; step >= 1; step >>= 1) {
+        const int q = pos + step;
+        if (q <= n && xs[q - 1] < v)
+            pos = q;
+    }
+    return pos;
+}
+
+// first j with row[j] >= r (0..128) for one row of the cumulative matrix.  `guide` (shared memory,
+// CGRB_NCHAN bytes of this row) gives a start at or before it -- guide[m] = lower bound of m/128 -- so
+// the forward walk is ~1-2 probes of the fp64 row; pathological rows (many channels inside one guide
+// cell) finish by bisection.  *v_at = row[result] when result < 128.
+__device__ __forceinline__ int guided_lower_bound(const uint8_t *guide, const double *__restrict__ row, double r,
+                                                  double *v_at)
+{
+    const int m = min(max((int)(r * (double)CGRB_NCHAN), 0), CGRB_NCHAN - 1);
+    int lo = guide[m];
+    double v = 0.0;
+    int steps = 0;
+    while (lo < CGRB_NCHAN) {
+        v = __ldg(row + lo);
+        if (!(v < r))
+            break;
+        lo++;
+        if (++steps == 6) {              // rare: finish by bisection on [lo, 128)
+            int hi = CGRB_NCHAN;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(row + mid) < r)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            if (lo < CGRB_NCHAN)
+                v = __ldg(row + lo);
+            break;
+        }
+    }
+    *v_at = v;
+    return lo;
+}
+
+// argmin_j |row[j] - r| with the first index on ties (response.py:18-24)
+__device__ __forceinline__ int nearest_cdf_guided(const uint8_t *guide, const double *__restrict__ row, double r)
+{
+    double vhi;
+    const int lo = guided_lower_bound(guide, row, r, &vhi);
+    if (lo == 0)
+        return 0;
+    const double vlo = __ldg(row + lo - 1);
+    if (lo < CGRB_NCHAN && fabs(vhi - r) < fabs(vlo - r))
+        return lo;                       // strictly nearer above; row[lo-1] < r <= row[lo]: no plateau below it
+    // tie or nearer below -> lo - 1; np.argmin returns the FIRST index holding that value (plateaus of
+    // zero-probability channels): the lower bound of the value itself
+    if (lo >= 2 && !(__ldg(row + lo - 2) < vlo)) {
+        double dummy;
+        return guided_lower_bound(guide, row, vlo, &dummy);
+    }
+    return lo - 1;
+}
+
+// Response.digitize of one photon (response.py:10-25): photon bin by a full search of the edges
+__device__ __forceinline__ int digitize_one(const double *edges, const uint8_t *guide, const double *__restrict__ cum,
+                                            double x, uint64_t seed, uint32_t stream_id, int64_t i)
+{
+    int b = lower_bound_255(edges, CGRB_NBINS + 1, x) - 1;      // searchsorted 'left', response.py:14
+    if (b < 0)
+        b += CGRB_NBINS;                                          // python negative index
+    b = min(b, CGRB_NBINS - 1);
+    Philox4 p = philox_at(make_key(seed), stream_id, ST_SRC_CHAN, (uint64_t)i, 0u);
+    return nearest_cdf_guided(guide + b * CGRB_NCHAN, cum + (size_t)b * CGRB_NCHAN, u53(p.x, p.y));
+}
+
+#define GUIDE_BYTES (CGRB_NBINS * CGRB_NCHAN)
+
+// one mbarrier-tracked bulk-async (TMA) copy of a detector's 17,920-byte search guide into shared memory;
+// called by one thread, every thread then waits with guide_wait()
+__device__ __forceinline__ void guide_stage(uint8_t *s_guide, uint64_t *s_bar, const double *dt)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_guide);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)GUIDE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(reinterpret_cast<const char *>(dt + CGRB_DT_GUIDE)), "r"((unsigned)GUIDE_BYTES), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void guide_wait(uint64_t *s_bar)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(0u)
+            : "memory");
+    }
+}
+
+// exp(z) for |z| <= 0.1 to ~3e-17 relative: Taylor polynomial of degree 9
+__device__ __forceinline__ double exp_small(double z)
+{
+    double p = 1.0 / 362880.0;
+    p = fma(p, z, 1.0 / 40320.0);
+    p = fma(p, z, 1.0 / 5040.0);
+    p = fma(p, z, 1.0 / 720.0);
+    p = fma(p, z, 1.0 / 120.0);
+    p = fma(p, z, 1.0 / 24.0);
+    p = fma(p, z, 1.0 / 6.0);
+    p = fma(p, z, 0.5);
+    p = fma(p, z, 1.0);
+    return fma(p, z, 1.0);
+}
+
+// 1/d for d in the float range, from the single-precision reciprocal and two Newton steps (~1e-16)
+__device__ __forceinline__ double rcp_fast(double d)
+{
+    double r = (double)__frcp_rn((float)d);
+    r = r * (2.0 - d * r);
+    return r * (2.0 - d * r);
 }
 
 struct EnvSmem {
     double xlo[CGRB_ENV_SEGS];
-    double logM[CGRB_ENV_SEGS];
+    double invMx[CGRB_ENV_SEGS];
     double logAmax[CGRB_ENV_SEGS];
-    double wk[CGRB_ENV_MAXW];
-    double hull_w[CGRB_NE_ENVELOPE];
-    int hull_m[CGRB_NE_ENVELOPE];
+    int kn[CGRB_ENV_SEGS];
+    double wk[CGRB_ENV_MAXW + 1];          // wk[n_w] = +inf
+    double hull_w[CGRB_NE_ENVELOPE + 1];   // hull_w[n_hull] = +inf
+    double hull_E[CGRB_NE_ENVELOPE];
+    double hull_lA5[CGRB_NE_ENVELOPE];
     double eax[CGRB_NBINS];
     double eay[CGRB_NBINS];
+    double esl[CGRB_NBINS];                // slope of the effective-area curve on [eax[m], eax[m+1]]
+    double edges[CGRB_NBINS + 1];
 };
 
+// One thread per photon, lanes refill from their warp's slice as they accept.  With pha_src != NULL the
+// kernel also folds the accepted energy through the response (Response.digitize) -- the photon's bin
+// follows from the effective-area bracket already in hand and the channel search starts from the
+// detector's guide table staged in shared memory -- so energies never have to travel through HBM
+// (energy_src may be NULL).
 __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__restrict__ dtab,
                                                           const cgrb_unit_t *__restrict__ units,
                                                           const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                           int interp_extrap, cgrb_rng_t rng, int64_t max_trials,
                                                           const EnergyUnitTab *__restrict__ etab,
                                                           const double *__restrict__ rows,
+                                                          const uint8_t *__restrict__ row_guides,
                                                           const double *__restrict__ times_src,
                                                           double *__restrict__ energy_src,
+                                                          uint8_t *__restrict__ pha_src,
                                                           int32_t *__restrict__ trials_out, cgrb_counts_t *counts)
 {
     __shared__ EnvSmem sm;
+    __shared__ __align__(128) uint8_t s_guide[GUIDE_BYTES];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ cgrb_unit_t u;
     __shared__ long long s_wl[NW];
+    __shared__ double ck[16];
     const int64_t w = blockIdx.x;
     if (w >= n_work)
         return;
@@ -1003,57 +1224,79 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
     if (threadIdx.x == 0)
         u = units[wk.unit];
     const int n_w = T->n_w;
+    const int n_hull = T->n_hull;
     for (int j = threadIdx.x; j < CGRB_ENV_SEGS; j += NT) {
         sm.xlo[j] = T->xlo[j];
-        sm.logM[j] = T->logM[j];
+        sm.invMx[j] = T->invMx[j];
         sm.logAmax[j] = T->logAmax[j];
+        sm.kn[j] = T->kn[j];
     }
-    for (int j = threadIdx.x; j < n_w; j += NT)
-        sm.wk[j] = T->wk[j];
-    const int n_hull = T->n_hull;
-    for (int j = threadIdx.x; j < n_hull; j += NT) {
-        sm.hull_w[j] = T->hull_w[j];
-        sm.hull_m[j] = T->hull_m[j];
+    for (int j = threadIdx.x; j <= n_w; j += NT)
+        sm.wk[j] = (j < n_w) ? T->wk[j] : INFINITY;
+    for (int j = threadIdx.x; j <= n_hull; j += NT) {
+        sm.hull_w[j] = (j < n_hull) ? T->hull_w[j] : INFINITY;
+        if (j < n_hull) {
+            sm.hull_E[j] = T->hull_E[j];
+            sm.hull_lA5[j] = T->hull_lA5[j];
+        }
     }
     __syncthreads();
     const double *dt = dtab + (size_t)u.det * CGRB_DT_SIZE;
+    if (threadIdx.x == 0 && pha_src)
+        guide_stage(s_guide, &s_bar, dt);
     for (int m = threadIdx.x; m < CGRB_NBINS; m += NT) {
-        sm.eax[m] = dt[CGRB_DT_EA_X + m];
-        sm.eay[m] = dt[CGRB_DT_EA_Y + m];
+        const double x0 = dt[CGRB_DT_EA_X + m], y0 = dt[CGRB_DT_EA_Y + m];
+        sm.eax[m] = x0;
+        sm.eay[m] = y0;
+        sm.esl[m] = (m < CGRB_NBINS - 1) ? (dt[CGRB_DT_EA_Y + m + 1] - y0) / (dt[CGRB_DT_EA_X + m + 1] - x0) : 0.0;
     }
+    for (int m = threadIdx.x; m <= CGRB_NBINS; m += NT)
+        sm.edges[m] = dt[CGRB_DT_EDGES + m];
     // loop constants live in shared memory (broadcast loads) to keep the trial loop's registers free
-    __shared__ double ck[12];
     if (threadIdx.x == 0) {
         const double alpha = u.alpha;
-        ck[0] = T->u0;
         ck[1] = T->du;
         ck[2] = T->a;
         ck[3] = T->logw0;
         ck[4] = T->inv_dlogw;
-        ck[5] = dt[CGRB_DT_EDGES];
         ck[6] = dt[CGRB_DT_EDGES + CGRB_NBINS];
-        ck[7] = (1.0 + u.z) * ((alpha == -2.0) ? 0.0001 : (2.0 + alpha));     // w = ck[7] / ep
+        // w(t) = (1+z)/ec(t) = wa + wb t   (ep = ep_start / (1 + t/tau); constant CPL: wb = 0)
+        const double wa = (1.0 + u.z) * ((alpha == -2.0) ? 0.0001 : (2.0 + alpha)) / u.ep_start;
+        ck[7] = wa;
+        ck[8] = (u.kind == 0) ? wa / u.ep_tau : 0.0;
+        // pulse amplitude is a normal number for t in (tlo, thi): trise/t + t/tdecay < 700
+        double tlo = INFINITY, thi = -INFINITY;
+        if (u.kind != 0) {
+            tlo = -INFINITY;
+            thi = INFINITY;
+        } else if (u.peak_flux > 0.0 && u.tdecay > 0.0 && u.trise >= 0.0) {
+            const double disc = 350.0 * 350.0 - u.trise / u.tdecay;
+            if (disc >= 0.0) {
+                const double r = 350.0 + sqrt(disc);
+                tlo = u.trise / r;
+                thi = u.tdecay * r;
+            }
+        }
+        ck[9] = tlo;
+        ck[10] = thi;
+        ck[11] = 1.0 / (1.0 + u.z);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        EaGuess g0 = make_ea_guess(sm.eax);
-        ck[8] = g0.log_x0;
-        ck[9] = g0.inv_dlog;
-    }
-    __syncthreads();
-#define c_u0 ck[0]
+    if (pha_src)
+        guide_wait(&s_bar);
 #define c_du ck[1]
 #define c_a ck[2]
 #define c_logw0 ck[3]
 #define c_inv_dlogw ck[4]
-#define c_emin ck[5]
 #define c_emax ck[6]
-#define c_wnum ck[7]
-    EaGuess eg;
-    eg.log_x0 = ck[8];
-    eg.inv_dlog = ck[9];
-    const double inv_opz = 1.0 / (1.0 + u.z);
+#define c_wa ck[7]
+#define c_wb ck[8]
+#define c_tlo ck[9]
+#define c_thi ck[10]
+#define c_inv_opz ck[11]
     const double *unit_rows = rows + u.etab_off * ENV_ROW;
+    const uint8_t *unit_guides = row_guides + u.etab_off * CGRB_ENV_SEGS;
+    const double *cum = dt + CGRB_DT_CUM;
 
     int64_t chunk_end = n_src;
     if (w + 1 < n_work && work[w + 1].unit == wk.unit)
@@ -1067,11 +1310,12 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
     int64_t next = wbeg;                 // warp-uniform
     long long my_trials = 0;
     bool capped = false, active = false, violated = false;
-    // per-lane photon state
+    // per-lane photon state; k (table row) and h (hull position) persist from photon to photon: a lane's
+    // photons come in time order, so both usually advance by zero or one step
     int64_t i = 0;
     uint32_t j = 0;
-    const double *row = unit_rows;
-    double wq = 0.0, wkk = 0.0, total = 0.0, s_idx = 0.0, A5 = 0.0, t_clip = 0.0;
+    int k = -1, h = -1;
+    double wq = 0.0, s_idx = 0.0, t_clip = 0.0, total = 0.0;
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !active);
         if (need) {
@@ -1081,34 +1325,65 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
                 i = cand;
                 j = 0;
                 const double t = times_src[u.src_off + i];
-                // pulse amplitude > 0 ?  (norris underflows for t -> 0+; constant CPL is always regular)
-                bool regular = (u.kind != 0) || (t > 0.0 && (u.trise / t + t / u.tdecay) < 700.0 && u.peak_flux > 0.0);
-                const double ep = (u.kind == 0) ? u.ep_start / (1.0 + t / u.ep_tau) : u.ep_start;
-                wq = c_wnum / ep;                               // (1+z) / ec
-                int k = (int)floor((log(wq) - c_logw0) * c_inv_dlogw);
-                k = max(0, min(k, n_w - 1));
-                if (sm.wk[k] > wq)
-                    k--;
-                if (k < 0 || !(sm.wk[max(k, 0)] <= wq))         // w below the unit's grid (or NaN)
-                    regular = false;
-                k = max(k, 0);
-                wkk = sm.wk[k];
-                row = unit_rows + (size_t)k * ENV_ROW;
-                total = __ldg(row + CGRB_ENV_SEGS);
-                if (!(total > 0.0) || isinf(total))
-                    regular = false;
+                bool regular = (t > c_tlo) && (t < c_thi) && n_hull > 0;
+                wq = c_wa + c_wb * t;                           // (1+z) / ec(t)
+                {
+                    int kk = k, steps = 0;
+                    if (kk >= 0)
+                        while (steps < 4 && sm.wk[kk + 1] <= wq) {
+                            kk++;
+                            steps++;
+                        }
+                    if (kk < 0 || steps == 4 || sm.wk[kk] > wq) {
+                        kk = (int)floor((log(wq) - c_logw0) * c_inv_dlogw);
+                        kk = max(0, min(kk, n_w - 1));
+                        if (sm.wk[kk] > wq)
+                            kk--;
+                        else if (sm.wk[kk + 1] <= wq)
+                            kk++;
+                    }
+                    if (kk < 0 || !(sm.wk[max(kk, 0)] <= wq))   // w below the unit's grid (or NaN)
+                        regular = false;
+                    k = min(max(kk, 0), n_w - 1);
+                }
                 if (regular) {
-                    const int idx = hull_lookup(sm.hull_m, sm.hull_w, n_hull, wq * inv_opz);
-                    s_idx = dt[CGRB_DT_G500_E + idx] * wq;
-                    A5 = 5.0 * dt[CGRB_DT_G500_A + idx];
-                    t_clip = log(A5) - s_idx;
+                    const double wh = wq * c_inv_opz;           // 1 / ec
+                    int hh = h, steps = 0;
+                    if (hh >= 0)
+                        while (steps < 4 && sm.hull_w[hh + 1] <= wh) {
+                            hh++;
+                            steps++;
+                        }
+                    if (hh < 0 || steps == 4 || sm.hull_w[hh] > wh) {
+                        int lo = 0, hi = n_hull;                // last entry with hull_w <= wh
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sm.hull_w[mid] <= wh)
+                                lo = mid;
+                            else
+                                hi = mid;
+                        }
+                        hh = lo;
+                    }
+                    h = hh;
+                    s_idx = sm.hull_E[h] * wq;
+                    t_clip = sm.hull_lA5[h] - s_idx;
+                    total = __ldg(unit_rows + (size_t)k * ENV_ROW + CGRB_ENV_SEGS);
+                    if (!(total > 0.0) || isinf(total))
+                        regular = false;
+                }
+                if (regular)
                     active = true;
-                } else {
+                else {
                     // degenerate photon: the literal loop, right here (rare)
                     int64_t ntr = 0;
+                    EaGuess eg = make_ea_guess(sm.eax);
                     const double x = literal_photon_serial(u, dt, sm.eax, sm.eay, eg, interp_extrap, rng.seed, i, t,
                                                            max_trials, &ntr, &capped);
-                    energy_src[u.src_off + i] = x;
+                    if (energy_src)
+                        energy_src[u.src_off + i] = x;
+                    if (pha_src)
+                        pha_src[u.src_off + i] = (uint8_t)digitize_one(sm.edges, s_guide, cum, x, rng.seed, u.stream_id, i);
                     if (trials_out)
                         trials_out[u.src_off + i] = (int32_t)ntr;
                     my_trials += ntr;
@@ -1121,35 +1396,74 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
             continue;
         }
         if (active) {
+            const double *row = unit_rows + (size_t)k * ENV_ROW;
             Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
             const double U = u53(p.x, p.y), V = u53(p.z, p.w);
             const double y = U * total;
-            int lo = 0, hi = CGRB_ENV_SEGS;         // segment: row[lo] <= y < row[lo+1]
-#pragma unroll
-            for (int it = 0; it < 8; it++) {        // CGRB_ENV_SEGS = 2^8
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(row + mid) <= y)
-                    lo = mid;
-                else
-                    hi = mid;
+            // segment: row[lo] <= y < row[lo+1], walking forward from the row's guide
+            int lo = unit_guides[(size_t)k * CGRB_ENV_SEGS + min((int)(U * (double)CGRB_ENV_SEGS), CGRB_ENV_SEGS - 1)];
+            double c0 = __ldg(row + lo), c1 = __ldg(row + lo + 1);
+            while (lo < CGRB_ENV_SEGS - 1 && c1 <= y) {
+                lo++;
+                c0 = c1;
+                c1 = __ldg(row + lo + 1);
             }
-            const double c0 = __ldg(row + lo), c1 = __ldg(row + lo + 1);
-            const double fr = fmin(fmax((y - c0) / (c1 - c0), 0.0), 1.0);
-            const double uu = c_u0 + ((double)lo + fr) * c_du;
-            const double x = fmin(fmax(exp(uu), c_emin), c_emax);
-            const double s = x * wq;
-            double A = fmax(interp_guess(sm.eax, sm.eay, CGRB_NBINS, x, uu, eg, interp_extrap), 0.0);
+            const double den = c1 - c0;
+            const double fr = fmin(fmax((den > 1e-30) ? (y - c0) * rcp_fast(den) : (y - c0) / den, 0.0), 1.0);
+            const double z = fr * c_du;                         // x = xlo e^z, z in [0, du]
             const double xl = sm.xlo[lo];
+            const double x = fmin(xl * exp_small(z), c_emax);
+            const double s = x * wq;
+            // effective area at x: bracket from the segment's first node, then the linear piece
+            int ib = min(max(sm.kn[lo] - 1, 0), CGRB_NBINS - 2);
+            while (ib < CGRB_NBINS - 2 && sm.eax[ib + 1] < x)
+                ib++;
+            double A = sm.eay[ib] + sm.esl[ib] * (x - sm.eax[ib]);
+            if (interp_extrap == 1) {
+                if (x <= sm.eax[0])
+                    A = sm.eay[0];
+                else if (x >= sm.eax[CGRB_NBINS - 1])
+                    A = sm.eay[CGRB_NBINS - 1];
+            }
+            A = fmax(A, 0.0);
             if (sm.logAmax[lo] - xl * wq > t_clip)
-                A = fmin(A, A5 * exp(s - s_idx));   // the literal envelope clips f here
-            // target x^(a) A e^{-s}  <=  envelope  M_lo e^{-xlo w_k}
-            const double ratio = A * exp(c_a * uu - s - sm.logM[lo] + xl * wkk);
+                A = fmin(A, exp(sm.hull_lA5[h] + s - s_idx));   // the literal envelope clips f here
+            // target / envelope = [A x^a / M_lo] exp(-d),  d = x w - xlo w_k >= 0, decided from the
+            // bounds 1 - d + d^2/2 - d^3/6 <= exp(-d) <= 1 - d + d^2/2 whenever they agree
+            const double base = A * sm.invMx[lo] * exp_small(c_a * z);
+            const double d = fmax(s - xl * sm.wk[k], 0.0);
+            const double qhi = fma(d, fma(d, 0.5, -1.0), 1.0);
+            const double qlo = qhi - d * d * d * (1.0 / 6.0);
             j++;
-            violated |= ratio > 1.000001;           // the envelope must dominate the target (self-check)
-            const bool acc = V <= ratio;
+            violated |= base * qlo > 1.000001;      // the envelope must dominate the target (self-check)
+            bool acc;
+            if (V <= base * qlo)
+                acc = true;
+            else if (V > base * qhi)
+                acc = false;
+            else
+                acc = V <= base * exp(-d);
             const bool cap = !acc && max_trials > 0 && (int64_t)j >= max_trials;
             if (acc || cap) {
-                energy_src[u.src_off + i] = acc ? x : nan("");
+                if (energy_src)
+                    energy_src[u.src_off + i] = acc ? x : nan("");
+                if (pha_src) {
+                    int pha;
+                    if (acc) {
+                        // photon bin = searchsorted(edges, x, 'left') - 1, walked from the bracket
+                        int b = ib;
+                        while (b < CGRB_NBINS - 1 && sm.edges[b + 1] < x)
+                            b++;
+                        while (b >= 0 && !(sm.edges[b] < x))
+                            b--;
+                        if (b < 0)
+                            b += CGRB_NBINS;                    // python negative index (x == emin)
+                        Philox4 pc = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_CHAN, (uint64_t)i, 0u);
+                        pha = nearest_cdf_guided(s_guide + b * CGRB_NCHAN, cum + (size_t)b * CGRB_NCHAN, u53(pc.x, pc.y));
+                    } else
+                        pha = digitize_one(sm.edges, s_guide, cum, nan(""), rng.seed, u.stream_id, i);
+                    pha_src[u.src_off + i] = (uint8_t)pha;
+                }
                 if (trials_out)
                     trials_out[u.src_off + i] = (int32_t)j;
                 my_trials += j;
@@ -1158,14 +1472,16 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
             }
         }
     }
-#undef c_u0
 #undef c_du
 #undef c_a
 #undef c_logw0
 #undef c_inv_dlogw
-#undef c_emin
 #undef c_emax
-#undef c_wnum
+#undef c_wa
+#undef c_wb
+#undef c_tlo
+#undef c_thi
+#undef c_inv_opz
     const long long tot = block_sum_ll(my_trials, s_wl);
     if (threadIdx.x == 0 && tot)
         atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)tot);
@@ -1181,62 +1497,15 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
 // The detector's 140x128 cumulative matrix (143,360 B) is staged into shared memory with one
 // mbarrier-tracked bulk-async (TMA) copy per CTA when the chunk is large enough to amortise it.
 // ==========================================================================================
-// lower bound (first index with xs[j] >= v) over n <= 255 ascending entries in a fixed 8 probes:
-// no data-dependent trip count, so a warp never diverges on it
-__device__ __forceinline__ int lower_bound_255(const double *xs, int n, double v)
-{
-    int pos = 0;
-#pragma unroll
-    for (int step = 128; step >= 1; step >>= 1) {
-        const int q = pos + step;
-        if (q <= n && xs[q - 1] < v)
-            pos = q;
-    }
-    return pos;
-}
-
-__device__ __forceinline__ int nearest_cdf(const double *row, double r)
-{
-    // lo = first index with row[j] >= r  (0 .. 128)
-    int lo = 0;
-#pragma unroll
-    for (int step = 64; step >= 1; step >>= 1)
-        if (row[lo + step - 1] < r)
-            lo += step;
-    if (row[lo] < r)
-        lo++;
-    const int jhi = min(lo, CGRB_NCHAN - 1);
-    const int jlo = max(lo - 1, 0);
-    const double vlo = row[jlo], vhi = row[jhi];
-    const double dlo = fabs(vlo - r), dhi = fabs(vhi - r);
-    int pick = (dhi < dlo) ? jhi : jlo;            // tie -> lower index
-    const double v = (dhi < dlo) ? vhi : vlo;
-    // np.argmin returns the FIRST index holding the nearest value (plateaus of zero-probability channels)
-    if (pick > 0 && !(row[pick - 1] < v)) {
-        int f = 0;
-#pragma unroll
-        for (int step = 64; step >= 1; step >>= 1)
-            if (row[f + step - 1] < v)
-                f += step;
-        pick = f;
-    }
-    return pick;
-}
-
-#define CUM_BYTES (CGRB_NBINS * CGRB_NCHAN * 8)
-#define DIGITIZE_STAGE_MIN 4096
-#define DIGITIZE_NT 1024     // one CTA per SM (the staged matrix takes 143 KB of its shared memory): 32 warps
-
-__global__ void __launch_bounds__(DIGITIZE_NT) k_digitize(const double *__restrict__ dtab,
+__global__ void __launch_bounds__(NT) k_digitize(const double *__restrict__ dtab,
                                                  const cgrb_unit_t *__restrict__ units,
                                                  const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                  cgrb_rng_t rng, const double *__restrict__ energy_src,
                                                  uint8_t *__restrict__ pha_src, const cgrb_counts_t *counts)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *s_cum = reinterpret_cast<double *>(smem_raw);                       // [140*128]
-    double *s_edges = reinterpret_cast<double *>(smem_raw + CUM_BYTES);          // [141] (+pad)
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + CUM_BYTES + 144 * 8);
+    __shared__ __align__(128) uint8_t s_guide[GUIDE_BYTES];
+    __shared__ double s_edges[CGRB_NBINS + 1];
+    __shared__ __align__(8) uint64_t s_bar;
 
     const int64_t w = blockIdx.x;
     if (w >= n_work)
@@ -1250,61 +1519,29 @@ __global__ void __launch_bounds__(DIGITIZE_NT) k_digitize(const double *__restri
         chunk_end = min(n_src, work[w + 1].start);
     const cgrb_unit_t *u = units + wk.unit;
     const double *dt = dtab + (size_t)u->det * CGRB_DT_SIZE;
-    const bool staged = (chunk_end - wk.start) >= DIGITIZE_STAGE_MIN;
-
-    if (staged && threadIdx.x == 0) {
-        unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
-        unsigned dst = (unsigned)__cvta_generic_to_shared(s_cum);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)CUM_BYTES)
-                     : "memory");
-        const char *src = reinterpret_cast<const char *>(dt + CGRB_DT_CUM);
-        const unsigned piece = CUM_BYTES / 8;      // 17,920 B, multiple of 16
-#pragma unroll
-        for (int c = 0; c < 8; c++)
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    dst + c * piece),
-                "l"(src + (size_t)c * piece), "r"(piece), "r"(bar)
-                : "memory");
-    }
-    for (int m = threadIdx.x; m <= CGRB_NBINS; m += DIGITIZE_NT)
+    if (threadIdx.x == 0)
+        guide_stage(s_guide, &s_bar, dt);
+    for (int m = threadIdx.x; m <= CGRB_NBINS; m += NT)
         s_edges[m] = dt[CGRB_DT_EDGES + m];
     __syncthreads();
-    if (staged) {
-        unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
-        unsigned done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n"
-                ".reg .pred p;\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-                "selp.u32 %0, 1, 0, p;\n"
-                "}\n"
-                : "=r"(done)
-                : "r"(bar), "r"(0u)
-                : "memory");
-        }
-    }
-    const double *cum = staged ? s_cum : dt + CGRB_DT_CUM;
+    guide_wait(&s_bar);
+    const double *cum = dt + CGRB_DT_CUM;
+    const uint32_t sid = u->stream_id;
+    const int64_t off = u->src_off;
 
-    for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += DIGITIZE_NT) {
-        const double e = energy_src[u->src_off + i];
-        int idx = lower_bound_255(s_edges, CGRB_NBINS + 1, e) - 1;        // searchsorted 'left', response.py:14
-        if (idx < 0)
-            idx += CGRB_NBINS;                                            // python negative index
-        if (idx > CGRB_NBINS - 1)
-            idx = CGRB_NBINS - 1;
-        double r;
-        if (rng.mode == 0) {
-            Philox4 p = philox_at(make_key(rng.seed), u->stream_id, ST_SRC_CHAN, (uint64_t)i, 0u);
-            r = u53(p.x, p.y);
-        } else {
-            int64_t o = rng.d_off ? rng.d_off[wk.unit] : 0;
-            r = rng.d_u[o + i];
+    for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += NT) {
+        const double e = energy_src[off + i];
+        if (rng.mode == 0)
+            pha_src[off + i] = (uint8_t)digitize_one(s_edges, s_guide, cum, e, rng.seed, sid, i);
+        else {
+            int idx = lower_bound_255(s_edges, CGRB_NBINS + 1, e) - 1;        // searchsorted 'left', response.py:14
+            if (idx < 0)
+                idx += CGRB_NBINS;                                            // python negative index
+            idx = min(idx, CGRB_NBINS - 1);
+            const int64_t o = rng.d_off ? rng.d_off[wk.unit] : 0;
+            pha_src[off + i] = (uint8_t)nearest_cdf_guided(s_guide + idx * CGRB_NCHAN, cum + (size_t)idx * CGRB_NCHAN,
+                                                           rng.d_u[o + i]);
         }
-        pha_src[u->src_off + i] = (uint8_t)nearest_cdf(cum + (size_t)idx * CGRB_NCHAN, r);
     }
 }
 
@@ -1737,7 +1974,7 @@ int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
     if (rc)
         return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH("k_gap_sums<0>", s, k_gap_sums<0><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng, d_segsum, d_counts));
+    LAUNCH("k_gap_prefix<0>", s, k_gap_prefix<0><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng, d_segsum, d_stage, d_counts));
     LAUNCH("k_seg_scan<0>", s, k_seg_scan<0><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
                                                            d_segstart, d_counts));
     LAUNCH("k_source_thin", s, k_source_thin<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng, d_segstart,
@@ -1772,17 +2009,18 @@ int64_t cgrb_energy_workspace_bytes(int n_units, int64_t n_rows)
 {
     int64_t tabs = (int64_t)sizeof(EnergyUnitTab) * (n_units > 0 ? n_units : 0);
     tabs = (tabs + 255) / 256 * 256;
-    return tabs + (int64_t)sizeof(double) * ENV_ROW * (n_rows > 0 ? n_rows : 0);
+    const int64_t nr = n_rows > 0 ? n_rows : 0;
+    return tabs + (int64_t)sizeof(double) * ENV_ROW * nr + (int64_t)CGRB_ENV_SEGS * nr;
 }
 
 int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                                 const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
                                 const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
-                                const double *d_times_src, double *d_energy_src, int32_t *d_trials,
-                                cgrb_counts_t *d_counts, void *stream)
+                                const double *d_times_src, double *d_energy_src, uint8_t *d_pha_src,
+                                int32_t *d_trials, cgrb_counts_t *d_counts, void *stream)
 {
-    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_src || !d_energy_src ||
-        !d_counts || !d_workspace || n_rows < n_units)
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_src ||
+        (!d_energy_src && !d_pha_src) || !d_counts || !d_workspace || n_rows < n_units)
         return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: bad argument%s");
     if (interp_extrap != 0 && interp_extrap != 1)
         return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: interp_extrap must be 0 (linear) or 1 (clamp)%s");
@@ -1796,11 +2034,12 @@ int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units
     EnergyUnitTab *etab = (EnergyUnitTab *)d_workspace;
     int64_t tabs = ((int64_t)sizeof(EnergyUnitTab) * n_units + 255) / 256 * 256;
     double *rows = (double *)((char *)d_workspace + tabs);
+    uint8_t *row_guides = (uint8_t *)(rows + (size_t)ENV_ROW * n_rows);
     LAUNCH("k_energy_tables", s, k_energy_tables<<<n_units, 256, 0, s>>>(d_dtab, d_units, n_units, interp_extrap, etab));
-    LAUNCH("k_energy_rows", s, k_energy_rows<<<(unsigned)n_rows, NT, 0, s>>>(d_units, n_units, etab, rows, n_rows));
+    LAUNCH("k_energy_rows", s, k_energy_rows<<<(unsigned)n_rows, NT, 0, s>>>(d_units, n_units, etab, rows, row_guides, n_rows));
     LAUNCH("k_sample_energy_env", s, k_sample_energy_env<<<(unsigned)n_work, NT, 0, s>>>(
-        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, rows, d_times_src, d_energy_src,
-        d_trials, d_counts));
+        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, rows, row_guides, d_times_src,
+        d_energy_src, d_pha_src, d_trials, d_counts));
     return check_launch("cgrb_sample_energy_envelope");
 }
 
@@ -1814,15 +2053,7 @@ int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
     int rc = check_rng(rng, "cgrb_digitize");
     if (rc)
         return rc;
-    const int smem = CUM_BYTES + 144 * 8 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_digitize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess)
-            return fail(CGRB_E_CUDA, "cgrb_digitize: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    LAUNCH("k_digitize", (cudaStream_t)stream, k_digitize<<<(unsigned)n_work, DIGITIZE_NT, smem, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
+    LAUNCH("k_digitize", (cudaStream_t)stream, k_digitize<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
                                                                      d_energy_src, d_pha_src, d_counts));
     return check_launch("cgrb_digitize");
 }
@@ -1849,7 +2080,7 @@ int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int
         chan = *rng_chan;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH("k_gap_sums<1>", s, k_gap_sums<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_counts));
+    LAUNCH("k_gap_prefix<1>", s, k_gap_prefix<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_times_bkg, d_counts));
     LAUNCH("k_seg_scan<1>", s, k_seg_scan<1><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
                                                            d_segstart, d_counts));
     LAUNCH("k_background", s, k_background<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng_time, chan, d_segstart,

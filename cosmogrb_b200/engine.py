@@ -22,7 +22,7 @@ from . import _capi
 from ._capi import COUNTS_DTYPE, UNIT_DTYPE, WORK_DTYPE, RngDesc
 
 DEFAULT_SEED = 0x00C0560612B
-ENERGY_CHUNK = 1024          # photons per CTA work item of the energy kernels
+ENERGY_CHUNK = 4096          # photons per CTA work item of the energy kernels
 DIGITIZE_CHUNK = 65536       # photons per CTA of the digitize kernel (amortises staging the 143 KB matrix)
 DEFAULT_MAX_TRIALS = 1 << 22
 
@@ -391,19 +391,28 @@ class Engine(object):
             "cgrb_sample_events")
         self.launches += 4
 
-    def sample_energy(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, want_trials=False, sampler=None):
+    def sample_energy(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, want_trials=False, sampler=None,
+                      fold=False, want_energy=True):
         """``sampler``: "literal" (the reference's rejection loop, trial for trial; always used under
-        injected uniforms) or "envelope" (same output distribution from a tight envelope, Philox
-        only; the default under Philox)."""
+        injected uniforms) or "envelope" (same output distribution from a tabulated envelope, Philox
+        only; the default under Philox).  ``fold=True`` (envelope sampler only) also folds every photon
+        through the response in the same kernel (``pha_src``, identical to ``digitize_batch`` with the
+        same Philox seed); the energies themselves are then written only if ``want_energy``.
+        Returns True if the channels were produced."""
         torch = _torch()
         sampler = sampler or self.energy_sampler
         if isinstance(rng, Injected):
             sampler = "literal"
         if sampler not in ("literal", "envelope"):
             raise ValueError("sampler must be 'literal' or 'envelope'")
+        fold = bool(fold) and sampler == "envelope"
         w, dw, _ = self._work(b, 3, ENERGY_CHUNK)
         t = b.t
-        t["energy_src"] = self.empty(b.n_src_slots, torch.float64)
+        en = None
+        if want_energy or not fold:
+            t["energy_src"] = en = self.empty(b.n_src_slots, torch.float64)
+        else:
+            t.pop("energy_src", None)
         tr = None
         if want_trials:
             t["trials"] = tr = torch.zeros(max(b.n_src_slots, 1), dtype=torch.int32, device=self.device)
@@ -411,15 +420,19 @@ class Engine(object):
         if sampler == "envelope":
             if "etab" not in t:
                 t["etab"] = self.empty(self.lib.cgrb_energy_workspace_bytes(b.n_units, b.n_etab_rows), torch.uint8)
+            pha = None
+            if fold:
+                t["pha_src"] = pha = self.empty(b.n_src_slots, torch.uint8)
             _capi.check(
                 self.lib.cgrb_sample_energy_envelope(
                     b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
                     self._extrap_code(b.interp_extrap), C.byref(desc), int(max_trials), t["etab"].data_ptr(),
-                    b.n_etab_rows, t["times_src"].data_ptr(), t["energy_src"].data_ptr(),
+                    b.n_etab_rows, t["times_src"].data_ptr(), en.data_ptr() if en is not None else None,
+                    pha.data_ptr() if pha is not None else None,
                     tr.data_ptr() if want_trials else None, b.d_counts.data_ptr(), self.stream),
                 "cgrb_sample_energy_envelope")
             self.launches += 3
-            return
+            return fold
         _capi.check(
             self.lib.cgrb_sample_energy(
                 b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
@@ -428,6 +441,7 @@ class Engine(object):
                 tr.data_ptr() if want_trials else None, b.d_counts.data_ptr(), self.stream),
             "cgrb_sample_energy")
         self.launches += 1
+        return False
 
     def digitize_batch(self, b, rng):
         torch = _torch()
@@ -498,8 +512,10 @@ class Engine(object):
         """LightCurve.process() for every unit of the batch (lightcurve.py:167-200): source times,
         energies, channels; background times, channels; combine; dead time."""
         self.sample_events(b, rng, want_candidates=diagnostics)
-        self.sample_energy(b, rng, max_trials=max_trials, want_trials=diagnostics, sampler=energy_sampler)
-        self.digitize_batch(b, rng)
+        folded = self.sample_energy(b, rng, max_trials=max_trials, want_trials=diagnostics, sampler=energy_sampler,
+                                    fold=True, want_energy=diagnostics)
+        if not folded:
+            self.digitize_batch(b, rng)
         self.sample_background(b, rng)
         self.combine(b)
         self.dead_time(b, want_selection=diagnostics)

@@ -136,6 +136,7 @@ class Response(object):
             t[oa:oa + n] = interp_table(self.effective_area_packed[0], self.effective_area_packed[1],
                                         grid, interp_extrap)
         t[_capi.DT_CUM:_capi.DT_CUM + nb * nc] = self._cumulative_maxtrix.reshape(-1)
+        t[_capi.DT_GUIDE:_capi.DT_GUIDE + nb * nc // 8] = channel_search_guide(self._cumulative_maxtrix).view("f8")
         self._device_tables[key] = t
         return t
 
@@ -186,4 +187,18 @@ class Response(object):
         return self._cumulative_maxtrix
 
 
-__all__ = ["Response", "interp_table", "Interp1D"]
+def channel_search_guide(cumulative_matrix):
+    """uint8 [NBINS*NCHAN] guide of the device channel search (include/cosmogrb_b200.h, CGRB_DT_GUIDE):
+    guide[b][m] = np.searchsorted(cum[b], m / NCHAN, 'left'), the first channel whose cumulative
+    probability reaches m/NCHAN (NCHAN if none).  The lower bound of any r in [m/NCHAN, (m+1)/NCHAN) is
+    at or after it, so the device walks forward from there and finds exactly what a full search finds."""
+    cum = np.asarray(cumulative_matrix, dtype="f8")
+    nb, nc = cum.shape
+    marks = np.arange(nc, dtype="f8") / nc
+    g = np.empty((nb, nc), dtype=np.uint8)
+    for b in range(nb):
+        g[b] = np.searchsorted(cum[b], marks, side="left")
+    return np.ascontiguousarray(g.reshape(-1))
+
+
+__all__ = ["Response", "interp_table", "Interp1D", "channel_search_guide"]

@@ -71,7 +71,10 @@ extern "C" {
 #define CGRB_DT_G500_E 720     /* [500] 10**linspace(log10 emin, log10 emax, 500)                     */
 #define CGRB_DT_G500_A 1220    /* [500] interp(ea_x, ea_y, G500_E)                                    */
 #define CGRB_DT_CUM 1720       /* [140*128] row-normalised cumulative matrix (16-byte aligned: 13760 B) */
-#define CGRB_DT_SIZE (1720 + 140 * 128) /* 19640 doubles = 157120 B per detector                     */
+#define CGRB_DT_GUIDE (1720 + 140 * 128) /* [140*128] BYTES: guide[b][m] = searchsorted(cum[b], m/128, 'left')
+                                           (0..128): the channel search for r starts at guide[b][floor(128 r)]
+                                           and walks forward -- same result as a full search, ~2 probes    */
+#define CGRB_DT_SIZE (1720 + 140 * 128 + 140 * 128 / 8) /* 21880 doubles = 175040 B per detector        */
 
 /* one (GRB, detector) work unit; 224 bytes, device array uploaded by the caller */
 typedef struct {
@@ -226,13 +229,16 @@ int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
  * ~1.1-1.3 trials per photon instead of tens to hundreds.  Every unit owns etab_nw >= 1 rows starting
  * at row etab_off (ascending); n_rows = total rows of the batch.  d_workspace:
  * cgrb_energy_workspace_bytes(n_units, n_rows) bytes of device memory.  Injected uniforms replay the
- * reference's stream and therefore must use cgrb_sample_energy (returns CGRB_E_UNSUPPORTED). */
+ * reference's stream and therefore must use cgrb_sample_energy (returns CGRB_E_UNSUPPORTED).
+ * Fused fold: with d_pha_src != NULL the kernel also performs Response.digitize on every accepted
+ * energy (same Philox counters as cgrb_digitize, hence the same channels) and d_energy_src may then
+ * be NULL, so photon energies never travel through HBM. */
 int64_t cgrb_energy_workspace_bytes(int n_units, int64_t n_rows);
 int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                                 const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
                                 const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
-                                const double *d_times_src, double *d_energy_src, int32_t *d_trials,
-                                cgrb_counts_t *d_counts, void *stream);
+                                const double *d_times_src, double *d_energy_src, uint8_t *d_pha_src,
+                                int32_t *d_trials, cgrb_counts_t *d_counts, void *stream);
 
 /* Response.digitize (response.py:156-174; numba _digitize :10-25): nearest-CDF channel.
  * Work list as for cgrb_sample_energy. */

@@ -195,6 +195,11 @@ def test_combine_and_dead_time_pipeline(engine):
     # energies inside the response range, channels valid
     e = b.view("energy_src", 0, "src")
     assert np.all((e >= rsp.emin) & (e <= rsp.emax))
+    # the fold fused into the energy kernel == the standalone digitize kernel on the same energies
+    # (same Philox counters), which in turn is the oracle's _digitize given the uniforms (test above)
+    fused = b.view("pha_src", 0, "src").copy()
+    engine.digitize_batch(b, Philox(1234))
+    assert np.array_equal(fused, b.view("pha_src", 0, "src"))
     # re-derive the source channels with the oracle from the same Philox uniforms is not possible
     # (device counters), so check determinism instead: same seed -> identical output
     rsp2, b2 = _batch(engine, params)
