@@ -188,6 +188,7 @@ KERNEL_BYTES = {
     "k_sample_energy_env": 16.0,  # reads time, writes energy per source event
     # algorithmic HBM bytes per EVENT of each kernel's own product
     "k_background": 9.0,        # writes f64 time + u8 channel per background event
+    "k_merge_deadtime": 18.0,   # reads 9 B (component lists), writes <= 9 B (survivors) per merged event
     "k_combine": 18.0,          # reads 9 B, writes 9 B per merged event
     "k_deadtime_count": 9.0,    # reads 9 B per merged event
     "k_deadtime_write": 18.0,   # reads 9 B, writes <= 9 B per merged event
@@ -299,7 +300,7 @@ def run_gpu(args):
     top = max(kern, key=lambda n: kern[n]["ms_per_step"])
     n_src, n_bkg = int(counts["n_src"].sum()), int(counts["n_bkg"].sum())
     n_tot = n_src + n_bkg
-    units_of = {"k_background": n_bkg, "k_combine": n_tot, "k_deadtime_count": n_tot, "k_deadtime_write": n_tot,
+    units_of = {"k_background": n_bkg, "k_merge_deadtime": n_tot, "k_gap_prefix": n_src, "k_combine": n_tot, "k_deadtime_count": n_tot, "k_deadtime_write": n_tot,
                 "k_source_thin": n_src, "k_source_gather": n_src, "k_sample_energy": n_src, "k_digitize": n_src,
                 "k_sample_energy_env": n_src}
     peaks = {}
@@ -322,8 +323,9 @@ def run_gpu(args):
     roofline = hbm_roofline(top)
     roofline["note"] = ("dominant kernel of this source-dominated workload is fp64-issue bound, not HBM bound: "
                         "its HBM fraction is small by construction; see profiles/ for issue utilisation")
-    hbm_kernels = [hbm_roofline(n) for n in kern if n.split("<")[0] in ("k_background", "k_combine",
-                                                                           "k_deadtime_count", "k_deadtime_write")]
+    hbm_kernels = [hbm_roofline(n) for n in kern if n.split("<")[0] in ("k_background", "k_merge_deadtime", "k_combine",
+                                                                           "k_deadtime_count", "k_deadtime_write",
+                                                                           "k_source_gather")]
 
     # ---- e2e arm: the public API, GBMGRB_CPL(...).go(): host objects in, host arrays out -------------
     # The burst object is built once (like the reference, construction = responses, backgrounds and

@@ -23,6 +23,7 @@ NT_FMAX = 50
 SEG = 8192
 MERGE_TILE = 2048
 DT_TILE = 2048
+MD_TILE = 2048
 ENV_MAXW = 256
 
 # detector table block layout (doubles) -- must match include/cosmogrb_b200.h
@@ -115,6 +116,8 @@ EXPORTS = (
     "cgrb_background_channels",
     "cgrb_combine",
     "cgrb_gbm_dead_time",
+    "cgrb_merge_dead_time_workspace_bytes",
+    "cgrb_merge_dead_time",
 )
 
 _lib = None
@@ -156,9 +159,13 @@ def load():
     lib.cgrb_background_channels.argtypes = [vp, i32, C.c_uint32, rp, i64, vp, vp]
     lib.cgrb_combine.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.cgrb_gbm_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_merge_dead_time_workspace_bytes.argtypes = [i64]
+    lib.cgrb_merge_dead_time_workspace_bytes.restype = i64
+    lib.cgrb_merge_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count", "cgrb_energy_workspace_bytes"):
+        if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count", "cgrb_energy_workspace_bytes",
+                        "cgrb_merge_dead_time_workspace_bytes"):
             fn.restype = i32
     if lib.cgrb_abi_version() != ABI_VERSION:
         raise EngineUnavailable(

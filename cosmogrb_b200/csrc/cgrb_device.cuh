@@ -39,11 +39,11 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
-// 53-bit uniform in [0,1): same construction as MT19937's random_sample
-// ((a >> 5) * 2^26 + (b >> 6)) / 2^53.
+// uniform double in [0,1) from 64 random bits: the top 52 bits become the mantissa of a double in
+// [1,2), minus one (resolution 2^-52; two shifts, two ORs and one add -- no integer-to-double conversions)
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b)
 {
-    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+    return __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)((a << 20) | (b >> 12))) - 1.0;
 }
 
 // stages (Philox counter word 3)

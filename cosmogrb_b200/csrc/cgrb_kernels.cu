@@ -5,6 +5,7 @@
 // repository root.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -1175,6 +1176,9 @@ __device__ __forceinline__ double rcp_fast(double d)
     return r * (2.0 - d * r);
 }
 
+#ifndef ENV_MIN_CTAS
+#define ENV_MIN_CTAS 3
+#endif
 struct EnvSmem {
     double xlo[CGRB_ENV_SEGS];
     double invMx[CGRB_ENV_SEGS];
@@ -1195,7 +1199,8 @@ struct EnvSmem {
 // follows from the effective-area bracket already in hand and the channel search starts from the
 // detector's guide table staged in shared memory -- so energies never have to travel through HBM
 // (energy_src may be NULL).
-__global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__restrict__ dtab,
+template <bool FOLD, bool DIAG, int MINB>   // FOLD: also digitize (pha_src); DIAG: write energies / trial counts
+__global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__restrict__ dtab,
                                                           const cgrb_unit_t *__restrict__ units,
                                                           const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                           int interp_extrap, cgrb_rng_t rng, int64_t max_trials,
@@ -1242,7 +1247,7 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
     }
     __syncthreads();
     const double *dt = dtab + (size_t)u.det * CGRB_DT_SIZE;
-    if (threadIdx.x == 0 && pha_src)
+    if (FOLD && threadIdx.x == 0)
         guide_stage(s_guide, &s_bar, dt);
     for (int m = threadIdx.x; m < CGRB_NBINS; m += NT) {
         const double x0 = dt[CGRB_DT_EA_X + m], y0 = dt[CGRB_DT_EA_Y + m];
@@ -1282,7 +1287,7 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
         ck[11] = 1.0 / (1.0 + u.z);
     }
     __syncthreads();
-    if (pha_src)
+    if (FOLD)
         guide_wait(&s_bar);
 #define c_du ck[1]
 #define c_a ck[2]
@@ -1301,6 +1306,7 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
     int64_t chunk_end = n_src;
     if (w + 1 < n_work && work[w + 1].unit == wk.unit)
         chunk_end = min(n_src, work[w + 1].start);
+    const uint32_t trial_cap = (max_trials > 0 && max_trials < 0xffffffffll) ? (uint32_t)max_trials : 0xffffffffu;
 
     // Lane refill: every warp owns a contiguous slice of the chunk; a lane that accepted immediately takes
     // the warp's next photon, so no lane idles on a neighbour's geometric tail.
@@ -1380,11 +1386,11 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
                     EaGuess eg = make_ea_guess(sm.eax);
                     const double x = literal_photon_serial(u, dt, sm.eax, sm.eay, eg, interp_extrap, rng.seed, i, t,
                                                            max_trials, &ntr, &capped);
-                    if (energy_src)
+                    if (DIAG && energy_src)
                         energy_src[u.src_off + i] = x;
-                    if (pha_src)
+                    if (FOLD)
                         pha_src[u.src_off + i] = (uint8_t)digitize_one(sm.edges, s_guide, cum, x, rng.seed, u.stream_id, i);
-                    if (trials_out)
+                    if (DIAG && trials_out)
                         trials_out[u.src_off + i] = (int32_t)ntr;
                     my_trials += ntr;
                 }
@@ -1401,7 +1407,7 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
             const double U = u53(p.x, p.y), V = u53(p.z, p.w);
             const double y = U * total;
             // segment: row[lo] <= y < row[lo+1], walking forward from the row's guide
-            int lo = unit_guides[(size_t)k * CGRB_ENV_SEGS + min((int)(U * (double)CGRB_ENV_SEGS), CGRB_ENV_SEGS - 1)];
+            int lo = unit_guides[k * CGRB_ENV_SEGS + min((int)(U * (double)CGRB_ENV_SEGS), CGRB_ENV_SEGS - 1)];
             double c0 = __ldg(row + lo), c1 = __ldg(row + lo + 1);
             while (lo < CGRB_ENV_SEGS - 1 && c1 <= y) {
                 lo++;
@@ -1416,7 +1422,8 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
             const double s = x * wq;
             // effective area at x: bracket from the segment's first node, then the linear piece
             int ib = min(max(sm.kn[lo] - 1, 0), CGRB_NBINS - 2);
-            while (ib < CGRB_NBINS - 2 && sm.eax[ib + 1] < x)
+            ib += (ib < CGRB_NBINS - 2 && sm.eax[ib + 1] < x) ? 1 : 0;   // a segment is narrower than a bin: 0 or 1 step
+            while (ib < CGRB_NBINS - 2 && sm.eax[ib + 1] < x)           // (any other table: keep walking)
                 ib++;
             double A = sm.eay[ib] + sm.esl[ib] * (x - sm.eax[ib]);
             if (interp_extrap == 1) {
@@ -1443,15 +1450,15 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
                 acc = false;
             else
                 acc = V <= base * exp(-d);
-            const bool cap = !acc && max_trials > 0 && (int64_t)j >= max_trials;
+            const bool cap = !acc && j >= trial_cap;
             if (acc || cap) {
-                if (energy_src)
+                if (DIAG && energy_src)
                     energy_src[u.src_off + i] = acc ? x : nan("");
-                if (pha_src) {
+                if (FOLD) {
                     int pha;
                     if (acc) {
                         // photon bin = searchsorted(edges, x, 'left') - 1, walked from the bracket
-                        int b = ib;
+                        int b = ib + ((sm.edges[ib + 1] < x) ? 1 : 0);   // the bin centre bracket straddles one edge
                         while (b < CGRB_NBINS - 1 && sm.edges[b + 1] < x)
                             b++;
                         while (b >= 0 && !(sm.edges[b] < x))
@@ -1464,7 +1471,7 @@ __global__ void __launch_bounds__(NT, 3) k_sample_energy_env(const double *__res
                         pha = digitize_one(sm.edges, s_guide, cum, nan(""), rng.seed, u.stream_id, i);
                     pha_src[u.src_off + i] = (uint8_t)pha;
                 }
-                if (trials_out)
+                if (DIAG && trials_out)
                     trials_out[u.src_off + i] = (int32_t)j;
                 my_trials += j;
                 capped |= cap;
@@ -1775,6 +1782,355 @@ __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__rest
     }
 }
 
+// ==========================================================================================
+// combine + dead time in ONE pass (lightcurve.py:131-151 then gbm_lightcurve.py:42-56): the merged
+// pre-dead-time list is not a product of LightCurve.process (light_curve_storage.py:16-80 keeps the two
+// component lists and the filtered total), so it never has to exist in HBM.  Each CTA merges one tile
+// of the merged order (plus a look-back halo) in shared memory, resolves the keep flags there with the
+// same literal rule as dt_keep, and appends the survivors to the unit's output at an offset obtained by a
+// decoupled look-back over the preceding tiles' survivor counts (integers: deterministic).
+// 9 B read + <= 9 B written per event.
+// ==========================================================================================
+#define MD_TILE 2048
+#define MD_HALO 256
+#define MD_N (MD_TILE + MD_HALO)
+#define MD_FLAG_AGG (1ull << 62)
+#define MD_FLAG_INC (2ull << 62)
+#define MD_VALUE_MASK ((1ull << 62) - 1ull)
+
+// merge-path split of diagonal d: number of background events among the first d merged events
+__device__ __forceinline__ int64_t merge_split(const double *__restrict__ A, int64_t nA, const double *__restrict__ B,
+                                               int64_t nB, int64_t d)
+{
+    int64_t lo = max((int64_t)0, d - nB), hi = min(d, nA);
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (A[mid] <= B[d - 1 - mid])     // ties: background first
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// merged event g read straight from the two global lists (O(log n) per access: the rare slow path)
+struct MergedGlobal {
+    const double *A, *B;
+    const uint8_t *pA, *pB;
+    int64_t nA, nB;
+    __device__ __forceinline__ void get(int64_t g, double *t, uint8_t *p) const
+    {
+        const int64_t ia = merge_split(A, nA, B, nB, g), ib = g - ia;
+        if (ia < nA && (ib >= nB || A[ia] <= B[ib])) {
+            *t = A[ia];
+            *p = pA[ia];
+        } else {
+            *t = B[ib];
+            *p = pB[ib];
+        }
+    }
+};
+
+// the literal dead-time rule for merged event g (same walk as dt_keep) on the slow accessor
+__device__ __noinline__ bool dt_keep_slow(const MergedGlobal &m, int64_t i)
+{
+    if (i == 0)
+        return true;
+    double ti, tj;
+    uint8_t pi, pj;
+    m.get(i, &ti, &pi);
+    int64_t found = -1;
+    for (int64_t j = i - 1; j >= 0; j--) {
+        m.get(j, &tj, &pj);
+        if (tj + DT_TAU < ti)
+            break;
+        if (pj == 127 || j == 0) {
+            found = j;
+            break;
+        }
+    }
+    if (found < 0)
+        return true;
+    int64_t head = found;
+    while (head > 0) {
+        double th;
+        uint8_t ph;
+        m.get(head, &th, &ph);
+        int64_t q = -1;
+        double tq = 0.0;
+        uint8_t pq = 0;
+        for (int64_t j = head - 1; j >= 0; j--) {
+            m.get(j, &tq, &pq);
+            if (tq + DT_TAU < th)
+                break;
+            if (pq == 127 || j == 0) {
+                q = j;
+                break;
+            }
+        }
+        if (q < 0 || tq + ((q == 0 && pq != 127) ? DT_NORMAL : DT_TAU) < th)
+            break;
+        head = q;
+    }
+    double th;
+    uint8_t ph;
+    m.get(head, &th, &ph);
+    double t_end = th + ((head == 0 && ph != 127) ? DT_NORMAL : DT_TAU);
+    for (int64_t j = head + 1; j < i; j++) {
+        m.get(j, &tj, &pj);
+        if (pj == 127 && tj > t_end)
+            t_end = tj + DT_TAU;
+    }
+    return ti > t_end;
+}
+
+// the same rule on the tile in shared memory: local index li <-> merged rank g0 + li.  Returns 0 / 1, or 2
+// if the walk would leave the tile's halo (the caller then takes the slow path).
+__device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, int li, int64_t g0)
+{
+    if (g0 + li == 0)
+        return 1;
+    const bool has0 = (g0 == 0);            // local index 0 is the unit's event 0
+    const double ti = t[li];
+    int found = -1;
+    int j = li - 1;
+    for (; j >= 0; j--) {
+        if (t[j] + DT_TAU < ti)
+            return 1;                       // nothing within the longest window: kept
+        if (p[j] == 127 || (has0 && j == 0)) {
+            found = j;
+            break;
+        }
+    }
+    if (found < 0)
+        return 2;                           // ran out of halo
+    int head = found;
+    for (;;) {
+        if (has0 && head == 0)
+            break;
+        const double th = t[head];
+        int q = -1;
+        int jj = head - 1;
+        bool gap = false;
+        for (; jj >= 0; jj--) {
+            if (t[jj] + DT_TAU < th) {
+                gap = true;
+                break;
+            }
+            if (p[jj] == 127 || (has0 && jj == 0)) {
+                q = jj;
+                break;
+            }
+        }
+        if (q < 0) {
+            if (gap)
+                break;                      // nothing before `head` can veto it
+            return 2;                       // ran out of halo
+        }
+        const double pe = t[q] + ((has0 && q == 0 && p[0] != 127) ? DT_NORMAL : DT_TAU);
+        if (pe < th)
+            break;
+        head = q;
+    }
+    double t_end = t[head] + ((has0 && head == 0 && p[0] != 127) ? DT_NORMAL : DT_TAU);
+    for (int jj = head + 1; jj < li; jj++)
+        if (p[jj] == 127) {
+            const double tj = t[jj];
+            if (tj > t_end)
+                t_end = tj + DT_TAU;
+        }
+    return ti > t_end ? 1 : 0;
+}
+
+// merge-path splits of every tile, one thread per tile: the ~23 dependent probes of each search are
+// hidden by the other tiles' searches instead of stalling a whole CTA at its first barrier.
+// splits[2w] = split at the tile's halo start, splits[2w+1] = split at the tile start.
+__global__ void __launch_bounds__(NT) k_merge_splits(const cgrb_unit_t *__restrict__ units,
+                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                     const double *__restrict__ times_bkg,
+                                                     const double *__restrict__ times_src,
+                                                     int64_t *__restrict__ splits, const cgrb_counts_t *counts)
+{
+    const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
+    if (wk.start >= nA + nB)
+        return;
+    const double *A = times_bkg + u->bkg_off;
+    const double *B = times_src + u->src_off;
+    splits[2 * w] = merge_split(A, nA, B, nB, max((int64_t)0, wk.start - MD_HALO));
+    splits[2 * w + 1] = merge_split(A, nA, B, nB, wk.start);
+}
+
+#define MD_PER (MD_N / NT)       // merged elements per thread in the serial merge (9)
+#define MD_R (MD_TILE / NT)     // tile elements per thread in the dead-time pass (8)
+
+__global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
+                                                       const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                       const int64_t *__restrict__ unit_work_begin,
+                                                       const double *__restrict__ times_bkg,
+                                                       const uint8_t *__restrict__ pha_bkg,
+                                                       const double *__restrict__ times_src,
+                                                       const uint8_t *__restrict__ pha_src,
+                                                       unsigned long long *tile_state,
+                                                       const int64_t *__restrict__ splits,
+                                                       double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
+                                                       cgrb_counts_t *counts)
+{
+    __shared__ double s_in_t[MD_N];         // the two input slices, background first
+    __shared__ double s_t[MD_N];            // merged
+    __shared__ uint8_t s_in_p[MD_N];
+    __shared__ uint8_t s_p[MD_N];
+    __shared__ int s_cnt[MD_R * NW];        // survivors per (round, warp), then their exclusive prefix
+    __shared__ long long s_excl;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
+    const int64_t total = nA + nB;
+    const int64_t wb = unit_work_begin[wk.unit], we = unit_work_begin[wk.unit + 1];
+    const double *A = times_bkg + u->bkg_off;
+    const double *B = times_src + u->src_off;
+    const uint8_t *pA = pha_bkg + u->bkg_off;
+    const uint8_t *pB = pha_src + u->src_off;
+    const int64_t d0 = wk.start, d1 = min(d0 + (int64_t)MD_TILE, total);
+    const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool live = d0 < total;
+    const int l0 = (int)(d0 - g0), nt = live ? (int)(d1 - d0) : 0;
+
+    unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
+    if (live) {
+        // d1 is either the next tile's start (same unit) or the end of the merged list
+        const int64_t i0 = splits[2 * w], i1 = (d1 == total) ? nA : splits[2 * (w + 1) + 1];
+        const int64_t j0 = g0 - i0, j1 = d1 - i1;
+        const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+        for (int k = threadIdx.x; k < na; k += NT) {
+            s_in_t[k] = A[i0 + k];
+            s_in_p[k] = pA[i0 + k];
+        }
+        for (int k = threadIdx.x; k < nb; k += NT) {
+            s_in_t[na + k] = B[j0 + k];
+            s_in_p[na + k] = pB[j0 + k];
+        }
+        __syncthreads();
+        // serial merge of MD_PER consecutive outputs per thread from its merge-path split
+        {
+            const double *a_ = s_in_t, *b_ = s_in_t + na;
+            const int n = na + nb;
+            const int q0 = min(threadIdx.x * MD_PER, n);
+            int lo = max(0, q0 - nb), hi = min(q0, na);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            int ia = lo, ib = q0 - lo;
+#pragma unroll
+            for (int r = 0; r < MD_PER; r++) {
+                const int q = q0 + r;
+                if (q < n) {
+                    const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
+                    const int src = take_a ? ia : na + ib;
+                    s_t[q] = s_in_t[src];
+                    s_p[q] = s_in_p[src];
+                    ia += take_a ? 1 : 0;
+                    ib += take_a ? 0 : 1;
+                }
+            }
+        }
+        __syncthreads();
+        // keep flags of the tile's own events (local indices [l0, l0 + nt))
+        MergedGlobal mg{A, B, pA, pB, nA, nB};
+#pragma unroll
+        for (int r = 0; r < MD_R; r++) {
+            const int e = r * NT + threadIdx.x;
+            int keep = 0;
+            if (e < nt) {
+                keep = dt_keep_local(s_t, s_p, l0 + e, g0);
+                if (keep == 2)
+                    keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0)
+                s_cnt[r * NW + wid] = __popc(bal);
+            // rank inside the (round, warp) group, kept in the upper bits
+            keep_bits |= (unsigned)keep << r;
+        }
+    } else if (threadIdx.x < MD_R * NW)
+        s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+
+    // warp 0: exclusive prefix of the 64 group counts, then the decoupled look-back over the unit's
+    // earlier tiles for this tile's offset in the unit's output
+    if (wid == 0) {
+        int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        int incl = warp_incl_scan_i(c0 + c1, lane);
+        const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
+        s_cnt[2 * lane] = incl - c0 - c1;
+        s_cnt[2 * lane + 1] = incl - c1;
+        if (lane == 0) {
+            const unsigned long long mine = (unsigned long long)cnt_tile | (w == wb ? MD_FLAG_INC : MD_FLAG_AGG);
+            atomicExch(tile_state + w, mine);
+        }
+        long long excl = 0;
+        if (w > wb) {
+            int64_t idx = w - 1;            // lanes look at idx, idx-1, ..., idx-31
+            for (;;) {
+                const int64_t my = idx - lane;
+                unsigned long long st = MD_FLAG_INC;            // before the unit's first tile: prefix 0
+                if (my >= wb) {
+                    do {
+                        st = *((volatile unsigned long long *)(tile_state + my));
+                    } while ((st >> 62) == 0ull);
+                }
+                const unsigned inc = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
+                const int first_inc = inc ? (__ffs(inc) - 1) : 32;     // nearest tile with an inclusive prefix
+                long long v = (lane <= first_inc && my >= wb) ? (long long)(st & MD_VALUE_MASK) : 0;
+#pragma unroll
+                for (int dlt = 16; dlt > 0; dlt >>= 1)
+                    v += __shfl_xor_sync(0xffffffffu, v, dlt);
+                excl += v;
+                if (inc)
+                    break;
+                idx -= 32;
+            }
+            if (lane == 0)
+                atomicExch(tile_state + w, (unsigned long long)(excl + cnt_tile) | MD_FLAG_INC);
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (w == wb)
+                counts[wk.unit].n_total = total;
+            if (w == we - 1)
+                counts[wk.unit].n_kept = excl + cnt_tile;
+        }
+    }
+    __syncthreads();
+    if (!live)
+        return;
+    double *ot = times_out + u->tot_off + s_excl;
+    uint8_t *op = pha_out + u->tot_off + s_excl;
+#pragma unroll
+    for (int r = 0; r < MD_R; r++) {
+        // survivors of (round r, this warp) before this lane
+        unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
+        if ((keep_bits >> r) & 1u) {
+            const int rank = s_cnt[r * NW + wid] + __popc(bal & ((1u << lane) - 1u));
+            const int li = l0 + r * NT + threadIdx.x;
+            ot[rank] = s_t[li];
+            op[rank] = s_p[li];
+        }
+    }
+}
+
 // BackgroundSpectrumTemplate.sample_channel(size) on its own (background.py:80-93): n draws from the
 // detector's channel cdf; Philox index = event index (stage ST_BKG, sub-stream 1), or injected u[i].
 __global__ void __launch_bounds__(NT) k_background_channels(const double *__restrict__ dtab, int det, uint32_t stream_id,
@@ -2037,9 +2393,30 @@ int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units
     uint8_t *row_guides = (uint8_t *)(rows + (size_t)ENV_ROW * n_rows);
     LAUNCH("k_energy_tables", s, k_energy_tables<<<n_units, 256, 0, s>>>(d_dtab, d_units, n_units, interp_extrap, etab));
     LAUNCH("k_energy_rows", s, k_energy_rows<<<(unsigned)n_rows, NT, 0, s>>>(d_units, n_units, etab, rows, row_guides, n_rows));
-    LAUNCH("k_sample_energy_env", s, k_sample_energy_env<<<(unsigned)n_work, NT, 0, s>>>(
-        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, rows, row_guides, d_times_src,
-        d_energy_src, d_pha_src, d_trials, d_counts));
+#define ENV_LAUNCH(F, D, M)                                                                                       \
+    LAUNCH("k_sample_energy_env", s, (k_sample_energy_env<F, D, M><<<(unsigned)n_work, NT, 0, s>>>(                \
+        d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, rows, row_guides, d_times_src,    \
+        d_energy_src, d_pha_src, d_trials, d_counts)))
+    const bool diag = d_energy_src != nullptr || d_trials != nullptr;
+    // resident CTAs per SM the production variant is compiled for (register budget); CGRB_ENV_MIN_CTAS=2|3
+    // switches it for tuning runs
+    static int minb = 0;
+    if (!minb) {
+        const char *e = getenv("CGRB_ENV_MIN_CTAS");
+        minb = (e && e[0] == '2') ? 2 : (e && e[0] == '4') ? 4 : ENV_MIN_CTAS;
+    }
+    if (d_pha_src && diag)
+        ENV_LAUNCH(true, true, ENV_MIN_CTAS);
+    else if (d_pha_src) {
+        if (minb == 2)
+            ENV_LAUNCH(true, false, 2);
+        else if (minb == 4)
+            ENV_LAUNCH(true, false, 4);
+        else
+            ENV_LAUNCH(true, false, 3);
+    } else
+        ENV_LAUNCH(false, true, ENV_MIN_CTAS);
+#undef ENV_LAUNCH
     return check_launch("cgrb_sample_energy_envelope");
 }
 
@@ -2133,6 +2510,29 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
                                                      d_pha_tot, d_tile_count, d_times_out, d_pha_out,
                                                      d_selection, d_counts));
     return check_launch("cgrb_gbm_dead_time");
+}
+
+int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 24 * (n_work > 0 ? n_work : 0); }
+
+int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
+                         const int64_t *d_unit_work_begin, const double *d_times_bkg, const uint8_t *d_pha_bkg,
+                         const double *d_times_src, const uint8_t *d_pha_src, void *d_workspace,
+                         double *d_times_out, uint8_t *d_pha_out, cgrb_counts_t *d_counts, void *stream)
+{
+    if (!d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_times_bkg || !d_pha_bkg ||
+        !d_times_src || !d_pha_src || !d_workspace || !d_times_out || !d_pha_out || !d_counts)
+        return fail(CGRB_E_BADARG, "cgrb_merge_dead_time: bad argument%s");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(d_workspace, 0, 8 * (size_t)n_work, s);
+    if (e != cudaSuccess)
+        return fail(CGRB_E_CUDA, "cgrb_merge_dead_time: memset: %s", cudaGetErrorString(e));
+    int64_t *splits = (int64_t *)d_workspace + n_work;
+    LAUNCH("k_merge_splits", s, k_merge_splits<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
+        d_units, d_work, n_work, d_times_bkg, d_times_src, splits, d_counts));
+    LAUNCH("k_merge_deadtime", s, k_merge_deadtime<<<(unsigned)n_work, NT, 0, s>>>(
+        d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
+        (unsigned long long *)d_workspace, splits, d_times_out, d_pha_out, d_counts));
+    return check_launch("cgrb_merge_dead_time");
 }
 
 }  // extern "C"

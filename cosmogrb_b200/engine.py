@@ -508,7 +508,26 @@ class Engine(object):
             "cgrb_gbm_dead_time")
         self.launches += 2
 
-    def process(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, diagnostics=False, energy_sampler=None):
+    def merge_dead_time(self, b):
+        """combine + dead time in one pass: only the survivors reach HBM (``times_out``/``pha_out``);
+        bit-identical to ``combine`` followed by ``dead_time``."""
+        torch = _torch()
+        w, dw, dwb = self._work(b, 2, _capi.MD_TILE)
+        t = b.t
+        t["tile_state"] = self.empty(self.lib.cgrb_merge_dead_time_workspace_bytes(len(w)), torch.uint8)
+        t["times_out"] = self.empty(b.n_tot_slots, torch.float64)
+        t["pha_out"] = self.empty(b.n_tot_slots, torch.uint8)
+        _capi.check(
+            self.lib.cgrb_merge_dead_time(
+                b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), dwb.data_ptr(),
+                t["times_bkg"].data_ptr(), t["pha_bkg"].data_ptr(), t["times_src"].data_ptr(),
+                t["pha_src"].data_ptr(), t["tile_state"].data_ptr(), t["times_out"].data_ptr(),
+                t["pha_out"].data_ptr(), b.d_counts.data_ptr(), self.stream),
+            "cgrb_merge_dead_time")
+        self.launches += 2
+
+    def process(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, diagnostics=False, energy_sampler=None,
+                keep_merged=False):
         """LightCurve.process() for every unit of the batch (lightcurve.py:167-200): source times,
         energies, channels; background times, channels; combine; dead time."""
         self.sample_events(b, rng, want_candidates=diagnostics)
@@ -517,8 +536,11 @@ class Engine(object):
         if not folded:
             self.digitize_batch(b, rng)
         self.sample_background(b, rng)
-        self.combine(b)
-        self.dead_time(b, want_selection=diagnostics)
+        if diagnostics or keep_merged:      # keeps the merged pre-dead-time list (and the per-event selection)
+            self.combine(b)
+            self.dead_time(b, want_selection=diagnostics)
+        else:
+            self.merge_dead_time(b)
         return b
 
     def check_status(self, b):
@@ -632,6 +654,33 @@ class Engine(object):
                                                       self.stream), "cgrb_background_channels")
         self.launches += 1
         return out[:n].cpu().numpy().astype(np.int64)
+
+    def combine_dead_time(self, times_bkg, pha_bkg, times_src, pha_src, fused=True):
+        """LightCurve._combine + GBMLightCurve._filter_deadtime for one detector's two time-sorted
+        event lists; returns (times, pha) of the survivors.  ``fused`` selects the one-pass kernel."""
+        torch = _torch()
+        nb, ns = len(times_bkg), len(times_src)
+        u = make_units(1)
+        u["src_cap"], u["bkg_cap"] = max(ns - 1, 0), max(nb - 1, 0)
+        b = Batch(self, u, None, self.interp_extrap)
+        b.n_src_slots, b.n_bkg_slots = int(u["src_cap"][0]) + 1, int(u["bkg_cap"][0]) + 1
+        b.n_tot_slots = b.n_src_slots + b.n_bkg_slots
+        b.d_units = self.to_device(u)
+        self.set_counts(b, n_src=ns, n_bkg=nb)
+        pad = lambda a, n, dt: np.concatenate((np.ascontiguousarray(a).astype(dt), np.zeros(max(n - len(a), 0) + 1, dt)))
+        b.t["times_src"] = self.to_device(pad(times_src, b.n_src_slots, "f8"))
+        b.t["pha_src"] = self.to_device(pad(pha_src, b.n_src_slots, np.uint8))
+        b.t["times_bkg"] = self.to_device(pad(times_bkg, b.n_bkg_slots, "f8"))
+        b.t["pha_bkg"] = self.to_device(pad(pha_bkg, b.n_bkg_slots, np.uint8))
+        if fused:
+            self.merge_dead_time(b)
+        else:
+            self.combine(b)
+            self.dead_time(b)
+        c = self.fetch_counts(b)
+        n = int(c["n_kept"][0])
+        assert int(c["n_total"][0]) == nb + ns
+        return b.t["times_out"][:n].cpu().numpy(), b.t["pha_out"][:n].cpu().numpy()
 
     def gbm_dead_time(self, times, pha):
         """_gbm_dead_time for one time-sorted event list; returns the boolean selection."""

@@ -106,7 +106,8 @@ def process_batch(lightcurves, seed=None, stream_ids=None, pinned=None):
     units = np.concatenate(units)
     need_fmax = bool(np.any(~(units["fmax"] > 0)))
     b = eng.new_batch(units, tabs, compute_fmax=need_fmax)
-    eng.process(b, Philox(eng.next_seed() if seed is None else seed))
-    extra = () if all(lc._deadtime for lc in lcs) else (("times_tot", "tot"), ("pha_tot", "tot"))
+    all_deadtime = all(lc._deadtime for lc in lcs)
+    eng.process(b, Philox(eng.next_seed() if seed is None else seed), keep_merged=not all_deadtime)
+    extra = () if all_deadtime else (("times_tot", "tot"), ("pha_tot", "tot"))
     arrays = eng.to_host(b, pinned, extra=extra)
     return [lc._storage_from(arrays, i) for i, lc in enumerate(lcs)]

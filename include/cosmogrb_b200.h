@@ -284,6 +284,20 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
                        double *d_times_out, uint8_t *d_pha_out, uint8_t *d_selection,
                        cgrb_counts_t *d_counts, void *stream);
 
+/* LightCurve._combine followed by GBMLightCurve._filter_deadtime in one pass (lightcurve.py:131-151,
+ * 189-190; gbm_lightcurve.py:42-56): the merged pre-dead-time list is not one of the products of
+ * LightCurve.process, so it is merged tile by tile in shared memory and only the survivors are written
+ * (compacted at tot_off; counts.n_total, counts.n_kept).  Bit-identical to cgrb_combine +
+ * cgrb_gbm_dead_time.  Work list: which=2, chunk=CGRB_MD_TILE; d_workspace:
+ * cgrb_merge_dead_time_workspace_bytes(n_work) bytes (tile states of the decoupled look-back; cleared
+ * by the call). */
+#define CGRB_MD_TILE 2048
+int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work);
+int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
+                         const int64_t *d_unit_work_begin, const double *d_times_bkg, const uint8_t *d_pha_bkg,
+                         const double *d_times_src, const uint8_t *d_pha_src, void *d_workspace,
+                         double *d_times_out, uint8_t *d_pha_out, cgrb_counts_t *d_counts, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,6 +172,33 @@ def test_dead_time_random(engine, rate, frac127):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("rate,frac127", [(500.0, 0.05), (2e5, 0.05), (2e6, 0.3), (5e6, 1.0)])
+def test_fused_merge_dead_time(engine, rate, frac127):
+    """The one-pass combine + dead-time kernel == the oracle's combine then _gbm_dead_time, bit for bit,
+    from sparse lists to rates where the dependence chains outrun the tile halo (slow path)."""
+    rs = np.random.RandomState(11)
+    n = 30_000 if rate > 1e6 else 1_000_000       # the slow path is O(chain length x log n) per event
+    ts = np.cumsum(rs.exponential(1.0 / rate, n))
+    tb = np.sort(rs.uniform(0.0, ts[-1], n // 3))
+    tb[5:8] = ts[100]                         # ties: background first
+    tb.sort()
+    ps = rs.randint(0, 127, n)
+    ps[rs.random_sample(n) < frac127] = 127
+    pb = rs.randint(0, 128, len(tb))
+    want_t, want_p = orc.combine(tb, pb, ts, ps)
+    sel = orc.gbm_dead_time(want_t, want_p)
+    for fused in (True, False):
+        got_t, got_p = engine.combine_dead_time(tb, pb, ts, ps, fused=fused)
+        assert np.array_equal(got_t, want_t[sel]), fused
+        assert np.array_equal(got_p.astype("f8"), want_p[sel]), fused
+    # degenerate shapes: one empty list, single events
+    for a, b_ in ((0, 5), (5, 0), (1, 1)):
+        got_t, got_p = engine.combine_dead_time(tb[:a], pb[:a], ts[:b_], ps[:b_])
+        wt, wp = orc.combine(tb[:a], pb[:a], ts[:b_], ps[:b_])
+        s2 = orc.gbm_dead_time(wt, wp)
+        assert np.array_equal(got_t, wt[s2]) and np.array_equal(got_p.astype("f8"), wp[s2])
+
+
 def test_combine_and_dead_time_pipeline(engine):
     """Full unit under Philox; the oracle re-does combine + dead time from the GPU's component lists."""
     params = h.CONFTEST_BRIGHT
@@ -203,9 +230,11 @@ def test_combine_and_dead_time_pipeline(engine):
     # re-derive the source channels with the oracle from the same Philox uniforms is not possible
     # (device counters), so check determinism instead: same seed -> identical output
     rsp2, b2 = _batch(engine, params)
-    engine.process(b2, Philox(1234))
-    engine.fetch_counts(b2)
+    engine.process(b2, Philox(1234))          # the production path: fused fold, fused combine + dead time
+    c2 = engine.fetch_counts(b2)
+    assert c2["n_total"][0] == c["n_total"][0] and c2["n_kept"][0] == c["n_kept"][0]
     assert np.array_equal(b2.view("times_out", 0, "kept"), want_t[sel])
+    assert np.array_equal(b2.view("pha_out", 0, "kept").astype("f8"), want_p[sel])
 
 
 def test_multi_unit_batch_independent_of_batching(engine):
