@@ -200,8 +200,32 @@ KERNEL_BYTES = {
 }
 
 
+def start_memlog():
+    """CGRB_MEMLOG=1: log this process's resident set size to stderr twice a second (debugging aid)"""
+    if not os.environ.get("CGRB_MEMLOG"):
+        return
+
+    def loop():
+        while True:
+            try:
+                with open("/proc/self/status") as f:
+                    rss = [l for l in f if l.startswith("VmRSS")][0].split()[1]
+                sys.stderr.write(f"[memlog] {time.time():.1f} rss_kb={rss} leg={_LEG[0]}\n")
+                sys.stderr.flush()
+            except Exception:
+                pass
+            time.sleep(0.5)
+
+    threading.Thread(target=loop, daemon=True).start()
+
+
+_LEG = ["init"]
+
+
 def run_gpu(args):
     import torch
+
+    start_memlog()
 
     import __graft_entry__ as ge
 
@@ -245,6 +269,7 @@ def run_gpu(args):
         return torch.cumsum(out.view(-1, 3), dim=0)
 
     # ---- resident-input arm ---------------------------------------------------------------------
+    _LEG[0] = "resident"
     batch = eng.new_batch(units, tabs)              # units + tables resident, fmax on device
 
     def step_resident(k):
@@ -334,6 +359,7 @@ def run_gpu(args):
     # of each of the 14 detectors in pinned host memory.
     from cosmogrb_b200 import gbm
 
+    _LEG[0] = "e2e"
     p = bright_params()
     grb = None if args.no_e2e else gbm.GBMGRB_CPL(ra=312.0, dec=-62.0, T0=0.1, name=f"bench_{rank}", **p)
 
@@ -369,6 +395,56 @@ def run_gpu(args):
         dist.all_reduce(ev_e2e_t, op=dist.ReduceOp.SUM)
     e2e_value = float(ev_e2e_t.item()) / (float(ms_e2e.item()) * 1e-3)
 
+    # ---- population leg (BASELINE.json configs[3]: 1,000 GRBs x 14 detectors per GPU, weak scaling) -------
+    # GRBs/s through the public API, Universe.go(): unit records built on the host, events stay in HBM,
+    # only the per-unit counters come back (+ the NCCL event-count gather across ranks).
+    population = None
+    _LEG[0] = "population"
+    if args.population > 0:
+        from cosmogrb_b200.instruments.gbm.gbm_universe import GBM_CPL_Universe
+        from cosmogrb_b200.universe import synthetic_population
+
+        warm = GBM_CPL_Universe(synthetic_population(64, seed=99 + rank), save_path=None)
+        warm.go(save=False, seed=seed)
+        uni = GBM_CPL_Universe(synthetic_population(args.population * world, seed=12345), save_path=None)
+        sync_all()
+        _capi.profile_enable(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        uni.go(save=False, seed=seed)
+        p1.record()
+        sync_all()
+        pprof = _capi.profile_read()
+        _capi.profile_enable(False)
+        ms_pop = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(ms_pop, op=dist.ReduceOp.MAX)
+        ms_pop = float(ms_pop.item())
+        ec = np.maximum(uni.event_counts, 0)          # skipped bursts read -1
+        n_ev = int(ec[:, :, 0].sum() + ec[:, :, 1].sum())
+        pk = {}
+        for name, m in pprof:
+            pk[name] = pk.get(name, 0.0) + m
+        tot_k = sum(pk.values()) or 1.0
+        # HBM roofline of the background-dominated kernels on this workload (local share of the events)
+        n_bkg_local = int(ec[uni.local_grbs][:, :, 1].sum())
+        n_tot_local = int(ec[uni.local_grbs][:, :, 0].sum()) + n_bkg_local
+        pop_roof = {}
+        for name, nb_, nu in (("k_background", 9.0, n_bkg_local), ("k_gap_prefix<1>", 8.0, n_bkg_local),
+                              ("k_merge_deadtime", 18.0, n_tot_local)):
+            if name in pk and pk[name] > 0:
+                ach = nb_ * nu / (pk[name] * 1e-3) / 1e9
+                pop_roof[name] = {"ms": pk[name], "achieved_gbs": ach, "frac_of_measured_hbm": ach / peak}
+        population = {
+            "workload": f"C4: {args.population} GRBs per GPU x 14 detectors, synthetic popsynth-style population "
+                        "(seed 12345), events stay in HBM, counters read back; bursts whose candidate count "
+                        "does not fit the memory budget are skipped (the reference's lambda(t) runs away for low Epeak)",
+            "n_grbs": int(uni.n_grbs), "n_skipped_per_gpu": len(uni.skipped), "events": n_ev, "ms": ms_pop, "grbs_per_s": uni.n_grbs / (ms_pop * 1e-3),
+            "events_per_s": n_ev / (ms_pop * 1e-3), "batches_per_gpu": int(uni.n_batches),
+            "kernel_ms_per_gpu": tot_k, "kernels": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])[:8]},
+            "hbm_kernels": pop_roof,
+        }
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as orc
@@ -398,7 +474,7 @@ def run_gpu(args):
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_hbm_kernels": hbm_kernels,
-            "kernels": kern, "cpu_baseline": cpu_baseline, "clocks": clk,
+            "kernels": kern, "cpu_baseline": cpu_baseline, "clocks": clk, "population": population,
         }
         emit(line)
     if dist is not None:
@@ -415,6 +491,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
+    ap.add_argument("--population", type=int, default=1000,
+                    help="GRBs per GPU of the population leg (GRBs/s through Universe.go); 0 = skip")
     args = ap.parse_args()
     # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, torchrun warnings)
     # write to fd 1 too, so everything else goes to stderr and the line is written to the real stdout

@@ -1435,10 +1435,12 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
             A = fmax(A, 0.0);
             if (sm.logAmax[lo] - xl * wq > t_clip)
                 A = fmin(A, exp(sm.hull_lA5[h] + s - s_idx));   // the literal envelope clips f here
-            // target / envelope = [A x^a / M_lo] exp(-d),  d = x w - xlo w_k >= 0, decided from the
-            // bounds 1 - d + d^2/2 - d^3/6 <= exp(-d) <= 1 - d + d^2/2 whenever they agree
+            // target / envelope = [A x^a / M_lo] exp(-d), decided from the bounds
+            // 1 - d + d^2/2 - d^3/6 <= exp(-d) <= 1 - d + d^2/2 whenever they agree.  The envelope of row k is
+            // M_j exp(-xlo_j w_k) exp(-emin (w - w_k)) >= M_j exp(-xlo_j w): the common factor in w - w_k costs
+            // nothing, so   d = (x - xlo) w + (xlo - emin) (w - w_k) >= 0.
             const double base = A * sm.invMx[lo] * exp_small(c_a * z);
-            const double d = fmax(s - xl * sm.wk[k], 0.0);
+            const double d = fmax((x - xl) * wq + (xl - sm.xlo[0]) * (wq - sm.wk[k]), 0.0);
             const double qhi = fma(d, fma(d, 0.5, -1.0), 1.0);
             const double qlo = qhi - d * d * d * (1.0 / 6.0);
             j++;

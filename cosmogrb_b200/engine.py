@@ -83,11 +83,20 @@ def fill_gamma_constants(units):
     return units
 
 
+CAPACITY_MAX = 1 << 62
+
+
 def capacity(rate, span):
     """Candidate capacity: Poisson mean + 8 sigma + slack.  The candidate count of thinning at
-    rate ``rate`` over ``span`` seconds is Poisson(rate*span); P(N > mean + 8 sigma) < 1e-15."""
-    mean = np.maximum(np.nan_to_num(np.asarray(rate, dtype="f8") * span, nan=0.0, posinf=0.0), 0.0)
-    return (np.ceil(mean + 8.0 * np.sqrt(mean)) + 64).astype(np.int64)
+    rate ``rate`` over ``span`` seconds is Poisson(rate*span); P(N > mean + 8 sigma) < 1e-15.
+    A non-finite or astronomically large mean saturates at CAPACITY_MAX (the engine then refuses the
+    unit) instead of wrapping around in the integer cast."""
+    with np.errstate(all="ignore"):
+        mean = np.asarray(rate, dtype="f8") * span
+        mean = np.where(np.isfinite(mean), np.maximum(mean, 0.0), np.inf)
+        cap = np.ceil(mean + 8.0 * np.sqrt(mean)) + 64
+        cap = np.where(cap < float(CAPACITY_MAX), cap, float(CAPACITY_MAX))
+    return cap.astype(np.int64)
 
 
 def _unit_work_begin(work, n_units):
@@ -146,6 +155,9 @@ class Engine(object):
         self.squeeze = bool(squeeze)
         self.squeeze_ratio, self.squeeze_min_candidates, self.squeeze_max_nodes = 8, 2048, 1 << 16
         self.energy_row_spacing, self.energy_candidates_per_row = 0.02, 256
+        # hard ceiling on the thinning candidates of ONE unit (fmax x duration): beyond it the unit's
+        # buffers cannot be sized sensibly (the reference's own loop would run for years); raised loudly
+        self.max_candidates_per_unit = 1 << 31
         self._call_counter = 0
         self._dtab_cache = {}
         self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
@@ -154,6 +166,12 @@ class Engine(object):
     @property
     def stream(self):
         return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def copy_stream(self):
+        """side stream for device->host copies that overlap the next batch's kernels"""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = _torch().cuda.Stream(device=self.device)
+        return self._copy_stream
 
     def next_seed(self):
         """A fresh Philox seed per sampler call (the reference reseeds from OS entropy before every
@@ -229,21 +247,26 @@ class Engine(object):
         return d
 
     # -- batch construction ---------------------------------------------------------------------
+    def fmax(self, units, tables, interp_extrap=None):
+        """Source._get_energy_integrated_max (source.py:88-110) of every unit: one launch, fmax returned."""
+        units = np.array(units, dtype=UNIT_DTYPE, copy=True)
+        fill_gamma_constants(units)
+        dtab = self.upload_tables(tables) if isinstance(tables, (list, tuple)) else tables
+        d_units = self.to_device(units)
+        _capi.check(self.lib.cgrb_fmax(dtab.data_ptr(), d_units.data_ptr(), len(units),
+                                       self._extrap_code(interp_extrap), self.stream), "cgrb_fmax")
+        self.launches += 1
+        return d_units.cpu().numpy().view(UNIT_DTYPE)["fmax"].copy()
+
     def new_batch(self, units, tables, interp_extrap=None, compute_fmax=True):
         """Upload units and detector tables, compute fmax on the device (unless given), size the
         per-unit capacities and offsets."""
-        torch = _torch()
         units = np.array(units, dtype=UNIT_DTYPE, copy=True)
         fill_gamma_constants(units)
         dtab = self.upload_tables(tables) if isinstance(tables, (list, tuple)) else tables
         b = Batch(self, units, dtab, interp_extrap or self.interp_extrap)
-        b.d_units = self.to_device(units)
         if compute_fmax:
-            _capi.check(self.lib.cgrb_fmax(dtab.data_ptr(), b.d_units.data_ptr(), b.n_units,
-                                           self._extrap_code(b.interp_extrap), self.stream), "cgrb_fmax")
-            self.launches += 1
-            host = b.d_units.cpu().numpy().view(UNIT_DTYPE)
-            units["fmax"] = host["fmax"]
+            units["fmax"] = self.fmax(units, dtab, b.interp_extrap)
         self.finalize_layout(b)
         return b
 
@@ -255,6 +278,12 @@ class Engine(object):
         bkg_cap = capacity(units["bkg_rate"], units["bkg_tstop"] - units["bkg_tstart"])
         src_cap[no_src] = 0
         bkg_cap[no_bkg] = 0
+        worst = int(np.argmax(np.maximum(src_cap, bkg_cap))) if len(units) else 0
+        if len(units) and max(int(src_cap[worst]), int(bkg_cap[worst])) > self.max_candidates_per_unit:
+            raise _capi.EngineError(
+                f"unit {worst} needs {float(max(src_cap[worst], bkg_cap[worst])):.3g} thinning candidates "
+                f"(fmax = {float(units['fmax'][worst]):.3g} /s over {float(units['src_tstop'][worst] - units['src_tstart'][worst]):.3g} s), "
+                f"more than max_candidates_per_unit = {self.max_candidates_per_unit}")
         keep_src = units["src_cap"] > 0
         keep_bkg = units["bkg_cap"] > 0
         units["src_cap"] = np.where(keep_src, units["src_cap"], src_cap)   # caller may pre-size
@@ -321,8 +350,30 @@ class Engine(object):
         one host array per list plus per-unit offsets.  ``pinned`` is a cache of pinned staging
         buffers that is reused (and grown) across calls."""
         torch = _torch()
-        c = self.fetch_counts(b)
+        self.fetch_counts(b)
         self.check_status(b)
+        out = self._enqueue_event_copies(b, pinned, extra)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    def to_host_async(self, b, ready_event, copy_stream, extra=()):
+        """``to_host`` on a side stream: waits for ``ready_event`` (recorded after the batch's kernels),
+        reads the unit counters, then enqueues the event-list copies on ``copy_stream`` and returns
+        without waiting for them -- the caller keeps launching the next batch on the compute stream and
+        synchronises ``copy_stream`` before touching the arrays."""
+        torch = _torch()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready_event)
+            cbuf = torch.empty(b.d_counts.numel(), dtype=torch.uint8, pin_memory=True)
+            cbuf.copy_(b.d_counts, non_blocking=True)
+            copy_stream.synchronize()           # the counters size the copies
+            b.counts = cbuf.numpy().view(COUNTS_DTYPE).copy()
+            self.check_status(b)
+            return self._enqueue_event_copies(b, None, extra)
+
+    def _enqueue_event_copies(self, b, pinned, extra):
+        torch = _torch()
+        c = b.counts
         # pinned=None: fresh pinned buffers per call (torch's caching host allocator recycles them), so
         # the returned arrays stay valid for as long as the caller keeps them
         n_of = {"kept": c["n_kept"], "src": c["n_src"], "bkg": c["n_bkg"], "tot": c["n_total"]}
@@ -348,7 +399,6 @@ class Engine(object):
             out[name] = buf[:total]
             out[name + "_offsets"] = starts
             out["d2h_bytes"] += total * src.element_size()
-        torch.cuda.current_stream(self.device).synchronize()
         return out
 
     def fetch_counts(self, b):

@@ -11,10 +11,13 @@ from ... import _capi
 from ...engine import Philox, get_engine, make_units
 from ...io.grb_save import write_grb_file
 from ...lightcurve.light_curve_storage import LightCurveStorage
+from ...utils.logging import setup_logger
 from ...universe.universe import GRBWrapper, ParameterServer, Universe, dist_info, gather_event_counts, shard_by_cost
 from .gbm_background import gbm_background_template
 from .gbm_grb import GBMGRB, GBMGRB_CPL, GBMGRB_CPL_Constant
 from .synthetic_response import GBM_DETECTORS, angle_factor, base_response, separation_angles
+
+logger = setup_logger(__name__)
 
 N_DET = len(GBM_DETECTORS)
 BYTES_PER_SLOT = 8 + 8 + 8 + 1 + 8 + 1 + 8 + 1 + 1      # stage/times/energy/pha + merged + filtered + flags
@@ -63,29 +66,56 @@ class _GBMBatchedUniverse(Universe):
         pf = np.asarray(self._local_parameters["peak_flux"])
         return 2e5 * N_DET + 2e10 * pf * self._duration
 
-    def _run_batched(self, grbs_per_batch=None, save=True, seed=None, memory_budget=48e9):
+    def _run_batched(self, grbs_per_batch=None, save=True, seed=None, memory_budget=64e9):
+        """Batches of GRBs sized to ``memory_budget`` bytes of event buffers.  A burst whose candidate
+        count (fmax x duration) does not fit the budget on its own is SKIPPED with a warning and listed in
+        ``self.skipped`` (its event counts read -1): the reference's model makes lambda(t) explode for
+        low-Epeak bursts at late times (the normalisation band drifts above the cutoff), and its own
+        thinning loop would take years on them."""
+        from ...engine import capacity
+
         eng = get_engine()
         rank, world = dist_info()
         mine = shard_by_cost(self.cost_estimate(), world)[rank]
         tabs = self.base_tables(eng.interp_extrap)
+        dtab = eng.upload_tables(tabs)
         seed = eng.seed if seed is None else seed
         local_counts = np.zeros((len(mine), N_DET, 3), dtype=np.int64)
         pinned = {}
-        pos = 0
         self.n_batches = 0
-        while pos < len(mine):
-            # size the batch from the capacities (needs fmax): grow until the memory budget is hit
-            step = grbs_per_batch or 256
-            idx = mine[pos:pos + step]
+        self.skipped = []
+        # fmax of every local unit (one launch per 4096 GRBs), then per-GRB buffer sizes
+        sizes = np.zeros(len(mine))
+        fmax_all = np.zeros((len(mine), N_DET))
+        for p0 in range(0, len(mine), 4096):
+            idx = mine[p0:p0 + 4096]
+            units, _ = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
+            f = eng.fmax(units, dtab)
+            fmax_all[p0:p0 + len(idx)] = f.reshape(-1, N_DET)
+            slots = (capacity(f, units["src_tstop"] - units["src_tstart"]).astype("f8")
+                     + capacity(units["bkg_rate"], units["bkg_tstop"] - units["bkg_tstart"]) + 2)
+            sizes[p0:p0 + len(idx)] = slots.reshape(-1, N_DET).sum(axis=1) * BYTES_PER_SLOT
+        too_big = (sizes > memory_budget) | ~np.isfinite(sizes)
+        for j in np.nonzero(too_big)[0]:
+            g = int(mine[j])
+            self.skipped.append(g)
+            local_counts[j] = -1
+            logger.warning(f"{self._name[g]}: {sizes[j] / BYTES_PER_SLOT:.3g} event slots do not fit the memory "
+                           f"budget ({memory_budget:.3g} B): skipped")
+        todo = np.nonzero(~too_big)[0]
+        pos = 0
+        while pos < len(todo):
+            # grow the batch until the memory budget (or grbs_per_batch) is reached
+            acc, end = 0.0, pos
+            while end < len(todo) and (end == pos or acc + sizes[todo[end]] <= memory_budget) and \
+                    (end - pos) < (grbs_per_batch or 512):
+                acc += sizes[todo[end]]
+                end += 1
+            sel = todo[pos:end]
+            idx = mine[sel]
             units, ang = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
-            b = eng.new_batch(units, tabs, compute_fmax=True)
-            if grbs_per_batch is None:
-                per_grb = (b.n_tot_slots * BYTES_PER_SLOT) / max(len(idx), 1)
-                fit = max(1, int(memory_budget / max(per_grb, 1.0)))
-                if fit < len(idx):
-                    idx = idx[:fit]
-                    units, ang = units[:fit * N_DET], ang[:fit]
-                    b = eng.new_batch(units, tabs, compute_fmax=True)
+            units["fmax"] = fmax_all[sel].reshape(-1)
+            b = eng.new_batch(units, dtab, compute_fmax=False)
             eng.process(b, Philox(seed))
             if save:
                 arrays = eng.to_host(b, pinned)
@@ -94,10 +124,10 @@ class _GBMBatchedUniverse(Universe):
             else:
                 c = eng.fetch_counts(b)
                 eng.check_status(b)
-            local_counts[pos:pos + len(idx), :, 0] = c["n_src"].reshape(-1, N_DET)
-            local_counts[pos:pos + len(idx), :, 1] = c["n_bkg"].reshape(-1, N_DET)
-            local_counts[pos:pos + len(idx), :, 2] = c["n_kept"].reshape(-1, N_DET)
-            pos += len(idx)
+            local_counts[sel, :, 0] = c["n_src"].reshape(-1, N_DET)
+            local_counts[sel, :, 1] = c["n_bkg"].reshape(-1, N_DET)
+            local_counts[sel, :, 2] = c["n_kept"].reshape(-1, N_DET)
+            pos = end
             self.n_batches += 1
         # the one exchange of the population run: per-unit event counts of every rank
         gathered = gather_event_counts(local_counts.reshape(-1, 3))

@@ -88,9 +88,41 @@ class LightCurve(object):
     lightcurve_storage = property(lambda self: self._lc_storage)
 
 
+#: light curves of one call are cut into chunks of about this many event slots when the call is large:
+#: the device->host copy of chunk k then overlaps the kernels of chunk k+1
+PIPELINE_MIN_SLOTS = 8_000_000
+PIPELINE_CHUNKS = 7
+
+
+def _chunks(units, eng):
+    """Positions of the units grouped into pipeline chunks (one chunk = everything for small calls)."""
+    from ..engine import capacity
+
+    n = len(units)
+    slots = (capacity(units["fmax"], units["src_tstop"] - units["src_tstart"])
+             + capacity(units["bkg_rate"], units["bkg_tstop"] - units["bkg_tstart"])).astype("f8")
+    total = float(slots.sum())
+    if n < 2 or not np.isfinite(total) or total < 2 * PIPELINE_MIN_SLOTS:
+        return [np.arange(n)]
+    target = max(total / PIPELINE_CHUNKS, PIPELINE_MIN_SLOTS)
+    chunks, cur, acc = [], [], 0.0
+    for i in range(n):
+        cur.append(i)
+        acc += slots[i]
+        if acc >= target:
+            chunks.append(np.array(cur))
+            cur, acc = [], 0.0
+    if cur:
+        chunks.append(np.array(cur))
+    return chunks
+
+
 def process_batch(lightcurves, seed=None, stream_ids=None, pinned=None):
-    """Run ``LightCurve.process()`` for many light curves as ONE batch of launches and return their
-    storages (same order).  ``stream_ids`` fixes the Philox stream of every unit (default: position)."""
+    """Run ``LightCurve.process()`` for many light curves as batched launches and return their storages
+    (same order).  ``stream_ids`` fixes the Philox stream of every unit (default: position).  Large calls
+    are pipelined: results do not depend on the chunking (Philox counters are per unit)."""
+    import torch
+
     eng = get_engine()
     lcs = list(lightcurves)
     if not lcs:
@@ -105,9 +137,39 @@ def process_batch(lightcurves, seed=None, stream_ids=None, pinned=None):
         units.append(lc.unit_record(det_index=tab_index[k], stream_id=i if stream_ids is None else stream_ids[i]))
     units = np.concatenate(units)
     need_fmax = bool(np.any(~(units["fmax"] > 0)))
-    b = eng.new_batch(units, tabs, compute_fmax=need_fmax)
     all_deadtime = all(lc._deadtime for lc in lcs)
-    eng.process(b, Philox(eng.next_seed() if seed is None else seed), keep_merged=not all_deadtime)
     extra = () if all_deadtime else (("times_tot", "tot"), ("pha_tot", "tot"))
-    arrays = eng.to_host(b, pinned, extra=extra)
-    return [lc._storage_from(arrays, i) for i, lc in enumerate(lcs)]
+    rng = Philox(eng.next_seed() if seed is None else seed)
+    chunks = [np.arange(len(lcs))] if (need_fmax or pinned is not None) else _chunks(units, eng)
+    if len(chunks) == 1:
+        b = eng.new_batch(units, tabs, compute_fmax=need_fmax)
+        eng.process(b, rng, keep_merged=not all_deadtime)
+        arrays = eng.to_host(b, pinned, extra=extra)
+        return [lc._storage_from(arrays, i) for i, lc in enumerate(lcs)]
+    # pipelined: kernels of chunk k+1 are enqueued before the host waits for chunk k's counters
+    dtab = eng.upload_tables(tabs)
+    compute = torch.cuda.current_stream(eng.device)
+    copy_stream = eng.copy_stream()
+    pending, results = [], [None] * len(lcs)
+
+    def drain(item):
+        pos, b, ev = item
+        arrays = eng.to_host_async(b, ev, copy_stream, extra=extra)
+        return pos, b, arrays
+
+    drained = []
+    for pos in chunks:
+        b = eng.new_batch(units[pos], dtab, compute_fmax=False)
+        eng.process(b, rng, keep_merged=not all_deadtime)
+        ev = torch.cuda.Event()
+        ev.record(compute)
+        pending.append((pos, b, ev))
+        if len(pending) > 1:
+            drained.append(drain(pending.pop(0)))
+    while pending:
+        drained.append(drain(pending.pop(0)))
+    copy_stream.synchronize()
+    for pos, b, arrays in drained:
+        for j, i in enumerate(pos):
+            results[int(i)] = lcs[int(i)]._storage_from(arrays, j)
+    return results

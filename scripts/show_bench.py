@@ -15,3 +15,11 @@ for path in sys.argv[1:]:
         print(f"   {k:28s} {v['ms_per_step']:8.3f} ms  {v['share']:.3f}")
     for r in d.get("roofline_hbm_kernels", []):
         print(f"   hbm {r['kernel']:24s} {r['achieved']:.0f} GB/s frac {r['frac']:.3f}")
+    if d.get("population"):
+        q = d["population"]
+        print(f"   population: {q['n_grbs']} GRBs {q['events']:.4g} events in {q['ms']:.1f} ms -> {q['grbs_per_s']:.1f} GRB/s "
+              f"{q['events_per_s']:.4g} ev/s; kernels {q['kernel_ms_per_gpu']:.1f} ms, batches {q['batches_per_gpu']}")
+        for k, v in q["kernels"].items():
+            print(f"      {k:26s} {v:9.3f} ms")
+        for k, v in q["hbm_kernels"].items():
+            print(f"      hbm {k:22s} {v['achieved_gbs']:.0f} GB/s frac {v['frac_of_measured_hbm']:.3f}")

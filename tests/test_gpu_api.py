@@ -45,6 +45,27 @@ def test_gbmgrb_cpl_go(grb):
     assert n_src[best] > n_src[worst]
 
 
+def test_go_pipelined_equals_single_batch(grb, monkeypatch):
+    """Large calls overlap the device->host copy of one chunk of detectors with the kernels of the next;
+    the chunking changes nothing (Philox counters are per unit)."""
+    from cosmogrb_b200.lightcurve import lightcurve as lcmod
+
+    units = np.concatenate([lc.unit_record(det_index=i) for i, lc in enumerate(grb.lightcurves.values())])
+    assert len(lcmod._chunks(units, None)) == 1
+    want = {}
+    for name, lc in grb.lightcurves.items():
+        st = lc.lightcurve_storage
+        want[name] = {a: np.array(getattr(st, a)) for a in ("times", "pha", "times_source", "pha_source",
+                                                             "times_background", "pha_background")}
+    monkeypatch.setattr(lcmod, "PIPELINE_MIN_SLOTS", 1000)
+    assert len(lcmod._chunks(units, None)) > 1
+    grb.go(seed=2024)                       # same burst object (same background rates), now pipelined
+    for name, lc in grb.lightcurves.items():
+        st = lc.lightcurve_storage
+        for attr, w in want[name].items():
+            assert np.array_equal(getattr(st, attr), w), (name, attr)
+
+
 def test_grb_save_and_reload(grb, tmp_path):
     from cosmogrb_b200 import GRBSave
 
@@ -149,3 +170,29 @@ def test_universe_run(engine, tmp_path):
     uni2.go(seed=11, grbs_per_batch=5)
     assert uni2.n_batches == 3
     assert np.array_equal(uni2.event_counts, uni.event_counts)
+
+
+def test_runaway_unit_is_refused_and_skipped(engine):
+    """The reference's model lets lambda(t) explode for low-Epeak bursts at late times (the 10-10^4 keV
+    normalisation band drifts above the cutoff): fmax x duration reaches 1e15 candidates.  The engine
+    refuses such a unit loudly instead of sizing buffers for it, and a population run skips the burst."""
+    from cosmogrb_b200 import _capi
+    from cosmogrb_b200.instruments.gbm.gbm_universe import GBM_CPL_Universe
+    from cosmogrb_b200.universe import synthetic_population
+    from cosmogrb_b200.universe.population import Population
+
+    bad = dict(z=4.72, peak_flux=1e-9, alpha=-0.853, ep_start=13.28, ep_tau=2.0, trise=1.0, tdecay=4.0,
+               duration=28.3)
+    rsp = h.response("n0")
+    with pytest.raises(_capi.EngineError, match="max_candidates_per_unit"):
+        engine.new_batch(h.unit(**bad), [rsp.device_table(h.bkg_weights("n0"), "linear")])
+    pop = synthetic_population(3, seed=7)
+    cols = {k: np.array(getattr(pop, k) if k != "fluxes_latent" else pop.fluxes.latent) for k in
+            ("ra", "dec", "distances", "duration", "ep", "alpha", "fluxes_latent", "trise", "tdecay", "tau")}
+    cols["distances"][1], cols["fluxes_latent"][1], cols["alpha"][1] = bad["z"], bad["peak_flux"], bad["alpha"]
+    cols["ep"][1], cols["tau"][1], cols["trise"][1] = bad["ep_start"], bad["ep_tau"], bad["trise"]
+    cols["tdecay"][1], cols["duration"][1] = bad["tdecay"], bad["duration"]
+    uni = GBM_CPL_Universe(Population(**cols), save_path=None)
+    uni.go(seed=3, save=False)
+    assert uni.skipped == [1]
+    assert np.all(uni.event_counts[1] == -1) and np.all(uni.event_counts[[0, 2], :, 1] > 1.8e5)
