@@ -185,7 +185,7 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 KERNEL_BYTES = {
-    "k_sample_energy_env": 16.0,  # reads time, writes energy per source event
+    "k_sample_energy_env": 9.0,   # reads the photon time (8 B), writes its channel (1 B): the fold is fused
     # algorithmic HBM bytes per EVENT of each kernel's own product
     "k_background": 9.0,        # writes f64 time + u8 channel per background event
     "k_merge_deadtime": 18.0,   # reads 9 B (component lists), writes <= 9 B (survivors) per merged event
@@ -337,12 +337,20 @@ def run_gpu(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
+    # DRAM bytes per launch measured by ncu (--set full) on this same workload, kept under profiles/
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch", {})
+    except Exception:
+        pass
+
     def hbm_roofline(name):
         key = name.split("<")[0]
         nbytes = KERNEL_BYTES.get(key, 0.0) * units_of.get(key, 0)
         ach = nbytes / (kern[name]["ms_per_launch"] * 1e-3) / 1e9 if name in kern else 0.0
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": kern[name]["ms_per_launch"],
+                "traffic": traffic.get(name, traffic.get(key)), "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": kern[name]["ms_per_launch"],
                 "share_of_step": kern[name]["share"], "peak_source": peak_src}
 
     roofline = hbm_roofline(top)
