@@ -24,6 +24,7 @@ SEG = 8192
 MERGE_TILE = 2048
 DT_TILE = 2048
 MD_TILE = 2048
+TRIG_TILE = 2048
 ENV_MAXW = 256
 
 # detector table block layout (doubles) -- must match include/cosmogrb_b200.h
@@ -79,8 +80,17 @@ COUNTS_DTYPE = np.dtype(
 )
 assert COUNTS_DTYPE.itemsize == 64
 
+TRIGGER_DTYPE = np.dtype([("detected", "<i4"), ("combo", "<i4"), ("n_bins", "<i4"), ("razor", "<i4"),
+                          ("time", "<f8"), ("time_scale", "<f8")])
+assert TRIGGER_DTYPE.itemsize == 32
+
 WORK_DTYPE = np.dtype([("unit", "<i4"), ("seg", "<i4"), ("start", "<i8")])
 assert WORK_DTYPE.itemsize == 16
+
+
+class TriggerPar(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("base_timescale", C.c_double), ("background_duration", C.c_double),
+                ("pre_window", C.c_double)]
 
 
 class RngDesc(C.Structure):
@@ -118,6 +128,8 @@ EXPORTS = (
     "cgrb_gbm_dead_time",
     "cgrb_merge_dead_time_workspace_bytes",
     "cgrb_merge_dead_time",
+    "cgrb_gbm_trigger_workspace_bytes",
+    "cgrb_gbm_trigger",
 )
 
 _lib = None
@@ -162,10 +174,13 @@ def load():
     lib.cgrb_merge_dead_time_workspace_bytes.argtypes = [i64]
     lib.cgrb_merge_dead_time_workspace_bytes.restype = i64
     lib.cgrb_merge_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_gbm_trigger_workspace_bytes.argtypes = [i32, i64]
+    lib.cgrb_gbm_trigger_workspace_bytes.restype = i64
+    lib.cgrb_gbm_trigger.argtypes = [vp, i32, vp, i64, vp, C.POINTER(TriggerPar), vp, vp, vp, i64, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count", "cgrb_energy_workspace_bytes",
-                        "cgrb_merge_dead_time_workspace_bytes"):
+                        "cgrb_merge_dead_time_workspace_bytes", "cgrb_gbm_trigger_workspace_bytes"):
             fn.restype = i32
     if lib.cgrb_abi_version() != ABI_VERSION:
         raise EngineUnavailable(

@@ -576,6 +576,55 @@ class Engine(object):
             "cgrb_merge_dead_time")
         self.launches += 2
 
+    def gbm_trigger(self, b, chan_bounds, threshold=4.5, background_duration=17.0, pre_window=4.0,
+                    base_timescale=0.016, fetch=True):
+        """GBMLightCurveAnalyzer for every unit of a processed batch, on the device (events stay in HBM).
+        ``chan_bounds``: int32 [n_detector_tables, 8] (gbm_lightcurve_analyzer.channel_bounds).  Returns the
+        per-unit results as a numpy array of ``_capi.TRIGGER_DTYPE`` (``fetch=False``: only enqueue; read
+        them later with ``fetch_trigger``)."""
+        torch = _torch()
+        w, dw, _ = self._work(b, 2, _capi.TRIG_TILE)
+        u = b.units
+        span = float(np.max(np.maximum(u["bkg_tstop"], u["src_tstop"]) - np.minimum(u["bkg_tstart"], u["src_tstart"])))
+        bins_per_unit = int(math.ceil(span / base_timescale)) + 4
+        cb = self.to_device(np.ascontiguousarray(chan_bounds, dtype=np.int32).reshape(-1, 8))
+        ws = self.empty(self.lib.cgrb_gbm_trigger_workspace_bytes(b.n_units, bins_per_unit), torch.uint8)
+        out = self.empty(b.n_units * _capi.TRIGGER_DTYPE.itemsize, torch.uint8)
+        par = _capi.TriggerPar(threshold, base_timescale, background_duration, pre_window)
+        _capi.check(
+            self.lib.cgrb_gbm_trigger(
+                b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), cb.data_ptr(), C.byref(par),
+                b.t["times_out"].data_ptr(), b.t["pha_out"].data_ptr(), b.d_counts.data_ptr(), bins_per_unit,
+                ws.data_ptr(), out.data_ptr(), self.stream),
+            "cgrb_gbm_trigger")
+        self.launches += 2
+        b.t["trigger"] = out
+        b._keep.append(cb)
+        return self.fetch_trigger(b) if fetch else None
+
+    def fetch_trigger(self, b):
+        n = b.n_units * _capi.TRIGGER_DTYPE.itemsize
+        return b.t["trigger"][:n].cpu().numpy().view(_capi.TRIGGER_DTYPE).copy()
+
+    def analyze_light_curve(self, times, pha, chan_bounds, n_counts_source, **par):
+        """The trigger analysis of ONE given light curve (host arrays: the time-sorted total list)."""
+        torch = _torch()
+        times = np.ascontiguousarray(times, dtype="f8")
+        n = len(times)
+        pha8 = np.ascontiguousarray(np.asarray(pha).astype(np.int64).clip(0, 255).astype(np.uint8))
+        u = make_units(1)
+        u["src_cap"], u["bkg_cap"] = max(n - 1, 0), 0
+        if n:
+            u["bkg_tstart"], u["bkg_tstop"] = times[0], times[-1]
+            u["src_tstart"], u["src_tstop"] = times[0], times[-1]
+        b = Batch(self, u, None, self.interp_extrap)
+        b.n_src_slots, b.n_bkg_slots, b.n_tot_slots = n + 1, 1, n + 2
+        b.d_units = self.to_device(u)
+        self.set_counts(b, n_kept=n, n_total=n, n_src=int(n_counts_source))
+        b.t["times_out"] = self.to_device(np.concatenate((times, [0.0, 0.0])))
+        b.t["pha_out"] = self.to_device(np.concatenate((pha8, np.zeros(2, np.uint8))))
+        return self.gbm_trigger(b, np.asarray(chan_bounds).reshape(1, 8), **par)[0]
+
     def process(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, diagnostics=False, energy_sampler=None,
                 keep_merged=False):
         """LightCurve.process() for every unit of the batch (lightcurve.py:167-200): source times,

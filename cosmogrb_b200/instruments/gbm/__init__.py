@@ -6,6 +6,7 @@ _LAZY = {
     "GBMLightCurve": ".gbm_lightcurve", "GBMBackground": ".gbm_background",
     "NaIResponse": ".synthetic_response", "BGOResponse": ".synthetic_response",
     "GBM_CPL_Universe": ".gbm_universe", "GBM_CPL_Constant_Universe": ".gbm_universe",
+    "GBMLightCurveAnalyzer": ".gbm_lightcurve_analyzer", "GBMTrigger": ".gbm_trigger",
 }
 
 __all__ = sorted(_LAZY)

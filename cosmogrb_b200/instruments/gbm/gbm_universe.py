@@ -66,14 +66,19 @@ class _GBMBatchedUniverse(Universe):
         pf = np.asarray(self._local_parameters["peak_flux"])
         return 2e5 * N_DET + 2e10 * pf * self._duration
 
-    def _run_batched(self, grbs_per_batch=None, save=True, seed=None, memory_budget=64e9):
+    def _run_batched(self, grbs_per_batch=None, save=True, seed=None, memory_budget=64e9, trigger=False,
+                     trigger_threshold=4.5, simul_trigger_window=0.5, max_n_dets=12):
         """Batches of GRBs sized to ``memory_budget`` bytes of event buffers.  A burst whose candidate
         count (fmax x duration) does not fit the budget on its own is SKIPPED with a warning and listed in
         ``self.skipped`` (its event counts read -1): the reference's model makes lambda(t) explode for
         low-Epeak bursts at late times (the normalisation band drifts above the cutoff), and its own
         thinning loop would take years on them."""
+        import time
+
         from ...engine import capacity
 
+        tm = self.timings = dict(fmax_pass=0.0, build_units=0.0, new_batch=0.0, launch=0.0, wait=0.0, gather=0.0)
+        t_ = time.perf_counter
         eng = get_engine()
         rank, world = dist_info()
         mine = shard_by_cost(self.cost_estimate(), world)[rank]
@@ -84,9 +89,16 @@ class _GBMBatchedUniverse(Universe):
         pinned = {}
         self.n_batches = 0
         self.skipped = []
+        if trigger:
+            from .gbm_lightcurve_analyzer import channel_bounds, simultaneous_trigger
+
+            chan_bounds = np.stack([channel_bounds(base_response(d).channel_edges) for d in GBM_DETECTORS])
+            local_trig = np.zeros((len(mine), N_DET), dtype=_capi.TRIGGER_DTYPE)
+            local_det = np.zeros(len(mine), dtype=bool)
         # fmax of every local unit (one launch per 4096 GRBs), then per-GRB buffer sizes
         sizes = np.zeros(len(mine))
         fmax_all = np.zeros((len(mine), N_DET))
+        t0 = t_()
         for p0 in range(0, len(mine), 4096):
             idx = mine[p0:p0 + 4096]
             units, _ = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
@@ -95,6 +107,7 @@ class _GBMBatchedUniverse(Universe):
             slots = (capacity(f, units["src_tstop"] - units["src_tstart"]).astype("f8")
                      + capacity(units["bkg_rate"], units["bkg_tstop"] - units["bkg_tstart"]) + 2)
             sizes[p0:p0 + len(idx)] = slots.reshape(-1, N_DET).sum(axis=1) * BYTES_PER_SLOT
+        tm["fmax_pass"] = t_() - t0
         too_big = (sizes > memory_budget) | ~np.isfinite(sizes)
         for j in np.nonzero(too_big)[0]:
             g = int(mine[j])
@@ -103,20 +116,11 @@ class _GBMBatchedUniverse(Universe):
             logger.warning(f"{self._name[g]}: {sizes[j] / BYTES_PER_SLOT:.3g} event slots do not fit the memory "
                            f"budget ({memory_budget:.3g} B): skipped")
         todo = np.nonzero(~too_big)[0]
-        pos = 0
-        while pos < len(todo):
-            # grow the batch until the memory budget (or grbs_per_batch) is reached
-            acc, end = 0.0, pos
-            while end < len(todo) and (end == pos or acc + sizes[todo[end]] <= memory_budget) and \
-                    (end - pos) < (grbs_per_batch or 512):
-                acc += sizes[todo[end]]
-                end += 1
-            sel = todo[pos:end]
-            idx = mine[sel]
-            units, ang = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
-            units["fmax"] = fmax_all[sel].reshape(-1)
-            b = eng.new_batch(units, dtab, compute_fmax=False)
-            eng.process(b, Philox(seed))
+
+        def finish(item):
+            """read back the counters of a launched batch (and its events when saving)"""
+            sel, idx, b, ang = item
+            t3 = t_()
             if save:
                 arrays = eng.to_host(b, pinned)
                 c = arrays["counts"]
@@ -124,19 +128,65 @@ class _GBMBatchedUniverse(Universe):
             else:
                 c = eng.fetch_counts(b)
                 eng.check_status(b)
+            if trigger:
+                tr = eng.fetch_trigger(b).reshape(-1, N_DET)
+                local_trig[sel] = tr
+                for j in range(len(sel)):
+                    local_det[sel[j]] = simultaneous_trigger(
+                        GBM_DETECTORS, ang[j], tr[j]["detected"], tr[j]["time"], tr[j]["time_scale"],
+                        simul_trigger_window=simul_trigger_window, max_n_dets=max_n_dets)[0]
+            tm["wait"] += t_() - t3
             local_counts[sel, :, 0] = c["n_src"].reshape(-1, N_DET)
             local_counts[sel, :, 1] = c["n_bkg"].reshape(-1, N_DET)
             local_counts[sel, :, 2] = c["n_kept"].reshape(-1, N_DET)
+
+        # two batches in flight: the host prepares and launches batch k+1 before it waits for batch k
+        budget = memory_budget / 2
+        pos, in_flight = 0, None
+        while pos < len(todo):
+            # grow the batch until the memory budget (or grbs_per_batch) is reached
+            acc, end = 0.0, pos
+            while end < len(todo) and (end == pos or acc + sizes[todo[end]] <= budget) and \
+                    (end - pos) < (grbs_per_batch or 512):
+                acc += sizes[todo[end]]
+                end += 1
+            sel = todo[pos:end]
+            idx = mine[sel]
+            t0 = t_()
+            units, ang = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
+            units["fmax"] = fmax_all[sel].reshape(-1)
+            t1 = t_()
+            b = eng.new_batch(units, dtab, compute_fmax=False)
+            t2 = t_()
+            eng.process(b, Philox(seed))
+            if trigger:
+                eng.gbm_trigger(b, chan_bounds, threshold=trigger_threshold, fetch=False)
+            t3 = t_()
+            tm["build_units"] += t1 - t0
+            tm["new_batch"] += t2 - t1
+            tm["launch"] += t3 - t2
+            if in_flight is not None:
+                finish(in_flight)
+            in_flight = (sel, idx, b, ang)
             pos = end
             self.n_batches += 1
+        if in_flight is not None:
+            finish(in_flight)
         # the one exchange of the population run: per-unit event counts of every rank
+        t0 = t_()
         gathered = gather_event_counts(local_counts.reshape(-1, 3))
+        tm["gather"] = t_() - t0
         shards = shard_by_cost(self.cost_estimate(), world)
         full = np.zeros((self._n_grbs, N_DET, 3), dtype=np.int64)
         for r in range(world):
             full[shards[r]] = gathered[r].reshape(-1, N_DET, 3)
         self.event_counts = full
         self.local_grbs = mine
+        if trigger:
+            # detection flags of the local bursts (the all_gather above carries counts only; a flag per burst
+            # travels the same way when a global view is wanted)
+            self.trigger_results = local_trig
+            self.detected = local_det
 
     def _save_chunk(self, idx, b, arrays, ang):
         def sl(name, i):

@@ -167,10 +167,13 @@ class Universe(object, metaclass=abc.ABCMeta):
             self._parameter_servers.append(ps)
 
     # -- dispatch ---------------------------------------------------------------------------------
-    def go(self, client=None, grbs_per_batch=None, save=True, seed=None):
+    def go(self, client=None, grbs_per_batch=None, save=True, seed=None, trigger=False):
         """Simulate the whole population (universe.py:123-149).  ``client`` is accepted for signature
-        compatibility (the dask map is replaced by batched GPU launches + rank sharding)."""
-        self._run_batched(grbs_per_batch=grbs_per_batch, save=save and self._save_path is not None, seed=seed)
+        compatibility (the dask map is replaced by batched GPU launches + rank sharding).  ``trigger=True``
+        also runs the GBM trigger (``Survey.process(GBMTrigger)``, survey.py:210-285) on the device while the
+        events are still in HBM: ``self.detected`` / ``self.trigger_results`` for the local bursts."""
+        kw = dict(trigger=True) if trigger else {}
+        self._run_batched(grbs_per_batch=grbs_per_batch, save=save and self._save_path is not None, seed=seed, **kw)
         self._is_processed = True
 
     @abc.abstractmethod

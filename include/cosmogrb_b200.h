@@ -298,6 +298,39 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
                          const double *d_times_src, const uint8_t *d_pha_src, void *d_workspace,
                          double *d_times_out, uint8_t *d_pha_out, cgrb_counts_t *d_counts, void *stream);
 
+/* ---- GBM trigger ----------------------------------------------------------- */
+
+/* GBMLightCurveAnalyzer (instruments/gbm/gbm_lightcurve_analyzer.py:13-271) for every unit of a batch, on
+ * the dead-time-filtered total list left in HBM by cgrb_merge_dead_time / cgrb_gbm_dead_time: 16 ms binning
+ * in the four trigger energy ranges (LightCurveStorage.binned_counts, light_curve_storage.py:154-294), dead
+ * time per bin, sliding-window significance over the trigger time scales; the first (energy range, time
+ * scale) in the reference's order that fires gives the detection time.  2.8e6 events per GRB reduce to
+ * 32 bytes per detector without leaving the device.
+ *   d_chan_bounds [n_det][8] int32: per detector table and energy range r, a channel c is selected iff
+ *       bounds[2r] < c < bounds[2r+1]  (= ebounds.searchsorted(emin) / (emax); no bound: -1 / 1<<30)
+ *   bins_per_unit: >= number of 16 ms bins any unit can have (host: ceil(span / base_timescale) + 2)
+ *   work list: which=2, chunk=CGRB_TRIG_TILE.  d_workspace: cgrb_gbm_trigger_workspace_bytes(). */
+#define CGRB_TRIG_TILE 2048
+typedef struct {
+    double threshold;            /* 4.5  */
+    double base_timescale;       /* 0.016 */
+    double background_duration;  /* 17    */
+    double pre_window;           /* 4     */
+} cgrb_trigger_par_t;
+typedef struct {
+    int32_t detected;      /* GBMLightCurveAnalyzer.is_detected                                         */
+    int32_t combo;         /* 16 * energy range (a..d = 0..3) + index of the time scale (longest = 0), -1 */
+    int32_t n_bins;        /* 16 ms bins of the light curve                                             */
+    int32_t razor;         /* some window's significance lies within 1e-9 (relative) of the threshold   */
+    double time;           /* detection_time                                                            */
+    double time_scale;     /* detection_time_scale                                                      */
+} cgrb_trigger_t;
+int64_t cgrb_gbm_trigger_workspace_bytes(int n_units, int64_t bins_per_unit);
+int cgrb_gbm_trigger(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
+                     const int32_t *d_chan_bounds, const cgrb_trigger_par_t *par, const double *d_times_out,
+                     const uint8_t *d_pha_out, const cgrb_counts_t *d_counts, int64_t bins_per_unit,
+                     void *d_workspace, cgrb_trigger_t *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
