@@ -2147,6 +2147,8 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
 #define TRIG_LOCAL 256          // bins a tile may span and still be accumulated in shared memory
 #define TRIG_NCOMBO 33
 #define TRIG_NARR 6             // per-bin integer arrays: counts of the 4 ranges, events, overflow events
+#define TRIG_CH 2048            // windows per staged chunk of the search
+#define TRIG_SPAN 1832          // >= background (1062) + longest gap (512) + source (250) bins
 
 // np.arange(tmin, tmax, dt): length and the fill rule  edge[i] = start + i * (fl(start + dt) - start)
 struct TrigGrid {
@@ -2275,8 +2277,6 @@ __global__ void __launch_bounds__(NT) k_trig_eval(const cgrb_unit_t *__restrict_
 {
     __shared__ double s_w[NW];
     __shared__ long long s_l[NW];
-    __shared__ long long s_first;
-    __shared__ int s_razor;
     const int ui = blockIdx.x;
     if (ui >= n_units)
         return;
@@ -2364,58 +2364,89 @@ __global__ void __launch_bounds__(NT) k_trig_eval(const cgrb_unit_t *__restrict_
         }
     }
     __syncthreads();
-    // the search: energy ranges a..d, time scales longest first; stop at the first combination that fires
+    // the search: energy ranges a..d, time scales longest first; the first combination (in that order) with
+    // a window at or above the threshold wins, at its first window.  The prefix sums of a chunk of windows
+    // (+ the longest window span) are staged in shared memory; all time scales of a range share the
+    // background window of a given i.
+    __shared__ double s_e[TRIG_CH + TRIG_SPAN + 1];
+    __shared__ int s_c[TRIG_CH + TRIG_SPAN + 1];
+    __shared__ long long s_hit[10];
     const int n_scales[4] = {10, 10, 9, 4};
     const int64_t n_bkg = (int64_t)floor(par.background_duration / dt);
     const int64_t n_src = (int64_t)floor(par.pre_window / dt);          // the "source" window (swapped arguments)
-    int combo = 0, razor = 0;
+    const double thr = par.threshold, thr2 = thr * thr;
+    int razor = 0;
     bool found = false;
-    for (int r = 0; r < 4 && !found; r++) {
+    // the staged layout needs n_bkg + longest gap + n_src <= TRIG_SPAN: true for the reference's constants
+    const bool staged_ok = (n_bkg + 512 + n_src <= TRIG_SPAN) && n_bkg > 0 && n_src > 0;
+    for (int r = 0; r < 4 && !found && staged_ok; r++) {
         const int64_t *cr = cs + r * (bins_per_unit + 1);
-        const bool empty = cr[nb] == 0;                                   // `if sum(counts) == 0: continue`
-        for (int sidx = 0; sidx < n_scales[r] && !found; sidx++, combo++) {
-            if (empty)
-                continue;
-            const double time_scale = dt * (double)(1 << (n_scales[r] - 1 - sidx));
-            const int64_t n_gap = (int64_t)floor(time_scale / dt);       // the gap before the source window
-            const int64_t n_i = nb - (n_bkg + n_gap + n_src);            // i + span < len(stops)
-            if (threadIdx.x == 0)
-                s_first = LLONG_MAX;
+        if (cr[nb] == 0)                                                  // `if sum(counts) == 0: continue`
+            continue;
+        const int ns = n_scales[r];
+        if (threadIdx.x < 10)
+            s_hit[threadIdx.x] = LLONG_MAX;
+        const int64_t n_i_max = nb - (n_bkg + 1 + n_src);                 // shortest gap: 1 bin
+        for (int64_t c0 = 0; c0 < n_i_max; c0 += TRIG_CH) {
             __syncthreads();
-            long long mine = LLONG_MAX;
-            for (int64_t i = threadIdx.x; i < n_i; i += NT) {
-                const double bkg_exposure = es[i + n_bkg] - es[i];
-                const double background_counts = (double)(cr[i + n_bkg] - cr[i]);
-                const int64_t si = i + n_bkg + n_gap;
-                const double src_exposure = es[si + n_src] - es[si];
-                const double src_counts = (double)(cr[si + n_src] - cr[si]);
-                const double alpha = src_exposure / bkg_exposure;
-                const double nbk = alpha * background_counts;
-                const double sig = (src_counts - nbk) / sqrt(nbk);
-                if (fabs(sig - par.threshold) < 1e-9 * par.threshold)
-                    razor = 1;
-                if (sig >= par.threshold && g.edge(si) > -1.0) {
-                    mine = i;
-                    break;                  // i ascends per thread: the first hit of this thread
+            const int64_t hi = min(nb, c0 + TRIG_CH + TRIG_SPAN);
+            const long long cbase = cr[c0];
+            for (int64_t k = c0 + threadIdx.x; k <= hi; k += NT) {
+                s_e[k - c0] = es[k];
+                s_c[k - c0] = (int)(cr[k] - cbase);
+            }
+            __syncthreads();
+            for (int64_t i = c0 + threadIdx.x; i < min(c0 + (int64_t)TRIG_CH, n_i_max); i += NT) {
+                const int li = (int)(i - c0);
+                const double eb = s_e[li + n_bkg] - s_e[li];
+                const double B = (double)(s_c[li + n_bkg] - s_c[li]);
+                for (int sidx = 0; sidx < ns; sidx++) {
+                    const int64_t n_gap = (int64_t)1 << (ns - 1 - sidx);
+                    if (i >= nb - (n_bkg + n_gap + n_src))                // i + span < len(stops)
+                        continue;
+                    const int ls = li + (int)(n_bkg + n_gap);
+                    const double ex = s_e[ls + n_src] - s_e[ls];
+                    const double S = (double)(s_c[ls + n_src] - s_c[ls]);
+                    // sig = (S - a B) / sqrt(a B), a = ex / eb: decided without the divisions when clear
+                    bool hit;
+                    const double d = S * eb - B * ex, rhs = thr2 * B * ex * eb;
+                    const double lhs = d * fabs(d);
+                    if (B > 0.0 && eb > 0.0 && ex > 0.0 && thr > 0.0 && lhs < rhs * (1.0 - 1e-8))
+                        hit = false;
+                    else if (B > 0.0 && eb > 0.0 && ex > 0.0 && thr > 0.0 && lhs > rhs * (1.0 + 1e-8))
+                        hit = true;
+                    else {
+                        const double alpha = ex / eb;
+                        const double nbk = alpha * B;
+                        const double sig = (S - nbk) / sqrt(nbk);
+                        if (fabs(sig - thr) < 1e-9 * thr)
+                            razor = 1;
+                        hit = sig >= thr;
+                    }
+                    if (hit && g.edge(i + n_bkg + n_gap) > -1.0)
+                        atomicMin(&s_hit[sidx], (long long)i);
                 }
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1)
-                mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, d));
-            if (lane == 0 && mine != LLONG_MAX)
-                atomicMin(&s_first, mine);
             __syncthreads();
-            const long long first = s_first;
-            __syncthreads();
+            if (s_hit[0] != LLONG_MAX)
+                break;              // the first time scale fired: nothing later can overrule it
+        }
+        __syncthreads();
+        for (int sidx = 0; sidx < ns; sidx++) {
+            const long long first = s_hit[sidx];
             if (first != LLONG_MAX) {
+                const int64_t n_gap = (int64_t)1 << (ns - 1 - sidx);
                 found = true;
                 res.detected = 1;
                 res.combo = r * 16 + sidx;
                 res.time = g.edge(first + n_bkg + n_gap);
-                res.time_scale = time_scale;
+                res.time_scale = dt * (double)n_gap;
+                break;
             }
         }
+        __syncthreads();
     }
+    __shared__ int s_razor;
     if (threadIdx.x == 0)
         s_razor = 0;
     __syncthreads();
@@ -2423,7 +2454,7 @@ __global__ void __launch_bounds__(NT) k_trig_eval(const cgrb_unit_t *__restrict_
         atomicOr(&s_razor, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        res.razor = s_razor;
+        res.razor = s_razor | (staged_ok ? 0 : 2);
         out[ui] = res;
     }
 }

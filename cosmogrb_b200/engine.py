@@ -180,11 +180,22 @@ class Engine(object):
         return (self.seed + 0x9E3779B97F4A7C15 * self._call_counter) & 0xFFFFFFFFFFFFFFFF
 
     def to_device(self, arr):
+        """Host array -> device tensor.  The copy runs on a dedicated upload stream so that it is not ordered
+        behind kernels already queued on the compute stream (a pageable host->device copy blocks the host
+        until the stream reaches it: on the compute stream that would serialise host preparation of the next
+        batch with the kernels of the current one); the compute stream then waits for the upload."""
         torch = _torch()
         a = np.ascontiguousarray(arr)
         if a.dtype.fields is not None:
             a = a.view(np.uint8)
-        return torch.from_numpy(a).to(self.device, non_blocking=False)
+        if getattr(self, "_upload_stream", None) is None:
+            self._upload_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._upload_stream):
+            d = torch.from_numpy(a).to(self.device, non_blocking=False)
+        cur.wait_stream(self._upload_stream)
+        d.record_stream(cur)
+        return d
 
     def empty(self, n, dtype):
         torch = _torch()
@@ -604,7 +615,11 @@ class Engine(object):
 
     def fetch_trigger(self, b):
         n = b.n_units * _capi.TRIGGER_DTYPE.itemsize
-        return b.t["trigger"][:n].cpu().numpy().view(_capi.TRIGGER_DTYPE).copy()
+        r = b.t["trigger"][:n].cpu().numpy().view(_capi.TRIGGER_DTYPE).copy()
+        if np.any(r["razor"] & 2):
+            raise _capi.EngineError("cgrb_gbm_trigger: background_duration + pre_window + longest time scale "
+                                    "exceed the kernel's staged window span (1832 bins of 16 ms)")
+        return r
 
     def analyze_light_curve(self, times, pha, chan_bounds, n_counts_source, **par):
         """The trigger analysis of ONE given light curve (host arrays: the time-sorted total list)."""
