@@ -2196,8 +2196,9 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
     const int32_t *cb = chan_bounds + 8 * u->det;
 
     // bin of an event: edge[k] <= t < edge[k+1] (last bin closed), -1 beyond the last edge
+    const double inv_delta = 1.0 / g.delta;
     auto bin_of = [&](double tt) -> int64_t {
-        int64_t k = (int64_t)floor((tt - g.t0) / g.delta);
+        int64_t k = (int64_t)floor((tt - g.t0) * inv_delta);       // a guess; the exact edges decide
         k = max((int64_t)0, min(k, nb - 1));
         while (k > 0 && tt < g.edge(k))
             k--;

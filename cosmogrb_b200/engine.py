@@ -22,7 +22,7 @@ from . import _capi
 from ._capi import COUNTS_DTYPE, UNIT_DTYPE, WORK_DTYPE, RngDesc
 
 DEFAULT_SEED = 0x00C0560612B
-ENERGY_CHUNK = 4096          # photons per CTA work item of the energy kernels
+ENERGY_CHUNK = 16384         # photons per CTA work item of the energy kernels (amortises the table prologue)
 DIGITIZE_CHUNK = 65536       # photons per CTA of the digitize kernel (amortises staging the 143 KB matrix)
 DEFAULT_MAX_TRIALS = 1 << 22
 
