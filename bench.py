@@ -158,7 +158,7 @@ def run_reference(args):
 
     orc.build()
     threads = len(os.sched_getaffinity(0))
-    n_windows, window_s = 8 * threads, 0.1
+    n_windows, window_s = 4 * threads, 0.1          # ~15-25 s of CPU work per step
     for _ in range(max(args.warmup, 0)):
         cpu_sample(threads, 0.01, threads)
     ev, secs = 0, 0.0
