@@ -67,3 +67,44 @@ def test_no_cpu_fallback():
 
     with pytest.raises(_capi.EngineUnavailable):
         Engine()
+
+
+def test_detector_table_guide_and_layout():
+    """the search guide of the detector block: guide[b][m] = searchsorted(cum[b], m/128) -- a start at or before
+    the lower bound of every r in [m/128, (m+1)/128), which is what the device walk relies on"""
+    from tests import helpers as h
+    from cosmogrb_b200.response.response import channel_search_guide
+
+    src = open(os.path.join(ROOT, "include", "cosmogrb_b200.h")).read()
+    assert _capi.DT_GUIDE == 1720 + 140 * 128 and _capi.DT_SIZE == _capi.DT_GUIDE + 140 * 128 // 8
+    assert f"#define CGRB_DT_SIZE (1720 + 140 * 128 + 140 * 128 / 8)" in src
+    rsp = h.response("n0")
+    tab = rsp.device_table(h.bkg_weights("n0"), "linear")
+    assert tab.shape == (_capi.DT_SIZE,)
+    cum = rsp.cumulative_matrix
+    g = tab[_capi.DT_GUIDE:].view(np.uint8).reshape(_capi.NBINS, _capi.NCHAN)
+    assert np.array_equal(g.reshape(-1), channel_search_guide(cum))
+    rs = np.random.RandomState(0)
+    r = rs.random_sample(20000)
+    b = rs.randint(0, _capi.NBINS, len(r))
+    m = np.minimum((r * _capi.NCHAN).astype(int), _capi.NCHAN - 1)
+    lb = np.array([np.searchsorted(cum[bi], ri, side="left") for bi, ri in zip(b, r)])
+    assert np.all(g[b, m] <= lb)
+    assert np.mean(lb - g[b, m]) < 3.0          # and the walk is short on the GBM-shaped matrix
+    assert _capi.TRIGGER_DTYPE.itemsize == 32
+
+
+def test_trigger_channel_bounds():
+    """channel selection of the trigger == LightCurveStorage._select_channel (light_curve_storage.py:154-182)"""
+    from tests import helpers as h
+    from oracle import trigger_oracle as trg
+    from cosmogrb_b200.instruments.gbm.gbm_lightcurve_analyzer import channel_bounds
+
+    for det in ("n0", "b0"):
+        eb = np.asarray(h.response(det).channel_edges)
+        cb = channel_bounds(eb)
+        pha = np.arange(128)
+        for r, (_, emin, emax) in enumerate(trg.TRIGGER_ENERGY_RANGES):
+            want = trg.select_channel(eb, emin, emax, pha)
+            got = (pha > cb[2 * r]) & (pha < cb[2 * r + 1])
+            assert np.array_equal(got, want)
