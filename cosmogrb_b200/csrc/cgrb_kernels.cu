@@ -481,7 +481,7 @@ __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_uni
 {
     if (squeeze) {
         const double q = (t - u.src_tstart) * sq_inv_h;
-        const int64_t kq = min(max((int64_t)q, (int64_t)0), u.tab_n - 2);
+        const int kq = min(max((int)q, 0), (int)u.tab_n - 2);       // tab_n < 2^31 (host: <= 65536 nodes)
         const double fr = q - (double)kq;
         const double2 n0 = __ldg(sq + kq), n1 = __ldg(sq + kq + 1);
         const double pl = n0.x + (n1.x - n0.x) * fr;
@@ -537,11 +537,20 @@ __global__ void __launch_bounds__(NT, 4) k_source_thin(const double *__restrict_
     long long n_exact = 0;
     int seg_n = 0;        // accepted so far in this segment
     int n_valid_total = 0;
+    // the stored running sums of the NEXT tile are requested before this tile is processed, so their DRAM
+    // latency hides behind the acceptance tests
+    double nxt_a = (2 * threadIdx.x < n) ? seg[2 * threadIdx.x] : INFINITY;
+    double nxt_b = (2 * threadIdx.x + 1 < n) ? seg[2 * threadIdx.x + 1] : INFINITY;
     for (int64_t base = 0; base < n; base += THIN_TILE) {
         const int64_t j0 = base + 2 * threadIdx.x;
         const bool in0 = j0 < n, in1 = j0 + 1 < n;
-        double ta = in0 ? t0 + seg[j0] : INFINITY;
-        double tb = in1 ? t0 + seg[j0 + 1] : INFINITY;
+        double ta = in0 ? t0 + nxt_a : INFINITY;
+        double tb = in1 ? t0 + nxt_b : INFINITY;
+        {
+            const int64_t jn = j0 + THIN_TILE;
+            nxt_a = (jn < n) ? seg[jn] : INFINITY;
+            nxt_b = (jn + 1 < n) ? seg[jn + 1] : INFINITY;
+        }
         // enforce non-decreasing times across association orders (1-ulp inversions)
         s_t[threadIdx.x] = in1 ? tb : ta;
         __syncthreads();

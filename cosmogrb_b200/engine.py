@@ -153,7 +153,7 @@ class Engine(object):
         self.interp_extrap = interp_extrap
         self.energy_sampler = energy_sampler
         self.squeeze = bool(squeeze)
-        self.squeeze_ratio, self.squeeze_min_candidates, self.squeeze_max_nodes = 8, 2048, 1 << 16
+        self.squeeze_ratio, self.squeeze_min_candidates, self.squeeze_max_nodes = 8, 2048, 1 << 14
         self.energy_row_spacing, self.energy_candidates_per_row = 0.02, 256
         # hard ceiling on the thinning candidates of ONE unit (fmax x duration): beyond it the unit's
         # buffers cannot be sized sensibly (the reference's own loop would run for years); raised loudly
