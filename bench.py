@@ -334,6 +334,28 @@ def run_gpu(args):
             peaks = json.load(f)
     except Exception:
         pass
+    # live denominators measured in this run (torch kernels as a yardstick only): a write-only fill and a copy
+    def live_bw(fn, nbytes, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 0.0
+        for _ in range(reps):
+            a.record()
+            fn()
+            b_.record()
+            b_.synchronize()
+            best = max(best, nbytes / (a.elapsed_time(b_) * 1e-3) / 1e9)
+        return best
+
+    try:
+        buf_a = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        buf_b = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+        peaks_live = {"fill_write_gbs": live_bw(lambda: buf_a.fill_(1), 1 << 30),
+                      "copy_read_write_gbs": live_bw(lambda: buf_b.copy_(buf_a), 2 << 30)}
+        del buf_a, buf_b
+    except Exception as e:          # noqa: BLE001
+        peaks_live = {"error": str(e)}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
@@ -486,6 +508,9 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // e2e_steps,
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "rates": {"candidates_per_s": float(counts["n_candidates"].sum()) * world / (ms_max / args.steps * 1e-3),
+                      "rejection_trials_per_s": float(counts["n_trials"].sum()) * world / (ms_max / args.steps * 1e-3)},
+            "peaks_live": peaks_live,
             "roofline": roofline, "roofline_hbm_kernels": hbm_kernels,
             "kernels": kern, "cpu_baseline": cpu_baseline, "clocks": clk, "population": population,
         }
