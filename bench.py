@@ -360,10 +360,11 @@ def run_gpu(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     # DRAM bytes per launch measured by ncu (--set full) on this same workload, kept under profiles/
-    traffic = {}
+    traffic, issue_frac = {}, {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch", {})
+            tj = json.load(f)
+        traffic, issue_frac = tj.get("dram_bytes_per_launch", {}), tj.get("issue_slots_busy_frac", {})
     except Exception:
         pass
 
@@ -373,7 +374,8 @@ def run_gpu(args):
         ach = nbytes / (kern[name]["ms_per_launch"] * 1e-3) / 1e9 if name in kern else 0.0
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic.get(name, traffic.get(key)), "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": kern[name]["ms_per_launch"],
-                "share_of_step": kern[name]["share"], "peak_source": peak_src}
+                "share_of_step": kern[name]["share"], "peak_source": peak_src,
+                "issue_slots_busy_frac_ncu": issue_frac.get(name, issue_frac.get(key))}
 
     roofline = hbm_roofline(top)
     roofline["note"] = ("dominant kernel of this source-dominated workload is fp64-issue bound, not HBM bound: "
