@@ -2014,7 +2014,16 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
     const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool live = d0 < total;
-    const int l0 = (int)(d0 - g0), nt = live ? (int)(d1 - d0) : 0;
+    if (!live) {
+        // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so nobody
+        // will look back at it (the last LIVE tile writes n_kept)
+        if (w == wb && threadIdx.x == 0) {
+            counts[wk.unit].n_total = total;
+            counts[wk.unit].n_kept = 0;
+        }
+        return;
+    }
+    const int l0 = (int)(d0 - g0), nt = (int)(d1 - d0);
 
     unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
     if (live) {
@@ -2094,25 +2103,35 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
         }
         long long excl = 0;
         if (w > wb) {
-            int64_t idx = w - 1;            // lanes look at idx, idx-1, ..., idx-31
-            for (;;) {
-                const int64_t my = idx - lane;
-                unsigned long long st = MD_FLAG_INC;            // before the unit's first tile: prefix 0
-                if (my >= wb) {
-                    do {
-                        st = *((volatile unsigned long long *)(tile_state + my));
-                    } while ((st >> 62) == 0ull);
-                }
-                const unsigned inc = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
-                const int first_inc = inc ? (__ffs(inc) - 1) : 32;     // nearest tile with an inclusive prefix
-                long long v = (lane <= first_inc && my >= wb) ? (long long)(st & MD_VALUE_MASK) : 0;
+            // 256 predecessors per round (8 loads in flight per lane): hundreds of tiles run concurrently, so
+            // the nearest tile with an inclusive prefix is typically that far back
+            int64_t idx = w - 1;
+            bool done = false;
+            while (!done) {
+                unsigned long long st[8];
 #pragma unroll
-                for (int dlt = 16; dlt > 0; dlt >>= 1)
-                    v += __shfl_xor_sync(0xffffffffu, v, dlt);
-                excl += v;
-                if (inc)
-                    break;
-                idx -= 32;
+                for (int q = 0; q < 8; q++) {
+                    const int64_t my = idx - 32 * q - lane;
+                    st[q] = (my >= wb) ? *((volatile unsigned long long *)(tile_state + my)) : MD_FLAG_INC;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (done)
+                        break;
+                    const int64_t my = idx - 32 * q - lane;
+                    while ((st[q] >> 62) == 0ull)
+                        st[q] = *((volatile unsigned long long *)(tile_state + my));
+                    const unsigned inc = __ballot_sync(0xffffffffu, (st[q] >> 62) == 2ull);
+                    const int first_inc = inc ? (__ffs(inc) - 1) : 32;     // nearest tile with an inclusive prefix
+                    long long v = (lane <= first_inc && my >= wb) ? (long long)(st[q] & MD_VALUE_MASK) : 0;
+#pragma unroll
+                    for (int dlt = 16; dlt > 0; dlt >>= 1)
+                        v += __shfl_xor_sync(0xffffffffu, v, dlt);
+                    excl += v;
+                    if (inc)
+                        done = true;
+                }
+                idx -= 256;
             }
             if (lane == 0)
                 atomicExch(tile_state + w, (unsigned long long)(excl + cnt_tile) | MD_FLAG_INC);
@@ -2121,8 +2140,8 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
             s_excl = excl;
             if (w == wb)
                 counts[wk.unit].n_total = total;
-            if (w == we - 1)
-                counts[wk.unit].n_kept = excl + cnt_tile;
+            if (d1 == total)
+                counts[wk.unit].n_kept = excl + cnt_tile;     // the last live tile of the unit
         }
     }
     __syncthreads();
