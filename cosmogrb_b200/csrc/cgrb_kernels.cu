@@ -494,7 +494,7 @@ __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_uni
     return u2 <= lambda_exact(tab, u, t) / u.fmax;   // `if test <= p_test`
 }
 
-__global__ void __launch_bounds__(NT, 4) k_source_thin(const double *__restrict__ dtab,
+__global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict__ dtab,
                                                     const cgrb_unit_t *__restrict__ units,
                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                     cgrb_rng_t rng, const double *__restrict__ segstart,
