@@ -191,36 +191,65 @@ __global__ void __launch_bounds__(256) k_energy_tables(const double *__restrict_
             T->a = a;
         }
     }
-    // upper hull of the 500 lines, built by one thread in shared memory (lines in order of increasing
-    // slope -gx: m = 499 .. 0), then written out by all
+    // upper hull of the 500 lines y_m(w) = gl[m] - gx[m] w, in parallel: line m is the argmax on
+    // [L_m, U_m) with L_m = max over t > m of the crossing with t (m beats t beyond it; ties go to the lower
+    // index, like np.argmax) and U_m = min over t < m of the crossing where t takes over.  It is on the hull
+    // iff L_m < U_m; hull entries are ordered by increasing w = decreasing m.  Crossings are compared by
+    // cross-multiplication (all denominators gx[t] - gx[m] are positive), one division per line at the end.
     __shared__ double s_hw[CGRB_NE_ENVELOPE];
     __shared__ int s_hm[CGRB_NE_ENVELOPE];
+    __shared__ unsigned char s_on[CGRB_NE_ENVELOPE];
+    __shared__ double s_L[CGRB_NE_ENVELOPE];
     __shared__ int s_nh;
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int m = CGRB_NE_ENVELOPE - 1; m >= 0; m--) {
-            if (!(s_gl[m] > -INFINITY))
-                continue;
-            double wx = -INFINITY;
-            while (n > 0) {
-                int t = s_hm[n - 1];
-                // line m overtakes line t (gx[t] > gx[m]) for w > (gl[t] - gl[m]) / (gx[t] - gx[m])
-                wx = (s_gl[t] - s_gl[m]) / (s_gx[t] - s_gx[m]);
-                if (wx <= s_hw[n - 1])
-                    n--;            // t never wins (ties resolve to the lower m, like np.argmax)
-                else
-                    break;
+    for (int m = threadIdx.x; m < CGRB_NE_ENVELOPE; m += blockDim.x) {
+        bool on = s_gl[m] > -INFINITY;
+        double ln = 0.0, ld = 0.0, un = 0.0, ud = 0.0;          // L = ln / ld, U = un / ud (d = 0: none yet)
+        if (on) {
+            const double gm = s_gl[m], xm = s_gx[m];
+            for (int t = m + 1; t < CGRB_NE_ENVELOPE; t++) {
+                const double gt = s_gl[t];
+                if (!(gt > -INFINITY))
+                    continue;
+                const double num = gt - gm, den = s_gx[t] - xm;      // crossing w* = num / den, den > 0
+                if (ld == 0.0 || num * ld > ln * den) {
+                    ln = num;
+                    ld = den;
+                }
             }
-            if (n == 0)
-                wx = -INFINITY;
-            s_hm[n] = m;
-            s_hw[n] = wx;
-            n++;
+            for (int t = 0; t < m; t++) {
+                const double gt = s_gl[t];
+                if (!(gt > -INFINITY))
+                    continue;
+                const double num = gm - gt, den = xm - s_gx[t];
+                if (ud == 0.0 || num * ud < un * den) {
+                    un = num;
+                    ud = den;
+                }
+            }
+            // nonempty interval: L < U
+            if (ld != 0.0 && ud != 0.0)
+                on = ln * ud < un * ld;
         }
-        s_nh = n;
-        T->n_hull = n;
+        s_on[m] = on ? 1 : 0;
+        s_L[m] = (on && ld != 0.0) ? ln / ld : -INFINITY;
     }
     __syncthreads();
+    if (threadIdx.x == 0)
+        s_nh = 0;
+    __syncthreads();
+    for (int m = threadIdx.x; m < CGRB_NE_ENVELOPE; m += blockDim.x) {
+        if (!s_on[m])
+            continue;
+        int rank = 0;                                           // hull lines with a larger index come first
+        for (int t = m + 1; t < CGRB_NE_ENVELOPE; t++)
+            rank += s_on[t];
+        s_hm[rank] = m;
+        s_hw[rank] = s_L[m];
+        atomicAdd(&s_nh, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        T->n_hull = s_nh;
     for (int k = threadIdx.x; k < s_nh; k += blockDim.x) {
         const int m = s_hm[k];
         T->hull_m[k] = m;
