@@ -443,6 +443,7 @@ def run_gpu(args):
         del warm
         uni = GBM_CPL_Universe(synthetic_population(args.population * world, seed=12345), save_path=None)
         sync_all()
+        eng.host_times.clear()
         _capi.profile_enable(True)
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
@@ -480,6 +481,7 @@ def run_gpu(args):
             "events_per_s": n_ev / (ms_pop * 1e-3), "batches_per_gpu": int(uni.n_batches),
             "kernel_ms_per_gpu": tot_k, "kernels": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])[:8]},
             "hbm_kernels": pop_roof, "host_seconds": {k: round(v, 4) for k, v in uni.timings.items()},
+            "host_detail": {k: round(v, 4) for k, v in eng.host_times.items()},
         }
 
     cpu_baseline = None

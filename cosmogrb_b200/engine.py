@@ -33,6 +33,12 @@ def _torch():
     return torch
 
 
+def _now():
+    import time
+
+    return time.perf_counter()
+
+
 # ----------------------------------------------------------------------------------------------
 # uniform sources
 # ----------------------------------------------------------------------------------------------
@@ -159,6 +165,8 @@ class Engine(object):
         # buffers cannot be sized sensibly (the reference's own loop would run for years); raised loudly
         self.max_candidates_per_unit = 1 << 31
         self._call_counter = 0
+        self.host_times = {}        # host seconds spent in allocation / uploads / work-list building (diagnostics)
+        self._pool = None
         self._dtab_cache = {}
         self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
 
@@ -185,6 +193,7 @@ class Engine(object):
         until the stream reaches it: on the compute stream that would serialise host preparation of the next
         batch with the kernels of the current one); the compute stream then waits for the upload."""
         torch = _torch()
+        t0 = _now()
         a = np.ascontiguousarray(arr)
         if a.dtype.fields is not None:
             a = a.view(np.uint8)
@@ -195,11 +204,45 @@ class Engine(object):
             d = torch.from_numpy(a).to(self.device, non_blocking=False)
         cur.wait_stream(self._upload_stream)
         d.record_stream(cur)
+        self.host_times["to_device"] = self.host_times.get("to_device", 0.0) + (_now() - t0)
         return d
 
     def empty(self, n, dtype):
+        """Uninitialised device buffer of at least ``n`` elements.  Inside ``use_pool`` the buffers of a batch
+        are recycled from the pool slot in call order (a batch issues the same sequence of requests every
+        time), so a long run of batches does not go through the allocator at all."""
         torch = _torch()
-        return torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
+        n = max(int(n), 1)
+        pool = self._pool
+        if pool is None:
+            t0 = _now()
+            t = torch.empty(n, dtype=dtype, device=self.device)
+            self.host_times["alloc"] = self.host_times.get("alloc", 0.0) + (_now() - t0)
+            return t
+        i = pool["i"]
+        pool["i"] = i + 1
+        bufs = pool["bufs"]
+        if i < len(bufs) and bufs[i].dtype == dtype and bufs[i].numel() >= n:
+            return bufs[i]
+        t0 = _now()
+        t = torch.empty(n + n // 4 + 1024, dtype=dtype, device=self.device)      # head-room: batches vary in size
+        self.host_times["alloc"] = self.host_times.get("alloc", 0.0) + (_now() - t0)
+        if i < len(bufs):
+            bufs[i] = t
+        else:
+            bufs.append(t)
+        return t
+
+    def use_pool(self, slot):
+        """Route ``empty`` through pool slot ``slot`` (0 / 1: two batches may be in flight), or None to go back
+        to plain allocations.  The caller guarantees that the slot's previous batch has been read back."""
+        if slot is None:
+            self._pool = None
+            return
+        slots = self.__dict__.setdefault("_pool_slots", {})
+        pool = slots.setdefault(slot, {"i": 0, "bufs": []})
+        pool["i"] = 0
+        self._pool = pool
 
     def upload_tables(self, tables):
         """tables: list of float64 blocks (Response.device_table) -> one device tensor."""
@@ -333,8 +376,12 @@ class Engine(object):
     def _work(self, b, which, chunk):
         key = (which, chunk)
         if key not in b.work:
+            t0 = _now()
             w = _capi.build_work(b.units, which, chunk)
-            b.work[key] = (w, self.to_device(w), self.to_device(_unit_work_begin(w, b.n_units)))
+            wb = _unit_work_begin(w, b.n_units)
+            t1 = _now()
+            b.work[key] = (w, self.to_device(w), self.to_device(wb))
+            self.host_times["work_build"] = self.host_times.get("work_build", 0.0) + (t1 - t0)
         return b.work[key]
 
     def set_counts(self, b, **cols):

@@ -156,11 +156,15 @@ class _GBMBatchedUniverse(Universe):
             units, ang = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
             units["fmax"] = fmax_all[sel].reshape(-1)
             t1 = t_()
-            b = eng.new_batch(units, dtab, compute_fmax=False)
-            t2 = t_()
-            eng.process(b, Philox(seed))
-            if trigger:
-                eng.gbm_trigger(b, chan_bounds, threshold=trigger_threshold, fetch=False)
+            eng.use_pool(self.n_batches % 2)          # event buffers recycled from the slot used two batches ago
+            try:
+                b = eng.new_batch(units, dtab, compute_fmax=False)
+                t2 = t_()
+                eng.process(b, Philox(seed))
+                if trigger:
+                    eng.gbm_trigger(b, chan_bounds, threshold=trigger_threshold, fetch=False)
+            finally:
+                eng.use_pool(None)
             t3 = t_()
             tm["build_units"] += t1 - t0
             tm["new_batch"] += t2 - t1

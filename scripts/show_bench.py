@@ -19,7 +19,7 @@ for path in sys.argv[1:]:
         q = d["population"]
         print(f"   population: {q['n_grbs']} GRBs {q['events']:.4g} events in {q['ms']:.1f} ms -> {q['grbs_per_s']:.1f} GRB/s "
               f"{q['events_per_s']:.4g} ev/s; kernels {q['kernel_ms_per_gpu']:.1f} ms, batches {q['batches_per_gpu']}")
-        print(f"      host seconds: {q.get('host_seconds')}")
+        print(f"      host seconds: {q.get('host_seconds')}  detail: {q.get('host_detail')}")
         for k, v in q["kernels"].items():
             print(f"      {k:26s} {v:9.3f} ms")
         for k, v in q["hbm_kernels"].items():
