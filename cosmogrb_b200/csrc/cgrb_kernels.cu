@@ -666,6 +666,7 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
                                                    cgrb_counts_t *counts)
 {
     __shared__ double s_cdf[CGRB_NCHAN];
+    __shared__ unsigned char s_cg[CGRB_NCHAN];      // guide: searchsorted(cdf, m/128, 'right')
     __shared__ int s_wi[NW];
     __shared__ double s_t[NT];
     __shared__ double s_last;
@@ -686,6 +687,17 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
     if (threadIdx.x == 0)
         s_last = t0;
     __syncthreads();
+    if (threadIdx.x < CGRB_NCHAN)
+        s_cg[threadIdx.x] = (unsigned char)min(searchsorted_right(s_cdf, CGRB_NCHAN, (double)threadIdx.x / CGRB_NCHAN),
+                                               CGRB_NCHAN - 1);
+    __syncthreads();
+    // np.searchsorted(cdf, u, 'right') clamped to the last channel, started from the guide: ~2 probes
+    auto channel_of = [&](double uc) -> uint8_t {
+        int j = s_cg[min(max((int)(uc * (double)CGRB_NCHAN), 0), CGRB_NCHAN - 1)];
+        while (j < CGRB_NCHAN - 1 && !(uc < s_cdf[j]))
+            j++;
+        return (uint8_t)j;
+    };
 
     if (wk.start == 0 && threadIdx.x == 0) {
         // event 0: tstart, with its own channel draw (sample_channel(size=len(times)))
@@ -698,7 +710,7 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
             uc = rng_chan.d_u[o];
         }
         times_bkg[off] = u->bkg_tstart;
-        pha_bkg[off] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, uc), CGRB_NCHAN - 1);
+        pha_bkg[off] = channel_of(uc);
         atomicAdd((unsigned long long *)&counts[wk.unit].n_bkg, 1ull);
     }
     if (t0 > tstop)
@@ -745,10 +757,10 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
                 }
             }
             seg_t[j0] = ta;
-            seg_p[j0] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, ua), CGRB_NCHAN - 1);
+            seg_p[j0] = channel_of(ua);
             if (vb) {
                 seg_t[j0 + 1] = tb;
-                seg_p[j0 + 1] = (uint8_t)min(searchsorted_right(s_cdf, CGRB_NCHAN, ub), CGRB_NCHAN - 1);
+                seg_p[j0 + 1] = channel_of(ub);
             }
         }
         const unsigned bala = __ballot_sync(0xffffffffu, va), balb = __ballot_sync(0xffffffffu, vb);
@@ -2298,7 +2310,7 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
 }
 
 // one CTA per unit: prefix sums over the bins, then the sliding-window search in the reference's order
-__global__ void __launch_bounds__(NT) k_trig_eval(const cgrb_unit_t *__restrict__ units, int n_units,
+__global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restrict__ units, int n_units,
                                                   cgrb_trigger_par_t par, const double *__restrict__ times_out,
                                                   const cgrb_counts_t *__restrict__ counts, int64_t bins_per_unit,
                                                   const int32_t *__restrict__ bins, int64_t *__restrict__ csum,
