@@ -1,0 +1,174 @@
+// cgrb_common.cuh -- block scans, thinning uniforms, the lambda(t) table shared by the kernels
+// Part of the single translation unit cgrb_kernels.cu (included in order; see that file).
+#pragma once
+
+#define NT 256            // threads per CTA of the event kernels
+#define NW (NT / 32)
+
+// ==========================================================================================
+// shared helpers
+// ==========================================================================================
+
+// inclusive block scan of doubles over NT threads; s_w holds NW doubles.  Returns the inclusive
+// value, *total = sum over the block.  Contains two __syncthreads and one trailing barrier.
+__device__ __forceinline__ double block_incl_scan(double v, double *s_w, double *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_incl_scan(v, lane);
+    if (lane == 31)
+        s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double w = (lane < NW) ? s_w[lane] : 0.0;
+        w = warp_incl_scan(w, lane);
+        if (lane < NW)
+            s_w[lane] = w;
+    }
+    __syncthreads();
+    double prefix = (wid > 0) ? s_w[wid - 1] : 0.0;
+    *total = s_w[NW - 1];
+    double r = prefix + v;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ int block_incl_scan_i(int v, int *s_w, int *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_incl_scan_i(v, lane);
+    if (lane == 31)
+        s_w[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < NW) ? s_w[lane] : 0;
+        w = warp_incl_scan_i(w, lane);
+        if (lane < NW)
+            s_w[lane] = w;
+    }
+    __syncthreads();
+    int prefix = (wid > 0) ? s_w[wid - 1] : 0;
+    *total = s_w[NW - 1];
+    int r = prefix + v;
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ long long block_sum_ll(long long v, long long *s_w)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0)
+        s_w[wid] = v;
+    __syncthreads();
+    long long t = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++)
+        t += s_w[w];
+    __syncthreads();
+    return t;
+}
+
+// exclusive block scan of doubles (sum of the values of the threads before this one, fixed association)
+__device__ __forceinline__ double block_excl_scan(double v, double *s_w, double *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double incl = warp_incl_scan(v, lane);
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0)
+        excl = 0.0;
+    if (lane == 31)
+        s_w[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        double w = (lane < NW) ? s_w[lane] : 0.0;
+        w = warp_incl_scan(w, lane);
+        if (lane < NW)
+            s_w[lane] = w;
+    }
+    __syncthreads();
+    const double prefix = (wid > 0) ? s_w[wid - 1] : 0.0;
+    *total = s_w[NW - 1];
+    const double r = prefix + excl;
+    __syncthreads();
+    return r;
+}
+
+// Thinning uniforms.  Candidate k of a unit consumes u1 (gap) and u2 (acceptance test for the source,
+// channel draw for the background).  Under Philox one call serves the candidate PAIR (2m, 2m+1):
+// counter (index m, sub 0) -> (u1 of 2m, u1 of 2m+1), (index m, sub 1) -> (u2 of 2m, u2 of 2m+1), so
+// the gap pass and the decision pass each cost half a Philox call per candidate.  Injected streams
+// keep the reference's order u1, u2, u1, u2, ... (Appendix A of SURVEY.md): candidate k reads
+// u[2k], u[2k+1]; the stream may end on an odd count.
+struct PairDraw {
+    double a, b;        // values for candidates 2m and 2m+1
+    bool exhausted;
+};
+__device__ __forceinline__ double injected_thin_uniform(const cgrb_rng_t &rng, int64_t off, int64_t len, int64_t k,
+                                                        int which, bool *exhausted)
+{
+    const int64_t pos = 2 * k + which;
+    if (pos < len)
+        return rng.d_u[off + pos];
+    if (which == 1)
+        return 0.5;                 // never consulted: the candidate's u1 was the last uniform or beyond
+    *exhausted = true;
+    return 0.0;                     // -log(0) = +inf: terminates the unit
+}
+__device__ __forceinline__ PairDraw pair_draw(const cgrb_rng_t &rng, int unit, uint32_t stream_id, uint32_t stage,
+                                              int64_t m, int which)
+{
+    PairDraw d;
+    d.exhausted = false;
+    if (rng.mode == 0) {
+        Philox4 p = philox_at(make_key(rng.seed), stream_id, stage, (uint64_t)m, (uint32_t)which);
+        d.a = u53(p.x, p.y);
+        d.b = u53(p.z, p.w);
+    } else {
+        const int64_t off = rng.d_off ? rng.d_off[unit] : 0;
+        const int64_t len = rng.d_len ? rng.d_len[unit] : ((int64_t)1 << 62);
+        d.a = injected_thin_uniform(rng, off, len, 2 * m, which, &d.exhausted);
+        d.b = injected_thin_uniform(rng, off, len, 2 * m + 1, which, &d.exhausted);
+    }
+    return d;
+}
+#define THIN_TILE (2 * NT)      // candidates per tile: two per thread
+
+// per-unit tables for lambda(t): lambda = norm * ec^-alpha * sum_m c_m exp(-x_m / ec)
+struct LambdaTab {
+    double c[CGRB_NE_LAMBDA];
+    double x[CGRB_NE_LAMBDA];
+};
+
+// builds the table cooperatively; caller syncs afterwards
+__device__ __forceinline__ void build_lambda_tab(LambdaTab *tab, const double *dt, const cgrb_unit_t &u)
+{
+    const double *E = dt + CGRB_DT_G75_E;
+    const double *A = dt + CGRB_DT_G75_A;
+    const double opz = 1.0 + u.z;
+    for (int m = threadIdx.x; m < CGRB_NE_LAMBDA; m += blockDim.x) {
+        // np.trapz weights of cpl_functions.py:325
+        double w;
+        if (m == 0)
+            w = 0.5 * (E[1] - E[0]);
+        else if (m == CGRB_NE_LAMBDA - 1)
+            w = 0.5 * (E[m] - E[m - 1]);
+        else
+            w = 0.5 * (E[m] - E[m - 1]) + 0.5 * (E[m + 1] - E[m]);
+        double x = E[m] * opz;                       // cpl_functions.py:95
+        tab->x[m] = x;
+        tab->c[m] = w * (A[m] * u.ea_scale) * pow(x, u.alpha);
+    }
+}
+
+__device__ __forceinline__ double lambda_at(const LambdaTab *tab, const cgrb_unit_t &u, double t)
+{
+    SpecT s = spec_at(u, t);
+    double acc = 0.0;
+#pragma unroll 5
+    for (int m = 0; m < CGRB_NE_LAMBDA; m++)
+        acc += tab->c[m] * exp(-tab->x[m] * s.inv_ec);
+    return s.norm * exp(-u.alpha * s.log_ec) * acc;
+}
+

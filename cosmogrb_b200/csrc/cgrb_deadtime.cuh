@@ -1,0 +1,599 @@
+// cgrb_deadtime.cuh -- combine (merge) and GBM dead time: the unfused pair and the one-pass kernel with decoupled look-back
+// Part of the single translation unit cgrb_kernels.cu (included in order; see that file).
+#pragma once
+
+// ==========================================================================================
+// combine (lightcurve.py:131-151): merge-path tiles; inside a tile each element finds its rank
+// by a binary search in the other list's slice held in shared memory.
+// ==========================================================================================
+__global__ void __launch_bounds__(NT) k_combine(const cgrb_unit_t *__restrict__ units,
+                                                const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                const double *__restrict__ times_bkg,
+                                                const uint8_t *__restrict__ pha_bkg,
+                                                const double *__restrict__ times_src,
+                                                const uint8_t *__restrict__ pha_src,
+                                                double *__restrict__ times_tot, uint8_t *__restrict__ pha_tot,
+                                                cgrb_counts_t *counts)
+{
+    __shared__ double s_t[CGRB_MERGE_TILE];
+    __shared__ uint8_t s_p[CGRB_MERGE_TILE];
+    __shared__ int64_t s_split[2];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
+    const int64_t total = nA + nB;
+    if (wk.start == 0 && threadIdx.x == 0)
+        counts[wk.unit].n_total = total;
+    if (wk.start >= total)
+        return;
+    const double *A = times_bkg + u->bkg_off;
+    const double *B = times_src + u->src_off;
+    const int64_t d0 = wk.start, d1 = min(d0 + (int64_t)CGRB_MERGE_TILE, total);
+    if (threadIdx.x < 2) {
+        const int64_t d = threadIdx.x ? d1 : d0;
+        int64_t lo = max((int64_t)0, d - nB), hi = min(d, nA);
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (A[mid] <= B[d - 1 - mid])     // ties: background first
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        s_split[threadIdx.x] = lo;
+    }
+    __syncthreads();
+    const int64_t i0 = s_split[0], i1 = s_split[1];
+    const int64_t j0 = d0 - i0, j1 = d1 - i1;
+    const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+    for (int k = threadIdx.x; k < na; k += NT) {
+        s_t[k] = A[i0 + k];
+        s_p[k] = pha_bkg[u->bkg_off + i0 + k];
+    }
+    for (int k = threadIdx.x; k < nb; k += NT) {
+        s_t[na + k] = B[j0 + k];
+        s_p[na + k] = pha_src[u->src_off + j0 + k];
+    }
+    __syncthreads();
+    double *out_t = times_tot + u->tot_off + d0;
+    uint8_t *out_p = pha_tot + u->tot_off + d0;
+    for (int k = threadIdx.x; k < na + nb; k += NT) {
+        const double t = s_t[k];
+        int rank;
+        if (k < na) {
+            // number of source events strictly earlier
+            int lo = 0, hi = nb;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (s_t[na + mid] < t)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            rank = k + lo;
+        } else {
+            // number of background events earlier or equal
+            int lo = 0, hi = na;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (t < s_t[mid])
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            rank = (k - na) + lo;
+        }
+        out_t[rank] = t;
+        out_p[rank] = s_p[k];
+    }
+}
+
+// ==========================================================================================
+// GBM dead time, literal reference semantics (gbm_lightcurve.py:80-115).
+//   event 0 is kept and opens a window (10.6 us if overflow channel, else 2.6 us);
+//   afterwards an event is kept iff t > t_end, and ONLY a kept overflow event moves t_end.
+// The chain of dependence runs only through overflow events closer than 10.6 us to each other,
+// so each event resolves its keep flag from a short local look-back (exact for any input).
+// ==========================================================================================
+#define DT_TAU 10.6e-6
+#define DT_NORMAL 2.6e-6
+
+__device__ __forceinline__ double dt_pe(const double *t, const uint8_t *p, int64_t j)
+{
+    return t[j] + ((j == 0 && p[0] != 127) ? DT_NORMAL : DT_TAU);
+}
+
+__device__ __forceinline__ bool dt_keep(const double *__restrict__ t, const uint8_t *__restrict__ p, int64_t i)
+{
+    if (i == 0)
+        return true;
+    const double ti = t[i];
+    // nearest earlier chain element (overflow event or event 0) whose window could cover ti
+    int64_t found = -1;
+    for (int64_t j = i - 1; j >= 0; j--) {
+        if (t[j] + DT_TAU < ti)
+            break;
+        if (p[j] == 127 || j == 0) {
+            found = j;
+            break;
+        }
+    }
+    if (found < 0)
+        return true;
+    // walk back to a chain element that is certainly kept
+    int64_t head = found;
+    while (head > 0) {
+        const double th = t[head];
+        int64_t q = -1;
+        for (int64_t j = head - 1; j >= 0; j--) {
+            if (t[j] + DT_TAU < th)
+                break;
+            if (p[j] == 127 || j == 0) {
+                q = j;
+                break;
+            }
+        }
+        if (q < 0 || dt_pe(t, p, q) < th)
+            break;          // nothing before `head` can veto it
+        head = q;
+    }
+    // replay the reference loop from the head
+    double t_end = dt_pe(t, p, head);
+    for (int64_t j = head + 1; j < i; j++) {
+        if (p[j] == 127) {
+            const double tj = t[j];
+            if (tj > t_end)
+                t_end = tj + DT_TAU;
+        }
+    }
+    return ti > t_end;
+}
+
+__global__ void __launch_bounds__(NT) k_deadtime_count(const cgrb_unit_t *__restrict__ units,
+                                                       const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                       const double *__restrict__ times_tot,
+                                                       const uint8_t *__restrict__ pha_tot,
+                                                       int32_t *__restrict__ tile_count,
+                                                       const cgrb_counts_t *counts)
+{
+    __shared__ int s_wi[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t n = counts[wk.unit].n_total;
+    int cnt = 0;
+    if (wk.start < n) {
+        const double *t = times_tot + u->tot_off;
+        const uint8_t *p = pha_tot + u->tot_off;
+        const int64_t end = min(wk.start + (int64_t)CGRB_DT_TILE, n);
+        for (int64_t i = wk.start + threadIdx.x; i < end; i += NT)
+            cnt += dt_keep(t, p, i) ? 1 : 0;
+    }
+    int total;
+    (void)block_incl_scan_i(cnt, s_wi, &total);
+    if (threadIdx.x == 0)
+        tile_count[w] = total;
+}
+
+__global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__restrict__ units,
+                                                       const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                       const int64_t *__restrict__ unit_work_begin,
+                                                       const double *__restrict__ times_tot,
+                                                       const uint8_t *__restrict__ pha_tot,
+                                                       const int32_t *__restrict__ tile_count,
+                                                       double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
+                                                       uint8_t *__restrict__ selection, cgrb_counts_t *counts)
+{
+    __shared__ long long s_wl[NW];
+    __shared__ int s_wi[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t n = counts[wk.unit].n_total;
+    const int64_t b = unit_work_begin[wk.unit], e = unit_work_begin[wk.unit + 1];
+    long long part = 0;
+    for (int64_t s = b + threadIdx.x; s < w; s += NT)
+        part += tile_count[s];
+    long long off = block_sum_ll(part, s_wl);
+    if (w == e - 1 && threadIdx.x == 0)
+        counts[wk.unit].n_kept = off + tile_count[w];
+    if (wk.start >= n)
+        return;
+    const double *t = times_tot + u->tot_off;
+    const uint8_t *p = pha_tot + u->tot_off;
+    double *ot = times_out + u->tot_off;
+    uint8_t *op = pha_out + u->tot_off;
+    const int64_t end = min(wk.start + (int64_t)CGRB_DT_TILE, n);
+    for (int64_t base = wk.start; base < end; base += NT) {
+        const int64_t i = base + threadIdx.x;
+        bool keep = false;
+        double ti = 0.0;
+        uint8_t pi = 0;
+        if (i < end) {
+            keep = dt_keep(t, p, i);
+            ti = t[i];
+            pi = p[i];
+            if (selection)
+                selection[u->tot_off + i] = keep ? 1 : 0;
+        }
+        int total;
+        int incl = block_incl_scan_i(keep ? 1 : 0, s_wi, &total);
+        if (keep) {
+            ot[off + incl - 1] = ti;
+            op[off + incl - 1] = pi;
+        }
+        off += total;
+    }
+}
+
+// ==========================================================================================
+// combine + dead time in ONE pass (lightcurve.py:131-151 then gbm_lightcurve.py:42-56): the merged
+// pre-dead-time list is not a product of LightCurve.process (light_curve_storage.py:16-80 keeps the two
+// component lists and the filtered total), so it never has to exist in HBM.  Each CTA merges one tile
+// of the merged order (plus a look-back halo) in shared memory, resolves the keep flags there with the
+// same literal rule as dt_keep, and appends the survivors to the unit's output at an offset obtained by a
+// decoupled look-back over the preceding tiles' survivor counts (integers: deterministic).
+// 9 B read + <= 9 B written per event.
+// ==========================================================================================
+#define MD_TILE 2048
+#define MD_HALO 256
+#define MD_N (MD_TILE + MD_HALO)
+#define MD_FLAG_AGG (1ull << 62)
+#define MD_FLAG_INC (2ull << 62)
+#define MD_VALUE_MASK ((1ull << 62) - 1ull)
+
+// merge-path split of diagonal d: number of background events among the first d merged events
+__device__ __forceinline__ int64_t merge_split(const double *__restrict__ A, int64_t nA, const double *__restrict__ B,
+                                               int64_t nB, int64_t d)
+{
+    int64_t lo = max((int64_t)0, d - nB), hi = min(d, nA);
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (A[mid] <= B[d - 1 - mid])     // ties: background first
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// merged event g read straight from the two global lists (O(log n) per access: the rare slow path)
+struct MergedGlobal {
+    const double *A, *B;
+    const uint8_t *pA, *pB;
+    int64_t nA, nB;
+    __device__ __forceinline__ void get(int64_t g, double *t, uint8_t *p) const
+    {
+        const int64_t ia = merge_split(A, nA, B, nB, g), ib = g - ia;
+        if (ia < nA && (ib >= nB || A[ia] <= B[ib])) {
+            *t = A[ia];
+            *p = pA[ia];
+        } else {
+            *t = B[ib];
+            *p = pB[ib];
+        }
+    }
+};
+
+// the literal dead-time rule for merged event g (same walk as dt_keep) on the slow accessor
+__device__ __noinline__ bool dt_keep_slow(const MergedGlobal &m, int64_t i)
+{
+    if (i == 0)
+        return true;
+    double ti, tj;
+    uint8_t pi, pj;
+    m.get(i, &ti, &pi);
+    int64_t found = -1;
+    for (int64_t j = i - 1; j >= 0; j--) {
+        m.get(j, &tj, &pj);
+        if (tj + DT_TAU < ti)
+            break;
+        if (pj == 127 || j == 0) {
+            found = j;
+            break;
+        }
+    }
+    if (found < 0)
+        return true;
+    int64_t head = found;
+    while (head > 0) {
+        double th;
+        uint8_t ph;
+        m.get(head, &th, &ph);
+        int64_t q = -1;
+        double tq = 0.0;
+        uint8_t pq = 0;
+        for (int64_t j = head - 1; j >= 0; j--) {
+            m.get(j, &tq, &pq);
+            if (tq + DT_TAU < th)
+                break;
+            if (pq == 127 || j == 0) {
+                q = j;
+                break;
+            }
+        }
+        if (q < 0 || tq + ((q == 0 && pq != 127) ? DT_NORMAL : DT_TAU) < th)
+            break;
+        head = q;
+    }
+    double th;
+    uint8_t ph;
+    m.get(head, &th, &ph);
+    double t_end = th + ((head == 0 && ph != 127) ? DT_NORMAL : DT_TAU);
+    for (int64_t j = head + 1; j < i; j++) {
+        m.get(j, &tj, &pj);
+        if (pj == 127 && tj > t_end)
+            t_end = tj + DT_TAU;
+    }
+    return ti > t_end;
+}
+
+// the same rule on the tile in shared memory: local index li <-> merged rank g0 + li.  Returns 0 / 1, or 2
+// if the walk would leave the tile's halo (the caller then takes the slow path).
+__device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, int li, int64_t g0)
+{
+    if (g0 + li == 0)
+        return 1;
+    const bool has0 = (g0 == 0);            // local index 0 is the unit's event 0
+    const double ti = t[li];
+    int found = -1;
+    int j = li - 1;
+    for (; j >= 0; j--) {
+        if (t[j] + DT_TAU < ti)
+            return 1;                       // nothing within the longest window: kept
+        if (p[j] == 127 || (has0 && j == 0)) {
+            found = j;
+            break;
+        }
+    }
+    if (found < 0)
+        return 2;                           // ran out of halo
+    int head = found;
+    for (;;) {
+        if (has0 && head == 0)
+            break;
+        const double th = t[head];
+        int q = -1;
+        int jj = head - 1;
+        bool gap = false;
+        for (; jj >= 0; jj--) {
+            if (t[jj] + DT_TAU < th) {
+                gap = true;
+                break;
+            }
+            if (p[jj] == 127 || (has0 && jj == 0)) {
+                q = jj;
+                break;
+            }
+        }
+        if (q < 0) {
+            if (gap)
+                break;                      // nothing before `head` can veto it
+            return 2;                       // ran out of halo
+        }
+        const double pe = t[q] + ((has0 && q == 0 && p[0] != 127) ? DT_NORMAL : DT_TAU);
+        if (pe < th)
+            break;
+        head = q;
+    }
+    double t_end = t[head] + ((has0 && head == 0 && p[0] != 127) ? DT_NORMAL : DT_TAU);
+    for (int jj = head + 1; jj < li; jj++)
+        if (p[jj] == 127) {
+            const double tj = t[jj];
+            if (tj > t_end)
+                t_end = tj + DT_TAU;
+        }
+    return ti > t_end ? 1 : 0;
+}
+
+// merge-path splits of every tile, one thread per tile: the ~23 dependent probes of each search are
+// hidden by the other tiles' searches instead of stalling a whole CTA at its first barrier.
+// splits[2w] = split at the tile's halo start, splits[2w+1] = split at the tile start.
+__global__ void __launch_bounds__(NT) k_merge_splits(const cgrb_unit_t *__restrict__ units,
+                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                     const double *__restrict__ times_bkg,
+                                                     const double *__restrict__ times_src,
+                                                     int64_t *__restrict__ splits, const cgrb_counts_t *counts)
+{
+    const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
+    if (wk.start >= nA + nB)
+        return;
+    const double *A = times_bkg + u->bkg_off;
+    const double *B = times_src + u->src_off;
+    splits[2 * w] = merge_split(A, nA, B, nB, max((int64_t)0, wk.start - MD_HALO));
+    splits[2 * w + 1] = merge_split(A, nA, B, nB, wk.start);
+}
+
+#define MD_PER (MD_N / NT)       // merged elements per thread in the serial merge (9)
+#define MD_R (MD_TILE / NT)     // tile elements per thread in the dead-time pass (8)
+
+__global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
+                                                       const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                       const int64_t *__restrict__ unit_work_begin,
+                                                       const double *__restrict__ times_bkg,
+                                                       const uint8_t *__restrict__ pha_bkg,
+                                                       const double *__restrict__ times_src,
+                                                       const uint8_t *__restrict__ pha_src,
+                                                       unsigned long long *tile_state,
+                                                       const int64_t *__restrict__ splits,
+                                                       double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
+                                                       cgrb_counts_t *counts)
+{
+    __shared__ double s_in_t[MD_N];         // the two input slices, background first
+    __shared__ double s_t[MD_N];            // merged
+    __shared__ uint8_t s_in_p[MD_N];
+    __shared__ uint8_t s_p[MD_N];
+    __shared__ int s_cnt[MD_R * NW];        // survivors per (round, warp), then their exclusive prefix
+    __shared__ long long s_excl;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
+    const int64_t total = nA + nB;
+    const int64_t wb = unit_work_begin[wk.unit];
+    const double *A = times_bkg + u->bkg_off;
+    const double *B = times_src + u->src_off;
+    const uint8_t *pA = pha_bkg + u->bkg_off;
+    const uint8_t *pB = pha_src + u->src_off;
+    const int64_t d0 = wk.start, d1 = min(d0 + (int64_t)MD_TILE, total);
+    const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool live = d0 < total;
+    if (!live) {
+        // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so nobody
+        // will look back at it (the last LIVE tile writes n_kept)
+        if (w == wb && threadIdx.x == 0) {
+            counts[wk.unit].n_total = total;
+            counts[wk.unit].n_kept = 0;
+        }
+        return;
+    }
+    const int l0 = (int)(d0 - g0), nt = (int)(d1 - d0);
+
+    unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
+    if (live) {
+        // d1 is either the next tile's start (same unit) or the end of the merged list
+        const int64_t i0 = splits[2 * w], i1 = (d1 == total) ? nA : splits[2 * (w + 1) + 1];
+        const int64_t j0 = g0 - i0, j1 = d1 - i1;
+        const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+        for (int k = threadIdx.x; k < na; k += NT) {
+            s_in_t[k] = A[i0 + k];
+            s_in_p[k] = pA[i0 + k];
+        }
+        for (int k = threadIdx.x; k < nb; k += NT) {
+            s_in_t[na + k] = B[j0 + k];
+            s_in_p[na + k] = pB[j0 + k];
+        }
+        __syncthreads();
+        // serial merge of MD_PER consecutive outputs per thread from its merge-path split
+        {
+            const double *a_ = s_in_t, *b_ = s_in_t + na;
+            const int n = na + nb;
+            const int q0 = min(threadIdx.x * MD_PER, n);
+            int lo = max(0, q0 - nb), hi = min(q0, na);
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            int ia = lo, ib = q0 - lo;
+#pragma unroll
+            for (int r = 0; r < MD_PER; r++) {
+                const int q = q0 + r;
+                if (q < n) {
+                    const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
+                    const int src = take_a ? ia : na + ib;
+                    s_t[q] = s_in_t[src];
+                    s_p[q] = s_in_p[src];
+                    ia += take_a ? 1 : 0;
+                    ib += take_a ? 0 : 1;
+                }
+            }
+        }
+        __syncthreads();
+        // keep flags of the tile's own events (local indices [l0, l0 + nt))
+        MergedGlobal mg{A, B, pA, pB, nA, nB};
+#pragma unroll
+        for (int r = 0; r < MD_R; r++) {
+            const int e = r * NT + threadIdx.x;
+            int keep = 0;
+            if (e < nt) {
+                keep = dt_keep_local(s_t, s_p, l0 + e, g0);
+                if (keep == 2)
+                    keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0)
+                s_cnt[r * NW + wid] = __popc(bal);
+            // rank inside the (round, warp) group, kept in the upper bits
+            keep_bits |= (unsigned)keep << r;
+        }
+    }
+    __syncthreads();
+
+    // warp 0: exclusive prefix of the 64 group counts, then the decoupled look-back over the unit's
+    // earlier tiles for this tile's offset in the unit's output
+    if (wid == 0) {
+        int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        int incl = warp_incl_scan_i(c0 + c1, lane);
+        const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
+        s_cnt[2 * lane] = incl - c0 - c1;
+        s_cnt[2 * lane + 1] = incl - c1;
+        if (lane == 0) {
+            const unsigned long long mine = (unsigned long long)cnt_tile | (w == wb ? MD_FLAG_INC : MD_FLAG_AGG);
+            atomicExch(tile_state + w, mine);
+        }
+        long long excl = 0;
+        if (w > wb) {
+            // 256 predecessors per round (8 loads in flight per lane): hundreds of tiles run concurrently, so
+            // the nearest tile with an inclusive prefix is typically that far back
+            int64_t idx = w - 1;
+            bool done = false;
+            while (!done) {
+                unsigned long long st[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int64_t my = idx - 32 * q - lane;
+                    st[q] = (my >= wb) ? *((volatile unsigned long long *)(tile_state + my)) : MD_FLAG_INC;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (done)
+                        break;
+                    const int64_t my = idx - 32 * q - lane;
+                    while ((st[q] >> 62) == 0ull)
+                        st[q] = *((volatile unsigned long long *)(tile_state + my));
+                    const unsigned inc = __ballot_sync(0xffffffffu, (st[q] >> 62) == 2ull);
+                    const int first_inc = inc ? (__ffs(inc) - 1) : 32;     // nearest tile with an inclusive prefix
+                    long long v = (lane <= first_inc && my >= wb) ? (long long)(st[q] & MD_VALUE_MASK) : 0;
+#pragma unroll
+                    for (int dlt = 16; dlt > 0; dlt >>= 1)
+                        v += __shfl_xor_sync(0xffffffffu, v, dlt);
+                    excl += v;
+                    if (inc)
+                        done = true;
+                }
+                idx -= 256;
+            }
+            if (lane == 0)
+                atomicExch(tile_state + w, (unsigned long long)(excl + cnt_tile) | MD_FLAG_INC);
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (w == wb)
+                counts[wk.unit].n_total = total;
+            if (d1 == total)
+                counts[wk.unit].n_kept = excl + cnt_tile;     // the last live tile of the unit
+        }
+    }
+    __syncthreads();
+    double *ot = times_out + u->tot_off + s_excl;
+    uint8_t *op = pha_out + u->tot_off + s_excl;
+#pragma unroll
+    for (int r = 0; r < MD_R; r++) {
+        // survivors of (round r, this warp) before this lane
+        unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
+        if ((keep_bits >> r) & 1u) {
+            const int rank = s_cnt[r * NW + wid] + __popc(bal & ((1u << lane) - 1u));
+            const int li = l0 + r * NT + threadIdx.x;
+            ot[rank] = s_t[li];
+            op[rank] = s_p[li];
+        }
+    }
+}
+

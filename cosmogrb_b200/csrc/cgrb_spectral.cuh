@@ -1,0 +1,141 @@
+// cgrb_spectral.cuh -- lambda(t), evolution, fmax and the squeeze table of the thinning acceptance test
+// Part of the single translation unit cgrb_kernels.cu (included in order; see that file).
+#pragma once
+
+// ==========================================================================================
+// spectral model kernels
+// ==========================================================================================
+
+// SourceFunction.energy_integrated_evolution at arbitrary times
+__global__ void __launch_bounds__(NT) k_lambda(const double *__restrict__ dtab, const cgrb_unit_t *units,
+                                               int unit_index, const double *__restrict__ times,
+                                               int64_t n, double *__restrict__ out)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    if (threadIdx.x == 0)
+        u = units[unit_index];
+    __syncthreads();
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * NT + threadIdx.x; i < n; i += (int64_t)gridDim.x * NT)
+        out[i] = lambda_at(&tab, u, times[i]);
+}
+
+// SourceFunction.evolution(energy, time): cpl_evolution without the response
+__global__ void __launch_bounds__(NT) k_evolution(const cgrb_unit_t *units, int unit_index,
+                                                  const double *__restrict__ energy, int64_t n_energy,
+                                                  const double *__restrict__ times, int64_t n_time,
+                                                  double *__restrict__ out)
+{
+    __shared__ cgrb_unit_t u;
+    if (threadIdx.x == 0)
+        u = units[unit_index];
+    __syncthreads();
+    const double opz = 1.0 + u.z;
+    for (int64_t it = blockIdx.x; it < n_time; it += gridDim.x) {
+        SpecT s = spec_at(u, times[it]);
+        for (int64_t m = threadIdx.x; m < n_energy; m += NT) {
+            double x = energy[m] * opz;
+            out[it * n_energy + m] = cpl_value(s, u.alpha, x, log(x));
+        }
+    }
+}
+
+// Source._get_energy_integrated_max: one CTA per unit, 50-point time grid (source.py:88-110)
+__global__ void __launch_bounds__(64) k_fmax(const double *__restrict__ dtab, cgrb_unit_t *units, int n_units)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    __shared__ double s_f[64];
+    const int ui = blockIdx.x;
+    if (ui >= n_units)
+        return;
+    if (threadIdx.x == 0)
+        u = units[ui];
+    __syncthreads();
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    __syncthreads();
+    double f = -INFINITY;
+    if (threadIdx.x < CGRB_NT_FMAX) {
+        // np.linspace(tstart, tstop, 50)
+        double step = (u.src_tstop - u.src_tstart) / (double)(CGRB_NT_FMAX - 1);
+        double t = (threadIdx.x == CGRB_NT_FMAX - 1) ? u.src_tstop : u.src_tstart + threadIdx.x * step;
+        f = lambda_at(&tab, u, t);
+    }
+    s_f[threadIdx.x] = f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double best = s_f[0];
+        bool has_nan = isnan(best);
+        for (int i = 1; i < CGRB_NT_FMAX; i++) {
+            has_nan |= isnan(s_f[i]);
+            if (s_f[i] > best)
+                best = s_f[i];
+        }
+        units[ui].fmax = has_nan ? nan("") : best;   // np.max propagates NaN
+    }
+}
+
+// ==========================================================================================
+// squeeze table of the thinning acceptance probability p(t) = lambda(t) / fmax (see the header):
+// nodes on a uniform time grid, then per-interval interpolation-error margins from second differences.
+// ==========================================================================================
+__global__ void __launch_bounds__(NT) k_thin_nodes(const double *__restrict__ dtab,
+                                                   const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   double *__restrict__ thin_tab)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    if (threadIdx.x == 0)
+        u = units[wk.unit];
+    __syncthreads();
+    if (u.tab_n < 4 || (u.flags & CGRB_UNIT_NO_SOURCE))
+        return;
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    __syncthreads();
+    const int64_t k = wk.start + threadIdx.x;
+    if (k >= u.tab_n)
+        return;
+    const double h = (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1);
+    const double t = (k == u.tab_n - 1) ? u.src_tstop : u.src_tstart + (double)k * h;
+    thin_tab[2 * (u.tab_off + k)] = lambda_at(&tab, u, t) / u.fmax;
+}
+
+__global__ void __launch_bounds__(NT) k_thin_margins(const cgrb_unit_t *__restrict__ units,
+                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                     double *__restrict__ thin_tab)
+{
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t n = u->tab_n;
+    if (n < 4 || (u->flags & CGRB_UNIT_NO_SOURCE))
+        return;
+    const int64_t k = wk.start + threadIdx.x;      // interval [k, k+1]
+    if (k >= n)
+        return;
+    const double *p = thin_tab + 2 * u->tab_off;
+    // |second differences| at the nodes k-1 .. k+2 (clamped to the interior nodes 1 .. n-2)
+    double m = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int d = -1; d <= 2; d++) {
+        int64_t c = min(max(k + d, (int64_t)1), n - 2);
+        double d2 = fabs(p[2 * (c - 1)] - 2.0 * p[2 * c] + p[2 * (c + 1)]);
+        bad |= !(d2 == d2) || isinf(d2);
+        m = fmax(m, d2);
+    }
+    // linear interpolation error <= h^2/8 sup|p''| ~ d2/8; x4 safety, plus rounding slack
+    double pk = fabs(p[2 * k]);
+    double margin = 0.5 * m + 1e-12 * (pk + 1.0);
+    thin_tab[2 * (u->tab_off + k) + 1] = bad ? INFINITY : margin;
+}
+

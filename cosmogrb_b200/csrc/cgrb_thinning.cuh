@@ -1,0 +1,409 @@
+// cgrb_thinning.cuh -- NHPP thinning of the source rate and the homogeneous background (gap pass, segment scan, decision pass)
+// Part of the single translation unit cgrb_kernels.cu (included in order; see that file).
+#pragma once
+
+// ==========================================================================================
+// thinning pass 1: exponential gaps of a segment, their running sum INSIDE the segment (stored: the
+// candidate's arrival time minus the segment's start time) and the segment total.  Pass 2 turns the
+// totals into segment start times, pass 3 adds the start time -- no gap is drawn twice.
+// The summation order is fixed (pairs, tiles of THIN_TILE, segments of CGRB_SEG), so times are reproducible.
+// ==========================================================================================
+template <int WHICH>  // 0 = source (prefix -> stage at src_off), 1 = background (prefix -> times_bkg at bkg_off + 1)
+__global__ void __launch_bounds__(NT) k_gap_prefix(const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   cgrb_rng_t rng, double *__restrict__ segsum,
+                                                   double *__restrict__ prefix_out, cgrb_counts_t *counts)
+{
+    __shared__ double s_w[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t cap = (WHICH == 0) ? u->src_cap : u->bkg_cap;
+    const double rate = (WHICH == 0) ? u->fmax : u->bkg_rate;
+    const double inv_f = 1.0 / rate;
+    const uint32_t stage = (WHICH == 0) ? ST_SRC_TIME : ST_BKG;
+    const uint32_t sid = u->stream_id;
+    const int64_t n = min((int64_t)CGRB_SEG, cap - wk.start);
+    double *out = prefix_out + ((WHICH == 0) ? u->src_off : u->bkg_off + 1) + wk.start;
+    double carry = 0.0;
+    bool exhausted = false;
+    for (int64_t base = 0; base < n; base += THIN_TILE) {
+        const int64_t j0 = base + 2 * threadIdx.x;          // wk.start and base are even
+        double g0 = 0.0, g1 = 0.0;
+        if (j0 < n) {
+            PairDraw d = pair_draw(rng, wk.unit, sid, stage, (wk.start + j0) >> 1, 0);
+            g0 = -(inv_f * log(d.a));                        // time - (1/fmax) * log(u)  cpl_functions.py:160
+            if (j0 + 1 < n)
+                g1 = -(inv_f * log(d.b));
+            exhausted |= d.exhausted;
+        }
+        double total;
+        const double excl = block_excl_scan(g0 + g1, s_w, &total);
+        const double p0 = (carry + excl) + g0, p1 = p0 + g1;
+        if (j0 < n)
+            out[j0] = p0;
+        if (j0 + 1 < n)
+            out[j0 + 1] = p1;
+        carry = carry + total;
+    }
+    if (threadIdx.x == 0)
+        segsum[w] = carry;
+    if (exhausted)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
+}
+
+// pass 2: sequential (association-exact) scan of the segment sums of each unit: one warp per unit
+template <int WHICH>
+__global__ void __launch_bounds__(128) k_seg_scan(const cgrb_unit_t *__restrict__ units, int n_units,
+                                                  const int64_t *__restrict__ unit_work_begin,
+                                                  const double *__restrict__ segsum,
+                                                  double *__restrict__ segstart, cgrb_counts_t *counts)
+{
+    const int lane = threadIdx.x & 31;
+    const int ui = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ui >= n_units)
+        return;
+    const cgrb_unit_t *u = units + ui;
+    const double tstart = (WHICH == 0) ? u->src_tstart : u->bkg_tstart;
+    const double tstop = (WHICH == 0) ? u->src_tstop : u->bkg_tstop;
+    const int64_t b = unit_work_begin[ui], e = unit_work_begin[ui + 1];
+    double t = tstart;
+    for (int64_t s0 = b; s0 < e; s0 += 32) {
+        double v = (s0 + lane < e) ? segsum[s0 + lane] : 0.0;
+        double mine = 0.0;
+        for (int j = 0; j < 32; j++) {
+            double vj = __shfl_sync(0xffffffffu, v, j);
+            if (lane == j)
+                mine = t;
+            t = t + vj;     // same order on every lane
+        }
+        if (s0 + lane < e)
+            segstart[s0 + lane] = mine;
+    }
+    const uint32_t disabled = (WHICH == 0) ? (u->flags & CGRB_UNIT_NO_SOURCE) : (u->flags & CGRB_UNIT_NO_BACKGROUND);
+    if (lane == 0 && !disabled && !(t > tstop))
+        atomicOr(&counts[ui].status, (WHICH == 0) ? CGRB_ST_SRC_CAPACITY : CGRB_ST_BKG_CAPACITY);
+}
+
+// ==========================================================================================
+// source thinning pass 3 (cpl_functions.py:134-188): candidate time = segment start + stored running
+// sum, acceptance by the squeeze table or the exact lambda(t), ordered compaction of the accepted
+// times -- in place, into the head of the segment's own slots of `stage`.
+// ==========================================================================================
+// the exact test is rare under the squeeze table: kept out of line so the common path stays lean
+__device__ __noinline__ double lambda_exact(const LambdaTab *tab, const cgrb_unit_t &u, double t)
+{
+    return lambda_at(tab, u, t);
+}
+
+__device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_unit_t &u, bool squeeze,
+                                            const double2 *__restrict__ sq, double sq_inv_h, double t, double u2,
+                                            long long *n_exact)
+{
+    if (squeeze) {
+        const double q = (t - u.src_tstart) * sq_inv_h;
+        const int kq = min(max((int)q, 0), (int)u.tab_n - 2);       // tab_n < 2^31 (host: <= 65536 nodes)
+        const double fr = q - (double)kq;
+        const double2 n0 = __ldg(sq + kq), n1 = __ldg(sq + kq + 1);
+        const double pl = n0.x + (n1.x - n0.x) * fr;
+        if (u2 <= pl - n0.y)
+            return true;
+        if (u2 > pl + n0.y)
+            return false;
+    }
+    (*n_exact)++;
+    return u2 <= lambda_exact(tab, u, t) / u.fmax;   // `if test <= p_test`
+}
+
+__global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict__ dtab,
+                                                    const cgrb_unit_t *__restrict__ units,
+                                                    const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                    cgrb_rng_t rng, const double *__restrict__ segstart,
+                                                    int32_t *__restrict__ segcount, double *stage,
+                                                    double *__restrict__ cand_times,
+                                                    uint8_t *__restrict__ cand_accept,
+                                                    const double *__restrict__ thin_tab, cgrb_counts_t *counts)
+{
+    __shared__ LambdaTab tab;
+    __shared__ cgrb_unit_t u;
+    __shared__ int s_wi[NW];
+    __shared__ double s_t[NT];
+    __shared__ double s_last;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    if (threadIdx.x == 0)
+        u = units[wk.unit];
+    __syncthreads();
+    const double t0 = segstart[w];
+    if ((u.flags & CGRB_UNIT_NO_SOURCE) || t0 > u.src_tstop) {   // dead segment
+        if (threadIdx.x == 0)
+            segcount[w] = 0;
+        return;
+    }
+    build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
+    if (threadIdx.x == 0)
+        s_last = t0;
+    __syncthreads();
+
+    const int64_t n = min((int64_t)CGRB_SEG, u.src_cap - wk.start);
+    // squeeze table of p(t) = lambda(t)/fmax (cgrb_thin_tables): decides most candidates without
+    // evaluating lambda; the rest take the exact test, so decisions are those of the exact test
+    const bool squeeze = thin_tab != nullptr && u.tab_n >= 4;
+    const double2 *sq = reinterpret_cast<const double2 *>(thin_tab) + (squeeze ? u.tab_off : 0);
+    const double sq_inv_h = squeeze ? (double)(u.tab_n - 1) / (u.src_tstop - u.src_tstart) : 0.0;
+    double *seg = stage + u.src_off + wk.start;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long n_exact = 0;
+    int seg_n = 0;        // accepted so far in this segment
+    int n_valid_total = 0;
+    // the stored running sums of the NEXT tile are requested before this tile is processed, so their DRAM
+    // latency hides behind the acceptance tests
+    double nxt_a = (2 * threadIdx.x < n) ? seg[2 * threadIdx.x] : INFINITY;
+    double nxt_b = (2 * threadIdx.x + 1 < n) ? seg[2 * threadIdx.x + 1] : INFINITY;
+    for (int64_t base = 0; base < n; base += THIN_TILE) {
+        const int64_t j0 = base + 2 * threadIdx.x;
+        const bool in0 = j0 < n, in1 = j0 + 1 < n;
+        double ta = in0 ? t0 + nxt_a : INFINITY;
+        double tb = in1 ? t0 + nxt_b : INFINITY;
+        {
+            const int64_t jn = j0 + THIN_TILE;
+            nxt_a = (jn < n) ? seg[jn] : INFINITY;
+            nxt_b = (jn + 1 < n) ? seg[jn + 1] : INFINITY;
+        }
+        // enforce non-decreasing times across association orders (1-ulp inversions)
+        s_t[threadIdx.x] = in1 ? tb : ta;
+        __syncthreads();
+        const double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
+        ta = fmax(ta, left);
+        tb = fmax(tb, ta);
+        const bool va = in0 && (ta <= u.src_tstop);   // `if time > tstop: break`
+        const bool vb = in1 && (tb <= u.src_tstop);
+        bool aa = false, ab = false;
+        if (va) {
+            PairDraw d = pair_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, (wk.start + j0) >> 1, 1);
+            aa = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact);
+            if (vb)
+                ab = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact);
+        }
+        // ordered compaction: per-thread counts (0..2 accepted, 0..2 valid) packed in one int
+        const int mine = (int)aa + (int)ab + (((int)va + (int)vb) << 16);
+        int incl = warp_incl_scan_i(mine, lane);
+        if (lane == 31)
+            s_wi[wid] = incl;
+        __syncthreads();            // also: every read of this tile's slots is done before any write below
+        int before = 0, tile_tot = 0;
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            const int c = s_wi[q];
+            if (q < wid)
+                before += c;
+            tile_tot += c;
+        }
+        const int rank = ((before + incl - mine) & 0xffff) + seg_n;
+        if (aa)
+            seg[rank] = ta;
+        if (ab)
+            seg[rank + (int)aa] = tb;
+        if (cand_times) {
+            if (va) {
+                cand_times[u.src_off + wk.start + j0] = ta;
+                cand_accept[u.src_off + wk.start + j0] = aa ? 1 : 0;
+            }
+            if (vb) {
+                cand_times[u.src_off + wk.start + j0 + 1] = tb;
+                cand_accept[u.src_off + wk.start + j0 + 1] = ab ? 1 : 0;
+            }
+        }
+        const int tile_acc = tile_tot & 0xffff, tile_valid = tile_tot >> 16;
+        seg_n += tile_acc;
+        n_valid_total += tile_valid;
+        if (threadIdx.x == NT - 1)
+            s_last = in1 ? tb : ta;
+        __syncthreads();
+        if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
+            break;      // crossed tstop: everything later is beyond it
+    }
+    {
+        long long *s_ll = reinterpret_cast<long long *>(s_t);      // s_t is free now
+        __syncthreads();
+        const long long tot_exact = block_sum_ll(n_exact, s_ll);
+        if (threadIdx.x == 0) {
+            segcount[w] = seg_n;
+            if (n_valid_total)
+                atomicAdd((unsigned long long *)&counts[wk.unit].n_candidates, (unsigned long long)n_valid_total);
+            if (tot_exact)
+                atomicAdd((unsigned long long *)&counts[wk.unit].n_exact, (unsigned long long)tot_exact);
+        }
+    }
+}
+
+// pass 5: gather the per-segment accepted times into the unit's contiguous list; entry 0 is the
+// spurious tstart event of cpl_functions.py:153-154.
+__global__ void __launch_bounds__(NT) k_source_gather(const cgrb_unit_t *__restrict__ units,
+                                                      const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                      const int64_t *__restrict__ unit_work_begin,
+                                                      const int32_t *__restrict__ segcount,
+                                                      const double *__restrict__ stage,
+                                                      double *__restrict__ times_src, cgrb_counts_t *counts)
+{
+    __shared__ long long s_w[NW];
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int64_t b = unit_work_begin[wk.unit], e = unit_work_begin[wk.unit + 1];
+    long long part = 0;
+    for (int64_t s = b + threadIdx.x; s < w; s += NT)
+        part += segcount[s];
+    const long long off = block_sum_ll(part, s_w);
+    const int cnt = segcount[w];
+    const double *src = stage + u->src_off + wk.start;
+    double *dst = times_src + u->src_off + 1 + off;
+    for (int j = threadIdx.x; j < cnt; j += NT)
+        dst[j] = src[j];
+    if (threadIdx.x == 0) {
+        if (w == b)
+            times_src[u->src_off] = u->src_tstart;
+        if (w == e - 1)
+            counts[wk.unit].n_src = (u->flags & CGRB_UNIT_NO_SOURCE) ? 0 : 1 + off + cnt;
+    }
+}
+
+// ==========================================================================================
+// background (background.py:13-44 + numpy choice :93): every candidate is an event; event j of
+// the unit is candidate j-1, event 0 is the spurious tstart event.  Pass 1 (k_gap_prefix<1>) left
+// each candidate's running gap sum in its time slot; this pass adds the segment start, draws the
+// channel from the template's cdf and cuts the list at tstop.
+// ==========================================================================================
+__global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dtab,
+                                                   const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   cgrb_rng_t rng, cgrb_rng_t rng_chan,
+                                                   const double *__restrict__ segstart,
+                                                   double *times_bkg, uint8_t *__restrict__ pha_bkg,
+                                                   cgrb_counts_t *counts)
+{
+    __shared__ double s_cdf[CGRB_NCHAN];
+    __shared__ unsigned char s_cg[CGRB_NCHAN];      // guide: searchsorted(cdf, m/128, 'right')
+    __shared__ int s_wi[NW];
+    __shared__ double s_t[NT];
+    __shared__ double s_last;
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    if (u->flags & CGRB_UNIT_NO_BACKGROUND)
+        return;
+    const double t0 = segstart[w];
+    const double tstop = u->bkg_tstop;
+    const int64_t off = u->bkg_off;
+    const uint32_t sid = u->stream_id;
+    const double *cdf_g = dtab + (size_t)u->det * CGRB_DT_SIZE + CGRB_DT_BKG_CDF;
+    if (threadIdx.x < CGRB_NCHAN)
+        s_cdf[threadIdx.x] = cdf_g[threadIdx.x];
+    if (threadIdx.x == 0)
+        s_last = t0;
+    __syncthreads();
+    if (threadIdx.x < CGRB_NCHAN)
+        s_cg[threadIdx.x] = (unsigned char)min(searchsorted_right(s_cdf, CGRB_NCHAN, (double)threadIdx.x / CGRB_NCHAN),
+                                               CGRB_NCHAN - 1);
+    __syncthreads();
+    // np.searchsorted(cdf, u, 'right') clamped to the last channel, started from the guide: ~2 probes
+    auto channel_of = [&](double uc) -> uint8_t {
+        int j = s_cg[min(max((int)(uc * (double)CGRB_NCHAN), 0), CGRB_NCHAN - 1)];
+        while (j < CGRB_NCHAN - 1 && !(uc < s_cdf[j]))
+            j++;
+        return (uint8_t)j;
+    };
+
+    if (wk.start == 0 && threadIdx.x == 0) {
+        // event 0: tstart, with its own channel draw (sample_channel(size=len(times)))
+        double uc;
+        if (rng.mode == 0) {
+            Philox4 p = philox_at(make_key(rng.seed), sid, ST_BKG, 0xFFFFFFFFFFull, 1u);
+            uc = u53(p.x, p.y);
+        } else {
+            int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
+            uc = rng_chan.d_u[o];
+        }
+        times_bkg[off] = u->bkg_tstart;
+        pha_bkg[off] = channel_of(uc);
+        atomicAdd((unsigned long long *)&counts[wk.unit].n_bkg, 1ull);
+    }
+    if (t0 > tstop)
+        return;
+
+    const int64_t n = min((int64_t)CGRB_SEG, u->bkg_cap - wk.start);
+    double *seg_t = times_bkg + off + 1 + wk.start;
+    uint8_t *seg_p = pha_bkg + off + 1 + wk.start;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int n_valid_total = 0;
+    bool exhausted = false;
+    for (int64_t base = 0; base < n; base += THIN_TILE) {
+        const int64_t j0 = base + 2 * threadIdx.x;
+        const bool in0 = j0 < n, in1 = j0 + 1 < n;
+        double ta = in0 ? t0 + seg_t[j0] : INFINITY;
+        double tb = in1 ? t0 + seg_t[j0 + 1] : INFINITY;
+        s_t[threadIdx.x] = in1 ? tb : ta;
+        __syncthreads();
+        const double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
+        ta = fmax(ta, left);
+        tb = fmax(tb, ta);
+        const bool va = in0 && (ta <= tstop);
+        const bool vb = in1 && (tb <= tstop);
+        if (va) {
+            double ua, ub = 0.5;
+            if (rng.mode == 0) {
+                PairDraw d = pair_draw(rng, wk.unit, sid, ST_BKG, (wk.start + j0) >> 1, 1);
+                ua = d.a;
+                ub = d.b;
+            } else {
+                const int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
+                const int64_t len = rng_chan.d_len ? rng_chan.d_len[wk.unit] : ((int64_t)1 << 62);
+                const int64_t e0 = wk.start + j0 + 1;           // event index of candidate j0
+                ua = 0.5;
+                if (e0 < len)
+                    ua = rng_chan.d_u[o + e0];
+                else
+                    exhausted = true;
+                if (vb) {
+                    if (e0 + 1 < len)
+                        ub = rng_chan.d_u[o + e0 + 1];
+                    else
+                        exhausted = true;
+                }
+            }
+            seg_t[j0] = ta;
+            seg_p[j0] = channel_of(ua);
+            if (vb) {
+                seg_t[j0 + 1] = tb;
+                seg_p[j0 + 1] = channel_of(ub);
+            }
+        }
+        const unsigned bala = __ballot_sync(0xffffffffu, va), balb = __ballot_sync(0xffffffffu, vb);
+        if (lane == 0)
+            s_wi[wid] = __popc(bala) + __popc(balb);
+        __syncthreads();
+        int tile_valid = 0;
+#pragma unroll
+        for (int q = 0; q < NW; q++)
+            tile_valid += s_wi[q];
+        n_valid_total += tile_valid;
+        if (threadIdx.x == NT - 1)
+            s_last = in1 ? tb : ta;
+        __syncthreads();
+        if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
+            break;
+    }
+    if (threadIdx.x == 0 && n_valid_total)
+        atomicAdd((unsigned long long *)&counts[wk.unit].n_bkg, (unsigned long long)n_valid_total);
+    if (exhausted)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
+}
+
