@@ -211,3 +211,32 @@ def test_gather_event_counts_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_capacity_saturates_instead_of_wrapping():
+    """fmax x duration of a runaway unit (1e19 candidates, inf, nan) must not wrap around in the integer cast:
+    it saturates and the engine then refuses the unit"""
+    from cosmogrb_b200.engine import CAPACITY_MAX, capacity
+
+    c = capacity(np.array([0.0, 500.0, 1e19, np.inf, np.nan, -3.0]), 30.0)
+    assert c[0] == 64 and c[5] == 64
+    assert 15000 + 8 * np.sqrt(15000) <= c[1] <= 15000 + 8 * np.sqrt(15000) + 66
+    assert np.all(c[2:5] == CAPACITY_MAX)
+    assert np.all(c >= 0)
+
+
+def test_pipeline_chunks_cover_every_unit_once():
+    """process_batch cuts a large call into chunks of detectors (device->host copy of one chunk overlaps the
+    kernels of the next); every unit appears exactly once, in order, and small calls stay in one piece"""
+    from cosmogrb_b200 import _capi
+    from cosmogrb_b200.lightcurve import lightcurve as lcmod
+
+    u = np.zeros(14, dtype=_capi.UNIT_DTYPE)
+    u["src_tstop"], u["bkg_tstart"], u["bkg_tstop"], u["bkg_rate"] = 300.0, -100.0, 300.0, 500.0
+    u["fmax"] = 3.6e4                                  # ~1.1e7 candidates per detector: the bright burst
+    chunks = lcmod._chunks(u, None)
+    assert len(chunks) >= 4
+    assert np.array_equal(np.concatenate(chunks), np.arange(14))
+    u["fmax"] = 100.0                                  # the README burst: one batch
+    assert len(lcmod._chunks(u, None)) == 1
+    assert len(lcmod._chunks(u[:1], None)) == 1
