@@ -148,3 +148,39 @@ def test_light_curve_and_count_spectrum_against_oracle(engine):
     assert stats.chi2.sf(chi2, ok.sum() - 1) > P_MIN
     gaps = np.diff(b.view("times_bkg", 1, "bkg")[1:])
     assert stats.kstest(gaps, "expon", args=(0, 1.0 / 500.0)).pvalue > P_MIN
+
+
+def test_envelope_sampler_population_sweep(engine):
+    """Random bursts of the synthetic population (soft and hard spectra, NaI and BGO detectors), photons at
+    early / middle / late times: the tabulated-envelope sampler agrees with the literal one (two-sample KS,
+    Bonferroni-corrected) and its envelope dominates the target everywhere (the kernel's self-check raises
+    CGRB_ST_ENVELOPE otherwise)."""
+    from cosmogrb_b200.universe import synthetic_population
+
+    pop = synthetic_population(400, seed=4321)
+    rs = np.random.RandomState(5)
+    cases, pvals = 0, []
+    for i in rs.permutation(400):
+        if cases >= 24:
+            break
+        params = dict(z=pop.distances[i], peak_flux=max(pop.fluxes.latent[i], 1e-7), alpha=pop.alpha[i],
+                      ep_start=pop.ep[i], ep_tau=pop.tau[i], trise=pop.trise[i], tdecay=pop.tdecay[i],
+                      duration=pop.duration[i])
+        det = ("n0", "n5", "b0", "b1")[cases % 4]
+        for frac in (0.05, 0.4, 0.95):
+            t0 = frac * params["duration"]
+            # skip regimes where the literal sampler itself needs > 2e4 trials per photon (it would hit its cap;
+            # the reference would take minutes per photon there)
+            e_lit, tr_lit = _energies(engine, params, np.full(64, t0), "literal", 900 + cases, det=det)
+            if tr_lit.mean() > 2e4 or not np.all(np.isfinite(e_lit)):
+                continue
+            n = 4000
+            e_lit, _ = _energies(engine, params, np.full(n, t0), "literal", 1000 + cases, det=det)
+            e_env, tr_env = _energies(engine, params, np.full(n, t0), "envelope", 2000 + cases, det=det)
+            assert np.all(np.isfinite(e_env))
+            pvals.append(stats.ks_2samp(e_lit, e_env).pvalue)
+        cases += 1
+    assert len(pvals) >= 30
+    assert min(pvals) > P_MIN / len(pvals), f"min p = {min(pvals)} over {len(pvals)} comparisons"
+    # and the p-values are not piled up near zero
+    assert np.mean(np.array(pvals) < 0.1) < 0.3
