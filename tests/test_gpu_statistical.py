@@ -184,3 +184,37 @@ def test_envelope_sampler_population_sweep(engine):
     assert min(pvals) > P_MIN / len(pvals), f"min p = {min(pvals)} over {len(pvals)} comparisons"
     # and the p-values are not piled up near zero
     assert np.mean(np.array(pvals) < 0.1) < 0.3
+
+
+def test_c3_background_only_interval(engine):
+    """BASELINE.json configs[2]: background-dominated 1000 s interval, all 14 detectors, source disabled.
+    Per detector: Poisson-consistent counts, uniform arrival times, exponential gaps, template channel spectrum;
+    the total list is the dead-time filtered background list (oracle's literal filter, bit for bit)."""
+    dets = h.GBM_DETECTORS
+    tabs = [h.response(d).device_table(h.bkg_weights(d), "linear") for d in dets]
+    p = dict(h.README_DEMO, peak_flux=5e-20)
+    units = np.concatenate([h.unit(det_index=i, stream_id=300 + i, flags=_capi.UNIT_NO_SOURCE,
+                                   bkg=(0.0, 1000.0, 500.0), **p) for i in range(len(dets))])
+    b = engine.new_batch(units, tabs)
+    engine.process(b, Philox(777))
+    c = engine.fetch_counts(b)
+    engine.check_status(b)
+    assert np.all(c["n_src"] == 0) and np.all(c["n_total"] == c["n_bkg"])
+    n = c["n_bkg"].astype("f8") - 1            # minus the spurious tstart event
+    assert np.all(np.abs(n - 5e5) < 6 * np.sqrt(5e5))
+    assert abs(n.sum() - 14 * 5e5) < 5 * np.sqrt(14 * 5e5)
+    for i in (0, 6, 13):
+        tb = b.view("times_bkg", i, "bkg")
+        pb = b.view("pha_bkg", i, "bkg")
+        assert tb[0] == 0.0 and np.all(np.diff(tb) >= 0) and tb[-1] <= 1000.0
+        assert stats.kstest(tb[1:] / 1000.0, "uniform").pvalue > P_MIN / 3
+        assert stats.kstest(np.diff(tb[1:]), "expon", args=(0, 1.0 / 500.0)).pvalue > P_MIN / 3
+        w = h.bkg_weights(dets[i]).astype("f8")
+        obs = np.bincount(pb.astype(int), minlength=128)
+        exp = w / w.sum() * obs.sum()
+        ok = exp >= 10
+        assert stats.chi2.sf(((obs[ok] - exp[ok]) ** 2 / exp[ok]).sum(), ok.sum() - 1) > P_MIN / 3
+        sel = orc.gbm_dead_time(tb, pb.astype("f8"))
+        assert np.array_equal(b.view("times_out", i, "kept"), tb[sel])
+        assert np.array_equal(b.view("pha_out", i, "kept"), pb[sel])
+        assert 0 < (~sel).sum() < 0.01 * len(tb)
