@@ -196,3 +196,26 @@ def test_runaway_unit_is_refused_and_skipped(engine):
     uni.go(seed=3, save=False)
     assert uni.skipped == [1]
     assert np.all(uni.event_counts[1] == -1) and np.all(uni.event_counts[[0, 2], :, 1] > 1.8e5)
+
+
+def test_c1_readme_demo(engine):
+    """BASELINE.json configs[0]: the README burst through GBMGRB_CPL(...).go().  Per detector the number of
+    source events is Poisson around the integral of lambda(t) (oracle, trapezoid on a fine grid) and the
+    background fills [-100, 300] s at ~500 Hz."""
+    from cosmogrb_b200 import gbm
+
+    g = gbm.GBMGRB_CPL(ra=312.0, dec=-62.0, z=1.0, peak_flux=5e-7, alpha=-0.66, ep_start=500.0, ep_tau=2.0,
+                       trise=1.0, tdecay=1.0, duration=80.0, T0=0.1, n_cores=6)     # unknown kwargs are dropped
+    g.go(seed=31)
+    tg = np.linspace(0.0, 80.0, 4001)
+    for name in ("n0", "n3", "n9", "b0"):
+        lc = g.lightcurves[name]
+        rsp = lc.response
+        s = h.oracle_source(rsp, **h.README_DEMO)
+        lam = orc.energy_integrated_evolution(s, rsp.effective_area_packed, tg)
+        mean = np.trapezoid(lam, tg)
+        st = lc.lightcurve_storage
+        n_src = st.n_counts_source - 1
+        assert abs(n_src - mean) < 5.0 * np.sqrt(mean) + 5.0, (name, n_src, mean)
+        assert st.times_source[-1] <= 80.0 and st.times_background[0] == -100.0
+        assert abs(st.n_counts_background - 2e5) < 6 * np.sqrt(2e5) + 40 * 400
