@@ -172,3 +172,56 @@ __device__ __forceinline__ double lambda_at(const LambdaTab *tab, const cgrb_uni
     return s.norm * exp(-u.alpha * s.log_ec) * acc;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Decoupled look-back (one warp): exclusive prefix of integer counts over the work items [wb, w) of a
+// unit.  Every item publishes (flag, count) in one 64-bit word: AGG = its own count, INC = the inclusive
+// prefix up to and including it; the first item of a unit publishes INC at once.  A warp looks at 256
+// predecessors per round (8 loads in flight per lane): hundreds of CTAs run concurrently, so the nearest
+// inclusive prefix is typically that far back.  Integer sums: the result does not depend on timing.
+// The state array must be zeroed before the launch.  Call with all 32 lanes of one warp.
+// ------------------------------------------------------------------------------------------
+#define LB_FLAG_AGG (1ull << 62)
+#define LB_FLAG_INC (2ull << 62)
+#define LB_VALUE_MASK ((1ull << 62) - 1ull)
+
+__device__ __forceinline__ long long lookback_exclusive(unsigned long long *state, int64_t w, int64_t wb,
+                                                        long long count, int lane)
+{
+    if (lane == 0)
+        atomicExch(state + w, (unsigned long long)count | (w == wb ? LB_FLAG_INC : LB_FLAG_AGG));
+    long long excl = 0;
+    if (w > wb) {
+        int64_t idx = w - 1;
+        bool done = false;
+        while (!done) {
+            unsigned long long st[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int64_t my = idx - 32 * q - lane;
+                st[q] = (my >= wb) ? *((volatile unsigned long long *)(state + my)) : LB_FLAG_INC;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (done)
+                    break;
+                const int64_t my = idx - 32 * q - lane;
+                while ((st[q] >> 62) == 0ull)
+                    st[q] = *((volatile unsigned long long *)(state + my));
+                const unsigned inc = __ballot_sync(0xffffffffu, (st[q] >> 62) == 2ull);
+                const int first_inc = inc ? (__ffs(inc) - 1) : 32;      // nearest item with an inclusive prefix
+                long long v = (lane <= first_inc && my >= wb) ? (long long)(st[q] & LB_VALUE_MASK) : 0;
+#pragma unroll
+                for (int dlt = 16; dlt > 0; dlt >>= 1)
+                    v += __shfl_xor_sync(0xffffffffu, v, dlt);
+                excl += v;
+                if (inc)
+                    done = true;
+            }
+            idx -= 256;
+        }
+        if (lane == 0)
+            atomicExch(state + w, (unsigned long long)(excl + count) | LB_FLAG_INC);
+    }
+    return excl;
+}

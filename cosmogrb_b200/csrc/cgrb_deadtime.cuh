@@ -244,9 +244,6 @@ __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__rest
 #define MD_TILE 2048
 #define MD_HALO 256
 #define MD_N (MD_TILE + MD_HALO)
-#define MD_FLAG_AGG (1ull << 62)
-#define MD_FLAG_INC (2ull << 62)
-#define MD_VALUE_MASK ((1ull << 62) - 1ull)
 
 // merge-path split of diagonal d: number of background events among the first d merged events
 __device__ __forceinline__ int64_t merge_split(const double *__restrict__ A, int64_t nA, const double *__restrict__ B,
@@ -534,45 +531,7 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
         const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
         s_cnt[2 * lane] = incl - c0 - c1;
         s_cnt[2 * lane + 1] = incl - c1;
-        if (lane == 0) {
-            const unsigned long long mine = (unsigned long long)cnt_tile | (w == wb ? MD_FLAG_INC : MD_FLAG_AGG);
-            atomicExch(tile_state + w, mine);
-        }
-        long long excl = 0;
-        if (w > wb) {
-            // 256 predecessors per round (8 loads in flight per lane): hundreds of tiles run concurrently, so
-            // the nearest tile with an inclusive prefix is typically that far back
-            int64_t idx = w - 1;
-            bool done = false;
-            while (!done) {
-                unsigned long long st[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int64_t my = idx - 32 * q - lane;
-                    st[q] = (my >= wb) ? *((volatile unsigned long long *)(tile_state + my)) : MD_FLAG_INC;
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    if (done)
-                        break;
-                    const int64_t my = idx - 32 * q - lane;
-                    while ((st[q] >> 62) == 0ull)
-                        st[q] = *((volatile unsigned long long *)(tile_state + my));
-                    const unsigned inc = __ballot_sync(0xffffffffu, (st[q] >> 62) == 2ull);
-                    const int first_inc = inc ? (__ffs(inc) - 1) : 32;     // nearest tile with an inclusive prefix
-                    long long v = (lane <= first_inc && my >= wb) ? (long long)(st[q] & MD_VALUE_MASK) : 0;
-#pragma unroll
-                    for (int dlt = 16; dlt > 0; dlt >>= 1)
-                        v += __shfl_xor_sync(0xffffffffu, v, dlt);
-                    excl += v;
-                    if (inc)
-                        done = true;
-                }
-                idx -= 256;
-            }
-            if (lane == 0)
-                atomicExch(tile_state + w, (unsigned long long)(excl + cnt_tile) | MD_FLAG_INC);
-        }
+        const long long excl = lookback_exclusive(tile_state, w, wb, cnt_tile, lane);
         if (lane == 0) {
             s_excl = excl;
             if (w == wb)
