@@ -81,10 +81,39 @@ class _GBMBatchedUniverse(Universe):
         t_ = time.perf_counter
         eng = get_engine()
         rank, world = dist_info()
-        mine = shard_by_cost(self.cost_estimate(), world)[rank]
         tabs = self.base_tables(eng.interp_extrap)
         dtab = eng.upload_tables(tabs)
         seed = eng.seed if seed is None else seed
+
+        def fmax_and_sizes(grbs):
+            """fmax of every unit of the bursts ``grbs`` (one launch per 4096 bursts) and the bytes of event
+            buffers each burst needs"""
+            fm = np.zeros((len(grbs), N_DET))
+            sz = np.zeros(len(grbs))
+            for p0 in range(0, len(grbs), 4096):
+                idx = grbs[p0:p0 + 4096]
+                units, _ = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
+                f = eng.fmax(units, dtab)
+                fm[p0:p0 + len(idx)] = f.reshape(-1, N_DET)
+                slots = (capacity(f, units["src_tstop"] - units["src_tstart"]).astype("f8")
+                         + capacity(units["bkg_rate"], units["bkg_tstop"] - units["bkg_tstart"]) + 2)
+                sz[p0:p0 + len(idx)] = slots.reshape(-1, N_DET).sum(axis=1) * BYTES_PER_SLOT
+            return fm, sz
+
+        t0 = t_()
+        if world > 1:
+            # every rank sizes every burst (a few ms per thousand bursts) so that the LPT deal sees the real cost:
+            # burst costs are heavy-tailed in ways the flux alone does not predict.  Bursts that will be skipped
+            # cost nothing.
+            fm_g, sz_g = fmax_and_sizes(np.arange(self._n_grbs))
+            cost = np.where((sz_g > memory_budget) | ~np.isfinite(sz_g), 0.0, sz_g)
+            self._shards = shard_by_cost(cost, world)
+            mine = self._shards[rank]
+            fmax_all, sizes = fm_g[mine], sz_g[mine]
+        else:
+            self._shards = [np.arange(self._n_grbs)]
+            mine = self._shards[0]
+            fmax_all, sizes = fmax_and_sizes(mine)
         local_counts = np.zeros((len(mine), N_DET, 3), dtype=np.int64)
         pinned = {}
         self.n_batches = 0
@@ -95,18 +124,6 @@ class _GBMBatchedUniverse(Universe):
             chan_bounds = np.stack([channel_bounds(base_response(d).channel_edges) for d in GBM_DETECTORS])
             local_trig = np.zeros((len(mine), N_DET), dtype=_capi.TRIGGER_DTYPE)
             local_det = np.zeros(len(mine), dtype=bool)
-        # fmax of every local unit (one launch per 4096 GRBs), then per-GRB buffer sizes
-        sizes = np.zeros(len(mine))
-        fmax_all = np.zeros((len(mine), N_DET))
-        t0 = t_()
-        for p0 in range(0, len(mine), 4096):
-            idx = mine[p0:p0 + 4096]
-            units, _ = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
-            f = eng.fmax(units, dtab)
-            fmax_all[p0:p0 + len(idx)] = f.reshape(-1, N_DET)
-            slots = (capacity(f, units["src_tstop"] - units["src_tstart"]).astype("f8")
-                     + capacity(units["bkg_rate"], units["bkg_tstop"] - units["bkg_tstart"]) + 2)
-            sizes[p0:p0 + len(idx)] = slots.reshape(-1, N_DET).sum(axis=1) * BYTES_PER_SLOT
         tm["fmax_pass"] = t_() - t0
         too_big = (sizes > memory_budget) | ~np.isfinite(sizes)
         for j in np.nonzero(too_big)[0]:
@@ -180,7 +197,7 @@ class _GBMBatchedUniverse(Universe):
         t0 = t_()
         gathered = gather_event_counts(local_counts.reshape(-1, 3))
         tm["gather"] = t_() - t0
-        shards = shard_by_cost(self.cost_estimate(), world)
+        shards = self._shards
         full = np.zeros((self._n_grbs, N_DET, 3), dtype=np.int64)
         for r in range(world):
             full[shards[r]] = gathered[r].reshape(-1, N_DET, 3)
