@@ -12,7 +12,6 @@ if ROOT not in sys.path:
 from cosmogrb_b200 import _capi  # noqa: E402
 from cosmogrb_b200.instruments.gbm.synthetic_response import (  # noqa: E402
     GBM_DETECTORS, BGOResponse, NaIResponse, gbm_tables)
-from oracle import oracle as orc  # noqa: E402
 
 README_DEMO = dict(z=1.0, peak_flux=5e-7, alpha=-0.66, ep_start=500.0, ep_tau=2.0, trise=1.0, tdecay=1.0,
                    duration=80.0)
@@ -47,6 +46,8 @@ def unit(kind=0, det_index=0, stream_id=0, flags=0, bkg=(-100.0, 300.0, 500.0), 
 
 
 def oracle_source(rsp, kind=0, interp_extrap="linear", **p):
+    from oracle import oracle as orc      # lazy: bench.py's GPU arm imports this module without touching oracle/
+
     return orc.source(kind=kind, interp_extrap=interp_extrap, peak_flux=p["peak_flux"],
                       ep_start=p.get("ep", p.get("ep_start")), ep_tau=p.get("ep_tau", 1.0), alpha=p["alpha"],
                       trise=p.get("trise", 1.0), tdecay=p.get("tdecay", 1.0), z=p["z"], emin=rsp.emin,
