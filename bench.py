@@ -436,9 +436,10 @@ def run_gpu(args):
         from cosmogrb_b200.instruments.gbm.gbm_universe import GBM_CPL_Universe
         from cosmogrb_b200.universe import synthetic_population
 
-        # warm-up pass of the same size (another population): first-touch costs -- cudaMalloc of the batch
-        # buffers by torch's caching allocator, NCCL's first collective -- are not part of the steady state
-        warm = GBM_CPL_Universe(synthetic_population(args.population * world, seed=99), save_path=None)
+        # warm-up pass on the same population: the steady state of a long run, where the pooled event buffers
+        # have reached their final sizes and NCCL has been through its first collective (first-touch costs --
+        # cudaMalloc of tens of GB by the caching allocator -- took between 5 and 260 ms in otherwise identical runs)
+        warm = GBM_CPL_Universe(synthetic_population(args.population * world, seed=12345), save_path=None)
         warm.go(save=False, seed=seed, trigger=True)
         del warm
         uni = GBM_CPL_Universe(synthetic_population(args.population * world, seed=12345), save_path=None)
