@@ -218,3 +218,39 @@ def test_c3_background_only_interval(engine):
         assert np.array_equal(b.view("times_out", i, "kept"), tb[sel])
         assert np.array_equal(b.view("pha_out", i, "kept"), pb[sel])
         assert 0 < (~sel).sum() < 0.01 * len(tb)
+
+
+def test_c2_bright_burst_counts_follow_lambda(engine):
+    """BASELINE.json configs[1] at full size (1.08e8 events): per detector the number of source events is Poisson
+    around the integral of lambda(t) (7.5e6 +- 2.7e3: a 4e-4 relative test of the thinning, squeeze table
+    included), the binned light curve follows lambda(t) (chi-square over 150 bins) and the thinning acceptance
+    matches the mean of lambda / fmax."""
+    dets = h.GBM_DETECTORS
+    p = h.BRIGHT_LONG
+    tabs = [h.response(d).device_table(h.bkg_weights(d), "linear") for d in dets]
+    units = np.concatenate([h.unit(det_index=i, stream_id=40 + i, **p) for i in range(len(dets))])
+    b = engine.new_batch(units, tabs)
+    engine.process(b, Philox(20261020))
+    c = engine.fetch_counts(b)
+    engine.check_status(b)
+    tg = np.linspace(0.0, p["duration"], 6001)
+    edges = np.linspace(0.0, p["duration"], 151)
+    for i in (0, 5, 12):
+        rsp = h.response(dets[i])
+        s = h.oracle_source(rsp, **p)
+        lam = orc.energy_integrated_evolution(s, rsp.effective_area_packed, tg)
+        mean = np.trapezoid(lam, tg)
+        n_src = int(c["n_src"][i]) - 1
+        assert abs(n_src - mean) < 5.0 * np.sqrt(mean) + 1e-5 * mean, (dets[i], n_src, mean)
+        # acceptance: accepted / candidates == mean(lambda) / fmax
+        fmax = float(b.units["fmax"][i])
+        acc = n_src / float(c["n_candidates"][i])
+        assert abs(acc - mean / (fmax * p["duration"])) < 5.0 * np.sqrt(acc * (1 - acc) / float(c["n_candidates"][i])) + 1e-5
+        # light curve
+        ts = b.view("times_src", i, "src")[1:]
+        obs, _ = np.histogram(ts, edges)
+        cum = np.concatenate(([0.0], np.cumsum(0.5 * (lam[1:] + lam[:-1]) * np.diff(tg))))
+        exp = np.diff(np.interp(edges, tg, cum))
+        ok = exp >= 20
+        chi2 = ((obs[ok] - exp[ok]) ** 2 / exp[ok]).sum()
+        assert stats.chi2.sf(chi2, ok.sum()) > P_MIN / 3, (dets[i], chi2, ok.sum())
