@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NBINS = 140
 NCHAN = 128
 NE_LAMBDA = 75
@@ -46,6 +46,7 @@ ST_UNIFORMS_EXHAUSTED = 4
 ST_TRIAL_CAP = 8
 ST_OUT_CAPACITY = 16
 ST_ENVELOPE = 32
+ST_DEADTIME_CHAIN = 64
 
 UNIT_NO_SOURCE = 1
 UNIT_NO_BACKGROUND = 2
@@ -91,6 +92,15 @@ assert WORK_DTYPE.itemsize == 16
 class TriggerPar(C.Structure):
     _fields_ = [("threshold", C.c_double), ("base_timescale", C.c_double), ("background_duration", C.c_double),
                 ("pre_window", C.c_double)]
+
+
+DEADTIME_REFERENCE = 0
+DEADTIME_PHYSICAL = 1
+
+
+class DeadtimeModel(C.Structure):
+    """cgrb_deadtime_model_t"""
+    _fields_ = [("mode", C.c_int32), ("pad", C.c_int32), ("tau", C.c_double), ("tau_overflow", C.c_double)]
 
 
 class RngDesc(C.Structure):
@@ -170,10 +180,11 @@ def load():
     lib.cgrb_sample_background.argtypes = [vp, vp, i32, vp, i64, vp, rp, rp, vp, vp, vp, vp, vp, vp]
     lib.cgrb_background_channels.argtypes = [vp, i32, C.c_uint32, rp, i64, vp, vp]
     lib.cgrb_combine.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
-    lib.cgrb_gbm_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    dp = C.POINTER(DeadtimeModel)
+    lib.cgrb_gbm_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, dp, vp]
     lib.cgrb_merge_dead_time_workspace_bytes.argtypes = [i64]
     lib.cgrb_merge_dead_time_workspace_bytes.restype = i64
-    lib.cgrb_merge_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_merge_dead_time.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, dp, vp]
     lib.cgrb_gbm_trigger_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_gbm_trigger_workspace_bytes.restype = i64
     lib.cgrb_gbm_trigger.argtypes = [vp, i32, vp, i64, vp, C.POINTER(TriggerPar), vp, vp, vp, i64, vp, vp, vp]

@@ -43,6 +43,12 @@ _DEFAULTS = {
         "energy_sampler": "envelope",
         # upper bound on CPL rejection trials per photon
         "max_trials": 1 << 22,
+        # GBM dead time: "reference" (literal _gbm_dead_time, gbm_lightcurve.py:80-115) | "physical"
+        # (non-paralyzable: every kept event opens a window of deadtime_tau, or deadtime_tau_overflow for
+        # the overflow channel)
+        "deadtime_mode": "reference",
+        "deadtime_tau": 2.6e-6,
+        "deadtime_tau_overflow": 10e-6,
     },
 }
 

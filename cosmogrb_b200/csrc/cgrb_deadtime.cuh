@@ -151,12 +151,89 @@ __device__ __forceinline__ bool dt_keep(const double *__restrict__ t, const uint
     return ti > t_end;
 }
 
+// ==========================================================================================
+// GBM dead time, physical (non-paralyzable) model -- SURVEY.md §8 f4; NOT what the reference computes.
+//   event 0 is kept; every KEPT event opens a window (tau_overflow if pha == 127, else tau) and an
+//   event is kept iff t > t_end of the last kept event.
+// The chain runs through every kept event, but it re-synchronises at any event that follows its
+// predecessor by more than the longest window: fl(t[s-1] + tau_max) >= any t_end set before s (rounding is
+// monotonic), so such an event is certainly kept.  Each event walks back to the nearest synchronisation
+// point and replays the serial rule from there (exact for any input; runs are short because the mean gap
+// is many windows long).  A walk longer than DT_PHYS_MAX_WALK events (event rate x longest window >~ 5: far
+// beyond anything GBM records) is refused with the unit's CGRB_ST_DEADTIME_CHAIN status bit instead of
+// running for O(n^2).
+// ==========================================================================================
+#define DT_PHYS_MAX_WALK 4096
+struct DtModel {
+    double tau, tau_ovf, tau_max;
+};
+
+struct EventArrays {
+    const double *t;
+    const uint8_t *p;
+    __device__ __forceinline__ void get(int64_t j, double *tt, uint8_t *pp) const
+    {
+        *tt = t[j];
+        *pp = p[j];
+    }
+};
+
+// keep flag of event i on accessor `m`, whose lowest readable index is 0; `has0` tells whether index 0 is
+// the unit's event 0.  Returns 0 / 1, or 2 if the walk would leave the readable range or exceed
+// DT_PHYS_MAX_WALK events.
+template <class Acc>
+__device__ __forceinline__ int dt_keep_phys(const Acc &m, int64_t i, bool has0, const DtModel md)
+{
+    double ts, tp;
+    uint8_t ps, pp;
+    m.get(i, &ts, &ps);
+    int64_t s = i;
+    for (;;) {
+        if (s == 0) {
+            if (!has0)
+                return 2;
+            break;
+        }
+        if (i - s >= DT_PHYS_MAX_WALK)
+            return 2;
+        m.get(s - 1, &tp, &pp);
+        if (ts > tp + md.tau_max)
+            break;                          // s is a synchronisation point: certainly kept
+        s--;
+        ts = tp;
+        ps = pp;
+    }
+    if (s == i)
+        return 1;
+    double t_end = ts + (ps == 127 ? md.tau_ovf : md.tau);
+    bool kept = true;
+    for (int64_t j = s + 1; j <= i; j++) {
+        m.get(j, &tp, &pp);
+        kept = tp > t_end;
+        if (kept)
+            t_end = tp + (pp == 127 ? md.tau_ovf : md.tau);
+    }
+    return kept ? 1 : 0;
+}
+
+// 0 / 1, or 2 = refused (physical mode only)
+template <int MODE>
+__device__ __forceinline__ int dt_keep_any(const double *__restrict__ t, const uint8_t *__restrict__ p, int64_t i,
+                                           const DtModel md)
+{
+    if (MODE == 0)
+        return dt_keep(t, p, i) ? 1 : 0;
+    EventArrays ev{t, p};
+    return dt_keep_phys(ev, i, true, md);
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(NT) k_deadtime_count(const cgrb_unit_t *__restrict__ units,
                                                        const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                        const double *__restrict__ times_tot,
                                                        const uint8_t *__restrict__ pha_tot,
                                                        int32_t *__restrict__ tile_count,
-                                                       const cgrb_counts_t *counts)
+                                                       const cgrb_counts_t *counts, const DtModel md)
 {
     __shared__ int s_wi[NW];
     const int64_t w = blockIdx.x;
@@ -171,7 +248,7 @@ __global__ void __launch_bounds__(NT) k_deadtime_count(const cgrb_unit_t *__rest
         const uint8_t *p = pha_tot + u->tot_off;
         const int64_t end = min(wk.start + (int64_t)CGRB_DT_TILE, n);
         for (int64_t i = wk.start + threadIdx.x; i < end; i += NT)
-            cnt += dt_keep(t, p, i) ? 1 : 0;
+            cnt += dt_keep_any<MODE>(t, p, i, md) == 1 ? 1 : 0;
     }
     int total;
     (void)block_incl_scan_i(cnt, s_wi, &total);
@@ -179,6 +256,7 @@ __global__ void __launch_bounds__(NT) k_deadtime_count(const cgrb_unit_t *__rest
         tile_count[w] = total;
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__restrict__ units,
                                                        const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                        const int64_t *__restrict__ unit_work_begin,
@@ -186,7 +264,8 @@ __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__rest
                                                        const uint8_t *__restrict__ pha_tot,
                                                        const int32_t *__restrict__ tile_count,
                                                        double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
-                                                       uint8_t *__restrict__ selection, cgrb_counts_t *counts)
+                                                       uint8_t *__restrict__ selection, cgrb_counts_t *counts,
+                                                       const DtModel md)
 {
     __shared__ long long s_wl[NW];
     __shared__ int s_wi[NW];
@@ -216,7 +295,10 @@ __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__rest
         double ti = 0.0;
         uint8_t pi = 0;
         if (i < end) {
-            keep = dt_keep(t, p, i);
+            const int k3 = dt_keep_any<MODE>(t, p, i, md);
+            if (MODE != 0 && k3 == 2)
+                atomicOr(&counts[wk.unit].status, CGRB_ST_DEADTIME_CHAIN);
+            keep = k3 == 1;
             ti = t[i];
             pi = p[i];
             if (selection)
@@ -389,6 +471,12 @@ __device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, 
     return ti > t_end ? 1 : 0;
 }
 
+// physical model on the slow accessor (kept out of line like dt_keep_slow)
+__device__ __noinline__ int dt_keep_phys_slow(const MergedGlobal &m, int64_t i, const DtModel md)
+{
+    return dt_keep_phys(m, i, true, md);
+}
+
 // merge-path splits of every tile, one thread per tile: the ~23 dependent probes of each search are
 // hidden by the other tiles' searches instead of stalling a whole CTA at its first barrier.
 // splits[2w] = split at the tile's halo start, splits[2w+1] = split at the tile start.
@@ -415,6 +503,7 @@ __global__ void __launch_bounds__(NT) k_merge_splits(const cgrb_unit_t *__restri
 #define MD_PER (MD_N / NT)       // merged elements per thread in the serial merge (9)
 #define MD_R (MD_TILE / NT)     // tile elements per thread in the dead-time pass (8)
 
+template <int MODE>
 __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
                                                        const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                        const int64_t *__restrict__ unit_work_begin,
@@ -425,7 +514,7 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
                                                        unsigned long long *tile_state,
                                                        const int64_t *__restrict__ splits,
                                                        double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
-                                                       cgrb_counts_t *counts)
+                                                       cgrb_counts_t *counts, const DtModel md)
 {
     __shared__ double s_in_t[MD_N];         // the two input slices, background first
     __shared__ double s_t[MD_N];            // merged
@@ -510,9 +599,20 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
             const int e = r * NT + threadIdx.x;
             int keep = 0;
             if (e < nt) {
-                keep = dt_keep_local(s_t, s_p, l0 + e, g0);
-                if (keep == 2)
-                    keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
+                if (MODE == 0) {
+                    keep = dt_keep_local(s_t, s_p, l0 + e, g0);
+                    if (keep == 2)
+                        keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
+                } else {
+                    const EventArrays ev{s_t, s_p};
+                    keep = dt_keep_phys(ev, (int64_t)(l0 + e), g0 == 0, md);
+                    if (keep == 2)
+                        keep = dt_keep_phys_slow(mg, d0 + e, md);
+                    if (keep == 2) {
+                        atomicOr(&counts[wk.unit].status, CGRB_ST_DEADTIME_CHAIN);
+                        keep = 0;
+                    }
+                }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (lane == 0)

@@ -452,20 +452,51 @@ int cgrb_combine(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_w
     return check_launch("cgrb_combine");
 }
 
+// validates a dead-time model; *physical = 1 for the non-paralyzable model
+static int deadtime_model(const cgrb_deadtime_model_t *model, DtModel *md, int *physical, const char *who)
+{
+    md->tau = md->tau_ovf = md->tau_max = 0.0;
+    *physical = 0;
+    if (!model || model->mode == CGRB_DEADTIME_REFERENCE)
+        return CGRB_OK;
+    if (model->mode != CGRB_DEADTIME_PHYSICAL)
+        return fail(CGRB_E_BADARG, "%s: unknown dead-time mode", who);
+    if (!(model->tau >= 0.0) || !(model->tau_overflow >= 0.0) || !(model->tau < 1e300) ||
+        !(model->tau_overflow < 1e300))
+        return fail(CGRB_E_BADARG, "%s: dead-time windows must be finite and >= 0", who);
+    md->tau = model->tau;
+    md->tau_ovf = model->tau_overflow;
+    md->tau_max = model->tau > model->tau_overflow ? model->tau : model->tau_overflow;
+    *physical = 1;
+    return CGRB_OK;
+}
+
 int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
                        const int64_t *d_unit_work_begin, const double *d_times_tot, const uint8_t *d_pha_tot,
                        int32_t *d_tile_count, double *d_times_out, uint8_t *d_pha_out, uint8_t *d_selection,
-                       cgrb_counts_t *d_counts, void *stream)
+                       cgrb_counts_t *d_counts, const cgrb_deadtime_model_t *model, void *stream)
 {
     if (!d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_times_tot ||
         !d_pha_tot || !d_tile_count || !d_times_out || !d_pha_out || !d_counts)
         return fail(CGRB_E_BADARG, "cgrb_gbm_dead_time: bad argument%s");
+    DtModel md;
+    int physical;
+    if (int rc = deadtime_model(model, &md, &physical, "cgrb_gbm_dead_time"))
+        return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH("k_deadtime_count", s, k_deadtime_count<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_times_tot, d_pha_tot,
-                                                     d_tile_count, d_counts));
-    LAUNCH("k_deadtime_write", s, k_deadtime_write<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_times_tot,
-                                                     d_pha_tot, d_tile_count, d_times_out, d_pha_out,
-                                                     d_selection, d_counts));
+    if (!physical) {
+        LAUNCH("k_deadtime_count", s, k_deadtime_count<0><<<(unsigned)n_work, NT, 0, s>>>(
+            d_units, d_work, n_work, d_times_tot, d_pha_tot, d_tile_count, d_counts, md));
+        LAUNCH("k_deadtime_write", s, k_deadtime_write<0><<<(unsigned)n_work, NT, 0, s>>>(
+            d_units, d_work, n_work, d_unit_work_begin, d_times_tot, d_pha_tot, d_tile_count, d_times_out,
+            d_pha_out, d_selection, d_counts, md));
+    } else {
+        LAUNCH("k_deadtime_count_phys", s, k_deadtime_count<1><<<(unsigned)n_work, NT, 0, s>>>(
+            d_units, d_work, n_work, d_times_tot, d_pha_tot, d_tile_count, d_counts, md));
+        LAUNCH("k_deadtime_write_phys", s, k_deadtime_write<1><<<(unsigned)n_work, NT, 0, s>>>(
+            d_units, d_work, n_work, d_unit_work_begin, d_times_tot, d_pha_tot, d_tile_count, d_times_out,
+            d_pha_out, d_selection, d_counts, md));
+    }
     return check_launch("cgrb_gbm_dead_time");
 }
 
@@ -474,11 +505,16 @@ int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 24 * (n_wo
 int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
                          const int64_t *d_unit_work_begin, const double *d_times_bkg, const uint8_t *d_pha_bkg,
                          const double *d_times_src, const uint8_t *d_pha_src, void *d_workspace,
-                         double *d_times_out, uint8_t *d_pha_out, cgrb_counts_t *d_counts, void *stream)
+                         double *d_times_out, uint8_t *d_pha_out, cgrb_counts_t *d_counts,
+                         const cgrb_deadtime_model_t *model, void *stream)
 {
     if (!d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_times_bkg || !d_pha_bkg ||
         !d_times_src || !d_pha_src || !d_workspace || !d_times_out || !d_pha_out || !d_counts)
         return fail(CGRB_E_BADARG, "cgrb_merge_dead_time: bad argument%s");
+    DtModel md;
+    int physical;
+    if (int rc = deadtime_model(model, &md, &physical, "cgrb_merge_dead_time"))
+        return rc;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(d_workspace, 0, 8 * (size_t)n_work, s);
     if (e != cudaSuccess)
@@ -486,9 +522,15 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
     int64_t *splits = (int64_t *)d_workspace + n_work;
     LAUNCH("k_merge_splits", s, k_merge_splits<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
         d_units, d_work, n_work, d_times_bkg, d_times_src, splits, d_counts));
-    LAUNCH("k_merge_deadtime", s, k_merge_deadtime<<<(unsigned)n_work, NT, 0, s>>>(
-        d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
-        (unsigned long long *)d_workspace, splits, d_times_out, d_pha_out, d_counts));
+    if (!physical) {
+        LAUNCH("k_merge_deadtime", s, k_merge_deadtime<0><<<(unsigned)n_work, NT, 0, s>>>(
+            d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
+            (unsigned long long *)d_workspace, splits, d_times_out, d_pha_out, d_counts, md));
+    } else {
+        LAUNCH("k_merge_deadtime_phys", s, k_merge_deadtime<1><<<(unsigned)n_work, NT, 0, s>>>(
+            d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
+            (unsigned long long *)d_workspace, splits, d_times_out, d_pha_out, d_counts, md));
+    }
     return check_launch("cgrb_merge_dead_time");
 }
 

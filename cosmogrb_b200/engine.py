@@ -145,7 +145,8 @@ class Batch(object):
 class Engine(object):
     """One engine per process and device."""
 
-    def __init__(self, device=None, seed=DEFAULT_SEED, interp_extrap="linear", energy_sampler="envelope", squeeze=True):
+    def __init__(self, device=None, seed=DEFAULT_SEED, interp_extrap="linear", energy_sampler="envelope", squeeze=True,
+                 deadtime_mode="reference", deadtime_tau=2.6e-6, deadtime_tau_overflow=10e-6):
         torch = _torch()
         self.lib = _capi.load()
         if not torch.cuda.is_available():
@@ -162,6 +163,9 @@ class Engine(object):
         self.interp_extrap = interp_extrap
         self.energy_sampler = energy_sampler
         self.squeeze = bool(squeeze)
+        # GBM dead-time model: "reference" = literal _gbm_dead_time (gbm_lightcurve.py:80-115), "physical" =
+        # non-paralyzable window after EVERY kept event
+        self.set_deadtime(deadtime_mode, deadtime_tau, deadtime_tau_overflow)
         self.squeeze_ratio, self.squeeze_min_candidates, self.squeeze_max_nodes = 8, 2048, 1 << 14
         self.energy_row_spacing, self.energy_candidates_per_row = 0.02, 256
         # hard ceiling on the thinning candidates of ONE unit (fmax x duration): beyond it the unit's
@@ -172,6 +176,18 @@ class Engine(object):
         self._pool = None
         self._dtab_cache = {}
         self.launches = 0           # kernels launched by this engine (bench.py's gpu_launches)
+
+    def set_deadtime(self, mode="reference", tau=2.6e-6, tau_overflow=10e-6):
+        if mode not in ("reference", "physical"):
+            raise ValueError(f"deadtime mode must be 'reference' or 'physical', got {mode!r}")
+        self.deadtime_mode, self.deadtime_tau, self.deadtime_tau_overflow = mode, float(tau), float(tau_overflow)
+
+    def _deadtime_model(self, mode=None):
+        mode = self.deadtime_mode if mode is None else mode
+        if mode not in ("reference", "physical"):
+            raise ValueError(f"deadtime mode must be 'reference' or 'physical', got {mode!r}")
+        return _capi.DeadtimeModel(_capi.DEADTIME_PHYSICAL if mode == "physical" else _capi.DEADTIME_REFERENCE, 0,
+                                   self.deadtime_tau, self.deadtime_tau_overflow)
 
     # -- small helpers --------------------------------------------------------------------------
     @property
@@ -600,8 +616,9 @@ class Engine(object):
             "cgrb_combine")
         self.launches += 1
 
-    def dead_time(self, b, want_selection=False):
+    def dead_time(self, b, want_selection=False, mode=None):
         torch = _torch()
+        model = self._deadtime_model(mode)
         w, dw, dwb = self._work(b, 2, _capi.DT_TILE)
         t = b.t
         t["tile_count"] = self.empty(len(w), torch.int32)
@@ -615,14 +632,15 @@ class Engine(object):
                 b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), dwb.data_ptr(),
                 t["times_tot"].data_ptr(), t["pha_tot"].data_ptr(), t["tile_count"].data_ptr(),
                 t["times_out"].data_ptr(), t["pha_out"].data_ptr(),
-                sel.data_ptr() if want_selection else None, b.d_counts.data_ptr(), self.stream),
+                sel.data_ptr() if want_selection else None, b.d_counts.data_ptr(), C.byref(model), self.stream),
             "cgrb_gbm_dead_time")
         self.launches += 2
 
-    def merge_dead_time(self, b):
+    def merge_dead_time(self, b, mode=None):
         """combine + dead time in one pass: only the survivors reach HBM (``times_out``/``pha_out``);
         bit-identical to ``combine`` followed by ``dead_time``."""
         torch = _torch()
+        model = self._deadtime_model(mode)
         w, dw, dwb = self._work(b, 2, _capi.MD_TILE)
         t = b.t
         t["tile_state"] = self.empty(self.lib.cgrb_merge_dead_time_workspace_bytes(len(w)), torch.uint8)
@@ -633,7 +651,7 @@ class Engine(object):
                 b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), dwb.data_ptr(),
                 t["times_bkg"].data_ptr(), t["pha_bkg"].data_ptr(), t["times_src"].data_ptr(),
                 t["pha_src"].data_ptr(), t["tile_state"].data_ptr(), t["times_out"].data_ptr(),
-                t["pha_out"].data_ptr(), b.d_counts.data_ptr(), self.stream),
+                t["pha_out"].data_ptr(), b.d_counts.data_ptr(), C.byref(model), self.stream),
             "cgrb_merge_dead_time")
         self.launches += 2
 
@@ -712,7 +730,8 @@ class Engine(object):
         bad = np.nonzero(c["status"])[0]
         if len(bad):
             names = {1: "source capacity", 2: "background capacity", 4: "injected uniforms exhausted",
-                     8: "trial cap", 16: "output capacity", 32: "energy envelope violated"}
+                     8: "trial cap", 16: "output capacity", 32: "energy envelope violated",
+                     64: "physical dead time: event rate x window too high (chain > 4096 events)"}
             ui = int(bad[0])
             st = int(c["status"][ui])
             what = ", ".join(v for k, v in names.items() if st & k)
@@ -819,7 +838,7 @@ class Engine(object):
         self.launches += 1
         return out[:n].cpu().numpy().astype(np.int64)
 
-    def combine_dead_time(self, times_bkg, pha_bkg, times_src, pha_src, fused=True):
+    def combine_dead_time(self, times_bkg, pha_bkg, times_src, pha_src, fused=True, mode=None):
         """LightCurve._combine + GBMLightCurve._filter_deadtime for one detector's two time-sorted
         event lists; returns (times, pha) of the survivors.  ``fused`` selects the one-pass kernel."""
         torch = _torch()
@@ -837,16 +856,17 @@ class Engine(object):
         b.t["times_bkg"] = self.to_device(pad(times_bkg, b.n_bkg_slots, "f8"))
         b.t["pha_bkg"] = self.to_device(pad(pha_bkg, b.n_bkg_slots, np.uint8))
         if fused:
-            self.merge_dead_time(b)
+            self.merge_dead_time(b, mode=mode)
         else:
             self.combine(b)
-            self.dead_time(b)
+            self.dead_time(b, mode=mode)
         c = self.fetch_counts(b)
+        self.check_status(b)
         n = int(c["n_kept"][0])
         assert int(c["n_total"][0]) == nb + ns
         return b.t["times_out"][:n].cpu().numpy(), b.t["pha_out"][:n].cpu().numpy()
 
-    def gbm_dead_time(self, times, pha):
+    def gbm_dead_time(self, times, pha, mode=None):
         """_gbm_dead_time for one time-sorted event list; returns the boolean selection."""
         torch = _torch()
         times = np.ascontiguousarray(times, dtype="f8")
@@ -863,7 +883,9 @@ class Engine(object):
         self.set_counts(b, n_total=n)
         b.t["times_tot"] = self.to_device(np.concatenate((times, [0.0, 0.0])))
         b.t["pha_tot"] = self.to_device(np.concatenate((pha8, np.zeros(2, np.uint8))))
-        self.dead_time(b, want_selection=True)
+        self.dead_time(b, want_selection=True, mode=mode)
+        self.fetch_counts(b)
+        self.check_status(b)
         return b.t["selection"][:n].cpu().numpy().astype(bool)
 
 
@@ -880,7 +902,10 @@ def get_engine(**kw):
 
             opts = dict(seed=cosmogrb_config["engine"]["seed"],
                         interp_extrap=cosmogrb_config["engine"]["interp_extrap"],
-                        energy_sampler=cosmogrb_config["engine"]["energy_sampler"])
+                        energy_sampler=cosmogrb_config["engine"]["energy_sampler"],
+                        deadtime_mode=cosmogrb_config["engine"]["deadtime_mode"],
+                        deadtime_tau=cosmogrb_config["engine"]["deadtime_tau"],
+                        deadtime_tau_overflow=cosmogrb_config["engine"]["deadtime_tau_overflow"])
             opts.update(kw)
             _engine = Engine(**opts)
         return _engine

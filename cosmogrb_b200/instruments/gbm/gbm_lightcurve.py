@@ -1,5 +1,6 @@
 """``GBMLightCurve`` (cosmogrb/instruments/gbm/gbm_lightcurve.py:11-115): a LightCurve whose merged
-event list goes through the GBM dead-time filter (literal reference semantics, on the GPU)."""
+event list goes through the GBM dead-time filter on the GPU (literal reference semantics by default;
+``cosmogrb_config.engine.deadtime_mode = "physical"`` selects the non-paralyzable model)."""
 import numpy as np
 
 from ...engine import get_engine
@@ -24,9 +25,10 @@ class GBMLightCurve(LightCurve):
         raise NotImplementedError("TTE FITS output is outside the photon-event hot path (SURVEY.md §8 f3)")
 
 
-def gbm_dead_time(time, pha):
+def gbm_dead_time(time, pha, mode=None):
     """``_gbm_dead_time`` (gbm_lightcurve.py:80-115) on the GPU: returns (filtered_time, filtered_pha,
-    selection) with the reference's conventions (zeros where an event is dropped)."""
+    selection) with the reference's conventions (zeros where an event is dropped).  ``mode``: None (the
+    engine's configured model) | "reference" | "physical"."""
     time, pha = np.asarray(time, dtype="f8"), np.asarray(pha, dtype="f8")
-    sel = get_engine().gbm_dead_time(time, pha)
+    sel = get_engine().gbm_dead_time(time, pha, mode=mode)
     return np.where(sel, time, 0.0), np.where(sel, pha, 0.0), sel.astype("f8")

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CGRB_ABI_VERSION 3
+#define CGRB_ABI_VERSION 4
 
 /* error codes */
 #define CGRB_OK 0
@@ -45,6 +45,7 @@ extern "C" {
 #define CGRB_ST_TRIAL_CAP 8u         /* energy rejection hit max_trials                     */
 #define CGRB_ST_OUT_CAPACITY 16u     /* an output buffer was too small                      */
 #define CGRB_ST_ENVELOPE 32u         /* energy envelope failed to dominate the target (bug)  */
+#define CGRB_ST_DEADTIME_CHAIN 64u   /* physical dead time: > 4096 consecutive events closer than the longest window */
 
 /* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
 #define CGRB_NBINS 140
@@ -273,8 +274,27 @@ int cgrb_combine(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_w
                  const double *d_times_src, const uint8_t *d_pha_src,
                  double *d_times_tot, uint8_t *d_pha_tot, cgrb_counts_t *d_counts, void *stream);
 
-/* GBMLightCurve._filter_deadtime (gbm_lightcurve.py:42-56; numba _gbm_dead_time :80-115), literal
- * reference semantics.  Work list: which=2, chunk=CGRB_DT_TILE; d_tile_count [n_work] int32 is
+/* Dead-time model (SURVEY.md §8b "dead-time with mode in {reference, physical}").
+ *   CGRB_DEADTIME_REFERENCE: the literal semantics of numba _gbm_dead_time (gbm_lightcurve.py:80-115):
+ *       event 0 kept, window 2.6 us (10.6 us if it is in the overflow channel 127); later events are kept
+ *       iff t > t_end, and ONLY a kept overflow event moves t_end (to t + 10.6 us).  tau / tau_overflow
+ *       are ignored.  This is what every parity test compares with the reference.
+ *   CGRB_DEADTIME_PHYSICAL: the non-paralyzable detector the reference's docstring describes (§8 f4):
+ *       EVERY kept event opens a window (tau_overflow for channel 127, else tau); an event is kept iff
+ *       t > t_end of the last kept event.  Not computed by the reference; checked against the serial
+ *       definition in oracle/cgrb_oracle.c (co_gbm_dead_time_physical).
+ * A NULL model pointer means CGRB_DEADTIME_REFERENCE. */
+#define CGRB_DEADTIME_REFERENCE 0
+#define CGRB_DEADTIME_PHYSICAL 1
+typedef struct {
+    int32_t mode;
+    int32_t pad;
+    double tau;            /* physical mode: window after a kept event, seconds (GBM: 2.6e-6)        */
+    double tau_overflow;   /* physical mode: window after a kept overflow-channel event (GBM: 10e-6) */
+} cgrb_deadtime_model_t;
+
+/* GBMLightCurve._filter_deadtime (gbm_lightcurve.py:42-56; numba _gbm_dead_time :80-115).
+ * Work list: which=2, chunk=CGRB_DT_TILE; d_tile_count [n_work] int32 is
  * workspace.  d_selection (optional) receives the per-event keep flag.  Output is compacted at
  * tot_off; counts.n_kept. */
 #define CGRB_DT_TILE 2048
@@ -282,7 +302,7 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
                        const int64_t *d_unit_work_begin,
                        const double *d_times_tot, const uint8_t *d_pha_tot, int32_t *d_tile_count,
                        double *d_times_out, uint8_t *d_pha_out, uint8_t *d_selection,
-                       cgrb_counts_t *d_counts, void *stream);
+                       cgrb_counts_t *d_counts, const cgrb_deadtime_model_t *model, void *stream);
 
 /* LightCurve._combine followed by GBMLightCurve._filter_deadtime in one pass (lightcurve.py:131-151,
  * 189-190; gbm_lightcurve.py:42-56): the merged pre-dead-time list is not one of the products of
@@ -296,7 +316,8 @@ int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work);
 int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
                          const int64_t *d_unit_work_begin, const double *d_times_bkg, const uint8_t *d_pha_bkg,
                          const double *d_times_src, const uint8_t *d_pha_src, void *d_workspace,
-                         double *d_times_out, uint8_t *d_pha_out, cgrb_counts_t *d_counts, void *stream);
+                         double *d_times_out, uint8_t *d_pha_out, cgrb_counts_t *d_counts,
+                         const cgrb_deadtime_model_t *model, void *stream);
 
 /* ---- GBM trigger ----------------------------------------------------------- */
 

@@ -551,6 +551,30 @@ int64_t co_gbm_dead_time(const double *time, const double *pha, int64_t n, uint8
     return kept;
 }
 
+/* Physical (non-paralyzable) GBM dead time -- SURVEY.md §8 f4.  NOT computed by the reference (its loop,
+ * restated above, only advances t_end on kept overflow events); this is the serial definition the
+ * engine's CGRB_DEADTIME_PHYSICAL mode is checked against: every kept event opens a window of `tau`
+ * seconds (`tau_overflow` for the overflow channel 127) and an event is kept iff it falls after the
+ * window of the last kept event. */
+int64_t co_gbm_dead_time_physical(const double *time, const double *pha, int64_t n, double tau,
+                                  double tau_overflow, uint8_t *selection)
+{
+    if (n <= 0)
+        return 0;
+    int64_t kept = 1;
+    memset(selection, 0, (size_t)n);
+    selection[0] = 1;
+    double t_end = time[0] + (pha[0] == 127 ? tau_overflow : tau);
+    for (int64_t i = 1; i < n; i++) {
+        if (time[i] > t_end) {
+            selection[i] = 1;
+            kept++;
+            t_end = time[i] + (pha[i] == 127 ? tau_overflow : tau);
+        }
+    }
+    return kept;
+}
+
 /* lightcurve/lightcurve.py:167-200 for one detector (GBMLightCurve), MT19937 streams in the
  * reference's consumption order: numba stream = source times, energies, channels, then
  * background times; numpy global stream = background channels. */

@@ -107,6 +107,9 @@ void co_combine(const double *t_bkg, const double *pha_bkg, int64_t n_bkg,
 
 /* instruments/gbm/gbm_lightcurve.py:80-115; returns the number of survivors */
 int64_t co_gbm_dead_time(const double *time, const double *pha, int64_t n, uint8_t *selection);
+/* non-paralyzable model (not the reference's; serial definition for CGRB_DEADTIME_PHYSICAL) */
+int64_t co_gbm_dead_time_physical(const double *time, const double *pha, int64_t n, double tau,
+                                  double tau_overflow, uint8_t *selection);
 
 /* lightcurve/lightcurve.py:167-200 for one detector, MT19937-seeded, used as the CPU baseline.
  * fmax_in > 0 overrides Source._fmax (used to time a window of a longer burst).

@@ -101,6 +101,8 @@ def lib():
     L.co_combine.restype = None
     L.co_gbm_dead_time.argtypes = [vp, vp, i64, vp]
     L.co_gbm_dead_time.restype = i64
+    L.co_gbm_dead_time_physical.argtypes = [vp, vp, i64, C.c_double, C.c_double, vp]
+    L.co_gbm_dead_time_physical.restype = i64
     L.co_process_detector.argtypes = [sp, vp, i32, vp, vp, vp, i32, vp, d, d, d, d, d, d,
                                       C.c_uint32, C.c_uint32, i64, vp]
     L.co_process_detector.restype = i64
@@ -271,6 +273,15 @@ def gbm_dead_time(times, pha):
     times, pha = _f8(times), _f8(pha)
     sel = np.zeros(len(times), np.uint8)
     lib().co_gbm_dead_time(times.ctypes.data, pha.ctypes.data, len(times), sel.ctypes.data)
+    return sel.astype(bool)
+
+
+def gbm_dead_time_physical(times, pha, tau=2.6e-6, tau_overflow=10e-6):
+    """serial definition of the non-paralyzable model (not the reference's rule)"""
+    times, pha = _f8(times), _f8(pha)
+    sel = np.zeros(len(times), np.uint8)
+    lib().co_gbm_dead_time_physical(times.ctypes.data, pha.ctypes.data, len(times), float(tau), float(tau_overflow),
+                                    sel.ctypes.data)
     return sel.astype(bool)
 
 

@@ -199,6 +199,66 @@ def test_fused_merge_dead_time(engine, rate, frac127):
         assert np.array_equal(got_t, wt[s2]) and np.array_equal(got_p.astype("f8"), wp[s2])
 
 
+def test_dead_time_physical_crafted(engine):
+    """CGRB_DEADTIME_PHYSICAL (non-paralyzable) against its serial definition."""
+    t = np.array([0, 1, 3, 4, 10, 15, 20.5, 20.7, 31.2, 32]) * 1e-6
+    pha = np.array([5, 6, 7, 8, 127, 9, 10, 11, 127, 12])
+    want = np.array([1, 0, 1, 0, 1, 0, 1, 0, 1, 0], dtype=bool)
+    assert np.array_equal(engine.gbm_dead_time(t, pha, mode="physical"), want)
+    assert np.array_equal(engine.gbm_dead_time(t[:1], pha[:1], mode="physical"), [True])
+    assert np.array_equal(engine.gbm_dead_time(t[:2], pha[:2], mode="physical"), [True, False])
+    # the default stays the reference's literal rule
+    assert np.array_equal(engine.gbm_dead_time(t, pha), orc.gbm_dead_time(t, pha))
+    # other window lengths, incl. tau > tau_overflow and zero windows
+    old = (engine.deadtime_mode, engine.deadtime_tau, engine.deadtime_tau_overflow)
+    try:
+        for tau, tovf in ((5e-6, 1e-6), (0.0, 0.0), (2.6e-6, 10.6e-6)):
+            engine.set_deadtime("physical", tau, tovf)
+            assert np.array_equal(engine.gbm_dead_time(t, pha), orc.gbm_dead_time_physical(t, pha, tau, tovf))
+    finally:
+        engine.set_deadtime(*old)
+    with pytest.raises(ValueError):
+        engine.gbm_dead_time(t, pha, mode="paralyzable")
+
+
+@pytest.mark.parametrize("rate,frac127", [(500.0, 0.05), (2e4, 0.05), (2e5, 0.1), (5e5, 0.3)])
+def test_dead_time_physical_random(engine, rate, frac127):
+    """1e6 random events from GBM-like rates up to 5e5 /s (runs of ~150 events between synchronisation
+    points), stand-alone and fused with the merge, bit-exact against the serial definition."""
+    rs = np.random.RandomState(17)
+    n = 1_000_000
+    t = np.cumsum(rs.exponential(1.0 / rate, n))
+    pha = rs.randint(0, 127, n)
+    pha[rs.random_sample(n) < frac127] = 127
+    want = orc.gbm_dead_time_physical(t, pha)
+    assert np.array_equal(engine.gbm_dead_time(t, pha, mode="physical"), want)
+    # fused: split the list into two interleaved "components" and let the kernel merge them back
+    is_src = rs.random_sample(n) < 0.7
+    ts, ps, tb, pb = t[is_src], pha[is_src], t[~is_src], pha[~is_src]
+    wt, wp = orc.combine(tb, pb, ts, ps)
+    sel = orc.gbm_dead_time_physical(wt, wp)
+    for fused in (True, False):
+        got_t, got_p = engine.combine_dead_time(tb, pb, ts, ps, fused=fused, mode="physical")
+        assert np.array_equal(got_t, wt[sel]), fused
+        assert np.array_equal(got_p.astype("f8"), wp[sel]), fused
+    # fraction lost ~ 1 - 1/(1 + rate * mean window) for a non-paralyzable counter
+    mean_tau = (1 - frac127) * 2.6e-6 + frac127 * 10e-6
+    assert abs(want.mean() - 1.0 / (1.0 + rate * mean_tau)) < 0.01
+
+
+def test_dead_time_physical_refuses_runaway_chains(engine):
+    """rate x window >> 1: no synchronisation point within 4096 events -> loud status, not an O(n^2) walk"""
+    n = 20000
+    t = np.arange(n) * 1e-7
+    pha = np.full(n, 127)
+    with pytest.raises(_capi.EngineError, match="physical dead time"):
+        engine.gbm_dead_time(t, pha, mode="physical")
+    with pytest.raises(_capi.EngineError, match="physical dead time"):
+        engine.combine_dead_time(t[::2], pha[::2], t[1::2], pha[1::2], mode="physical")
+    # the literal rule has no such limit
+    assert np.array_equal(engine.gbm_dead_time(t, pha), orc.gbm_dead_time(t, pha))
+
+
 def test_combine_and_dead_time_pipeline(engine):
     """Full unit under Philox; the oracle re-does combine + dead time from the GPU's component lists."""
     params = h.CONFTEST_BRIGHT

@@ -96,6 +96,34 @@ def test_dead_time():
         assert np.array_equal(orc.gbm_dead_time(t, pha), want)
 
 
+def test_dead_time_physical_definition():
+    """The non-paralyzable model (not computed by the reference): hand-worked case and a
+    pure-Python replay of the serial definition."""
+    t = np.array([0, 1, 3, 4, 10, 15, 20.5, 20.7, 31.2, 32]) * 1e-6
+    pha = np.array([5, 6, 7, 8, 127, 9, 10, 11, 127, 12])
+    # windows: 0 -> 2.6; 3 -> 5.6 (4 dropped); 10 (ovf) -> 20; 15 dropped; 20.5 -> 23.1 (20.7 dropped);
+    # 31.2 (ovf) -> 41.2; 32 dropped
+    want = np.array([1, 0, 1, 0, 1, 0, 1, 0, 1, 0], dtype=bool)
+    assert np.array_equal(orc.gbm_dead_time_physical(t, pha), want)
+    # the reference's literal rule differs on this input (only overflow events move t_end)
+    assert not np.array_equal(orc.gbm_dead_time(t, pha), want)
+    rs = np.random.RandomState(3)
+    n = 20000
+    t = np.cumsum(rs.exponential(1.0 / 2e5, n))
+    pha = rs.randint(0, 128, n)
+    pha[rs.random_sample(n) < 0.1] = 127
+    sel = np.zeros(n, bool)
+    t_end = -np.inf
+    for i in range(n):
+        if i == 0 or t[i] > t_end:
+            sel[i] = True
+            t_end = t[i] + (10e-6 if pha[i] == 127 else 2.6e-6)
+    assert np.array_equal(orc.gbm_dead_time_physical(t, pha, 2.6e-6, 10e-6), sel)
+    assert len(orc.gbm_dead_time_physical(t[:0], pha[:0])) == 0
+    # zero-length windows keep everything that is strictly later than its predecessor
+    assert orc.gbm_dead_time_physical(t, pha, 0.0, 0.0).all()
+
+
 def test_background():
     g = load("background.npz")
     t = orc.background_times(-10.0, 30.0, 497.25, orc.Rng(seed=9))
