@@ -21,8 +21,30 @@ class GBMLightCurve(LightCurve):
         self._times = np.asarray(self._times)[sel]
         self._pha = np.asarray(self._pha)[sel]
 
-    def write_tte(self):
-        raise NotImplementedError("TTE FITS output is outside the photon-event hot path (SURVEY.md §8 f3)")
+    def write_tte(self, file_name=None):
+        """TTE FITS file of the (dead-time-filtered) event list, ``<grb>_<detector>.fits``
+        (gbm_lightcurve.py:58-77); needs ``process()`` to have run."""
+        from ...utils.tte_file import TTEFile
+
+        if self._times is None or self._pha is None:
+            raise RuntimeError("write_tte() needs a processed light curve: call process() first")
+        rsp = self._response
+        tte_file = TTEFile(
+            det_name=rsp.detector_name,
+            tstart=self._background.tstart + rsp.T0,
+            tstop=self._background.tstop + rsp.T0,
+            trigger_time=rsp.trigger_time,
+            ra=rsp.ra,
+            dec=rsp.dec,
+            channel=np.arange(0, 128, dtype=np.int16),
+            emin=rsp.channel_edges[:-1],
+            emax=rsp.channel_edges[1:],
+            pha=np.asarray(self._pha).astype(np.int16),
+            time=np.asarray(self._times, dtype="f8") + rsp.T0,
+        )
+        file_name = file_name or f"{self._grb_name}_{self._name}.fits"
+        tte_file.writeto(file_name, overwrite=True)
+        return file_name
 
 
 def gbm_dead_time(time, pha, mode=None):

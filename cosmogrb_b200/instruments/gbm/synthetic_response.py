@@ -166,6 +166,14 @@ class SyntheticGBMResponse(Response):
         return self._trigger_time
 
     @property
+    def ra(self):
+        return self._ra
+
+    @property
+    def dec(self):
+        return self._dec
+
+    @property
     def T0(self):
         return self._trigger_time
 

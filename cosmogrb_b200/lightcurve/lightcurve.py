@@ -31,6 +31,8 @@ class LightCurve(object):
         self._instrument = instrument
         self._extra_info = {}
         self._lc_storage = None
+        self._times = None          # the total list after process() (lightcurve.py:189-190)
+        self._pha = None
 
     def set_time_adjustment(self, t):
         self._time_adjustment = t
@@ -58,6 +60,7 @@ class LightCurve(object):
         pha, times = sl("pha_out"), sl("times_out")
         if not self._deadtime:
             pha, times = sl("pha_tot"), sl("times_tot")
+        self._times, self._pha = times, pha
         return LightCurveStorage(
             name=self._name, tstart=self._tstart, tstop=self._tstop, time_adjustment=self._time_adjustment,
             pha=pha, times=times, pha_source=sl("pha_src"), times_source=sl("times_src"),

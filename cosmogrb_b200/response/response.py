@@ -187,6 +187,29 @@ class Response(object):
         return self._cumulative_maxtrix
 
 
+def _response_to_fits(self, filename, telescope_name="telescope", instrument_name="detector", overwrite=False):
+    """Write the matrix as an OGIP ``.rsp`` FITS file (response.py:238-263)."""
+    from ..utils.response_file import RSP
+
+    RSP(self._energy_edges, self._channel_edges, self.matrix.T, telescope_name, instrument_name).writeto(
+        filename, overwrite=overwrite)
+
+
+def _response_from_fits(cls, filename, geometric_area, extension=None):
+    """Build a ``Response`` from an OGIP response file (SPECRESP MATRIX + EBOUNDS, grouped or plain, e.g. a
+    real GBM ``.rsp`` / one matrix of an ``.rsp2``): the real-DRM ingestion route of SURVEY.md §8 f4 that
+    needs no ``gbm_drm_gen``.  Not in the reference (its responses come from ``DRMGenTTE``)."""
+    from ..utils.response_file import read_response
+
+    r = read_response(filename, extension=extension)
+    return cls(matrix=r["matrix"], geometric_area=geometric_area, energy_edges=r["energy_edges"],
+               channel_edges=r["channel_edges"])
+
+
+Response.to_fits = _response_to_fits
+Response.from_fits = classmethod(_response_from_fits)
+
+
 def channel_search_guide(cumulative_matrix):
     """uint8 [NBINS*NCHAN] guide of the device channel search (include/cosmogrb_b200.h, CGRB_DT_GUIDE):
     guide[b][m] = np.searchsorted(cum[b], m / NCHAN, 'left'), the first channel whose cumulative

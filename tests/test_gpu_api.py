@@ -82,6 +82,42 @@ def test_grb_save_and_reload(grb, tmp_path):
         assert got.extra_info["angle"] == pytest.approx(lc.response.separation_angle)
 
 
+def test_grb_to_gbm_fits_products(grb, tmp_path):
+    """go() -> GRB.save -> grbsave_to_gbm_fits (io/gbm_fits.py:9-83): one TTE + one RSP file per detector whose
+    events are the dead-time-filtered total list; GBMLightCurve.write_tte (gbm_lightcurve.py:58-77) writes the
+    same events; a response read back from its RSP file drives the engine to the same channels."""
+    from cosmogrb_b200.io import grbsave_to_gbm_fits
+    from cosmogrb_b200.response import Response
+    from cosmogrb_b200.utils.tte_file import read_tte
+
+    fn = tmp_path / "burst.h5"
+    grb.save(fn)
+    files = grbsave_to_gbm_fits(str(fn), destination=str(tmp_path), detectors=["n0", "b1"])
+    assert sorted(files) == ["b1", "n0"]
+    for det, f in files.items():
+        st = grb.lightcurves[det].lightcurve_storage
+        r = read_tte(f["tte"])
+        assert np.array_equal(r["time"], st.times + st.time_adjustment) and np.array_equal(r["pha"], st.pha)
+        assert r["det_name"] == {"n0": "NAI_00", "b1": "BGO_01"}[det]
+        rsp = grb.lightcurves[det].response
+        r2 = Response.from_fits(f["rsp"], geometric_area=rsp.geometric_area)
+        assert np.array_equal(r2.cumulative_matrix, rsp.cumulative_matrix)
+        # photon edges went through float32 in the file: digitize agrees wherever the energy is not within
+        # float32 rounding of an edge
+        rs = np.random.RandomState(3)
+        e = 10 ** rs.uniform(np.log10(rsp.emin * 1.01), np.log10(rsp.emax * 0.99), 20000)
+        near = np.min(np.abs(e[:, None] / rsp.energy_edges[None, :] - 1.0), axis=1) < 1e-6
+        from cosmogrb_b200.engine import Philox, get_engine
+        eng = get_engine()
+        a, b = eng.digitize(rsp, e, rng=Philox(5)), eng.digitize(r2, e, rng=Philox(5))
+        assert near.sum() < 100 and np.array_equal(a[~near], b[~near])
+    lc = grb.lightcurves["n3"]
+    out = lc.write_tte(str(tmp_path / "n3_direct.fits"))
+    r = read_tte(out)
+    st = lc.lightcurve_storage
+    assert np.array_equal(r["time"], st.times + lc.response.T0) and np.array_equal(r["pha"], st.pha)
+
+
 def test_go_is_reproducible_and_seed_dependent(engine):
     from cosmogrb_b200 import gbm
 
