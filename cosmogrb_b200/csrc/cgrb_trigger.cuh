@@ -144,8 +144,6 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
                                                   const int32_t *__restrict__ bins, int64_t *__restrict__ csum,
                                                   double *__restrict__ esum, cgrb_trigger_t *__restrict__ out)
 {
-    __shared__ double s_w[NW];
-    __shared__ long long s_l[NW];
     const int ui = blockIdx.x;
     if (ui >= n_units)
         return;
@@ -178,7 +176,12 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
     int64_t *cs = csum + (size_t)ui * 4 * (bins_per_unit + 1);
     double *es = esum + (size_t)ui * (bins_per_unit + 1);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // prefix sums: counts after the reference's float round trip, exposures = (stop - start) - dead time
+    // prefix sums: counts after the reference's float round trip, exposures = (stop - start) - dead time.
+    // One block scan per 256 bins carries all five quantities: warp scans by shuffles, the 8 warp totals
+    // exchanged through double-buffered shared memory (ONE barrier per round), the next round's bins
+    // prefetched before the barrier.  Fixed association, so the sums are reproducible.
+    __shared__ double s_pw[2][NW];
+    __shared__ int s_pi[2][4][NW];
     long long carry_c[4] = {0, 0, 0, 0};
     double carry_e = 0.0;
     if (threadIdx.x == 0) {
@@ -186,58 +189,73 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
             cs[r * (bins_per_unit + 1)] = 0;
         es[0] = 0.0;
     }
-    for (int64_t base = 0; base < nb; base += NT) {
+    int raw[TRIG_NARR];
+#pragma unroll
+    for (int a = 0; a < TRIG_NARR; a++)
+        raw[a] = (threadIdx.x < nb) ? ub[a * bins_per_unit + threadIdx.x] : 0;
+    int par_ = 0;
+    for (int64_t base = 0; base < nb; base += NT, par_ ^= 1) {
         const int64_t k = base + threadIdx.x;
         const bool in = k < nb;
-        long long c[4];
+        int c[4];
         double e = 0.0;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int raw = in ? ub[r * bins_per_unit + k] : 0;
-            c[r] = (long long)(__dmul_rn(__ddiv_rn((double)raw, dt), dt));      // (rate * dt).astype(int)
-        }
+        for (int r = 0; r < 4; r++)
+            c[r] = (int)(__dmul_rn(__ddiv_rn((double)raw[r], dt), dt));         // (rate * dt).astype(int)
         if (in) {
-            const int na = ub[4 * bins_per_unit + k], no = ub[5 * bins_per_unit + k];
+            const int na = raw[4], no = raw[5];
             const double dead = __dadd_rn(__dmul_rn((double)(na - no), 2.0e-6), __dmul_rn((double)no, 10.0e-6));
             e = __dadd_rn(__dadd_rn(g.edge(k + 1), -g.edge(k)), -dead);
         }
-        // block inclusive scans (fixed association)
-        double tot_e;
-        const double incl_e = block_incl_scan(e, s_w, &tot_e);
-        if (in)
-            es[k + 1] = carry_e + incl_e;
+        // prefetch the next round
+        const int64_t kn = k + NT;
+#pragma unroll
+        for (int a = 0; a < TRIG_NARR; a++)
+            raw[a] = (kn < nb) ? ub[a * bins_per_unit + kn] : 0;
+        e = warp_incl_scan(e, lane);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            c[r] = warp_incl_scan_i(c[r], lane);
+        if (lane == 31) {
+            s_pw[par_][wid] = e;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                s_pi[par_][r][wid] = c[r];
+        }
+        __syncthreads();
+        double before_e = 0.0, tot_e = 0.0;
+        int before_c[4] = {0, 0, 0, 0}, tot_c[4] = {0, 0, 0, 0};     // one round: 256 bins, far below 2^31
+#pragma unroll
+        for (int q = 0; q < NW; q++) {
+            const double we = s_pw[par_][q];
+            if (q < wid)
+                before_e += we;
+            tot_e += we;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int wc = s_pi[par_][r][q];
+                if (q < wid)
+                    before_c[r] += wc;
+                tot_c[r] += wc;
+            }
+        }
+        if (in) {
+            es[k + 1] = carry_e + (before_e + e);
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                cs[r * (bins_per_unit + 1) + k + 1] = carry_c[r] + (long long)(before_c[r] + c[r]);
+        }
         carry_e += tot_e;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            long long v = c[r];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const long long o = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane >= d)
-                    v += o;
-            }
-            if (lane == 31)
-                s_l[wid] = v;
-            __syncthreads();
-            long long before = 0, tot = 0;
-#pragma unroll
-            for (int q = 0; q < NW; q++) {
-                if (q < wid)
-                    before += s_l[q];
-                tot += s_l[q];
-            }
-            if (in)
-                cs[r * (bins_per_unit + 1) + k + 1] = carry_c[r] + before + v;
-            carry_c[r] += tot;
-            __syncthreads();
-        }
+        for (int r = 0; r < 4; r++)
+            carry_c[r] += tot_c[r];
     }
     __syncthreads();
     // the search: energy ranges a..d, time scales longest first; the first combination (in that order) with
     // a window at or above the threshold wins, at its first window.  The prefix sums of a chunk of windows
     // (+ the longest window span) are staged in shared memory; all time scales of a range share the
     // background window of a given i.
-    __shared__ double s_e[TRIG_CH + TRIG_SPAN + 1];
+    __shared__ float s_ef[TRIG_CH + TRIG_SPAN + 1];     // exposure prefix relative to the chunk start, fp32
     __shared__ int s_c[TRIG_CH + TRIG_SPAN + 1];
     __shared__ long long s_hit[10];
     const int n_scales[4] = {10, 10, 9, 4};
@@ -248,6 +266,9 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
     bool found = false;
     // the staged layout needs n_bkg + longest gap + n_src <= TRIG_SPAN: true for the reference's constants
     const bool staged_ok = (n_bkg + 512 + n_src <= TRIG_SPAN) && n_bkg > 0 && n_src > 0;
+    const bool pre_params_ok = (thr >= 1.0) && (thr < 1e15) && (n_src <= n_bkg);
+    const float thr2f = (float)thr2;
+    const float min_eb = 0.25f * (float)((double)n_bkg * dt), min_ex = 0.25f * (float)((double)n_src * dt);
     for (int r = 0; r < 4 && !found && staged_ok; r++) {
         const int64_t *cr = cs + r * (bins_per_unit + 1);
         if (cr[nb] == 0)                                                  // `if sum(counts) == 0: continue`
@@ -260,22 +281,43 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
             __syncthreads();
             const int64_t hi = min(nb, c0 + TRIG_CH + TRIG_SPAN);
             const long long cbase = cr[c0];
+            const double ebase = es[c0];
             for (int64_t k = c0 + threadIdx.x; k <= hi; k += NT) {
-                s_e[k - c0] = es[k];
+                s_ef[k - c0] = (float)(es[k] - ebase);
                 s_c[k - c0] = (int)(cr[k] - cbase);
             }
+            // fp32 prefilter (see below) needs exact int -> float counts and a sane threshold / window pair
+            const bool use_pre = pre_params_ok && (cr[hi] - cbase) < (1ll << 24);
             __syncthreads();
             for (int64_t i = c0 + threadIdx.x; i < min(c0 + (int64_t)TRIG_CH, n_i_max); i += NT) {
                 const int li = (int)(i - c0);
-                const double eb = s_e[li + n_bkg] - s_e[li];
-                const double B = (double)(s_c[li + n_bkg] - s_c[li]);
+                const int Bi = s_c[li + n_bkg] - s_c[li];
+                const float ebf = s_ef[li + n_bkg] - s_ef[li], Bf = (float)Bi;
+                const bool pre_i = use_pre && Bi > 0 && ebf > min_eb;
+                const double B = (double)Bi;
                 for (int sidx = 0; sidx < ns; sidx++) {
                     const int64_t n_gap = (int64_t)1 << (ns - 1 - sidx);
                     if (i >= nb - (n_bkg + n_gap + n_src))                // i + span < len(stops)
                         continue;
                     const int ls = li + (int)(n_bkg + n_gap);
-                    const double ex = s_e[ls + n_src] - s_e[ls];
-                    const double S = (double)(s_c[ls + n_src] - s_c[ls]);
+                    const int Si = s_c[ls + n_src] - s_c[ls];
+                    if (pre_i) {
+                        // Nearly every window is far below the threshold: decide that in fp32 (full rate, no
+                        // 64-bit conversions).  A hit needs d = S eb - B ex >= thr sqrt(B ex eb); the fp32 value of
+                        // d is off by at most ~3e-6 (S eb + B ex), i.e. by < 2.5 % of d for any window that could
+                        // fire (counts < 2^24, thr >= 1, source window not longer than the background window),
+                        // so d^2 < 0.9 thr^2 B ex eb is a certain miss.  Everything else takes the exact path.
+                        const float exf = s_ef[ls + n_src] - s_ef[ls];
+                        if (exf > min_ex) {
+                            const float d32 = (float)Si * ebf - Bf * exf;
+                            if (d32 <= 0.0f || d32 * d32 < 0.9f * (thr2f * Bf * exf * ebf))
+                                continue;
+                        }
+                    }
+                    const int64_t gs = i + n_bkg + n_gap;
+                    const double eb = es[i + n_bkg] - es[i];
+                    const double ex = es[gs + n_src] - es[gs];
+                    const double S = (double)Si;
                     // sig = (S - a B) / sqrt(a B), a = ex / eb: decided without the divisions when clear
                     bool hit;
                     const double d = S * eb - B * ex, rhs = thr2 * B * ex * eb;
