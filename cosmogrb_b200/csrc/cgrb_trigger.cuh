@@ -12,7 +12,9 @@
 // ((c / dt) * dt).astype(int), the swapped window arguments, the inclusive dead-time interval.
 // ==========================================================================================
 #define TRIG_TILE 2048
-#define TRIG_LOCAL 256          // bins a tile may span and still be accumulated in shared memory
+#define TRIG_LOCAL 512          // bins a tile may span and still be accumulated in shared memory (2048 events
+                                // at the 500 /s background are 256 bins of 16 ms)
+#define TRIG_EPT (TRIG_TILE / NT)   // events per thread
 #define TRIG_NCOMBO 33
 #define TRIG_NARR 6             // per-bin integer arrays: counts of the 4 ranges, events, overflow events
 #define TRIG_CH 2048            // windows per staged chunk of the search
@@ -23,6 +25,8 @@ struct TrigGrid {
     double t0, delta;
     int64_t n_edges;
     __device__ __forceinline__ double edge(int64_t i) const { return __dadd_rn(t0, __dmul_rn((double)i, delta)); }
+    // the same for an index known to fit 32 bits (a 32-bit integer-to-double conversion is 4x cheaper)
+    __device__ __forceinline__ double edge32(int i) const { return __dadd_rn(t0, __dmul_rn((double)i, delta)); }
 };
 __device__ __forceinline__ TrigGrid trig_grid(double tmin, double tmax, double dt)
 {
@@ -34,6 +38,9 @@ __device__ __forceinline__ TrigGrid trig_grid(double tmin, double tmax, double d
     return g;
 }
 
+// Shared-memory histogram of a tile, three packed words per bin (a tile holds 2048 events, so every 16-bit
+// field stays below 2 x 2048): word 0 = range a | range b << 16, word 1 = range c | range d << 16,
+// word 2 = events | overflow events << 16 (the two dead-time counters).
 __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__ units,
                                                  const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                  const int32_t *__restrict__ chan_bounds, double dt,
@@ -42,8 +49,9 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
                                                  const cgrb_counts_t *__restrict__ counts, int64_t bins_per_unit,
                                                  int32_t *__restrict__ bins)
 {
-    __shared__ int s_h[TRIG_NARR][TRIG_LOCAL];
-    __shared__ int64_t s_k0;
+    __shared__ int s_h[3][TRIG_LOCAL];
+    __shared__ uint8_t s_cm[256];           // channel -> membership mask of the four trigger ranges
+    __shared__ int s_k0;
     __shared__ int s_local;
     const int64_t w = blockIdx.x;
     if (w >= n_work)
@@ -56,89 +64,145 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
     const double *t = times_out + u->tot_off;
     const uint8_t *p = pha_out + u->tot_off;
     const TrigGrid g = trig_grid(t[0], t[n - 1], dt);
-    const int64_t nb = g.n_edges - 1;                   // np.histogram bins
-    if (nb < 1)
+    if (g.n_edges - 1 < 1 || g.n_edges > 0x7fffffff)    // (more bins than the host can have allocated)
         return;
+    const int nb = (int)(g.n_edges - 1);                // np.histogram bins
     const int64_t end = min(wk.start + (int64_t)TRIG_TILE, n);
     int32_t *ub = bins + (size_t)wk.unit * TRIG_NARR * bins_per_unit;
     const int32_t *cb = chan_bounds + 8 * u->det;
 
     // bin of an event: edge[k] <= t < edge[k+1] (last bin closed), -1 beyond the last edge
     const double inv_delta = 1.0 / g.delta;
-    auto bin_of = [&](double tt) -> int64_t {
-        int64_t k = (int64_t)floor((tt - g.t0) * inv_delta);       // a guess; the exact edges decide
-        k = max((int64_t)0, min(k, nb - 1));
-        while (k > 0 && tt < g.edge(k))
+    const double last_edge = g.edge32(nb);
+    auto bin_of = [&](double tt) -> int {
+        const double q = (tt - g.t0) * inv_delta;           // a guess; the exact edges decide
+        int k = (q < (double)(nb - 1)) ? (int)q : nb - 1;
+        k = max(0, k);
+        while (k > 0 && tt < g.edge32(k))
             k--;
-        while (k < nb - 1 && tt >= g.edge(k + 1))
+        while (k < nb - 1 && tt >= g.edge32(k + 1))
             k++;
-        if (tt > g.edge(nb))
+        if (tt > last_edge)
             return -1;
         return k;
     };
+    // this thread's events (loads issued together)
+    double tt[TRIG_EPT];
+    int cc[TRIG_EPT];
+#pragma unroll
+    for (int r = 0; r < TRIG_EPT; r++) {
+        const int64_t i = wk.start + r * NT + threadIdx.x;
+        const bool in = i < end;
+        tt[r] = in ? t[i] : 0.0;
+        cc[r] = in ? (int)p[i] : -1;
+    }
     if (threadIdx.x == 0) {
-        const int64_t ka = bin_of(t[wk.start]);
-        int64_t kb = bin_of(t[end - 1]);
+        const int ka = bin_of(t[wk.start]);
+        int kb = bin_of(t[end - 1]);
         if (kb < 0)
             kb = nb - 1;
-        s_k0 = (ka < 0) ? nb : max((int64_t)0, ka - 1);         // one spare bin below: inclusive dead-time edge
+        s_k0 = (ka < 0) ? nb : max(0, ka - 1);          // one spare bin below: inclusive dead-time edge
         s_local = (ka >= 0 && kb - s_k0 < TRIG_LOCAL) ? 1 : 0;
     }
-    for (int j = threadIdx.x; j < TRIG_NARR * TRIG_LOCAL; j += NT)
+    {
+        const int c = threadIdx.x;                      // NT == 256 channels values of a byte
+        int m = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            m |= (c > cb[2 * r] && c < cb[2 * r + 1]) ? (1 << r) : 0;
+        s_cm[c] = (uint8_t)m;
+    }
+    for (int j = threadIdx.x; j < 3 * TRIG_LOCAL; j += NT)
         (&s_h[0][0])[j] = 0;
     __syncthreads();
-    const int64_t k0 = s_k0;
+    const int k0 = s_k0;
     const bool local = s_local != 0;
-    for (int64_t i = wk.start + threadIdx.x; i < end; i += NT) {
-        const double tt = t[i];
-        const int c = p[i];
-        const int64_t k = bin_of(tt);
+#pragma unroll
+    for (int r = 0; r < TRIG_EPT; r++) {
+        const int c = cc[r];
+        if (c < 0)
+            continue;
+        const int k = bin_of(tt[r]);
         if (k < 0)
             continue;
-        const int ovf = (c == 127) ? 1 : 0;
+        const int m = s_cm[c];
+        const int add_a = (m & 1) | ((m & 2) << 15);
+        const int add_b = ((m >> 2) & 1) | ((m & 8) << 13);
+        const int add_c = 1 | ((c == 127) ? (1 << 16) : 0);
         // dead time: every bin with start <= t <= stop (an event on an inner edge belongs to both neighbours)
-        const bool also_prev = (k > 0) && (tt == g.edge(k));
+        const bool also_prev = (k > 0) && (tt[r] == g.edge32(k));
         if (local) {
-            const int l = (int)(k - k0);
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-                if (c > cb[2 * r] && c < cb[2 * r + 1])
-                    atomicAdd(&s_h[r][l], 1);
-            atomicAdd(&s_h[4][l], 1);
-            if (ovf)
-                atomicAdd(&s_h[5][l], 1);
-            if (also_prev) {
-                atomicAdd(&s_h[4][l - 1], 1);
-                if (ovf)
-                    atomicAdd(&s_h[5][l - 1], 1);
-            }
+            const int l = k - k0;
+            if (add_a)
+                atomicAdd(&s_h[0][l], add_a);
+            if (add_b)
+                atomicAdd(&s_h[1][l], add_b);
+            atomicAdd(&s_h[2][l], add_c);
+            if (also_prev)
+                atomicAdd(&s_h[2][l - 1], add_c);
         } else {
 #pragma unroll
-            for (int r = 0; r < 4; r++)
-                if (c > cb[2 * r] && c < cb[2 * r + 1])
-                    atomicAdd(ub + r * bins_per_unit + k, 1);
+            for (int q = 0; q < 4; q++)
+                if (m & (1 << q))
+                    atomicAdd(ub + q * bins_per_unit + k, 1);
             atomicAdd(ub + 4 * bins_per_unit + k, 1);
-            if (ovf)
+            if (c == 127)
                 atomicAdd(ub + 5 * bins_per_unit + k, 1);
             if (also_prev) {
                 atomicAdd(ub + 4 * bins_per_unit + k - 1, 1);
-                if (ovf)
+                if (c == 127)
                     atomicAdd(ub + 5 * bins_per_unit + k - 1, 1);
             }
         }
     }
     __syncthreads();
     if (local)
-        for (int j = threadIdx.x; j < TRIG_NARR * TRIG_LOCAL; j += NT) {
+        for (int j = threadIdx.x; j < 3 * TRIG_LOCAL; j += NT) {
             const int a = j / TRIG_LOCAL, l = j % TRIG_LOCAL;
             const int v = s_h[a][l];
-            if (v && k0 + l < nb)
-                atomicAdd(ub + a * bins_per_unit + k0 + l, v);
+            if (v && k0 + l < nb) {
+                const int lo = v & 0xffff, hi = (int)((unsigned)v >> 16);
+                if (lo)
+                    atomicAdd(ub + (2 * a) * bins_per_unit + k0 + l, lo);
+                if (hi)
+                    atomicAdd(ub + (2 * a + 1) * bins_per_unit + k0 + l, hi);
+            }
         }
 }
 
+// The exact significance test of one (window start i, gap) pair, from the 64-bit prefix sums in global memory
+// (rare: only windows the fp32 prefilter could not rule out).  sig = (S - a B) / sqrt(a B), a = ex / eb, decided
+// without the divisions when clear.  Returns 1 if sig >= thr; *razor is set when sig is within 1e-9 of thr.
+__device__ __noinline__ int trig_exact(const int64_t *__restrict__ cr, const double *__restrict__ es, int64_t i,
+                                       int64_t n_bkg, int64_t n_gap, int64_t n_src, double thr, int *razor)
+{
+    const int64_t gs = i + n_bkg + n_gap;
+    const double eb = es[i + n_bkg] - es[i], ex = es[gs + n_src] - es[gs];
+    const double B = (double)(cr[i + n_bkg] - cr[i]), S = (double)(cr[gs + n_src] - cr[gs]);
+    const double thr2 = thr * thr;
+    const double d = S * eb - B * ex, rhs = thr2 * B * ex * eb;
+    const double lhs = d * fabs(d);
+    if (B > 0.0 && eb > 0.0 && ex > 0.0 && thr > 0.0 && lhs < rhs * (1.0 - 1e-8))
+        return 0;
+    if (B > 0.0 && eb > 0.0 && ex > 0.0 && thr > 0.0 && lhs > rhs * (1.0 + 1e-8))
+        return 1;
+    const double alpha = ex / eb;
+    const double nbk = alpha * B;
+    const double sig = (S - nbk) / sqrt(nbk);
+    if (fabs(sig - thr) < 1e-9 * thr)
+        *razor = 1;
+    return sig >= thr ? 1 : 0;
+}
+
+#ifndef TRIG_PB
+#define TRIG_PB 4               // bins per thread and round in the prefix pass
+#endif
+#ifndef TRIG_EVAL_CTAS
+#define TRIG_EVAL_CTAS 4
+#endif
+
 // one CTA per unit: prefix sums over the bins, then the sliding-window search in the reference's order
-__global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restrict__ units, int n_units,
+__global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_unit_t *__restrict__ units, int n_units,
                                                   cgrb_trigger_par_t par, const double *__restrict__ times_out,
                                                   const cgrb_counts_t *__restrict__ counts, int64_t bins_per_unit,
                                                   const int32_t *__restrict__ bins, int64_t *__restrict__ csum,
@@ -166,8 +230,8 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
     const double dt = par.base_timescale;
     const TrigGrid g = trig_grid(t[0], t[n - 1], dt);
     const int64_t nb = g.n_edges - 1;
-    res.n_bins = (int32_t)max((int64_t)0, nb);
-    if (nb < 1) {
+    res.n_bins = (int32_t)max((int64_t)0, min(nb, (int64_t)0x7fffffff));
+    if (nb < 1 || nb >= 0x7fffffff) {
         if (threadIdx.x == 0)
             out[ui] = res;
         return;
@@ -177,9 +241,9 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
     double *es = esum + (size_t)ui * (bins_per_unit + 1);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // prefix sums: counts after the reference's float round trip, exposures = (stop - start) - dead time.
-    // One block scan per 256 bins carries all five quantities: warp scans by shuffles, the 8 warp totals
-    // exchanged through double-buffered shared memory (ONE barrier per round), the next round's bins
-    // prefetched before the barrier.  Fixed association, so the sums are reproducible.
+    // Every thread owns TRIG_PB consecutive bins per round (serial prefix inside), the thread totals of all
+    // five quantities go through one block scan: warp scans by shuffles, the 8 warp totals exchanged through
+    // double-buffered shared memory (one barrier per round).  Fixed association, so the sums are reproducible.
     __shared__ double s_pw[2][NW];
     __shared__ int s_pi[2][4][NW];
     long long carry_c[4] = {0, 0, 0, 0};
@@ -189,42 +253,51 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
             cs[r * (bins_per_unit + 1)] = 0;
         es[0] = 0.0;
     }
-    int raw[TRIG_NARR];
-#pragma unroll
-    for (int a = 0; a < TRIG_NARR; a++)
-        raw[a] = (threadIdx.x < nb) ? ub[a * bins_per_unit + threadIdx.x] : 0;
     int par_ = 0;
-    for (int64_t base = 0; base < nb; base += NT, par_ ^= 1) {
-        const int64_t k = base + threadIdx.x;
-        const bool in = k < nb;
-        int c[4];
-        double e = 0.0;
+    for (int64_t base = 0; base < nb; base += TRIG_PB * NT, par_ ^= 1) {
+        const int64_t kf = base + (int64_t)TRIG_PB * threadIdx.x;      // this thread's first bin
+        int c[4][TRIG_PB];
+        double e[TRIG_PB];
 #pragma unroll
         for (int r = 0; r < 4; r++)
-            c[r] = (int)(__dmul_rn(__ddiv_rn((double)raw[r], dt), dt));         // (rate * dt).astype(int)
-        if (in) {
-            const int na = raw[4], no = raw[5];
-            const double dead = __dadd_rn(__dmul_rn((double)(na - no), 2.0e-6), __dmul_rn((double)no, 10.0e-6));
-            e = __dadd_rn(__dadd_rn(g.edge(k + 1), -g.edge(k)), -dead);
+#pragma unroll
+            for (int j = 0; j < TRIG_PB; j++) {
+                const int raw = (kf + j < nb) ? ub[r * bins_per_unit + kf + j] : 0;
+                c[r][j] = raw ? (int)(__dmul_rn(__ddiv_rn((double)raw, dt), dt)) : 0;     // (rate * dt).astype(int)
+            }
+#pragma unroll
+        for (int j = 0; j < TRIG_PB; j++) {
+            e[j] = 0.0;
+            if (kf + j < nb) {
+                const int na = ub[4 * bins_per_unit + kf + j], no = ub[5 * bins_per_unit + kf + j];
+                const double dead = __dadd_rn(__dmul_rn((double)(na - no), 2.0e-6), __dmul_rn((double)no, 10.0e-6));
+                const int kk = (int)(kf + j);
+                e[j] = __dadd_rn(__dadd_rn(g.edge32(kk + 1), -g.edge32(kk)), -dead);
+            }
         }
-        // prefetch the next round
-        const int64_t kn = k + NT;
+        // serial inclusive prefix inside the thread
 #pragma unroll
-        for (int a = 0; a < TRIG_NARR; a++)
-            raw[a] = (kn < nb) ? ub[a * bins_per_unit + kn] : 0;
-        e = warp_incl_scan(e, lane);
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-            c[r] = warp_incl_scan_i(c[r], lane);
-        if (lane == 31) {
-            s_pw[par_][wid] = e;
+        for (int j = 1; j < TRIG_PB; j++) {
+            e[j] += e[j - 1];
 #pragma unroll
             for (int r = 0; r < 4; r++)
-                s_pi[par_][r][wid] = c[r];
+                c[r][j] += c[r][j - 1];
+        }
+        const double te = e[TRIG_PB - 1];
+        const double ie = warp_incl_scan(te, lane);
+        int ic[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            ic[r] = warp_incl_scan_i(c[r][TRIG_PB - 1], lane);
+        if (lane == 31) {
+            s_pw[par_][wid] = ie;
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                s_pi[par_][r][wid] = ic[r];
         }
         __syncthreads();
         double before_e = 0.0, tot_e = 0.0;
-        int before_c[4] = {0, 0, 0, 0}, tot_c[4] = {0, 0, 0, 0};     // one round: 256 bins, far below 2^31
+        int before_c[4] = {0, 0, 0, 0}, tot_c[4] = {0, 0, 0, 0};     // one round: 1024 bins, far below 2^31
 #pragma unroll
         for (int q = 0; q < NW; q++) {
             const double we = s_pw[par_][q];
@@ -239,36 +312,42 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
                 tot_c[r] += wc;
             }
         }
-        if (in) {
-            es[k + 1] = carry_e + (before_e + e);
+        const double off_e = carry_e + (before_e + (ie - te));
 #pragma unroll
-            for (int r = 0; r < 4; r++)
-                cs[r * (bins_per_unit + 1) + k + 1] = carry_c[r] + (long long)(before_c[r] + c[r]);
+        for (int j = 0; j < TRIG_PB; j++)
+            if (kf + j < nb)
+                es[kf + j + 1] = off_e + e[j];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const long long off_c = carry_c[r] + (long long)(before_c[r] + ic[r] - c[r][TRIG_PB - 1]);
+#pragma unroll
+            for (int j = 0; j < TRIG_PB; j++)
+                if (kf + j < nb)
+                    cs[r * (bins_per_unit + 1) + kf + j + 1] = off_c + c[r][j];
+            carry_c[r] += tot_c[r];
         }
         carry_e += tot_e;
-#pragma unroll
-        for (int r = 0; r < 4; r++)
-            carry_c[r] += tot_c[r];
     }
     __syncthreads();
     // the search: energy ranges a..d, time scales longest first; the first combination (in that order) with
     // a window at or above the threshold wins, at its first window.  The prefix sums of a chunk of windows
-    // (+ the longest window span) are staged in shared memory; all time scales of a range share the
-    // background window of a given i.
-    __shared__ float s_ef[TRIG_CH + TRIG_SPAN + 1];     // exposure prefix relative to the chunk start, fp32
-    __shared__ int s_c[TRIG_CH + TRIG_SPAN + 1];
+    // (+ the longest window span) are staged in shared memory as fp32 relative to the chunk start; all time
+    // scales of a range share the background window of a given i.
+    __shared__ float s_ef[TRIG_CH + TRIG_SPAN + 1];     // exposure prefix
+    __shared__ float s_cf[TRIG_CH + TRIG_SPAN + 1];     // count prefix (exact in fp32 below 2^24)
     __shared__ long long s_hit[10];
     const int n_scales[4] = {10, 10, 9, 4};
     const int64_t n_bkg = (int64_t)floor(par.background_duration / dt);
     const int64_t n_src = (int64_t)floor(par.pre_window / dt);          // the "source" window (swapped arguments)
-    const double thr = par.threshold, thr2 = thr * thr;
+    const double thr = par.threshold;
     int razor = 0;
     bool found = false;
     // the staged layout needs n_bkg + longest gap + n_src <= TRIG_SPAN: true for the reference's constants
     const bool staged_ok = (n_bkg + 512 + n_src <= TRIG_SPAN) && n_bkg > 0 && n_src > 0;
     const bool pre_params_ok = (thr >= 1.0) && (thr < 1e15) && (n_src <= n_bkg);
-    const float thr2f = (float)thr2;
+    const float thr2f = (float)(thr * thr);
     const float min_eb = 0.25f * (float)((double)n_bkg * dt), min_ex = 0.25f * (float)((double)n_src * dt);
+    const int nbk = (int)n_bkg, nsr = (int)n_src;
     for (int r = 0; r < 4 && !found && staged_ok; r++) {
         const int64_t *cr = cs + r * (bins_per_unit + 1);
         if (cr[nb] == 0)                                                  // `if sum(counts) == 0: continue`
@@ -282,60 +361,43 @@ __global__ void __launch_bounds__(NT, 4) k_trig_eval(const cgrb_unit_t *__restri
             const int64_t hi = min(nb, c0 + TRIG_CH + TRIG_SPAN);
             const long long cbase = cr[c0];
             const double ebase = es[c0];
+            // Nearly every window is far below the threshold: that is decided in fp32 (full rate, no 64-bit
+            // conversions).  A hit needs d = S eb - B ex >= thr sqrt(B ex eb); the fp32 value of d is off by at
+            // most ~3e-6 (S eb + B ex), i.e. by < 2.5 % of d for any window that could fire (counts < 2^24 so
+            // that they are exact in fp32, thr >= 1, source window not longer than the background window), so
+            // d^2 < 0.9 thr^2 B ex eb is a certain miss.  Everything else takes the exact path.
+            const bool use_pre = pre_params_ok && (cr[hi] - cbase) < (1ll << 24);
             for (int64_t k = c0 + threadIdx.x; k <= hi; k += NT) {
                 s_ef[k - c0] = (float)(es[k] - ebase);
-                s_c[k - c0] = (int)(cr[k] - cbase);
+                s_cf[k - c0] = (float)(int)min(cr[k] - cbase, (long long)(1 << 24));
             }
-            // fp32 prefilter (see below) needs exact int -> float counts and a sane threshold / window pair
-            const bool use_pre = pre_params_ok && (cr[hi] - cbase) < (1ll << 24);
             __syncthreads();
-            for (int64_t i = c0 + threadIdx.x; i < min(c0 + (int64_t)TRIG_CH, n_i_max); i += NT) {
-                const int li = (int)(i - c0);
-                const int Bi = s_c[li + n_bkg] - s_c[li];
-                const float ebf = s_ef[li + n_bkg] - s_ef[li], Bf = (float)Bi;
-                const bool pre_i = use_pre && Bi > 0 && ebf > min_eb;
-                const double B = (double)Bi;
-                for (int sidx = 0; sidx < ns; sidx++) {
-                    const int64_t n_gap = (int64_t)1 << (ns - 1 - sidx);
-                    if (i >= nb - (n_bkg + n_gap + n_src))                // i + span < len(stops)
+            const int i_end = (int)(min(c0 + (int64_t)TRIG_CH, n_i_max) - c0);
+            // window i with gap n_gap exists iff i + n_bkg + n_gap + n_src < nb, i.e. n_gap < room(i)
+            const int64_t room0 = nb - n_bkg - n_src - c0;
+            for (int li = threadIdx.x; li < i_end; li += NT) {
+                const int room = (int)min(room0 - li, (int64_t)1024);
+                const float Bf = s_cf[li + nbk] - s_cf[li];
+                const float ebf = s_ef[li + nbk] - s_ef[li];
+                const bool pre_i = use_pre && Bf > 0.0f && ebf > min_eb;
+                const float kf = 0.9f * thr2f * Bf * ebf;
+                const float *pc = s_cf + li + nbk, *pe = s_ef + li + nbk;
+                const float *pcs = pc + nsr, *pes = pe + nsr;
+#pragma unroll
+                for (int gx = 9; gx >= 0; gx--) {
+                    const int n_gap = 1 << gx;
+                    if (gx >= ns || n_gap >= room)
                         continue;
-                    const int ls = li + (int)(n_bkg + n_gap);
-                    const int Si = s_c[ls + n_src] - s_c[ls];
                     if (pre_i) {
-                        // Nearly every window is far below the threshold: decide that in fp32 (full rate, no
-                        // 64-bit conversions).  A hit needs d = S eb - B ex >= thr sqrt(B ex eb); the fp32 value of
-                        // d is off by at most ~3e-6 (S eb + B ex), i.e. by < 2.5 % of d for any window that could
-                        // fire (counts < 2^24, thr >= 1, source window not longer than the background window),
-                        // so d^2 < 0.9 thr^2 B ex eb is a certain miss.  Everything else takes the exact path.
-                        const float exf = s_ef[ls + n_src] - s_ef[ls];
-                        if (exf > min_ex) {
-                            const float d32 = (float)Si * ebf - Bf * exf;
-                            if (d32 <= 0.0f || d32 * d32 < 0.9f * (thr2f * Bf * exf * ebf))
-                                continue;
-                        }
+                        const float exf = pes[n_gap] - pe[n_gap];
+                        const float Sf = pcs[n_gap] - pc[n_gap];
+                        const float d32 = Sf * ebf - Bf * exf;
+                        if (exf > min_ex && (d32 <= 0.0f || d32 * d32 < kf * exf))
+                            continue;
                     }
-                    const int64_t gs = i + n_bkg + n_gap;
-                    const double eb = es[i + n_bkg] - es[i];
-                    const double ex = es[gs + n_src] - es[gs];
-                    const double S = (double)Si;
-                    // sig = (S - a B) / sqrt(a B), a = ex / eb: decided without the divisions when clear
-                    bool hit;
-                    const double d = S * eb - B * ex, rhs = thr2 * B * ex * eb;
-                    const double lhs = d * fabs(d);
-                    if (B > 0.0 && eb > 0.0 && ex > 0.0 && thr > 0.0 && lhs < rhs * (1.0 - 1e-8))
-                        hit = false;
-                    else if (B > 0.0 && eb > 0.0 && ex > 0.0 && thr > 0.0 && lhs > rhs * (1.0 + 1e-8))
-                        hit = true;
-                    else {
-                        const double alpha = ex / eb;
-                        const double nbk = alpha * B;
-                        const double sig = (S - nbk) / sqrt(nbk);
-                        if (fabs(sig - thr) < 1e-9 * thr)
-                            razor = 1;
-                        hit = sig >= thr;
-                    }
-                    if (hit && g.edge(i + n_bkg + n_gap) > -1.0)
-                        atomicMin(&s_hit[sidx], (long long)i);
+                    const int64_t i = c0 + li;
+                    if (trig_exact(cr, es, i, n_bkg, n_gap, n_src, thr, &razor) && g.edge(i + n_bkg + n_gap) > -1.0)
+                        atomicMin(&s_hit[ns - 1 - gx], (long long)i);
                 }
             }
             __syncthreads();
