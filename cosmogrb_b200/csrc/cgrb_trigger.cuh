@@ -20,13 +20,19 @@
 #define TRIG_CH 2048            // windows per staged chunk of the search
 #define TRIG_SPAN 1832          // >= background (1062) + longest gap (512) + source (250) bins
 
+// exact (double)i for 0 <= i < 2^32 without the quarter-rate I2F.F64: 2^52 + i is representable, subtract 2^52
+__device__ __forceinline__ double trig_u2d(unsigned i)
+{
+    return __hiloint2double(0x43300000, (int)i) - 4503599627370496.0;
+}
+
 // np.arange(tmin, tmax, dt): length and the fill rule  edge[i] = start + i * (fl(start + dt) - start)
 struct TrigGrid {
     double t0, delta;
     int64_t n_edges;
     __device__ __forceinline__ double edge(int64_t i) const { return __dadd_rn(t0, __dmul_rn((double)i, delta)); }
-    // the same for an index known to fit 32 bits (a 32-bit integer-to-double conversion is 4x cheaper)
-    __device__ __forceinline__ double edge32(int i) const { return __dadd_rn(t0, __dmul_rn((double)i, delta)); }
+    // the same for 0 <= i < 2^31, with the exact integer-to-double conversion done by one addition
+    __device__ __forceinline__ double edge32(int i) const { return __dadd_rn(t0, __dmul_rn(trig_u2d((unsigned)i), delta)); }
 };
 __device__ __forceinline__ TrigGrid trig_grid(double tmin, double tmax, double dt)
 {
@@ -86,6 +92,13 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
             return -1;
         return k;
     };
+    // Fast path: q = (t - t0) / delta differs from the position among the floating-point edges by a few ulps of
+    // the largest time, so when its fractional part is farther than `eps` from 0 and 1 the bin is floor(q) and
+    // the event is on no edge -- no integer <-> double conversions (quarter-rate on the SM), the floor comes
+    // from the 2^52 trick.  The rare event near an edge (or outside the interior bins) takes bin_of.
+    const double eps = fma((fabs(g.t0) + fabs(last_edge)) * inv_delta, 64.0 * 2.220446049250313e-16, 1e-9);
+    const bool fast_ok = eps < 0.25 && nb > 2;
+    const double MAGIC = 6755399441055744.0;                // 2^52 + 2^51
     // this thread's events (loads issued together)
     double tt[TRIG_EPT];
     int cc[TRIG_EPT];
@@ -122,15 +135,30 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
         const int c = cc[r];
         if (c < 0)
             continue;
-        const int k = bin_of(tt[r]);
-        if (k < 0)
-            continue;
+        int k;
+        bool also_prev = false;
+        {
+            const double q = (tt[r] - g.t0) * inv_delta;
+            const double m = q + MAGIC;
+            k = __double2loint(m);                          // round-to-nearest(q) for 0 <= q < 2^31
+            double fr = q - (m - MAGIC);                    // in [-0.5, 0.5]
+            if (fr < 0.0) {
+                k--;
+                fr += 1.0;
+            }
+            if (!(fast_ok && fr > eps && fr < 1.0 - eps && q > 1.0 && q < (double)(nb - 1))) {
+                k = bin_of(tt[r]);
+                if (k < 0)
+                    continue;
+                also_prev = (k > 0) && (tt[r] == g.edge32(k));
+            }
+        }
         const int m = s_cm[c];
         const int add_a = (m & 1) | ((m & 2) << 15);
         const int add_b = ((m >> 2) & 1) | ((m & 8) << 13);
         const int add_c = 1 | ((c == 127) ? (1 << 16) : 0);
-        // dead time: every bin with start <= t <= stop (an event on an inner edge belongs to both neighbours)
-        const bool also_prev = (k > 0) && (tt[r] == g.edge32(k));
+        // dead time: every bin with start <= t <= stop (an event on an inner edge belongs to both neighbours:
+        // `also_prev`, only possible on the exact path)
         if (local) {
             const int l = k - k0;
             if (add_a)
@@ -194,6 +222,7 @@ __device__ __noinline__ int trig_exact(const int64_t *__restrict__ cr, const dou
     return sig >= thr ? 1 : 0;
 }
 
+#define TRIG_LOSS_N 4096
 #ifndef TRIG_PB
 #define TRIG_PB 4               // bins per thread and round in the prefix pass
 #endif
@@ -246,6 +275,16 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     // double-buffered shared memory (one barrier per round).  Fixed association, so the sums are reproducible.
     __shared__ double s_pw[2][NW];
     __shared__ int s_pi[2][4][NW];
+    // (c / dt) * dt truncated loses one count for a fixed set of c: one bit per c < 4096, built once per CTA
+    // (16 divisions per thread instead of 4 per bin; 64-bit conversions and divisions are quarter-rate)
+    __shared__ unsigned s_loss[TRIG_LOSS_N / 32];
+    if (threadIdx.x < TRIG_LOSS_N / 32)
+        s_loss[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int c = threadIdx.x; c < TRIG_LOSS_N; c += NT)
+        if ((int)(__dmul_rn(__ddiv_rn((double)c, dt), dt)) < c)
+            atomicOr(&s_loss[c >> 5], 1u << (c & 31));
+    __syncthreads();
     long long carry_c[4] = {0, 0, 0, 0};
     double carry_e = 0.0;
     if (threadIdx.x == 0) {
@@ -263,14 +302,17 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
 #pragma unroll
             for (int j = 0; j < TRIG_PB; j++) {
                 const int raw = (kf + j < nb) ? ub[r * bins_per_unit + kf + j] : 0;
-                c[r][j] = raw ? (int)(__dmul_rn(__ddiv_rn((double)raw, dt), dt)) : 0;     // (rate * dt).astype(int)
+                // (rate * dt).astype(int)
+                c[r][j] = ((unsigned)raw < TRIG_LOSS_N) ? raw - (int)((s_loss[raw >> 5] >> (raw & 31)) & 1u)
+                                                       : (int)(__dmul_rn(__ddiv_rn((double)raw, dt), dt));
             }
 #pragma unroll
         for (int j = 0; j < TRIG_PB; j++) {
             e[j] = 0.0;
             if (kf + j < nb) {
                 const int na = ub[4 * bins_per_unit + kf + j], no = ub[5 * bins_per_unit + kf + j];
-                const double dead = __dadd_rn(__dmul_rn((double)(na - no), 2.0e-6), __dmul_rn((double)no, 10.0e-6));
+                const double dead = __dadd_rn(__dmul_rn(trig_u2d((unsigned)(na - no)), 2.0e-6),
+                                              __dmul_rn(trig_u2d((unsigned)no), 10.0e-6));
                 const int kk = (int)(kf + j);
                 e[j] = __dadd_rn(__dadd_rn(g.edge32(kk + 1), -g.edge32(kk)), -dead);
             }
@@ -367,9 +409,29 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
             // that they are exact in fp32, thr >= 1, source window not longer than the background window), so
             // d^2 < 0.9 thr^2 B ex eb is a certain miss.  Everything else takes the exact path.
             const bool use_pre = pre_params_ok && (cr[hi] - cbase) < (1ll << 24);
-            for (int64_t k = c0 + threadIdx.x; k <= hi; k += NT) {
-                s_ef[k - c0] = (float)(es[k] - ebase);
-                s_cf[k - c0] = (float)(int)min(cr[k] - cbase, (long long)(1 << 24));
+            {
+                // loads batched four deep: the staging is latency-bound otherwise
+                const int n_st = (int)(hi - c0) + 1;
+                const double *ep = es + c0;
+                const int64_t *cp = cr + c0;
+                for (int k = threadIdx.x; k < n_st; k += 4 * NT) {
+                    double ev[4];
+                    long long cv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int kk = min(k + q * NT, n_st - 1);
+                        ev[q] = ep[kk];
+                        cv[q] = cp[kk];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int kk = k + q * NT;
+                        if (kk < n_st) {
+                            s_ef[kk] = (float)(ev[q] - ebase);
+                            s_cf[kk] = (float)(int)min(cv[q] - cbase, (long long)(1 << 24));
+                        }
+                    }
+                }
             }
             __syncthreads();
             const int i_end = (int)(min(c0 + (int64_t)TRIG_CH, n_i_max) - c0);
