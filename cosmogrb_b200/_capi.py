@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 NBINS = 140
 NCHAN = 128
 NE_LAMBDA = 75
@@ -47,6 +47,7 @@ ST_TRIAL_CAP = 8
 ST_OUT_CAPACITY = 16
 ST_ENVELOPE = 32
 ST_DEADTIME_CHAIN = 64
+ST_MAJORANT = 128
 
 UNIT_NO_SOURCE = 1
 UNIT_NO_BACKGROUND = 2
@@ -126,6 +127,7 @@ EXPORTS = (
     "cgrb_energy_integrated_evolution",
     "cgrb_evolution",
     "cgrb_fmax",
+    "cgrb_thin_cum_bytes",
     "cgrb_thin_tables",
     "cgrb_sample_events",
     "cgrb_sample_energy",
@@ -170,8 +172,11 @@ def load():
     lib.cgrb_evolution.argtypes = [vp, i32, vp, i64, vp, i64, vp, vp]
     lib.cgrb_fmax.argtypes = [vp, vp, i32, i32, vp]
     rp = C.POINTER(RngDesc)
-    lib.cgrb_thin_tables.argtypes = [vp, vp, i32, vp, i64, vp, vp]
-    lib.cgrb_sample_events.argtypes = [vp, vp, i32, vp, i64, vp, i32, rp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_thin_cum_bytes.argtypes = [i64]
+    lib.cgrb_thin_cum_bytes.restype = i64
+    lib.cgrb_thin_tables.argtypes = [vp, vp, i32, vp, i64, vp, vp, i64, vp]
+    lib.cgrb_sample_events.argtypes = [vp, vp, i32, vp, i64, vp, i32, rp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64,
+                                       vp, vp]
     lib.cgrb_sample_energy.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, vp, vp, vp, vp]
     lib.cgrb_energy_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_energy_workspace_bytes.restype = i64
@@ -191,7 +196,8 @@ def load():
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count", "cgrb_energy_workspace_bytes",
-                        "cgrb_merge_dead_time_workspace_bytes", "cgrb_gbm_trigger_workspace_bytes"):
+                        "cgrb_merge_dead_time_workspace_bytes", "cgrb_gbm_trigger_workspace_bytes",
+                        "cgrb_thin_cum_bytes"):
             fn.restype = i32
     if lib.cgrb_abi_version() != ABI_VERSION:
         raise EngineUnavailable(

@@ -41,6 +41,8 @@ _DEFAULTS = {
         "interp_extrap": "linear",
         # photon-energy sampler under Philox: "envelope" (tight exact envelope) | "literal"
         "energy_sampler": "envelope",
+        # source-time proposal under Philox: "majorant" (piecewise bound from the squeeze table) | "literal"
+        "thinning": "majorant",
         # upper bound on CPL rejection trials per photon
         "max_trials": 1 << 22,
         # GBM dead time: "reference" (literal _gbm_dead_time, gbm_lightcurve.py:80-115) | "physical"

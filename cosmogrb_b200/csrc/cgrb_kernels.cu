@@ -249,14 +249,20 @@ int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int inter
     return check_launch("cgrb_fmax");
 }
 
+int64_t cgrb_thin_cum_bytes(int64_t n_nodes_total) { return 12 * (n_nodes_total > 0 ? n_nodes_total : 0) + 8; }
+
 int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work,
-                     int64_t n_work, double *d_thin_tab, void *stream)
+                     int64_t n_work, double *d_thin_tab, void *d_thin_cum, int64_t n_nodes_total, void *stream)
 {
-    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_thin_tab)
+    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_thin_tab ||
+        (d_thin_cum && n_nodes_total <= 0))
         return fail(CGRB_E_BADARG, "cgrb_thin_tables: bad argument%s");
     cudaStream_t s = (cudaStream_t)stream;
     LAUNCH("k_thin_nodes", s, k_thin_nodes<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, d_thin_tab));
     LAUNCH("k_thin_margins", s, k_thin_margins<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_thin_tab));
+    if (d_thin_cum)
+        LAUNCH("k_thin_cum", s, k_thin_cum<<<n_units, NT, 0, s>>>(d_units, n_units, d_thin_tab, (double *)d_thin_cum,
+                                                                  n_nodes_total));
     return check_launch("cgrb_thin_tables");
 }
 
@@ -275,7 +281,8 @@ int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
                        const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
                        int interp_extrap, const cgrb_rng_t *rng, double *d_segsum, double *d_segstart,
                        int32_t *d_segcount, double *d_stage, double *d_times_src, double *d_cand_times,
-                       uint8_t *d_cand_accept, const double *d_thin_tab, cgrb_counts_t *d_counts, void *stream)
+                       uint8_t *d_cand_accept, const double *d_thin_tab, const void *d_thin_cum,
+                       int64_t n_nodes_total, cgrb_counts_t *d_counts, void *stream)
 {
     (void)interp_extrap;
     if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_segsum ||
@@ -286,12 +293,17 @@ int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
     int rc = check_rng(rng, "cgrb_sample_events");
     if (rc)
         return rc;
+    if (d_thin_cum && (!d_thin_tab || n_nodes_total <= 0))
+        return fail(CGRB_E_BADARG, "cgrb_sample_events: the majorant table needs the squeeze table and its node count%s");
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH("k_gap_prefix<0>", s, k_gap_prefix<0><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng, d_segsum, d_stage, d_counts));
+    const double *cum = (rng->mode == 0) ? (const double *)d_thin_cum : nullptr;
+    LAUNCH("k_gap_prefix<0>", s, k_gap_prefix<0><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng, d_segsum, d_stage, d_counts,
+                                                                                 cum, n_nodes_total));
     LAUNCH("k_seg_scan<0>", s, k_seg_scan<0><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
-                                                           d_segstart, d_counts));
+                                                           d_segstart, d_counts, *rng, cum));
     LAUNCH("k_source_thin", s, k_source_thin<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng, d_segstart,
-                                                  d_segcount, d_stage, d_cand_times, d_cand_accept, d_thin_tab, d_counts));
+                                                  d_segcount, d_stage, d_cand_times, d_cand_accept, d_thin_tab, d_counts,
+                                                  cum, n_nodes_total));
     LAUNCH("k_source_gather", s, k_source_gather<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_unit_work_begin, d_segcount,
                                                     d_stage, d_times_src, d_counts));
     return check_launch("cgrb_sample_events");
@@ -414,9 +426,10 @@ int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int
         chan = *rng_chan;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH("k_gap_prefix<1>", s, k_gap_prefix<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_times_bkg, d_counts));
+    LAUNCH("k_gap_prefix<1>", s, k_gap_prefix<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_times_bkg, d_counts,
+                                                                                 nullptr, 0));
     LAUNCH("k_seg_scan<1>", s, k_seg_scan<1><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
-                                                           d_segstart, d_counts));
+                                                           d_segstart, d_counts, *rng_time, nullptr));
     LAUNCH("k_background", s, k_background<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng_time, chan, d_segstart,
                                                  d_times_bkg, d_pha_bkg, d_counts));
     return check_launch("cgrb_sample_background");

@@ -8,11 +8,96 @@
 // totals into segment start times, pass 3 adds the start time -- no gap is drawn twice.
 // The summation order is fixed (pairs, tiles of THIN_TILE, segments of CGRB_SEG), so times are reproducible.
 // ==========================================================================================
+// ------------------------------------------------------------------------------------------
+// Piecewise-constant majorant of the thinning (Philox mode only; injected uniforms replay the reference's
+// single-fmax loop).  The reference proposes candidates at the constant rate fmax over the whole window and
+// keeps each with probability min(p, 1), p(t) = lambda(t) / fmax (cpl_functions.py:134-188): for a pulse that
+// fills a fraction of the window nearly all candidates are wasted (8 % acceptance over the §8d population).
+// The squeeze table already bounds p on every cell of its uniform time grid: |p - linear interpolation| <=
+// margin, so P_j = min(1, max(p_j, p_j+1) + margin_j) >= min(p, 1) on cell j.  Candidates are drawn as a
+// unit-rate Poisson process in operational time tau = Lambda(t) = fmax * integral of P (the same stored
+// exponential gaps, with rate 1), mapped back through the piecewise-linear Lambda, and kept with probability
+// min(p, 1) / P_j: the accepted events are the same process, min(lambda, fmax), from Lambda_T candidates
+// instead of fmax * T.  `thin_cum`: per node the cumulative Lambda (double), then per node a search guide
+// (int32: the cell of tau = g * Lambda_T / (n - 1)).
+// ------------------------------------------------------------------------------------------
+struct ThinCum {
+    const double *L;        // [tab_n] cumulative operational time at the nodes
+    const int32_t *guide;   // [tab_n - 1]
+};
+__device__ __forceinline__ ThinCum thin_cum_of(const double *thin_cum, int64_t n_nodes_total, const cgrb_unit_t &u)
+{
+    ThinCum c;
+    c.L = thin_cum + u.tab_off;
+    c.guide = reinterpret_cast<const int32_t *>(thin_cum + n_nodes_total) + u.tab_off;
+    return c;
+}
+__device__ __forceinline__ bool unit_uses_majorant(const double *thin_cum, const cgrb_rng_t &rng, const cgrb_unit_t &u)
+{
+    return thin_cum != nullptr && rng.mode == 0 && u.tab_n >= 4 && !(u.flags & CGRB_UNIT_NO_SOURCE);
+}
+__device__ __forceinline__ double majorant_of(const double2 n0, const double2 n1)
+{
+    const double P = fmax(n0.x, n1.x) + n0.y;
+    return (P <= 1.0) ? fmax(P, 0.0) : 1.0;        // NaN / inf margins -> 1 (the reference's own ceiling)
+}
+// candidates a unit can need: N with S_N > Lambda_T, N ~ Lambda_T +- sqrt(Lambda_T)
+__device__ __forceinline__ double majorant_cap(double LT)
+{
+    return LT + 10.0 * sqrt(LT) + 64.0;
+}
+
+// one CTA per unit: cumulative majorant at the nodes (fixed association) and the search guide
+__global__ void __launch_bounds__(NT) k_thin_cum(const cgrb_unit_t *__restrict__ units, int n_units,
+                                                 const double *__restrict__ thin_tab, double *__restrict__ thin_cum,
+                                                 int64_t n_nodes_total)
+{
+    __shared__ double s_w[NW];
+    const int ui = blockIdx.x;
+    if (ui >= n_units)
+        return;
+    const cgrb_unit_t *u = units + ui;
+    const int n = (int)u->tab_n;
+    if (n < 4 || (u->flags & CGRB_UNIT_NO_SOURCE))
+        return;
+    const double2 *sq = reinterpret_cast<const double2 *>(thin_tab) + u->tab_off;
+    double *L = thin_cum + u->tab_off;
+    int32_t *guide = reinterpret_cast<int32_t *>(thin_cum + n_nodes_total) + u->tab_off;
+    const double scale = u->fmax * ((u->src_tstop - u->src_tstart) / (double)(n - 1));
+    double carry = 0.0;
+    if (threadIdx.x == 0)
+        L[0] = 0.0;
+    for (int base = 0; base < n - 1; base += NT) {
+        const int j = base + threadIdx.x;
+        const double v = (j < n - 1) ? scale * majorant_of(sq[j], sq[j + 1]) : 0.0;
+        double total;
+        const double incl = block_incl_scan(v, s_w, &total);
+        if (j < n - 1)
+            L[j + 1] = carry + incl;
+        carry = carry + total;
+    }
+    __syncthreads();
+    const double LT = carry;
+    for (int g = threadIdx.x; g < n - 1; g += NT) {
+        const double target = (double)g * LT / (double)(n - 1);
+        int lo = 0, hi = n - 1;                     // largest j in [0, n-2] with L[j] <= target
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (L[mid] <= target)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        guide[g] = lo;
+    }
+}
+
 template <int WHICH>  // 0 = source (prefix -> stage at src_off), 1 = background (prefix -> times_bkg at bkg_off + 1)
 __global__ void __launch_bounds__(NT) k_gap_prefix(const cgrb_unit_t *__restrict__ units,
                                                    const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                    cgrb_rng_t rng, double *__restrict__ segsum,
-                                                   double *__restrict__ prefix_out, cgrb_counts_t *counts)
+                                                   double *__restrict__ prefix_out, cgrb_counts_t *counts,
+                                                   const double *__restrict__ thin_cum, int64_t n_nodes_total)
 {
     __shared__ double s_w[NW];
     const int64_t w = blockIdx.x;
@@ -21,7 +106,17 @@ __global__ void __launch_bounds__(NT) k_gap_prefix(const cgrb_unit_t *__restrict
     const cgrb_work_t wk = work[w];
     const cgrb_unit_t *u = units + wk.unit;
     const int64_t cap = (WHICH == 0) ? u->src_cap : u->bkg_cap;
-    const double rate = (WHICH == 0) ? u->fmax : u->bkg_rate;
+    double rate = (WHICH == 0) ? u->fmax : u->bkg_rate;
+    if (WHICH == 0 && unit_uses_majorant(thin_cum, rng, *u)) {
+        // operational time: unit-rate gaps; segments beyond the candidates the unit can need are dead
+        rate = 1.0;
+        const double LT = thin_cum[u->tab_off + u->tab_n - 1];
+        if ((double)wk.start > majorant_cap(LT)) {
+            if (threadIdx.x == 0)
+                segsum[w] = INFINITY;
+            return;
+        }
+    }
     const double inv_f = 1.0 / rate;
     const uint32_t stage = (WHICH == 0) ? ST_SRC_TIME : ST_BKG;
     const uint32_t sid = u->stream_id;
@@ -59,15 +154,20 @@ template <int WHICH>
 __global__ void __launch_bounds__(128) k_seg_scan(const cgrb_unit_t *__restrict__ units, int n_units,
                                                   const int64_t *__restrict__ unit_work_begin,
                                                   const double *__restrict__ segsum,
-                                                  double *__restrict__ segstart, cgrb_counts_t *counts)
+                                                  double *__restrict__ segstart, cgrb_counts_t *counts,
+                                                  cgrb_rng_t rng, const double *__restrict__ thin_cum)
 {
     const int lane = threadIdx.x & 31;
     const int ui = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ui >= n_units)
         return;
     const cgrb_unit_t *u = units + ui;
-    const double tstart = (WHICH == 0) ? u->src_tstart : u->bkg_tstart;
-    const double tstop = (WHICH == 0) ? u->src_tstop : u->bkg_tstop;
+    double tstart = (WHICH == 0) ? u->src_tstart : u->bkg_tstart;
+    double tstop = (WHICH == 0) ? u->src_tstop : u->bkg_tstop;
+    if (WHICH == 0 && unit_uses_majorant(thin_cum, rng, *u)) {
+        tstart = 0.0;                                       // operational time runs over [0, Lambda_T]
+        tstop = thin_cum[u->tab_off + u->tab_n - 1];
+    }
     const int64_t b = unit_work_begin[ui], e = unit_work_begin[ui + 1];
     double t = tstart;
     for (int64_t s0 = b; s0 < e; s0 += 32) {
@@ -117,6 +217,52 @@ __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_uni
     return u2 <= lambda_exact(tab, u, t) / u.fmax;   // `if test <= p_test`
 }
 
+// Majorant mode: candidate at operational time tau -> cell j (guide + short walk over the cumulative table),
+// real time t inside the cell, acceptance with probability min(p(t), 1) / P_j by the same squeeze test.
+// *t_out receives the real time.  *violated is set if an exact evaluation finds p(t) above the cell's bound.
+__device__ __forceinline__ bool thin_accept_majorant(const LambdaTab *tab, const cgrb_unit_t &u,
+                                                     const double2 *__restrict__ sq, const ThinCum tc, double gscale,
+                                                     double h, double tau, double u2, double *t_out,
+                                                     long long *n_exact, bool *violated)
+{
+    const int n = (int)u.tab_n;
+    int j = __ldg(tc.guide + min(max((int)(tau * gscale), 0), n - 2));
+    double Lj = __ldg(tc.L + j), Lj1 = __ldg(tc.L + j + 1);
+    while (j < n - 2 && Lj1 <= tau) {
+        j++;
+        Lj = Lj1;
+        Lj1 = __ldg(tc.L + j + 1);
+    }
+    const double2 n0 = __ldg(sq + j), n1 = __ldg(sq + j + 1);
+    const double P = majorant_of(n0, n1);
+    const double wdt = Lj1 - Lj;                    // = fmax h P_j: expected candidates of the cell
+    double fr = 0.0;
+    if (wdt > 1e-30) {
+        double r = (double)__frcp_rn((float)wdt);   // 1 / wdt by two Newton steps (monotone map inside the cell)
+        r = r * (2.0 - wdt * r);
+        r = r * (2.0 - wdt * r);
+        fr = fmin(fmax((tau - Lj) * r, 0.0), 1.0);
+    } else if (wdt > 0.0)
+        fr = fmin(fmax((tau - Lj) / wdt, 0.0), 1.0);
+    const double tj = u.src_tstart + (double)j * h;
+    const double tj1 = (j == n - 2) ? u.src_tstop : u.src_tstart + (double)(j + 1) * h;
+    const double t = fmin(fma(fr, h, tj), tj1);
+    *t_out = t;
+    if (!(P > 0.0))
+        return false;
+    const double v = u2 * P;
+    const double pl = n0.x + (n1.x - n0.x) * fr;
+    if (v <= pl - n0.y)
+        return true;
+    if (v > pl + n0.y)
+        return false;
+    (*n_exact)++;
+    const double pe = lambda_exact(tab, u, t) / u.fmax;
+    if (P < 1.0 && pe > P * (1.0 + 1e-9))
+        *violated = true;
+    return v <= pe;
+}
+
 __global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict__ dtab,
                                                     const cgrb_unit_t *__restrict__ units,
                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
@@ -124,7 +270,8 @@ __global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict_
                                                     int32_t *__restrict__ segcount, double *stage,
                                                     double *__restrict__ cand_times,
                                                     uint8_t *__restrict__ cand_accept,
-                                                    const double *__restrict__ thin_tab, cgrb_counts_t *counts)
+                                                    const double *__restrict__ thin_tab, cgrb_counts_t *counts,
+                                                    const double *__restrict__ thin_cum, int64_t n_nodes_total)
 {
     __shared__ LambdaTab tab;
     __shared__ cgrb_unit_t u;
@@ -139,7 +286,11 @@ __global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict_
         u = units[wk.unit];
     __syncthreads();
     const double t0 = segstart[w];
-    if ((u.flags & CGRB_UNIT_NO_SOURCE) || t0 > u.src_tstop) {   // dead segment
+    // majorant mode: segment starts, running sums and the stop are in operational time until the acceptance test
+    const bool maj = unit_uses_majorant(thin_cum, rng, u);
+    const ThinCum tc = thin_cum_of(thin_cum, n_nodes_total, u);
+    const double stop = maj ? __ldg(tc.L + u.tab_n - 1) : u.src_tstop;
+    if ((u.flags & CGRB_UNIT_NO_SOURCE) || !(t0 <= stop)) {   // dead segment
         if (threadIdx.x == 0)
             segcount[w] = 0;
         return;
@@ -155,6 +306,9 @@ __global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict_
     const bool squeeze = thin_tab != nullptr && u.tab_n >= 4;
     const double2 *sq = reinterpret_cast<const double2 *>(thin_tab) + (squeeze ? u.tab_off : 0);
     const double sq_inv_h = squeeze ? (double)(u.tab_n - 1) / (u.src_tstop - u.src_tstart) : 0.0;
+    const double maj_h = maj ? (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1) : 0.0;
+    const double maj_gscale = (maj && stop > 0.0) ? (double)(u.tab_n - 1) / stop : 0.0;
+    bool violated = false;
     double *seg = stage + u.src_off + wk.start;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     long long n_exact = 0;
@@ -180,14 +334,22 @@ __global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict_
         const double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
         ta = fmax(ta, left);
         tb = fmax(tb, ta);
-        const bool va = in0 && (ta <= u.src_tstop);   // `if time > tstop: break`
-        const bool vb = in1 && (tb <= u.src_tstop);
+        const double tile_last = in1 ? tb : ta;     // (operational time in majorant mode)
+        const bool va = in0 && (ta <= stop);   // `if time > tstop: break`
+        const bool vb = in1 && (tb <= stop);
         bool aa = false, ab = false;
         if (va) {
             PairDraw d = pair_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, (wk.start + j0) >> 1, 1);
-            aa = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact);
-            if (vb)
-                ab = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact);
+            if (maj) {
+                const double tau_a = ta, tau_b = tb;
+                aa = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_a, d.a, &ta, &n_exact, &violated);
+                if (vb)
+                    ab = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_b, d.b, &tb, &n_exact, &violated);
+            } else {
+                aa = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact);
+                if (vb)
+                    ab = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact);
+            }
         }
         // ordered compaction: per-thread counts (0..2 accepted, 0..2 valid) packed in one int
         const int mine = (int)aa + (int)ab + (((int)va + (int)vb) << 16);
@@ -222,11 +384,13 @@ __global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict_
         seg_n += tile_acc;
         n_valid_total += tile_valid;
         if (threadIdx.x == NT - 1)
-            s_last = in1 ? tb : ta;
+            s_last = tile_last;
         __syncthreads();
         if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
             break;      // crossed tstop: everything later is beyond it
     }
+    if (violated)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_MAJORANT);
     {
         long long *s_ll = reinterpret_cast<long long *>(s_t);      // s_t is free now
         __syncthreads();

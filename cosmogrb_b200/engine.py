@@ -146,7 +146,7 @@ class Engine(object):
     """One engine per process and device."""
 
     def __init__(self, device=None, seed=DEFAULT_SEED, interp_extrap="linear", energy_sampler="envelope", squeeze=True,
-                 deadtime_mode="reference", deadtime_tau=2.6e-6, deadtime_tau_overflow=10e-6):
+                 deadtime_mode="reference", deadtime_tau=2.6e-6, deadtime_tau_overflow=10e-6, thinning="majorant"):
         torch = _torch()
         self.lib = _capi.load()
         if not torch.cuda.is_available():
@@ -163,6 +163,12 @@ class Engine(object):
         self.interp_extrap = interp_extrap
         self.energy_sampler = energy_sampler
         self.squeeze = bool(squeeze)
+        # candidate proposal of the source thinning under Philox: "majorant" (piecewise-constant bound built
+        # from the squeeze table: same point process, far fewer candidates) | "literal" (the reference's single
+        # fmax over the whole window).  Injected uniforms always replay the literal loop.
+        if thinning not in ("majorant", "literal"):
+            raise ValueError("thinning must be 'majorant' or 'literal'")
+        self.thinning = thinning
         # GBM dead-time model: "reference" = literal _gbm_dead_time (gbm_lightcurve.py:80-115), "physical" =
         # non-paralyzable window after EVERY kept event
         self.set_deadtime(deadtime_mode, deadtime_tau, deadtime_tau_overflow)
@@ -498,15 +504,20 @@ class Engine(object):
             t["cand_times"] = cand_t = self.empty(b.n_src_slots, torch.float64)
             t["cand_accept"] = cand_a = torch.zeros(max(b.n_src_slots, 1), dtype=torch.uint8, device=self.device)
         desc = self._rng_desc(rng, b, "thin")
-        thin_tab = None
+        thin_tab = thin_cum = None
         if b.n_tab_nodes > 0:
             # rebuilt on every call (it is part of the sampling work, ~1/8 of a lambda per candidate)
             w4, dw4, _ = self._work(b, 4, 256)
             t["thin_tab"] = thin_tab = self.empty(2 * b.n_tab_nodes, torch.float64)
+            t.pop("thin_cum", None)
+            if self.thinning == "majorant" and not isinstance(rng, Injected):
+                t["thin_cum"] = thin_cum = self.empty(self.lib.cgrb_thin_cum_bytes(b.n_tab_nodes), torch.uint8)
             _capi.check(self.lib.cgrb_thin_tables(b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units,
-                                                  dw4.data_ptr(), len(w4), thin_tab.data_ptr(), self.stream),
+                                                  dw4.data_ptr(), len(w4), thin_tab.data_ptr(),
+                                                  thin_cum.data_ptr() if thin_cum is not None else None,
+                                                  b.n_tab_nodes, self.stream),
                         "cgrb_thin_tables")
-            self.launches += 2
+            self.launches += 2 + (thin_cum is not None)
         _capi.check(
             self.lib.cgrb_sample_events(
                 b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), nw, dwb.data_ptr(),
@@ -514,9 +525,26 @@ class Engine(object):
                 t["segstart"].data_ptr(), t["segcount"].data_ptr(), t["stage"].data_ptr(),
                 t["times_src"].data_ptr(), cand_t.data_ptr() if want_candidates else None,
                 cand_a.data_ptr() if want_candidates else None,
-                thin_tab.data_ptr() if thin_tab is not None else None, b.d_counts.data_ptr(), self.stream),
+                thin_tab.data_ptr() if thin_tab is not None else None,
+                thin_cum.data_ptr() if thin_cum is not None else None, b.n_tab_nodes,
+                b.d_counts.data_ptr(), self.stream),
             "cgrb_sample_events")
         self.launches += 4
+
+    def majorant_totals(self, b):
+        """Expected candidates per unit under the majorant proposal (Lambda_T = fmax x integral of the
+        piecewise bound), NaN for units without a table; None if the last ``sample_events`` used the literal
+        proposal."""
+        if "thin_cum" not in b.t:
+            return None
+        torch = _torch()
+        L = b.t["thin_cum"][:8 * b.n_tab_nodes].view(torch.float64)
+        out = np.full(b.n_units, np.nan)
+        has = b.units["tab_n"] >= 4
+        last = (b.units["tab_off"] + b.units["tab_n"] - 1)[has]
+        if has.any():
+            out[has] = L[torch.as_tensor(last.astype(np.int64), device=self.device)].cpu().numpy()
+        return out
 
     def sample_energy(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, want_trials=False, sampler=None,
                       fold=False, want_energy=True):
@@ -731,7 +759,8 @@ class Engine(object):
         if len(bad):
             names = {1: "source capacity", 2: "background capacity", 4: "injected uniforms exhausted",
                      8: "trial cap", 16: "output capacity", 32: "energy envelope violated",
-                     64: "physical dead time: event rate x window too high (chain > 4096 events)"}
+                     64: "physical dead time: event rate x window too high (chain > 4096 events)",
+                     128: "thinning majorant violated"}
             ui = int(bad[0])
             st = int(c["status"][ui])
             what = ", ".join(v for k, v in names.items() if st & k)
@@ -905,7 +934,8 @@ def get_engine(**kw):
                         energy_sampler=cosmogrb_config["engine"]["energy_sampler"],
                         deadtime_mode=cosmogrb_config["engine"]["deadtime_mode"],
                         deadtime_tau=cosmogrb_config["engine"]["deadtime_tau"],
-                        deadtime_tau_overflow=cosmogrb_config["engine"]["deadtime_tau_overflow"])
+                        deadtime_tau_overflow=cosmogrb_config["engine"]["deadtime_tau_overflow"],
+                        thinning=cosmogrb_config["engine"]["thinning"])
             opts.update(kw)
             _engine = Engine(**opts)
         return _engine

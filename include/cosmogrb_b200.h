@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CGRB_ABI_VERSION 4
+#define CGRB_ABI_VERSION 5
 
 /* error codes */
 #define CGRB_OK 0
@@ -45,6 +45,7 @@ extern "C" {
 #define CGRB_ST_TRIAL_CAP 8u         /* energy rejection hit max_trials                     */
 #define CGRB_ST_OUT_CAPACITY 16u     /* an output buffer was too small                      */
 #define CGRB_ST_ENVELOPE 32u         /* energy envelope failed to dominate the target (bug)  */
+#define CGRB_ST_MAJORANT 128u        /* thinning majorant failed to dominate lambda(t) (bug)            */
 #define CGRB_ST_DEADTIME_CHAIN 64u   /* physical dead time: > 4096 consecutive events closer than the longest window */
 
 /* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
@@ -193,9 +194,16 @@ int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int inter
  * accepts a candidate outright if u2 <= p_lin - m, rejects it if u2 > p_lin + m, and evaluates
  * lambda(t) exactly (the reference's 75-point trapezoid) only in between, so the accept/reject
  * decisions are those of the exact test.  d_thin_tab: 2 doubles per node (p, m), sum(tab_n) nodes.
- * Work list: which=4, chunk=256. */
+ * Work list: which=4, chunk=256.
+ *
+ * d_thin_cum (optional, NULL = not built): the piecewise-constant MAJORANT of the same table for
+ * cgrb_sample_events under Philox -- cgrb_thin_cum_bytes(n_nodes_total) bytes: per node the cumulative
+ * operational time Lambda_k = fmax * sum_{j<k} P_j h, P_j = min(1, max(p_j, p_j+1) + m_j) >= min(p, 1) on
+ * cell j, then per node an int32 search guide.  n_nodes_total = sum(tab_n) (units' tab_off index both). */
+int64_t cgrb_thin_cum_bytes(int64_t n_nodes_total);
 int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
-                     const cgrb_work_t *d_work, int64_t n_work, double *d_thin_tab, void *stream);
+                     const cgrb_work_t *d_work, int64_t n_work, double *d_thin_tab, void *d_thin_cum,
+                     int64_t n_nodes_total, void *stream);
 
 /* SourceFunction.sample_events (cpl_source.py:98-114; numba cpl_functions.py:134-188,
  * cpl_constant_functions.py:65-105).  Work list: which=0, chunk=CGRB_SEG.
@@ -204,13 +212,19 @@ int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_uni
  *   d_times_src [sum (src_cap+1)]: output, unit u at src_off; entry 0 is tstart
  *   d_cand_times / d_cand_accept: optional (may be NULL) per-candidate outputs at src_off
  *   d_thin_tab: squeeze table from cgrb_thin_tables, or NULL (every candidate evaluated exactly)
+ *   d_thin_cum: majorant table from cgrb_thin_tables, or NULL.  With it, and only under Philox (injected
+ *       uniforms always replay the reference's loop), units with a table draw their candidates as a unit-rate
+ *       Poisson process in operational time, map them back through Lambda and keep each with probability
+ *       min(p, 1) / P_j: the same point process min(lambda, fmax) as the reference's single-fmax thinning
+ *       from integral(P) fmax candidates instead of fmax T.  CGRB_ST_MAJORANT flags a violated bound.
  * counts: n_candidates, n_src, status. */
 int cgrb_sample_events(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                        const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
                        int interp_extrap, const cgrb_rng_t *rng,
                        double *d_segsum, double *d_segstart, int32_t *d_segcount, double *d_stage,
                        double *d_times_src, double *d_cand_times, uint8_t *d_cand_accept,
-                       const double *d_thin_tab, cgrb_counts_t *d_counts, void *stream);
+                       const double *d_thin_tab, const void *d_thin_cum, int64_t n_nodes_total,
+                       cgrb_counts_t *d_counts, void *stream);
 
 /* SourceFunction.sample_energy (cpl_source.py:116-132; numba cpl_functions.py:191-286).
  * Work list: which=3 with any chunk size (photon index space, bounded by counts.n_src).

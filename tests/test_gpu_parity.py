@@ -325,7 +325,7 @@ def test_squeeze_changes_no_decision(params):
 
     out = {}
     for squeeze in (True, False):
-        eng = Engine(squeeze=squeeze)
+        eng = Engine(squeeze=squeeze, thinning="literal")     # the reference's single-fmax proposal
         rsp = h.response("n0")
         b = eng.new_batch(h.unit(**params), [rsp.device_table(h.bkg_weights("n0"), "linear")])
         assert (b.units["tab_n"][0] > 0) == squeeze
