@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
+# COSMOGRB_B200_LIB selects another build of the same library (tuning runs: variants compiled with -D flags)
+LIB_PATH = os.environ.get("COSMOGRB_B200_LIB") or os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
 
 ABI_VERSION = 5
 NBINS = 140

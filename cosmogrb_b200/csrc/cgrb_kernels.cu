@@ -260,9 +260,11 @@ int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_uni
     cudaStream_t s = (cudaStream_t)stream;
     LAUNCH("k_thin_nodes", s, k_thin_nodes<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, d_thin_tab));
     LAUNCH("k_thin_margins", s, k_thin_margins<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_thin_tab));
-    if (d_thin_cum)
-        LAUNCH("k_thin_cum", s, k_thin_cum<<<n_units, NT, 0, s>>>(d_units, n_units, d_thin_tab, (double *)d_thin_cum,
-                                                                  n_nodes_total));
+    if (d_thin_cum) {
+        LAUNCH("k_thin_cum", s, k_thin_cum<<<n_units, NT, 0, s>>>(d_units, n_units, d_thin_tab, (double *)d_thin_cum));
+        LAUNCH("k_thin_guide", s, k_thin_guide<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, (double *)d_thin_cum,
+                                                                               n_nodes_total));
+    }
     return check_launch("cgrb_thin_tables");
 }
 

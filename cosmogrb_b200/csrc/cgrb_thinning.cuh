@@ -47,10 +47,10 @@ __device__ __forceinline__ double majorant_cap(double LT)
     return LT + 10.0 * sqrt(LT) + 64.0;
 }
 
-// one CTA per unit: cumulative majorant at the nodes (fixed association) and the search guide
+#define THIN_CUM_K 8
+// one CTA per unit: cumulative majorant at the nodes (fixed association)
 __global__ void __launch_bounds__(NT) k_thin_cum(const cgrb_unit_t *__restrict__ units, int n_units,
-                                                 const double *__restrict__ thin_tab, double *__restrict__ thin_cum,
-                                                 int64_t n_nodes_total)
+                                                 const double *__restrict__ thin_tab, double *__restrict__ thin_cum)
 {
     __shared__ double s_w[NW];
     const int ui = blockIdx.x;
@@ -62,34 +62,65 @@ __global__ void __launch_bounds__(NT) k_thin_cum(const cgrb_unit_t *__restrict__
         return;
     const double2 *sq = reinterpret_cast<const double2 *>(thin_tab) + u->tab_off;
     double *L = thin_cum + u->tab_off;
-    int32_t *guide = reinterpret_cast<int32_t *>(thin_cum + n_nodes_total) + u->tab_off;
     const double scale = u->fmax * ((u->src_tstop - u->src_tstart) / (double)(n - 1));
     double carry = 0.0;
     if (threadIdx.x == 0)
         L[0] = 0.0;
-    for (int base = 0; base < n - 1; base += NT) {
-        const int j = base + threadIdx.x;
-        const double v = (j < n - 1) ? scale * majorant_of(sq[j], sq[j + 1]) : 0.0;
+    // THIN_CUM_K consecutive cells per thread (serial prefix), the thread totals through one block scan
+    for (int base = 0; base < n - 1; base += THIN_CUM_K * NT) {
+        const int j0 = base + THIN_CUM_K * threadIdx.x;
+        double v[THIN_CUM_K];
+        double2 prev = (j0 < n) ? sq[j0] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < THIN_CUM_K; q++) {
+            const int j = j0 + q;
+            double2 nxt = prev;
+            double x = 0.0;
+            if (j < n - 1) {
+                nxt = sq[j + 1];
+                x = scale * majorant_of(prev, nxt);
+            }
+            v[q] = (q ? v[q - 1] : 0.0) + x;
+            prev = nxt;
+        }
         double total;
-        const double incl = block_incl_scan(v, s_w, &total);
-        if (j < n - 1)
-            L[j + 1] = carry + incl;
+        const double excl = block_excl_scan(v[THIN_CUM_K - 1], s_w, &total);
+#pragma unroll
+        for (int q = 0; q < THIN_CUM_K; q++)
+            if (j0 + q < n - 1)
+                L[j0 + q + 1] = carry + (excl + v[q]);
         carry = carry + total;
     }
-    __syncthreads();
-    const double LT = carry;
-    for (int g = threadIdx.x; g < n - 1; g += NT) {
-        const double target = (double)g * LT / (double)(n - 1);
-        int lo = 0, hi = n - 1;                     // largest j in [0, n-2] with L[j] <= target
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (L[mid] <= target)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        guide[g] = lo;
+}
+
+// search guide of the cumulative table, one thread per entry (node work list: which=4, chunk=256)
+__global__ void __launch_bounds__(NT) k_thin_guide(const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   double *__restrict__ thin_cum, int64_t n_nodes_total)
+{
+    const int64_t w = blockIdx.x;
+    if (w >= n_work)
+        return;
+    const cgrb_work_t wk = work[w];
+    const cgrb_unit_t *u = units + wk.unit;
+    const int n = (int)u->tab_n;
+    if (n < 4 || (u->flags & CGRB_UNIT_NO_SOURCE))
+        return;
+    const int g = (int)wk.start + threadIdx.x;
+    if (g >= n - 1)
+        return;
+    const double *L = thin_cum + u->tab_off;
+    int32_t *guide = reinterpret_cast<int32_t *>(thin_cum + n_nodes_total) + u->tab_off;
+    const double target = (double)g * L[n - 1] / (double)(n - 1);
+    int lo = 0, hi = n - 1;                     // largest j in [0, n-2] with L[j] <= target
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (L[mid] <= target)
+            lo = mid;
+        else
+            hi = mid;
     }
+    guide[g] = lo;
 }
 
 template <int WHICH>  // 0 = source (prefix -> stage at src_off), 1 = background (prefix -> times_bkg at bkg_off + 1)
@@ -263,7 +294,10 @@ __device__ __forceinline__ bool thin_accept_majorant(const LambdaTab *tab, const
     return v <= pe;
 }
 
-__global__ void __launch_bounds__(NT, 3) k_source_thin(const double *__restrict__ dtab,
+#ifndef THIN_CTAS
+#define THIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__restrict__ dtab,
                                                     const cgrb_unit_t *__restrict__ units,
                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                     cgrb_rng_t rng, const double *__restrict__ segstart,

@@ -517,7 +517,7 @@ class Engine(object):
                                                   thin_cum.data_ptr() if thin_cum is not None else None,
                                                   b.n_tab_nodes, self.stream),
                         "cgrb_thin_tables")
-            self.launches += 2 + (thin_cum is not None)
+            self.launches += 2 + 2 * (thin_cum is not None)
         _capi.check(
             self.lib.cgrb_sample_events(
                 b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), nw, dwb.data_ptr(),
