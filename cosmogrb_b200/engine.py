@@ -78,17 +78,18 @@ def make_units(n):
 
 
 def fill_gamma_constants(units):
-    """Per-GRB constants of a = 2 + alpha used by the device igamc (host libm)."""
-    for i in range(len(units)):
-        a = 2.0 + float(units["alpha"][i])
+    """Per-GRB constants of a = 2 + alpha used by the device igamc (CPython's math.gamma / math.lgamma, evaluated
+    once per distinct alpha: the 14 detectors of a burst share it)."""
+    alpha = np.asarray(units["alpha"], dtype="f8")
+    uniq, inv = np.unique(alpha, return_inverse=True)
+    g = np.full(len(uniq), np.nan)
+    lg = np.full(len(uniq), np.nan)
+    lg1 = np.full(len(uniq), np.nan)
+    for k, al in enumerate(uniq):
+        a = 2.0 + float(al)
         if a > 0:
-            units["gamma_a"][i] = math.gamma(a)
-            units["lgamma_a"][i] = math.lgamma(a)
-            units["lgamma_1pa"][i] = math.lgamma(1.0 + a)
-        else:
-            units["gamma_a"][i] = np.nan
-            units["lgamma_a"][i] = np.nan
-            units["lgamma_1pa"][i] = np.nan
+            g[k], lg[k], lg1[k] = math.gamma(a), math.lgamma(a), math.lgamma(1.0 + a)
+    units["gamma_a"], units["lgamma_a"], units["lgamma_1pa"] = g[inv], lg[inv], lg1[inv]
     return units
 
 
@@ -335,7 +336,10 @@ class Engine(object):
         _capi.check(self.lib.cgrb_fmax(dtab.data_ptr(), d_units.data_ptr(), len(units),
                                        self._extrap_code(interp_extrap), self.stream), "cgrb_fmax")
         self.launches += 1
-        return d_units.cpu().numpy().view(UNIT_DTYPE)["fmax"].copy()
+        # read back the fmax column only (8 of the record's 224 bytes)
+        torch = _torch()
+        col = UNIT_DTYPE.fields["fmax"][1] // 8
+        return d_units.view(torch.uint8).view(torch.float64).view(len(units), UNIT_DTYPE.itemsize // 8)[:, col].cpu().numpy()
 
     def new_batch(self, units, tables, interp_extrap=None, compute_fmax=True):
         """Upload units and detector tables, compute fmax on the device (unless given), size the
@@ -453,6 +457,32 @@ class Engine(object):
             b.counts = cbuf.numpy().view(COUNTS_DTYPE).copy()
             self.check_status(b)
             return self._enqueue_event_copies(b, None, extra)
+
+    def fetch_results_after(self, b, ready_event, want_trigger=False):
+        """Counters (and trigger results) of a batch read back on the copy stream once ``ready_event`` (recorded
+        after the batch's last kernel) has fired -- NOT stream-ordered behind whatever the compute stream has
+        been given since, so a later batch keeps the GPU busy while this one is read."""
+        torch = _torch()
+        cs = self.copy_stream()
+        with torch.cuda.stream(cs):
+            cs.wait_event(ready_event)
+            cbuf = torch.empty(b.d_counts.numel(), dtype=torch.uint8, pin_memory=True)
+            cbuf.copy_(b.d_counts, non_blocking=True)
+            tbuf = None
+            if want_trigger:
+                nbytes = b.n_units * _capi.TRIGGER_DTYPE.itemsize
+                tbuf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+                tbuf.copy_(b.t["trigger"][:nbytes], non_blocking=True)
+            cs.synchronize()
+        b.counts = cbuf.numpy().view(COUNTS_DTYPE).copy()
+        self.check_status(b)
+        if not want_trigger:
+            return b.counts, None
+        r = tbuf.numpy().view(_capi.TRIGGER_DTYPE).copy()
+        if np.any(r["razor"] & 2):
+            raise _capi.EngineError("cgrb_gbm_trigger: background_duration + pre_window + longest time scale "
+                                    "exceed the kernel's staged window span (1832 bins of 16 ms)")
+        return b.counts, r
 
     def _enqueue_event_copies(self, b, pinned, extra):
         torch = _torch()

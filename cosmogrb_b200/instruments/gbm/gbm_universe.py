@@ -50,16 +50,21 @@ class _GBMBatchedUniverse(Universe):
         u["src_tstart"] = 0.0
         u["src_tstop"] = np.repeat(self._duration[idx], N_DET)
         u["bkg_tstart"], u["bkg_tstop"] = GBMGRB._background_start, GBMGRB._background_stop
-        # Background._background_rate ~ N(500, 10) per detector (background.py:125, gbm_grb.py:120),
-        # drawn from a generator keyed by the GRB index so that sharding does not change it
-        rates = np.empty((n, N_DET))
-        for j, g in enumerate(idx):
-            rates[j] = np.random.default_rng([rate_seed, int(g)]).normal(500.0, 10.0, N_DET)
-        u["bkg_rate"] = rates.reshape(-1)
+        # Background._background_rate ~ N(500, 10) per detector (background.py:125, gbm_grb.py:120): one table
+        # for the whole population, drawn once per seed and indexed by GRB, so that neither the sharding nor
+        # the batching changes a burst's rates
+        u["bkg_rate"] = self._background_rates(rate_seed)[idx].reshape(-1)
         ang = separation_angles(self._ra[idx], self._dec[idx])              # [n, 14]
         fac = np.stack([angle_factor(d, ang[:, j]) for j, d in enumerate(GBM_DETECTORS)], axis=1)
         u["ea_scale"] = fac.reshape(-1)
         return u, ang
+
+    def _background_rates(self, rate_seed):
+        cache = self.__dict__.setdefault("_rate_cache", {})
+        if rate_seed not in cache:
+            cache.clear()
+            cache[rate_seed] = np.random.default_rng([0x6B67, int(rate_seed)]).normal(500.0, 10.0, (self._n_grbs, N_DET))
+        return cache[rate_seed]
 
     def cost_estimate(self):
         """relative cost of each GRB for the LPT deal: background events + a flux-weighted source term"""
@@ -75,6 +80,8 @@ class _GBMBatchedUniverse(Universe):
         thinning loop would take years on them."""
         import time
 
+        import torch
+
         from ...engine import capacity
 
         tm = self.timings = dict(fmax_pass=0.0, build_units=0.0, new_batch=0.0, launch=0.0, wait=0.0, gather=0.0)
@@ -85,6 +92,8 @@ class _GBMBatchedUniverse(Universe):
         dtab = eng.upload_tables(tabs)
         seed = eng.seed if seed is None else seed
 
+        unit_cache = {}      # GRB index -> (its 14 unit records, angles) built in the sizing pass
+
         def fmax_and_sizes(grbs):
             """fmax of every unit of the bursts ``grbs`` (one launch per 4096 bursts) and the bytes of event
             buffers each burst needs"""
@@ -92,7 +101,8 @@ class _GBMBatchedUniverse(Universe):
             sz = np.zeros(len(grbs))
             for p0 in range(0, len(grbs), 4096):
                 idx = grbs[p0:p0 + 4096]
-                units, _ = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
+                units, ang = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
+                unit_cache[(int(idx[0]), int(idx[-1]), len(idx))] = (idx, units, ang)
                 f = eng.fmax(units, dtab)
                 fm[p0:p0 + len(idx)] = f.reshape(-1, N_DET)
                 slots = (capacity(f, units["src_tstop"] - units["src_tstart"]).astype("f8")
@@ -136,17 +146,21 @@ class _GBMBatchedUniverse(Universe):
 
         def finish(item):
             """read back the counters of a launched batch (and its events when saving)"""
-            sel, idx, b, ang = item
+            sel, idx, b, ang, ready = item
             t3 = t_()
+            tr = None
             if save:
                 arrays = eng.to_host(b, pinned)
                 c = arrays["counts"]
                 self._save_chunk(idx, b, arrays, ang)
+                if trigger:
+                    tr = eng.fetch_trigger(b)
             else:
-                c = eng.fetch_counts(b)
-                eng.check_status(b)
+                # read on the copy stream behind the batch's own event: a plain .cpu() would queue behind the
+                # NEXT batch's kernels on the compute stream and serialise the pipeline
+                c, tr = eng.fetch_results_after(b, ready, want_trigger=trigger)
             if trigger:
-                tr = eng.fetch_trigger(b).reshape(-1, N_DET)
+                tr = tr.reshape(-1, N_DET)
                 local_trig[sel] = tr
                 for j in range(len(sel)):
                     local_det[sel[j]] = simultaneous_trigger(
@@ -156,6 +170,15 @@ class _GBMBatchedUniverse(Universe):
             local_counts[sel, :, 0] = c["n_src"].reshape(-1, N_DET)
             local_counts[sel, :, 1] = c["n_bkg"].reshape(-1, N_DET)
             local_counts[sel, :, 2] = c["n_kept"].reshape(-1, N_DET)
+
+        def cached_units(idx):
+            """unit records of the bursts ``idx`` cut from the sizing pass's blocks (rebuilt if not there)"""
+            for (cidx, cunits, cang) in unit_cache.values():
+                pos = np.searchsorted(cidx, idx)
+                if cidx[0] <= idx[0] and idx[-1] <= cidx[-1] and np.all(pos < len(cidx)) and np.array_equal(cidx[pos], idx):
+                    rows = (pos[:, None] * N_DET + np.arange(N_DET)[None, :]).reshape(-1)
+                    return cunits[rows].copy(), cang[pos]
+            return self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
 
         # two batches in flight: the host prepares and launches batch k+1 before it waits for batch k
         budget = memory_budget / 2
@@ -170,7 +193,7 @@ class _GBMBatchedUniverse(Universe):
             sel = todo[pos:end]
             idx = mine[sel]
             t0 = t_()
-            units, ang = self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
+            units, ang = cached_units(idx)
             units["fmax"] = fmax_all[sel].reshape(-1)
             t1 = t_()
             eng.use_pool(self.n_batches % 2)          # event buffers recycled from the slot used two batches ago
@@ -182,13 +205,15 @@ class _GBMBatchedUniverse(Universe):
                     eng.gbm_trigger(b, chan_bounds, threshold=trigger_threshold, fetch=False)
             finally:
                 eng.use_pool(None)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(eng.device))
             t3 = t_()
             tm["build_units"] += t1 - t0
             tm["new_batch"] += t2 - t1
             tm["launch"] += t3 - t2
             if in_flight is not None:
                 finish(in_flight)
-            in_flight = (sel, idx, b, ang)
+            in_flight = (sel, idx, b, ang, ready)
             pos = end
             self.n_batches += 1
         if in_flight is not None:
