@@ -555,6 +555,16 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
         const int64_t i0 = splits[2 * w], i1 = (d1 == total) ? nA : splits[2 * (w + 1) + 1];
         const int64_t j0 = g0 - i0, j1 = d1 - i1;
         const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+        if (na == 0 || nb == 0) {
+            // a tile fed by one list only (nearly every tile of a background-dominated unit, and of a bright
+            // burst's peak): the slice IS the merged order, straight into place
+            const double *X = na ? A + i0 : B + j0;
+            const uint8_t *pX = na ? pA + i0 : pB + j0;
+            for (int k = threadIdx.x; k < na + nb; k += NT) {
+                s_t[k] = X[k];
+                s_p[k] = pX[k];
+            }
+        } else {
         for (int k = threadIdx.x; k < na; k += NT) {
             s_in_t[k] = A[i0 + k];
             s_in_p[k] = pA[i0 + k];
@@ -590,6 +600,7 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
                     ib += take_a ? 0 : 1;
                 }
             }
+        }
         }
         __syncthreads();
         // keep flags of the tile's own events (local indices [l0, l0 + nt))
