@@ -184,14 +184,18 @@ __device__ __noinline__ double literal_photon_serial(const cgrb_unit_t &u, const
     const PropConst pc = make_prop_const(dt[CGRB_DT_EDGES], dt[CGRB_DT_EDGES + CGRB_NBINS], alpha);
     double best = -INFINITY;
     int idx = 0;
-    for (int m = 0; m < CGRB_NE_ENVELOPE; m++) {
-        double A = dt[CGRB_DT_G500_A + m], xg = dt[CGRB_DT_G500_E + m] * opz;
-        double g = (A > 0.0) ? log(A) + alpha * log(xg) - xg * sp.inv_ec : -INFINITY;
-        if (g > best) {
-            best = g;
-            idx = m;
+    // The spurious tstart photon of every unit has pulse amplitude 0: the whole 500-point row is zero, argmax
+    // is 0 and the search below (1000 logarithms by ONE lane while its CTA waits at the next barrier -- it was
+    // two thirds of this kernel's time on a population) cannot change that.
+    if (sp.norm > 0.0)
+        for (int m = 0; m < CGRB_NE_ENVELOPE; m++) {
+            double A = dt[CGRB_DT_G500_A + m], xg = dt[CGRB_DT_G500_E + m] * opz;
+            double g = (A > 0.0) ? log(A) + alpha * log(xg) - xg * sp.inv_ec : -INFINITY;
+            if (g > best) {
+                best = g;
+                idx = m;
+            }
         }
-    }
     double A_idx = dt[CGRB_DT_G500_A + idx], x_idx = dt[CGRB_DT_G500_E + idx] * opz;
     double f_idx = A_idx * cpl_value(sp, alpha, x_idx, log(x_idx));
     if (!(f_idx > 0.0)) {       // np.argmax of an all-zero row -> 0
