@@ -12,7 +12,8 @@ from ...engine import Philox, get_engine, make_units
 from ...io.grb_save import write_grb_file
 from ...lightcurve.light_curve_storage import LightCurveStorage
 from ...utils.logging import setup_logger
-from ...universe.universe import GRBWrapper, ParameterServer, Universe, dist_info, gather_event_counts, shard_by_cost
+from ...universe.universe import (GRBWrapper, ParameterServer, Universe, dist_info, gather_event_counts, gather_rows,
+                                  shard_by_cost)
 from .gbm_background import gbm_background_template
 from .gbm_grb import GBMGRB, GBMGRB_CPL, GBMGRB_CPL_Constant
 from .synthetic_response import GBM_DETECTORS, angle_factor, base_response, separation_angles
@@ -112,10 +113,15 @@ class _GBMBatchedUniverse(Universe):
 
         t0 = t_()
         if world > 1:
-            # every rank sizes every burst (a few ms per thousand bursts) so that the LPT deal sees the real cost:
-            # burst costs are heavy-tailed in ways the flux alone does not predict.  Bursts that will be skipped
-            # cost nothing.
-            fm_g, sz_g = fmax_and_sizes(np.arange(self._n_grbs))
+            # The LPT deal needs the real cost of every burst (costs are heavy-tailed in ways the flux alone does
+            # not predict; bursts that will be skipped cost nothing).  Each rank sizes 1 / world of the bursts and
+            # the rows (14 fmax + bytes) are exchanged: the sizing head stays constant under weak scaling.
+            parts = np.array_split(np.arange(self._n_grbs), world)
+            fm_p, sz_p = fmax_and_sizes(parts[rank])
+            rows = gather_rows(np.concatenate((fm_p, sz_p[:, None]), axis=1))
+            allrows = np.concatenate(rows, axis=0)
+            assert allrows.shape == (self._n_grbs, N_DET + 1)
+            fm_g, sz_g = allrows[:, :N_DET], allrows[:, N_DET]
             cost = np.where((sz_g > memory_budget) | ~np.isfinite(sz_g), 0.0, sz_g)
             self._shards = shard_by_cost(cost, world)
             mine = self._shards[rank]

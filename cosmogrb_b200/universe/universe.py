@@ -106,6 +106,32 @@ def gather_event_counts(local_counts, device=None):
     return [o[:int(k.item())].cpu().numpy() for o, k in zip(out, ns)]
 
 
+def gather_rows(local, device=None):
+    """all_gather of a float64 [n_local, k] block per rank (ranks may hold different n_local) -> list of
+    per-rank arrays.  Used by the sizing pass of a population run: every rank sizes 1 / world of the bursts
+    (fmax of their 14 units + bytes of event buffers) and all ranks need every burst's cost for the LPT deal."""
+    rank, world = dist_info()
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    local = local.reshape(local.shape[0], -1)
+    if world == 1:
+        return [local]
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend()
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if backend == "nccl" else torch.device("cpu"))
+    n = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    nmax = int(max(int(x.item()) for x in ns))
+    pad = torch.zeros((nmax, local.shape[1]), dtype=torch.float64, device=dev)
+    pad[:local.shape[0]] = torch.from_numpy(local).to(dev)
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return [o[:int(k.item())].cpu().numpy() for o, k in zip(out, ns)]
+
+
 class Universe(object, metaclass=abc.ABCMeta):
     """Generate a Universe of GRBs from a population file."""
 

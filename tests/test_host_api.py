@@ -181,7 +181,7 @@ GLOO_WORKER = r"""
 import os, sys
 sys.path.insert(0, sys.argv[1])
 import numpy as np, torch.distributed as dist
-from cosmogrb_b200.universe.universe import gather_event_counts, dist_info, shard_by_cost
+from cosmogrb_b200.universe.universe import gather_event_counts, gather_rows, dist_info, shard_by_cost
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank, world = dist_info()
 assert world == 2
@@ -196,6 +196,12 @@ want = np.stack([np.arange(11) * 10 + k for k in (1, 2, 3)], axis=1)
 assert np.array_equal(full, want), full
 offsets = np.concatenate(([0], np.cumsum(full[:, 2])))[:-1]              # global event offsets
 assert offsets[1] == 3
+# sizing pass: each rank sizes its slice of the bursts, every rank ends up with every burst's row
+parts = np.array_split(np.arange(11), world)
+rows = np.stack([parts[rank] + 0.25, np.where(parts[rank] == 3, np.inf, parts[rank] * 2.0)], axis=1)
+allrows = np.concatenate(gather_rows(rows), axis=0)
+assert allrows.shape == (11, 2) and np.array_equal(allrows[:, 0], np.arange(11) + 0.25)
+assert np.isinf(allrows[3, 1]) and allrows[4, 1] == 8.0
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
