@@ -480,7 +480,7 @@ def run_gpu(args):
             "gbm_trigger": {"on_device": True, "detected_local": int(uni.detected.sum()), "local_grbs": int(len(uni.local_grbs)),
                             "kernel_ms": round(pk.get("k_trig_bin", 0.0) + pk.get("k_trig_eval", 0.0), 3)}, "ms": ms_pop, "grbs_per_s": uni.n_grbs / (ms_pop * 1e-3),
             "events_per_s": n_ev / (ms_pop * 1e-3), "batches_per_gpu": int(uni.n_batches),
-            "kernel_ms_per_gpu": tot_k, "kernels": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])[:8]},
+            "kernel_ms_per_gpu": tot_k, "kernels": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])[:24]},
             "hbm_kernels": pop_roof, "host_seconds": {k: round(v, 4) for k, v in uni.timings.items()},
             "host_detail": {k: round(v, 4) for k, v in eng.host_times.items()},
         }

@@ -25,7 +25,7 @@ SEG = 8192
 MERGE_TILE = 2048
 DT_TILE = 2048
 MD_TILE = 2048
-TRIG_TILE = 2048
+TRIG_TILE = 4096
 ENV_MAXW = 256
 
 # detector table block layout (doubles) -- must match include/cosmogrb_b200.h

@@ -11,10 +11,11 @@
 // The quirks of the reference are reproduced (see oracle/trigger_oracle.py): the count round trip
 // ((c / dt) * dt).astype(int), the swapped window arguments, the inclusive dead-time interval.
 // ==========================================================================================
-#define TRIG_TILE 2048
-#define TRIG_LOCAL 512          // bins a tile may span and still be accumulated in shared memory (2048 events
-                                // at the 500 /s background are 256 bins of 16 ms)
-#define TRIG_EPT (TRIG_TILE / NT)   // events per thread
+#define TRIG_TILE 4096          // events per CTA (two passes of TRIG_EPT per thread)
+#define TRIG_LOCAL 1024         // bins a tile may span and still be accumulated in shared memory (4096 events
+                                // at the 500 /s background are 512 bins of 16 ms)
+#define TRIG_EPT 8              // events per thread and pass
+#define TRIG_PASSES (TRIG_TILE / (TRIG_EPT * NT))
 #define TRIG_NCOMBO 33
 #define TRIG_NARR 6             // per-bin integer arrays: counts of the 4 ranges, events, overflow events
 #define TRIG_CH 2048            // windows per staged chunk of the search
@@ -44,8 +45,8 @@ __device__ __forceinline__ TrigGrid trig_grid(double tmin, double tmax, double d
     return g;
 }
 
-// Shared-memory histogram of a tile, three packed words per bin (a tile holds 2048 events, so every 16-bit
-// field stays below 2 x 2048): word 0 = range a | range b << 16, word 1 = range c | range d << 16,
+// Shared-memory histogram of a tile, three packed words per bin (a tile holds TRIG_TILE events, so every 16-bit
+// field stays below 2 x TRIG_TILE < 65536): word 0 = range a | range b << 16, word 1 = range c | range d << 16,
 // word 2 = events | overflow events << 16 (the two dead-time counters).
 __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__ units,
                                                  const cgrb_work_t *__restrict__ work, int64_t n_work,
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
     const double eps = fma((fabs(g.t0) + fabs(last_edge)) * inv_delta, 64.0 * 2.220446049250313e-16, 1e-9);
     const bool fast_ok = eps < 0.25 && nb > 2;
     const double MAGIC = 6755399441055744.0;                // 2^52 + 2^51
-    // this thread's events (loads issued together)
+    // this thread's events of the first pass (loads issued together)
     double tt[TRIG_EPT];
     int cc[TRIG_EPT];
 #pragma unroll
@@ -130,6 +131,16 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
     __syncthreads();
     const int k0 = s_k0;
     const bool local = s_local != 0;
+    for (int pass = 0; pass < TRIG_PASSES; pass++) {
+    if (pass > 0) {
+#pragma unroll
+        for (int r = 0; r < TRIG_EPT; r++) {
+            const int64_t i = wk.start + (int64_t)(pass * TRIG_EPT + r) * NT + threadIdx.x;
+            const bool in = i < end;
+            tt[r] = in ? t[i] : 0.0;
+            cc[r] = in ? (int)p[i] : -1;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < TRIG_EPT; r++) {
         const int c = cc[r];
@@ -182,6 +193,7 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
                     atomicAdd(ub + 5 * bins_per_unit + k - 1, 1);
             }
         }
+    }
     }
     __syncthreads();
     if (local)

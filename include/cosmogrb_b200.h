@@ -345,7 +345,7 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
  *       bounds[2r] < c < bounds[2r+1]  (= ebounds.searchsorted(emin) / (emax); no bound: -1 / 1<<30)
  *   bins_per_unit: >= number of 16 ms bins any unit can have (host: ceil(span / base_timescale) + 2)
  *   work list: which=2, chunk=CGRB_TRIG_TILE.  d_workspace: cgrb_gbm_trigger_workspace_bytes(). */
-#define CGRB_TRIG_TILE 2048
+#define CGRB_TRIG_TILE 4096
 typedef struct {
     double threshold;            /* 4.5  */
     double base_timescale;       /* 0.016 */

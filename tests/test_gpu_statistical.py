@@ -209,6 +209,10 @@ def test_c3_background_only_interval(engine):
         assert tb[0] == 0.0 and np.all(np.diff(tb) >= 0) and tb[-1] <= 1000.0
         assert stats.kstest(tb[1:] / 1000.0, "uniform").pvalue > P_MIN / 3
         assert stats.kstest(np.diff(tb[1:]), "expon", args=(0, 1.0 / 500.0)).pvalue > P_MIN / 3
+        # counts in 997 equal bins: Poisson dispersion
+        hist = np.histogram(tb[1:], bins=997, range=(0.0, 1000.0))[0]
+        disp = ((hist - hist.mean()) ** 2).sum() / hist.mean()
+        assert stats.chi2.sf(disp, 996) > P_MIN / 3 and stats.chi2.cdf(disp, 996) > P_MIN / 3
         w = h.bkg_weights(dets[i]).astype("f8")
         obs = np.bincount(pb.astype(int), minlength=128)
         exp = w / w.sum() * obs.sum()
