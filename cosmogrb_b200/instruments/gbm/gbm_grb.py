@@ -15,7 +15,7 @@ from ...sampler.source import Source
 from ...utils.logging import setup_logger
 from .gbm_background import GBMBackground
 from .gbm_lightcurve import GBMLightCurve
-from .synthetic_response import GBM_DETECTORS, BGOResponse, NaIResponse
+from .synthetic_response import GBM_DETECTORS, BGOResponse, GBMResponseFile, NaIResponse
 
 logger = setup_logger(__name__)
 
@@ -32,8 +32,13 @@ class GBMGRB(GRB):
     _background_stop = 300
     _gbm_detectors = GBM_DETECTORS
 
-    def __init__(self, source_function_class, **kwargs):
+    def __init__(self, source_function_class, response_files=None, **kwargs):
+        """``response_files`` (not in the reference, whose DRMs come from ``gbm_drm_gen``): ``{detector: path}``
+        of OGIP ``.rsp`` files (140 x 128) to use instead of the synthetic matrices for those detectors."""
         self._use_plaw_sample = True
+        self._response_files = dict(response_files or {})
+        for det in self._response_files:
+            assert det in self._gbm_detectors, f"{det} is not a GBM detector"
         super(GBMGRB, self).__init__(source_function_class=source_function_class, **kwargs)
 
     def _setup_source(self):
@@ -58,8 +63,11 @@ class GBMGRB(GRB):
 
     def _setup(self):
         for det in self._gbm_detectors:
-            cls = BGOResponse if det[0] == "b" else NaIResponse
-            rsp = cls(det, self.ra, self.dec, save=False, name=self.name)
+            if det in self._response_files:
+                rsp = GBMResponseFile(det, self.ra, self.dec, self._response_files[det], name=self.name)
+            else:
+                cls = BGOResponse if det[0] == "b" else NaIResponse
+                rsp = cls(det, self.ra, self.dec, save=False, name=self.name)
             self._add_response(det, rsp)
             bkg = GBMBackground(self._background_start, self._background_stop, average_rate=500, detector=det)
             self._add_background(det, bkg)
@@ -74,8 +82,8 @@ class GBMGRB_CPL(GBMGRB):
     trise = SourceParameter()
     tdecay = SourceParameter()
 
-    def __init__(self, **kwargs):
-        super(GBMGRB_CPL, self).__init__(source_function_class=CPLSourceFunction, **kwargs)
+    def __init__(self, response_files=None, **kwargs):
+        super(GBMGRB_CPL, self).__init__(source_function_class=CPLSourceFunction, response_files=response_files, **kwargs)
 
 
 class GBMGRB_CPL_Constant(GBMGRB):
@@ -83,8 +91,8 @@ class GBMGRB_CPL_Constant(GBMGRB):
     alpha = SourceParameter()
     ep = SourceParameter()
 
-    def __init__(self, **kwargs):
-        super(GBMGRB_CPL_Constant, self).__init__(source_function_class=ConstantCPL, **kwargs)
+    def __init__(self, response_files=None, **kwargs):
+        super(GBMGRB_CPL_Constant, self).__init__(source_function_class=ConstantCPL, response_files=response_files, **kwargs)
 
 
 __all__ = ["GBMGRB", "GBMGRB_CPL", "GBMGRB_CPL_Constant"]

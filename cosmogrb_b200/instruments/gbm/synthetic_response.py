@@ -178,6 +178,38 @@ class SyntheticGBMResponse(Response):
         return self._trigger_time
 
 
+class GBMResponseFile(SyntheticGBMResponse):
+    """A GBM detector response read from an OGIP ``.rsp`` file (SPECRESP MATRIX + EBOUNDS; one matrix of an
+    ``.rsp2`` via ``extension``) instead of the synthetic generator: the real-DRM route of SURVEY.md §8 f4 without
+    ``gbm_drm_gen``.  The matrix must have the engine's 140 photon bins x 128 channels (what GBM responses have).
+    Geometry (separation angle, geometric area) follows the detector table exactly as for the synthetic
+    responses (gbm_response.py:154-169, 274-289)."""
+
+    def __init__(self, detector_name, ra, dec, file_name, extension=None, trigger_time=0.0, name=None):
+        from ...utils.response_file import read_response
+
+        assert detector_name in GBM_DETECTORS, "must use a proper GBM detector n<> or b<>"
+        self._detector_name = detector_name
+        self._ra, self._dec = ra, dec
+        self._radius, self._height = 0.5 * 12.7, (12.7 if detector_name[0] == "b" else 1.27)
+        self._separation_angle = separation_angle(detector_name, ra, dec)
+        self._trigger_time = trigger_time
+        self._name = name
+        self._file_name = str(file_name)
+        r = read_response(file_name, extension=extension)
+        if r["matrix"].shape != (140, 128):
+            raise ValueError(f"{file_name}: matrix is {r['matrix'].shape[0]} photon bins x {r['matrix'].shape[1]} "
+                             "channels; the engine's tables are built for GBM's 140 x 128")
+        Response.__init__(self, matrix=r["matrix"], geometric_area=self._compute_geometric_area(),
+                          energy_edges=r["energy_edges"], channel_edges=r["channel_edges"])
+
+    def _compute_geometric_area(self):
+        if self._detector_name[0] == "b":
+            a = self._separation_angle + 0.5 * np.pi
+            return np.fabs(np.pi * self._radius ** 2 * np.cos(a)) + np.fabs(2 * self._radius * self._height * np.sin(a))
+        return SyntheticGBMResponse._compute_geometric_area(self)
+
+
 class NaIResponse(SyntheticGBMResponse):
     def __init__(self, detector_name, ra, dec, rng=None, save=False, name=None):
         super(NaIResponse, self).__init__(detector_name, ra, dec, radius=0.5 * 12.7, height=1.27, name=name)
@@ -193,5 +225,5 @@ class BGOResponse(SyntheticGBMResponse):
         return np.fabs(np.pi * self._radius ** 2 * np.cos(a)) + np.fabs(2 * self._radius * self._height * np.sin(a))
 
 
-__all__ = ["GBM_DETECTORS", "gbm_tables", "synthetic_matrix", "NaIResponse", "BGOResponse",
+__all__ = ["GBM_DETECTORS", "gbm_tables", "synthetic_matrix", "NaIResponse", "BGOResponse", "GBMResponseFile",
            "SyntheticGBMResponse", "separation_angle", "separation_angles", "angle_factor", "base_response"]

@@ -281,3 +281,32 @@ def test_grbsave_to_gbm_fits(tmp_path):
     assert list(only) == ["b0"]
     with pytest.raises(AssertionError):
         grbsave_to_gbm_fits(fn, destination=str(tmp_path), detectors=["n5"])
+
+
+def test_gbm_response_from_file(tmp_path):
+    """GBMResponseFile: the detector response of a GBM burst read from an OGIP file -- same
+    geometry as the synthetic responses, the file's matrix, the device table the engine consumes."""
+    from cosmogrb_b200.instruments.gbm.synthetic_response import BGOResponse, GBMResponseFile, NaIResponse
+
+    for det, cls in (("n4", NaIResponse), ("b0", BGOResponse)):
+        syn = cls(det, 312.0, -62.0)
+        fn = tmp_path / f"{det}.rsp"
+        syn.to_fits(fn, telescope_name="fermi", instrument_name=det)
+        rsp = GBMResponseFile(det, 312.0, -62.0, fn, trigger_time=3.5)
+        assert np.array_equal(rsp.matrix, syn.matrix) and rsp.geometric_area == syn.geometric_area
+        assert rsp.separation_angle == syn.separation_angle and rsp.detector_name == det
+        assert (rsp.ra, rsp.dec, rsp.T0, rsp.trigger_time) == (312.0, -62.0, 3.5, 3.5)
+        assert np.array_equal(rsp.cumulative_matrix, syn.cumulative_matrix)
+        # photon edges went through float32 in the file; everything built from the matrix alone is identical
+        a, b = rsp.device_table(h.bkg_weights(det), "linear"), syn.device_table(h.bkg_weights(det), "linear")
+        assert a.shape == b.shape
+        from cosmogrb_b200 import _capi
+        assert np.array_equal(a[_capi.DT_CUM:_capi.DT_GUIDE], b[_capi.DT_CUM:_capi.DT_GUIDE])
+        np.testing.assert_allclose(a[_capi.DT_EDGES:_capi.DT_EDGES + 141], b[_capi.DT_EDGES:_capi.DT_EDGES + 141], rtol=1e-7)
+    small = Response(matrix=np.ones((20, 16)), geometric_area=1.0, energy_edges=np.logspace(1, 3, 21),
+                     channel_edges=np.logspace(1, 3, 17))
+    small.to_fits(tmp_path / "small.rsp")
+    with pytest.raises(ValueError, match="140 x 128"):
+        GBMResponseFile("n0", 0.0, 0.0, tmp_path / "small.rsp")
+    with pytest.raises(AssertionError):
+        GBMResponseFile("x9", 0.0, 0.0, fn)

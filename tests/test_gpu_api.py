@@ -111,6 +111,20 @@ def test_grb_to_gbm_fits_products(grb, tmp_path):
         eng = get_engine()
         a, b = eng.digitize(rsp, e, rng=Philox(5)), eng.digitize(r2, e, rng=Philox(5))
         assert near.sum() < 100 and np.array_equal(a[~near], b[~near])
+    # a burst whose n0 / b1 responses come from those files (real-DRM route): same matrices, so the same light
+    # curves in distribution as the fixture's
+    from cosmogrb_b200 import gbm
+
+    g2 = gbm.GBMGRB_CPL(ra=312.0, dec=-62.0, z=1.0, peak_flux=1e-5, alpha=-0.66, ep_start=500.0, ep_tau=2.0,
+                        trise=0.1, tdecay=1.0, duration=2.0, T0=0.1,
+                        response_files={d: f["rsp"] for d, f in files.items()})
+    g2.go(seed=77)
+    for det in ("n0", "b1", "n5"):
+        a = grb.lightcurves[det].lightcurve_storage.n_counts_source
+        b = g2.lightcurves[det].lightcurve_storage.n_counts_source
+        assert abs(a - b) < 6.0 * np.sqrt(a + b) + 10, (det, a, b)
+    assert type(g2.lightcurves["n0"].response).__name__ == "GBMResponseFile"
+    assert type(g2.lightcurves["n5"].response).__name__ == "NaIResponse"
     lc = grb.lightcurves["n3"]
     out = lc.write_tte(str(tmp_path / "n3_direct.fits"))
     r = read_tte(out)
