@@ -187,7 +187,11 @@ class _GBMBatchedUniverse(Universe):
             return self.build_units(idx, rate_seed=seed & 0xFFFFFFFF)
 
         # two batches in flight: the host prepares and launches batch k+1 before it waits for batch k
-        budget = memory_budget / 2
+        import os
+
+        # bytes of event buffers per batch (two batches are in flight); COSMOGRB_B200_BATCH_BYTES overrides it for
+        # tuning runs without moving the skip threshold above
+        budget = float(os.environ.get("COSMOGRB_B200_BATCH_BYTES", memory_budget / 2))
         pos, in_flight = 0, None
         while pos < len(todo):
             # grow the batch until the memory budget (or grbs_per_batch) is reached
