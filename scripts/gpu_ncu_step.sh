@@ -1,4 +1,4 @@
-tag=r3
+tag=${1:-rX}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --population 0"
 $CMD > gpurun_out/plain_${tag}.log 2>&1 &&

@@ -161,8 +161,35 @@ def test_population_and_universe_setup(tmp_path):
     assert np.all((units["ea_scale"] > 0) & (units["ea_scale"] <= 1))
     u2, _ = uni.build_units(np.array([7]))                    # unit records do not depend on the batching
     assert np.array_equal(units[14:].tobytes(), u2.tobytes())
+    # background rates ~ N(500, 10): one table per seed for the whole population, so neither the batching nor
+    # the sharding changes a burst's rates; another seed gives other rates
+    u3, _ = uni.build_units(np.arange(200), rate_seed=5)
+    u4, _ = uni.build_units(np.array([11, 150]), rate_seed=5)
+    assert np.array_equal(u3["bkg_rate"][11 * 14:12 * 14], u4["bkg_rate"][:14])
+    assert np.array_equal(u3["bkg_rate"][150 * 14:151 * 14], u4["bkg_rate"][14:])
+    assert abs(u3["bkg_rate"].mean() - 500.0) < 1.0 and 8.0 < u3["bkg_rate"].std() < 12.0
+    u5, _ = uni.build_units(np.array([11]), rate_seed=6)
+    assert not np.array_equal(u5["bkg_rate"], u4["bkg_rate"][:14])
     with pytest.raises(RuntimeError):
         Population(ra=[1.0], dec=[2.0])
+
+
+def test_gamma_constants_per_distinct_alpha():
+    """fill_gamma_constants evaluates math.gamma / lgamma once per distinct alpha: same values as unit by unit"""
+    import math
+
+    from cosmogrb_b200.engine import fill_gamma_constants, make_units
+
+    u = make_units(30)
+    u["alpha"] = np.repeat([-0.66, -1.5, -1.0 + 1e-9, -2.5, 0.3], 6)
+    fill_gamma_constants(u)
+    for i in range(30):
+        a = 2.0 + float(u["alpha"][i])
+        if a > 0:
+            assert u["gamma_a"][i] == math.gamma(a) and u["lgamma_a"][i] == math.lgamma(a)
+            assert u["lgamma_1pa"][i] == math.lgamma(1.0 + a)
+        else:
+            assert np.isnan(u["gamma_a"][i]) and np.isnan(u["lgamma_a"][i]) and np.isnan(u["lgamma_1pa"][i])
 
 
 def test_shard_by_cost():
