@@ -16,6 +16,9 @@ namespace cgrb {
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011).  counter = (c0,c1,c2,c3), key = (k0,k1).
 // ------------------------------------------------------------------------------------------
+#ifndef CGRB_PHILOX_ROUNDS
+#define CGRB_PHILOX_ROUNDS 10       // Philox4x32-10; other values only for tuning measurements
+#endif
 struct Philox4 {
     uint32_t x, y, z, w;
 };
@@ -25,7 +28,7 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < CGRB_PHILOX_ROUNDS; r++) {
         uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
         uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
