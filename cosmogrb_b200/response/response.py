@@ -187,6 +187,20 @@ class Response(object):
         return self._cumulative_maxtrix
 
 
+def _response_set_function(self, integral_function=None):
+    """``integral_function(e1, e2, t1, t2)`` -> integral of the model over [e1, e2] x [t1, t2] (response.py:202-211)."""
+    self._integral_function = integral_function
+
+
+def _response_convolve(self, t1, t2):
+    """Expected counts per channel over [t1, t2]: the model integrated over every photon bin, folded through the
+    matrix (response.py:213-236; host-side, not on the sampling path).  Non-finite bin fluxes count as zero."""
+    e = self._energy_edges
+    true_fluxes = np.array([self._integral_function(e[i], e[i + 1], t1, t2) for i in range(len(e) - 1)], dtype="f8")
+    true_fluxes[~np.isfinite(true_fluxes)] = 0.0
+    return np.dot(true_fluxes, self._matrix)
+
+
 def _response_to_fits(self, filename, telescope_name="telescope", instrument_name="detector", overwrite=False):
     """Write the matrix as an OGIP ``.rsp`` FITS file (response.py:238-263)."""
     from ..utils.response_file import RSP
@@ -206,6 +220,8 @@ def _response_from_fits(cls, filename, geometric_area, extension=None):
                channel_edges=r["channel_edges"])
 
 
+Response.set_function = _response_set_function
+Response.convolve = _response_convolve
 Response.to_fits = _response_to_fits
 Response.from_fits = classmethod(_response_from_fits)
 

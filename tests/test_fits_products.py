@@ -310,3 +310,14 @@ def test_gbm_response_from_file(tmp_path):
         GBMResponseFile("n0", 0.0, 0.0, tmp_path / "small.rsp")
     with pytest.raises(AssertionError):
         GBMResponseFile("x9", 0.0, 0.0, fn)
+
+
+def test_response_convolve():
+    """Response.set_function / convolve (response.py:202-236): bin integrals folded through the matrix."""
+    rsp = h.response("n0")
+    rsp.set_function(lambda e1, e2, t1, t2: (t2 - t1) * (np.log(e2 / e1) if e1 > 6.0 else np.inf))   # E^-1, one bad bin
+    got = rsp.convolve(0.0, 2.0)
+    e = rsp.energy_edges
+    flux = 2.0 * np.log(e[1:] / e[:-1])
+    flux[e[:-1] <= 6.0] = 0.0
+    assert got.shape == (128,) and np.allclose(got, flux @ rsp.matrix, rtol=1e-13)
