@@ -107,3 +107,38 @@ class LightCurveStorage(object):
         if tmax is not None:
             idx &= times <= tmax
         return np.bincount(np.asarray(pha)[idx].astype(int), minlength=len(self._channels))
+
+    def _output(self, as_display=False):
+        """summary table (light_curve_storage.py:605-640): a pandas Series when pandas is importable, else an
+        ordered dict; ``as_display`` prints it (the reference hands it to IPython's display)"""
+        import collections
+
+        d = collections.OrderedDict()
+        d["name"] = self._name
+        d["instrument"] = self._instrument
+        d["tstart"] = self._tstart
+        d["tstop"] = self._tstop
+        d["time adjustment"] = self._time_adjustment
+        d["T0"] = self._T0
+        d["n_counts"] = self._n_counts
+        d["n_counts_source"] = self._n_counts_source
+        d["n_counts_background"] = self._n_counts_background
+        if self._extra_info:
+            for k, v in self._extra_info.items():
+                d[k] = v
+        try:
+            import pandas as pd
+
+            out = pd.Series(data=d, index=list(d.keys()))
+        except ImportError:          # pragma: no cover
+            out = d
+        if as_display:
+            print(out.to_string() if hasattr(out, "to_string") else "\n".join(f"{k:<22}{v}" for k, v in out.items()))
+        return out
+
+    def __repr__(self):
+        out = self._output()
+        return out.to_string() if hasattr(out, "to_string") else "\n".join(f"{k:<22}{v}" for k, v in out.items())
+
+    def info(self):
+        self._output(as_display=True)

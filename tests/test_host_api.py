@@ -132,6 +132,8 @@ def test_grb_file_round_trip(tmp_path, backend):
 
 def test_storage_binning():
     lc, _ = _storage("n0", n=2000)
+    txt = repr(lc)                              # light_curve_storage.py:597-640
+    assert "n_counts_source" in txt and "time adjustment" in txt and "angle" in txt and "GBM" in txt
     bins, counts = lc.binned_counts(1.0, None, None, tmin=-100, tmax=300)
     assert bins.shape[1] == 2 and counts.sum() <= 2000 and counts.sum() >= 1990
     assert lc.count_spectrum().sum() == 2000
