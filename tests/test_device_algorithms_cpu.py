@@ -1,0 +1,160 @@
+"""CPU: line-by-line Python restatements of three device-side algorithms whose equivalence to the serial reference
+rule is an ARGUMENT in the kernels' comments, checked here against the oracle without a GPU:
+
+* ``dt_keep`` (csrc/cgrb_deadtime.cuh): the literal GBM dead-time rule resolved per event from a short look-back
+  through overflow events, against the serial loop of gbm_lightcurve.py:80-115 (oracle ``co_gbm_dead_time``);
+* ``dt_keep_phys``: the physical (non-paralyzable) rule resolved per event from the nearest synchronisation point,
+  against its serial definition (``co_gbm_dead_time_physical``);
+* the conversion-free bin index of ``k_trig_bin`` (2^52 floor trick + an ulp-scaled safety margin, exact edge test
+  otherwise) against ``np.histogram`` on ``np.arange`` edges (light_curve_storage.py:218-269).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+TAU, NORMAL = 10.6e-6, 2.6e-6
+
+
+def dt_pe(t, p, j):
+    return t[j] + (NORMAL if (j == 0 and p[0] != 127) else TAU)
+
+
+def dt_keep(t, p, i):
+    """csrc/cgrb_deadtime.cuh: dt_keep"""
+    if i == 0:
+        return True
+    ti = t[i]
+    found = -1
+    j = i - 1
+    while j >= 0:
+        if t[j] + TAU < ti:
+            break
+        if p[j] == 127 or j == 0:
+            found = j
+            break
+        j -= 1
+    if found < 0:
+        return True
+    head = found
+    while head > 0:
+        th = t[head]
+        q = -1
+        j = head - 1
+        while j >= 0:
+            if t[j] + TAU < th:
+                break
+            if p[j] == 127 or j == 0:
+                q = j
+                break
+            j -= 1
+        if q < 0 or dt_pe(t, p, q) < th:
+            break
+        head = q
+    t_end = dt_pe(t, p, head)
+    for j in range(head + 1, i):
+        if p[j] == 127 and t[j] > t_end:
+            t_end = t[j] + TAU
+    return ti > t_end
+
+
+def dt_keep_phys(t, p, i, tau, tau_ovf):
+    """csrc/cgrb_deadtime.cuh: dt_keep_phys (has0 = True, no walk limit)"""
+    tau_max = max(tau, tau_ovf)
+    s, ts, ps = i, t[i], p[i]
+    while s > 0:
+        tp = t[s - 1]
+        if ts > tp + tau_max:
+            break
+        s -= 1
+        ts, ps = tp, p[s]
+    if s == i:
+        return True
+    t_end = ts + (tau_ovf if ps == 127 else tau)
+    kept = True
+    for j in range(s + 1, i + 1):
+        kept = t[j] > t_end
+        if kept:
+            t_end = t[j] + (tau_ovf if p[j] == 127 else tau)
+    return kept
+
+
+def _events(rs, n, rate, frac127, ties=False):
+    t = np.cumsum(rs.exponential(1.0 / rate, n))
+    if ties:
+        # adversarial: events exactly one window after another, and exact duplicates
+        k = rs.randint(1, n - 1, n // 20)
+        t[k] = t[k - 1] + rs.choice([TAU, NORMAL, 10e-6, 0.0], len(k))
+        t = np.sort(t)
+    p = rs.randint(0, 127, n)
+    p[rs.random_sample(n) < frac127] = 127
+    return t, p
+
+
+@pytest.mark.parametrize("rate,frac127,ties", [(500.0, 0.05, False), (2e5, 0.05, True), (2e6, 0.3, True), (5e6, 1.0, False),
+                                               (1e5, 0.0, True)])
+def test_literal_dead_time_look_back_equals_the_serial_rule(rate, frac127, ties):
+    rs = np.random.RandomState(int(rate) % 1000 + int(100 * frac127))
+    n = 4000 if rate > 1e6 else 12000
+    for first127 in (False, True):
+        t, p = _events(rs, n, rate, frac127, ties)
+        p[0] = 127 if first127 else 5
+        want = orc.gbm_dead_time(t, p)
+        got = np.array([dt_keep(t, p, i) for i in range(n)])
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("rate,frac127,tau,tovf", [(500.0, 0.05, 2.6e-6, 10e-6), (2e5, 0.1, 2.6e-6, 10e-6),
+                                                   (5e5, 0.3, 2.6e-6, 10e-6), (1e5, 0.5, 5e-6, 1e-6), (2e5, 0.2, 0.0, 0.0)])
+def test_physical_dead_time_sync_points_equal_the_serial_rule(rate, frac127, tau, tovf):
+    rs = np.random.RandomState(int(rate) % 977 + 3)
+    n = 12000
+    t, p = _events(rs, n, rate, frac127, ties=True)
+    want = orc.gbm_dead_time_physical(t, p, tau, tovf)
+    got = np.array([dt_keep_phys(t, p, i, tau, tovf) for i in range(n)])
+    assert np.array_equal(got, want)
+
+
+def _bin_fast(tt, t0, delta, nb, last_edge):
+    """k_trig_bin's fast path; returns (bin, took_fast_path)"""
+    inv_delta = 1.0 / delta
+    eps = (abs(t0) + abs(last_edge)) * inv_delta * (64.0 * 2.220446049250313e-16) + 1e-9
+    fast_ok = eps < 0.25 and nb > 2
+    MAGIC = 6755399441055744.0
+    q = (tt - t0) * inv_delta
+    m = q + MAGIC
+    k = int(np.float64(m).view(np.uint64) & 0xFFFFFFFF)          # __double2loint
+    if k >= 1 << 31:
+        k -= 1 << 32
+    fr = q - (m - MAGIC)
+    if fr < 0.0:
+        k -= 1
+        fr += 1.0
+    return k, bool(fast_ok and eps < fr < 1.0 - eps and 1.0 < q < float(nb - 1))
+
+
+@pytest.mark.parametrize("t0,span", [(-100.0, 400.0), (0.0, 1000.0), (5.0e8, 400.0), (-3.3e9, 123.4), (1e-3, 50.0)])
+def test_trigger_bin_index_fast_path_is_exact(t0, span):
+    rs = np.random.RandomState(11)
+    dt = 0.016
+    tmax = t0 + span
+    edges = np.arange(t0, tmax, dt)                               # the reference's bin edges
+    nb = len(edges) - 1
+    delta = (t0 + dt) - t0
+    # np.arange's fill rule as restated in the kernel: edge[i] = t0 + i * delta
+    assert np.array_equal(edges, t0 + np.arange(len(edges)) * delta)
+    tt = np.concatenate((rs.uniform(t0, edges[-1], 20000),
+                         edges[rs.randint(1, nb, 300)],                                  # exactly on an edge
+                         np.nextafter(edges[rs.randint(1, nb, 300)], -np.inf),           # one ulp below / above
+                         np.nextafter(edges[rs.randint(1, nb, 300)], np.inf)))
+    want = np.clip(np.searchsorted(edges, tt, "right") - 1, 0, nb - 1)                   # edge[k] <= t < edge[k+1]
+    n_fast = 0
+    for x, w in zip(tt, want):
+        k, fast = _bin_fast(float(x), t0, delta, nb, float(edges[-1]))
+        if fast:
+            n_fast += 1
+            assert k == w, (x, k, w)
+    # the fast path must carry nearly all random events unless the times are so large that an ulp is a
+    # sizeable fraction of a bin (then everything takes the exact edge test)
+    if abs(t0) < 1e9:
+        assert n_fast > 0.95 * 20000
