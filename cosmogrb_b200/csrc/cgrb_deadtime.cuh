@@ -159,11 +159,11 @@ __device__ __forceinline__ bool dt_keep(const double *__restrict__ t, const uint
 // predecessor by more than the longest window: fl(t[s-1] + tau_max) >= any t_end set before s (rounding is
 // monotonic), so such an event is certainly kept.  Each event walks back to the nearest synchronisation
 // point and replays the serial rule from there (exact for any input; runs are short because the mean gap
-// is many windows long).  A walk longer than DT_PHYS_MAX_WALK events (event rate x longest window >~ 5: far
-// beyond anything GBM records) is refused with the unit's CGRB_ST_DEADTIME_CHAIN status bit instead of
-// running for O(n^2).
+// is many windows long).  A walk that leaves the tile's halo (fused kernel: 256 events) or exceeds
+// DT_PHYS_MAX_WALK events (event rate x longest window >~ 3: far beyond anything GBM records) flags the unit
+// (CGRB_ST_DEADTIME_CHAIN) for the serial fix-up kernel at the end of this file instead of running for O(n^2).
 // ==========================================================================================
-#define DT_PHYS_MAX_WALK 4096
+#define DT_PHYS_MAX_WALK 1024
 struct DtModel {
     double tau, tau_ovf, tau_max;
 };
@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__rest
         double ti = 0.0;
         uint8_t pi = 0;
         if (i < end) {
-            const int k3 = dt_keep_any<MODE>(t, p, i, md);
+            const bool flagged = (MODE != 0) && ((*(volatile uint32_t *)&counts[wk.unit].status) & CGRB_ST_DEADTIME_CHAIN);
+            const int k3 = flagged ? 0 : dt_keep_any<MODE>(t, p, i, md);
             if (MODE != 0 && k3 == 2)
                 atomicOr(&counts[wk.unit].status, CGRB_ST_DEADTIME_CHAIN);
             keep = k3 == 1;
@@ -471,12 +472,6 @@ __device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, 
     return ti > t_end ? 1 : 0;
 }
 
-// physical model on the slow accessor (kept out of line like dt_keep_slow)
-__device__ __noinline__ int dt_keep_phys_slow(const MergedGlobal &m, int64_t i, const DtModel md)
-{
-    return dt_keep_phys(m, i, true, md);
-}
-
 // merge-path splits of every tile, one thread per tile: the ~23 dependent probes of each search are
 // hidden by the other tiles' searches instead of stalling a whole CTA at its first barrier.
 // splits[2w] = split at the tile's halo start, splits[2w+1] = split at the tile start.
@@ -605,6 +600,9 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
         __syncthreads();
         // keep flags of the tile's own events (local indices [l0, l0 + nt))
         MergedGlobal mg{A, B, pA, pB, nA, nB};
+        // physical mode: a unit already flagged for the serial fix-up needs no more work here
+        const bool flagged = (MODE != 0) && ((*(volatile uint32_t *)&counts[wk.unit].status) & CGRB_ST_DEADTIME_CHAIN);
+        (void)flagged;
 #pragma unroll
         for (int r = 0; r < MD_R; r++) {
             const int e = r * NT + threadIdx.x;
@@ -615,10 +613,10 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
                     if (keep == 2)
                         keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
                 } else {
+                    // no synchronisation point inside the tile's halo (256 events closer than the longest
+                    // window: never at GBM rates): the unit goes to the serial fix-up kernel
                     const EventArrays ev{s_t, s_p};
-                    keep = dt_keep_phys(ev, (int64_t)(l0 + e), g0 == 0, md);
-                    if (keep == 2)
-                        keep = dt_keep_phys_slow(mg, d0 + e, md);
+                    keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), g0 == 0, md);
                     if (keep == 2) {
                         atomicOr(&counts[wk.unit].status, CGRB_ST_DEADTIME_CHAIN);
                         keep = 0;
@@ -667,3 +665,72 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
     }
 }
 
+
+// ==========================================================================================
+// Physical dead time, serial fix-up.  A unit whose events stay closer than the longest window for more than
+// DT_PHYS_MAX_WALK events in a row has no synchronisation point for the parallel resolution above (event rate x
+// window > ~5: far beyond anything GBM records); the kernels flag it (CGRB_ST_DEADTIME_CHAIN) and this kernel
+// -- one warp per unit, lane 0 working, a no-op for every unflagged unit -- redoes that unit with the serial
+// definition itself, merging the two component lists on the fly when there is no merged list, and clears the flag.
+// ==========================================================================================
+__global__ void __launch_bounds__(128) k_deadtime_phys_fixup(const cgrb_unit_t *__restrict__ units, int n_units,
+                                                             const double *__restrict__ times_tot,
+                                                             const uint8_t *__restrict__ pha_tot,
+                                                             const double *__restrict__ times_bkg,
+                                                             const uint8_t *__restrict__ pha_bkg,
+                                                             const double *__restrict__ times_src,
+                                                             const uint8_t *__restrict__ pha_src,
+                                                             double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
+                                                             uint8_t *__restrict__ selection, cgrb_counts_t *counts,
+                                                             const DtModel md)
+{
+    const int ui = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (ui >= n_units || (threadIdx.x & 31) != 0)
+        return;
+    if (!(counts[ui].status & CGRB_ST_DEADTIME_CHAIN))
+        return;
+    const cgrb_unit_t *u = units + ui;
+    double *ot = times_out + u->tot_off;
+    uint8_t *op = pha_out + u->tot_off;
+    int64_t kept = 0;
+    double t_end = -INFINITY;
+    if (times_tot) {
+        const double *t = times_tot + u->tot_off;
+        const uint8_t *p = pha_tot + u->tot_off;
+        const int64_t n = counts[ui].n_total;
+        for (int64_t i = 0; i < n; i++) {
+            const double ti = t[i];
+            const uint8_t pi = p[i];
+            const bool keep = (i == 0) || ti > t_end;
+            if (keep) {
+                t_end = ti + (pi == 127 ? md.tau_ovf : md.tau);
+                ot[kept] = ti;
+                op[kept] = pi;
+                kept++;
+            }
+            if (selection)
+                selection[u->tot_off + i] = keep ? 1 : 0;
+        }
+    } else {
+        const double *A = times_bkg + u->bkg_off, *B = times_src + u->src_off;
+        const uint8_t *pA = pha_bkg + u->bkg_off, *pB = pha_src + u->src_off;
+        const int64_t nA = counts[ui].n_bkg, nB = counts[ui].n_src;
+        int64_t ia = 0, ib = 0;
+        for (int64_t i = 0; i < nA + nB; i++) {
+            const bool take_a = ia < nA && (ib >= nB || A[ia] <= B[ib]);     // ties: background first
+            const double ti = take_a ? A[ia] : B[ib];
+            const uint8_t pi = take_a ? pA[ia] : pB[ib];
+            ia += take_a ? 1 : 0;
+            ib += take_a ? 0 : 1;
+            if (i == 0 || ti > t_end) {
+                t_end = ti + (pi == 127 ? md.tau_ovf : md.tau);
+                ot[kept] = ti;
+                op[kept] = pi;
+                kept++;
+            }
+        }
+        counts[ui].n_total = nA + nB;
+    }
+    counts[ui].n_kept = kept;
+    counts[ui].status &= ~CGRB_ST_DEADTIME_CHAIN;
+}

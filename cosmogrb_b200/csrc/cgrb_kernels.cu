@@ -511,6 +511,9 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
         LAUNCH("k_deadtime_write_phys", s, k_deadtime_write<1><<<(unsigned)n_work, NT, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_tot, d_pha_tot, d_tile_count, d_times_out,
             d_pha_out, d_selection, d_counts, md));
+        LAUNCH("k_deadtime_phys_fixup", s, k_deadtime_phys_fixup<<<(n_units * 32 + 127) / 128, 128, 0, s>>>(
+            d_units, n_units, d_times_tot, d_pha_tot, nullptr, nullptr, nullptr, nullptr, d_times_out, d_pha_out,
+            d_selection, d_counts, md));
     }
     return check_launch("cgrb_gbm_dead_time");
 }
@@ -545,6 +548,9 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
         LAUNCH("k_merge_deadtime_phys", s, k_merge_deadtime<1><<<(unsigned)n_work, NT, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
             (unsigned long long *)d_workspace, splits, d_times_out, d_pha_out, d_counts, md));
+        LAUNCH("k_deadtime_phys_fixup", s, k_deadtime_phys_fixup<<<(n_units * 32 + 127) / 128, 128, 0, s>>>(
+            d_units, n_units, nullptr, nullptr, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src, d_times_out,
+            d_pha_out, nullptr, d_counts, md));
     }
     return check_launch("cgrb_merge_dead_time");
 }

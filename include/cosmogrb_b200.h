@@ -46,7 +46,7 @@ extern "C" {
 #define CGRB_ST_OUT_CAPACITY 16u     /* an output buffer was too small                      */
 #define CGRB_ST_ENVELOPE 32u         /* energy envelope failed to dominate the target (bug)  */
 #define CGRB_ST_MAJORANT 128u        /* thinning majorant failed to dominate lambda(t) (bug)            */
-#define CGRB_ST_DEADTIME_CHAIN 64u   /* physical dead time: > 4096 consecutive events closer than the longest window */
+#define CGRB_ST_DEADTIME_CHAIN 64u   /* physical dead time: unit handed to the serial fix-up (transient; cleared by it) */
 
 /* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
 #define CGRB_NBINS 140
@@ -296,7 +296,9 @@ int cgrb_combine(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_w
  *   CGRB_DEADTIME_PHYSICAL: the non-paralyzable detector the reference's docstring describes (§8 f4):
  *       EVERY kept event opens a window (tau_overflow for channel 127, else tau); an event is kept iff
  *       t > t_end of the last kept event.  Not computed by the reference; checked against the serial
- *       definition in oracle/cgrb_oracle.c (co_gbm_dead_time_physical).
+ *       definition in oracle/cgrb_oracle.c (co_gbm_dead_time_physical).  Resolved in parallel from
+ *       synchronisation points (gaps longer than the longest window); a unit without one inside the
+ *       look-back range (event rate x window > ~3) is redone serially by a fix-up kernel of the same call.
  * A NULL model pointer means CGRB_DEADTIME_REFERENCE. */
 #define CGRB_DEADTIME_REFERENCE 0
 #define CGRB_DEADTIME_PHYSICAL 1

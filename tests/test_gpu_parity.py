@@ -246,17 +246,28 @@ def test_dead_time_physical_random(engine, rate, frac127):
     assert abs(want.mean() - 1.0 / (1.0 + rate * mean_tau)) < 0.01
 
 
-def test_dead_time_physical_refuses_runaway_chains(engine):
-    """rate x window >> 1: no synchronisation point within 4096 events -> loud status, not an O(n^2) walk"""
-    n = 20000
-    t = np.arange(n) * 1e-7
-    pha = np.full(n, 127)
-    with pytest.raises(_capi.EngineError, match="physical dead time"):
-        engine.gbm_dead_time(t, pha, mode="physical")
-    with pytest.raises(_capi.EngineError, match="physical dead time"):
-        engine.combine_dead_time(t[::2], pha[::2], t[1::2], pha[1::2], mode="physical")
-    # the literal rule has no such limit
-    assert np.array_equal(engine.gbm_dead_time(t, pha), orc.gbm_dead_time(t, pha))
+def test_dead_time_physical_runaway_chains_take_the_serial_fix_up(engine):
+    """rate x window >> 1: no synchronisation point inside the look-back range -> the unit is flagged and redone by
+    the serial fix-up kernel of the same call (exact, status clear), not walked in O(n^2) and not refused"""
+    n = 60000
+    rs = np.random.RandomState(5)
+    t = np.cumsum(rs.exponential(1e-7, n))              # 1e7 events/s: every gap far below the 10 us window
+    pha = rs.randint(0, 128, n)
+    want = orc.gbm_dead_time_physical(t, pha)
+    assert 0.005 < want.mean() < 0.05
+    assert np.array_equal(engine.gbm_dead_time(t, pha, mode="physical"), want)
+    is_src = rs.random_sample(n) < 0.5
+    wt, wp = orc.combine(t[~is_src], pha[~is_src], t[is_src], pha[is_src])
+    sel = orc.gbm_dead_time_physical(wt, wp)
+    for fused in (True, False):
+        got_t, got_p = engine.combine_dead_time(t[~is_src], pha[~is_src], t[is_src], pha[is_src], fused=fused,
+                                                mode="physical")
+        assert np.array_equal(got_t, wt[sel]) and np.array_equal(got_p.astype("f8"), wp[sel]), fused
+    # a regular arithmetic train of overflow events (every 11th kept), and the literal rule on the same input
+    t2 = np.arange(20000) * 1e-6
+    p2 = np.full(20000, 127)
+    assert np.array_equal(engine.gbm_dead_time(t2, p2, mode="physical"), orc.gbm_dead_time_physical(t2, p2))
+    assert np.array_equal(engine.gbm_dead_time(t2, p2), orc.gbm_dead_time(t2, p2))
 
 
 def test_combine_and_dead_time_pipeline(engine):
