@@ -39,6 +39,31 @@ def test_struct_layouts_match_header():
         assert int(m.group(1)) == getattr(_capi, f"DT_{name}")
 
 
+def test_small_structs_and_constants_match_header():
+    """ctypes mirrors of the small C structs and the tile / status constants the host relies on"""
+    src = open(os.path.join(ROOT, "include", "cosmogrb_b200.h")).read()
+    assert ctypes.sizeof(_capi.DeadtimeModel) == 24 and ctypes.sizeof(_capi.TriggerPar) == 32
+    assert ctypes.sizeof(_capi.RngDesc) == 40
+    for name, val in (("CGRB_TRIG_TILE", _capi.TRIG_TILE), ("CGRB_MD_TILE", _capi.MD_TILE), ("CGRB_DT_TILE", _capi.DT_TILE),
+                      ("CGRB_MERGE_TILE", _capi.MERGE_TILE), ("CGRB_ABI_VERSION", _capi.ABI_VERSION),
+                      ("CGRB_DEADTIME_PHYSICAL", _capi.DEADTIME_PHYSICAL)):
+        m = re.search(rf"#define {name} (\d+)", src)
+        assert m and int(m.group(1)) == val, name
+    for name, val in (("CGRB_ST_DEADTIME_CHAIN", _capi.ST_DEADTIME_CHAIN), ("CGRB_ST_MAJORANT", _capi.ST_MAJORANT),
+                      ("CGRB_ST_ENVELOPE", _capi.ST_ENVELOPE), ("CGRB_ST_OUT_CAPACITY", _capi.ST_OUT_CAPACITY)):
+        m = re.search(rf"#define {name} (\d+)u", src)
+        assert m and int(m.group(1)) == val, name
+    # dead-time model validation happens before any launch: testable without a device
+    lib = _capi.load()
+    bad = _capi.DeadtimeModel(7, 0, 2.6e-6, 10e-6)
+    one = np.zeros(8, dtype=np.uint8).ctypes.data
+    rc = lib.cgrb_gbm_dead_time(one, 1, one, 1, one, one, one, one, one, one, None, one, ctypes.byref(bad), None)
+    assert rc == -1 and b"dead-time mode" in lib.cgrb_last_error()
+    neg = _capi.DeadtimeModel(_capi.DEADTIME_PHYSICAL, 0, -1.0, 10e-6)
+    rc = lib.cgrb_merge_dead_time(one, 1, one, 1, one, one, one, one, one, one, one, one, one, ctypes.byref(neg), None)
+    assert rc == -1 and b"finite and >= 0" in lib.cgrb_last_error()
+
+
 def test_build_work():
     u = np.zeros(3, dtype=_capi.UNIT_DTYPE)
     u["src_cap"] = [0, 8192, 20000]
