@@ -158,3 +158,87 @@ def test_trigger_bin_index_fast_path_is_exact(t0, span):
     # sizeable fraction of a bin (then everything takes the exact edge test)
     if abs(t0) < 1e9:
         assert n_fast > 0.95 * 20000
+
+
+def merge_split(A, B, d):
+    """csrc/cgrb_deadtime.cuh: merge_split -- number of background events among the first d merged events"""
+    nA, nB = len(A), len(B)
+    lo, hi = max(0, d - nB), min(d, nA)
+    while lo < hi:
+        mid = (lo + hi) >> 1
+        if A[mid] <= B[d - 1 - mid]:        # ties: background first
+            lo = mid + 1
+        else:
+            hi = mid
+    return lo
+
+
+def test_merge_path_tiles_equal_the_reference_combine():
+    """k_merge_splits / k_merge_deadtime: every tile of the merged order (+ its look-back halo) is rebuilt from the
+    merge-path splits of its ends and per-thread serial merges of 9 elements; stitched together the tiles are the
+    oracle's combine (lightcurve.py:131-151: stable two-way merge, background first on ties)."""
+    rs = np.random.RandomState(2)
+    TILE, HALO, NT = 2048, 256, 256
+    PER = (TILE + HALO) // NT
+    for nA, nB, ties in ((7000, 9000, True), (0, 5000, False), (5000, 0, False), (1, 1, True), (30000, 300, True)):
+        A = np.sort(rs.uniform(0, 10, nA))
+        B = np.sort(rs.uniform(0, 10, nB))
+        if ties and nA > 10 and nB > 10:
+            B[5:9] = A[3]
+            A[100:103] = B[50] if nB > 50 else A[100:103]
+            A.sort()
+            B.sort()
+        pA, pB = rs.randint(0, 128, nA), rs.randint(0, 128, nB)
+        want_t, want_p = orc.combine(A, pA, B, pB)
+        total = nA + nB
+        got_t, got_p = np.empty(total), np.empty(total)
+        for d0 in range(0, total, TILE):
+            d1 = min(d0 + TILE, total)
+            g0 = max(0, d0 - HALO)
+            i0, i1 = merge_split(A, B, g0), (nA if d1 == total else merge_split(A, B, d1))
+            j0, j1 = g0 - i0, d1 - i1
+            a_, b_ = A[i0:i1], B[j0:j1]
+            pa_, pb_ = pA[i0:i1], pB[j0:j1]
+            na, nb = len(a_), len(b_)
+            n = na + nb
+            st, sp = np.empty(n), np.empty(n)
+            for tid in range(NT):                   # one thread: PER consecutive outputs from its own split
+                q0 = min(tid * PER, n)
+                ia = merge_split(a_, b_, q0)
+                ib = q0 - ia
+                for r in range(PER):
+                    q = q0 + r
+                    if q >= n:
+                        break
+                    take_a = ia < na and (ib >= nb or a_[ia] <= b_[ib])
+                    st[q], sp[q] = (a_[ia], pa_[ia]) if take_a else (b_[ib], pb_[ib])
+                    ia += 1 if take_a else 0
+                    ib += 0 if take_a else 1
+            l0 = d0 - g0
+            got_t[d0:d1], got_p[d0:d1] = st[l0:l0 + (d1 - d0)], sp[l0:l0 + (d1 - d0)]
+            # the halo really is the merged order just before the tile
+            assert np.array_equal(st[:l0], want_t[g0:d0])
+        assert np.array_equal(got_t, want_t) and np.array_equal(got_p, want_p)
+
+
+def test_background_channel_guide_equals_numpy_choice():
+    """k_background: channel = searchsorted(cdf, u, 'right') clamped to the last channel (numpy's legacy choice,
+    background.py:93), found from a 128-entry guide (guide[m] = searchsorted(cdf, m / 128, 'right')) and a forward
+    walk"""
+    from tests import helpers as h
+
+    rs = np.random.RandomState(9)
+    for det in ("n0", "b1"):
+        w = np.asarray(h.bkg_weights(det)).astype("f8")
+        cdf = w.cumsum()
+        cdf /= cdf[-1]
+        guide = np.minimum(np.searchsorted(cdf, np.arange(128) / 128.0, "right"), 127)
+        u = np.concatenate((rs.random_sample(50000), cdf[:-1], np.nextafter(cdf[:-1], 0), [0.0, np.nextafter(1.0, 0)]))
+        want = np.minimum(np.searchsorted(cdf, u, "right"), 127)
+        got = np.empty(len(u), dtype=int)
+        for k, uc in enumerate(u):
+            j = int(guide[min(max(int(uc * 128.0), 0), 127)])
+            while j < 127 and not (uc < cdf[j]):
+                j += 1
+            got[k] = j
+        assert np.array_equal(got, want)
