@@ -79,16 +79,43 @@ def test_sample_events_injected(engine, params, seed):
     assert np.all(np.diff(got_t) >= 0)
 
 
-def test_sample_energy_injected_serial_replay(engine):
+@pytest.mark.parametrize("det,extrap,kind", [("n5", "linear", 0), ("n5", "clamp", 0), ("b0", "linear", 0),
+                                             ("b0", "clamp", 0), ("n0", "clamp", 0), ("n3", "linear", 1),
+                                             ("b1", "clamp", 1)])
+def test_sample_events_injected_detectors_and_variants(engine, det, extrap, kind):
+    """the same decision-level check on other NaI detectors, the BGO detectors, the `clamp` interpolation variant
+    and the constant CPL (cpl_constant_functions.py:66-105)"""
+    params = h.CONFTEST_BRIGHT if kind == 0 else dict(z=1.0, peak_flux=4e-6, alpha=-0.9, ep=300.0, duration=3.0)
+    rsp, b = _batch(engine, params, det=det, kind=kind, interp_extrap=extrap)
+    s = h.oracle_source(rsp, kind=kind, interp_extrap=extrap, **params)
+    fmax = float(b.units["fmax"][0])
+    assert fmax == pytest.approx(orc.fmax(s, rsp.effective_area_packed, 0.0, params["duration"]), rel=1e-11)
+    cap = int(b.units["src_cap"][0])
+    u = np.random.RandomState(13).random_sample(2 * cap + 2)
+    want_t, want_nc, want_ct, want_acc = orc.sample_events(s, rsp.effective_area_packed, 0.0, params["duration"],
+                                                            fmax, orc.Rng(u=u), want_candidates=True)
+    engine.sample_events(b, Injected(thin=[u]), want_candidates=True)
+    c = engine.fetch_counts(b)
+    assert c["status"][0] == 0 and c["n_candidates"][0] == want_nc and want_nc > 100
+    assert np.array_equal(b.t["cand_accept"][:want_nc].cpu().numpy().astype(bool), want_acc)
+    np.testing.assert_allclose(b.t["cand_times"][:want_nc].cpu().numpy(), want_ct, rtol=TIGHT)
+    np.testing.assert_allclose(b.view("times_src", 0, "src"), want_t, rtol=TIGHT)
+
+
+@pytest.mark.parametrize("det,extrap,kind", [("n0", "linear", 0), ("n0", "clamp", 0), ("n5", "linear", 0),
+                                             ("b0", "linear", 0), ("b0", "clamp", 0), ("n0", "linear", 1),
+                                             ("b0", "clamp", 1)])
+def test_sample_energy_injected_serial_replay(engine, det, extrap, kind):
     """Strict serial replay: per-photon offsets are the positions the reference's serial stream
     reaches (cumulative 2 x trials), so the GPU consumes exactly the reference's uniforms."""
-    params = h.CONFTEST_BRIGHT
-    rsp, b = _batch(engine, params)
-    s = h.oracle_source(rsp, **params)
+    params = h.CONFTEST_BRIGHT if kind == 0 else dict(z=1.0, peak_flux=4e-6, alpha=-0.9, ep=300.0, duration=3.0)
+    rsp, b = _batch(engine, params, det=det, kind=kind, interp_extrap=extrap)
+    s = h.oracle_source(rsp, kind=kind, interp_extrap=extrap, **params)
     rs = np.random.RandomState(5)
     times = np.sort(rs.uniform(0.05, 2.0, 600))
-    u = rs.random_sample(600 * 2 * 400)
+    u = rs.random_sample(600 * 2 * 1500)
     want_e, want_tr = orc.sample_energy(s, rsp.effective_area_packed, times, orc.Rng(u=u))
+    assert 2 * int(want_tr.sum()) < len(u)
     off = np.concatenate(([0], np.cumsum(2 * want_tr.astype(np.int64))[:-1]))
     n = len(times)
     assert n <= b.units["src_cap"][0]

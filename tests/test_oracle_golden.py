@@ -168,3 +168,49 @@ def test_gammaincc_against_scipy():
     got = orc.gammaincc(a, x)
     ok = want > 1e-290
     assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) < 1e-12
+
+
+# ---- second golden set (oracle/make_golden_r2.py): ConstantCPL at ~1300 events, BGO / n5 detectors, a window of
+# ---- the benchmarked bright long burst
+EXTRA_CASES = [("constant_n0_s4", "n0", 1, 4), ("constant_n0_s5", "n0", 1, 5), ("constant_b0_s4", "b0", 1, 4),
+               ("constant_b0_s5", "b0", 1, 5), ("bright_n5_s0", "n5", 0, 0), ("bright_b0_s0", "b0", 0, 0)]
+
+
+def extra_params(key):
+    from oracle import make_golden_r2 as mg2
+
+    return mg2.CONSTANT_BRIGHT if key.startswith("constant") else h.CONFTEST_BRIGHT
+
+
+@pytest.mark.parametrize("extrap", ["linear", "clamp"])
+@pytest.mark.parametrize("key,det,kind,seed", EXTRA_CASES)
+def test_extra_source_stream_replay(extrap, key, det, kind, seed):
+    g = load(f"spectral_extra_{extrap}.npz")
+    p = extra_params(key)
+    rsp = h.response(det)
+    ea = rsp.effective_area_packed
+    s = h.oracle_source(rsp, kind=kind, interp_extrap=extrap, **p)
+    fm = float(g[f"fmax_{key}"])
+    assert abs(orc.fmax(s, ea, 0.0, p["duration"]) - fm) <= 1e-12 * fm
+    rng = orc.Rng(seed=seed)
+    t, nc = orc.sample_events(s, ea, 0.0, p["duration"], fm, rng)
+    assert nc == int(g[f"ncand_{key}"]) and len(t) == len(g[f"events_{key}"])
+    np.testing.assert_allclose(t, g[f"events_{key}"], rtol=1e-12)
+    n_e = len(g[f"energy_{key}"])
+    e, tr = orc.sample_energy(s, ea, g[f"events_{key}"][:n_e], rng)
+    np.testing.assert_allclose(e, g[f"energy_{key}"], rtol=1e-12)
+    assert np.array_equal(tr, g[f"trials_{key}"])
+    pha = orc.digitize(g[f"energy_{key}"], rsp.energy_edges, rsp.cumulative_matrix, rng)
+    assert np.array_equal(pha, g[f"pha_{key}"].astype("f8"))
+
+
+def test_extra_bright_long_window():
+    from oracle import make_golden_r2 as mg2
+
+    g = load("spectral_extra_linear.npz")
+    rsp = h.response("n0")
+    s = h.oracle_source(rsp, **h.BRIGHT_LONG)
+    t, nc = orc.sample_events(s, rsp.effective_area_packed, mg2.C2_WINDOW[0], mg2.C2_WINDOW[1],
+                              float(g["fmax_long_window_n0_s7"]), orc.Rng(seed=7))
+    assert nc == int(g["ncand_long_window_n0_s7"])
+    np.testing.assert_allclose(t, g["events_long_window_n0_s7"], rtol=1e-12)
