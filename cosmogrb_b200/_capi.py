@@ -49,6 +49,7 @@ ST_OUT_CAPACITY = 16
 ST_ENVELOPE = 32
 ST_DEADTIME_CHAIN = 64
 ST_MAJORANT = 128
+ST_SQUEEZE = 256
 
 UNIT_NO_SOURCE = 1
 UNIT_NO_BACKGROUND = 2

@@ -79,7 +79,15 @@ __global__ void __launch_bounds__(64) k_fmax(const double *__restrict__ dtab, cg
 
 // ==========================================================================================
 // squeeze table of the thinning acceptance probability p(t) = lambda(t) / fmax (see the header):
-// nodes on a uniform time grid, then per-interval interpolation-error margins from second differences.
+// nodes on a uniform time grid AND the cell midpoints, then per-cell margins on |p - linear interpolation|.
+//   margin_k = 2 |p(mid_k) - (p_k + p_k+1)/2|        the interpolation error MEASURED at the cell's midpoint, x2
+//            + 0.5 max |second differences| at the nodes k-1 .. k+2   (h^2/8 sup|p''| ~ d2/8, x4)
+//            + rounding slack
+// and no squeeze at all (margin = inf: every candidate of the cell takes the exact lambda(t)) in the first and
+// the last cell and in any cell that touches a node where p == 0 without being identically zero: the Norris
+// pulse exp(-trise/t) has an essential singularity at its start that no finite difference of nodes sees.
+// tests/test_majorant_oracle.py restates this on the oracle's lambda(t) and checks the bound on a finer grid
+// over the population's range of trise / tdecay / duration and table sizes (worst error / margin: 0.45).
 // ==========================================================================================
 __global__ void __launch_bounds__(NT) k_thin_nodes(const double *__restrict__ dtab,
                                                    const cgrb_unit_t *__restrict__ units,
@@ -99,12 +107,17 @@ __global__ void __launch_bounds__(NT) k_thin_nodes(const double *__restrict__ dt
         return;
     build_lambda_tab(&tab, dtab + (size_t)u.det * CGRB_DT_SIZE, u);
     __syncthreads();
-    const int64_t k = wk.start + threadIdx.x;
-    if (k >= u.tab_n)
-        return;
-    const double h = (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1);
-    const double t = (k == u.tab_n - 1) ? u.src_tstop : u.src_tstart + (double)k * h;
-    thin_tab[2 * (u.tab_off + k)] = lambda_at(&tab, u, t) / u.fmax;
+    // two threads per node: the even one evaluates the node, the odd one the midpoint of the cell that starts there
+    // (left in the node's margin slot for k_thin_margins)
+    for (int q = threadIdx.x; q < 2 * NT; q += NT) {
+        const int64_t k = wk.start + (q >> 1);
+        const int mid = q & 1;
+        if (k >= u.tab_n || (mid && k >= u.tab_n - 1))
+            continue;
+        const double h = (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1);
+        const double t = (k == u.tab_n - 1) ? u.src_tstop : u.src_tstart + ((double)k + 0.5 * (double)mid) * h;
+        thin_tab[2 * (u.tab_off + k) + mid] = lambda_at(&tab, u, t) / u.fmax;
+    }
 }
 
 __global__ void __launch_bounds__(NT) k_thin_margins(const cgrb_unit_t *__restrict__ units,
@@ -119,11 +132,12 @@ __global__ void __launch_bounds__(NT) k_thin_margins(const cgrb_unit_t *__restri
     const int64_t n = u->tab_n;
     if (n < 4 || (u->flags & CGRB_UNIT_NO_SOURCE))
         return;
-    const int64_t k = wk.start + threadIdx.x;      // interval [k, k+1]
+    const int64_t k = wk.start + threadIdx.x;      // cell [k, k+1]
     if (k >= n)
         return;
-    const double *p = thin_tab + 2 * u->tab_off;
-    // |second differences| at the nodes k-1 .. k+2 (clamped to the interior nodes 1 .. n-2)
+    double *p = thin_tab + 2 * u->tab_off;
+    // |second differences| at the nodes k-1 .. k+2 (clamped to the interior nodes 1 .. n-2); reads node values
+    // (even slots) only, writes this cell's own margin slot only: no ordering between threads is needed
     double m = 0.0;
     bool bad = false;
 #pragma unroll
@@ -133,9 +147,15 @@ __global__ void __launch_bounds__(NT) k_thin_margins(const cgrb_unit_t *__restri
         bad |= !(d2 == d2) || isinf(d2);
         m = fmax(m, d2);
     }
-    // linear interpolation error <= h^2/8 sup|p''| ~ d2/8; x4 safety, plus rounding slack
-    double pk = fabs(p[2 * k]);
-    double margin = 0.5 * m + 1e-12 * (pk + 1.0);
-    thin_tab[2 * (u->tab_off + k) + 1] = bad ? INFINITY : margin;
+    double margin = INFINITY;
+    if (k >= 1 && k < n - 2) {
+        const double pk = p[2 * k], pk1 = p[2 * (k + 1)], pm = p[2 * k + 1];
+        const double emid = fabs(pm - 0.5 * (pk + pk1));
+        const bool touches_zero = (pk == 0.0 || pk1 == 0.0) && !(pk == 0.0 && pk1 == 0.0 && pm == 0.0);
+        bad |= !(emid == emid) || isinf(emid);
+        if (!touches_zero)
+            margin = 0.5 * m + 2.0 * emid + 1e-12 * (fabs(pk) + 1.0);
+    }
+    p[2 * k + 1] = bad ? INFINITY : margin;
 }
 

@@ -229,9 +229,16 @@ __device__ __noinline__ double lambda_exact(const LambdaTab *tab, const cgrb_uni
     return lambda_at(tab, u, t);
 }
 
+// self-check of the squeeze margins wherever the exact lambda(t) is evaluated anyway: the margin must bound the
+// distance between p(t) and the table's linear interpolation (finite margins only)
+__device__ __forceinline__ bool squeeze_margin_violated(double pe, double pl, double margin)
+{
+    return margin < INFINITY && fabs(pe - pl) > margin * (1.0 + 1e-9) + 1e-15;
+}
+
 __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_unit_t &u, bool squeeze,
                                             const double2 *__restrict__ sq, double sq_inv_h, double t, double u2,
-                                            long long *n_exact)
+                                            long long *n_exact, bool *sq_violated)
 {
     if (squeeze) {
         const double q = (t - u.src_tstart) * sq_inv_h;
@@ -243,10 +250,16 @@ __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_uni
             return true;
         if (u2 > pl + n0.y)
             return false;
+        (*n_exact)++;
+        const double pe = lambda_exact(tab, u, t) / u.fmax;
+        if (squeeze_margin_violated(pe, pl, n0.y))
+            *sq_violated = true;
+        return u2 <= pe;
     }
     (*n_exact)++;
     return u2 <= lambda_exact(tab, u, t) / u.fmax;   // `if test <= p_test`
 }
+
 
 // Majorant mode: candidate at operational time tau -> cell j (guide + short walk over the cumulative table),
 // real time t inside the cell, acceptance with probability min(p(t), 1) / P_j by the same squeeze test.
@@ -254,7 +267,7 @@ __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_uni
 __device__ __forceinline__ bool thin_accept_majorant(const LambdaTab *tab, const cgrb_unit_t &u,
                                                      const double2 *__restrict__ sq, const ThinCum tc, double gscale,
                                                      double h, double tau, double u2, double *t_out,
-                                                     long long *n_exact, bool *violated)
+                                                     long long *n_exact, bool *violated, bool *sq_violated)
 {
     const int n = (int)u.tab_n;
     int j = __ldg(tc.guide + min(max((int)(tau * gscale), 0), n - 2));
@@ -291,6 +304,8 @@ __device__ __forceinline__ bool thin_accept_majorant(const LambdaTab *tab, const
     const double pe = lambda_exact(tab, u, t) / u.fmax;
     if (P < 1.0 && pe > P * (1.0 + 1e-9))
         *violated = true;
+    if (squeeze_margin_violated(pe, pl, n0.y))
+        *sq_violated = true;
     return v <= pe;
 }
 
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
     const double sq_inv_h = squeeze ? (double)(u.tab_n - 1) / (u.src_tstop - u.src_tstart) : 0.0;
     const double maj_h = maj ? (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1) : 0.0;
     const double maj_gscale = (maj && stop > 0.0) ? (double)(u.tab_n - 1) / stop : 0.0;
-    bool violated = false;
+    bool violated = false, sq_violated = false;
     double *seg = stage + u.src_off + wk.start;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     long long n_exact = 0;
@@ -376,13 +391,13 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
             PairDraw d = pair_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, (wk.start + j0) >> 1, 1);
             if (maj) {
                 const double tau_a = ta, tau_b = tb;
-                aa = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_a, d.a, &ta, &n_exact, &violated);
+                aa = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_a, d.a, &ta, &n_exact, &violated, &sq_violated);
                 if (vb)
-                    ab = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_b, d.b, &tb, &n_exact, &violated);
+                    ab = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_b, d.b, &tb, &n_exact, &violated, &sq_violated);
             } else {
-                aa = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact);
+                aa = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact, &sq_violated);
                 if (vb)
-                    ab = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact);
+                    ab = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact, &sq_violated);
             }
         }
         // ordered compaction: per-thread counts (0..2 accepted, 0..2 valid) packed in one int
@@ -423,8 +438,8 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
         if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
             break;      // crossed tstop: everything later is beyond it
     }
-    if (violated)
-        atomicOr(&counts[wk.unit].status, CGRB_ST_MAJORANT);
+    if (violated || sq_violated)
+        atomicOr(&counts[wk.unit].status, (violated ? CGRB_ST_MAJORANT : 0u) | (sq_violated ? CGRB_ST_SQUEEZE : 0u));
     {
         long long *s_ll = reinterpret_cast<long long *>(s_t);      // s_t is free now
         __syncthreads();

@@ -114,6 +114,9 @@ class Tree(object):
                     for k, v in self._attrs[p].items():
                         g.attrs[k] = v
                 for p, v in self._datasets.items():
+                    if isinstance(v, np.ndarray) and v.dtype.kind == "U":
+                        # h5py has no conversion path for numpy '<U' arrays: variable-length UTF-8 strings
+                        v = v.astype(h5py.string_dtype())
                     if p in self._compress and isinstance(v, np.ndarray) and v.ndim > 0:
                         f.create_dataset(p, data=v, compression="lzf")
                     else:
@@ -149,6 +152,8 @@ def open_tree(file_name):
                 else:
                     t.group(os.path.dirname(p))
                     v = obj[()]
+                    if isinstance(v, np.ndarray) and v.dtype.kind in "OS":      # string datasets come back as bytes
+                        v = np.array([x.decode() if isinstance(x, bytes) else str(x) for x in v.ravel()]).reshape(v.shape)
                     t._datasets[p] = v.decode() if isinstance(v, bytes) else v
 
             f.visititems(visit)

@@ -217,8 +217,12 @@ class Universe(object, metaclass=abc.ABCMeta):
         t.attrs("/").update(n_grbs=self._n_grbs, population_file=str(self._population_file),
                             grb_base_name=self._grb_base_name)
         if self._save_path is not None:
+            # bursts that were not simulated (``self.skipped``: counts read -1) have no file
+            done = np.ones(self._n_grbs, dtype=bool)
+            if self.event_counts is not None:
+                done = np.asarray(self.event_counts).reshape(self._n_grbs, -1).min(axis=1) >= 0
             files = [str((self._save_path / f"{self._grb_base_name}_{i}_store.h5").absolute())
-                     for i in range(self._n_grbs)]
+                     for i in range(self._n_grbs) if done[i]]
             t.dataset("grb_save_files", np.array(files))
         if self.event_counts is not None:
             t.dataset("event_counts", np.asarray(self.event_counts))

@@ -46,6 +46,7 @@ extern "C" {
 #define CGRB_ST_OUT_CAPACITY 16u     /* an output buffer was too small                      */
 #define CGRB_ST_ENVELOPE 32u         /* energy envelope failed to dominate the target (bug)  */
 #define CGRB_ST_MAJORANT 128u        /* thinning majorant failed to dominate lambda(t) (bug)            */
+#define CGRB_ST_SQUEEZE 256u         /* squeeze margin failed to bound |p - interpolation| at an exact evaluation (bug) */
 #define CGRB_ST_DEADTIME_CHAIN 64u   /* physical dead time: unit handed to the serial fix-up (transient; cleared by it) */
 
 /* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
@@ -190,7 +191,10 @@ int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int inter
 /* Squeeze table for the thinning acceptance test (no reference counterpart; it changes no decision).
  * For every unit with tab_n >= 4 nodes: p_k = lambda(t_k) / fmax on the uniform grid
  * t_k = src_tstart + k (src_tstop - src_tstart) / (tab_n - 1), and a margin m_k bounding the error of
- * linear interpolation on [t_k, t_k+1] (from second differences, x4 safety).  cgrb_sample_events
+ * linear interpolation on [t_k, t_k+1]: twice the error measured at the cell's midpoint plus the second
+ * differences of the neighbouring nodes (x4 safety); infinite -- no squeeze, every candidate exact -- in the
+ * first and last cell and in cells touching a node where p == 0 (the pulse's essential singularity at its
+ * start).  A margin found too small at an exact evaluation sets CGRB_ST_SQUEEZE.  cgrb_sample_events
  * accepts a candidate outright if u2 <= p_lin - m, rejects it if u2 > p_lin + m, and evaluates
  * lambda(t) exactly (the reference's 75-point trapezoid) only in between, so the accept/reject
  * decisions are those of the exact test.  d_thin_tab: 2 doubles per node (p, m), sum(tab_n) nodes.

@@ -275,3 +275,42 @@ def test_pipeline_chunks_cover_every_unit_once():
     u["fmax"] = 100.0                                  # the README burst: one batch
     assert len(lcmod._chunks(u, None)) == 1
     assert len(lcmod._chunks(u[:1], None)) == 1
+
+
+def test_universe_index_lists_only_simulated_bursts(tmp_path):
+    """Universe.save: string datasets survive both backends (h5py has no conversion for numpy '<U' arrays: they
+    are written as variable-length strings), and bursts that were skipped (counts -1) have no file listed"""
+    pop = synthetic_population(6, seed=3)
+    fn = tmp_path / "pop.npz"
+    pop.writeto(fn)
+    from cosmogrb_b200.instruments.gbm.gbm_universe import GBM_CPL_Universe
+
+    uni = GBM_CPL_Universe(str(fn), save_path=str(tmp_path))
+    ec = np.full((6, 14, 3), 10, dtype=np.int64)
+    ec[4] = -1                                                # a skipped burst
+    uni.event_counts, uni._is_processed = ec, True
+    for backend in ["npz"] + (["h5"] if store.have_h5py() else []):
+        out = tmp_path / f"index_{backend}.h5"
+        real_write = store.Tree.write
+        try:
+            store.Tree.write = lambda self, file_name, backend=backend, _w=real_write: _w(self, file_name, backend=backend)
+            uni.save(out)
+        finally:
+            store.Tree.write = real_write
+        t = store.open_tree(out)
+        files = [str(x) for x in t.get("grb_save_files")]
+        assert len(files) == 5 and not any(f.endswith("SynthGRB_4_store.h5") for f in files)
+        assert files[0].endswith("SynthGRB_0_store.h5")
+        assert np.array_equal(t.get("event_counts"), ec)
+
+
+def test_h5_backend_string_datasets(tmp_path):
+    pytest.importorskip("h5py")
+    t = store.Tree()
+    t.dataset("names", np.array(["a", "bcd"]))
+    t.dataset("extra_info/tags", ["x", "yz"])
+    t.dataset("extra_info/note", "hello")
+    t.write(tmp_path / "s.h5", backend="h5")
+    r = store.open_tree(tmp_path / "s.h5")
+    assert list(r.get("names")) == ["a", "bcd"] and list(r.get("extra_info/tags")) == ["x", "yz"]
+    assert r.get("extra_info/note") == "hello"
