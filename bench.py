@@ -49,20 +49,16 @@ def emit(line):
 
 
 def bright_params():
-    from tests import helpers as h
+    from cosmogrb_b200 import workloads
 
-    return dict(h.BRIGHT_LONG)
+    return dict(workloads.BRIGHT_LONG)
 
 
 def build_inputs(grb_index=0):
     """Host-side inputs of one bright GRB: 14 unit records + 14 detector table blocks."""
-    from tests import helpers as h
+    from cosmogrb_b200 import workloads
 
-    p = bright_params()
-    dets = h.GBM_DETECTORS
-    tabs = [h.response(d).device_table(h.bkg_weights(d), "linear") for d in dets]
-    units = np.concatenate([h.unit(det_index=i, stream_id=16 * grb_index + i, **p) for i in range(len(dets))])
-    return units, tabs
+    return workloads.burst_inputs(bright_params(), grb_index=grb_index)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -124,12 +120,13 @@ def cpu_sample(n_windows, window_s, threads, seed=1):
     Returns (events, seconds, n_candidates, n_trials)."""
     from concurrent.futures import ThreadPoolExecutor
 
+    from cosmogrb_b200 import workloads as h
     from oracle import oracle as orc
-    from tests import helpers as h
 
     p = bright_params()
     rsp = h.response("n0")
-    s = h.oracle_source(rsp, **p)
+    s = orc.source(kind=0, interp_extrap="linear", peak_flux=p["peak_flux"], ep_start=p["ep_start"], ep_tau=p["ep_tau"],
+                   alpha=p["alpha"], trise=p["trise"], tdecay=p["tdecay"], z=p["z"], emin=rsp.emin, emax=rsp.emax)
     ea = rsp.effective_area_packed
     fm = orc.fmax(s, ea, 0.0, p["duration"])
     w = h.bkg_weights("n0")
