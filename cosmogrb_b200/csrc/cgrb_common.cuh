@@ -162,14 +162,23 @@ __device__ __forceinline__ void build_lambda_tab(LambdaTab *tab, const double *d
     }
 }
 
-__device__ __forceinline__ double lambda_at(const LambdaTab *tab, const cgrb_unit_t &u, double t)
+__device__ __forceinline__ double lambda_of(const LambdaTab *tab, const cgrb_unit_t &u, const SpecT s)
 {
-    SpecT s = spec_at(u, t);
     double acc = 0.0;
 #pragma unroll 5
     for (int m = 0; m < CGRB_NE_LAMBDA; m++)
         acc += tab->c[m] * exp(-tab->x[m] * s.inv_ec);
     return s.norm * exp(-u.alpha * s.log_ec) * acc;
+}
+__device__ __forceinline__ double lambda_at(const LambdaTab *tab, const cgrb_unit_t &u, double t)
+{
+    return lambda_of(tab, u, spec_at(u, t));
+}
+// counts/s per unit of energy flux at time t: lambda(t) / F(t), a smooth function of t through ep(t) only
+// (time-evolving CPL; no pulse factor, hence no singularity at the pulse start)
+__device__ __forceinline__ double lambda_per_flux_at(const LambdaTab *tab, const cgrb_unit_t &u, double t)
+{
+    return lambda_of(tab, u, spec_with(u, 1.0, u.ep_start / (1.0 + t / u.ep_tau)));
 }
 
 

@@ -203,16 +203,9 @@ __device__ __forceinline__ double norris(double x, double K, double t_rise, doub
     return 0.0;
 }
 
-__device__ __forceinline__ SpecT spec_at(const cgrb_unit_t &u, double t)
+// spectrum with energy flux F and peak energy ep
+__device__ __forceinline__ SpecT spec_with(const cgrb_unit_t &u, double F, double ep)
 {
-    double F, ep;
-    if (u.kind == 0) {
-        F = norris(t, u.peak_flux, u.trise, u.tdecay);   // cpl_functions.py:86-88
-        ep = u.ep_start / (1.0 + t / u.ep_tau);          // :90
-    } else {
-        F = u.peak_flux;                                 // cpl_constant_functions.py:40-42
-        ep = u.ep_start;
-    }
     const double opz = 1.0 + u.z;
     const double a = 10.0 * opz, b = 1.0e4 * opz;        // :78-79
     double ec = (u.alpha == -2.0) ? ep / 0.0001 : ep / (2.0 + u.alpha);  // :13-20
@@ -226,6 +219,14 @@ __device__ __forceinline__ SpecT spec_at(const cgrb_unit_t &u, double t)
     s.log_ec = log(ec);
     s.inv_ec = 1.0 / ec;
     return s;
+}
+
+__device__ __forceinline__ SpecT spec_at(const cgrb_unit_t &u, double t)
+{
+    if (u.kind == 0)
+        return spec_with(u, norris(t, u.peak_flux, u.trise, u.tdecay),       // cpl_functions.py:86-88
+                         u.ep_start / (1.0 + t / u.ep_tau));                 // :90
+    return spec_with(u, u.peak_flux, u.ep_start);                            // cpl_constant_functions.py:40-42
 }
 
 // literal cpl value at rest-frame energy x with log(x) supplied (cpl_functions.py:37-44)

@@ -83,10 +83,15 @@ __global__ void __launch_bounds__(64) k_fmax(const double *__restrict__ dtab, cg
 //   margin_k = 2 |p(mid_k) - (p_k + p_k+1)/2|        the interpolation error MEASURED at the cell's midpoint, x2
 //            + 0.5 max |second differences| at the nodes k-1 .. k+2   (h^2/8 sup|p''| ~ d2/8, x4)
 //            + rounding slack
-// and no squeeze at all (margin = inf: every candidate of the cell takes the exact lambda(t)) in the first and
-// the last cell and in any cell that touches a node where p == 0 without being identically zero: the Norris
-// pulse exp(-trise/t) has an essential singularity at its start that no finite difference of nodes sees.
-// tests/test_majorant_oracle.py restates this on the oracle's lambda(t) and checks the bound on a finer grid
+// Cells without a squeeze (every candidate takes the exact lambda(t)) are marked in the margin slot:
+//   +inf    no bound known: the majorant proposal uses P = 1 there (cells touching a node where p == 0 without
+//           being identically zero; non-finite values)
+//   -B < 0  the FIRST cell of a time-evolving CPL: the Norris pulse exp(-trise/t) has an essential singularity at
+//           its start that no finite difference of nodes sees, so the cell is not interpolated at all; the majorant
+//           proposal uses the bound  p <= B = sup K x sup G / fmax  with K the pulse (monotone up to its maximum at
+//           sqrt(trise tdecay): sup over the cell is analytic) and G = lambda / K, a smooth function of ep(t) only
+//           (sup from its values at the cell's ends and midpoint plus twice their second difference).
+// tests/test_majorant_oracle.py restates this on the oracle's lambda(t) and checks the bounds on a finer grid
 // over the population's range of trise / tdecay / duration and table sizes (worst error / margin: 0.45).
 // ==========================================================================================
 __global__ void __launch_bounds__(NT) k_thin_nodes(const double *__restrict__ dtab,
@@ -115,6 +120,18 @@ __global__ void __launch_bounds__(NT) k_thin_nodes(const double *__restrict__ dt
         if (k >= u.tab_n || (mid && k >= u.tab_n - 1))
             continue;
         const double h = (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1);
+        if (mid && k == 0 && u.kind == 0) {
+            // first cell of a pulse: -B, the bound on p over the cell (see above)
+            const double a = u.src_tstart, b = u.src_tstart + h;
+            const double tpk = sqrt(u.trise * u.tdecay);
+            const double supK = (b > 0.0) ? norris(fmin(fmax(tpk, a), b), u.peak_flux, u.trise, u.tdecay) : 0.0;
+            const double g0 = lambda_per_flux_at(&tab, u, a), gm = lambda_per_flux_at(&tab, u, a + 0.5 * h),
+                         g1 = lambda_per_flux_at(&tab, u, b);
+            const double supG = fmax(g0, fmax(gm, g1)) + 2.0 * fabs(g0 - 2.0 * gm + g1);
+            const double B = supK * supG / u.fmax * (1.0 + 1e-6) + 1e-300;
+            thin_tab[2 * u.tab_off + 1] = (B == B && B < INFINITY) ? -B : INFINITY;
+            continue;
+        }
         const double t = (k == u.tab_n - 1) ? u.src_tstop : u.src_tstart + ((double)k + 0.5 * (double)mid) * h;
         thin_tab[2 * (u.tab_off + k) + mid] = lambda_at(&tab, u, t) / u.fmax;
     }
@@ -148,7 +165,12 @@ __global__ void __launch_bounds__(NT) k_thin_margins(const cgrb_unit_t *__restri
         m = fmax(m, d2);
     }
     double margin = INFINITY;
-    if (k >= 1 && k < n - 2) {
+    if (k == 0 && u->kind == 0) {
+        const double mb = p[1];             // -B, left by k_thin_nodes
+        if (mb < 0.0)
+            margin = mb;
+        bad = false;
+    } else if (k < n - 1) {
         const double pk = p[2 * k], pk1 = p[2 * (k + 1)], pm = p[2 * k + 1];
         const double emid = fabs(pm - 0.5 * (pk + pk1));
         const bool touches_zero = (pk == 0.0 || pk1 == 0.0) && !(pk == 0.0 && pk1 == 0.0 && pm == 0.0);

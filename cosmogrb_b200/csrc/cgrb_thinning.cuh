@@ -38,6 +38,8 @@ __device__ __forceinline__ bool unit_uses_majorant(const double *thin_cum, const
 }
 __device__ __forceinline__ double majorant_of(const double2 n0, const double2 n1)
 {
+    if (n0.y < 0.0)
+        return fmin(-n0.y, 1.0);                    // first cell of a pulse: the stored bound, no squeeze
     const double P = fmax(n0.x, n1.x) + n0.y;
     return (P <= 1.0) ? fmax(P, 0.0) : 1.0;        // NaN / inf margins -> 1 (the reference's own ceiling)
 }
@@ -233,7 +235,7 @@ __device__ __noinline__ double lambda_exact(const LambdaTab *tab, const cgrb_uni
 // distance between p(t) and the table's linear interpolation (finite margins only)
 __device__ __forceinline__ bool squeeze_margin_violated(double pe, double pl, double margin)
 {
-    return margin < INFINITY && fabs(pe - pl) > margin * (1.0 + 1e-9) + 1e-15;
+    return margin >= 0.0 && margin < INFINITY && fabs(pe - pl) > margin * (1.0 + 1e-9) + 1e-15;
 }
 
 __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_unit_t &u, bool squeeze,
@@ -246,10 +248,12 @@ __device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_uni
         const double fr = q - (double)kq;
         const double2 n0 = __ldg(sq + kq), n1 = __ldg(sq + kq + 1);
         const double pl = n0.x + (n1.x - n0.x) * fr;
-        if (u2 <= pl - n0.y)
-            return true;
-        if (u2 > pl + n0.y)
-            return false;
+        if (n0.y >= 0.0) {                  // negative: a cell without squeeze
+            if (u2 <= pl - n0.y)
+                return true;
+            if (u2 > pl + n0.y)
+                return false;
+        }
         (*n_exact)++;
         const double pe = lambda_exact(tab, u, t) / u.fmax;
         if (squeeze_margin_violated(pe, pl, n0.y))
@@ -296,10 +300,12 @@ __device__ __forceinline__ bool thin_accept_majorant(const LambdaTab *tab, const
         return false;
     const double v = u2 * P;
     const double pl = n0.x + (n1.x - n0.x) * fr;
-    if (v <= pl - n0.y)
-        return true;
-    if (v > pl + n0.y)
-        return false;
+    if (n0.y >= 0.0) {                      // negative: a cell without squeeze
+        if (v <= pl - n0.y)
+            return true;
+        if (v > pl + n0.y)
+            return false;
+    }
     (*n_exact)++;
     const double pe = lambda_exact(tab, u, t) / u.fmax;
     if (P < 1.0 && pe > P * (1.0 + 1e-9))

@@ -22,20 +22,34 @@ SQUEEZE_RATIO, MIN_CAND, MAX_NODES = 8, 2048, 1 << 14       # engine.py: squeeze
 
 def _margins(p, pm):
     """k_thin_margins: per cell, 2 x the interpolation error measured at the midpoint + 0.5 x the largest second
-    difference of the nodes k-1 .. k+2 + rounding slack; infinite (no squeeze) in the first and last cell and in
-    cells touching a node where p == 0 without being identically zero"""
+    difference of the nodes k-1 .. k+2 + rounding slack; infinite (no squeeze) in cells touching a node where p == 0
+    without being identically zero.  (The first cell of a pulse is overwritten by ``_first_cell_bound``.)"""
     n = len(p)
     d2 = np.abs(p[:-2] - 2.0 * p[1:-1] + p[2:])                 # second differences at the interior nodes 1 .. n-2
     idx = np.clip(np.arange(n - 1)[:, None] + np.arange(-1, 3)[None, :], 1, n - 2) - 1
     m = 0.5 * d2[idx].max(axis=1) + 2.0 * np.abs(pm - 0.5 * (p[:-1] + p[1:])) + 1e-12 * (np.abs(p[:-1]) + 1.0)
-    m[0] = m[-1] = np.inf
     z0, z1, zm = p[:-1] == 0, p[1:] == 0, pm == 0
     m[(z0 | z1) & ~(z0 & z1 & zm)] = np.inf
     return m
 
 
+def _first_cell_bound(s, ea, fmax, h):
+    """k_thin_nodes, first cell of a time-evolving CPL: B = sup K x sup G / fmax with K the Norris pulse (its sup over
+    [0, h] is at min(h, sqrt(trise tdecay))) and G = lambda / K, evaluated as the constant-CPL rate at unit flux and
+    ep(t), at the cell's ends and midpoint"""
+    tpk = np.sqrt(s.trise * s.tdecay)
+    supK = orc.lib().co_norris(min(max(tpk, 0.0), h), s.peak_flux, 0.0, s.trise, s.tdecay)
+    g = []
+    for t in (0.0, 0.5 * h, h):
+        c = orc.source(kind=1, interp_extrap=s.interp_extrap, peak_flux=1.0, ep_start=s.ep_start / (1.0 + t / s.ep_tau),
+                       alpha=s.alpha, z=s.z, emin=s.emin, emax=s.emax)
+        g.append(orc.energy_integrated_evolution(c, ea, [0.0])[0])
+    supG = max(g) + 2.0 * abs(g[0] - 2.0 * g[1] + g[2])
+    return supK * supG / fmax * (1.0 + 1e-6) + 1e-300
+
+
 def _table(s, ea, fmax, duration, n=None):
-    """nodes p_j, margins m_j, bounds P_j and cumulative operational time, as the kernels build them"""
+    """nodes p_j, margins m_j (inf: no squeeze), bounds P_j and cumulative operational time, as the kernels build them"""
     mean = fmax * duration
     cap = int(np.ceil(mean + 8.0 * np.sqrt(mean))) + 64
     if n is None:
@@ -43,12 +57,16 @@ def _table(s, ea, fmax, duration, n=None):
             return None
         n = int(np.clip(cap // SQUEEZE_RATIO, 64, MAX_NODES))
     t = np.linspace(0.0, duration, n)
+    h = duration / (n - 1)
     p = orc.energy_integrated_evolution(s, ea, t) / fmax
-    pm = orc.energy_integrated_evolution(s, ea, t[:-1] + 0.5 * duration / (n - 1)) / fmax
+    pm = orc.energy_integrated_evolution(s, ea, t[:-1] + 0.5 * h) / fmax
     m = _margins(p, pm)
     with np.errstate(invalid="ignore"):
         P = np.minimum(1.0, np.maximum(np.maximum(p[:-1], p[1:]) + m, 0.0))
-    L = np.concatenate(([0.0], np.cumsum(fmax * (duration / (n - 1)) * P)))
+    if s.kind == 0:
+        m[0] = np.inf                                           # every candidate of the first cell is exact ...
+        P[0] = min(1.0, _first_cell_bound(s, ea, fmax, h))      # ... and the proposal uses the analytic bound
+    L = np.concatenate(([0.0], np.cumsum(fmax * h * P)))
     return t, p, m, P, L
 
 
@@ -143,7 +161,12 @@ def test_squeeze_margins_bound_the_interpolation_error(T, trise, tdecay, n):
     cell = np.minimum(np.arange(len(fine)) // F, n - 2)
     err = np.abs(orc.energy_integrated_evolution(s, ea, fine) / fmax - np.interp(fine, t, p))
     assert np.all(err <= m[cell] + 1e-15), (float(np.max(err - m[cell])), np.unique(cell[err > m[cell] + 1e-15])[:8])
-    # the first cell is always exact; the old margins failed there
-    assert np.isinf(m[0]) and np.isinf(m[-1])
+    # the first cell of a pulse is never interpolated (the old margins failed there); its majorant is the analytic
+    # bound, which must dominate p on the cell and stay far below 1 for a pulse that starts slowly
+    assert np.isinf(m[0])
+    pf = orc.energy_integrated_evolution(s, ea, fine[:F + 1]) / fmax
+    assert np.all(np.minimum(pf, 1.0) <= P[0] * (1 + 1e-12))
+    if trise / (T / (n - 1)) > 50:
+        assert P[0] < 1e-6
     finite = np.isfinite(m[cell])
     assert np.max(err[finite] / m[cell][finite]) < 0.75         # measured worst case 0.45: head-room, not luck
