@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # COSMOGRB_B200_LIB selects another build of the same library (tuning runs: variants compiled with -D flags)
 LIB_PATH = os.environ.get("COSMOGRB_B200_LIB") or os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 NBINS = 140
 NCHAN = 128
 NE_LAMBDA = 75
@@ -50,6 +50,7 @@ ST_ENVELOPE = 32
 ST_DEADTIME_CHAIN = 64
 ST_MAJORANT = 128
 ST_SQUEEZE = 256
+ST_INTERNAL = 512
 
 UNIT_NO_SOURCE = 1
 UNIT_NO_BACKGROUND = 2

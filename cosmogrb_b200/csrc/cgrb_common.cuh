@@ -189,13 +189,19 @@ __device__ __forceinline__ double lambda_per_flux_at(const LambdaTab *tab, const
 // predecessors per round (8 loads in flight per lane): hundreds of CTAs run concurrently, so the nearest
 // inclusive prefix is typically that far back.  Integer sums: the result does not depend on timing.
 // The state array must be zeroed before the launch.  Call with all 32 lanes of one warp.
+//
+// Forward progress: the caller takes its item index `w` from an atomic TICKET counter (zeroed with the state
+// array), not from blockIdx: every predecessor a warp can wait for was claimed by a CTA that is already running.
+// A warp only waits for the lanes at or before the nearest inclusive prefix, and a wait that outlasts
+// LB_SPIN_LIMIT polls (seconds) gives up and reports it through *timed_out instead of hanging the device.
 // ------------------------------------------------------------------------------------------
 #define LB_FLAG_AGG (1ull << 62)
 #define LB_FLAG_INC (2ull << 62)
 #define LB_VALUE_MASK ((1ull << 62) - 1ull)
+#define LB_SPIN_LIMIT (1 << 22)
 
 __device__ __forceinline__ long long lookback_exclusive(unsigned long long *state, int64_t w, int64_t wb,
-                                                        long long count, int lane)
+                                                        long long count, int lane, bool *timed_out)
 {
     if (lane == 0)
         atomicExch(state + w, (unsigned long long)count | (w == wb ? LB_FLAG_INC : LB_FLAG_AGG));
@@ -215,16 +221,28 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long *stat
                 if (done)
                     break;
                 const int64_t my = idx - 32 * q - lane;
-                while ((st[q] >> 62) == 0ull)
-                    st[q] = *((volatile unsigned long long *)(state + my));
-                const unsigned inc = __ballot_sync(0xffffffffu, (st[q] >> 62) == 2ull);
+                unsigned inc;
+                for (int spin = 0;; spin++) {
+                    inc = __ballot_sync(0xffffffffu, (st[q] >> 62) == 2ull);
+                    const unsigned pend = __ballot_sync(0xffffffffu, (st[q] >> 62) == 0ull);
+                    // lanes beyond the nearest inclusive prefix do not matter (lane 0 is the nearest predecessor)
+                    const unsigned upto = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;
+                    if (!(pend & upto))
+                        break;
+                    if (spin >= LB_SPIN_LIMIT) {
+                        *timed_out = true;
+                        break;
+                    }
+                    if ((st[q] >> 62) == 0ull)
+                        st[q] = *((volatile unsigned long long *)(state + my));
+                }
                 const int first_inc = inc ? (__ffs(inc) - 1) : 32;      // nearest item with an inclusive prefix
-                long long v = (lane <= first_inc && my >= wb) ? (long long)(st[q] & LB_VALUE_MASK) : 0;
+                long long v = (lane <= first_inc && my >= wb && (st[q] >> 62) != 0ull) ? (long long)(st[q] & LB_VALUE_MASK) : 0;
 #pragma unroll
                 for (int dlt = 16; dlt > 0; dlt >>= 1)
                     v += __shfl_xor_sync(0xffffffffu, v, dlt);
                 excl += v;
-                if (inc)
+                if (inc || *timed_out)
                     done = true;
             }
             idx -= 256;

@@ -497,27 +497,107 @@ __global__ void __launch_bounds__(NT) k_merge_splits(const cgrb_unit_t *__restri
 
 #define MD_PER (MD_N / NT)       // merged elements per thread in the serial merge (9)
 #define MD_R (MD_TILE / NT)     // tile elements per thread in the dead-time pass (8)
+#define MD_WORDS (MD_N / 32)    // words of the chain bitmap (72)
 
-template <int MODE>
-__global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
-                                                       const cgrb_work_t *__restrict__ work, int64_t n_work,
-                                                       const int64_t *__restrict__ unit_work_begin,
-                                                       const double *__restrict__ times_bkg,
-                                                       const uint8_t *__restrict__ pha_bkg,
-                                                       const double *__restrict__ times_src,
-                                                       const uint8_t *__restrict__ pha_src,
-                                                       unsigned long long *tile_state,
-                                                       const int64_t *__restrict__ splits,
-                                                       double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
-                                                       cgrb_counts_t *counts, const DtModel md)
+// ------------------------------------------------------------------------------------------
+// bulk-async (TMA) staging of a contiguous slice of a global list into shared memory.  cp.async.bulk moves
+// multiples of 16 bytes between 16-byte aligned addresses, a slice starts anywhere: element k of the slice lands at
+// dst[k] with dst chosen by the caller so that (shared address of dst[k]) == (global address of src[k]) mod 16;
+// the aligned middle part goes through the bulk engine (one instruction, no registers, no LSU traffic), the
+// < 16-byte head and tail are plain loads by the first threads.  Nothing outside [src, src + n) is read.
+// ------------------------------------------------------------------------------------------
+struct BulkPlan {
+    int head, body;         // elements before the aligned part, elements in it (the tail is the rest)
+};
+template <int ELEM>
+__device__ __forceinline__ BulkPlan bulk_plan(const void *src, int n)
 {
-    __shared__ double s_in_t[MD_N];         // the two input slices, background first
-    __shared__ double s_t[MD_N];            // merged
-    __shared__ uint8_t s_in_p[MD_N];
-    __shared__ uint8_t s_p[MD_N];
-    __shared__ int s_cnt[MD_R * NW];        // survivors per (round, warp), then their exclusive prefix
-    __shared__ long long s_excl;
-    const int64_t w = blockIdx.x;
+    constexpr int PER16 = 16 / ELEM;
+    BulkPlan pl;
+    const int mis = (int)(((uintptr_t)src & 15u) / ELEM);
+    pl.head = min(n, (PER16 - mis) & (PER16 - 1));
+    pl.body = ((n - pl.head) / PER16) * PER16;
+    return pl;
+}
+__device__ __forceinline__ void bulk_issue(void *dst, const void *src, unsigned bytes, uint64_t *s_bar)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// bounded wait on phase `parity` of an mbarrier; false if it never completed (reported, not hung)
+__device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done)
+            return true;
+    }
+    return false;
+}
+
+struct MdSmem {
+    alignas(16) double t[MD_N + 4];         // slack: the alignment shift of up to two staged slices
+    alignas(16) uint8_t p[MD_N + 48];
+    uint32_t chain[MD_WORDS];               // bit li: local event li is a chain element (overflow channel / event 0)
+    uint32_t rarekeep[MD_TILE / 32];        // keep flags of the tile elements resolved by the chain walk
+    uint16_t rare[MD_TILE];                 // tile elements that need the chain walk
+    int cnt[MD_R * NW];                     // survivors per (round, warp), then their exclusive prefix
+    int n_rare;
+    long long excl;
+    long long ticket;
+    alignas(8) uint64_t bar;
+};
+
+// One CTA per tile of MD_TILE merged events, tile index from a ticket counter (see lookback_exclusive).
+//  1. the tile's slices of the two component lists (+ MD_HALO events of look-back) are staged by the bulk-async
+//     engine; a tile fed by one list only -- nearly every tile of a background-dominated unit -- is then already in
+//     merged order, otherwise each thread merges MD_PER consecutive outputs from its merge-path split (registers,
+//     then back in place);
+//  2. literal dead time: a bitmap of the chain elements (overflow channel, the unit's event 0) gives every event
+//     its nearest earlier chain element in a few bit operations; only if that one lies within the longest window
+//     does the event join the `rare` list, which is then resolved densely by the exact walk (dt_keep_local, or
+//     the global accessor when the chain leaves the halo);
+//  3. survivors are appended at the unit's output offset from the decoupled look-back.
+template <int MODE>
+__global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
+                                                          const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                          const int64_t *__restrict__ unit_work_begin,
+                                                          const double *__restrict__ times_bkg,
+                                                          const uint8_t *__restrict__ pha_bkg,
+                                                          const double *__restrict__ times_src,
+                                                          const uint8_t *__restrict__ pha_src,
+                                                          unsigned long long *tile_state,
+                                                          unsigned long long *ticket_counter,
+                                                          const int64_t *__restrict__ splits,
+                                                          double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
+                                                          cgrb_counts_t *counts, const DtModel md)
+{
+    __shared__ MdSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        sm.ticket = (long long)atomicAdd(ticket_counter, 1ull);
+        sm.n_rare = 0;
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < MD_TILE / 32)
+        sm.rarekeep[tid] = 0u;
+    __syncthreads();
+    const int64_t w = sm.ticket;
     if (w >= n_work)
         return;
     const cgrb_work_t wk = work[w];
@@ -525,142 +605,248 @@ __global__ void __launch_bounds__(NT) k_merge_deadtime(const cgrb_unit_t *__rest
     const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
     const int64_t total = nA + nB;
     const int64_t wb = unit_work_begin[wk.unit];
-    const double *A = times_bkg + u->bkg_off;
-    const double *B = times_src + u->src_off;
-    const uint8_t *pA = pha_bkg + u->bkg_off;
-    const uint8_t *pB = pha_src + u->src_off;
     const int64_t d0 = wk.start, d1 = min(d0 + (int64_t)MD_TILE, total);
-    const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const bool live = d0 < total;
-    if (!live) {
+    if (d0 >= total) {
         // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so nobody
         // will look back at it (the last LIVE tile writes n_kept)
-        if (w == wb && threadIdx.x == 0) {
+        if (w == wb && tid == 0) {
             counts[wk.unit].n_total = total;
             counts[wk.unit].n_kept = 0;
         }
         return;
     }
+    const double *A = times_bkg + u->bkg_off;
+    const double *B = times_src + u->src_off;
+    const uint8_t *pA = pha_bkg + u->bkg_off;
+    const uint8_t *pB = pha_src + u->src_off;
+    const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
     const int l0 = (int)(d0 - g0), nt = (int)(d1 - d0);
+    // d1 is either the next tile's start (same unit) or the end of the merged list
+    const int64_t i0 = splits[2 * w], i1 = (d1 == total) ? nA : splits[2 * (w + 1) + 1];
+    const int64_t j0 = g0 - i0, j1 = d1 - i1;
+    const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
+    const int n = na + nb;                                    // = d1 - g0 <= MD_N
 
-    unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
-    if (live) {
-        // d1 is either the next tile's start (same unit) or the end of the merged list
-        const int64_t i0 = splits[2 * w], i1 = (d1 == total) ? nA : splits[2 * (w + 1) + 1];
-        const int64_t j0 = g0 - i0, j1 = d1 - i1;
-        const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
-        if (na == 0 || nb == 0) {
-            // a tile fed by one list only (nearly every tile of a background-dominated unit, and of a bright
-            // burst's peak): the slice IS the merged order, straight into place
-            const double *X = na ? A + i0 : B + j0;
-            const uint8_t *pX = na ? pA + i0 : pB + j0;
-            for (int k = threadIdx.x; k < na + nb; k += NT) {
-                s_t[k] = X[k];
-                s_p[k] = pX[k];
-            }
-        } else {
-        for (int k = threadIdx.x; k < na; k += NT) {
-            s_in_t[k] = A[i0 + k];
-            s_in_p[k] = pA[i0 + k];
+    // ---- 1. stage the slices -------------------------------------------------------------------------
+    // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]; shared and global addresses agree mod 16
+    const double *gA = A + i0, *gB = B + j0;
+    const uint8_t *hA = pA + i0, *hB = pB + j0;
+    const int ta = (int)(((uintptr_t)gA >> 3) & 1u);
+    const int tb = ((ta + na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
+    const int qa = (int)((uintptr_t)hA & 15u);
+    const int qb = ((qa + na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
+    const BulkPlan ptA = bulk_plan<8>(gA, na), ptB = bulk_plan<8>(gB, nb);
+    const BulkPlan ppA = bulk_plan<1>(hA, na), ppB = bulk_plan<1>(hB, nb);
+    const unsigned bulk_bytes = 8u * (unsigned)(ptA.body + ptB.body) + (unsigned)(ppA.body + ppB.body);
+    if (tid == 0 && bulk_bytes) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bulk_bytes) : "memory");
+        if (ptA.body)
+            bulk_issue(sm.t + ta + ptA.head, gA + ptA.head, 8u * ptA.body, &sm.bar);
+        if (ptB.body)
+            bulk_issue(sm.t + tb + ptB.head, gB + ptB.head, 8u * ptB.body, &sm.bar);
+        if (ppA.body)
+            bulk_issue(sm.p + qa + ppA.head, hA + ppA.head, (unsigned)ppA.body, &sm.bar);
+        if (ppB.body)
+            bulk_issue(sm.p + qb + ppB.head, hB + ppB.head, (unsigned)ppB.body, &sm.bar);
+    }
+    // heads and tails (< 16 bytes each): plain loads
+    if (tid < 64) {
+        const int which = tid >> 4, k = tid & 15;           // 0: t of A, 1: t of B, 2: p of A, 3: p of B
+        const BulkPlan pl = which == 0 ? ptA : which == 1 ? ptB : which == 2 ? ppA : ppB;
+        const int cnt = (which & 1) ? nb : na;
+        const int tail0 = pl.head + pl.body;                // first element of the tail
+        int e = -1;
+        if (k < pl.head)
+            e = k;
+        else if (k - pl.head < cnt - tail0)
+            e = tail0 + (k - pl.head);
+        // (a time slice has at most one head and one tail element, a pha slice at most 15 + 15: k covers 16 of
+        //  them, the remaining tail bytes below)
+        if (e >= 0) {
+            if (which == 0)
+                sm.t[ta + e] = gA[e];
+            else if (which == 1)
+                sm.t[tb + e] = gB[e];
+            else if (which == 2)
+                sm.p[qa + e] = hA[e];
+            else
+                sm.p[qb + e] = hB[e];
         }
-        for (int k = threadIdx.x; k < nb; k += NT) {
-            s_in_t[na + k] = B[j0 + k];
-            s_in_p[na + k] = pB[j0 + k];
+    } else if (tid < 96) {
+        // pha tails beyond the 16 head + tail bytes handled above
+        const int which = 2 + ((tid - 64) >> 4), k = tid & 15;
+        const BulkPlan pl = which == 2 ? ppA : ppB;
+        const int cnt = (which & 1) ? nb : na;
+        const int e = pl.head + pl.body + (16 - pl.head) + k;
+        if (e < cnt) {
+            if (which == 2)
+                sm.p[qa + e] = hA[e];
+            else
+                sm.p[qb + e] = hB[e];
         }
-        __syncthreads();
-        // serial merge of MD_PER consecutive outputs per thread from its merge-path split
-        {
-            const double *a_ = s_in_t, *b_ = s_in_t + na;
-            const int n = na + nb;
-            const int q0 = min(threadIdx.x * MD_PER, n);
-            int lo = max(0, q0 - nb), hi = min(q0, na);
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
-                    lo = mid + 1;
-                else
-                    hi = mid;
-            }
-            int ia = lo, ib = q0 - lo;
+    }
+    bool failed = false;
+    if (bulk_bytes)
+        failed = !mbar_wait(&sm.bar, 0u);
+    __syncthreads();
+
+    const double *T = sm.t;
+    const uint8_t *P = sm.p;
+    if (na == 0 || nb == 0) {
+        // a tile fed by one list only: the slice IS the merged order
+        T = sm.t + (na ? ta : tb);
+        P = sm.p + (na ? qa : qb);
+    } else {
+        // serial merge of MD_PER consecutive outputs per thread from its merge-path split, in place through registers
+        const double *a_ = sm.t + ta, *b_ = sm.t + tb;
+        const uint8_t *pa_ = sm.p + qa, *pb_ = sm.p + qb;
+        const int q0 = min(tid * MD_PER, n);
+        int lo = max(0, q0 - nb), hi = min(q0, na);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        int ia = lo, ib = q0 - lo;
+        double rt[MD_PER];
+        uint8_t rp[MD_PER];
 #pragma unroll
-            for (int r = 0; r < MD_PER; r++) {
-                const int q = q0 + r;
-                if (q < n) {
-                    const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
-                    const int src = take_a ? ia : na + ib;
-                    s_t[q] = s_in_t[src];
-                    s_p[q] = s_in_p[src];
-                    ia += take_a ? 1 : 0;
-                    ib += take_a ? 0 : 1;
-                }
+        for (int r = 0; r < MD_PER; r++) {
+            rt[r] = 0.0;
+            rp[r] = 0;
+            if (q0 + r < n) {
+                const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
+                rt[r] = take_a ? a_[ia] : b_[ib];
+                rp[r] = take_a ? pa_[ia] : pb_[ib];
+                ia += take_a ? 1 : 0;
+                ib += take_a ? 0 : 1;
             }
         }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < MD_PER; r++)
+            if (q0 + r < n) {
+                sm.t[q0 + r] = rt[r];
+                sm.p[q0 + r] = rp[r];
+            }
+        __syncthreads();
+    }
+
+    // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
+    unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
+    MergedGlobal mg{A, B, pA, pB, nA, nB};
+    if (MODE == 0) {
+        const bool has0 = (g0 == 0);
+#pragma unroll
+        for (int r = 0; r < MD_PER; r++) {
+            const int li = r * NT + tid;
+            const bool c = li < n && (P[li] == 127 || (has0 && li == 0));
+            const unsigned bal = __ballot_sync(0xffffffffu, c);
+            if (lane == 0)
+                sm.chain[r * NW + wid] = bal;
         }
         __syncthreads();
-        // keep flags of the tile's own events (local indices [l0, l0 + nt))
-        MergedGlobal mg{A, B, pA, pB, nA, nB};
-        // physical mode: a unit already flagged for the serial fix-up needs no more work here
-        const bool flagged = (MODE != 0) && ((*(volatile uint32_t *)&counts[wk.unit].status) & CGRB_ST_DEADTIME_CHAIN);
-        (void)flagged;
 #pragma unroll
         for (int r = 0; r < MD_R; r++) {
-            const int e = r * NT + threadIdx.x;
-            int keep = 0;
+            const int e = r * NT + tid;
             if (e < nt) {
-                if (MODE == 0) {
-                    keep = dt_keep_local(s_t, s_p, l0 + e, g0);
-                    if (keep == 2)
-                        keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
-                } else {
-                    // no synchronisation point inside the tile's halo (256 events closer than the longest
-                    // window: never at GBM rates): the unit goes to the serial fix-up kernel
-                    const EventArrays ev{s_t, s_p};
-                    keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), g0 == 0, md);
-                    if (keep == 2) {
-                        atomicOr(&counts[wk.unit].status, CGRB_ST_DEADTIME_CHAIN);
+                const int li = l0 + e;
+                int keep = 1;
+                if (g0 + li != 0) {
+                    const double ti = T[li];
+                    // nearest chain element before li
+                    int wd = li >> 5;
+                    unsigned m = sm.chain[wd] & ((1u << (li & 31)) - 1u);
+                    while (m == 0u && wd > 0)
+                        m = sm.chain[--wd];
+                    // none in the halo: kept iff the halo's first event already lies outside the longest window
+                    const int j = m ? (wd << 5) + 31 - __clz(m) : 0;
+                    if (!(T[j] + DT_TAU < ti)) {
+                        // a chain element (or an exhausted halo) within the window: the exact walk decides
+                        sm.rare[atomicAdd(&sm.n_rare, 1)] = (uint16_t)e;
                         keep = 0;
                     }
                 }
+                keep_bits |= (unsigned)keep << r;
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0)
-                s_cnt[r * NW + wid] = __popc(bal);
-            // rank inside the (round, warp) group, kept in the upper bits
+        }
+        __syncthreads();
+        const int n_rare = sm.n_rare;
+        if (n_rare > 0) {
+            for (int k = tid; k < n_rare; k += NT) {
+                const int e = sm.rare[k];
+                int keep = dt_keep_local(T, P, l0 + e, g0);
+                if (keep == 2)
+                    keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
+                if (keep)
+                    atomicOr(&sm.rarekeep[e >> 5], 1u << (e & 31));
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < MD_R; r++)
+                keep_bits |= ((sm.rarekeep[r * NW + wid] >> lane) & 1u) << r;
+        }
+    } else {
+        // physical mode: a unit already flagged for the serial fix-up needs no more work here
+        const bool flagged = ((*(volatile uint32_t *)&counts[wk.unit].status) & CGRB_ST_DEADTIME_CHAIN) != 0;
+        const EventArrays ev{T, P};
+#pragma unroll
+        for (int r = 0; r < MD_R; r++) {
+            const int e = r * NT + tid;
+            int keep = 0;
+            if (e < nt) {
+                // no synchronisation point inside the tile's halo (256 events closer than the longest
+                // window: never at GBM rates): the unit goes to the serial fix-up kernel
+                keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), g0 == 0, md);
+                if (keep == 2) {
+                    atomicOr(&counts[wk.unit].status, CGRB_ST_DEADTIME_CHAIN);
+                    keep = 0;
+                }
+            }
             keep_bits |= (unsigned)keep << r;
         }
     }
+#pragma unroll
+    for (int r = 0; r < MD_R; r++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
+        if (lane == 0)
+            sm.cnt[r * NW + wid] = __popc(bal);
+    }
     __syncthreads();
 
-    // warp 0: exclusive prefix of the 64 group counts, then the decoupled look-back over the unit's
-    // earlier tiles for this tile's offset in the unit's output
+    // ---- 3. output offset: warp 0 scans the 64 group counts, then looks back over the unit's earlier tiles ----
     if (wid == 0) {
-        int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        int c0 = sm.cnt[2 * lane], c1 = sm.cnt[2 * lane + 1];
         int incl = warp_incl_scan_i(c0 + c1, lane);
         const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
-        s_cnt[2 * lane] = incl - c0 - c1;
-        s_cnt[2 * lane + 1] = incl - c1;
-        const long long excl = lookback_exclusive(tile_state, w, wb, cnt_tile, lane);
+        sm.cnt[2 * lane] = incl - c0 - c1;
+        sm.cnt[2 * lane + 1] = incl - c1;
+        const long long excl = lookback_exclusive(tile_state, w, wb, cnt_tile, lane, &failed);
         if (lane == 0) {
-            s_excl = excl;
+            sm.excl = excl;
             if (w == wb)
                 counts[wk.unit].n_total = total;
             if (d1 == total)
                 counts[wk.unit].n_kept = excl + cnt_tile;     // the last live tile of the unit
         }
     }
+    if (failed)
+        atomicOr(&counts[wk.unit].status, CGRB_ST_INTERNAL);
     __syncthreads();
-    double *ot = times_out + u->tot_off + s_excl;
-    uint8_t *op = pha_out + u->tot_off + s_excl;
+    double *ot = times_out + u->tot_off + sm.excl;
+    uint8_t *op = pha_out + u->tot_off + sm.excl;
 #pragma unroll
     for (int r = 0; r < MD_R; r++) {
         // survivors of (round r, this warp) before this lane
-        unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
+        const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
         if ((keep_bits >> r) & 1u) {
-            const int rank = s_cnt[r * NW + wid] + __popc(bal & ((1u << lane) - 1u));
-            const int li = l0 + r * NT + threadIdx.x;
-            ot[rank] = s_t[li];
-            op[rank] = s_p[li];
+            const int rank = sm.cnt[r * NW + wid] + __popc(bal & ((1u << lane) - 1u));
+            const int li = l0 + r * NT + tid;
+            ot[rank] = T[li];
+            op[rank] = P[li];
         }
     }
 }

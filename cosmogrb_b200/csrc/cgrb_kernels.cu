@@ -518,7 +518,8 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
     return check_launch("cgrb_gbm_dead_time");
 }
 
-int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 24 * (n_work > 0 ? n_work : 0); }
+// tile states [n_work], ticket counter + pad [2], merge-path splits [2 n_work]  (8 bytes each)
+int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 24 * (n_work > 0 ? n_work : 0) + 16; }
 
 int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
                          const int64_t *d_unit_work_begin, const double *d_times_bkg, const uint8_t *d_pha_bkg,
@@ -534,20 +535,21 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
     if (int rc = deadtime_model(model, &md, &physical, "cgrb_merge_dead_time"))
         return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(d_workspace, 0, 8 * (size_t)n_work, s);
+    cudaError_t e = cudaMemsetAsync(d_workspace, 0, 8 * (size_t)n_work + 16, s);
     if (e != cudaSuccess)
         return fail(CGRB_E_CUDA, "cgrb_merge_dead_time: memset: %s", cudaGetErrorString(e));
-    int64_t *splits = (int64_t *)d_workspace + n_work;
+    unsigned long long *ticket = (unsigned long long *)d_workspace + n_work;
+    int64_t *splits = (int64_t *)d_workspace + n_work + 2;
     LAUNCH("k_merge_splits", s, k_merge_splits<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
         d_units, d_work, n_work, d_times_bkg, d_times_src, splits, d_counts));
     if (!physical) {
         LAUNCH("k_merge_deadtime", s, k_merge_deadtime<0><<<(unsigned)n_work, NT, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
-            (unsigned long long *)d_workspace, splits, d_times_out, d_pha_out, d_counts, md));
+            (unsigned long long *)d_workspace, ticket, splits, d_times_out, d_pha_out, d_counts, md));
     } else {
         LAUNCH("k_merge_deadtime_phys", s, k_merge_deadtime<1><<<(unsigned)n_work, NT, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
-            (unsigned long long *)d_workspace, splits, d_times_out, d_pha_out, d_counts, md));
+            (unsigned long long *)d_workspace, ticket, splits, d_times_out, d_pha_out, d_counts, md));
         LAUNCH("k_deadtime_phys_fixup", s, k_deadtime_phys_fixup<<<(n_units * 32 + 127) / 128, 128, 0, s>>>(
             d_units, n_units, nullptr, nullptr, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src, d_times_out,
             d_pha_out, nullptr, d_counts, md));

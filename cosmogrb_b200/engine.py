@@ -790,7 +790,8 @@ class Engine(object):
             names = {1: "source capacity", 2: "background capacity", 4: "injected uniforms exhausted",
                      8: "trial cap", 16: "output capacity", 32: "energy envelope violated",
                      64: "physical dead time: event rate x window too high (chain > 4096 events)",
-                     128: "thinning majorant violated", 256: "thinning squeeze margin violated"}
+                     128: "thinning majorant violated", 256: "thinning squeeze margin violated",
+                     512: "internal: a bounded wait inside a kernel gave up"}
             ui = int(bad[0])
             st = int(c["status"][ui])
             what = ", ".join(v for k, v in names.items() if st & k)

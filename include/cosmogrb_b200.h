@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CGRB_ABI_VERSION 5
+#define CGRB_ABI_VERSION 6
 
 /* error codes */
 #define CGRB_OK 0
@@ -47,6 +47,7 @@ extern "C" {
 #define CGRB_ST_ENVELOPE 32u         /* energy envelope failed to dominate the target (bug)  */
 #define CGRB_ST_MAJORANT 128u        /* thinning majorant failed to dominate lambda(t) (bug)            */
 #define CGRB_ST_SQUEEZE 256u         /* squeeze margin failed to bound |p - interpolation| at an exact evaluation (bug) */
+#define CGRB_ST_INTERNAL 512u        /* a bounded wait inside a kernel gave up (look-back / bulk copy; never expected) */
 #define CGRB_ST_DEADTIME_CHAIN 64u   /* physical dead time: unit handed to the serial fix-up (transient; cleared by it) */
 
 /* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
@@ -329,8 +330,8 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
  * LightCurve.process, so it is merged tile by tile in shared memory and only the survivors are written
  * (compacted at tot_off; counts.n_total, counts.n_kept).  Bit-identical to cgrb_combine +
  * cgrb_gbm_dead_time.  Work list: which=2, chunk=CGRB_MD_TILE; d_workspace:
- * cgrb_merge_dead_time_workspace_bytes(n_work) bytes (tile states of the decoupled look-back; cleared
- * by the call). */
+ * cgrb_merge_dead_time_workspace_bytes(n_work) bytes (tile states of the decoupled look-back, the tile ticket
+ * counter and the merge-path splits; cleared by the call). */
 #define CGRB_MD_TILE 2048
 int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work);
 int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,

@@ -242,3 +242,114 @@ def test_background_channel_guide_equals_numpy_choice():
                 j += 1
             got[k] = j
         assert np.array_equal(got, want)
+
+
+# ---- k_merge_deadtime (round 2): chain bitmap + rare list inside a tile with halo ------------------------------
+def dt_keep_local(t, p, li, g0):
+    """csrc/cgrb_deadtime.cuh: dt_keep_local on a tile held in shared memory (local index 0 <-> merged rank g0);
+    0 / 1, or 2 when the walk leaves the halo"""
+    if g0 + li == 0:
+        return 1
+    has0 = g0 == 0
+    ti = t[li]
+    found = -1
+    j = li - 1
+    while j >= 0:
+        if t[j] + TAU < ti:
+            return 1
+        if p[j] == 127 or (has0 and j == 0):
+            found = j
+            break
+        j -= 1
+    if found < 0:
+        return 2
+    head = found
+    while True:
+        if has0 and head == 0:
+            break
+        th = t[head]
+        q, gap = -1, False
+        jj = head - 1
+        while jj >= 0:
+            if t[jj] + TAU < th:
+                gap = True
+                break
+            if p[jj] == 127 or (has0 and jj == 0):
+                q = jj
+                break
+            jj -= 1
+        if q < 0:
+            if gap:
+                break
+            return 2
+        pe = t[q] + (NORMAL if (has0 and q == 0 and p[0] != 127) else TAU)
+        if pe < th:
+            break
+        head = q
+    t_end = t[head] + (NORMAL if (has0 and head == 0 and p[0] != 127) else TAU)
+    for jj in range(head + 1, li):
+        if p[jj] == 127 and t[jj] > t_end:
+            t_end = t[jj] + TAU
+    return 1 if ti > t_end else 0
+
+
+def tile_keep_flags(t, p, d0, tile=2048, halo=256):
+    """k_merge_deadtime<0>, step 2, for the tile of merged ranks [d0, d0 + tile): chain bitmap of the staged events,
+    nearest earlier chain element by bit operations, the rare list resolved by dt_keep_local (global walk = dt_keep
+    when the chain leaves the halo).  Returns (keep flags, number of rare events, number of global walks)."""
+    n_all = len(t)
+    g0 = max(0, d0 - halo)
+    d1 = min(d0 + tile, n_all)
+    T, P = t[g0:d1], p[g0:d1]
+    n = len(T)
+    l0 = d0 - g0
+    has0 = g0 == 0
+    words = np.zeros((n + 31) // 32 + 1, dtype=np.uint64)
+    for li in range(n):
+        if P[li] == 127 or (has0 and li == 0):
+            words[li >> 5] |= np.uint64(1) << np.uint64(li & 31)
+    keep = np.ones(d1 - d0, dtype=bool)
+    rare = []
+    for e in range(d1 - d0):
+        li = l0 + e
+        if g0 + li == 0:
+            continue
+        wd = li >> 5
+        m = int(words[wd]) & ((1 << (li & 31)) - 1)
+        while m == 0 and wd > 0:
+            wd -= 1
+            m = int(words[wd])
+        j = (wd << 5) + m.bit_length() - 1 if m else 0
+        if not (T[j] + TAU < T[li]):
+            rare.append(e)
+            keep[e] = False
+    n_slow = 0
+    for e in rare:
+        k = dt_keep_local(T, P, l0 + e, g0)
+        if k == 2:
+            n_slow += 1
+            k = 1 if dt_keep(t, p, d0 + e) else 0
+        keep[e] = bool(k)
+    return keep, len(rare), n_slow
+
+
+@pytest.mark.parametrize("rate,frac127,ties", [(500.0, 0.05, False), (7.5e4, 0.05, True), (2e5, 0.3, True),
+                                               (2e6, 0.3, True), (3e7, 0.02, False), (1e5, 0.0, True)])
+def test_tile_chain_bitmap_equals_the_serial_rule(rate, frac127, ties):
+    rs = np.random.RandomState(int(rate) % 991 + int(100 * frac127) + 1)
+    n = 3 * 2048 + 700
+    for first127 in (False, True):
+        t, p = _events(rs, n, rate, frac127, ties)
+        p[0] = 127 if first127 else 5
+        want = orc.gbm_dead_time(t, p)
+        got, n_rare, n_slow = [], 0, 0
+        for d0 in range(0, n, 2048):
+            k, r, s_ = tile_keep_flags(t, p, d0)
+            got.append(k)
+            n_rare += r
+            n_slow += s_
+        assert np.array_equal(np.concatenate(got), want)
+        if rate <= 500.0:
+            assert n_rare < 0.01 * n           # GBM background: the rare list is (nearly) empty
+        if rate >= 3e7:
+            assert n_slow > 0                  # 256 events inside one window: the halo runs out
