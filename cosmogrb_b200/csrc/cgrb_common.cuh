@@ -193,12 +193,18 @@ __device__ __forceinline__ double lambda_per_flux_at(const LambdaTab *tab, const
 // Forward progress: the caller takes its item index `w` from an atomic TICKET counter (zeroed with the state
 // array), not from blockIdx: every predecessor a warp can wait for was claimed by a CTA that is already running.
 // A warp only waits for the lanes at or before the nearest inclusive prefix, and a wait that outlasts
-// LB_SPIN_LIMIT polls (seconds) gives up and reports it through *timed_out instead of hanging the device.
+// LB_WAIT_NS (20 s) gives up and reports it through *timed_out instead of hanging the device.
 // ------------------------------------------------------------------------------------------
 #define LB_FLAG_AGG (1ull << 62)
 #define LB_FLAG_INC (2ull << 62)
 #define LB_VALUE_MASK ((1ull << 62) - 1ull)
-#define LB_SPIN_LIMIT (1 << 22)
+#define LB_WAIT_NS 20000000000ull       // 20 s
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ long long lookback_exclusive(unsigned long long *state, int64_t w, int64_t wb,
                                                         long long count, int lane, bool *timed_out)
@@ -222,6 +228,7 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long *stat
                     break;
                 const int64_t my = idx - 32 * q - lane;
                 unsigned inc;
+                unsigned long long t_begin = 0;
                 for (int spin = 0;; spin++) {
                     inc = __ballot_sync(0xffffffffu, (st[q] >> 62) == 2ull);
                     const unsigned pend = __ballot_sync(0xffffffffu, (st[q] >> 62) == 0ull);
@@ -229,9 +236,15 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long *stat
                     const unsigned upto = inc ? ((2u << (__ffs(inc) - 1)) - 1u) : 0xffffffffu;
                     if (!(pend & upto))
                         break;
-                    if (spin >= LB_SPIN_LIMIT) {
-                        *timed_out = true;
-                        break;
+                    if ((spin & 1023) == 1023) {
+                        // (a predecessor in the global slow path may legitimately take seconds)
+                        const unsigned long long now = __shfl_sync(0xffffffffu, global_timer_ns(), 0);
+                        if (t_begin == 0)
+                            t_begin = now;
+                        else if (now - t_begin > LB_WAIT_NS) {
+                            *timed_out = true;
+                            break;
+                        }
                     }
                     if ((st[q] >> 62) == 0ull)
                         st[q] = *((volatile unsigned long long *)(state + my));

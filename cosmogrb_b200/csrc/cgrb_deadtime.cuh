@@ -755,16 +755,27 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
             if (e < nt) {
                 const int li = l0 + e;
                 int keep = 1;
-                if (g0 + li != 0) {
-                    const double ti = T[li];
-                    // nearest chain element before li
+                const double ti = T[li];
+                // (li == 0 only for the unit's event 0, which is kept)  Nobody within the longest window: kept.
+                if (li > 0 && !(T[li - 1] + DT_TAU < ti)) {
+                    // nearest chain element before li, looked for only as far back as the window reaches
                     int wd = li >> 5;
                     unsigned m = sm.chain[wd] & ((1u << (li & 31)) - 1u);
-                    while (m == 0u && wd > 0)
+                    int j = -1;
+                    for (;;) {
+                        if (m) {
+                            j = (wd << 5) + 31 - __clz(m);
+                            break;
+                        }
+                        if (wd == 0) {
+                            j = 0;                          // halo exhausted: its first event decides (g0 > 0 here)
+                            break;
+                        }
+                        if (T[(wd << 5) - 1] + DT_TAU < ti)
+                            break;                          // everything in the earlier words lies outside the window
                         m = sm.chain[--wd];
-                    // none in the halo: kept iff the halo's first event already lies outside the longest window
-                    const int j = m ? (wd << 5) + 31 - __clz(m) : 0;
-                    if (!(T[j] + DT_TAU < ti)) {
+                    }
+                    if (j >= 0 && !(T[j] + DT_TAU < ti)) {
                         // a chain element (or an exhausted halo) within the window: the exact walk decides
                         sm.rare[atomicAdd(&sm.n_rare, 1)] = (uint16_t)e;
                         keep = 0;

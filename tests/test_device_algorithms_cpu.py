@@ -312,15 +312,24 @@ def tile_keep_flags(t, p, d0, tile=2048, halo=256):
     rare = []
     for e in range(d1 - d0):
         li = l0 + e
-        if g0 + li == 0:
-            continue
+        ti = T[li]
+        if li == 0 or T[li - 1] + TAU < ti:
+            continue                           # the unit's event 0 / nobody within the longest window
         wd = li >> 5
         m = int(words[wd]) & ((1 << (li & 31)) - 1)
-        while m == 0 and wd > 0:
+        j = -1
+        while True:
+            if m:
+                j = (wd << 5) + m.bit_length() - 1
+                break
+            if wd == 0:
+                j = 0                          # halo exhausted: its first event decides
+                break
+            if T[(wd << 5) - 1] + TAU < ti:
+                break                          # the earlier words lie outside the window
             wd -= 1
             m = int(words[wd])
-        j = (wd << 5) + m.bit_length() - 1 if m else 0
-        if not (T[j] + TAU < T[li]):
+        if j >= 0 and not (T[j] + TAU < ti):
             rare.append(e)
             keep[e] = False
     n_slow = 0
