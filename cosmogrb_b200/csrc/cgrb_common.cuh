@@ -246,6 +246,7 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long *stat
                             break;
                         }
                     }
+                    __nanosleep(32);            // leave the issue slots to the warps that have work
                     if ((st[q] >> 62) == 0ull)
                         st[q] = *((volatile unsigned long long *)(state + my));
                 }

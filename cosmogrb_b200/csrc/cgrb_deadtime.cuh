@@ -548,31 +548,58 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
     return false;
 }
 
+#define MD_SPARSE 64             // a tile whose minority list has at most this many events is merged by insertion
+
+// everything a tile's threads need to know about it, worked out once by thread 0
+struct MdPlan {
+    int64_t w, wb, d0;
+    int64_t nA, nB;
+    int unit;
+    int live;
+    int na, nb;                 // staged events of list A (background) / B (source): halo + tile
+    int l0, nt;                 // first local index and number of the tile's own events
+    int has0;                   // local index 0 is the unit's event 0
+    int last;                   // the unit's last live tile
+    int ta, tb, qa, qb;         // staging offsets (doubles / bytes) of the two slices
+    BulkPlan ptA, ptB, ppA, ppB;
+    unsigned bulk_bytes;
+};
+
 struct MdSmem {
     alignas(16) double t[MD_N + 4];         // slack: the alignment shift of up to two staged slices
     alignas(16) uint8_t p[MD_N + 48];
     uint32_t chain[MD_WORDS];               // bit li: local event li is a chain element (overflow channel / event 0)
     uint32_t rarekeep[MD_TILE / 32];        // keep flags of the tile elements resolved by the chain walk
     uint16_t rare[MD_TILE];                 // tile elements that need the chain walk
+    uint16_t ins[MD_SPARSE];                // insertion merge: majority events preceding minority event i
+    uint8_t cblk[MD_WORDS + 4];             // insertion merge: minority events inserted before majority index 32 b
     int cnt[MD_R * NW];                     // survivors per (round, warp), then their exclusive prefix
     int n_rare;
     long long excl;
-    long long ticket;
+    MdPlan plan;
     alignas(8) uint64_t bar;
 };
 
 // One CTA per tile of MD_TILE merged events, tile index from a ticket counter (see lookback_exclusive).
-//  1. the tile's slices of the two component lists (+ MD_HALO events of look-back) are staged by the bulk-async
-//     engine; a tile fed by one list only -- nearly every tile of a background-dominated unit -- is then already in
-//     merged order, otherwise each thread merges MD_PER consecutive outputs from its merge-path split (registers,
-//     then back in place);
-//  2. literal dead time: a bitmap of the chain elements (overflow channel, the unit's event 0) gives every event
-//     its nearest earlier chain element in a few bit operations; only if that one lies within the longest window
-//     does the event join the `rare` list, which is then resolved densely by the exact walk (dt_keep_local, or
-//     the global accessor when the chain leaves the halo);
+//  1. thread 0 works out the tile's plan and hands the tile's slices of the two component lists (+ MD_HALO events
+//     of look-back) to the bulk-async engine.  A tile fed by one list only -- nearly every tile of a
+//     background-dominated unit -- is then already in merged order.  A tile with a sparse minority (<= MD_SPARSE
+//     events of one list: the background under a bright burst, the burst's photons in the background) is merged by
+//     insertion: every minority event finds its place in the majority by bisection, every majority event shifts by
+//     the number of insertions before it (a count per 32 events + the few insertions of its own block).  Anything
+//     else takes the general merge-path: MD_PER consecutive outputs per thread from its split.  In place, through
+//     registers.
+//  2. literal dead time: a bitmap of the chain elements (overflow channel, the unit's event 0); every warp derives
+//     the nearest chain element before each 32-event word by a prefix maximum over the words (registers), so an
+//     event finds its nearest earlier chain element from one word and one shuffle.  Only if that one lies within the
+//     longest window does the event join the `rare` list, which is then resolved densely by the exact walk
+//     (dt_keep_local, or the global accessor when the chain leaves the halo).
 //  3. survivors are appended at the unit's output offset from the decoupled look-back.
+#ifndef MD_CTAS
+#define MD_CTAS 6               // resident CTAs per SM the kernel is compiled for (register budget)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
+__global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
                                                           const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                           const int64_t *__restrict__ unit_work_begin,
                                                           const double *__restrict__ times_bkg,
@@ -587,107 +614,116 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
 {
     __shared__ MdSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // ---- 0. plan (thread 0) ------------------------------------------------------------------------------
     if (tid == 0) {
-        sm.ticket = (long long)atomicAdd(ticket_counter, 1ull);
+        MdPlan pl;
+        pl.w = (int64_t)atomicAdd(ticket_counter, 1ull);
+        pl.live = 0;
+        if (pl.w < n_work) {
+            const cgrb_work_t wk = work[pl.w];
+            const cgrb_unit_t *u = units + wk.unit;
+            pl.unit = wk.unit;
+            pl.nA = counts[wk.unit].n_bkg;
+            pl.nB = counts[wk.unit].n_src;
+            const int64_t total = pl.nA + pl.nB;
+            pl.wb = unit_work_begin[wk.unit];
+            pl.d0 = wk.start;
+            if (pl.d0 >= total) {
+                // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so nobody
+                // will look back at it (the last LIVE tile writes n_kept)
+                if (pl.w == pl.wb) {
+                    counts[wk.unit].n_total = total;
+                    counts[wk.unit].n_kept = 0;
+                }
+            } else {
+                pl.live = 1;
+                const int64_t d1 = min(pl.d0 + (int64_t)MD_TILE, total);
+                const int64_t g0 = max((int64_t)0, pl.d0 - MD_HALO);    // first merged rank held in shared memory
+                pl.l0 = (int)(pl.d0 - g0);
+                pl.nt = (int)(d1 - pl.d0);
+                pl.has0 = g0 == 0;
+                pl.last = d1 == total;
+                // d1 is either the next tile's start (same unit) or the end of the merged list
+                const int64_t i0 = splits[2 * pl.w], i1 = pl.last ? pl.nA : splits[2 * (pl.w + 1) + 1];
+                const int64_t j0 = g0 - i0, j1 = d1 - i1;
+                pl.na = (int)(i1 - i0);
+                pl.nb = (int)(j1 - j0);
+                // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]: shared and global addresses
+                // agree mod 16
+                const double *gA = times_bkg + u->bkg_off + i0, *gB = times_src + u->src_off + j0;
+                const uint8_t *hA = pha_bkg + u->bkg_off + i0, *hB = pha_src + u->src_off + j0;
+                pl.ta = (int)(((uintptr_t)gA >> 3) & 1u);
+                pl.tb = ((pl.ta + pl.na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
+                pl.qa = (int)((uintptr_t)hA & 15u);
+                pl.qb = ((pl.qa + pl.na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
+                pl.ptA = bulk_plan<8>(gA, pl.na);
+                pl.ptB = bulk_plan<8>(gB, pl.nb);
+                pl.ppA = bulk_plan<1>(hA, pl.na);
+                pl.ppB = bulk_plan<1>(hB, pl.nb);
+                pl.bulk_bytes = 8u * (unsigned)(pl.ptA.body + pl.ptB.body) + (unsigned)(pl.ppA.body + pl.ppB.body);
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                if (pl.bulk_bytes) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(pl.bulk_bytes)
+                                 : "memory");
+                    if (pl.ptA.body)
+                        bulk_issue(sm.t + pl.ta + pl.ptA.head, gA + pl.ptA.head, 8u * pl.ptA.body, &sm.bar);
+                    if (pl.ptB.body)
+                        bulk_issue(sm.t + pl.tb + pl.ptB.head, gB + pl.ptB.head, 8u * pl.ptB.body, &sm.bar);
+                    if (pl.ppA.body)
+                        bulk_issue(sm.p + pl.qa + pl.ppA.head, hA + pl.ppA.head, (unsigned)pl.ppA.body, &sm.bar);
+                    if (pl.ppB.body)
+                        bulk_issue(sm.p + pl.qb + pl.ppB.head, hB + pl.ppB.head, (unsigned)pl.ppB.body, &sm.bar);
+                }
+            }
+        }
+        sm.plan = pl;
         sm.n_rare = 0;
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < MD_TILE / 32)
         sm.rarekeep[tid] = 0u;
     __syncthreads();
-    const int64_t w = sm.ticket;
-    if (w >= n_work)
+    if (!sm.plan.live)
         return;
-    const cgrb_work_t wk = work[w];
-    const cgrb_unit_t *u = units + wk.unit;
-    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
-    const int64_t total = nA + nB;
-    const int64_t wb = unit_work_begin[wk.unit];
-    const int64_t d0 = wk.start, d1 = min(d0 + (int64_t)MD_TILE, total);
-    if (d0 >= total) {
-        // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so nobody
-        // will look back at it (the last LIVE tile writes n_kept)
-        if (w == wb && tid == 0) {
-            counts[wk.unit].n_total = total;
-            counts[wk.unit].n_kept = 0;
-        }
-        return;
-    }
-    const double *A = times_bkg + u->bkg_off;
-    const double *B = times_src + u->src_off;
-    const uint8_t *pA = pha_bkg + u->bkg_off;
-    const uint8_t *pB = pha_src + u->src_off;
-    const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
-    const int l0 = (int)(d0 - g0), nt = (int)(d1 - d0);
-    // d1 is either the next tile's start (same unit) or the end of the merged list
-    const int64_t i0 = splits[2 * w], i1 = (d1 == total) ? nA : splits[2 * (w + 1) + 1];
-    const int64_t j0 = g0 - i0, j1 = d1 - i1;
-    const int na = (int)(i1 - i0), nb = (int)(j1 - j0);
-    const int n = na + nb;                                    // = d1 - g0 <= MD_N
+    const int na = sm.plan.na, nb = sm.plan.nb, n = na + nb;    // n = d1 - g0 <= MD_N
+    const int l0 = sm.plan.l0, nt = sm.plan.nt;
+    const int ta = sm.plan.ta, tb = sm.plan.tb, qa = sm.plan.qa, qb = sm.plan.qb;
+    const int unit = sm.plan.unit;
 
-    // ---- 1. stage the slices -------------------------------------------------------------------------
-    // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]; shared and global addresses agree mod 16
-    const double *gA = A + i0, *gB = B + j0;
-    const uint8_t *hA = pA + i0, *hB = pB + j0;
-    const int ta = (int)(((uintptr_t)gA >> 3) & 1u);
-    const int tb = ((ta + na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
-    const int qa = (int)((uintptr_t)hA & 15u);
-    const int qb = ((qa + na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
-    const BulkPlan ptA = bulk_plan<8>(gA, na), ptB = bulk_plan<8>(gB, nb);
-    const BulkPlan ppA = bulk_plan<1>(hA, na), ppB = bulk_plan<1>(hB, nb);
-    const unsigned bulk_bytes = 8u * (unsigned)(ptA.body + ptB.body) + (unsigned)(ppA.body + ppB.body);
-    if (tid == 0 && bulk_bytes) {
-        const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bulk_bytes) : "memory");
-        if (ptA.body)
-            bulk_issue(sm.t + ta + ptA.head, gA + ptA.head, 8u * ptA.body, &sm.bar);
-        if (ptB.body)
-            bulk_issue(sm.t + tb + ptB.head, gB + ptB.head, 8u * ptB.body, &sm.bar);
-        if (ppA.body)
-            bulk_issue(sm.p + qa + ppA.head, hA + ppA.head, (unsigned)ppA.body, &sm.bar);
-        if (ppB.body)
-            bulk_issue(sm.p + qb + ppB.head, hB + ppB.head, (unsigned)ppB.body, &sm.bar);
-    }
-    // heads and tails (< 16 bytes each): plain loads
-    if (tid < 64) {
-        const int which = tid >> 4, k = tid & 15;           // 0: t of A, 1: t of B, 2: p of A, 3: p of B
-        const BulkPlan pl = which == 0 ? ptA : which == 1 ? ptB : which == 2 ? ppA : ppB;
+    // ---- 1. stage the slices: heads and tails (< 16 bytes each) by plain loads, the rest is in flight -------
+    if (tid < 96) {
+        const cgrb_unit_t *u = units + unit;
+        const int64_t d1 = sm.plan.d0 + nt;
+        const int64_t i0 = (sm.plan.last ? sm.plan.nA : splits[2 * (sm.plan.w + 1) + 1]) - na, j0 = d1 - n - i0;
+        const int which = tid < 64 ? (tid >> 4) : 2 + ((tid - 64) >> 4);    // 0: t of A, 1: t of B, 2: p of A, 3: p of B
+        const int k = tid & 15;
+        const BulkPlan pl = which == 0 ? sm.plan.ptA : which == 1 ? sm.plan.ptB : which == 2 ? sm.plan.ppA : sm.plan.ppB;
         const int cnt = (which & 1) ? nb : na;
         const int tail0 = pl.head + pl.body;                // first element of the tail
         int e = -1;
-        if (k < pl.head)
-            e = k;
-        else if (k - pl.head < cnt - tail0)
-            e = tail0 + (k - pl.head);
-        // (a time slice has at most one head and one tail element, a pha slice at most 15 + 15: k covers 16 of
-        //  them, the remaining tail bytes below)
+        if (tid < 64) {
+            // a time slice has at most one head and one tail element, a pha slice at most 15 + 15: k covers the
+            // head and the first 16 - head tail bytes, the threads 64 .. 95 the remaining tail bytes
+            if (k < pl.head)
+                e = k;
+            else if (k - pl.head < cnt - tail0)
+                e = tail0 + (k - pl.head);
+        } else if (tail0 + (16 - pl.head) + k < cnt)
+            e = tail0 + (16 - pl.head) + k;
         if (e >= 0) {
             if (which == 0)
-                sm.t[ta + e] = gA[e];
+                sm.t[ta + e] = times_bkg[u->bkg_off + i0 + e];
             else if (which == 1)
-                sm.t[tb + e] = gB[e];
+                sm.t[tb + e] = times_src[u->src_off + j0 + e];
             else if (which == 2)
-                sm.p[qa + e] = hA[e];
+                sm.p[qa + e] = pha_bkg[u->bkg_off + i0 + e];
             else
-                sm.p[qb + e] = hB[e];
-        }
-    } else if (tid < 96) {
-        // pha tails beyond the 16 head + tail bytes handled above
-        const int which = 2 + ((tid - 64) >> 4), k = tid & 15;
-        const BulkPlan pl = which == 2 ? ppA : ppB;
-        const int cnt = (which & 1) ? nb : na;
-        const int e = pl.head + pl.body + (16 - pl.head) + k;
-        if (e < cnt) {
-            if (which == 2)
-                sm.p[qa + e] = hA[e];
-            else
-                sm.p[qb + e] = hB[e];
+                sm.p[qb + e] = pha_src[u->src_off + j0 + e];
         }
     }
     bool failed = false;
-    if (bulk_bytes)
+    if (sm.plan.bulk_bytes)
         failed = !mbar_wait(&sm.bar, 0u);
     __syncthreads();
 
@@ -697,6 +733,62 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
         // a tile fed by one list only: the slice IS the merged order
         T = sm.t + (na ? ta : tb);
         P = sm.p + (na ? qa : qb);
+    } else if (min(na, nb) <= MD_SPARSE) {
+        // insertion merge: minority M (nm events) into majority J (nj events).  Ties: background first, so a
+        // background event precedes the source events >= it, a source event follows the background events <= it.
+        const bool minor_a = na <= nb;
+        const int nm = minor_a ? na : nb, nj = n - nm;
+        const double *M = sm.t + (minor_a ? ta : tb), *J = sm.t + (minor_a ? tb : ta);
+        const uint8_t *pM = sm.p + (minor_a ? qa : qb), *pJ = sm.p + (minor_a ? qb : qa);
+        double rt[MD_PER], mt = 0.0;
+        uint8_t rp[MD_PER], mp = 0;
+        int mdest = 0;
+#pragma unroll
+        for (int r = 0; r < MD_PER; r++) {
+            const int k = r * NT + tid;
+            rt[r] = (k < nj) ? J[k] : 0.0;
+            rp[r] = (k < nj) ? pJ[k] : 0;
+        }
+        if (tid < nm) {
+            mt = M[tid];
+            mp = pM[tid];
+            int lo = 0, hi = nj;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const double v = J[mid];
+                if (minor_a ? (v < mt) : (v <= mt))
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            sm.ins[tid] = (uint16_t)lo;
+            mdest = lo + tid;
+        }
+        __syncthreads();
+        if (tid <= (nj + 31) / 32) {
+            int c = 0;                                      // minority events inserted before majority index 32 tid
+            while (c < nm && (int)sm.ins[c] < 32 * tid)
+                c++;
+            sm.cblk[tid] = (uint8_t)c;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < MD_PER; r++) {
+            const int k = r * NT + tid;
+            if (k < nj) {
+                const int c1 = sm.cblk[(k >> 5) + 1];
+                int c = sm.cblk[k >> 5];
+                for (int i = c; i < c1; i++)
+                    c += ((int)sm.ins[i] <= k) ? 1 : 0;
+                sm.t[k + c] = rt[r];
+                sm.p[k + c] = rp[r];
+            }
+        }
+        if (tid < nm) {
+            sm.t[mdest] = mt;
+            sm.p[mdest] = mp;
+        }
+        __syncthreads();
     } else {
         // serial merge of MD_PER consecutive outputs per thread from its merge-path split, in place through registers
         const double *a_ = sm.t + ta, *b_ = sm.t + tb;
@@ -737,9 +829,9 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
 
     // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
     unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
-    MergedGlobal mg{A, B, pA, pB, nA, nB};
+    const int64_t d0 = sm.plan.d0;
     if (MODE == 0) {
-        const bool has0 = (g0 == 0);
+        const bool has0 = sm.plan.has0 != 0;
 #pragma unroll
         for (int r = 0; r < MD_PER; r++) {
             const int li = r * NT + tid;
@@ -749,33 +841,43 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
                 sm.chain[r * NW + wid] = bal;
         }
         __syncthreads();
+        // nearest chain element before each word (exclusive prefix maximum over the 72 words, per warp in registers:
+        // lane l of chunk c holds the value for word 32 c + l); "none": the halo's first event decides (index 0; a
+        // unit's event 0 is itself a chain element, so with has0 "none" only happens to event 0)
+        int carry[3];
+        {
+            int run = 0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const int wd = 32 * c + lane;
+                const unsigned m = (wd < MD_WORDS) ? sm.chain[wd] : 0u;
+                int v = m ? (wd << 5) + 31 - __clz(m) : 0;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, v, dlt);
+                    if (lane >= dlt)
+                        v = max(v, o);
+                }
+                int ex = __shfl_up_sync(0xffffffffu, v, 1);
+                if (lane == 0)
+                    ex = 0;
+                carry[c] = max(run, ex);
+                run = max(run, __shfl_sync(0xffffffffu, v, 31));
+            }
+        }
+        const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
         for (int r = 0; r < MD_R; r++) {
             const int e = r * NT + tid;
+            const int wd = (l0 >> 5) + r * NW + wid;            // l0 is 0 or MD_HALO: li & 31 == lane
+            const int cw = __shfl_sync(0xffffffffu, wd < 32 ? carry[0] : wd < 64 ? carry[1] : carry[2], wd & 31);
             if (e < nt) {
                 const int li = l0 + e;
                 int keep = 1;
-                const double ti = T[li];
-                // (li == 0 only for the unit's event 0, which is kept)  Nobody within the longest window: kept.
-                if (li > 0 && !(T[li - 1] + DT_TAU < ti)) {
-                    // nearest chain element before li, looked for only as far back as the window reaches
-                    int wd = li >> 5;
-                    unsigned m = sm.chain[wd] & ((1u << (li & 31)) - 1u);
-                    int j = -1;
-                    for (;;) {
-                        if (m) {
-                            j = (wd << 5) + 31 - __clz(m);
-                            break;
-                        }
-                        if (wd == 0) {
-                            j = 0;                          // halo exhausted: its first event decides (g0 > 0 here)
-                            break;
-                        }
-                        if (T[(wd << 5) - 1] + DT_TAU < ti)
-                            break;                          // everything in the earlier words lies outside the window
-                        m = sm.chain[--wd];
-                    }
-                    if (j >= 0 && !(T[j] + DT_TAU < ti)) {
+                if (!(has0 && li == 0)) {
+                    const unsigned m = sm.chain[wd] & lt;
+                    const int j = m ? (wd << 5) + 31 - __clz(m) : cw;
+                    if (!(T[j] + DT_TAU < T[li])) {
                         // a chain element (or an exhausted halo) within the window: the exact walk decides
                         sm.rare[atomicAdd(&sm.n_rare, 1)] = (uint16_t)e;
                         keep = 0;
@@ -787,6 +889,10 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
         __syncthreads();
         const int n_rare = sm.n_rare;
         if (n_rare > 0) {
+            const cgrb_unit_t *u = units + unit;
+            const MergedGlobal mg{times_bkg + u->bkg_off, times_src + u->src_off, pha_bkg + u->bkg_off,
+                                  pha_src + u->src_off, sm.plan.nA, sm.plan.nB};
+            const int64_t g0 = d0 - l0;
             for (int k = tid; k < n_rare; k += NT) {
                 const int e = sm.rare[k];
                 int keep = dt_keep_local(T, P, l0 + e, g0);
@@ -802,7 +908,7 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
         }
     } else {
         // physical mode: a unit already flagged for the serial fix-up needs no more work here
-        const bool flagged = ((*(volatile uint32_t *)&counts[wk.unit].status) & CGRB_ST_DEADTIME_CHAIN) != 0;
+        const bool flagged = ((*(volatile uint32_t *)&counts[unit].status) & CGRB_ST_DEADTIME_CHAIN) != 0;
         const EventArrays ev{T, P};
 #pragma unroll
         for (int r = 0; r < MD_R; r++) {
@@ -811,18 +917,21 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
             if (e < nt) {
                 // no synchronisation point inside the tile's halo (256 events closer than the longest
                 // window: never at GBM rates): the unit goes to the serial fix-up kernel
-                keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), g0 == 0, md);
+                keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), sm.plan.has0 != 0, md);
                 if (keep == 2) {
-                    atomicOr(&counts[wk.unit].status, CGRB_ST_DEADTIME_CHAIN);
+                    atomicOr(&counts[unit].status, CGRB_ST_DEADTIME_CHAIN);
                     keep = 0;
                 }
             }
             keep_bits |= (unsigned)keep << r;
         }
     }
+    // survivors per (round, warp); this lane's rank inside its group, 8 bits per round
+    unsigned long long ranks = 0ull;
 #pragma unroll
     for (int r = 0; r < MD_R; r++) {
         const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
+        ranks |= (unsigned long long)__popc(bal & ((1u << lane) - 1u)) << (8 * r);
         if (lane == 0)
             sm.cnt[r * NW + wid] = __popc(bal);
     }
@@ -835,26 +944,25 @@ __global__ void __launch_bounds__(NT, 6) k_merge_deadtime(const cgrb_unit_t *__r
         const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
         sm.cnt[2 * lane] = incl - c0 - c1;
         sm.cnt[2 * lane + 1] = incl - c1;
-        const long long excl = lookback_exclusive(tile_state, w, wb, cnt_tile, lane, &failed);
+        const long long excl = lookback_exclusive(tile_state, sm.plan.w, sm.plan.wb, cnt_tile, lane, &failed);
         if (lane == 0) {
             sm.excl = excl;
-            if (w == wb)
-                counts[wk.unit].n_total = total;
-            if (d1 == total)
-                counts[wk.unit].n_kept = excl + cnt_tile;     // the last live tile of the unit
+            if (sm.plan.w == sm.plan.wb)
+                counts[unit].n_total = sm.plan.nA + sm.plan.nB;
+            if (sm.plan.last)
+                counts[unit].n_kept = excl + cnt_tile;        // the last live tile of the unit
         }
     }
     if (failed)
-        atomicOr(&counts[wk.unit].status, CGRB_ST_INTERNAL);
+        atomicOr(&counts[unit].status, CGRB_ST_INTERNAL);
     __syncthreads();
-    double *ot = times_out + u->tot_off + sm.excl;
-    uint8_t *op = pha_out + u->tot_off + sm.excl;
+    const int64_t out0 = units[unit].tot_off + sm.excl;
+    double *ot = times_out + out0;
+    uint8_t *op = pha_out + out0;
 #pragma unroll
     for (int r = 0; r < MD_R; r++) {
-        // survivors of (round r, this warp) before this lane
-        const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
         if ((keep_bits >> r) & 1u) {
-            const int rank = sm.cnt[r * NW + wid] + __popc(bal & ((1u << lane) - 1u));
+            const int rank = sm.cnt[r * NW + wid] + (int)((ranks >> (8 * r)) & 0xffull);
             const int li = l0 + r * NT + tid;
             ot[rank] = T[li];
             op[rank] = P[li];
