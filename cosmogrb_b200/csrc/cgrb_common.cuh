@@ -199,6 +199,9 @@ __device__ __forceinline__ double lambda_per_flux_at(const LambdaTab *tab, const
 #define LB_FLAG_INC (2ull << 62)
 #define LB_VALUE_MASK ((1ull << 62) - 1ull)
 #define LB_WAIT_NS 20000000000ull       // 20 s
+#ifndef LB_SLEEP_NS
+#define LB_SLEEP_NS 0
+#endif
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -246,7 +249,9 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long *stat
                             break;
                         }
                     }
-                    __nanosleep(32);            // leave the issue slots to the warps that have work
+#if LB_SLEEP_NS > 0
+                    __nanosleep(LB_SLEEP_NS);   // leave the issue slots to the warps that have work
+#endif
                     if ((st[q] >> 62) == 0ull)
                         st[q] = *((volatile unsigned long long *)(state + my));
                 }

@@ -531,7 +531,15 @@ __device__ __forceinline__ void bulk_issue(void *dst, const void *src, unsigned 
 __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
 {
     const unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar);
-    for (int spin = 0; spin < (1 << 24); spin++) {
+    unsigned long long t_begin = 0;
+    for (int spin = 0;; spin++) {
+        if ((spin & 255) == 255) {
+            const unsigned long long now = global_timer_ns();
+            if (t_begin == 0)
+                t_begin = now;
+            else if (now - t_begin > LB_WAIT_NS)
+                return false;
+        }
         unsigned done;
         asm volatile(
             "{\n"
@@ -545,18 +553,22 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
         if (done)
             return true;
     }
-    return false;
 }
 
 #define MD_SPARSE 64             // a tile whose minority list has at most this many events is merged by insertion
+#define MD_NT_ALL (NT + 32)      // consumers + the producer warp
+#ifndef MD_CTAS
+#define MD_CTAS 4                // resident CTAs per SM (two staging buffers each: 47 KB of shared memory)
+#endif
 
-// everything a tile's threads need to know about it, worked out once by thread 0
+// everything the consumers need to know about a tile, worked out by the producer
 struct MdPlan {
     int64_t w, wb, d0;
     int64_t nA, nB;
+    int64_t i0, j0;             // first staged event of list A (background) / B (source)
     int unit;
-    int live;
-    int na, nb;                 // staged events of list A (background) / B (source): halo + tile
+    int live;                   // 1: a tile to process, 0: no more tiles
+    int na, nb;                 // staged events of list A / B: halo + tile
     int l0, nt;                 // first local index and number of the tile's own events
     int has0;                   // local index 0 is the unit's event 0
     int last;                   // the unit's last live tile
@@ -565,9 +577,14 @@ struct MdPlan {
     unsigned bulk_bytes;
 };
 
-struct MdSmem {
+struct MdStage {
     alignas(16) double t[MD_N + 4];         // slack: the alignment shift of up to two staged slices
     alignas(16) uint8_t p[MD_N + 48];
+};
+
+struct MdSmem {
+    MdStage st[2];
+    MdPlan plan[2];
     uint32_t chain[MD_WORDS];               // bit li: local event li is a chain element (overflow channel / event 0)
     uint32_t rarekeep[MD_TILE / 32];        // keep flags of the tile elements resolved by the chain walk
     uint16_t rare[MD_TILE];                 // tile elements that need the chain walk
@@ -576,30 +593,48 @@ struct MdSmem {
     int cnt[MD_R * NW];                     // survivors per (round, warp), then their exclusive prefix
     int n_rare;
     long long excl;
-    MdPlan plan;
-    alignas(8) uint64_t bar;
+    alignas(8) uint64_t full[2];            // stage filled (producer lanes + bulk bytes)
+    alignas(8) uint64_t empty[2];           // stage released by the consumers
 };
 
-// One CTA per tile of MD_TILE merged events, tile index from a ticket counter (see lookback_exclusive).
-//  1. thread 0 works out the tile's plan and hands the tile's slices of the two component lists (+ MD_HALO events
-//     of look-back) to the bulk-async engine.  A tile fed by one list only -- nearly every tile of a
-//     background-dominated unit -- is then already in merged order.  A tile with a sparse minority (<= MD_SPARSE
-//     events of one list: the background under a bright burst, the burst's photons in the background) is merged by
-//     insertion: every minority event finds its place in the majority by bisection, every majority event shifts by
-//     the number of insertions before it (a count per 32 events + the few insertions of its own block).  Anything
-//     else takes the general merge-path: MD_PER consecutive outputs per thread from its split.  In place, through
-//     registers.
+__device__ __forceinline__ void mbar_init(uint64_t *b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)),
+                 "r"(bytes)
+                 : "memory");
+}
+// barrier among the NT consumer threads only (the producer warp never joins it)
+__device__ __forceinline__ void consumer_sync()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+
+// Persistent, software-pipelined: MD_CTAS CTAs per SM, each with a PRODUCER warp that claims the next tile from the
+// ticket counter (see lookback_exclusive), works out its plan and stages its slices of the two component lists
+// (+ MD_HALO events of look-back) into one of two buffers -- the aligned middle by the bulk-async engine, the
+// < 16-byte heads and tails by plain loads -- while the eight CONSUMER warps resolve the previous tile:
+//  1. merge.  A tile fed by one list only -- nearly every tile of a background-dominated unit -- is already in
+//     merged order.  A tile with a sparse minority (<= MD_SPARSE events of one list: the background under a bright
+//     burst, the burst's photons in the background) is merged by insertion: every minority event finds its place
+//     in the majority by bisection, every majority event shifts by the number of insertions before it (a count per
+//     32 events + the few insertions of its own block).  Anything else takes the general merge-path: MD_PER
+//     consecutive outputs per thread from its split.  In place, through registers.
 //  2. literal dead time: a bitmap of the chain elements (overflow channel, the unit's event 0); every warp derives
 //     the nearest chain element before each 32-event word by a prefix maximum over the words (registers), so an
 //     event finds its nearest earlier chain element from one word and one shuffle.  Only if that one lies within the
 //     longest window does the event join the `rare` list, which is then resolved densely by the exact walk
 //     (dt_keep_local, or the global accessor when the chain leaves the halo).
 //  3. survivors are appended at the unit's output offset from the decoupled look-back.
-#ifndef MD_CTAS
-#define MD_CTAS 6               // resident CTAs per SM the kernel is compiled for (register budget)
-#endif
 template <int MODE>
-__global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
+__global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
                                                           const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                           const int64_t *__restrict__ unit_work_begin,
                                                           const double *__restrict__ times_bkg,
@@ -614,359 +649,393 @@ __global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_
 {
     __shared__ MdSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    // ---- 0. plan (thread 0) ------------------------------------------------------------------------------
     if (tid == 0) {
-        MdPlan pl;
-        pl.w = (int64_t)atomicAdd(ticket_counter, 1ull);
-        pl.live = 0;
-        if (pl.w < n_work) {
-            const cgrb_work_t wk = work[pl.w];
-            const cgrb_unit_t *u = units + wk.unit;
-            pl.unit = wk.unit;
-            pl.nA = counts[wk.unit].n_bkg;
-            pl.nB = counts[wk.unit].n_src;
-            const int64_t total = pl.nA + pl.nB;
-            pl.wb = unit_work_begin[wk.unit];
-            pl.d0 = wk.start;
-            if (pl.d0 >= total) {
-                // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so nobody
-                // will look back at it (the last LIVE tile writes n_kept)
-                if (pl.w == pl.wb) {
-                    counts[wk.unit].n_total = total;
-                    counts[wk.unit].n_kept = 0;
-                }
-            } else {
-                pl.live = 1;
-                const int64_t d1 = min(pl.d0 + (int64_t)MD_TILE, total);
-                const int64_t g0 = max((int64_t)0, pl.d0 - MD_HALO);    // first merged rank held in shared memory
-                pl.l0 = (int)(pl.d0 - g0);
-                pl.nt = (int)(d1 - pl.d0);
-                pl.has0 = g0 == 0;
-                pl.last = d1 == total;
-                // d1 is either the next tile's start (same unit) or the end of the merged list
-                const int64_t i0 = splits[2 * pl.w], i1 = pl.last ? pl.nA : splits[2 * (pl.w + 1) + 1];
-                const int64_t j0 = g0 - i0, j1 = d1 - i1;
-                pl.na = (int)(i1 - i0);
-                pl.nb = (int)(j1 - j0);
-                // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]: shared and global addresses
-                // agree mod 16
-                const double *gA = times_bkg + u->bkg_off + i0, *gB = times_src + u->src_off + j0;
-                const uint8_t *hA = pha_bkg + u->bkg_off + i0, *hB = pha_src + u->src_off + j0;
-                pl.ta = (int)(((uintptr_t)gA >> 3) & 1u);
-                pl.tb = ((pl.ta + pl.na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
-                pl.qa = (int)((uintptr_t)hA & 15u);
-                pl.qb = ((pl.qa + pl.na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
-                pl.ptA = bulk_plan<8>(gA, pl.na);
-                pl.ptB = bulk_plan<8>(gB, pl.nb);
-                pl.ppA = bulk_plan<1>(hA, pl.na);
-                pl.ppB = bulk_plan<1>(hB, pl.nb);
-                pl.bulk_bytes = 8u * (unsigned)(pl.ptA.body + pl.ptB.body) + (unsigned)(pl.ppA.body + pl.ppB.body);
-                const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                if (pl.bulk_bytes) {
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(pl.bulk_bytes)
-                                 : "memory");
-                    if (pl.ptA.body)
-                        bulk_issue(sm.t + pl.ta + pl.ptA.head, gA + pl.ptA.head, 8u * pl.ptA.body, &sm.bar);
-                    if (pl.ptB.body)
-                        bulk_issue(sm.t + pl.tb + pl.ptB.head, gB + pl.ptB.head, 8u * pl.ptB.body, &sm.bar);
-                    if (pl.ppA.body)
-                        bulk_issue(sm.p + pl.qa + pl.ppA.head, hA + pl.ppA.head, (unsigned)pl.ppA.body, &sm.bar);
-                    if (pl.ppB.body)
-                        bulk_issue(sm.p + pl.qb + pl.ppB.head, hB + pl.ppB.head, (unsigned)pl.ppB.body, &sm.bar);
+        mbar_init(&sm.full[0], 32);
+        mbar_init(&sm.full[1], 32);
+        mbar_init(&sm.empty[0], 1);
+        mbar_init(&sm.empty[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wid == NW) {
+        // =============================== producer warp =========================================================
+        for (int it = 0;; it++) {
+            const int s = it & 1;
+            MdStage &S = sm.st[s];
+            MdPlan pl{};
+            const double *gA = nullptr, *gB = nullptr;
+            const uint8_t *hA = nullptr, *hB = nullptr;
+            if (lane == 0) {
+                for (;;) {
+                    pl.w = (int64_t)atomicAdd(ticket_counter, 1ull);
+                    if (pl.w >= n_work)
+                        break;
+                    const cgrb_work_t wk = work[pl.w];
+                    const cgrb_unit_t *u = units + wk.unit;
+                    pl.unit = wk.unit;
+                    pl.nA = counts[wk.unit].n_bkg;
+                    pl.nB = counts[wk.unit].n_src;
+                    const int64_t total = pl.nA + pl.nB;
+                    pl.wb = unit_work_begin[wk.unit];
+                    pl.d0 = wk.start;
+                    if (pl.d0 >= total) {
+                        // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so
+                        // nobody will look back at it (the last LIVE tile writes n_kept)
+                        if (pl.w == pl.wb) {
+                            counts[wk.unit].n_total = total;
+                            counts[wk.unit].n_kept = 0;
+                        }
+                        continue;
+                    }
+                    pl.live = 1;
+                    const int64_t d1 = min(pl.d0 + (int64_t)MD_TILE, total);
+                    const int64_t g0 = max((int64_t)0, pl.d0 - MD_HALO);    // first merged rank held in shared memory
+                    pl.l0 = (int)(pl.d0 - g0);
+                    pl.nt = (int)(d1 - pl.d0);
+                    pl.has0 = g0 == 0;
+                    pl.last = d1 == total;
+                    // d1 is either the next tile's start (same unit) or the end of the merged list
+                    const int64_t i1 = pl.last ? pl.nA : splits[2 * (pl.w + 1) + 1];
+                    pl.i0 = splits[2 * pl.w];
+                    pl.j0 = g0 - pl.i0;
+                    pl.na = (int)(i1 - pl.i0);
+                    pl.nb = (int)((d1 - i1) - pl.j0);
+                    // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]: shared and global
+                    // addresses agree mod 16
+                    gA = times_bkg + u->bkg_off + pl.i0;
+                    gB = times_src + u->src_off + pl.j0;
+                    hA = pha_bkg + u->bkg_off + pl.i0;
+                    hB = pha_src + u->src_off + pl.j0;
+                    pl.ta = (int)(((uintptr_t)gA >> 3) & 1u);
+                    pl.tb = ((pl.ta + pl.na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
+                    pl.qa = (int)((uintptr_t)hA & 15u);
+                    pl.qb = ((pl.qa + pl.na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
+                    pl.ptA = bulk_plan<8>(gA, pl.na);
+                    pl.ptB = bulk_plan<8>(gB, pl.nb);
+                    pl.ppA = bulk_plan<1>(hA, pl.na);
+                    pl.ppB = bulk_plan<1>(hB, pl.nb);
+                    pl.bulk_bytes = 8u * (unsigned)(pl.ptA.body + pl.ptB.body) + (unsigned)(pl.ppA.body + pl.ppB.body);
+                    break;
                 }
             }
-        }
-        sm.plan = pl;
-        sm.n_rare = 0;
-    }
-    if (tid < MD_TILE / 32)
-        sm.rarekeep[tid] = 0u;
-    __syncthreads();
-    if (!sm.plan.live)
-        return;
-    const int na = sm.plan.na, nb = sm.plan.nb, n = na + nb;    // n = d1 - g0 <= MD_N
-    const int l0 = sm.plan.l0, nt = sm.plan.nt;
-    const int ta = sm.plan.ta, tb = sm.plan.tb, qa = sm.plan.qa, qb = sm.plan.qb;
-    const int unit = sm.plan.unit;
-
-    // ---- 1. stage the slices: heads and tails (< 16 bytes each) by plain loads, the rest is in flight -------
-    if (tid < 96) {
-        const cgrb_unit_t *u = units + unit;
-        const int64_t d1 = sm.plan.d0 + nt;
-        const int64_t i0 = (sm.plan.last ? sm.plan.nA : splits[2 * (sm.plan.w + 1) + 1]) - na, j0 = d1 - n - i0;
-        const int which = tid < 64 ? (tid >> 4) : 2 + ((tid - 64) >> 4);    // 0: t of A, 1: t of B, 2: p of A, 3: p of B
-        const int k = tid & 15;
-        const BulkPlan pl = which == 0 ? sm.plan.ptA : which == 1 ? sm.plan.ptB : which == 2 ? sm.plan.ppA : sm.plan.ppB;
-        const int cnt = (which & 1) ? nb : na;
-        const int tail0 = pl.head + pl.body;                // first element of the tail
-        int e = -1;
-        if (tid < 64) {
-            // a time slice has at most one head and one tail element, a pha slice at most 15 + 15: k covers the
-            // head and the first 16 - head tail bytes, the threads 64 .. 95 the remaining tail bytes
-            if (k < pl.head)
-                e = k;
-            else if (k - pl.head < cnt - tail0)
-                e = tail0 + (k - pl.head);
-        } else if (tail0 + (16 - pl.head) + k < cnt)
-            e = tail0 + (16 - pl.head) + k;
-        if (e >= 0) {
-            if (which == 0)
-                sm.t[ta + e] = times_bkg[u->bkg_off + i0 + e];
-            else if (which == 1)
-                sm.t[tb + e] = times_src[u->src_off + j0 + e];
-            else if (which == 2)
-                sm.p[qa + e] = pha_bkg[u->bkg_off + i0 + e];
-            else
-                sm.p[qb + e] = pha_src[u->src_off + j0 + e];
-        }
-    }
-    bool failed = false;
-    if (sm.plan.bulk_bytes)
-        failed = !mbar_wait(&sm.bar, 0u);
-    __syncthreads();
-
-    const double *T = sm.t;
-    const uint8_t *P = sm.p;
-    if (na == 0 || nb == 0) {
-        // a tile fed by one list only: the slice IS the merged order
-        T = sm.t + (na ? ta : tb);
-        P = sm.p + (na ? qa : qb);
-    } else if (min(na, nb) <= MD_SPARSE) {
-        // insertion merge: minority M (nm events) into majority J (nj events).  Ties: background first, so a
-        // background event precedes the source events >= it, a source event follows the background events <= it.
-        const bool minor_a = na <= nb;
-        const int nm = minor_a ? na : nb, nj = n - nm;
-        const double *M = sm.t + (minor_a ? ta : tb), *J = sm.t + (minor_a ? tb : ta);
-        const uint8_t *pM = sm.p + (minor_a ? qa : qb), *pJ = sm.p + (minor_a ? qb : qa);
-        double rt[MD_PER], mt = 0.0;
-        uint8_t rp[MD_PER], mp = 0;
-        int mdest = 0;
+            // the stage must have been released by the consumers of its previous tile
+            bool ok = true;
+            if (it >= 2)
+                ok = mbar_wait(&sm.empty[s], (unsigned)(((it >> 1) & 1) ^ 1));
+            if (lane == 0) {
+                if (!ok && pl.live)
+                    atomicOr(&counts[pl.unit].status, CGRB_ST_INTERNAL);
+                sm.plan[s] = pl;
+            }
+            __syncwarp();
+            const int live = sm.plan[s].live;
+            if (live) {
+                // heads and tails (< 16 bytes each) by plain loads: a time slice has at most one head and one tail
+                // element, a pha slice at most 15 + 15
+                const MdPlan &q = sm.plan[s];
+                const cgrb_unit_t *u = units + q.unit;
+                const double *xa = times_bkg + u->bkg_off + q.i0, *xb = times_src + u->src_off + q.j0;
+                const uint8_t *ya = pha_bkg + u->bkg_off + q.i0, *yb = pha_src + u->src_off + q.j0;
 #pragma unroll
-        for (int r = 0; r < MD_PER; r++) {
-            const int k = r * NT + tid;
-            rt[r] = (k < nj) ? J[k] : 0.0;
-            rp[r] = (k < nj) ? pJ[k] : 0;
+                for (int which = 0; which < 4; which++) {       // 0: t of A, 1: t of B, 2: p of A, 3: p of B
+                    const BulkPlan bp = which == 0 ? q.ptA : which == 1 ? q.ptB : which == 2 ? q.ppA : q.ppB;
+                    const int cnt = (which & 1) ? q.nb : q.na;
+                    const int tail0 = bp.head + bp.body, ntail = cnt - tail0;
+                    const int e = lane < bp.head ? lane : (lane - bp.head < ntail ? tail0 + (lane - bp.head) : -1);
+                    if (e >= 0) {
+                        if (which == 0)
+                            S.t[q.ta + e] = xa[e];
+                        else if (which == 1)
+                            S.t[q.tb + e] = xb[e];
+                        else if (which == 2)
+                            S.p[q.qa + e] = ya[e];
+                        else
+                            S.p[q.qb + e] = yb[e];
+                    }
+                }
+            }
+            if (lane == 0) {
+                if (pl.bulk_bytes) {
+                    mbar_arrive_expect_tx(&sm.full[s], pl.bulk_bytes);
+                    if (pl.ptA.body)
+                        bulk_issue(S.t + pl.ta + pl.ptA.head, gA + pl.ptA.head, 8u * pl.ptA.body, &sm.full[s]);
+                    if (pl.ptB.body)
+                        bulk_issue(S.t + pl.tb + pl.ptB.head, gB + pl.ptB.head, 8u * pl.ptB.body, &sm.full[s]);
+                    if (pl.ppA.body)
+                        bulk_issue(S.p + pl.qa + pl.ppA.head, hA + pl.ppA.head, (unsigned)pl.ppA.body, &sm.full[s]);
+                    if (pl.ppB.body)
+                        bulk_issue(S.p + pl.qb + pl.ppB.head, hB + pl.ppB.head, (unsigned)pl.ppB.body, &sm.full[s]);
+                } else
+                    mbar_arrive(&sm.full[s]);
+            } else
+                mbar_arrive(&sm.full[s]);
+            if (!live)
+                return;
         }
-        if (tid < nm) {
-            mt = M[tid];
-            mp = pM[tid];
-            int lo = 0, hi = nj;
+    }
+
+    // =================================== consumer warps ===========================================================
+    for (int it = 0;; it++) {
+        const int s = it & 1;
+        bool failed = !mbar_wait(&sm.full[s], (unsigned)((it >> 1) & 1));
+        const MdPlan &pl = sm.plan[s];
+        if (!pl.live)
+            return;
+        MdStage &S = sm.st[s];
+        const int na = pl.na, nb = pl.nb, n = na + nb;      // n = d1 - g0 <= MD_N
+        const int l0 = pl.l0, nt = pl.nt;
+        const int ta = pl.ta, tb = pl.tb, qa = pl.qa, qb = pl.qb;
+        const int unit = pl.unit;
+        if (tid < MD_TILE / 32)
+            sm.rarekeep[tid] = 0u;
+        if (tid == 0)
+            sm.n_rare = 0;
+
+        const double *T = S.t;
+        const uint8_t *P = S.p;
+        if (na == 0 || nb == 0) {
+            // a tile fed by one list only: the slice IS the merged order
+            T = S.t + (na ? ta : tb);
+            P = S.p + (na ? qa : qb);
+        } else if (min(na, nb) <= MD_SPARSE) {
+            // insertion merge: minority M (nm events) into majority J (nj events).  Ties: background first, so a
+            // background event precedes the source events >= it, a source event follows the background events <= it.
+            const bool minor_a = na <= nb;
+            const int nm = minor_a ? na : nb, nj = n - nm;
+            const double *M = S.t + (minor_a ? ta : tb), *J = S.t + (minor_a ? tb : ta);
+            const uint8_t *pM = S.p + (minor_a ? qa : qb), *pJ = S.p + (minor_a ? qb : qa);
+            double rt[MD_PER], mt = 0.0;
+            uint8_t rp[MD_PER], mp = 0;
+            int mdest = 0;
+#pragma unroll
+            for (int r = 0; r < MD_PER; r++) {
+                const int k = r * NT + tid;
+                rt[r] = (k < nj) ? J[k] : 0.0;
+                rp[r] = (k < nj) ? pJ[k] : 0;
+            }
+            if (tid < nm) {
+                mt = M[tid];
+                mp = pM[tid];
+                int lo = 0, hi = nj;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const double v = J[mid];
+                    if (minor_a ? (v < mt) : (v <= mt))
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                sm.ins[tid] = (uint16_t)lo;
+                mdest = lo + tid;
+            }
+            consumer_sync();
+            if (tid <= (nj + 31) / 32) {
+                int c = 0;                                  // minority events inserted before majority index 32 tid
+                while (c < nm && (int)sm.ins[c] < 32 * tid)
+                    c++;
+                sm.cblk[tid] = (uint8_t)c;
+            }
+            consumer_sync();
+#pragma unroll
+            for (int r = 0; r < MD_PER; r++) {
+                const int k = r * NT + tid;
+                if (k < nj) {
+                    const int c1 = sm.cblk[(k >> 5) + 1];
+                    int c = sm.cblk[k >> 5];
+                    for (int i = c; i < c1; i++)
+                        c += ((int)sm.ins[i] <= k) ? 1 : 0;
+                    S.t[k + c] = rt[r];
+                    S.p[k + c] = rp[r];
+                }
+            }
+            if (tid < nm) {
+                S.t[mdest] = mt;
+                S.p[mdest] = mp;
+            }
+        } else {
+            // serial merge of MD_PER consecutive outputs per thread from its merge-path split, in place through
+            // registers
+            const double *a_ = S.t + ta, *b_ = S.t + tb;
+            const uint8_t *pa_ = S.p + qa, *pb_ = S.p + qb;
+            const int q0 = min(tid * MD_PER, n);
+            int lo = max(0, q0 - nb), hi = min(q0, na);
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                const double v = J[mid];
-                if (minor_a ? (v < mt) : (v <= mt))
+                if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
                     lo = mid + 1;
                 else
                     hi = mid;
             }
-            sm.ins[tid] = (uint16_t)lo;
-            mdest = lo + tid;
-        }
-        __syncthreads();
-        if (tid <= (nj + 31) / 32) {
-            int c = 0;                                      // minority events inserted before majority index 32 tid
-            while (c < nm && (int)sm.ins[c] < 32 * tid)
-                c++;
-            sm.cblk[tid] = (uint8_t)c;
-        }
-        __syncthreads();
+            int ia = lo, ib = q0 - lo;
+            double rt[MD_PER];
+            uint8_t rp[MD_PER];
 #pragma unroll
-        for (int r = 0; r < MD_PER; r++) {
-            const int k = r * NT + tid;
-            if (k < nj) {
-                const int c1 = sm.cblk[(k >> 5) + 1];
-                int c = sm.cblk[k >> 5];
-                for (int i = c; i < c1; i++)
-                    c += ((int)sm.ins[i] <= k) ? 1 : 0;
-                sm.t[k + c] = rt[r];
-                sm.p[k + c] = rp[r];
-            }
-        }
-        if (tid < nm) {
-            sm.t[mdest] = mt;
-            sm.p[mdest] = mp;
-        }
-        __syncthreads();
-    } else {
-        // serial merge of MD_PER consecutive outputs per thread from its merge-path split, in place through registers
-        const double *a_ = sm.t + ta, *b_ = sm.t + tb;
-        const uint8_t *pa_ = sm.p + qa, *pb_ = sm.p + qb;
-        const int q0 = min(tid * MD_PER, n);
-        int lo = max(0, q0 - nb), hi = min(q0, na);
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        int ia = lo, ib = q0 - lo;
-        double rt[MD_PER];
-        uint8_t rp[MD_PER];
-#pragma unroll
-        for (int r = 0; r < MD_PER; r++) {
-            rt[r] = 0.0;
-            rp[r] = 0;
-            if (q0 + r < n) {
-                const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
-                rt[r] = take_a ? a_[ia] : b_[ib];
-                rp[r] = take_a ? pa_[ia] : pb_[ib];
-                ia += take_a ? 1 : 0;
-                ib += take_a ? 0 : 1;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < MD_PER; r++)
-            if (q0 + r < n) {
-                sm.t[q0 + r] = rt[r];
-                sm.p[q0 + r] = rp[r];
-            }
-        __syncthreads();
-    }
-
-    // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
-    unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
-    const int64_t d0 = sm.plan.d0;
-    if (MODE == 0) {
-        const bool has0 = sm.plan.has0 != 0;
-#pragma unroll
-        for (int r = 0; r < MD_PER; r++) {
-            const int li = r * NT + tid;
-            const bool c = li < n && (P[li] == 127 || (has0 && li == 0));
-            const unsigned bal = __ballot_sync(0xffffffffu, c);
-            if (lane == 0)
-                sm.chain[r * NW + wid] = bal;
-        }
-        __syncthreads();
-        // nearest chain element before each word (exclusive prefix maximum over the 72 words, per warp in registers:
-        // lane l of chunk c holds the value for word 32 c + l); "none": the halo's first event decides (index 0; a
-        // unit's event 0 is itself a chain element, so with has0 "none" only happens to event 0)
-        int carry[3];
-        {
-            int run = 0;
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const int wd = 32 * c + lane;
-                const unsigned m = (wd < MD_WORDS) ? sm.chain[wd] : 0u;
-                int v = m ? (wd << 5) + 31 - __clz(m) : 0;
-#pragma unroll
-                for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, v, dlt);
-                    if (lane >= dlt)
-                        v = max(v, o);
+            for (int r = 0; r < MD_PER; r++) {
+                rt[r] = 0.0;
+                rp[r] = 0;
+                if (q0 + r < n) {
+                    const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
+                    rt[r] = take_a ? a_[ia] : b_[ib];
+                    rp[r] = take_a ? pa_[ia] : pb_[ib];
+                    ia += take_a ? 1 : 0;
+                    ib += take_a ? 0 : 1;
                 }
-                int ex = __shfl_up_sync(0xffffffffu, v, 1);
-                if (lane == 0)
-                    ex = 0;
-                carry[c] = max(run, ex);
-                run = max(run, __shfl_sync(0xffffffffu, v, 31));
             }
-        }
-        const unsigned lt = (1u << lane) - 1u;
+            consumer_sync();
 #pragma unroll
-        for (int r = 0; r < MD_R; r++) {
-            const int e = r * NT + tid;
-            const int wd = (l0 >> 5) + r * NW + wid;            // l0 is 0 or MD_HALO: li & 31 == lane
-            const int cw = __shfl_sync(0xffffffffu, wd < 32 ? carry[0] : wd < 64 ? carry[1] : carry[2], wd & 31);
-            if (e < nt) {
-                const int li = l0 + e;
-                int keep = 1;
-                if (!(has0 && li == 0)) {
-                    const unsigned m = sm.chain[wd] & lt;
-                    const int j = m ? (wd << 5) + 31 - __clz(m) : cw;
-                    if (!(T[j] + DT_TAU < T[li])) {
-                        // a chain element (or an exhausted halo) within the window: the exact walk decides
-                        sm.rare[atomicAdd(&sm.n_rare, 1)] = (uint16_t)e;
+            for (int r = 0; r < MD_PER; r++)
+                if (q0 + r < n) {
+                    S.t[q0 + r] = rt[r];
+                    S.p[q0 + r] = rp[r];
+                }
+        }
+        consumer_sync();        // merged order in place; rarekeep / n_rare cleared
+
+        // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
+        unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
+        const int64_t d0 = pl.d0;
+        if (MODE == 0) {
+            const bool has0 = pl.has0 != 0;
+#pragma unroll
+            for (int r = 0; r < MD_PER; r++) {
+                const int li = r * NT + tid;
+                const bool c = li < n && (P[li] == 127 || (has0 && li == 0));
+                const unsigned bal = __ballot_sync(0xffffffffu, c);
+                if (lane == 0)
+                    sm.chain[r * NW + wid] = bal;
+            }
+            consumer_sync();
+            // nearest chain element before each word (exclusive prefix maximum over the 72 words, per warp in
+            // registers: lane l of chunk c holds the value for word 32 c + l); "none": the halo's first event decides
+            // (index 0; a unit's event 0 is itself a chain element, so with has0 "none" only happens to event 0)
+            int carry[3];
+            {
+                int run = 0;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const int wd = 32 * c + lane;
+                    const unsigned m = (wd < MD_WORDS) ? sm.chain[wd] : 0u;
+                    int v = m ? (wd << 5) + 31 - __clz(m) : 0;
+#pragma unroll
+                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, v, dlt);
+                        if (lane >= dlt)
+                            v = max(v, o);
+                    }
+                    int ex = __shfl_up_sync(0xffffffffu, v, 1);
+                    if (lane == 0)
+                        ex = 0;
+                    carry[c] = max(run, ex);
+                    run = max(run, __shfl_sync(0xffffffffu, v, 31));
+                }
+            }
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int r = 0; r < MD_R; r++) {
+                const int e = r * NT + tid;
+                const int wd = (l0 >> 5) + r * NW + wid;            // l0 is 0 or MD_HALO: li & 31 == lane
+                const int cw = __shfl_sync(0xffffffffu, wd < 32 ? carry[0] : wd < 64 ? carry[1] : carry[2], wd & 31);
+                if (e < nt) {
+                    const int li = l0 + e;
+                    int keep = 1;
+                    if (!(has0 && li == 0)) {
+                        const unsigned m = sm.chain[wd] & lt;
+                        const int j = m ? (wd << 5) + 31 - __clz(m) : cw;
+                        if (!(T[j] + DT_TAU < T[li])) {
+                            // a chain element (or an exhausted halo) within the window: the exact walk decides
+                            sm.rare[atomicAdd(&sm.n_rare, 1)] = (uint16_t)e;
+                            keep = 0;
+                        }
+                    }
+                    keep_bits |= (unsigned)keep << r;
+                }
+            }
+            consumer_sync();
+            const int n_rare = sm.n_rare;
+            if (n_rare > 0) {
+                const cgrb_unit_t *u = units + unit;
+                const MergedGlobal mg{times_bkg + u->bkg_off, times_src + u->src_off, pha_bkg + u->bkg_off,
+                                      pha_src + u->src_off, pl.nA, pl.nB};
+                const int64_t g0 = d0 - l0;
+                for (int k = tid; k < n_rare; k += NT) {
+                    const int e = sm.rare[k];
+                    int keep = dt_keep_local(T, P, l0 + e, g0);
+                    if (keep == 2)
+                        keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
+                    if (keep)
+                        atomicOr(&sm.rarekeep[e >> 5], 1u << (e & 31));
+                }
+                consumer_sync();
+#pragma unroll
+                for (int r = 0; r < MD_R; r++)
+                    keep_bits |= ((sm.rarekeep[r * NW + wid] >> lane) & 1u) << r;
+            }
+        } else {
+            // physical mode: a unit already flagged for the serial fix-up needs no more work here
+            const bool flagged = ((*(volatile uint32_t *)&counts[unit].status) & CGRB_ST_DEADTIME_CHAIN) != 0;
+            const EventArrays ev{T, P};
+#pragma unroll
+            for (int r = 0; r < MD_R; r++) {
+                const int e = r * NT + tid;
+                int keep = 0;
+                if (e < nt) {
+                    // no synchronisation point inside the tile's halo (256 events closer than the longest
+                    // window: never at GBM rates): the unit goes to the serial fix-up kernel
+                    keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), pl.has0 != 0, md);
+                    if (keep == 2) {
+                        atomicOr(&counts[unit].status, CGRB_ST_DEADTIME_CHAIN);
                         keep = 0;
                     }
                 }
                 keep_bits |= (unsigned)keep << r;
             }
         }
-        __syncthreads();
-        const int n_rare = sm.n_rare;
-        if (n_rare > 0) {
-            const cgrb_unit_t *u = units + unit;
-            const MergedGlobal mg{times_bkg + u->bkg_off, times_src + u->src_off, pha_bkg + u->bkg_off,
-                                  pha_src + u->src_off, sm.plan.nA, sm.plan.nB};
-            const int64_t g0 = d0 - l0;
-            for (int k = tid; k < n_rare; k += NT) {
-                const int e = sm.rare[k];
-                int keep = dt_keep_local(T, P, l0 + e, g0);
-                if (keep == 2)
-                    keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
-                if (keep)
-                    atomicOr(&sm.rarekeep[e >> 5], 1u << (e & 31));
-            }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < MD_R; r++)
-                keep_bits |= ((sm.rarekeep[r * NW + wid] >> lane) & 1u) << r;
-        }
-    } else {
-        // physical mode: a unit already flagged for the serial fix-up needs no more work here
-        const bool flagged = ((*(volatile uint32_t *)&counts[unit].status) & CGRB_ST_DEADTIME_CHAIN) != 0;
-        const EventArrays ev{T, P};
+        // survivors per (round, warp); this lane's rank inside its group, 8 bits per round
+        unsigned long long ranks = 0ull;
 #pragma unroll
         for (int r = 0; r < MD_R; r++) {
-            const int e = r * NT + tid;
-            int keep = 0;
-            if (e < nt) {
-                // no synchronisation point inside the tile's halo (256 events closer than the longest
-                // window: never at GBM rates): the unit goes to the serial fix-up kernel
-                keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), sm.plan.has0 != 0, md);
-                if (keep == 2) {
-                    atomicOr(&counts[unit].status, CGRB_ST_DEADTIME_CHAIN);
-                    keep = 0;
-                }
-            }
-            keep_bits |= (unsigned)keep << r;
+            const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
+            ranks |= (unsigned long long)__popc(bal & ((1u << lane) - 1u)) << (8 * r);
+            if (lane == 0)
+                sm.cnt[r * NW + wid] = __popc(bal);
         }
-    }
-    // survivors per (round, warp); this lane's rank inside its group, 8 bits per round
-    unsigned long long ranks = 0ull;
-#pragma unroll
-    for (int r = 0; r < MD_R; r++) {
-        const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
-        ranks |= (unsigned long long)__popc(bal & ((1u << lane) - 1u)) << (8 * r);
-        if (lane == 0)
-            sm.cnt[r * NW + wid] = __popc(bal);
-    }
-    __syncthreads();
+        consumer_sync();
 
-    // ---- 3. output offset: warp 0 scans the 64 group counts, then looks back over the unit's earlier tiles ----
-    if (wid == 0) {
-        int c0 = sm.cnt[2 * lane], c1 = sm.cnt[2 * lane + 1];
-        int incl = warp_incl_scan_i(c0 + c1, lane);
-        const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
-        sm.cnt[2 * lane] = incl - c0 - c1;
-        sm.cnt[2 * lane + 1] = incl - c1;
-        const long long excl = lookback_exclusive(tile_state, sm.plan.w, sm.plan.wb, cnt_tile, lane, &failed);
-        if (lane == 0) {
-            sm.excl = excl;
-            if (sm.plan.w == sm.plan.wb)
-                counts[unit].n_total = sm.plan.nA + sm.plan.nB;
-            if (sm.plan.last)
-                counts[unit].n_kept = excl + cnt_tile;        // the last live tile of the unit
+        // ---- 3. output offset: warp 0 scans the 64 group counts, then looks back over the unit's earlier tiles ----
+        if (wid == 0) {
+            int c0 = sm.cnt[2 * lane], c1 = sm.cnt[2 * lane + 1];
+            int incl = warp_incl_scan_i(c0 + c1, lane);
+            const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
+            sm.cnt[2 * lane] = incl - c0 - c1;
+            sm.cnt[2 * lane + 1] = incl - c1;
+            const long long excl = lookback_exclusive(tile_state, pl.w, pl.wb, cnt_tile, lane, &failed);
+            if (lane == 0) {
+                sm.excl = excl;
+                if (pl.w == pl.wb)
+                    counts[unit].n_total = pl.nA + pl.nB;
+                if (pl.last)
+                    counts[unit].n_kept = excl + cnt_tile;        // the last live tile of the unit
+            }
         }
-    }
-    if (failed)
-        atomicOr(&counts[unit].status, CGRB_ST_INTERNAL);
-    __syncthreads();
-    const int64_t out0 = units[unit].tot_off + sm.excl;
-    double *ot = times_out + out0;
-    uint8_t *op = pha_out + out0;
+        if (failed)
+            atomicOr(&counts[unit].status, CGRB_ST_INTERNAL);
+        consumer_sync();
+        const int64_t out0 = units[unit].tot_off + sm.excl;
+        double *ot = times_out + out0;
+        uint8_t *op = pha_out + out0;
 #pragma unroll
-    for (int r = 0; r < MD_R; r++) {
-        if ((keep_bits >> r) & 1u) {
-            const int rank = sm.cnt[r * NW + wid] + (int)((ranks >> (8 * r)) & 0xffull);
-            const int li = l0 + r * NT + tid;
-            ot[rank] = T[li];
-            op[rank] = P[li];
+        for (int r = 0; r < MD_R; r++) {
+            if ((keep_bits >> r) & 1u) {
+                const int rank = sm.cnt[r * NW + wid] + (int)((ranks >> (8 * r)) & 0xffull);
+                const int li = l0 + r * NT + tid;
+                ot[rank] = T[li];
+                op[rank] = P[li];
+            }
         }
+        consumer_sync();            // every consumer is done with the stage and with the tile's private tables
+        if (tid == 0)
+            mbar_arrive(&sm.empty[s]);
     }
 }
 
