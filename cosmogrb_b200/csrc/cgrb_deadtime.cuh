@@ -472,14 +472,30 @@ __device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, 
     return ti > t_end ? 1 : 0;
 }
 
-// merge-path splits of every tile, one thread per tile: the ~23 dependent probes of each search are
-// hidden by the other tiles' searches instead of stalling a whole CTA at its first barrier.
-// splits[2w] = split at the tile's halo start, splits[2w+1] = split at the tile start.
-__global__ void __launch_bounds__(NT) k_merge_splits(const cgrb_unit_t *__restrict__ units,
-                                                     const cgrb_work_t *__restrict__ work, int64_t n_work,
-                                                     const double *__restrict__ times_bkg,
-                                                     const double *__restrict__ times_src,
-                                                     int64_t *__restrict__ splits, const cgrb_counts_t *counts)
+// Per-tile records of the one-pass kernel, one thread per tile: the ~23 dependent probes of each merge-path
+// search are hidden by the other tiles' searches, and the persistent kernel's producer warps get everything they
+// need about a tile from ONE 64-byte record (ticket -> record -> staging is the whole dependence chain).
+struct MdTile {
+    int64_t a_off, b_off;       // first staged event (halo start) in the flat background / source arrays
+    int64_t wb;                 // first tile of the unit (look-back bound)
+    int64_t d0;                 // merged rank of the tile's first event
+    int32_t na, nb;             // staged events of each list: halo + tile
+    int32_t nt;                 // the tile's own events
+    int32_t unit;
+    uint32_t flags;             // MDT_*
+    int32_t pad[3];
+};
+static_assert(sizeof(MdTile) == 64, "MdTile is one 64-byte record");
+#define MDT_LIVE 1u
+#define MDT_HAS0 2u             // the staged range starts at the unit's event 0
+#define MDT_LAST 4u             // the unit's last live tile: writes n_kept
+
+__global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict__ units,
+                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+                                                   const int64_t *__restrict__ unit_work_begin,
+                                                   const double *__restrict__ times_bkg,
+                                                   const double *__restrict__ times_src,
+                                                   MdTile *__restrict__ tiles, cgrb_counts_t *counts)
 {
     const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
     if (w >= n_work)
@@ -487,12 +503,36 @@ __global__ void __launch_bounds__(NT) k_merge_splits(const cgrb_unit_t *__restri
     const cgrb_work_t wk = work[w];
     const cgrb_unit_t *u = units + wk.unit;
     const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
-    if (wk.start >= nA + nB)
-        return;
-    const double *A = times_bkg + u->bkg_off;
-    const double *B = times_src + u->src_off;
-    splits[2 * w] = merge_split(A, nA, B, nB, max((int64_t)0, wk.start - MD_HALO));
-    splits[2 * w + 1] = merge_split(A, nA, B, nB, wk.start);
+    const int64_t total = nA + nB;
+    MdTile t;
+    t.wb = unit_work_begin[wk.unit];
+    t.d0 = wk.start;
+    t.unit = wk.unit;
+    t.flags = 0u;
+    t.a_off = t.b_off = 0;
+    t.na = t.nb = t.nt = 0;
+    t.pad[0] = t.pad[1] = t.pad[2] = 0;
+    if (w == t.wb) {
+        counts[wk.unit].n_total = total;
+        if (total == 0)
+            counts[wk.unit].n_kept = 0;     // no live tile will write it
+    }
+    if (wk.start < total) {
+        const double *A = times_bkg + u->bkg_off;
+        const double *B = times_src + u->src_off;
+        const int64_t d1 = min(wk.start + (int64_t)MD_TILE, total);
+        const int64_t g0 = max((int64_t)0, wk.start - MD_HALO);     // first merged rank held in shared memory
+        const int64_t i0 = merge_split(A, nA, B, nB, g0);
+        const int64_t i1 = (d1 == total) ? nA : merge_split(A, nA, B, nB, d1);
+        const int64_t j0 = g0 - i0;
+        t.a_off = u->bkg_off + i0;
+        t.b_off = u->src_off + j0;
+        t.na = (int32_t)(i1 - i0);
+        t.nb = (int32_t)((d1 - i1) - j0);
+        t.nt = (int32_t)(d1 - wk.start);
+        t.flags = MDT_LIVE | (g0 == 0 ? MDT_HAS0 : 0u) | (d1 == total ? MDT_LAST : 0u);
+    }
+    tiles[w] = t;
 }
 
 #define MD_PER (MD_N / NT)       // merged elements per thread in the serial merge (9)
@@ -561,20 +601,12 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
 #define MD_CTAS 4                // resident CTAs per SM (two staging buffers each: 47 KB of shared memory)
 #endif
 
-// everything the consumers need to know about a tile, worked out by the producer
+// everything the consumers need to know about a tile: its record and the staging layout chosen by the producer
 struct MdPlan {
-    int64_t w, wb, d0;
-    int64_t nA, nB;
-    int64_t i0, j0;             // first staged event of list A (background) / B (source)
-    int unit;
+    MdTile tile;
+    int64_t w;                  // the tile's ticket
     int live;                   // 1: a tile to process, 0: no more tiles
-    int na, nb;                 // staged events of list A / B: halo + tile
-    int l0, nt;                 // first local index and number of the tile's own events
-    int has0;                   // local index 0 is the unit's event 0
-    int last;                   // the unit's last live tile
     int ta, tb, qa, qb;         // staging offsets (doubles / bytes) of the two slices
-    BulkPlan ptA, ptB, ppA, ppB;
-    unsigned bulk_bytes;
 };
 
 struct MdStage {
@@ -643,7 +675,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                                                           const uint8_t *__restrict__ pha_src,
                                                           unsigned long long *tile_state,
                                                           unsigned long long *ticket_counter,
-                                                          const int64_t *__restrict__ splits,
+                                                          const MdTile *__restrict__ tiles,
                                                           double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
                                                           cgrb_counts_t *counts, const DtModel md)
 {
@@ -660,118 +692,96 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
 
     if (wid == NW) {
         // =============================== producer warp =========================================================
+        // The ticket of tile it is claimed when the consumers START tile it - 1 (stage released / first stage
+        // filled), never earlier: every CTA claims exactly one tile ahead, so tiles start in ticket order across the
+        // grid and a look-back never waits for a tile parked behind another CTA's backlog.
         for (int it = 0;; it++) {
             const int s = it & 1;
             MdStage &S = sm.st[s];
-            MdPlan pl{};
-            const double *gA = nullptr, *gB = nullptr;
-            const uint8_t *hA = nullptr, *hB = nullptr;
-            if (lane == 0) {
-                for (;;) {
-                    pl.w = (int64_t)atomicAdd(ticket_counter, 1ull);
-                    if (pl.w >= n_work)
-                        break;
-                    const cgrb_work_t wk = work[pl.w];
-                    const cgrb_unit_t *u = units + wk.unit;
-                    pl.unit = wk.unit;
-                    pl.nA = counts[wk.unit].n_bkg;
-                    pl.nB = counts[wk.unit].n_src;
-                    const int64_t total = pl.nA + pl.nB;
-                    pl.wb = unit_work_begin[wk.unit];
-                    pl.d0 = wk.start;
-                    if (pl.d0 >= total) {
-                        // a tile beyond the end of the merged list: nothing to merge, and no live tile follows it, so
-                        // nobody will look back at it (the last LIVE tile writes n_kept)
-                        if (pl.w == pl.wb) {
-                            counts[wk.unit].n_total = total;
-                            counts[wk.unit].n_kept = 0;
-                        }
-                        continue;
-                    }
-                    pl.live = 1;
-                    const int64_t d1 = min(pl.d0 + (int64_t)MD_TILE, total);
-                    const int64_t g0 = max((int64_t)0, pl.d0 - MD_HALO);    // first merged rank held in shared memory
-                    pl.l0 = (int)(pl.d0 - g0);
-                    pl.nt = (int)(d1 - pl.d0);
-                    pl.has0 = g0 == 0;
-                    pl.last = d1 == total;
-                    // d1 is either the next tile's start (same unit) or the end of the merged list
-                    const int64_t i1 = pl.last ? pl.nA : splits[2 * (pl.w + 1) + 1];
-                    pl.i0 = splits[2 * pl.w];
-                    pl.j0 = g0 - pl.i0;
-                    pl.na = (int)(i1 - pl.i0);
-                    pl.nb = (int)((d1 - i1) - pl.j0);
-                    // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]: shared and global
-                    // addresses agree mod 16
-                    gA = times_bkg + u->bkg_off + pl.i0;
-                    gB = times_src + u->src_off + pl.j0;
-                    hA = pha_bkg + u->bkg_off + pl.i0;
-                    hB = pha_src + u->src_off + pl.j0;
-                    pl.ta = (int)(((uintptr_t)gA >> 3) & 1u);
-                    pl.tb = ((pl.ta + pl.na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
-                    pl.qa = (int)((uintptr_t)hA & 15u);
-                    pl.qb = ((pl.qa + pl.na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
-                    pl.ptA = bulk_plan<8>(gA, pl.na);
-                    pl.ptB = bulk_plan<8>(gB, pl.nb);
-                    pl.ppA = bulk_plan<1>(hA, pl.na);
-                    pl.ppB = bulk_plan<1>(hB, pl.nb);
-                    pl.bulk_bytes = 8u * (unsigned)(pl.ptA.body + pl.ptB.body) + (unsigned)(pl.ppA.body + pl.ppB.body);
-                    break;
-                }
-            }
-            // the stage must have been released by the consumers of its previous tile
             bool ok = true;
             if (it >= 2)
                 ok = mbar_wait(&sm.empty[s], (unsigned)(((it >> 1) & 1) ^ 1));
-            if (lane == 0) {
-                if (!ok && pl.live)
-                    atomicOr(&counts[pl.unit].status, CGRB_ST_INTERNAL);
-                sm.plan[s] = pl;
+            else if (it == 1)
+                ok = mbar_wait(&sm.full[0], 0u);
+            // claim the next live tile (dead tiles -- beyond the end of a unit's merged list -- are skipped: nobody
+            // looks back at them); all lanes read the record (one 64-byte line, broadcast)
+            MdTile t;
+            int64_t w;
+            for (;;) {
+                unsigned long long tk = 0;
+                if (lane == 0)
+                    tk = atomicAdd(ticket_counter, 1ull);
+                w = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+                t.flags = 0u;
+                if (w >= n_work)
+                    break;
+                t = tiles[w];
+                if (t.flags & MDT_LIVE)
+                    break;
             }
-            __syncwarp();
-            const int live = sm.plan[s].live;
-            if (live) {
-                // heads and tails (< 16 bytes each) by plain loads: a time slice has at most one head and one tail
-                // element, a pha slice at most 15 + 15
-                const MdPlan &q = sm.plan[s];
-                const cgrb_unit_t *u = units + q.unit;
-                const double *xa = times_bkg + u->bkg_off + q.i0, *xb = times_src + u->src_off + q.j0;
-                const uint8_t *ya = pha_bkg + u->bkg_off + q.i0, *yb = pha_src + u->src_off + q.j0;
-#pragma unroll
-                for (int which = 0; which < 4; which++) {       // 0: t of A, 1: t of B, 2: p of A, 3: p of B
-                    const BulkPlan bp = which == 0 ? q.ptA : which == 1 ? q.ptB : which == 2 ? q.ppA : q.ppB;
-                    const int cnt = (which & 1) ? q.nb : q.na;
-                    const int tail0 = bp.head + bp.body, ntail = cnt - tail0;
-                    const int e = lane < bp.head ? lane : (lane - bp.head < ntail ? tail0 + (lane - bp.head) : -1);
-                    if (e >= 0) {
-                        if (which == 0)
-                            S.t[q.ta + e] = xa[e];
-                        else if (which == 1)
-                            S.t[q.tb + e] = xb[e];
-                        else if (which == 2)
-                            S.p[q.qa + e] = ya[e];
-                        else
-                            S.p[q.qb + e] = yb[e];
-                    }
+            const bool live = (t.flags & MDT_LIVE) != 0;
+            if (!live) {
+                if (lane == 0)
+                    sm.plan[s].live = 0;
+                mbar_arrive(&sm.full[s]);
+                return;
+            }
+            // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]: shared and global addresses agree
+            // mod 16
+            const double *gA = times_bkg + t.a_off, *gB = times_src + t.b_off;
+            const uint8_t *hA = pha_bkg + t.a_off, *hB = pha_src + t.b_off;
+            const int ta = (int)(((uintptr_t)gA >> 3) & 1u);
+            const int tb = ((ta + t.na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
+            const int qa = (int)((uintptr_t)hA & 15u);
+            const int qb = ((qa + t.na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
+            const BulkPlan ptA = bulk_plan<8>(gA, t.na), ptB = bulk_plan<8>(gB, t.nb);
+            const BulkPlan ppA = bulk_plan<1>(hA, t.na), ppB = bulk_plan<1>(hB, t.nb);
+            const unsigned bulk_bytes = 8u * (unsigned)(ptA.body + ptB.body) + (unsigned)(ppA.body + ppB.body);
+            if (lane == 0) {
+                if (!ok)
+                    atomicOr(&counts[t.unit].status, CGRB_ST_INTERNAL);
+                MdPlan &q = sm.plan[s];
+                q.tile = t;
+                q.w = w;
+                q.live = 1;
+                q.ta = ta;
+                q.tb = tb;
+                q.qa = qa;
+                q.qb = qb;
+                if (bulk_bytes) {
+                    mbar_arrive_expect_tx(&sm.full[s], bulk_bytes);
+                    if (ptA.body)
+                        bulk_issue(S.t + ta + ptA.head, gA + ptA.head, 8u * ptA.body, &sm.full[s]);
+                    if (ptB.body)
+                        bulk_issue(S.t + tb + ptB.head, gB + ptB.head, 8u * ptB.body, &sm.full[s]);
+                    if (ppA.body)
+                        bulk_issue(S.p + qa + ppA.head, hA + ppA.head, (unsigned)ppA.body, &sm.full[s]);
+                    if (ppB.body)
+                        bulk_issue(S.p + qb + ppB.head, hB + ppB.head, (unsigned)ppB.body, &sm.full[s]);
                 }
             }
-            if (lane == 0) {
-                if (pl.bulk_bytes) {
-                    mbar_arrive_expect_tx(&sm.full[s], pl.bulk_bytes);
-                    if (pl.ptA.body)
-                        bulk_issue(S.t + pl.ta + pl.ptA.head, gA + pl.ptA.head, 8u * pl.ptA.body, &sm.full[s]);
-                    if (pl.ptB.body)
-                        bulk_issue(S.t + pl.tb + pl.ptB.head, gB + pl.ptB.head, 8u * pl.ptB.body, &sm.full[s]);
-                    if (pl.ppA.body)
-                        bulk_issue(S.p + pl.qa + pl.ppA.head, hA + pl.ppA.head, (unsigned)pl.ppA.body, &sm.full[s]);
-                    if (pl.ppB.body)
-                        bulk_issue(S.p + pl.qb + pl.ppB.head, hB + pl.ppB.head, (unsigned)pl.ppB.body, &sm.full[s]);
-                } else
-                    mbar_arrive(&sm.full[s]);
-            } else
+            // heads and tails (< 16 bytes each) by plain loads: a time slice has at most one head and one tail
+            // element, a pha slice at most 15 + 15
+#pragma unroll
+            for (int which = 0; which < 4; which++) {       // 0: t of A, 1: t of B, 2: p of A, 3: p of B
+                const BulkPlan bp = which == 0 ? ptA : which == 1 ? ptB : which == 2 ? ppA : ppB;
+                const int cnt = (which & 1) ? t.nb : t.na;
+                const int tail0 = bp.head + bp.body, ntail = cnt - tail0;
+                const int l1 = lane - 1;        // lane 0 has already arrived on the barrier (expect_tx): it stores nothing
+                const int e = l1 < 0 ? -1 : l1 < bp.head ? l1 : (l1 - bp.head < ntail ? tail0 + (l1 - bp.head) : -1);
+                if (e >= 0) {
+                    if (which == 0)
+                        S.t[ta + e] = gA[e];
+                    else if (which == 1)
+                        S.t[tb + e] = gB[e];
+                    else if (which == 2)
+                        S.p[qa + e] = hA[e];
+                    else
+                        S.p[qb + e] = hB[e];
+                }
+            }
+            if (lane != 0 || !bulk_bytes)
                 mbar_arrive(&sm.full[s]);
-            if (!live)
-                return;
         }
     }
 
@@ -783,10 +793,12 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
         if (!pl.live)
             return;
         MdStage &S = sm.st[s];
-        const int na = pl.na, nb = pl.nb, n = na + nb;      // n = d1 - g0 <= MD_N
-        const int l0 = pl.l0, nt = pl.nt;
+        const int na = pl.tile.na, nb = pl.tile.nb, n = na + nb;      // n = d1 - g0 <= MD_N
+        const int64_t d0 = pl.tile.d0;
+        const int l0 = (int)min(d0, (int64_t)MD_HALO), nt = pl.tile.nt;
         const int ta = pl.ta, tb = pl.tb, qa = pl.qa, qb = pl.qb;
-        const int unit = pl.unit;
+        const int unit = pl.tile.unit;
+        const bool has0 = (pl.tile.flags & MDT_HAS0) != 0;
         if (tid < MD_TILE / 32)
             sm.rarekeep[tid] = 0u;
         if (tid == 0)
@@ -894,9 +906,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
 
         // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
         unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
-        const int64_t d0 = pl.d0;
         if (MODE == 0) {
-            const bool has0 = pl.has0 != 0;
 #pragma unroll
             for (int r = 0; r < MD_PER; r++) {
                 const int li = r * NT + tid;
@@ -956,7 +966,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
             if (n_rare > 0) {
                 const cgrb_unit_t *u = units + unit;
                 const MergedGlobal mg{times_bkg + u->bkg_off, times_src + u->src_off, pha_bkg + u->bkg_off,
-                                      pha_src + u->src_off, pl.nA, pl.nB};
+                                      pha_src + u->src_off, counts[unit].n_bkg, counts[unit].n_src};
                 const int64_t g0 = d0 - l0;
                 for (int k = tid; k < n_rare; k += NT) {
                     const int e = sm.rare[k];
@@ -982,7 +992,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                 if (e < nt) {
                     // no synchronisation point inside the tile's halo (256 events closer than the longest
                     // window: never at GBM rates): the unit goes to the serial fix-up kernel
-                    keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), pl.has0 != 0, md);
+                    keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), has0, md);
                     if (keep == 2) {
                         atomicOr(&counts[unit].status, CGRB_ST_DEADTIME_CHAIN);
                         keep = 0;
@@ -1009,12 +1019,10 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
             const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
             sm.cnt[2 * lane] = incl - c0 - c1;
             sm.cnt[2 * lane + 1] = incl - c1;
-            const long long excl = lookback_exclusive(tile_state, pl.w, pl.wb, cnt_tile, lane, &failed);
+            const long long excl = lookback_exclusive(tile_state, pl.w, pl.tile.wb, cnt_tile, lane, &failed);
             if (lane == 0) {
                 sm.excl = excl;
-                if (pl.w == pl.wb)
-                    counts[unit].n_total = pl.nA + pl.nB;
-                if (pl.last)
+                if (pl.tile.flags & MDT_LAST)
                     counts[unit].n_kept = excl + cnt_tile;        // the last live tile of the unit
             }
         }

@@ -11,7 +11,7 @@
 //   cgrb_thinning.cuh        k_gap_prefix, k_seg_scan, k_source_thin, k_source_gather, k_background
 //   cgrb_fold.cuh            guided channel search, guide staging (cp.async.bulk), k_digitize
 //   cgrb_energy_kernels.cuh  k_sample_energy, k_energy_rows, k_sample_energy_env
-//   cgrb_deadtime.cuh        k_combine, k_deadtime_count/write, k_merge_splits, k_merge_deadtime
+//   cgrb_deadtime.cuh        k_combine, k_deadtime_count/write, k_merge_plan, k_merge_deadtime
 //   cgrb_trigger.cuh         k_trig_bin, k_trig_eval
 #include <cuda_runtime.h>
 #include <limits.h>
@@ -518,8 +518,8 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
     return check_launch("cgrb_gbm_dead_time");
 }
 
-// tile states [n_work], ticket counter + pad [2], merge-path splits [2 n_work]  (8 bytes each)
-int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 24 * (n_work > 0 ? n_work : 0) + 16; }
+// tile states [n_work] (8 bytes each), ticket counter + pad (64 bytes), tile records [n_work] (64 bytes each)
+int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 72 * (n_work > 0 ? n_work : 0) + 128; }
 
 int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
                          const int64_t *d_unit_work_begin, const double *d_times_bkg, const uint8_t *d_pha_bkg,
@@ -539,9 +539,9 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
     if (e != cudaSuccess)
         return fail(CGRB_E_CUDA, "cgrb_merge_dead_time: memset: %s", cudaGetErrorString(e));
     unsigned long long *ticket = (unsigned long long *)d_workspace + n_work;
-    int64_t *splits = (int64_t *)d_workspace + n_work + 2;
-    LAUNCH("k_merge_splits", s, k_merge_splits<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
-        d_units, d_work, n_work, d_times_bkg, d_times_src, splits, d_counts));
+    MdTile *tiles = (MdTile *)((char *)d_workspace + ((8 * (size_t)n_work + 16 + 63) / 64) * 64);
+    LAUNCH("k_merge_plan", s, k_merge_plan<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
+        d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_times_src, tiles, d_counts));
     // persistent CTAs: MD_CTAS per SM, tiles claimed from the ticket counter
     static int n_sm = 0;
     if (!n_sm) {
@@ -554,11 +554,11 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
     if (!physical) {
         LAUNCH("k_merge_deadtime", s, k_merge_deadtime<0><<<md_grid, MD_NT_ALL, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
-            (unsigned long long *)d_workspace, ticket, splits, d_times_out, d_pha_out, d_counts, md));
+            (unsigned long long *)d_workspace, ticket, tiles, d_times_out, d_pha_out, d_counts, md));
     } else {
         LAUNCH("k_merge_deadtime_phys", s, k_merge_deadtime<1><<<md_grid, MD_NT_ALL, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
-            (unsigned long long *)d_workspace, ticket, splits, d_times_out, d_pha_out, d_counts, md));
+            (unsigned long long *)d_workspace, ticket, tiles, d_times_out, d_pha_out, d_counts, md));
         LAUNCH("k_deadtime_phys_fixup", s, k_deadtime_phys_fixup<<<(n_units * 32 + 127) / 128, 128, 0, s>>>(
             d_units, n_units, nullptr, nullptr, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src, d_times_out,
             d_pha_out, nullptr, d_counts, md));
