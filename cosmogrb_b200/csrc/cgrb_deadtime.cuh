@@ -595,6 +595,13 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
     }
 }
 
+#ifdef MD_TIMING
+#define MDT_DECL(n) long long tacc[n] = {0}; long long tlast = clock64(); int ttiles = 0;
+#define MDT_MARK(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define MDT_DECL(n)
+#define MDT_MARK(i)
+#endif
 #define MD_SPARSE 64             // a tile whose minority list has at most this many events is merged by insertion
 #define MD_NT_ALL (NT + 32)      // consumers + the producer warp
 #ifndef MD_CTAS
@@ -695,14 +702,17 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
         // The ticket of tile it is claimed when the consumers START tile it - 1 (stage released / first stage
         // filled), never earlier: every CTA claims exactly one tile ahead, so tiles start in ticket order across the
         // grid and a look-back never waits for a tile parked behind another CTA's backlog.
+        MDT_DECL(4)
         for (int it = 0;; it++) {
             const int s = it & 1;
             MdStage &S = sm.st[s];
             bool ok = true;
+            MDT_MARK(3);
             if (it >= 2)
                 ok = mbar_wait(&sm.empty[s], (unsigned)(((it >> 1) & 1) ^ 1));
             else if (it == 1)
                 ok = mbar_wait(&sm.full[0], 0u);
+            MDT_MARK(0);
             // claim the next live tile (dead tiles -- beyond the end of a unit's merged list -- are skipped: nobody
             // looks back at them); all lanes read the record (one 64-byte line, broadcast)
             MdTile t;
@@ -720,10 +730,16 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                     break;
             }
             const bool live = (t.flags & MDT_LIVE) != 0;
+            MDT_MARK(1);
             if (!live) {
                 if (lane == 0)
                     sm.plan[s].live = 0;
                 mbar_arrive(&sm.full[s]);
+#ifdef MD_TIMING
+                if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 300))
+                    printf("MDT producer cta %d tiles %d: wait_empty %lld claim %lld stage %lld other %lld\n", blockIdx.x, it,
+                           tacc[0], tacc[1], tacc[2], tacc[3]);
+#endif
                 return;
             }
             // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]: shared and global addresses agree
@@ -782,16 +798,26 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
             }
             if (lane != 0 || !bulk_bytes)
                 mbar_arrive(&sm.full[s]);
+            MDT_MARK(2);
         }
     }
 
     // =================================== consumer warps ===========================================================
+    MDT_DECL(8)
     for (int it = 0;; it++) {
         const int s = it & 1;
+        MDT_MARK(7);
         bool failed = !mbar_wait(&sm.full[s], (unsigned)((it >> 1) & 1));
+        MDT_MARK(0);
         const MdPlan &pl = sm.plan[s];
-        if (!pl.live)
+        if (!pl.live) {
+#ifdef MD_TIMING
+            if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 300))
+                printf("MDT consumer cta %d tiles %d: wait_full %lld merge %lld chain %lld keep %lld count %lld lookback %lld write %lld other %lld\n",
+                       blockIdx.x, it, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
+#endif
             return;
+        }
         MdStage &S = sm.st[s];
         const int na = pl.tile.na, nb = pl.tile.nb, n = na + nb;      // n = d1 - g0 <= MD_N
         const int64_t d0 = pl.tile.d0;
@@ -903,6 +929,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                 }
         }
         consumer_sync();        // merged order in place; rarekeep / n_rare cleared
+        MDT_MARK(1);
 
         // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
         unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
@@ -916,6 +943,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                     sm.chain[r * NW + wid] = bal;
             }
             consumer_sync();
+            MDT_MARK(2);
             // nearest chain element before each word (exclusive prefix maximum over the 72 words, per warp in
             // registers: lane l of chunk c holds the value for word 32 c + l); "none": the halo's first event decides
             // (index 0; a unit's event 0 is itself a chain element, so with has0 "none" only happens to event 0)
@@ -1001,6 +1029,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                 keep_bits |= (unsigned)keep << r;
             }
         }
+        MDT_MARK(3);
         // survivors per (round, warp); this lane's rank inside its group, 8 bits per round
         unsigned long long ranks = 0ull;
 #pragma unroll
@@ -1011,6 +1040,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                 sm.cnt[r * NW + wid] = __popc(bal);
         }
         consumer_sync();
+        MDT_MARK(4);
 
         // ---- 3. output offset: warp 0 scans the 64 group counts, then looks back over the unit's earlier tiles ----
         if (wid == 0) {
@@ -1029,6 +1059,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
         if (failed)
             atomicOr(&counts[unit].status, CGRB_ST_INTERNAL);
         consumer_sync();
+        MDT_MARK(5);
         const int64_t out0 = units[unit].tot_off + sm.excl;
         double *ot = times_out + out0;
         uint8_t *op = pha_out + out0;
@@ -1042,6 +1073,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
             }
         }
         consumer_sync();            // every consumer is done with the stage and with the tile's private tables
+        MDT_MARK(6);
         if (tid == 0)
             mbar_arrive(&sm.empty[s]);
     }
