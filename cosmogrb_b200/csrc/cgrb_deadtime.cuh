@@ -603,18 +603,9 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
 #define MDT_MARK(i)
 #endif
 #define MD_SPARSE 64             // a tile whose minority list has at most this many events is merged by insertion
-#define MD_NT_ALL (NT + 32)      // consumers + the producer warp
 #ifndef MD_CTAS
-#define MD_CTAS 4                // resident CTAs per SM (two staging buffers each: 47 KB of shared memory)
+#define MD_CTAS 6                // resident CTAs per SM the kernel is compiled for (register budget; 26 KB of shared memory each)
 #endif
-
-// everything the consumers need to know about a tile: its record and the staging layout chosen by the producer
-struct MdPlan {
-    MdTile tile;
-    int64_t w;                  // the tile's ticket
-    int live;                   // 1: a tile to process, 0: no more tiles
-    int ta, tb, qa, qb;         // staging offsets (doubles / bytes) of the two slices
-};
 
 struct MdStage {
     alignas(16) double t[MD_N + 4];         // slack: the alignment shift of up to two staged slices
@@ -622,8 +613,7 @@ struct MdStage {
 };
 
 struct MdSmem {
-    MdStage st[2];
-    MdPlan plan[2];
+    MdStage st;
     uint32_t chain[MD_WORDS];               // bit li: local event li is a chain element (overflow channel / event 0)
     uint32_t rarekeep[MD_TILE / 32];        // keep flags of the tile elements resolved by the chain walk
     uint16_t rare[MD_TILE];                 // tile elements that need the chain walk
@@ -632,8 +622,8 @@ struct MdSmem {
     int cnt[MD_R * NW];                     // survivors per (round, warp), then their exclusive prefix
     int n_rare;
     long long excl;
-    alignas(8) uint64_t full[2];            // stage filled (producer lanes + bulk bytes)
-    alignas(8) uint64_t empty[2];           // stage released by the consumers
+    long long ticket;
+    alignas(8) uint64_t full;               // the staged slices have landed
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t *b, unsigned count)
@@ -650,16 +640,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, unsigned byte
                  "r"(bytes)
                  : "memory");
 }
-// barrier among the NT consumer threads only (the producer warp never joins it)
-__device__ __forceinline__ void consumer_sync()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-}
-
-// Persistent, software-pipelined: MD_CTAS CTAs per SM, each with a PRODUCER warp that claims the next tile from the
-// ticket counter (see lookback_exclusive), works out its plan and stages its slices of the two component lists
-// (+ MD_HALO events of look-back) into one of two buffers -- the aligned middle by the bulk-async engine, the
-// < 16-byte heads and tails by plain loads -- while the eight CONSUMER warps resolve the previous tile:
+// One CTA per tile of MD_TILE merged events; the tile index comes from a ticket counter (see lookback_exclusive)
+// and everything about the tile from ONE 64-byte record written by k_merge_plan, so the dependence chain in front
+// of the data is ticket -> record -> staging.  Many small CTAs per SM (MD_CTAS, 26 KB of shared memory each) overlap
+// one tile's latencies -- staging, barriers, the look-back -- with the other tiles' work.  (A persistent variant
+// with a producer warp and a two-stage ring was built and measured: CTAs that hold claimed tiles behind the one
+// they are processing turn the look-back into a convoy, 56-89 % of the time was spent waiting in it)
+//  0. staging: the aligned middle of each list slice (+ MD_HALO events of look-back) by the bulk-async engine, the
+//     < 16-byte heads and tails by plain loads.
 //  1. merge.  A tile fed by one list only -- nearly every tile of a background-dominated unit -- is already in
 //     merged order.  A tile with a sparse minority (<= MD_SPARSE events of one list: the background under a bright
 //     burst, the burst's photons in the background) is merged by insertion: every minority event finds its place
@@ -673,7 +661,7 @@ __device__ __forceinline__ void consumer_sync()
 //     (dt_keep_local, or the global accessor when the chain leaves the halo).
 //  3. survivors are appended at the unit's output offset from the decoupled look-back.
 template <int MODE>
-__global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
+__global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
                                                           const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                           const int64_t *__restrict__ unit_work_begin,
                                                           const double *__restrict__ times_bkg,
@@ -688,147 +676,75 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
 {
     __shared__ MdSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    MDT_DECL(8)
     if (tid == 0) {
-        mbar_init(&sm.full[0], 32);
-        mbar_init(&sm.full[1], 32);
-        mbar_init(&sm.empty[0], 1);
-        mbar_init(&sm.empty[1], 1);
+        sm.ticket = (long long)atomicAdd(ticket_counter, 1ull);
+        sm.n_rare = 0;
+        mbar_init(&sm.full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < MD_TILE / 32)
+        sm.rarekeep[tid] = 0u;
     __syncthreads();
-
-    if (wid == NW) {
-        // =============================== producer warp =========================================================
-        // The ticket of tile it is claimed when the consumers START tile it - 1 (stage released / first stage
-        // filled), never earlier: every CTA claims exactly one tile ahead, so tiles start in ticket order across the
-        // grid and a look-back never waits for a tile parked behind another CTA's backlog.
-        MDT_DECL(4)
-        for (int it = 0;; it++) {
-            const int s = it & 1;
-            MdStage &S = sm.st[s];
-            bool ok = true;
-            MDT_MARK(3);
-            if (it >= 2)
-                ok = mbar_wait(&sm.empty[s], (unsigned)(((it >> 1) & 1) ^ 1));
-            else if (it == 1)
-                ok = mbar_wait(&sm.full[0], 0u);
-            MDT_MARK(0);
-            // claim the next live tile (dead tiles -- beyond the end of a unit's merged list -- are skipped: nobody
-            // looks back at them); all lanes read the record (one 64-byte line, broadcast)
-            MdTile t;
-            int64_t w;
-            for (;;) {
-                unsigned long long tk = 0;
-                if (lane == 0)
-                    tk = atomicAdd(ticket_counter, 1ull);
-                w = (int64_t)__shfl_sync(0xffffffffu, tk, 0);
-                t.flags = 0u;
-                if (w >= n_work)
-                    break;
-                t = tiles[w];
-                if (t.flags & MDT_LIVE)
-                    break;
-            }
-            const bool live = (t.flags & MDT_LIVE) != 0;
-            MDT_MARK(1);
-            if (!live) {
-                if (lane == 0)
-                    sm.plan[s].live = 0;
-                mbar_arrive(&sm.full[s]);
-#ifdef MD_TIMING
-                if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == 300))
-                    printf("MDT producer cta %d tiles %d: wait_empty %lld claim %lld stage %lld other %lld\n", blockIdx.x, it,
-                           tacc[0], tacc[1], tacc[2], tacc[3]);
-#endif
-                return;
-            }
-            // slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]: shared and global addresses agree
-            // mod 16
-            const double *gA = times_bkg + t.a_off, *gB = times_src + t.b_off;
-            const uint8_t *hA = pha_bkg + t.a_off, *hB = pha_src + t.b_off;
-            const int ta = (int)(((uintptr_t)gA >> 3) & 1u);
-            const int tb = ((ta + t.na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
-            const int qa = (int)((uintptr_t)hA & 15u);
-            const int qb = ((qa + t.na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
-            const BulkPlan ptA = bulk_plan<8>(gA, t.na), ptB = bulk_plan<8>(gB, t.nb);
-            const BulkPlan ppA = bulk_plan<1>(hA, t.na), ppB = bulk_plan<1>(hB, t.nb);
-            const unsigned bulk_bytes = 8u * (unsigned)(ptA.body + ptB.body) + (unsigned)(ppA.body + ppB.body);
-            if (lane == 0) {
-                if (!ok)
-                    atomicOr(&counts[t.unit].status, CGRB_ST_INTERNAL);
-                MdPlan &q = sm.plan[s];
-                q.tile = t;
-                q.w = w;
-                q.live = 1;
-                q.ta = ta;
-                q.tb = tb;
-                q.qa = qa;
-                q.qb = qb;
-                if (bulk_bytes) {
-                    mbar_arrive_expect_tx(&sm.full[s], bulk_bytes);
-                    if (ptA.body)
-                        bulk_issue(S.t + ta + ptA.head, gA + ptA.head, 8u * ptA.body, &sm.full[s]);
-                    if (ptB.body)
-                        bulk_issue(S.t + tb + ptB.head, gB + ptB.head, 8u * ptB.body, &sm.full[s]);
-                    if (ppA.body)
-                        bulk_issue(S.p + qa + ppA.head, hA + ppA.head, (unsigned)ppA.body, &sm.full[s]);
-                    if (ppB.body)
-                        bulk_issue(S.p + qb + ppB.head, hB + ppB.head, (unsigned)ppB.body, &sm.full[s]);
-                }
-            }
-            // heads and tails (< 16 bytes each) by plain loads: a time slice has at most one head and one tail
-            // element, a pha slice at most 15 + 15
-#pragma unroll
-            for (int which = 0; which < 4; which++) {       // 0: t of A, 1: t of B, 2: p of A, 3: p of B
-                const BulkPlan bp = which == 0 ? ptA : which == 1 ? ptB : which == 2 ? ppA : ppB;
-                const int cnt = (which & 1) ? t.nb : t.na;
-                const int tail0 = bp.head + bp.body, ntail = cnt - tail0;
-                const int l1 = lane - 1;        // lane 0 has already arrived on the barrier (expect_tx): it stores nothing
-                const int e = l1 < 0 ? -1 : l1 < bp.head ? l1 : (l1 - bp.head < ntail ? tail0 + (l1 - bp.head) : -1);
-                if (e >= 0) {
-                    if (which == 0)
-                        S.t[ta + e] = gA[e];
-                    else if (which == 1)
-                        S.t[tb + e] = gB[e];
-                    else if (which == 2)
-                        S.p[qa + e] = hA[e];
-                    else
-                        S.p[qb + e] = hB[e];
-                }
-            }
-            if (lane != 0 || !bulk_bytes)
-                mbar_arrive(&sm.full[s]);
-            MDT_MARK(2);
+    const int64_t w = sm.ticket;
+    if (w >= n_work)
+        return;
+    const MdTile tile = tiles[w];
+    if (!(tile.flags & MDT_LIVE))
+        return;                 // beyond the end of the unit's merged list: nobody looks back at it
+    {
+        MdStage &S = sm.st;
+        const int na = tile.na, nb = tile.nb, n = na + nb;      // n = d1 - g0 <= MD_N
+        const int64_t d0 = tile.d0;
+        const int l0 = (int)min(d0, (int64_t)MD_HALO), nt = tile.nt;
+        const int unit = tile.unit;
+        const bool has0 = (tile.flags & MDT_HAS0) != 0;
+        // ---- 0. staging: slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]; shared and global
+        // addresses agree mod 16
+        const double *gA = times_bkg + tile.a_off, *gB = times_src + tile.b_off;
+        const uint8_t *hA = pha_bkg + tile.a_off, *hB = pha_src + tile.b_off;
+        const int ta = (int)(((uintptr_t)gA >> 3) & 1u);
+        const int tb = ((ta + na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
+        const int qa = (int)((uintptr_t)hA & 15u);
+        const int qb = ((qa + na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
+        const BulkPlan ptA = bulk_plan<8>(gA, na), ptB = bulk_plan<8>(gB, nb);
+        const BulkPlan ppA = bulk_plan<1>(hA, na), ppB = bulk_plan<1>(hB, nb);
+        const unsigned bulk_bytes = 8u * (unsigned)(ptA.body + ptB.body) + (unsigned)(ppA.body + ppB.body);
+        if (tid == 0 && bulk_bytes) {
+            mbar_arrive_expect_tx(&sm.full, bulk_bytes);
+            if (ptA.body)
+                bulk_issue(S.t + ta + ptA.head, gA + ptA.head, 8u * ptA.body, &sm.full);
+            if (ptB.body)
+                bulk_issue(S.t + tb + ptB.head, gB + ptB.head, 8u * ptB.body, &sm.full);
+            if (ppA.body)
+                bulk_issue(S.p + qa + ppA.head, hA + ppA.head, (unsigned)ppA.body, &sm.full);
+            if (ppB.body)
+                bulk_issue(S.p + qb + ppB.head, hB + ppB.head, (unsigned)ppB.body, &sm.full);
         }
-    }
-
-    // =================================== consumer warps ===========================================================
-    MDT_DECL(8)
-    for (int it = 0;; it++) {
-        const int s = it & 1;
-        MDT_MARK(7);
-        bool failed = !mbar_wait(&sm.full[s], (unsigned)((it >> 1) & 1));
+        if (wid >= 1 && wid <= 4) {
+            // heads and tails (< 16 bytes each) by plain loads, one warp per slice: a time slice has at most one head
+            // and one tail element, a pha slice at most 15 + 15
+            const int which = wid - 1;                      // 0: t of A, 1: t of B, 2: p of A, 3: p of B
+            const BulkPlan bp = which == 0 ? ptA : which == 1 ? ptB : which == 2 ? ppA : ppB;
+            const int cnt = (which & 1) ? nb : na;
+            const int tail0 = bp.head + bp.body, ntail = cnt - tail0;
+            const int e = lane < bp.head ? lane : (lane - bp.head < ntail ? tail0 + (lane - bp.head) : -1);
+            if (e >= 0) {
+                if (which == 0)
+                    S.t[ta + e] = gA[e];
+                else if (which == 1)
+                    S.t[tb + e] = gB[e];
+                else if (which == 2)
+                    S.p[qa + e] = hA[e];
+                else
+                    S.p[qb + e] = hB[e];
+            }
+        }
+        bool failed = false;
+        if (bulk_bytes)
+            failed = !mbar_wait(&sm.full, 0u);
+        __syncthreads();
         MDT_MARK(0);
-        const MdPlan &pl = sm.plan[s];
-        if (!pl.live) {
-#ifdef MD_TIMING
-            if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 300))
-                printf("MDT consumer cta %d tiles %d: wait_full %lld merge %lld chain %lld keep %lld count %lld lookback %lld write %lld other %lld\n",
-                       blockIdx.x, it, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
-#endif
-            return;
-        }
-        MdStage &S = sm.st[s];
-        const int na = pl.tile.na, nb = pl.tile.nb, n = na + nb;      // n = d1 - g0 <= MD_N
-        const int64_t d0 = pl.tile.d0;
-        const int l0 = (int)min(d0, (int64_t)MD_HALO), nt = pl.tile.nt;
-        const int ta = pl.ta, tb = pl.tb, qa = pl.qa, qb = pl.qb;
-        const int unit = pl.tile.unit;
-        const bool has0 = (pl.tile.flags & MDT_HAS0) != 0;
-        if (tid < MD_TILE / 32)
-            sm.rarekeep[tid] = 0u;
-        if (tid == 0)
-            sm.n_rare = 0;
 
         const double *T = S.t;
         const uint8_t *P = S.p;
@@ -867,14 +783,19 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                 sm.ins[tid] = (uint16_t)lo;
                 mdest = lo + tid;
             }
-            consumer_sync();
+            __syncthreads();
             if (tid <= (nj + 31) / 32) {
-                int c = 0;                                  // minority events inserted before majority index 32 tid
-                while (c < nm && (int)sm.ins[c] < 32 * tid)
-                    c++;
+                int c = 0, hi = nm;                         // minority events inserted before majority index 32 tid
+                while (c < hi) {
+                    const int mid = (c + hi) >> 1;
+                    if ((int)sm.ins[mid] < 32 * tid)
+                        c = mid + 1;
+                    else
+                        hi = mid;
+                }
                 sm.cblk[tid] = (uint8_t)c;
             }
-            consumer_sync();
+            __syncthreads();
 #pragma unroll
             for (int r = 0; r < MD_PER; r++) {
                 const int k = r * NT + tid;
@@ -920,7 +841,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                     ib += take_a ? 0 : 1;
                 }
             }
-            consumer_sync();
+            __syncthreads();
 #pragma unroll
             for (int r = 0; r < MD_PER; r++)
                 if (q0 + r < n) {
@@ -928,7 +849,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                     S.p[q0 + r] = rp[r];
                 }
         }
-        consumer_sync();        // merged order in place; rarekeep / n_rare cleared
+        __syncthreads();        // merged order in place; rarekeep / n_rare cleared
         MDT_MARK(1);
 
         // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
@@ -942,7 +863,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                 if (lane == 0)
                     sm.chain[r * NW + wid] = bal;
             }
-            consumer_sync();
+            __syncthreads();
             MDT_MARK(2);
             // nearest chain element before each word (exclusive prefix maximum over the 72 words, per warp in
             // registers: lane l of chunk c holds the value for word 32 c + l); "none": the halo's first event decides
@@ -989,7 +910,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                     keep_bits |= (unsigned)keep << r;
                 }
             }
-            consumer_sync();
+            __syncthreads();
             const int n_rare = sm.n_rare;
             if (n_rare > 0) {
                 const cgrb_unit_t *u = units + unit;
@@ -1004,7 +925,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                     if (keep)
                         atomicOr(&sm.rarekeep[e >> 5], 1u << (e & 31));
                 }
-                consumer_sync();
+                __syncthreads();
 #pragma unroll
                 for (int r = 0; r < MD_R; r++)
                     keep_bits |= ((sm.rarekeep[r * NW + wid] >> lane) & 1u) << r;
@@ -1039,7 +960,7 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
             if (lane == 0)
                 sm.cnt[r * NW + wid] = __popc(bal);
         }
-        consumer_sync();
+        __syncthreads();
         MDT_MARK(4);
 
         // ---- 3. output offset: warp 0 scans the 64 group counts, then looks back over the unit's earlier tiles ----
@@ -1049,16 +970,16 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
             const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
             sm.cnt[2 * lane] = incl - c0 - c1;
             sm.cnt[2 * lane + 1] = incl - c1;
-            const long long excl = lookback_exclusive(tile_state, pl.w, pl.tile.wb, cnt_tile, lane, &failed);
+            const long long excl = lookback_exclusive(tile_state, w, tile.wb, cnt_tile, lane, &failed);
             if (lane == 0) {
                 sm.excl = excl;
-                if (pl.tile.flags & MDT_LAST)
+                if (tile.flags & MDT_LAST)
                     counts[unit].n_kept = excl + cnt_tile;        // the last live tile of the unit
             }
         }
         if (failed)
             atomicOr(&counts[unit].status, CGRB_ST_INTERNAL);
-        consumer_sync();
+        __syncthreads();
         MDT_MARK(5);
         const int64_t out0 = units[unit].tot_off + sm.excl;
         double *ot = times_out + out0;
@@ -1072,10 +993,12 @@ __global__ void __launch_bounds__(MD_NT_ALL, MD_CTAS) k_merge_deadtime(const cgr
                 op[rank] = P[li];
             }
         }
-        consumer_sync();            // every consumer is done with the stage and with the tile's private tables
         MDT_MARK(6);
-        if (tid == 0)
-            mbar_arrive(&sm.empty[s]);
+#ifdef MD_TIMING
+        if (tid == 0 && (w % 20000) == 777)
+            printf("MDT tile %lld: stage %lld merge %lld chain %lld keep %lld count %lld lookback %lld write %lld\n",
+                   (long long)w, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6]);
+#endif
     }
 }
 

@@ -542,21 +542,13 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
     MdTile *tiles = (MdTile *)((char *)d_workspace + ((8 * (size_t)n_work + 16 + 63) / 64) * 64);
     LAUNCH("k_merge_plan", s, k_merge_plan<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
         d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_times_src, tiles, d_counts));
-    // persistent CTAs: MD_CTAS per SM, tiles claimed from the ticket counter
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0)
-            n_sm = 148;
-    }
-    const unsigned md_grid = (unsigned)min((int64_t)n_sm * MD_CTAS, n_work);
+    const unsigned md_grid = (unsigned)n_work;      // one tile per CTA, tile index from the ticket counter
     if (!physical) {
-        LAUNCH("k_merge_deadtime", s, k_merge_deadtime<0><<<md_grid, MD_NT_ALL, 0, s>>>(
+        LAUNCH("k_merge_deadtime", s, k_merge_deadtime<0><<<md_grid, NT, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
             (unsigned long long *)d_workspace, ticket, tiles, d_times_out, d_pha_out, d_counts, md));
     } else {
-        LAUNCH("k_merge_deadtime_phys", s, k_merge_deadtime<1><<<md_grid, MD_NT_ALL, 0, s>>>(
+        LAUNCH("k_merge_deadtime_phys", s, k_merge_deadtime<1><<<md_grid, NT, 0, s>>>(
             d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
             (unsigned long long *)d_workspace, ticket, tiles, d_times_out, d_pha_out, d_counts, md));
         LAUNCH("k_deadtime_phys_fixup", s, k_deadtime_phys_fixup<<<(n_units * 32 + 127) / 128, 128, 0, s>>>(
