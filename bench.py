@@ -350,18 +350,25 @@ def run_gpu(args):
         buf_b = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
         peaks_live = {"fill_write_gbs": live_bw(lambda: buf_a.fill_(1), 1 << 30),
                       "copy_read_write_gbs": live_bw(lambda: buf_b.copy_(buf_a), 2 << 30)}
-        del buf_a, buf_b
+        # bare device->host yardstick of the e2e arm: ONE plain async copy of 1 GiB into pinned host memory, all
+        # ranks at the same time (at N > 1 the GPUs of a box share the host's PCIe / memory side)
+        pin = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+        sync_all()
+        peaks_live["d2h_pinned_gbs_per_gpu_all_ranks_concurrent"] = live_bw(lambda: pin.copy_(buf_a, non_blocking=True), 1 << 30, reps=3)
+        sync_all()
+        del buf_a, buf_b, pin
     except Exception as e:          # noqa: BLE001
         peaks_live = {"error": str(e)}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
     # DRAM bytes per launch measured by ncu (--set full) on this same workload, kept under profiles/
-    traffic, issue_frac = {}, {}
+    traffic, issue_frac, warp_inst, tj = {}, {}, {}, {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         traffic, issue_frac = tj.get("dram_bytes_per_launch", {}), tj.get("issue_slots_busy_frac", {})
+        warp_inst = tj.get("warp_inst_per_launch", {})
     except Exception:
         pass
 
@@ -374,9 +381,32 @@ def run_gpu(args):
                 "share_of_step": kern[name]["share"], "peak_source": peak_src,
                 "issue_slots_busy_frac_ncu": issue_frac.get(name, issue_frac.get(key))}
 
-    roofline = hbm_roofline(top)
-    roofline["note"] = ("dominant kernel of this source-dominated workload is fp64-issue bound, not HBM bound: "
-                        "its HBM fraction is small by construction; see profiles/ for issue utilisation")
+    def issue_roofline(name):
+        """The regime that binds an RNG / rejection kernel: warp instructions issued per second against the SMs'
+        issue slots (SMs x 4 schedulers x 1 instruction per clock x the SM clock sampled during the timed region).
+        The instruction count per launch is ncu's smsp__inst_executed.sum of the tracked capture of this same
+        workload (profiles/traffic.json); the duration is this run's live CUDA-event time of the kernel.  The
+        instruction count is the builder's choice, so `warp_inst_per_event` is the progress metric, `frac` how
+        busy the issue slots are."""
+        key = name.split("<")[0]
+        wi = warp_inst.get(name, warp_inst.get(key))
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = clk.get("sm_mhz") or clk.get("sm_max_mhz") or 1965.0
+        peak_i = sms * 4 * mhz * 1e6 / 1e9                 # G warp-instructions / s
+        ach = (wi / (kern[name]["ms_per_launch"] * 1e-3) / 1e9) if wi else None
+        nu = units_of.get(key, 0)
+        return {"kernel": name, "bound": "issue", "achieved": ach, "peak": peak_i, "unit": "Gwarp-inst/s",
+                "frac": (ach / peak_i) if ach else None, "traffic": traffic.get(name, traffic.get(key)),
+                "warp_inst_per_launch_ncu": wi, "warp_inst_per_event": (wi / nu) if (wi and nu) else None,
+                "ms_per_launch": kern[name]["ms_per_launch"], "share_of_step": kern[name]["share"],
+                "peak_source": f"{sms} SMs x 4 issue slots x {mhz:.0f} MHz (clock sampled in this run)",
+                "issue_slots_busy_frac_ncu": issue_frac.get(name, issue_frac.get(key)),
+                "hbm": {k: v for k, v in hbm_roofline(name).items() if k in ("achieved", "peak", "frac", "unit",
+                                                                           "algorithmic_bytes_per_launch", "peak_source")}}
+
+    ISSUE_BOUND = ("k_sample_energy_env", "k_source_thin", "k_gap_prefix", "k_sample_energy", "k_thin_nodes")
+    roofline = issue_roofline(top) if top.split("<")[0] in ISSUE_BOUND else hbm_roofline(top)
+    roofline_issue_kernels = [issue_roofline(n) for n in kern if n.split("<")[0] in ISSUE_BOUND and n != top]
     hbm_kernels = [hbm_roofline(n) for n in kern if n.split("<")[0] in ("k_background", "k_merge_deadtime", "k_combine",
                                                                            "k_deadtime_count", "k_deadtime_write",
                                                                            "k_source_gather")]
@@ -423,23 +453,30 @@ def run_gpu(args):
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
         dist.all_reduce(ev_e2e_t, op=dist.ReduceOp.SUM)
     e2e_value = float(ev_e2e_t.item()) / (float(ms_e2e.item()) * 1e-3)
+    # the e2e arm against its own roofline: bytes this rank copied device->host per second vs the bare-copy yardstick
+    e2e_d2h_gbs = (d2h / (float(ms_e2e.item()) * 1e-3) / 1e9) if d2h else 0.0
+    d2h_peak = peaks_live.get("d2h_pinned_gbs_per_gpu_all_ranks_concurrent")
 
-    # ---- population leg (BASELINE.json configs[3]: 1,000 GRBs x 14 detectors per GPU, weak scaling) -------
-    # GRBs/s through the public API, Universe.go(): unit records built on the host, events stay in HBM,
-    # only the per-unit counters come back (+ the NCCL event-count gather across ranks).
+    # ---- population leg (BASELINE.json configs[4]: 100,000 GRBs x 14 detectors, STRONG scaling) ------------
+    # GRBs/s through the public API, Universe.go(): the SAME population at every N, its bursts dealt over the
+    # ranks (LPT on the sizing pass's costs); unit records built on the host, events stay in HBM, the GBM
+    # trigger runs on the device, only the per-unit counters + 32 B per detector come back, then the NCCL
+    # event-count gather.  `--population P` (P bursts per GPU, weak scaling) is kept for profiling runs.
     population = None
     _LEG[0] = "population"
-    if args.population > 0:
+    n_pop = args.population * world if args.population > 0 else args.population_total
+    if n_pop > 0:
         from cosmogrb_b200.instruments.gbm.gbm_universe import GBM_CPL_Universe
         from cosmogrb_b200.universe import synthetic_population
 
-        # warm-up pass on the same population: the steady state of a long run, where the pooled event buffers
-        # have reached their final sizes and NCCL has been through its first collective (first-touch costs --
-        # cudaMalloc of tens of GB by the caching allocator -- took between 5 and 260 ms in otherwise identical runs)
-        warm = GBM_CPL_Universe(synthetic_population(args.population * world, seed=12345), save_path=None)
+        strong = args.population <= 0
+        # warm-up pass on a 2000-burst-per-GPU population: the steady state of a long run, where the pooled event
+        # buffers have reached their final sizes and NCCL has been through its first collective (first-touch costs
+        # -- cudaMalloc of tens of GB by the caching allocator -- took between 5 and 260 ms in otherwise identical runs)
+        warm = GBM_CPL_Universe(synthetic_population(min(n_pop, 2000 * world), seed=12345), save_path=None)
         warm.go(save=False, seed=seed, trigger=True)
         del warm
-        uni = GBM_CPL_Universe(synthetic_population(args.population * world, seed=12345), save_path=None)
+        uni = GBM_CPL_Universe(synthetic_population(n_pop, seed=12345), save_path=None)
         sync_all()
         eng.host_times.clear()
         _capi.profile_enable(True)
@@ -451,33 +488,49 @@ def run_gpu(args):
         pprof = _capi.profile_read()
         _capi.profile_enable(False)
         ms_pop = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        kms = torch.tensor([sum(m for _, m in pprof)], dtype=torch.float64, device=dev)
+        kms_all = [kms]
         if dist is not None:
             dist.all_reduce(ms_pop, op=dist.ReduceOp.MAX)
+            kms_all = [torch.zeros_like(kms) for _ in range(world)]
+            dist.all_gather(kms_all, kms)
         ms_pop = float(ms_pop.item())
-        ec = np.maximum(uni.event_counts, 0)          # skipped bursts read -1
+        # simulated bursts only: a skipped burst (runaway lambda(t)) reads -1 and counts for nothing
+        simulated = np.asarray(uni.event_counts).reshape(uni.n_grbs, -1).min(axis=1) >= 0
+        n_sim = int(simulated.sum())
+        ec = np.maximum(uni.event_counts, 0)
         n_ev = int(ec[:, :, 0].sum() + ec[:, :, 1].sum())
         pk = {}
         for name, m in pprof:
             pk[name] = pk.get(name, 0.0) + m
         tot_k = sum(pk.values()) or 1.0
         # HBM roofline of the background-dominated kernels on this workload (local share of the events)
+        n_src_local = int(ec[uni.local_grbs][:, :, 0].sum())
         n_bkg_local = int(ec[uni.local_grbs][:, :, 1].sum())
-        n_tot_local = int(ec[uni.local_grbs][:, :, 0].sum()) + n_bkg_local
+        n_tot_local = n_src_local + n_bkg_local
+        ptraffic = tj.get("population", {}) if isinstance(tj, dict) else {}
         pop_roof = {}
         for name, nb_, nu in (("k_background", 9.0, n_bkg_local), ("k_gap_prefix<1>", 8.0, n_bkg_local),
-                              ("k_merge_deadtime", 18.0, n_tot_local)):
+                              ("k_merge_deadtime", 18.0, n_tot_local), ("k_trig_bin", 9.0, n_tot_local)):
             if name in pk and pk[name] > 0:
                 ach = nb_ * nu / (pk[name] * 1e-3) / 1e9
-                pop_roof[name] = {"ms": pk[name], "achieved_gbs": ach, "frac_of_measured_hbm": ach / peak}
+                pop_roof[name] = {"ms": pk[name], "achieved_gbs": ach, "frac_of_measured_hbm": ach / peak,
+                                  "algorithmic_bytes_per_event": nb_,
+                                  "traffic_bytes_per_event_ncu": ptraffic.get("dram_bytes_per_event", {}).get(name),
+                                  "issue_slots_busy_frac_ncu": ptraffic.get("issue_slots_busy_frac", {}).get(name)}
         population = {
-            "workload": f"C4: {args.population} GRBs per GPU x 14 detectors, synthetic popsynth-style population "
+            "workload": f"C5: {n_pop} GRBs x 14 detectors over {world} GPU(s), synthetic popsynth-style population "
                         "(seed 12345), events stay in HBM, GBM trigger on the device, counters + 32 B per detector read back; bursts whose candidate count "
-                        "does not fit the memory budget are skipped (the reference's lambda(t) runs away for low Epeak)",
-            "n_grbs": int(uni.n_grbs), "n_skipped_per_gpu": len(uni.skipped), "events": n_ev,
+                        "does not fit the memory budget are skipped and NOT counted (the reference's lambda(t) runs away for low Epeak)",
+            "metric": "GRBs/s", "scaling": "strong" if strong else "weak",
+            "n_grbs": int(uni.n_grbs), "n_simulated": n_sim, "n_skipped": int(uni.n_grbs) - n_sim,
+            "n_skipped_local": len(uni.skipped), "events": n_ev,
             "gbm_trigger": {"on_device": True, "detected_local": int(uni.detected.sum()), "local_grbs": int(len(uni.local_grbs)),
-                            "kernel_ms": round(pk.get("k_trig_bin", 0.0) + pk.get("k_trig_eval", 0.0), 3)}, "ms": ms_pop, "grbs_per_s": uni.n_grbs / (ms_pop * 1e-3),
+                            "kernel_ms": round(pk.get("k_trig_bin", 0.0) + pk.get("k_trig_eval", 0.0), 3)}, "ms": ms_pop,
+            "grbs_per_s": n_sim / (ms_pop * 1e-3),
             "events_per_s": n_ev / (ms_pop * 1e-3), "batches_per_gpu": int(uni.n_batches),
-            "kernel_ms_per_gpu": tot_k, "kernels": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])[:24]},
+            "kernel_ms_per_gpu": tot_k, "kernel_ms_all_ranks": [round(float(x.item()), 2) for x in kms_all],
+            "kernels": {k: round(v, 4) for k, v in sorted(pk.items(), key=lambda kv: -kv[1])[:24]},
             "hbm_kernels": pop_roof, "host_seconds": {k: round(v, 4) for k, v in uni.timings.items()},
             "host_detail": {k: round(v, 4) for k, v in eng.host_times.items()},
         }
@@ -506,14 +559,22 @@ def run_gpu(args):
                        "exact_lambda_evaluations": int(counts["n_exact"].sum()),
                        "kept_after_dead_time": int(counts["n_kept"].sum()), "rng": "philox4x32-10",
                        "l2": "no flush needed: each step streams > 2 GB of event buffers (L2 is 126 MB)",
-                       "parallelism": f"{world} x (1 GRB = 14 units per GPU per step)"},
+                       "parallelism": f"{world} x (1 GRB = 14 units per GPU per step)",
+                       # second metric of BASELINE.json ("GRBs/s at 1/2/4/8 B200"): the 100k-burst population under
+                       # STRONG scaling (same population at every N); details under the top-level "population" key
+                       "population": None if population is None else {
+                           k: population[k] for k in ("metric", "scaling", "n_grbs", "n_simulated", "n_skipped",
+                                                      "grbs_per_s", "events_per_s", "ms", "kernel_ms_all_ranks")}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // e2e_steps,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "d2h_gbs_per_gpu": e2e_d2h_gbs, "d2h_yardstick_gbs_per_gpu": d2h_peak,
+                    "frac_of_d2h_yardstick": (e2e_d2h_gbs / d2h_peak) if d2h_peak else None,
+                    "note": "bound by the device->host copy of the six event lists (18 B per event); the yardstick is one "
+                            "bare cudaMemcpyAsync of 1 GiB into pinned memory issued by all ranks at once"},
             "gpu_launches": int(launches),
             "rates": {"candidates_per_s": float(counts["n_candidates"].sum()) * world / (ms_max / args.steps * 1e-3),
                       "rejection_trials_per_s": float(counts["n_trials"].sum()) * world / (ms_max / args.steps * 1e-3)},
             "peaks_live": peaks_live,
-            "roofline": roofline, "roofline_hbm_kernels": hbm_kernels,
+            "roofline": roofline, "roofline_hbm_kernels": hbm_kernels, "roofline_issue_kernels": roofline_issue_kernels,
             "kernels": kern, "cpu_baseline": cpu_baseline, "clocks": clk, "population": population,
         }
         emit(line)
@@ -531,8 +592,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the e2e leg (profiling runs)")
-    ap.add_argument("--population", type=int, default=1000,
-                    help="GRBs per GPU of the population leg (GRBs/s through Universe.go); 0 = skip")
+    ap.add_argument("--population-total", type=int, default=100000,
+                    help="GRBs of the population leg, dealt over ALL ranks (BASELINE configs[4], strong scaling); 0 = skip")
+    ap.add_argument("--population", type=int, default=0,
+                    help="if > 0: GRBs PER GPU of the population leg instead (weak scaling; profiling runs)")
     args = ap.parse_args()
     # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, torchrun warnings)
     # write to fd 1 too, so everything else goes to stderr and the line is written to the real stdout

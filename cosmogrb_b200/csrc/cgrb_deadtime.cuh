@@ -324,10 +324,6 @@ __global__ void __launch_bounds__(NT) k_deadtime_write(const cgrb_unit_t *__rest
 // decoupled look-back over the preceding tiles' survivor counts (integers: deterministic).
 // 9 B read + <= 9 B written per event.
 // ==========================================================================================
-#define MD_TILE 2048
-#define MD_HALO 256
-#define MD_N (MD_TILE + MD_HALO)
-
 // merge-path split of diagonal d: number of background events among the first d merged events
 __device__ __forceinline__ int64_t merge_split(const double *__restrict__ A, int64_t nA, const double *__restrict__ B,
                                                int64_t nB, int64_t d)
@@ -472,72 +468,200 @@ __device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, 
     return ti > t_end ? 1 : 0;
 }
 
-// Per-tile records of the one-pass kernel, one thread per tile: the ~23 dependent probes of each merge-path
-// search are hidden by the other tiles' searches, and the persistent kernel's producer warps get everything they
-// need about a tile from ONE 64-byte record (ticket -> record -> staging is the whole dependence chain).
+// ------------------------------------------------------------------------------------------
+// Launch order of the tiles.  The survivors of a tile are appended behind those of the unit's earlier tiles, so a
+// tile has to learn how many events the earlier tiles kept (decoupled look-back below).  If the tiles were launched
+// unit by unit, the ~900 tiles in flight would all belong to the same unit and every one of them would wait for
+// its in-flight predecessors (measured: 25-40 % of a tile's life).  They are launched LEVEL-MAJOR instead: tile k
+// of every unit that has one, then tile k+1 of every unit, ... -- in a population batch (thousands of units) the
+// predecessor of a tile finished a whole level ago and the look-back is one load; with few units (the bright
+// burst: 14) the tiles in flight are spread over the units.
+// k_merge_order (one CTA) turns the per-unit live tile counts n_u (known on the device: counts) into
+//   cum[k]    = sum_u min(n_u, k)          first ticket of level k
+//   sorted[r] = units by descending n_u    (the units alive at level k are sorted[0 .. above[k]) )
+// and k_merge_plan maps ticket T -> (level k by bisection of cum, unit sorted[T - cum[k]]) and writes the tile's
+// 64-byte record at position T.  A tile only ever waits for tiles with smaller tickets.
+// ------------------------------------------------------------------------------------------
+struct MdOrder {
+    int32_t *hist;          // [cap + 2] zeroed by the caller: hist[n] = #{u : n_u == n}
+    int32_t *above;         // [cap + 2] above[k] = #{u : n_u > k}
+    int64_t *cum;           // [cap + 2]
+    int32_t *sorted;        // [n_units]
+    int32_t *eq;            // [n_units] scratch: rank of a unit among those with the same n_u
+    int64_t *header;        // [0] = number of live tickets, [1] = levels (max n_u)
+    int64_t cap;            // bound on any n_u (the work list's length)
+};
+
+#define MD_TILE 2048
+#ifndef MD_HALO
+#define MD_HALO 64              // look-back events staged in front of a tile (a multiple of 32)
+#endif
+#define MD_N (MD_TILE + MD_HALO)
+
+#define ORDER_NT 1024
+__device__ __forceinline__ long long order_block_excl_scan(long long v, long long *s_w, long long *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += o;
+    }
+    if (lane == 31)
+        s_w[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        long long x = s_w[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d)
+                x += o;
+        }
+        s_w[lane] = x;
+    }
+    __syncthreads();
+    const long long r = (wid > 0 ? s_w[wid - 1] : 0) + incl - v;
+    *total = s_w[ORDER_NT / 32 - 1];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(ORDER_NT) k_merge_order(const int64_t *__restrict__ unit_work_begin, int n_units,
+                                                          cgrb_counts_t *counts, MdOrder o)
+{
+    __shared__ long long s_w[ORDER_NT / 32];
+    __shared__ int s_max;
+    if (threadIdx.x == 0)
+        s_max = 0;
+    __syncthreads();
+    int mx = 0;
+    for (int u = threadIdx.x; u < n_units; u += ORDER_NT) {
+        const int64_t total = counts[u].n_bkg + counts[u].n_src;
+        counts[u].n_total = total;
+        if (total == 0)
+            counts[u].n_kept = 0;           // no tile will write it
+        const int64_t tiles_cap = unit_work_begin[u + 1] - unit_work_begin[u];
+        const int n = (int)min(min((total + MD_TILE - 1) / MD_TILE, tiles_cap), o.cap);
+        o.eq[u] = atomicAdd(&o.hist[n], 1);
+        mx = max(mx, n);
+    }
+    atomicMax(&s_max, mx);
+    __threadfence();
+    __syncthreads();
+    const int levels = s_max;
+    // above[k] = #{u : n_u > k} = sum of hist[k+1 ..]: a scan from the top, 1024 levels per round
+    long long carry = 0;
+    for (int top = levels; top > 0; top -= ORDER_NT) {
+        const int k = top - 1 - (int)threadIdx.x;           // this round covers k = top-1 .. top-1024, descending
+        const long long v = (k >= 0) ? o.hist[k + 1] : 0;
+        long long tot;
+        const long long ex = order_block_excl_scan(v, s_w, &tot);
+        if (k >= 0)
+            o.above[k] = (int32_t)(carry + ex + v);
+        carry += tot;
+    }
+    if (threadIdx.x == 0)
+        o.above[levels] = 0;
+    __threadfence();
+    __syncthreads();
+    // position of a unit in the descending order: the units with more tiles, then its rank among its equals
+    for (int u = threadIdx.x; u < n_units; u += ORDER_NT) {
+        const int64_t total = counts[u].n_total;
+        const int64_t tiles_cap = unit_work_begin[u + 1] - unit_work_begin[u];
+        const int n = (int)min(min((total + MD_TILE - 1) / MD_TILE, tiles_cap), o.cap);
+        if (n > 0)
+            o.sorted[o.above[n] + o.eq[u]] = u;
+    }
+    // cum[k] = sum_{k' < k} above[k'], k = 0 .. levels
+    carry = 0;
+    for (int base = 0; base <= levels; base += ORDER_NT) {
+        const int k = base + (int)threadIdx.x;
+        const long long v = (k < levels) ? o.above[k] : 0;
+        long long tot;
+        const long long ex = order_block_excl_scan(v, s_w, &tot);
+        if (k <= levels)
+            o.cum[k] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        o.header[0] = carry;
+        o.header[1] = levels;
+    }
+}
+
+// Per-tile records, one thread per ticket: the ~23 dependent probes of each merge-path search are hidden by the
+// other tiles' searches, and a CTA of the one-pass kernel gets everything about its tile from ONE 64-byte record.
 struct MdTile {
     int64_t a_off, b_off;       // first staged event (halo start) in the flat background / source arrays
-    int64_t wb;                 // first tile of the unit (look-back bound)
+    int64_t wb;                 // first tile of the unit in the state array (look-back bound)
     int64_t d0;                 // merged rank of the tile's first event
+    int64_t tot_off;            // the unit's slice of the output arrays
     int32_t na, nb;             // staged events of each list: halo + tile
     int32_t nt;                 // the tile's own events
     int32_t unit;
     uint32_t flags;             // MDT_*
-    int32_t pad[3];
+    int32_t pad;
 };
 static_assert(sizeof(MdTile) == 64, "MdTile is one 64-byte record");
 #define MDT_LIVE 1u
 #define MDT_HAS0 2u             // the staged range starts at the unit's event 0
 #define MDT_LAST 4u             // the unit's last live tile: writes n_kept
 
-__global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict__ units,
-                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
+__global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict__ units, int64_t n_work,
                                                    const int64_t *__restrict__ unit_work_begin,
                                                    const double *__restrict__ times_bkg,
-                                                   const double *__restrict__ times_src,
-                                                   MdTile *__restrict__ tiles, cgrb_counts_t *counts)
+                                                   const double *__restrict__ times_src, const MdOrder o,
+                                                   MdTile *__restrict__ tiles, const cgrb_counts_t *__restrict__ counts)
 {
-    const int64_t w = (int64_t)blockIdx.x * NT + threadIdx.x;
-    if (w >= n_work)
+    const int64_t T = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (T >= n_work)
         return;
-    const cgrb_work_t wk = work[w];
-    const cgrb_unit_t *u = units + wk.unit;
-    const int64_t nA = counts[wk.unit].n_bkg, nB = counts[wk.unit].n_src;
-    const int64_t total = nA + nB;
     MdTile t;
-    t.wb = unit_work_begin[wk.unit];
-    t.d0 = wk.start;
-    t.unit = wk.unit;
+    t.a_off = t.b_off = t.wb = t.d0 = t.tot_off = 0;
+    t.na = t.nb = t.nt = t.unit = t.pad = 0;
     t.flags = 0u;
-    t.a_off = t.b_off = 0;
-    t.na = t.nb = t.nt = 0;
-    t.pad[0] = t.pad[1] = t.pad[2] = 0;
-    if (w == t.wb) {
-        counts[wk.unit].n_total = total;
-        if (total == 0)
-            counts[wk.unit].n_kept = 0;     // no live tile will write it
-    }
-    if (wk.start < total) {
+    if (T < o.header[0]) {
+        // level: the last k with cum[k] <= T
+        int lo = 0, hi = (int)o.header[1];
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (o.cum[mid] <= T)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int unit = o.sorted[T - o.cum[lo]];
+        const cgrb_unit_t *u = units + unit;
+        const int64_t nA = counts[unit].n_bkg, nB = counts[unit].n_src;
+        const int64_t total = nA + nB;
+        const int64_t d0 = (int64_t)lo * MD_TILE;
         const double *A = times_bkg + u->bkg_off;
         const double *B = times_src + u->src_off;
-        const int64_t d1 = min(wk.start + (int64_t)MD_TILE, total);
-        const int64_t g0 = max((int64_t)0, wk.start - MD_HALO);     // first merged rank held in shared memory
+        const int64_t d1 = min(d0 + (int64_t)MD_TILE, total);
+        const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
         const int64_t i0 = merge_split(A, nA, B, nB, g0);
         const int64_t i1 = (d1 == total) ? nA : merge_split(A, nA, B, nB, d1);
         const int64_t j0 = g0 - i0;
         t.a_off = u->bkg_off + i0;
         t.b_off = u->src_off + j0;
+        t.wb = unit_work_begin[unit];
+        t.d0 = d0;
+        t.tot_off = u->tot_off;
         t.na = (int32_t)(i1 - i0);
         t.nb = (int32_t)((d1 - i1) - j0);
-        t.nt = (int32_t)(d1 - wk.start);
+        t.nt = (int32_t)(d1 - d0);
+        t.unit = unit;
         t.flags = MDT_LIVE | (g0 == 0 ? MDT_HAS0 : 0u) | (d1 == total ? MDT_LAST : 0u);
     }
-    tiles[w] = t;
+    tiles[T] = t;
 }
 
-#define MD_PER (MD_N / NT)       // merged elements per thread in the serial merge (9)
-#define MD_R (MD_TILE / NT)     // tile elements per thread in the dead-time pass (8)
-#define MD_WORDS (MD_N / 32)    // words of the chain bitmap (72)
+#define MD_PER ((MD_N + NT - 1) / NT)   // merged elements per thread in the merges (9)
+#define MD_R (MD_TILE / NT)             // tile elements per thread (8)
+#define MD_WORDS (MD_N / 32)            // words of a bitmap over the staged events (66)
 
 // ------------------------------------------------------------------------------------------
 // bulk-async (TMA) staging of a contiguous slice of a global list into shared memory.  cp.async.bulk moves
@@ -596,7 +720,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
 }
 
 #ifdef MD_TIMING
-#define MDT_DECL(n) long long tacc[n] = {0}; long long tlast = clock64(); int ttiles = 0;
+#define MDT_DECL(n) long long tacc[n] = {0}; long long tlast = clock64();
 #define MDT_MARK(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
 #else
 #define MDT_DECL(n)
@@ -604,25 +728,17 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
 #endif
 #define MD_SPARSE 64             // a tile whose minority list has at most this many events is merged by insertion
 #ifndef MD_CTAS
-#define MD_CTAS 6                // resident CTAs per SM the kernel is compiled for (register budget; 26 KB of shared memory each)
+#define MD_CTAS 6                // resident CTAs per SM the kernel is compiled for (register budget; ~20 KB of shared memory each)
 #endif
 
-struct MdStage {
+struct MdSmem {
     alignas(16) double t[MD_N + 4];         // slack: the alignment shift of up to two staged slices
     alignas(16) uint8_t p[MD_N + 48];
-};
-
-struct MdSmem {
-    MdStage st;
-    uint32_t chain[MD_WORDS];               // bit li: local event li is a chain element (overflow channel / event 0)
-    uint32_t rarekeep[MD_TILE / 32];        // keep flags of the tile elements resolved by the chain walk
-    uint16_t rare[MD_TILE];                 // tile elements that need the chain walk
+    uint32_t rare[MD_WORDS + 2];            // bit li: staged event li needs the exact chain walk
     uint16_t ins[MD_SPARSE];                // insertion merge: majority events preceding minority event i
-    uint8_t cblk[MD_WORDS + 4];             // insertion merge: minority events inserted before majority index 32 b
-    int cnt[MD_R * NW];                     // survivors per (round, warp), then their exclusive prefix
-    int n_rare;
+    uint8_t cblk[MD_WORDS + 6];             // insertion merge: minority events inserted before majority index 32 b
+    int wtot[NW];                           // survivors per warp
     long long excl;
-    long long ticket;
     alignas(8) uint64_t full;               // the staged slices have landed
 };
 
@@ -630,22 +746,129 @@ __device__ __forceinline__ void mbar_init(uint64_t *b, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *b)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)),
                  "r"(bytes)
                  : "memory");
 }
-// One CTA per tile of MD_TILE merged events; the tile index comes from a ticket counter (see lookback_exclusive)
-// and everything about the tile from ONE 64-byte record written by k_merge_plan, so the dependence chain in front
-// of the data is ticket -> record -> staging.  Many small CTAs per SM (MD_CTAS, 26 KB of shared memory each) overlap
-// one tile's latencies -- staging, barriers, the look-back -- with the other tiles' work.  (A persistent variant
-// with a producer warp and a two-stage ring was built and measured: CTAs that hold claimed tiles behind the one
-// they are processing turn the look-back into a convoy, 56-89 % of the time was spent waiting in it)
+// The two in-place merges of a staged tile (slice A at t[ta ..] / p[qa ..], slice B at t[tb ..] / p[qb ..]) into
+// merged order at t[0 ..] / p[0 ..]; out of line so that their register arrays do not weigh on the main path.
+// Called by every thread of the CTA (they contain barriers).
+__device__ __noinline__ void md_merge_insertion(MdSmem &sm, int na, int nb, int ta, int tb, int qa, int qb)
+{
+    const int tid = threadIdx.x, n = na + nb;
+    // insertion merge: minority M (nm events) into majority J (nj events).  Ties: background first, so a
+    // background event precedes the source events >= it, a source event follows the background events <= it.
+    const bool minor_a = na <= nb;
+    const int nm = minor_a ? na : nb, nj = n - nm;
+    const double *M = sm.t + (minor_a ? ta : tb), *J = sm.t + (minor_a ? tb : ta);
+    const uint8_t *pM = sm.p + (minor_a ? qa : qb), *pJ = sm.p + (minor_a ? qb : qa);
+    double rt[MD_PER], mt = 0.0;
+    uint8_t rp[MD_PER], mp = 0;
+    int mdest = 0;
+#pragma unroll
+    for (int r = 0; r < MD_PER; r++) {
+        const int k = r * NT + tid;
+        rt[r] = (k < nj) ? J[k] : 0.0;
+        rp[r] = (k < nj) ? pJ[k] : 0;
+    }
+    if (tid < nm) {
+        mt = M[tid];
+        mp = pM[tid];
+        int lo = 0, hi = nj;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const double v = J[mid];
+            if (minor_a ? (v < mt) : (v <= mt))
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        sm.ins[tid] = (uint16_t)lo;
+        mdest = lo + tid;
+    }
+    __syncthreads();
+    if (tid <= (nj + 31) / 32) {
+        int c = 0, hi = nm;                         // minority events inserted before majority index 32 tid
+        while (c < hi) {
+            const int mid = (c + hi) >> 1;
+            if ((int)sm.ins[mid] < 32 * tid)
+                c = mid + 1;
+            else
+                hi = mid;
+        }
+        sm.cblk[tid] = (uint8_t)c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < MD_PER; r++) {
+        const int k = r * NT + tid;
+        if (k < nj) {
+            const int c1 = sm.cblk[(k >> 5) + 1];
+            int c = sm.cblk[k >> 5];
+            for (int i = c; i < c1; i++)
+                c += ((int)sm.ins[i] <= k) ? 1 : 0;
+            sm.t[k + c] = rt[r];
+            sm.p[k + c] = rp[r];
+        }
+    }
+    if (tid < nm) {
+        sm.t[mdest] = mt;
+        sm.p[mdest] = mp;
+    }
+    __syncthreads();
+}
+
+__device__ __noinline__ void md_merge_general(MdSmem &sm, int na, int nb, int ta, int tb, int qa, int qb)
+{
+    const int tid = threadIdx.x, n = na + nb;
+    // serial merge of MD_PER consecutive outputs per thread from its merge-path split, in place through
+    // registers
+    const double *a_ = sm.t + ta, *b_ = sm.t + tb;
+    const uint8_t *pa_ = sm.p + qa, *pb_ = sm.p + qb;
+    const int q0 = min(tid * MD_PER, n);
+    int lo = max(0, q0 - nb), hi = min(q0, na);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    int ia = lo, ib = q0 - lo;
+    double rt[MD_PER];
+    uint8_t rp[MD_PER];
+#pragma unroll
+    for (int r = 0; r < MD_PER; r++) {
+        rt[r] = 0.0;
+        rp[r] = 0;
+        if (q0 + r < n) {
+            const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
+            rt[r] = take_a ? a_[ia] : b_[ib];
+            rp[r] = take_a ? pa_[ia] : pb_[ib];
+            ia += take_a ? 1 : 0;
+            ib += take_a ? 0 : 1;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < MD_PER; r++)
+        if (q0 + r < n) {
+            sm.t[q0 + r] = rt[r];
+            sm.p[q0 + r] = rp[r];
+        }
+    __syncthreads();
+}
+
+// One CTA per tile of MD_TILE merged events; blockIdx.x is the tile's TICKET in the level-major order above and
+// everything about the tile comes from ONE 64-byte record written by k_merge_plan, so the dependence chain in front
+// of the data is record -> staging.  Several small CTAs per SM (MD_CTAS, ~20 KB of shared memory each) overlap one
+// tile's latencies with the other tiles' work.  Forward progress of the look-back needs every tile with a smaller
+// ticket to be running or finished: CTAs of a 1-D grid are dispatched in blockIdx order (the assumption CUB's
+// decoupled look-back scan makes too); a wait that outlasts LB_WAIT_NS gives up and sets CGRB_ST_INTERNAL instead
+// of hanging.  (A persistent variant with a producer warp and a two-stage ring was built and measured: CTAs that
+// hold claimed tiles behind the one they are processing turn the look-back into a convoy)
 //  0. staging: the aligned middle of each list slice (+ MD_HALO events of look-back) by the bulk-async engine, the
 //     < 16-byte heads and tails by plain loads.
 //  1. merge.  A tile fed by one list only -- nearly every tile of a background-dominated unit -- is already in
@@ -654,22 +877,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, unsigned byte
 //     in the majority by bisection, every majority event shifts by the number of insertions before it (a count per
 //     32 events + the few insertions of its own block).  Anything else takes the general merge-path: MD_PER
 //     consecutive outputs per thread from its split.  In place, through registers.
-//  2. literal dead time: a bitmap of the chain elements (overflow channel, the unit's event 0); every warp derives
-//     the nearest chain element before each 32-event word by a prefix maximum over the words (registers), so an
-//     event finds its nearest earlier chain element from one word and one shuffle.  Only if that one lies within the
-//     longest window does the event join the `rare` list, which is then resolved densely by the exact walk
-//     (dt_keep_local, or the global accessor when the chain leaves the halo).
-//  3. survivors are appended at the unit's output offset from the decoupled look-back.
+//  2. every warp owns 256 consecutive events of the tile, lane l the events 32 r + l (r = 0..7), held in registers
+//     from here on.  Literal dead time: only an event that follows a CHAIN element (overflow channel, the unit's
+//     event 0; the first staged event stands in for whatever lies before the halo) by at most the longest window
+//     can be removed, so the chain elements -- a few per cent of the events -- mark their followers in a bitmap,
+//     and only marked events take the exact walk (dt_keep_local, or the global accessor when the chain leaves the
+//     halo).  Everything else is kept without further work.
+//  3. survivors are ranked by ballots (per warp) and a sum over the warps, warp 0 publishes the tile's count and
+//     looks back, and every thread stores its survivors at rank order: lane-consecutive, coalesced stores.
 template <int MODE>
 __global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_t *__restrict__ units,
-                                                          const cgrb_work_t *__restrict__ work, int64_t n_work,
-                                                          const int64_t *__restrict__ unit_work_begin,
                                                           const double *__restrict__ times_bkg,
                                                           const uint8_t *__restrict__ pha_bkg,
                                                           const double *__restrict__ times_src,
                                                           const uint8_t *__restrict__ pha_src,
                                                           unsigned long long *tile_state,
-                                                          unsigned long long *ticket_counter,
                                                           const MdTile *__restrict__ tiles,
                                                           double *__restrict__ times_out, uint8_t *__restrict__ pha_out,
                                                           cgrb_counts_t *counts, const DtModel md)
@@ -677,49 +899,44 @@ __global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_
     __shared__ MdSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     MDT_DECL(8)
+    const MdTile tile = tiles[blockIdx.x];
+    if (!(tile.flags & MDT_LIVE))
+        return;                 // beyond the last live ticket
     if (tid == 0) {
-        sm.ticket = (long long)atomicAdd(ticket_counter, 1ull);
-        sm.n_rare = 0;
         mbar_init(&sm.full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < MD_TILE / 32)
-        sm.rarekeep[tid] = 0u;
+    if (tid < MD_WORDS + 2)
+        sm.rare[tid] = 0u;
     __syncthreads();
-    const int64_t w = sm.ticket;
-    if (w >= n_work)
-        return;
-    const MdTile tile = tiles[w];
-    if (!(tile.flags & MDT_LIVE))
-        return;                 // beyond the end of the unit's merged list: nobody looks back at it
+    const int na = tile.na, nb = tile.nb, n = na + nb;      // n = halo + tile <= MD_N
+    const int64_t d0 = tile.d0;
+    const int l0 = (int)min(d0, (int64_t)MD_HALO), nt = tile.nt;     // l0 is 0 or MD_HALO
+    const int unit = tile.unit;
+    const bool has0 = (tile.flags & MDT_HAS0) != 0;
+    // ---- 0. staging: slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]; shared and global
+    // addresses agree mod 16
+    const double *gA = times_bkg + tile.a_off, *gB = times_src + tile.b_off;
+    const uint8_t *hA = pha_bkg + tile.a_off, *hB = pha_src + tile.b_off;
+    const int ta = (int)(((uintptr_t)gA >> 3) & 1u);
+    const int tb = ((ta + na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
+    const int qa = (int)((uintptr_t)hA & 15u);
+    const int qb = ((qa + na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
+    bool failed = false;
     {
-        MdStage &S = sm.st;
-        const int na = tile.na, nb = tile.nb, n = na + nb;      // n = d1 - g0 <= MD_N
-        const int64_t d0 = tile.d0;
-        const int l0 = (int)min(d0, (int64_t)MD_HALO), nt = tile.nt;
-        const int unit = tile.unit;
-        const bool has0 = (tile.flags & MDT_HAS0) != 0;
-        // ---- 0. staging: slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]; shared and global
-        // addresses agree mod 16
-        const double *gA = times_bkg + tile.a_off, *gB = times_src + tile.b_off;
-        const uint8_t *hA = pha_bkg + tile.a_off, *hB = pha_src + tile.b_off;
-        const int ta = (int)(((uintptr_t)gA >> 3) & 1u);
-        const int tb = ((ta + na + 1) & ~1) + (int)(((uintptr_t)gB >> 3) & 1u);
-        const int qa = (int)((uintptr_t)hA & 15u);
-        const int qb = ((qa + na + 15) & ~15) + (int)((uintptr_t)hB & 15u);
         const BulkPlan ptA = bulk_plan<8>(gA, na), ptB = bulk_plan<8>(gB, nb);
         const BulkPlan ppA = bulk_plan<1>(hA, na), ppB = bulk_plan<1>(hB, nb);
         const unsigned bulk_bytes = 8u * (unsigned)(ptA.body + ptB.body) + (unsigned)(ppA.body + ppB.body);
         if (tid == 0 && bulk_bytes) {
             mbar_arrive_expect_tx(&sm.full, bulk_bytes);
             if (ptA.body)
-                bulk_issue(S.t + ta + ptA.head, gA + ptA.head, 8u * ptA.body, &sm.full);
+                bulk_issue(sm.t + ta + ptA.head, gA + ptA.head, 8u * ptA.body, &sm.full);
             if (ptB.body)
-                bulk_issue(S.t + tb + ptB.head, gB + ptB.head, 8u * ptB.body, &sm.full);
+                bulk_issue(sm.t + tb + ptB.head, gB + ptB.head, 8u * ptB.body, &sm.full);
             if (ppA.body)
-                bulk_issue(S.p + qa + ppA.head, hA + ppA.head, (unsigned)ppA.body, &sm.full);
+                bulk_issue(sm.p + qa + ppA.head, hA + ppA.head, (unsigned)ppA.body, &sm.full);
             if (ppB.body)
-                bulk_issue(S.p + qb + ppB.head, hB + ppB.head, (unsigned)ppB.body, &sm.full);
+                bulk_issue(sm.p + qb + ppB.head, hB + ppB.head, (unsigned)ppB.body, &sm.full);
         }
         if (wid >= 1 && wid <= 4) {
             // heads and tails (< 16 bytes each) by plain loads, one warp per slice: a time slice has at most one head
@@ -731,275 +948,158 @@ __global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_
             const int e = lane < bp.head ? lane : (lane - bp.head < ntail ? tail0 + (lane - bp.head) : -1);
             if (e >= 0) {
                 if (which == 0)
-                    S.t[ta + e] = gA[e];
+                    sm.t[ta + e] = gA[e];
                 else if (which == 1)
-                    S.t[tb + e] = gB[e];
+                    sm.t[tb + e] = gB[e];
                 else if (which == 2)
-                    S.p[qa + e] = hA[e];
+                    sm.p[qa + e] = hA[e];
                 else
-                    S.p[qb + e] = hB[e];
+                    sm.p[qb + e] = hB[e];
             }
         }
-        bool failed = false;
         if (bulk_bytes)
             failed = !mbar_wait(&sm.full, 0u);
-        __syncthreads();
-        MDT_MARK(0);
+    }
+    __syncthreads();
+    MDT_MARK(0);
 
-        const double *T = S.t;
-        const uint8_t *P = S.p;
-        if (na == 0 || nb == 0) {
-            // a tile fed by one list only: the slice IS the merged order
-            T = S.t + (na ? ta : tb);
-            P = S.p + (na ? qa : qb);
-        } else if (min(na, nb) <= MD_SPARSE) {
-            // insertion merge: minority M (nm events) into majority J (nj events).  Ties: background first, so a
-            // background event precedes the source events >= it, a source event follows the background events <= it.
-            const bool minor_a = na <= nb;
-            const int nm = minor_a ? na : nb, nj = n - nm;
-            const double *M = S.t + (minor_a ? ta : tb), *J = S.t + (minor_a ? tb : ta);
-            const uint8_t *pM = S.p + (minor_a ? qa : qb), *pJ = S.p + (minor_a ? qb : qa);
-            double rt[MD_PER], mt = 0.0;
-            uint8_t rp[MD_PER], mp = 0;
-            int mdest = 0;
-#pragma unroll
-            for (int r = 0; r < MD_PER; r++) {
-                const int k = r * NT + tid;
-                rt[r] = (k < nj) ? J[k] : 0.0;
-                rp[r] = (k < nj) ? pJ[k] : 0;
+    // ---- 1. merged order of the staged events: T[0 .. n), P[0 .. n) ---------------------------------------
+    const double *T = sm.t;
+    const uint8_t *P = sm.p;
+    if (na == 0 || nb == 0) {
+        // a tile fed by one list only: the slice IS the merged order
+        T = sm.t + (na ? ta : tb);
+        P = sm.p + (na ? qa : qb);
+    } else if (min(na, nb) <= MD_SPARSE)
+        md_merge_insertion(sm, na, nb, ta, tb, qa, qb);
+    else
+        md_merge_general(sm, na, nb, ta, tb, qa, qb);
+    MDT_MARK(1);
+
+    // ---- 2. keep flags of this thread's events (local indices l0 + 256 wid + 32 r + lane) ---------------------
+    const int e0 = wid * (32 * MD_R) + lane;    // tile element of round 0
+    unsigned keep_bits = 0;                     // bit r: the event of round r survives
+    if (MODE == 0) {
+        if (tid < l0) {
+            // halo: its overflow events, and its first event in place of whatever lies before the halo
+            if (tid == 0 || P[tid] == 127) {
+                const double te = T[tid] + DT_TAU;
+                for (int k = tid + 1; k < n && !(te < T[k]); k++)
+                    if (k >= l0)
+                        atomicOr(&sm.rare[k >> 5], 1u << (k & 31));
             }
-            if (tid < nm) {
-                mt = M[tid];
-                mp = pM[tid];
-                int lo = 0, hi = nj;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    const double v = J[mid];
-                    if (minor_a ? (v < mt) : (v <= mt))
-                        lo = mid + 1;
-                    else
-                        hi = mid;
-                }
-                sm.ins[tid] = (uint16_t)lo;
-                mdest = lo + tid;
-            }
-            __syncthreads();
-            if (tid <= (nj + 31) / 32) {
-                int c = 0, hi = nm;                         // minority events inserted before majority index 32 tid
-                while (c < hi) {
-                    const int mid = (c + hi) >> 1;
-                    if ((int)sm.ins[mid] < 32 * tid)
-                        c = mid + 1;
-                    else
-                        hi = mid;
-                }
-                sm.cblk[tid] = (uint8_t)c;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < MD_PER; r++) {
-                const int k = r * NT + tid;
-                if (k < nj) {
-                    const int c1 = sm.cblk[(k >> 5) + 1];
-                    int c = sm.cblk[k >> 5];
-                    for (int i = c; i < c1; i++)
-                        c += ((int)sm.ins[i] <= k) ? 1 : 0;
-                    S.t[k + c] = rt[r];
-                    S.p[k + c] = rp[r];
-                }
-            }
-            if (tid < nm) {
-                S.t[mdest] = mt;
-                S.p[mdest] = mp;
-            }
-        } else {
-            // serial merge of MD_PER consecutive outputs per thread from its merge-path split, in place through
-            // registers
-            const double *a_ = S.t + ta, *b_ = S.t + tb;
-            const uint8_t *pa_ = S.p + qa, *pb_ = S.p + qb;
-            const int q0 = min(tid * MD_PER, n);
-            int lo = max(0, q0 - nb), hi = min(q0, na);
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (a_[mid] <= b_[q0 - 1 - mid])     // ties: background first
-                    lo = mid + 1;
-                else
-                    hi = mid;
-            }
-            int ia = lo, ib = q0 - lo;
-            double rt[MD_PER];
-            uint8_t rp[MD_PER];
-#pragma unroll
-            for (int r = 0; r < MD_PER; r++) {
-                rt[r] = 0.0;
-                rp[r] = 0;
-                if (q0 + r < n) {
-                    const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
-                    rt[r] = take_a ? a_[ia] : b_[ib];
-                    rp[r] = take_a ? pa_[ia] : pb_[ib];
-                    ia += take_a ? 1 : 0;
-                    ib += take_a ? 0 : 1;
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < MD_PER; r++)
-                if (q0 + r < n) {
-                    S.t[q0 + r] = rt[r];
-                    S.p[q0 + r] = rp[r];
-                }
         }
-        __syncthreads();        // merged order in place; rarekeep / n_rare cleared
-        MDT_MARK(1);
-
-        // ---- 2. keep flags of the tile's own events (local indices [l0, l0 + nt)) ---------------------------
-        unsigned keep_bits = 0;                 // bit r: tile element r * NT + tid survives
-        if (MODE == 0) {
+        unsigned chain_bits = 0;                // bit r: the event of round r is a chain element
 #pragma unroll
-            for (int r = 0; r < MD_PER; r++) {
-                const int li = r * NT + tid;
-                const bool c = li < n && (P[li] == 127 || (has0 && li == 0));
-                const unsigned bal = __ballot_sync(0xffffffffu, c);
-                if (lane == 0)
-                    sm.chain[r * NW + wid] = bal;
-            }
-            __syncthreads();
-            MDT_MARK(2);
-            // nearest chain element before each word (exclusive prefix maximum over the 72 words, per warp in
-            // registers: lane l of chunk c holds the value for word 32 c + l); "none": the halo's first event decides
-            // (index 0; a unit's event 0 is itself a chain element, so with has0 "none" only happens to event 0)
-            int carry[3];
-            {
-                int run = 0;
+        for (int r = 0; r < MD_R; r++) {
+            const int e = e0 + 32 * r, li = l0 + e;
+            chain_bits |= ((e < nt && (P[li] == 127 || (has0 && li == 0))) ? 1u : 0u) << r;
+        }
+        while (chain_bits) {
+            // a chain element: its followers within the longest window need the exact walk
+            const int li = l0 + e0 + 32 * (__ffs(chain_bits) - 1);
+            chain_bits &= chain_bits - 1u;
+            const double te = T[li] + DT_TAU;
+            for (int k = li + 1; k < n && !(te < T[k]); k++)
+                atomicOr(&sm.rare[k >> 5], 1u << (k & 31));
+        }
+        __syncthreads();
+        MDT_MARK(2);
+        const int64_t g0 = d0 - l0;
+        keep_bits = (1u << min(max((nt - e0 + 31) >> 5, 0), MD_R)) - 1u;       // this thread's events inside the tile
+        unsigned rare_bits = 0;
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const int wd = 32 * c + lane;
-                    const unsigned m = (wd < MD_WORDS) ? sm.chain[wd] : 0u;
-                    int v = m ? (wd << 5) + 31 - __clz(m) : 0;
-#pragma unroll
-                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                        const int o = __shfl_up_sync(0xffffffffu, v, dlt);
-                        if (lane >= dlt)
-                            v = max(v, o);
-                    }
-                    int ex = __shfl_up_sync(0xffffffffu, v, 1);
-                    if (lane == 0)
-                        ex = 0;
-                    carry[c] = max(run, ex);
-                    run = max(run, __shfl_sync(0xffffffffu, v, 31));
-                }
-            }
-            const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-            for (int r = 0; r < MD_R; r++) {
-                const int e = r * NT + tid;
-                const int wd = (l0 >> 5) + r * NW + wid;            // l0 is 0 or MD_HALO: li & 31 == lane
-                const int cw = __shfl_sync(0xffffffffu, wd < 32 ? carry[0] : wd < 64 ? carry[1] : carry[2], wd & 31);
-                if (e < nt) {
-                    const int li = l0 + e;
-                    int keep = 1;
-                    if (!(has0 && li == 0)) {
-                        const unsigned m = sm.chain[wd] & lt;
-                        const int j = m ? (wd << 5) + 31 - __clz(m) : cw;
-                        if (!(T[j] + DT_TAU < T[li])) {
-                            // a chain element (or an exhausted halo) within the window: the exact walk decides
-                            sm.rare[atomicAdd(&sm.n_rare, 1)] = (uint16_t)e;
-                            keep = 0;
-                        }
-                    }
-                    keep_bits |= (unsigned)keep << r;
-                }
-            }
-            __syncthreads();
-            const int n_rare = sm.n_rare;
-            if (n_rare > 0) {
+        for (int r = 0; r < MD_R; r++)
+            rare_bits |= ((sm.rare[(l0 >> 5) + wid * MD_R + r] >> lane) & 1u) << r;     // word li >> 5: one per warp and round
+        rare_bits &= keep_bits;
+        while (rare_bits) {
+            const int r = __ffs(rare_bits) - 1;
+            rare_bits &= rare_bits - 1u;
+            const int e = e0 + 32 * r;
+            int k3 = dt_keep_local(T, P, l0 + e, g0);
+            if (k3 == 2) {
                 const cgrb_unit_t *u = units + unit;
                 const MergedGlobal mg{times_bkg + u->bkg_off, times_src + u->src_off, pha_bkg + u->bkg_off,
                                       pha_src + u->src_off, counts[unit].n_bkg, counts[unit].n_src};
-                const int64_t g0 = d0 - l0;
-                for (int k = tid; k < n_rare; k += NT) {
-                    const int e = sm.rare[k];
-                    int keep = dt_keep_local(T, P, l0 + e, g0);
-                    if (keep == 2)
-                        keep = dt_keep_slow(mg, d0 + e) ? 1 : 0;
-                    if (keep)
-                        atomicOr(&sm.rarekeep[e >> 5], 1u << (e & 31));
-                }
-                __syncthreads();
-#pragma unroll
-                for (int r = 0; r < MD_R; r++)
-                    keep_bits |= ((sm.rarekeep[r * NW + wid] >> lane) & 1u) << r;
+                k3 = dt_keep_slow(mg, d0 + e) ? 1 : 0;
             }
-        } else {
-            // physical mode: a unit already flagged for the serial fix-up needs no more work here
-            const bool flagged = ((*(volatile uint32_t *)&counts[unit].status) & CGRB_ST_DEADTIME_CHAIN) != 0;
-            const EventArrays ev{T, P};
-#pragma unroll
-            for (int r = 0; r < MD_R; r++) {
-                const int e = r * NT + tid;
-                int keep = 0;
-                if (e < nt) {
-                    // no synchronisation point inside the tile's halo (256 events closer than the longest
-                    // window: never at GBM rates): the unit goes to the serial fix-up kernel
-                    keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)(l0 + e), has0, md);
-                    if (keep == 2) {
-                        atomicOr(&counts[unit].status, CGRB_ST_DEADTIME_CHAIN);
-                        keep = 0;
-                    }
-                }
-                keep_bits |= (unsigned)keep << r;
-            }
+            if (!k3)
+                keep_bits &= ~(1u << r);
         }
-        MDT_MARK(3);
-        // survivors per (round, warp); this lane's rank inside its group, 8 bits per round
-        unsigned long long ranks = 0ull;
+    } else {
+        // physical mode: a unit already flagged for the serial fix-up needs no more work here
+        const bool flagged = ((*(volatile uint32_t *)&counts[unit].status) & CGRB_ST_DEADTIME_CHAIN) != 0;
+        const EventArrays ev{T, P};
 #pragma unroll
         for (int r = 0; r < MD_R; r++) {
-            const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
-            ranks |= (unsigned long long)__popc(bal & ((1u << lane) - 1u)) << (8 * r);
-            if (lane == 0)
-                sm.cnt[r * NW + wid] = __popc(bal);
-        }
-        __syncthreads();
-        MDT_MARK(4);
-
-        // ---- 3. output offset: warp 0 scans the 64 group counts, then looks back over the unit's earlier tiles ----
-        if (wid == 0) {
-            int c0 = sm.cnt[2 * lane], c1 = sm.cnt[2 * lane + 1];
-            int incl = warp_incl_scan_i(c0 + c1, lane);
-            const int cnt_tile = __shfl_sync(0xffffffffu, incl, 31);
-            sm.cnt[2 * lane] = incl - c0 - c1;
-            sm.cnt[2 * lane + 1] = incl - c1;
-            const long long excl = lookback_exclusive(tile_state, w, tile.wb, cnt_tile, lane, &failed);
-            if (lane == 0) {
-                sm.excl = excl;
-                if (tile.flags & MDT_LAST)
-                    counts[unit].n_kept = excl + cnt_tile;        // the last live tile of the unit
+            const int e = e0 + 32 * r, li = l0 + e;
+            int keep = 0;
+            if (e < nt) {
+                // no synchronisation point inside the tile's halo (MD_HALO events closer than the longest
+                // window: never at GBM rates): the unit goes to the serial fix-up kernel
+                keep = flagged ? 0 : dt_keep_phys(ev, (int64_t)li, has0, md);
+                if (keep == 2) {
+                    atomicOr(&counts[unit].status, CGRB_ST_DEADTIME_CHAIN);
+                    keep = 0;
+                }
             }
+            keep_bits |= (unsigned)keep << r;
         }
-        if (failed)
-            atomicOr(&counts[unit].status, CGRB_ST_INTERNAL);
-        __syncthreads();
-        MDT_MARK(5);
-        const int64_t out0 = units[unit].tot_off + sm.excl;
-        double *ot = times_out + out0;
-        uint8_t *op = pha_out + out0;
-#pragma unroll
-        for (int r = 0; r < MD_R; r++) {
-            if ((keep_bits >> r) & 1u) {
-                const int rank = sm.cnt[r * NW + wid] + (int)((ranks >> (8 * r)) & 0xffull);
-                const int li = l0 + r * NT + tid;
-                ot[rank] = T[li];
-                op[rank] = P[li];
-            }
-        }
-        MDT_MARK(6);
-#ifdef MD_TIMING
-        if (tid == 0 && (w % 20000) == 777)
-            printf("MDT tile %lld: stage %lld merge %lld chain %lld keep %lld count %lld lookback %lld write %lld\n",
-                   (long long)w, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6]);
-#endif
     }
+    MDT_MARK(3);
+    // rank of each survivor inside its warp's 256 events (8 bits per round), survivors of the warp
+    unsigned long long ranks = 0ull;
+    int wsum = 0;
+#pragma unroll
+    for (int r = 0; r < MD_R; r++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, (keep_bits >> r) & 1u);
+        ranks |= (unsigned long long)(wsum + __popc(bal & ((1u << lane) - 1u))) << (8 * r);
+        wsum += __popc(bal);
+    }
+    if (lane == 0)
+        sm.wtot[wid] = wsum;
+    __syncthreads();
+    MDT_MARK(4);
+
+    // ---- 3. output offset: sum over the warps; warp 0 publishes the tile's count and looks back ----------------
+    int wbase = 0, cnt_tile = 0;
+#pragma unroll
+    for (int q = 0; q < NW; q++) {
+        const int c = sm.wtot[q];
+        wbase += (q < wid) ? c : 0;
+        cnt_tile += c;
+    }
+    if (wid == 0) {
+        const int64_t w = tile.wb + d0 / MD_TILE;
+        const long long excl = lookback_exclusive(tile_state, w, tile.wb, cnt_tile, lane, &failed);
+        if (lane == 0) {
+            sm.excl = excl;
+            if (tile.flags & MDT_LAST)
+                counts[unit].n_kept = excl + cnt_tile;        // the last live tile of the unit
+        }
+    }
+    if (failed)
+        atomicOr(&counts[unit].status, CGRB_ST_INTERNAL);
+    __syncthreads();
+    MDT_MARK(5);
+    const int64_t out0 = tile.tot_off + sm.excl + wbase;
+    double *ot = times_out + out0;
+    uint8_t *op = pha_out + out0;
+#pragma unroll
+    for (int r = 0; r < MD_R; r++) {
+        if ((keep_bits >> r) & 1u) {
+            const int rank = (int)((ranks >> (8 * r)) & 0xffull);
+            const int li = l0 + e0 + 32 * r;
+            ot[rank] = T[li];
+            op[rank] = P[li];
+        }
+    }
+    MDT_MARK(6);
+#ifdef MD_TIMING
+    if (tid == 0 && (blockIdx.x % 20000) == 777)
+        printf("MDT tile %lld: stage %lld merge %lld mark %lld keep %lld count %lld lookback %lld write %lld\n",
+               (long long)blockIdx.x, tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6]);
+#endif
 }
 
 

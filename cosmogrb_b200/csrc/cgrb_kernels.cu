@@ -518,8 +518,9 @@ int cgrb_gbm_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_
     return check_launch("cgrb_gbm_dead_time");
 }
 
-// tile states [n_work] (8 bytes each), ticket counter + pad (64 bytes), tile records [n_work] (64 bytes each)
-int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 72 * (n_work > 0 ? n_work : 0) + 128; }
+// tile states [n_work] (8 B each), header (64 B), tile records [n_work] (64 B each), the level-major order's tables:
+// hist / above (int32 [n_work + 2] each), cum (int64 [n_work + 2]), sorted / eq (int32 [n_units <= n_work] each)
+int64_t cgrb_merge_dead_time_workspace_bytes(int64_t n_work) { return 96 * (n_work > 0 ? n_work : 0) + 512; }
 
 int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
                          const int64_t *d_unit_work_begin, const double *d_times_bkg, const uint8_t *d_pha_bkg,
@@ -528,29 +529,45 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
                          const cgrb_deadtime_model_t *model, void *stream)
 {
     if (!d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_times_bkg || !d_pha_bkg ||
-        !d_times_src || !d_pha_src || !d_workspace || !d_times_out || !d_pha_out || !d_counts)
+        !d_times_src || !d_pha_src || !d_workspace || !d_times_out || !d_pha_out || !d_counts || n_units > n_work)
         return fail(CGRB_E_BADARG, "cgrb_merge_dead_time: bad argument%s");
     DtModel md;
     int physical;
     if (int rc = deadtime_model(model, &md, &physical, "cgrb_merge_dead_time"))
         return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(d_workspace, 0, 8 * (size_t)n_work + 16, s);
+    char *ws = (char *)d_workspace;
+    unsigned long long *state = (unsigned long long *)ws;
+    MdOrder o;
+    o.header = (int64_t *)(ws + 8 * (size_t)n_work);
+    MdTile *tiles = (MdTile *)(ws + 8 * (size_t)n_work + 64);
+    char *q = (char *)(tiles + n_work);
+    o.cum = (int64_t *)q;
+    q += 8 * ((size_t)n_work + 2);
+    o.hist = (int32_t *)q;
+    q += 4 * ((size_t)n_work + 2);
+    o.above = (int32_t *)q;
+    q += 4 * ((size_t)n_work + 2);
+    o.sorted = (int32_t *)q;
+    q += 4 * (size_t)n_work;
+    o.eq = (int32_t *)q;
+    o.cap = n_work;
+    // zero the tile states + header, and the histogram
+    cudaError_t e = cudaMemsetAsync(ws, 0, 8 * (size_t)n_work + 64, s);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(o.hist, 0, 4 * ((size_t)n_work + 2), s);
     if (e != cudaSuccess)
         return fail(CGRB_E_CUDA, "cgrb_merge_dead_time: memset: %s", cudaGetErrorString(e));
-    unsigned long long *ticket = (unsigned long long *)d_workspace + n_work;
-    MdTile *tiles = (MdTile *)((char *)d_workspace + ((8 * (size_t)n_work + 16 + 63) / 64) * 64);
+    LAUNCH("k_merge_order", s, k_merge_order<<<1, ORDER_NT, 0, s>>>(d_unit_work_begin, n_units, d_counts, o));
     LAUNCH("k_merge_plan", s, k_merge_plan<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
-        d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_times_src, tiles, d_counts));
-    const unsigned md_grid = (unsigned)n_work;      // one tile per CTA, tile index from the ticket counter
+        d_units, n_work, d_unit_work_begin, d_times_bkg, d_times_src, o, tiles, d_counts));
+    const unsigned md_grid = (unsigned)n_work;      // one tile per CTA; blockIdx.x = ticket in the level-major order
     if (!physical) {
         LAUNCH("k_merge_deadtime", s, k_merge_deadtime<0><<<md_grid, NT, 0, s>>>(
-            d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
-            (unsigned long long *)d_workspace, ticket, tiles, d_times_out, d_pha_out, d_counts, md));
+            d_units, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src, state, tiles, d_times_out, d_pha_out, d_counts, md));
     } else {
         LAUNCH("k_merge_deadtime_phys", s, k_merge_deadtime<1><<<md_grid, NT, 0, s>>>(
-            d_units, d_work, n_work, d_unit_work_begin, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src,
-            (unsigned long long *)d_workspace, ticket, tiles, d_times_out, d_pha_out, d_counts, md));
+            d_units, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src, state, tiles, d_times_out, d_pha_out, d_counts, md));
         LAUNCH("k_deadtime_phys_fixup", s, k_deadtime_phys_fixup<<<(n_units * 32 + 127) / 128, 128, 0, s>>>(
             d_units, n_units, nullptr, nullptr, d_times_bkg, d_pha_bkg, d_times_src, d_pha_src, d_times_out,
             d_pha_out, nullptr, d_counts, md));

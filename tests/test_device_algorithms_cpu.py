@@ -174,12 +174,12 @@ def merge_split(A, B, d):
 
 
 def test_merge_path_tiles_equal_the_reference_combine():
-    """k_merge_splits / k_merge_deadtime: every tile of the merged order (+ its look-back halo) is rebuilt from the
+    """k_merge_plan / k_merge_deadtime (md_merge_general): every tile of the merged order (+ its look-back halo) is rebuilt from the
     merge-path splits of its ends and per-thread serial merges of 9 elements; stitched together the tiles are the
     oracle's combine (lightcurve.py:131-151: stable two-way merge, background first on ties)."""
     rs = np.random.RandomState(2)
-    TILE, HALO, NT = 2048, 256, 256
-    PER = (TILE + HALO) // NT
+    TILE, HALO, NT = 2048, 64, 256
+    PER = (TILE + HALO + NT - 1) // NT
     for nA, nB, ties in ((7000, 9000, True), (0, 5000, False), (5000, 0, False), (1, 1, True), (30000, 300, True)):
         A = np.sort(rs.uniform(0, 10, nA))
         B = np.sort(rs.uniform(0, 10, nB))
@@ -244,7 +244,7 @@ def test_background_channel_guide_equals_numpy_choice():
         assert np.array_equal(got, want)
 
 
-# ---- k_merge_deadtime (round 2): chain bitmap + rare list inside a tile with halo ------------------------------
+# ---- k_merge_deadtime (round 2): chain elements mark their followers inside a tile with halo ------------------------------
 def dt_keep_local(t, p, li, g0):
     """csrc/cgrb_deadtime.cuh: dt_keep_local on a tile held in shared memory (local index 0 <-> merged rank g0);
     0 / 1, or 2 when the walk leaves the halo"""
@@ -293,10 +293,12 @@ def dt_keep_local(t, p, li, g0):
     return 1 if ti > t_end else 0
 
 
-def tile_keep_flags(t, p, d0, tile=2048, halo=256):
-    """k_merge_deadtime<0>, step 2, for the tile of merged ranks [d0, d0 + tile): chain bitmap of the staged events,
-    nearest earlier chain element by bit operations, the rare list resolved by dt_keep_local (global walk = dt_keep
-    when the chain leaves the halo).  Returns (keep flags, number of rare events, number of global walks)."""
+def tile_keep_flags(t, p, d0, tile=2048, halo=64):
+    """k_merge_deadtime<0>, step 2, for the tile of merged ranks [d0, d0 + tile): every chain element of the staged
+    events (overflow channel, the unit's event 0, and the first staged event in place of whatever lies before the
+    halo) marks the events that follow it by at most the longest window; only marked events take the exact walk
+    (dt_keep_local; the global walk = dt_keep when the chain leaves the halo), everything else is kept.
+    Returns (keep flags, number of marked events, number of global walks)."""
     n_all = len(t)
     g0 = max(0, d0 - halo)
     d1 = min(d0 + tile, n_all)
@@ -304,47 +306,76 @@ def tile_keep_flags(t, p, d0, tile=2048, halo=256):
     n = len(T)
     l0 = d0 - g0
     has0 = g0 == 0
-    words = np.zeros((n + 31) // 32 + 1, dtype=np.uint64)
+    rare = np.zeros(n, dtype=bool)
     for li in range(n):
-        if P[li] == 127 or (has0 and li == 0):
-            words[li >> 5] |= np.uint64(1) << np.uint64(li & 31)
+        if P[li] == 127 or li == 0:            # li == 0: the unit's event 0 (has0) or the stand-in for the past
+            te = T[li] + TAU
+            k = li + 1
+            while k < n and not (te < T[k]):
+                if k >= l0:
+                    rare[k] = True
+                k += 1
     keep = np.ones(d1 - d0, dtype=bool)
-    rare = []
+    n_slow = 0
     for e in range(d1 - d0):
         li = l0 + e
-        ti = T[li]
-        if li == 0 or T[li - 1] + TAU < ti:
-            continue                           # the unit's event 0 / nobody within the longest window
-        wd = li >> 5
-        m = int(words[wd]) & ((1 << (li & 31)) - 1)
-        j = -1
-        while True:
-            if m:
-                j = (wd << 5) + m.bit_length() - 1
-                break
-            if wd == 0:
-                j = 0                          # halo exhausted: its first event decides
-                break
-            if T[(wd << 5) - 1] + TAU < ti:
-                break                          # the earlier words lie outside the window
-            wd -= 1
-            m = int(words[wd])
-        if j >= 0 and not (T[j] + TAU < ti):
-            rare.append(e)
-            keep[e] = False
-    n_slow = 0
-    for e in rare:
-        k = dt_keep_local(T, P, l0 + e, g0)
+        if not rare[li]:
+            continue
+        k = dt_keep_local(T, P, li, g0)
         if k == 2:
             n_slow += 1
             k = 1 if dt_keep(t, p, d0 + e) else 0
         keep[e] = bool(k)
-    return keep, len(rare), n_slow
+    return keep, int(rare[l0:].sum()), n_slow
+
+
+def level_major_order(n_tiles):
+    """k_merge_order + k_merge_plan: ticket T -> (unit, level).  hist / above / cum / sorted exactly as the kernels
+    build them (the rank of a unit among its equals is whatever the atomics gave: any order works)."""
+    n_tiles = np.asarray(n_tiles, dtype=np.int64)
+    levels = int(n_tiles.max()) if len(n_tiles) else 0
+    hist = np.bincount(n_tiles, minlength=levels + 2)
+    above = np.array([hist[k + 1:].sum() for k in range(levels + 1)], dtype=np.int64)    # units with n_u > k
+    cum = np.concatenate(([0], np.cumsum(above[:levels])))
+    eq = np.zeros(len(n_tiles), dtype=np.int64)
+    seen = {}
+    for u in np.random.RandomState(5).permutation(len(n_tiles)):      # arrival order of the atomics: arbitrary
+        eq[u] = seen.get(int(n_tiles[u]), 0)
+        seen[int(n_tiles[u])] = eq[u] + 1
+    srt = np.full(int(above[0]) if levels else 0, -1, dtype=np.int64)
+    for u, n in enumerate(n_tiles):
+        if n > 0:
+            srt[above[n] + eq[u]] = u
+    out = []
+    for T in range(int(cum[levels])):
+        lo, hi = 0, levels
+        while hi - lo > 1:
+            mid = (lo + hi) >> 1
+            if cum[mid] <= T:
+                lo = mid
+            else:
+                hi = mid
+        out.append((int(srt[T - cum[lo]]), lo))
+    return out
+
+
+@pytest.mark.parametrize("n_tiles", [[3, 1, 4, 1, 5, 0, 2, 6], [7], [0, 0, 2], [1] * 40, list(range(25)) + [100, 3, 3]])
+def test_level_major_ticket_order_is_a_dependency_respecting_permutation(n_tiles):
+    """every live (unit, tile) pair gets exactly one ticket, and tile k of a unit has a larger ticket than its
+    tiles < k (the look-back only ever waits for smaller tickets); the tiles in flight spread over the units"""
+    order = level_major_order(n_tiles)
+    assert sorted(order) == sorted((u, k) for u, n in enumerate(n_tiles) for k in range(n))
+    ticket = {uk: T for T, uk in enumerate(order)}
+    for (u, k), T in ticket.items():
+        if k > 0:
+            assert ticket[(u, k - 1)] < T
+    levels = [k for _, k in order]
+    assert levels == sorted(levels)
 
 
 @pytest.mark.parametrize("rate,frac127,ties", [(500.0, 0.05, False), (7.5e4, 0.05, True), (2e5, 0.3, True),
                                                (2e6, 0.3, True), (3e7, 0.02, False), (1e5, 0.0, True)])
-def test_tile_chain_bitmap_equals_the_serial_rule(rate, frac127, ties):
+def test_tile_chain_marking_equals_the_serial_rule(rate, frac127, ties):
     rs = np.random.RandomState(int(rate) % 991 + int(100 * frac127) + 1)
     n = 3 * 2048 + 700
     for first127 in (False, True):
@@ -361,4 +392,4 @@ def test_tile_chain_bitmap_equals_the_serial_rule(rate, frac127, ties):
         if rate <= 500.0:
             assert n_rare < 0.01 * n           # GBM background: the rare list is (nearly) empty
         if rate >= 3e7:
-            assert n_slow > 0                  # 256 events inside one window: the halo runs out
+            assert n_slow > 0                  # more than 64 events inside one window: the halo runs out
