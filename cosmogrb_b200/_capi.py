@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # COSMOGRB_B200_LIB selects another build of the same library (tuning runs: variants compiled with -D flags)
 LIB_PATH = os.environ.get("COSMOGRB_B200_LIB") or os.path.join(_HERE, "_lib", "libcosmogrb_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 NBINS = 140
 NCHAN = 128
 NE_LAMBDA = 75
@@ -25,6 +25,7 @@ SEG = 8192
 MERGE_TILE = 2048
 DT_TILE = 2048
 MD_TILE = 2048
+BKG_TILE = 2048
 TRIG_TILE = 4096
 ENV_MAXW = 256
 
@@ -39,7 +40,8 @@ DT_G500_E = 720
 DT_G500_A = 1220
 DT_CUM = 1720
 DT_GUIDE = 1720 + NBINS * NCHAN           # NBINS*NCHAN bytes of uint8 search guides
-DT_SIZE = DT_GUIDE + NBINS * NCHAN // 8
+DT_BKG_GUIDE = DT_GUIDE + NBINS * NCHAN // 8    # NCHAN doubles: guide of the background channel draw
+DT_SIZE = DT_BKG_GUIDE + NCHAN
 
 ST_SRC_CAPACITY = 1
 ST_BKG_CAPACITY = 2
@@ -137,6 +139,7 @@ EXPORTS = (
     "cgrb_energy_workspace_bytes",
     "cgrb_sample_energy_envelope",
     "cgrb_digitize",
+    "cgrb_sample_background_workspace_bytes",
     "cgrb_sample_background",
     "cgrb_background_channels",
     "cgrb_combine",
@@ -185,7 +188,9 @@ def load():
     lib.cgrb_energy_workspace_bytes.restype = i64
     lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.cgrb_digitize.argtypes = [vp, vp, i32, vp, i64, rp, vp, vp, vp, vp]
-    lib.cgrb_sample_background.argtypes = [vp, vp, i32, vp, i64, vp, rp, rp, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_sample_background_workspace_bytes.argtypes = [i32, i64]
+    lib.cgrb_sample_background_workspace_bytes.restype = i64
+    lib.cgrb_sample_background.argtypes = [vp, vp, i32, i64, rp, rp, vp, vp, vp, vp, vp]
     lib.cgrb_background_channels.argtypes = [vp, i32, C.c_uint32, rp, i64, vp, vp]
     lib.cgrb_combine.argtypes = [vp, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     dp = C.POINTER(DeadtimeModel)
@@ -200,6 +205,7 @@ def load():
         fn = getattr(lib, name)
         if name not in ("cgrb_last_error", "cgrb_build_work", "cgrb_launch_count", "cgrb_energy_workspace_bytes",
                         "cgrb_merge_dead_time_workspace_bytes", "cgrb_gbm_trigger_workspace_bytes",
+                        "cgrb_sample_background_workspace_bytes",
                         "cgrb_thin_cum_bytes"):
             fn.restype = i32
     if lib.cgrb_abi_version() != ABI_VERSION:

@@ -271,3 +271,174 @@ __device__ __forceinline__ long long lookback_exclusive(unsigned long long *stat
     }
     return excl;
 }
+
+// ------------------------------------------------------------------------------------------
+// LEVEL-MAJOR launch order of the tiles of a batch.  Tile k of a unit depends on the unit's tiles < k: the survivors
+// of a dead-time tile are appended behind those of the earlier tiles (decoupled look-back above), a background tile
+// starts at the time where the previous one ended.  If the tiles were launched unit by unit, the ~900 tiles in
+// flight would all belong to the same unit and every one of them would wait for its in-flight predecessors
+// (measured in k_merge_deadtime: 25-40 % of a tile's life).  They are launched level-major instead: tile k of every
+// unit that has one, then tile k+1 of every unit, ... -- in a population batch (thousands of units) the predecessor
+// of a tile finished a whole level ago and the wait is one load; with few units (the bright burst: 14) the tiles
+// in flight are spread over the units.
+// k_level_order (one CTA) turns the per-unit tile counts n_u (computed on the device) into
+//   cum[k]    = sum_u min(n_u, k)          first ticket of level k
+//   sorted[r] = units by descending n_u    (the units alive at level k are sorted[0 .. above[k]) )
+//   ubeg[u]   = sum_{u' < u} n_u'          the unit's first slot in a per-tile state array
+// and a plan kernel maps ticket T -> (level k by bisection of cum, unit sorted[T - cum[k]]).  A tile only ever
+// waits for tiles with smaller tickets; CTAs of a 1-D grid are dispatched in blockIdx order (the assumption CUB's
+// decoupled look-back scan makes too), and every wait is bounded (CGRB_ST_INTERNAL instead of a hang).
+// ------------------------------------------------------------------------------------------
+struct LevelOrder {
+    int32_t *hist;          // [cap + 2] zeroed by the caller: hist[n] = #{u : n_u == n}
+    int32_t *above;         // [cap + 2] above[k] = #{u : n_u > k}
+    int64_t *cum;           // [cap + 2]
+    int32_t *sorted;        // [n_units]
+    int32_t *eq;            // [n_units] scratch: rank of a unit among those with the same n_u
+    int64_t *ubeg;          // [n_units + 1] or NULL
+    int64_t *header;        // [0] = number of live tickets, [1] = levels (max n_u)
+    int64_t cap;            // bound on any n_u
+};
+#define BKG_TILE 2048           // candidates per tile of the one-pass background kernel
+
+#define ORDER_NT 1024
+__device__ __forceinline__ long long order_block_excl_scan(long long v, long long *s_w, long long *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d)
+            incl += o;
+    }
+    if (lane == 31)
+        s_w[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        long long x = s_w[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long o = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d)
+                x += o;
+        }
+        s_w[lane] = x;
+    }
+    __syncthreads();
+    const long long r = (wid > 0 ? s_w[wid - 1] : 0) + incl - v;
+    *total = s_w[ORDER_NT / 32 - 1];
+    __syncthreads();
+    return r;
+}
+
+// tiles of unit u.  WHICH 0: live tiles of the one-pass combine + dead time (MD_TILE merged events each, from the
+// event counts; also records n_total); WHICH 1: tiles of the one-pass background (BKG_TILE candidates each, from the
+// capacity; a unit with background owns at least one: it carries the tstart event)
+template <int WHICH>
+__device__ __forceinline__ int level_tiles_of(const cgrb_unit_t *__restrict__ units,
+                                              const int64_t *__restrict__ unit_work_begin, cgrb_counts_t *counts,
+                                              int u, int64_t cap, bool first_pass)
+{
+    if (WHICH == 0) {
+        const int64_t total = counts[u].n_bkg + counts[u].n_src;
+        if (first_pass) {
+            counts[u].n_total = total;
+            if (total == 0)
+                counts[u].n_kept = 0;           // no tile will write it
+        }
+        const int64_t tiles_cap = unit_work_begin[u + 1] - unit_work_begin[u];
+        return (int)min(min((total + 2048 - 1) / 2048, tiles_cap), cap);
+    }
+    if (units[u].flags & CGRB_UNIT_NO_BACKGROUND)
+        return 0;
+    return (int)min(max((units[u].bkg_cap + BKG_TILE - 1) / BKG_TILE, (int64_t)1), cap);
+}
+
+template <int WHICH>
+__global__ void __launch_bounds__(ORDER_NT) k_level_order(const cgrb_unit_t *__restrict__ units,
+                                                          const int64_t *__restrict__ unit_work_begin, int n_units,
+                                                          cgrb_counts_t *counts, LevelOrder o)
+{
+    __shared__ long long s_w[ORDER_NT / 32];
+    __shared__ int s_max;
+    if (threadIdx.x == 0)
+        s_max = 0;
+    __syncthreads();
+    int mx = 0;
+    for (int u = threadIdx.x; u < n_units; u += ORDER_NT) {
+        const int n = level_tiles_of<WHICH>(units, unit_work_begin, counts, u, o.cap, true);
+        o.eq[u] = atomicAdd(&o.hist[n], 1);
+        mx = max(mx, n);
+    }
+    atomicMax(&s_max, mx);
+    __threadfence();
+    __syncthreads();
+    const int levels = s_max;
+    // above[k] = #{u : n_u > k} = sum of hist[k+1 ..]: a scan from the top, 1024 levels per round
+    long long carry = 0;
+    for (int top = levels; top > 0; top -= ORDER_NT) {
+        const int k = top - 1 - (int)threadIdx.x;           // this round covers k = top-1 .. top-1024, descending
+        const long long v = (k >= 0) ? o.hist[k + 1] : 0;
+        long long tot;
+        const long long ex = order_block_excl_scan(v, s_w, &tot);
+        if (k >= 0)
+            o.above[k] = (int32_t)(carry + ex + v);
+        carry += tot;
+    }
+    if (threadIdx.x == 0)
+        o.above[levels] = 0;
+    __threadfence();
+    __syncthreads();
+    // position of a unit in the descending order: the units with more tiles, then its rank among its equals;
+    // the unit's first state slot: exclusive sum of the tile counts in unit order
+    carry = 0;
+    for (int base = 0; base < n_units; base += ORDER_NT) {
+        const int u = base + (int)threadIdx.x;
+        const int n = (u < n_units) ? level_tiles_of<WHICH>(units, unit_work_begin, counts, u, o.cap, false) : 0;
+        if (n > 0)
+            o.sorted[o.above[n] + o.eq[u]] = u;
+        if (o.ubeg) {
+            long long tot;
+            const long long ex = order_block_excl_scan(n, s_w, &tot);
+            if (u < n_units)
+                o.ubeg[u] = carry + ex;
+            carry += tot;
+        }
+    }
+    if (o.ubeg && threadIdx.x == 0)
+        o.ubeg[n_units] = carry;
+    // cum[k] = sum_{k' < k} above[k'], k = 0 .. levels
+    carry = 0;
+    for (int base = 0; base <= levels; base += ORDER_NT) {
+        const int k = base + (int)threadIdx.x;
+        const long long v = (k < levels) ? o.above[k] : 0;
+        long long tot;
+        const long long ex = order_block_excl_scan(v, s_w, &tot);
+        if (k <= levels)
+            o.cum[k] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        o.header[0] = carry;
+        o.header[1] = levels;
+    }
+}
+
+// ticket -> (unit, level); false beyond the last live ticket
+__device__ __forceinline__ bool level_ticket(const LevelOrder &o, int64_t T, int *unit, int *level)
+{
+    if (T >= o.header[0])
+        return false;
+    int lo = 0, hi = (int)o.header[1];      // the last k with cum[k] <= T
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (o.cum[mid] <= T)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    *unit = o.sorted[T - o.cum[lo]];
+    *level = lo;
+    return true;
+}

@@ -468,129 +468,11 @@ __device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, 
     return ti > t_end ? 1 : 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// Launch order of the tiles.  The survivors of a tile are appended behind those of the unit's earlier tiles, so a
-// tile has to learn how many events the earlier tiles kept (decoupled look-back below).  If the tiles were launched
-// unit by unit, the ~900 tiles in flight would all belong to the same unit and every one of them would wait for
-// its in-flight predecessors (measured: 25-40 % of a tile's life).  They are launched LEVEL-MAJOR instead: tile k
-// of every unit that has one, then tile k+1 of every unit, ... -- in a population batch (thousands of units) the
-// predecessor of a tile finished a whole level ago and the look-back is one load; with few units (the bright
-// burst: 14) the tiles in flight are spread over the units.
-// k_merge_order (one CTA) turns the per-unit live tile counts n_u (known on the device: counts) into
-//   cum[k]    = sum_u min(n_u, k)          first ticket of level k
-//   sorted[r] = units by descending n_u    (the units alive at level k are sorted[0 .. above[k]) )
-// and k_merge_plan maps ticket T -> (level k by bisection of cum, unit sorted[T - cum[k]]) and writes the tile's
-// 64-byte record at position T.  A tile only ever waits for tiles with smaller tickets.
-// ------------------------------------------------------------------------------------------
-struct MdOrder {
-    int32_t *hist;          // [cap + 2] zeroed by the caller: hist[n] = #{u : n_u == n}
-    int32_t *above;         // [cap + 2] above[k] = #{u : n_u > k}
-    int64_t *cum;           // [cap + 2]
-    int32_t *sorted;        // [n_units]
-    int32_t *eq;            // [n_units] scratch: rank of a unit among those with the same n_u
-    int64_t *header;        // [0] = number of live tickets, [1] = levels (max n_u)
-    int64_t cap;            // bound on any n_u (the work list's length)
-};
-
 #define MD_TILE 2048
 #ifndef MD_HALO
 #define MD_HALO 64              // look-back events staged in front of a tile (a multiple of 32)
 #endif
 #define MD_N (MD_TILE + MD_HALO)
-
-#define ORDER_NT 1024
-__device__ __forceinline__ long long order_block_excl_scan(long long v, long long *s_w, long long *total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    long long incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const long long o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d)
-            incl += o;
-    }
-    if (lane == 31)
-        s_w[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        long long x = s_w[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const long long o = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= d)
-                x += o;
-        }
-        s_w[lane] = x;
-    }
-    __syncthreads();
-    const long long r = (wid > 0 ? s_w[wid - 1] : 0) + incl - v;
-    *total = s_w[ORDER_NT / 32 - 1];
-    __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(ORDER_NT) k_merge_order(const int64_t *__restrict__ unit_work_begin, int n_units,
-                                                          cgrb_counts_t *counts, MdOrder o)
-{
-    __shared__ long long s_w[ORDER_NT / 32];
-    __shared__ int s_max;
-    if (threadIdx.x == 0)
-        s_max = 0;
-    __syncthreads();
-    int mx = 0;
-    for (int u = threadIdx.x; u < n_units; u += ORDER_NT) {
-        const int64_t total = counts[u].n_bkg + counts[u].n_src;
-        counts[u].n_total = total;
-        if (total == 0)
-            counts[u].n_kept = 0;           // no tile will write it
-        const int64_t tiles_cap = unit_work_begin[u + 1] - unit_work_begin[u];
-        const int n = (int)min(min((total + MD_TILE - 1) / MD_TILE, tiles_cap), o.cap);
-        o.eq[u] = atomicAdd(&o.hist[n], 1);
-        mx = max(mx, n);
-    }
-    atomicMax(&s_max, mx);
-    __threadfence();
-    __syncthreads();
-    const int levels = s_max;
-    // above[k] = #{u : n_u > k} = sum of hist[k+1 ..]: a scan from the top, 1024 levels per round
-    long long carry = 0;
-    for (int top = levels; top > 0; top -= ORDER_NT) {
-        const int k = top - 1 - (int)threadIdx.x;           // this round covers k = top-1 .. top-1024, descending
-        const long long v = (k >= 0) ? o.hist[k + 1] : 0;
-        long long tot;
-        const long long ex = order_block_excl_scan(v, s_w, &tot);
-        if (k >= 0)
-            o.above[k] = (int32_t)(carry + ex + v);
-        carry += tot;
-    }
-    if (threadIdx.x == 0)
-        o.above[levels] = 0;
-    __threadfence();
-    __syncthreads();
-    // position of a unit in the descending order: the units with more tiles, then its rank among its equals
-    for (int u = threadIdx.x; u < n_units; u += ORDER_NT) {
-        const int64_t total = counts[u].n_total;
-        const int64_t tiles_cap = unit_work_begin[u + 1] - unit_work_begin[u];
-        const int n = (int)min(min((total + MD_TILE - 1) / MD_TILE, tiles_cap), o.cap);
-        if (n > 0)
-            o.sorted[o.above[n] + o.eq[u]] = u;
-    }
-    // cum[k] = sum_{k' < k} above[k'], k = 0 .. levels
-    carry = 0;
-    for (int base = 0; base <= levels; base += ORDER_NT) {
-        const int k = base + (int)threadIdx.x;
-        const long long v = (k < levels) ? o.above[k] : 0;
-        long long tot;
-        const long long ex = order_block_excl_scan(v, s_w, &tot);
-        if (k <= levels)
-            o.cum[k] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) {
-        o.header[0] = carry;
-        o.header[1] = levels;
-    }
-}
 
 // Per-tile records, one thread per ticket: the ~23 dependent probes of each merge-path search are hidden by the
 // other tiles' searches, and a CTA of the one-pass kernel gets everything about its tile from ONE 64-byte record.
@@ -613,7 +495,7 @@ static_assert(sizeof(MdTile) == 64, "MdTile is one 64-byte record");
 __global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict__ units, int64_t n_work,
                                                    const int64_t *__restrict__ unit_work_begin,
                                                    const double *__restrict__ times_bkg,
-                                                   const double *__restrict__ times_src, const MdOrder o,
+                                                   const double *__restrict__ times_src, const LevelOrder o,
                                                    MdTile *__restrict__ tiles, const cgrb_counts_t *__restrict__ counts)
 {
     const int64_t T = (int64_t)blockIdx.x * NT + threadIdx.x;
@@ -623,17 +505,8 @@ __global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict
     t.a_off = t.b_off = t.wb = t.d0 = t.tot_off = 0;
     t.na = t.nb = t.nt = t.unit = t.pad = 0;
     t.flags = 0u;
-    if (T < o.header[0]) {
-        // level: the last k with cum[k] <= T
-        int lo = 0, hi = (int)o.header[1];
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (o.cum[mid] <= T)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        const int unit = o.sorted[T - o.cum[lo]];
+    int unit, lo;
+    if (level_ticket(o, T, &unit, &lo)) {
         const cgrb_unit_t *u = units + unit;
         const int64_t nA = counts[unit].n_bkg, nB = counts[unit].n_src;
         const int64_t total = nA + nB;

@@ -406,14 +406,20 @@ int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
     return check_launch("cgrb_digitize");
 }
 
-int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
-                           const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
-                           const cgrb_rng_t *rng_time, const cgrb_rng_t *rng_chan, double *d_segsum,
-                           double *d_segstart, double *d_times_bkg, uint8_t *d_pha_bkg,
-                           cgrb_counts_t *d_counts, void *stream)
+// state words [n_tiles] (8 B), header (64 B), tile records [n_tiles] (64 B), the level-major order's tables:
+// cum (int64 [n_tiles + 2]), hist / above (int32 [n_tiles + 2] each), ubeg (int64 [n_units + 1]), sorted / eq (int32 [n_units])
+int64_t cgrb_sample_background_workspace_bytes(int n_units, int64_t n_tiles)
 {
-    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_unit_work_begin || !d_segsum ||
-        !d_segstart || !d_times_bkg || !d_pha_bkg || !d_counts)
+    if (n_units < 0 || n_tiles < 0)
+        return 0;
+    return 88 * (n_tiles + 2) + 16 * ((int64_t)n_units + 1) + 256;
+}
+
+int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, int64_t n_tiles,
+                           const cgrb_rng_t *rng_time, const cgrb_rng_t *rng_chan, void *d_workspace,
+                           double *d_times_bkg, uint8_t *d_pha_bkg, cgrb_counts_t *d_counts, void *stream)
+{
+    if (!d_dtab || !d_units || n_units <= 0 || n_tiles <= 0 || !d_workspace || !d_times_bkg || !d_pha_bkg || !d_counts)
         return fail(CGRB_E_BADARG, "cgrb_sample_background: bad argument%s");
     int rc = check_rng(rng_time, "cgrb_sample_background");
     if (rc)
@@ -428,12 +434,37 @@ int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int
         chan = *rng_chan;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH("k_gap_prefix<1>", s, k_gap_prefix<1><<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, *rng_time, d_segsum, d_times_bkg, d_counts,
-                                                                                 nullptr, 0));
-    LAUNCH("k_seg_scan<1>", s, k_seg_scan<1><<<(n_units * 32 + 127) / 128, 128, 0, s>>>(d_units, n_units, d_unit_work_begin, d_segsum,
-                                                           d_segstart, d_counts, *rng_time, nullptr));
-    LAUNCH("k_background", s, k_background<<<(unsigned)n_work, NT, 0, s>>>(d_dtab, d_units, d_work, n_work, *rng_time, chan, d_segstart,
-                                                 d_times_bkg, d_pha_bkg, d_counts));
+    char *ws = (char *)d_workspace;
+    unsigned long long *state = (unsigned long long *)ws;
+    LevelOrder o;
+    o.header = (int64_t *)(ws + 8 * (size_t)n_tiles);
+    char *q = ws + 8 * (size_t)n_tiles + 64;
+    BkgTile *tiles = (BkgTile *)q;
+    q += 64 * (size_t)n_tiles;
+    o.cum = (int64_t *)q;
+    q += 8 * ((size_t)n_tiles + 2);
+    o.ubeg = (int64_t *)q;
+    q += 8 * ((size_t)n_units + 1);
+    o.hist = (int32_t *)q;
+    q += 4 * ((size_t)n_tiles + 2);
+    o.above = (int32_t *)q;
+    q += 4 * ((size_t)n_tiles + 2);
+    o.sorted = (int32_t *)q;
+    q += 4 * (size_t)n_units;
+    o.eq = (int32_t *)q;
+    o.cap = n_tiles;
+    // state words: "not ready"; header + histogram: zero
+    cudaError_t e = cudaMemsetAsync(state, 0xFF, 8 * (size_t)n_tiles, s);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(o.header, 0, 64, s);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(o.hist, 0, 4 * ((size_t)n_tiles + 2), s);
+    if (e != cudaSuccess)
+        return fail(CGRB_E_CUDA, "cgrb_sample_background: memset: %s", cudaGetErrorString(e));
+    LAUNCH("k_background_order", s, k_level_order<1><<<1, ORDER_NT, 0, s>>>(d_units, nullptr, n_units, d_counts, o));
+    LAUNCH("k_background_plan", s, k_background_plan<<<(unsigned)((n_tiles + NT - 1) / NT), NT, 0, s>>>(d_units, n_tiles, o, tiles));
+    LAUNCH("k_background", s, k_background<<<(unsigned)n_tiles, NT, 0, s>>>(d_dtab, tiles, *rng_time, chan, state,
+                                                                         d_times_bkg, d_pha_bkg, d_counts));
     return check_launch("cgrb_sample_background");
 }
 
@@ -538,7 +569,8 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
     cudaStream_t s = (cudaStream_t)stream;
     char *ws = (char *)d_workspace;
     unsigned long long *state = (unsigned long long *)ws;
-    MdOrder o;
+    LevelOrder o;
+    o.ubeg = nullptr;
     o.header = (int64_t *)(ws + 8 * (size_t)n_work);
     MdTile *tiles = (MdTile *)(ws + 8 * (size_t)n_work + 64);
     char *q = (char *)(tiles + n_work);
@@ -558,7 +590,7 @@ int cgrb_merge_dead_time(const cgrb_unit_t *d_units, int n_units, const cgrb_wor
         e = cudaMemsetAsync(o.hist, 0, 4 * ((size_t)n_work + 2), s);
     if (e != cudaSuccess)
         return fail(CGRB_E_CUDA, "cgrb_merge_dead_time: memset: %s", cudaGetErrorString(e));
-    LAUNCH("k_merge_order", s, k_merge_order<<<1, ORDER_NT, 0, s>>>(d_unit_work_begin, n_units, d_counts, o));
+    LAUNCH("k_merge_order", s, k_level_order<0><<<1, ORDER_NT, 0, s>>>(d_units, d_unit_work_begin, n_units, d_counts, o));
     LAUNCH("k_merge_plan", s, k_merge_plan<<<(unsigned)((n_work + NT - 1) / NT), NT, 0, s>>>(
         d_units, n_work, d_unit_work_begin, d_times_bkg, d_times_src, o, tiles, d_counts));
     const unsigned md_grid = (unsigned)n_work;      // one tile per CTA; blockIdx.x = ticket in the level-major order

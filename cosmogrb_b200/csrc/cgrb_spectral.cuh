@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(64) k_fmax(const double *__restrict__ dtab, cg
 // tests/test_majorant_oracle.py restates this on the oracle's lambda(t) and checks the bounds on a finer grid
 // over the population's range of trise / tdecay / duration and table sizes (worst error / margin: 0.45).
 // ==========================================================================================
-__global__ void __launch_bounds__(NT) k_thin_nodes(const double *__restrict__ dtab,
+#ifndef THINNODES_CTAS
+#define THINNODES_CTAS 2          // 128 registers: 0.246 -> 0.192 ms on the bright burst (1 CTA/SM left the fp64 chains exposed)
+#endif
+__global__ void __launch_bounds__(NT, THINNODES_CTAS) k_thin_nodes(const double *__restrict__ dtab,
                                                    const cgrb_unit_t *__restrict__ units,
                                                    const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                    double *__restrict__ thin_tab)

@@ -238,40 +238,60 @@ __device__ __forceinline__ bool squeeze_margin_violated(double pe, double pl, do
     return margin >= 0.0 && margin < INFINITY && fabs(pe - pl) > margin * (1.0 + 1e-9) + 1e-15;
 }
 
-__device__ __forceinline__ bool thin_accept(const LambdaTab *tab, const cgrb_unit_t &u, bool squeeze,
-                                            const double2 *__restrict__ sq, double sq_inv_h, double t, double u2,
-                                            long long *n_exact, bool *sq_violated)
+// The exact test with its self-checks, out of line: nothing of the common path stays live across it.  Returns
+// bit 0: accept (v <= p(t)), bit 1: p(t) above the cell's majorant P (P < 1), bit 2: squeeze margin violated.
+#define THIN_ACC 1u
+#define THIN_MAJ_VIOLATED 2u
+#define THIN_SQ_VIOLATED 4u
+__device__ __noinline__ unsigned thin_exact(const LambdaTab *tab, const cgrb_unit_t &u, const double2 *__restrict__ sq,
+                                            int j, double fr, double t, double v, double P)
 {
+    const double pe = lambda_at(tab, u, t) / u.fmax;
+    unsigned r = (v <= pe) ? THIN_ACC : 0u;         // `if test <= p_test`
+    if (sq) {
+        const double2 n0 = __ldg(sq + j), n1 = __ldg(sq + j + 1);
+        const double pl = n0.x + (n1.x - n0.x) * fr;
+        if (P < 1.0 && pe > P * (1.0 + 1e-9))
+            r |= THIN_MAJ_VIOLATED;
+        if (squeeze_margin_violated(pe, pl, n0.y))
+            r |= THIN_SQ_VIOLATED;
+    }
+    return r;
+}
+
+// returns THIN_ACC | violation bits
+__device__ __forceinline__ unsigned thin_accept(const LambdaTab *tab, const cgrb_unit_t &u, bool squeeze,
+                                                const double2 *__restrict__ sq, double sq_inv_h, double t, double u2,
+                                                long long *n_exact)
+{
+    int kq = 0;
+    double fr = 0.0;
     if (squeeze) {
         const double q = (t - u.src_tstart) * sq_inv_h;
-        const int kq = min(max((int)q, 0), (int)u.tab_n - 2);       // tab_n < 2^31 (host: <= 65536 nodes)
-        const double fr = q - (double)kq;
+        kq = min(max((int)q, 0), (int)u.tab_n - 2);       // tab_n < 2^31 (host: <= 65536 nodes)
+        fr = q - (double)kq;
         const double2 n0 = __ldg(sq + kq), n1 = __ldg(sq + kq + 1);
         const double pl = n0.x + (n1.x - n0.x) * fr;
         if (n0.y >= 0.0) {                  // negative: a cell without squeeze
             if (u2 <= pl - n0.y)
-                return true;
+                return THIN_ACC;
             if (u2 > pl + n0.y)
-                return false;
+                return 0u;
         }
-        (*n_exact)++;
-        const double pe = lambda_exact(tab, u, t) / u.fmax;
-        if (squeeze_margin_violated(pe, pl, n0.y))
-            *sq_violated = true;
-        return u2 <= pe;
     }
     (*n_exact)++;
-    return u2 <= lambda_exact(tab, u, t) / u.fmax;   // `if test <= p_test`
+    return thin_exact(tab, u, squeeze ? sq : nullptr, kq, fr, t, u2, 1.0);
 }
 
 
 // Majorant mode: candidate at operational time tau -> cell j (guide + short walk over the cumulative table),
 // real time t inside the cell, acceptance with probability min(p(t), 1) / P_j by the same squeeze test.
-// *t_out receives the real time.  *violated is set if an exact evaluation finds p(t) above the cell's bound.
-__device__ __forceinline__ bool thin_accept_majorant(const LambdaTab *tab, const cgrb_unit_t &u,
-                                                     const double2 *__restrict__ sq, const ThinCum tc, double gscale,
-                                                     double h, double tau, double u2, double *t_out,
-                                                     long long *n_exact, bool *violated, bool *sq_violated)
+// *t_out receives the real time.  Returns THIN_ACC | violation bits (an exact evaluation that finds p(t) above the
+// cell's bound, or farther from the interpolation than the margin).
+__device__ __forceinline__ unsigned thin_accept_majorant(const LambdaTab *tab, const cgrb_unit_t &u,
+                                                         const double2 *__restrict__ sq, const ThinCum tc, double gscale,
+                                                         double h, double tau, double u2, double *t_out,
+                                                         long long *n_exact)
 {
     const int n = (int)u.tab_n;
     int j = __ldg(tc.guide + min(max((int)(tau * gscale), 0), n - 2));
@@ -297,22 +317,17 @@ __device__ __forceinline__ bool thin_accept_majorant(const LambdaTab *tab, const
     const double t = fmin(fma(fr, h, tj), tj1);
     *t_out = t;
     if (!(P > 0.0))
-        return false;
+        return 0u;
     const double v = u2 * P;
     const double pl = n0.x + (n1.x - n0.x) * fr;
     if (n0.y >= 0.0) {                      // negative: a cell without squeeze
         if (v <= pl - n0.y)
-            return true;
+            return THIN_ACC;
         if (v > pl + n0.y)
-            return false;
+            return 0u;
     }
     (*n_exact)++;
-    const double pe = lambda_exact(tab, u, t) / u.fmax;
-    if (P < 1.0 && pe > P * (1.0 + 1e-9))
-        *violated = true;
-    if (squeeze_margin_violated(pe, pl, n0.y))
-        *sq_violated = true;
-    return v <= pe;
+    return thin_exact(tab, u, sq, j, fr, t, v, P);
 }
 
 #ifndef THIN_CTAS
@@ -363,7 +378,7 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
     const double sq_inv_h = squeeze ? (double)(u.tab_n - 1) / (u.src_tstop - u.src_tstart) : 0.0;
     const double maj_h = maj ? (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1) : 0.0;
     const double maj_gscale = (maj && stop > 0.0) ? (double)(u.tab_n - 1) / stop : 0.0;
-    bool violated = false, sq_violated = false;
+    unsigned vflags = 0u;                  // THIN_*_VIOLATED bits of the exact evaluations
     double *seg = stage + u.src_off + wk.start;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     long long n_exact = 0;
@@ -397,13 +412,19 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
             PairDraw d = pair_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, (wk.start + j0) >> 1, 1);
             if (maj) {
                 const double tau_a = ta, tau_b = tb;
-                aa = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_a, d.a, &ta, &n_exact, &violated, &sq_violated);
+                unsigned ra = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_a, d.a, &ta, &n_exact), rb = 0u;
                 if (vb)
-                    ab = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_b, d.b, &tb, &n_exact, &violated, &sq_violated);
+                    rb = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_b, d.b, &tb, &n_exact);
+                aa = (ra & THIN_ACC) != 0u;
+                ab = (rb & THIN_ACC) != 0u;
+                vflags |= ra | rb;
             } else {
-                aa = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact, &sq_violated);
+                unsigned ra = thin_accept(&tab, u, squeeze, sq, sq_inv_h, ta, d.a, &n_exact), rb = 0u;
                 if (vb)
-                    ab = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact, &sq_violated);
+                    rb = thin_accept(&tab, u, squeeze, sq, sq_inv_h, tb, d.b, &n_exact);
+                aa = (ra & THIN_ACC) != 0u;
+                ab = (rb & THIN_ACC) != 0u;
+                vflags |= ra | rb;
             }
         }
         // ordered compaction: per-thread counts (0..2 accepted, 0..2 valid) packed in one int
@@ -444,8 +465,9 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
         if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
             break;      // crossed tstop: everything later is beyond it
     }
-    if (violated || sq_violated)
-        atomicOr(&counts[wk.unit].status, (violated ? CGRB_ST_MAJORANT : 0u) | (sq_violated ? CGRB_ST_SQUEEZE : 0u));
+    if (vflags & (THIN_MAJ_VIOLATED | THIN_SQ_VIOLATED))
+        atomicOr(&counts[wk.unit].status, ((vflags & THIN_MAJ_VIOLATED) ? CGRB_ST_MAJORANT : 0u) |
+                                              ((vflags & THIN_SQ_VIOLATED) ? CGRB_ST_SQUEEZE : 0u));
     {
         long long *s_ll = reinterpret_cast<long long *>(s_t);      // s_t is free now
         __syncthreads();
@@ -494,98 +516,212 @@ __global__ void __launch_bounds__(NT) k_source_gather(const cgrb_unit_t *__restr
 }
 
 // ==========================================================================================
-// background (background.py:13-44 + numpy choice :93): every candidate is an event; event j of
-// the unit is candidate j-1, event 0 is the spurious tstart event.  Pass 1 (k_gap_prefix<1>) left
-// each candidate's running gap sum in its time slot; this pass adds the segment start, draws the
-// channel from the template's cdf and cuts the list at tstop.
+// background (background.py:13-44 + numpy choice :93) in ONE pass: every candidate is an event; event j of the
+// unit is candidate j-1, event 0 is the spurious tstart event.  A CTA owns a tile of BKG_TILE consecutive candidates:
+//   1. exponential gaps (one Philox call per candidate pair) and their running sum inside the tile, in registers;
+//   2. the tile's start time is the END time of the unit's previous tile, read from a per-tile state word (the
+//      tiles are launched level-major, k_level_order: in a population batch the previous tile finished a whole
+//      level ago; with few units the chain costs one L2 round trip per tile, while the gaps of all the tiles in
+//      flight are drawn in parallel); the tile publishes its own end time at once;
+//   3. time = start + running sum, channel from the template's cdf (guide + short walk), list cut at tstop.
+// 9 B per event reach HBM (the two-pass version wrote and re-read an 8-byte running sum per candidate: 25 B).
+// The running sums are built so that the list is sorted BY CONSTRUCTION: every partial sum that starts a lane, a
+// round, a warp or a tile is the very value the element before it was given (see the comments below), and fp64
+// addition is monotone.  The association is fixed, so the times are reproducible.
 // ==========================================================================================
-__global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dtab,
-                                                   const cgrb_unit_t *__restrict__ units,
-                                                   const cgrb_work_t *__restrict__ work, int64_t n_work,
-                                                   cgrb_rng_t rng, cgrb_rng_t rng_chan,
-                                                   const double *__restrict__ segstart,
-                                                   double *times_bkg, uint8_t *__restrict__ pha_bkg,
-                                                   cgrb_counts_t *counts)
-{
-    __shared__ double s_cdf[CGRB_NCHAN];
-    __shared__ unsigned char s_cg[CGRB_NCHAN];      // guide: searchsorted(cdf, m/128, 'right')
-    __shared__ int s_wi[NW];
-    __shared__ double s_t[NT];
-    __shared__ double s_last;
-    const int64_t w = blockIdx.x;
-    if (w >= n_work)
-        return;
-    const cgrb_work_t wk = work[w];
-    const cgrb_unit_t *u = units + wk.unit;
-    if (u->flags & CGRB_UNIT_NO_BACKGROUND)
-        return;
-    const double t0 = segstart[w];
-    const double tstop = u->bkg_tstop;
-    const int64_t off = u->bkg_off;
-    const uint32_t sid = u->stream_id;
-    const double *cdf_g = dtab + (size_t)u->det * CGRB_DT_SIZE + CGRB_DT_BKG_CDF;
-    if (threadIdx.x < CGRB_NCHAN)
-        s_cdf[threadIdx.x] = cdf_g[threadIdx.x];
-    if (threadIdx.x == 0)
-        s_last = t0;
-    __syncthreads();
-    if (threadIdx.x < CGRB_NCHAN)
-        s_cg[threadIdx.x] = (unsigned char)min(searchsorted_right(s_cdf, CGRB_NCHAN, (double)threadIdx.x / CGRB_NCHAN),
-                                               CGRB_NCHAN - 1);
-    __syncthreads();
-    // np.searchsorted(cdf, u, 'right') clamped to the last channel, started from the guide: ~2 probes
-    auto channel_of = [&](double uc) -> uint8_t {
-        int j = s_cg[min(max((int)(uc * (double)CGRB_NCHAN), 0), CGRB_NCHAN - 1)];
-        while (j < CGRB_NCHAN - 1 && !(uc < s_cdf[j]))
-            j++;
-        return (uint8_t)j;
-    };
+struct BkgTile {
+    int64_t sidx;           // the tile's state word; the unit's previous tile is sidx - 1
+    int64_t off;            // slot of the tile's candidate 0 in times_bkg / pha_bkg (the unit's event 1 + k BKG_TILE)
+    double tstart, tstop, inv_rate;
+    int32_t unit;           // -1: beyond the last live ticket
+    int32_t k;              // tile of the unit: candidates [k BKG_TILE, (k+1) BKG_TILE)
+    int32_t n;              // candidates of the tile (the unit's capacity may end inside it)
+    uint32_t sid;           // Philox stream of the unit
+    int32_t det;            // detector table
+    uint32_t last;          // the unit's last tile
+};
+static_assert(sizeof(BkgTile) == 64, "BkgTile is one 64-byte record");
 
-    if (wk.start == 0 && threadIdx.x == 0) {
+// one thread per ticket: everything a tile needs in ONE record (the kernel's dependence chain in front of its
+// arithmetic is a single load)
+__global__ void __launch_bounds__(NT) k_background_plan(const cgrb_unit_t *__restrict__ units, int64_t n_tickets,
+                                                        const LevelOrder o, BkgTile *__restrict__ tiles)
+{
+    const int64_t T = (int64_t)blockIdx.x * NT + threadIdx.x;
+    if (T >= n_tickets)
+        return;
+    BkgTile t;
+    t.sidx = t.off = 0;
+    t.tstart = t.tstop = t.inv_rate = 0.0;
+    t.unit = -1;
+    t.k = t.n = t.det = 0;
+    t.sid = t.last = 0u;
+    int unit, level;
+    if (level_ticket(o, T, &unit, &level)) {
+        const cgrb_unit_t *u = units + unit;
+        const int64_t start = (int64_t)level * BKG_TILE;
+        t.sidx = o.ubeg[unit] + level;
+        t.off = u->bkg_off + 1 + start;
+        t.tstart = u->bkg_tstart;
+        t.tstop = u->bkg_tstop;
+        t.inv_rate = 1.0 / u->bkg_rate;
+        t.unit = unit;
+        t.k = level;
+        t.n = (int)max((int64_t)0, min((int64_t)BKG_TILE, u->bkg_cap - start));
+        t.sid = u->stream_id;
+        t.det = u->det;
+        t.last = (start + BKG_TILE >= u->bkg_cap) ? 1u : 0u;
+    }
+    tiles[T] = t;
+}
+
+#define BKG_NOT_READY 0xFFFFFFFFFFFFFFFFull     // state words are set to this (a NaN no tile can publish) before the launch
+#ifndef BKG_CTAS
+#define BKG_CTAS 5
+#endif
+#define BKG_R (BKG_TILE / (2 * NT))             // rounds: a thread owns one candidate PAIR per round (4)
+
+// np.searchsorted(cdf, u, 'right') clamped to the last channel (numpy's legacy choice, background.py:93), started
+// from the detector's guide (guide[m] = searchsorted(cdf, m / 128, 'right'), built with the table): ~2 probes.  The
+// 14 tables (1 KB + 128 B each) stay in L1: no staging, no barrier.
+__device__ __forceinline__ uint8_t bkg_channel_of(const double *__restrict__ cdf, const double *__restrict__ guide,
+                                                  double uc)
+{
+    int j = (int)__ldg(guide + min(max((int)(uc * (double)CGRB_NCHAN), 0), CGRB_NCHAN - 1));
+    while (j < CGRB_NCHAN - 1 && !(uc < __ldg(cdf + j)))
+        j++;
+    return (uint8_t)j;
+}
+
+__global__ void __launch_bounds__(NT, BKG_CTAS) k_background(const double *__restrict__ dtab,
+                                                             const BkgTile *__restrict__ tiles, cgrb_rng_t rng,
+                                                             cgrb_rng_t rng_chan, unsigned long long *state,
+                                                             double *__restrict__ times_bkg,
+                                                             uint8_t *__restrict__ pha_bkg, cgrb_counts_t *counts)
+{
+    __shared__ double s_wsum[NW];
+    __shared__ int s_wi[NW];
+    __shared__ double s_t0;
+    const BkgTile tl = tiles[blockIdx.x];
+    if (tl.unit < 0)
+        return;
+    const double tstop = tl.tstop;
+    const int n = tl.n;
+    const int64_t start = (int64_t)tl.k * BKG_TILE;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double *cdf = dtab + (size_t)tl.det * CGRB_DT_SIZE + CGRB_DT_BKG_CDF;
+    const double *guide = dtab + (size_t)tl.det * CGRB_DT_SIZE + CGRB_DT_BKG_GUIDE;
+    // the previous tile's end time, asked for now and needed after the gaps (level-major order: it is there)
+    unsigned long long prev = BKG_NOT_READY;
+    if (threadIdx.x == 0 && tl.k > 0)
+        prev = *((volatile unsigned long long *)(state + tl.sidx - 1));
+
+    // ---- 1. gaps and running sums.  Warp w owns the candidates [256 w, 256 w + 256) of the tile, round r the 64
+    // candidates from 256 w + 64 r, lane l the pair 2 l, 2 l + 1 of them.
+    const double inv_f = tl.inv_rate;
+    double p0[BKG_R], p1[BKG_R];
+    bool exhausted = false;
+    double rc = 0.0;                // running sum of the warp's earlier rounds
+#pragma unroll
+    for (int r = 0; r < BKG_R; r++) {
+        const int j0 = 256 * wid + 64 * r + 2 * lane;           // start and j0 are even
+        double g0 = 0.0, g1 = 0.0;
+        if (j0 < n) {
+            PairDraw d = pair_draw(rng, tl.unit, tl.sid, ST_BKG, (start + j0) >> 1, 0);
+            g0 = -(inv_f * log(d.a));                        // time - (1/rate) * log(u)  background.py:33
+            if (j0 + 1 < n)
+                g1 = -(inv_f * log(d.b));
+            exhausted |= d.exhausted;
+        }
+        const double incl = warp_incl_scan(g0 + g1, lane);
+        double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0)
+            excl = 0.0;
+        // the pair's second sum IS the value the next lane starts from (rc + incl), the round's last one IS the
+        // next round's rc: no element can fall below its predecessor.  Inside the pair the two roundings differ.
+        p1[r] = rc + incl;
+        p0[r] = fmin((rc + excl) + g0, p1[r]);
+        rc = rc + __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0)
+        s_wsum[wid] = rc;
+    __syncthreads();
+    // sum over the earlier warps in a fixed order: wbase(w + 1) = wbase(w) + W(w) is the last element of warp w
+    double wbase = 0.0, total = 0.0;
+#pragma unroll
+    for (int q = 0; q < NW; q++) {
+        if (q == wid)
+            wbase = total;
+        total = total + s_wsum[q];
+    }
+
+    // ---- 2. start time: the end of the unit's previous tile; publish this tile's end
+    if (threadIdx.x == 0) {
+        double t0 = tl.tstart;
+        bool failed = false;
+        if (tl.k > 0) {
+            unsigned long long t_begin = 0;
+            for (int spin = 0; prev == BKG_NOT_READY; spin++) {
+                prev = *((volatile unsigned long long *)(state + tl.sidx - 1));
+                if ((spin & 1023) == 1023) {
+                    const unsigned long long now = global_timer_ns();
+                    if (t_begin == 0)
+                        t_begin = now;
+                    else if (now - t_begin > LB_WAIT_NS) {
+                        failed = true;
+                        break;
+                    }
+                }
+            }
+            t0 = failed ? INFINITY : __longlong_as_double((long long)prev);
+        }
+        double t_end = t0 + total;      // == the last candidate's time
+        if (!(t_end == t_end))
+            t_end = INFINITY;           // never publish the NOT_READY pattern
+        *((volatile unsigned long long *)(state + tl.sidx)) = (unsigned long long)__double_as_longlong(t_end);
+        s_t0 = t0;
+        if (failed)
+            atomicOr(&counts[tl.unit].status, CGRB_ST_INTERNAL);
+    }
+    __syncthreads();
+    const double t0 = s_t0;
+
+    if (tl.k == 0 && threadIdx.x == 0) {
         // event 0: tstart, with its own channel draw (sample_channel(size=len(times)))
         double uc;
         if (rng.mode == 0) {
-            Philox4 p = philox_at(make_key(rng.seed), sid, ST_BKG, 0xFFFFFFFFFFull, 1u);
+            Philox4 p = philox_at(make_key(rng.seed), tl.sid, ST_BKG, 0xFFFFFFFFFFull, 1u);
             uc = u53(p.x, p.y);
         } else {
-            int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
+            int64_t o = rng_chan.d_off ? rng_chan.d_off[tl.unit] : 0;
             uc = rng_chan.d_u[o];
         }
-        times_bkg[off] = u->bkg_tstart;
-        pha_bkg[off] = channel_of(uc);
-        atomicAdd((unsigned long long *)&counts[wk.unit].n_bkg, 1ull);
+        times_bkg[tl.off - 1] = tl.tstart;
+        pha_bkg[tl.off - 1] = bkg_channel_of(cdf, guide, uc);
     }
     if (t0 > tstop)
-        return;
+        return;         // the list ended in an earlier tile (which recorded the count)
 
-    const int64_t n = min((int64_t)CGRB_SEG, u->bkg_cap - wk.start);
-    double *seg_t = times_bkg + off + 1 + wk.start;
-    uint8_t *seg_p = pha_bkg + off + 1 + wk.start;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int n_valid_total = 0;
-    bool exhausted = false;
-    for (int64_t base = 0; base < n; base += THIN_TILE) {
-        const int64_t j0 = base + 2 * threadIdx.x;
-        const bool in0 = j0 < n, in1 = j0 + 1 < n;
-        double ta = in0 ? t0 + seg_t[j0] : INFINITY;
-        double tb = in1 ? t0 + seg_t[j0 + 1] : INFINITY;
-        s_t[threadIdx.x] = in1 ? tb : ta;
-        __syncthreads();
-        const double left = (threadIdx.x > 0) ? s_t[threadIdx.x - 1] : s_last;
-        ta = fmax(ta, left);
-        tb = fmax(tb, ta);
-        const bool va = in0 && (ta <= tstop);
-        const bool vb = in1 && (tb <= tstop);
+    // ---- 3. times, channels, the cut at tstop
+    double *seg_t = times_bkg + tl.off;
+    uint8_t *seg_p = pha_bkg + tl.off;
+    int n_valid = 0;
+#pragma unroll
+    for (int r = 0; r < BKG_R; r++) {
+        const int j0 = 256 * wid + 64 * r + 2 * lane;
+        const double ta = t0 + (wbase + p0[r]), tb = t0 + (wbase + p1[r]);
+        const bool va = (j0 < n) && (ta <= tstop);
+        const bool vb = (j0 + 1 < n) && (tb <= tstop);
         if (va) {
             double ua, ub = 0.5;
             if (rng.mode == 0) {
-                PairDraw d = pair_draw(rng, wk.unit, sid, ST_BKG, (wk.start + j0) >> 1, 1);
+                PairDraw d = pair_draw(rng, tl.unit, tl.sid, ST_BKG, (start + j0) >> 1, 1);
                 ua = d.a;
                 ub = d.b;
             } else {
-                const int64_t o = rng_chan.d_off ? rng_chan.d_off[wk.unit] : 0;
-                const int64_t len = rng_chan.d_len ? rng_chan.d_len[wk.unit] : ((int64_t)1 << 62);
-                const int64_t e0 = wk.start + j0 + 1;           // event index of candidate j0
+                const int64_t o = rng_chan.d_off ? rng_chan.d_off[tl.unit] : 0;
+                const int64_t len = rng_chan.d_len ? rng_chan.d_len[tl.unit] : ((int64_t)1 << 62);
+                const int64_t e0 = start + j0 + 1;              // event index of candidate j0
                 ua = 0.5;
                 if (e0 < len)
                     ua = rng_chan.d_u[o + e0];
@@ -599,30 +735,28 @@ __global__ void __launch_bounds__(NT) k_background(const double *__restrict__ dt
                 }
             }
             seg_t[j0] = ta;
-            seg_p[j0] = channel_of(ua);
+            seg_p[j0] = bkg_channel_of(cdf, guide, ua);
             if (vb) {
                 seg_t[j0 + 1] = tb;
-                seg_p[j0 + 1] = channel_of(ub);
+                seg_p[j0 + 1] = bkg_channel_of(cdf, guide, ub);
             }
         }
-        const unsigned bala = __ballot_sync(0xffffffffu, va), balb = __ballot_sync(0xffffffffu, vb);
-        if (lane == 0)
-            s_wi[wid] = __popc(bala) + __popc(balb);
-        __syncthreads();
-        int tile_valid = 0;
+        n_valid += __popc(__ballot_sync(0xffffffffu, va)) + __popc(__ballot_sync(0xffffffffu, vb));
+    }
+    if (lane == 0)
+        s_wi[wid] = n_valid;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int valid = 0;
 #pragma unroll
         for (int q = 0; q < NW; q++)
-            tile_valid += s_wi[q];
-        n_valid_total += tile_valid;
-        if (threadIdx.x == NT - 1)
-            s_last = in1 ? tb : ta;
-        __syncthreads();
-        if (tile_valid < (int)min((int64_t)THIN_TILE, n - base))
-            break;
+            valid += s_wi[q];
+        // the tile in which the list ends records the count: tstart + the candidates up to tstop
+        if (valid < n || tl.last)
+            counts[tl.unit].n_bkg = 1 + start + valid;
+        if (tl.last && valid == n)
+            atomicOr(&counts[tl.unit].status, CGRB_ST_BKG_CAPACITY);    // the buffer ended before tstop
     }
-    if (threadIdx.x == 0 && n_valid_total)
-        atomicAdd((unsigned long long *)&counts[wk.unit].n_bkg, (unsigned long long)n_valid_total);
     if (exhausted)
-        atomicOr(&counts[wk.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
+        atomicOr(&counts[tl.unit].status, CGRB_ST_UNIFORMS_EXHAUSTED);
 }
-

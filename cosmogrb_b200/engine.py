@@ -643,20 +643,22 @@ class Engine(object):
 
     def sample_background(self, b, rng):
         torch = _torch()
-        w, dw, dwb = self._work(b, 1, _capi.SEG)
-        nw = len(w)
+        u = b.units
+        has = (u["flags"] & _capi.UNIT_NO_BACKGROUND) == 0
+        n_tiles = int(np.maximum((u["bkg_cap"][has] + _capi.BKG_TILE - 1) // _capi.BKG_TILE, 1).sum())
         t = b.t
-        t["bsegsum"] = self.empty(nw, torch.float64)
-        t["bsegstart"] = self.empty(nw, torch.float64)
         t["times_bkg"] = self.empty(b.n_bkg_slots, torch.float64)
         t["pha_bkg"] = self.empty(b.n_bkg_slots, torch.uint8)
+        if n_tiles == 0:
+            return
+        t["bkg_ws"] = self.empty(self.lib.cgrb_sample_background_workspace_bytes(b.n_units, n_tiles), torch.uint8)
         d_time = self._rng_desc(rng, b, "bkg_time")
         d_chan = self._rng_desc(rng, b, "bkg_chan") if isinstance(rng, Injected) else d_time
         _capi.check(
             self.lib.cgrb_sample_background(
-                b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), nw, dwb.data_ptr(),
-                C.byref(d_time), C.byref(d_chan), t["bsegsum"].data_ptr(), t["bsegstart"].data_ptr(),
-                t["times_bkg"].data_ptr(), t["pha_bkg"].data_ptr(), b.d_counts.data_ptr(), self.stream),
+                b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, n_tiles, C.byref(d_time), C.byref(d_chan),
+                t["bkg_ws"].data_ptr(), t["times_bkg"].data_ptr(), t["pha_bkg"].data_ptr(), b.d_counts.data_ptr(),
+                self.stream),
             "cgrb_sample_background")
         self.launches += 3
 
@@ -870,6 +872,10 @@ class Engine(object):
         if getattr(self, "_utab", None) is None:
             t = np.zeros(_capi.DT_SIZE)
             t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + _capi.NCHAN] = np.arange(1, _capi.NCHAN + 1) / _capi.NCHAN
+            from .response.response import background_guide
+
+            t[_capi.DT_BKG_GUIDE:_capi.DT_BKG_GUIDE + _capi.NCHAN] = background_guide(
+                t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + _capi.NCHAN])
             self._utab = [t]
         return self._utab
 

@@ -128,6 +128,7 @@ class Response(object):
             t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + nc] = cdf
         else:
             t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + nc] = np.arange(1, nc + 1) / nc
+        t[_capi.DT_BKG_GUIDE:_capi.DT_BKG_GUIDE + nc] = background_guide(t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + nc])
         # 10**linspace(log10 emin, log10 emax, n): cpl_functions.py:208,305
         for n, oe, oa in ((_capi.NE_LAMBDA, _capi.DT_G75_E, _capi.DT_G75_A),
                           (_capi.NE_ENVELOPE, _capi.DT_G500_E, _capi.DT_G500_A)):
@@ -224,6 +225,14 @@ Response.set_function = _response_set_function
 Response.convolve = _response_convolve
 Response.to_fits = _response_to_fits
 Response.from_fits = classmethod(_response_from_fits)
+
+
+def background_guide(cdf):
+    """float64 [NCHAN] guide of the device background-channel draw (include/cosmogrb_b200.h, CGRB_DT_BKG_GUIDE):
+    guide[m] = min(searchsorted(cdf, m / NCHAN, 'right'), NCHAN - 1) -- a start at or before the channel of every
+    u in [m / NCHAN, (m + 1) / NCHAN); the device walks forward from it (numpy's legacy ``choice``, background.py:93)"""
+    nc = len(cdf)
+    return np.minimum(np.searchsorted(cdf, np.arange(nc) / float(nc), "right"), nc - 1).astype("f8")
 
 
 def channel_search_guide(cumulative_matrix):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CGRB_ABI_VERSION 6
+#define CGRB_ABI_VERSION 7
 
 /* error codes */
 #define CGRB_OK 0
@@ -78,7 +78,9 @@ extern "C" {
 #define CGRB_DT_GUIDE (1720 + 140 * 128) /* [140*128] BYTES: guide[b][m] = searchsorted(cum[b], m/128, 'left')
                                            (0..128): the channel search for r starts at guide[b][floor(128 r)]
                                            and walks forward -- same result as a full search, ~2 probes    */
-#define CGRB_DT_SIZE (1720 + 140 * 128 + 140 * 128 / 8) /* 21880 doubles = 175040 B per detector        */
+#define CGRB_DT_BKG_GUIDE (1720 + 140 * 128 + 140 * 128 / 8) /* [128] guide of the background channel draw, stored as
+                                           doubles: guide[m] = min(searchsorted(bkg_cdf, m/128, 'right'), 127)      */
+#define CGRB_DT_SIZE (1720 + 140 * 128 + 140 * 128 / 8 + 128) /* 22008 doubles = 176064 B per detector  */
 
 /* one (GRB, detector) work unit; 224 bytes, device array uploaded by the caller */
 typedef struct {
@@ -267,14 +269,16 @@ int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                   const double *d_energy_src, uint8_t *d_pha_src, const cgrb_counts_t *d_counts,
                   void *stream);
 
-/* Background.sample_times + sample_channel (background.py:136-174; numba :13-44; numpy choice :93).
- * Work list: which=1, chunk=CGRB_SEG.  rng_chan is used for the channel draw in injected mode
- * (one uniform per event, incl. event 0); in Philox mode both come from one counter.
+/* Background.sample_times + sample_channel (background.py:136-174; numba :13-44; numpy choice :93), one pass:
+ * tiles of CGRB_BKG_TILE candidates, launched level-major over the units (no work list).  n_tiles: an upper bound
+ * on sum over the units with background of max(1, ceil(bkg_cap / CGRB_BKG_TILE)) (the grid size); d_workspace:
+ * cgrb_sample_background_workspace_bytes(n_units, n_tiles) bytes.  rng_chan is used for the channel draw in
+ * injected mode (one uniform per event, incl. event 0); in Philox mode both come from one counter.
  * counts: n_bkg, status. */
-int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
-                           const cgrb_work_t *d_work, int64_t n_work, const int64_t *d_unit_work_begin,
-                           const cgrb_rng_t *rng_time, const cgrb_rng_t *rng_chan,
-                           double *d_segsum, double *d_segstart,
+#define CGRB_BKG_TILE 2048
+int64_t cgrb_sample_background_workspace_bytes(int n_units, int64_t n_tiles);
+int cgrb_sample_background(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, int64_t n_tiles,
+                           const cgrb_rng_t *rng_time, const cgrb_rng_t *rng_chan, void *d_workspace,
                            double *d_times_bkg, uint8_t *d_pha_bkg, cgrb_counts_t *d_counts,
                            void *stream);
 

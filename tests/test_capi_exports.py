@@ -101,13 +101,15 @@ def test_detector_table_guide_and_layout():
     from cosmogrb_b200.response.response import channel_search_guide
 
     src = open(os.path.join(ROOT, "include", "cosmogrb_b200.h")).read()
-    assert _capi.DT_GUIDE == 1720 + 140 * 128 and _capi.DT_SIZE == _capi.DT_GUIDE + 140 * 128 // 8
-    assert f"#define CGRB_DT_SIZE (1720 + 140 * 128 + 140 * 128 / 8)" in src
+    assert _capi.DT_GUIDE == 1720 + 140 * 128 and _capi.DT_BKG_GUIDE == _capi.DT_GUIDE + 140 * 128 // 8
+    assert _capi.DT_SIZE == _capi.DT_BKG_GUIDE + 128
+    assert "#define CGRB_DT_BKG_GUIDE (1720 + 140 * 128 + 140 * 128 / 8)" in src
+    assert "#define CGRB_DT_SIZE (1720 + 140 * 128 + 140 * 128 / 8 + 128)" in src
     rsp = h.response("n0")
     tab = rsp.device_table(h.bkg_weights("n0"), "linear")
     assert tab.shape == (_capi.DT_SIZE,)
     cum = rsp.cumulative_matrix
-    g = tab[_capi.DT_GUIDE:].view(np.uint8).reshape(_capi.NBINS, _capi.NCHAN)
+    g = tab[_capi.DT_GUIDE:_capi.DT_BKG_GUIDE].view(np.uint8).reshape(_capi.NBINS, _capi.NCHAN)
     assert np.array_equal(g.reshape(-1), channel_search_guide(cum))
     rs = np.random.RandomState(0)
     r = rs.random_sample(20000)
