@@ -40,8 +40,9 @@ DT_G500_E = 720
 DT_G500_A = 1220
 DT_CUM = 1720
 DT_GUIDE = 1720 + NBINS * NCHAN           # NBINS*NCHAN bytes of uint8 search guides
-DT_BKG_GUIDE = DT_GUIDE + NBINS * NCHAN // 8    # NCHAN doubles: guide of the background channel draw
-DT_SIZE = DT_BKG_GUIDE + NCHAN
+BKG_GUIDE_N = 1024
+DT_BKG_GUIDE = DT_GUIDE + NBINS * NCHAN // 8    # BKG_GUIDE_N bytes: guide of the background channel draw
+DT_SIZE = DT_BKG_GUIDE + BKG_GUIDE_N // 8
 
 ST_SRC_CAPACITY = 1
 ST_BKG_CAPACITY = 2
@@ -187,7 +188,7 @@ def load():
     lib.cgrb_energy_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_energy_workspace_bytes.restype = i64
     lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
-    lib.cgrb_digitize.argtypes = [vp, vp, i32, vp, i64, rp, vp, vp, vp, vp]
+    lib.cgrb_digitize.argtypes = [vp, vp, i32, vp, i64, rp, vp, vp, vp, vp, vp]
     lib.cgrb_sample_background_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_sample_background_workspace_bytes.restype = i64
     lib.cgrb_sample_background.argtypes = [vp, vp, i32, i64, rp, rp, vp, vp, vp, vp, vp]

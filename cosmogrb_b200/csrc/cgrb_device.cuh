@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "../../include/cosmogrb_b200.h"
+#include "cgrb_logtab.cuh"
 
 namespace cgrb {
 
@@ -49,11 +50,54 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b)
     return __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)((a << 20) | (b >> 12))) - 1.0;
 }
 
+// -ln(u) for a positive normal double (the exponential gaps under Philox: u = u53(...) is a multiple of 2^-52).
+// u = 2^k z, z in [0.6875, 1.375) cut into 128 intervals by its top mantissa bits; the table holds 1 / c and ln c
+// of each interval's centre (scripts/make_logtab.py), so ln u = k ln2 + ln c + log1p(r) with r = z / c - 1 from one
+// fused multiply-add, |r| < 2^-7.8, and a degree-7 polynomial.  ~20 instructions against ~85 for log(); error
+// <= 1.5 ulp of max(|ln u|, 1) (checked by the generator against long-double logarithms and on the device
+// against log() in tests/test_gpu_guards.py).  u == 0 gives +inf like -log(0).  Injected uniforms keep log().
+__device__ __forceinline__ double neglog_fast(double u)
+{
+    const int hi = __double2hiint(u);
+    const int tmp = hi - 0x3FE60000;
+    const int k = tmp >> 20;
+    const double2 tc = __ldg(&CGRB_LOGTAB[(tmp >> 13) & 127]);
+    const double z = __hiloint2double(hi - (tmp & (int)0xFFF00000), __double2loint(u));
+    const double r = fma(z, tc.x, -1.0);
+    double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+    p = fma(p, r, 0.2);
+    p = fma(p, r, -0.25);
+    p = fma(p, r, 1.0 / 3.0);
+    p = fma(p, r, -0.5);
+    const double w = fma((double)k, 0.6931471805599453, tc.y);
+    const double v = -(w + fma(r * r, p, r));
+    return (u > 0.0) ? v : INFINITY;
+}
+
+// One Philox call carries a whole trial of the tabulated-envelope energy sampler: 48 bits for the proposal, 48 for
+// the height, 32 for the channel draw of the photon if this trial accepts it (independent bits of one output).
+// Uniforms in [0,1) with resolution 2^-48 / 2^-32, built like u53 (mantissa bits of a double in [1,2), minus one).
+__device__ __forceinline__ double u48(uint32_t a, uint32_t b16)
+{
+    return __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)((a << 20) | (b16 << 4))) - 1.0;
+}
+__device__ __forceinline__ double u32d(uint32_t a)
+{
+    return __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)(a << 20)) - 1.0;
+}
+struct TrialDraw {
+    double U, V, C;     // proposal, height, channel
+};
+__device__ __forceinline__ TrialDraw trial_draw(const Philox4 p)
+{
+    return TrialDraw{u48(p.x, p.y >> 16), u48(p.z, p.y & 0xffffu), u32d(p.w)};
+}
+
 // stages (Philox counter word 3)
 enum Stage : uint32_t {
     ST_SRC_TIME = 1,   // candidate k: xy -> gap uniform, zw -> acceptance uniform
-    ST_SRC_ENERGY = 2, // photon i, trial j: xy -> proposal, zw -> height
-    ST_SRC_CHAN = 3,   // photon i: xy -> channel uniform
+    ST_SRC_ENERGY = 2, // photon i, trial j: literal sampler xy -> proposal, zw -> height; envelope sampler: trial_draw
+    ST_SRC_CHAN = 3,   // photon i: xy -> channel uniform (stand-alone fold, photons of the literal loop)
     ST_BKG = 4,        // candidate k: xy -> gap uniform, zw -> channel uniform of event k+1
 };
 

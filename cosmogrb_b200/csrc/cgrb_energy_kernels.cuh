@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
                     if (FOLD)
                         pha_src[u.src_off + i] = (uint8_t)digitize_one(sm.edges, s_guide, cum, x, rng.seed, u.stream_id, i);
                     if (DIAG && trials_out)
-                        trials_out[u.src_off + i] = (int32_t)ntr;
+                        trials_out[u.src_off + i] = -(int32_t)ntr;      // negative: the literal loop (its channel comes from ST_SRC_CHAN)
                     my_trials += ntr;
                 }
             }
@@ -514,7 +514,8 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
         if (active) {
             const double *row = unit_rows + (size_t)k * ENV_ROW;
             Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
-            const double U = u53(p.x, p.y), V = u53(p.z, p.w);
+            const TrialDraw td = trial_draw(p);     // proposal, height and (if accepted) the channel from ONE call
+            const double U = td.U, V = td.V;
             const double y = U * total;
             // segment: row[lo] <= y < row[lo+1], walking forward from the row's guide
             int lo = unit_guides[k * CGRB_ENV_SEGS + min((int)(U * (double)CGRB_ENV_SEGS), CGRB_ENV_SEGS - 1)];
@@ -577,8 +578,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
                             b--;
                         if (b < 0)
                             b += CGRB_NBINS;                    // python negative index (x == emin)
-                        Philox4 pc = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_CHAN, (uint64_t)i, 0u);
-                        pha = nearest_cdf_guided(s_guide + b * CGRB_NCHAN, cum + (size_t)b * CGRB_NCHAN, u53(pc.x, pc.y));
+                        pha = nearest_cdf_guided(s_guide + b * CGRB_NCHAN, cum + (size_t)b * CGRB_NCHAN, td.C);
                     } else
                         pha = digitize_one(sm.edges, s_guide, cum, nan(""), rng.seed, u.stream_id, i);
                     pha_src[u.src_off + i] = (uint8_t)pha;

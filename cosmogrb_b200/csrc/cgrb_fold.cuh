@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(NT) k_digitize(const double *__restrict__ dtab
                                                  const cgrb_unit_t *__restrict__ units,
                                                  const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                  cgrb_rng_t rng, const double *__restrict__ energy_src,
+                                                 const int32_t *__restrict__ trials,
                                                  uint8_t *__restrict__ pha_src, const cgrb_counts_t *counts)
 {
     __shared__ __align__(128) uint8_t s_guide[GUIDE_BYTES];
@@ -176,7 +177,17 @@ __global__ void __launch_bounds__(NT) k_digitize(const double *__restrict__ dtab
 
     for (int64_t i = wk.start + threadIdx.x; i < chunk_end; i += NT) {
         const double e = energy_src[off + i];
-        if (rng.mode == 0)
+        if (rng.mode == 0 && trials && trials[off + i] > 0 && e == e) {
+            // a photon of the tabulated-envelope sampler: its channel uniform rides in the Philox call of the trial
+            // that accepted it (trial_draw), so the fused fold can be replayed here from the trial counts
+            int idx = lower_bound_255(s_edges, CGRB_NBINS + 1, e) - 1;
+            if (idx < 0)
+                idx += CGRB_NBINS;
+            idx = min(idx, CGRB_NBINS - 1);
+            const Philox4 p = philox_at(make_key(rng.seed), sid, ST_SRC_ENERGY, (uint64_t)i, (uint32_t)(trials[off + i] - 1));
+            pha_src[off + i] = (uint8_t)nearest_cdf_guided(s_guide + idx * CGRB_NCHAN, cum + (size_t)idx * CGRB_NCHAN,
+                                                           trial_draw(p).C);
+        } else if (rng.mode == 0)
             pha_src[off + i] = (uint8_t)digitize_one(s_edges, s_guide, cum, e, rng.seed, sid, i);
         else {
             int idx = lower_bound_255(s_edges, CGRB_NBINS + 1, e) - 1;        // searchsorted 'left', response.py:14

@@ -392,8 +392,8 @@ int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units
 }
 
 int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work,
-                  int64_t n_work, const cgrb_rng_t *rng, const double *d_energy_src, uint8_t *d_pha_src,
-                  const cgrb_counts_t *d_counts, void *stream)
+                  int64_t n_work, const cgrb_rng_t *rng, const double *d_energy_src, const int32_t *d_trials,
+                  uint8_t *d_pha_src, const cgrb_counts_t *d_counts, void *stream)
 {
     if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_energy_src || !d_pha_src ||
         !d_counts)
@@ -402,7 +402,7 @@ int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
     if (rc)
         return rc;
     LAUNCH("k_digitize", (cudaStream_t)stream, k_digitize<<<(unsigned)n_work, NT, 0, (cudaStream_t)stream>>>(d_dtab, d_units, d_work, n_work, *rng,
-                                                                     d_energy_src, d_pha_src, d_counts));
+                                                                     d_energy_src, d_trials, d_pha_src, d_counts));
     return check_launch("cgrb_digitize");
 }
 

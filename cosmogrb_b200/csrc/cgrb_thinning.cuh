@@ -162,9 +162,10 @@ __global__ void __launch_bounds__(NT) k_gap_prefix(const cgrb_unit_t *__restrict
         double g0 = 0.0, g1 = 0.0;
         if (j0 < n) {
             PairDraw d = pair_draw(rng, wk.unit, sid, stage, (wk.start + j0) >> 1, 0);
-            g0 = -(inv_f * log(d.a));                        // time - (1/fmax) * log(u)  cpl_functions.py:160
+            // time - (1/fmax) * log(u)  cpl_functions.py:160
+            g0 = (rng.mode == 0) ? inv_f * neglog_fast(d.a) : -(inv_f * log(d.a));
             if (j0 + 1 < n)
-                g1 = -(inv_f * log(d.b));
+                g1 = (rng.mode == 0) ? inv_f * neglog_fast(d.b) : -(inv_f * log(d.b));
             exhausted |= d.exhausted;
         }
         double total;
@@ -582,12 +583,13 @@ __global__ void __launch_bounds__(NT) k_background_plan(const cgrb_unit_t *__res
 #define BKG_R (BKG_TILE / (2 * NT))             // rounds: a thread owns one candidate PAIR per round (4)
 
 // np.searchsorted(cdf, u, 'right') clamped to the last channel (numpy's legacy choice, background.py:93), started
-// from the detector's guide (guide[m] = searchsorted(cdf, m / 128, 'right'), built with the table): ~2 probes.  The
-// 14 tables (1 KB + 128 B each) stay in L1: no staging, no barrier.
-__device__ __forceinline__ uint8_t bkg_channel_of(const double *__restrict__ cdf, const double *__restrict__ guide,
+// from the detector's guide (1024 bytes: guide[m] = searchsorted(cdf, m / 1024, 'right'), built with the table):
+// a guide cell holds a channel boundary one time in eight, so the walk is one probe, rarely two.  The 14 tables
+// (1 KB + 1 KB each) stay in L1: no staging, no barrier.
+__device__ __forceinline__ uint8_t bkg_channel_of(const double *__restrict__ cdf, const uint8_t *__restrict__ guide,
                                                   double uc)
 {
-    int j = (int)__ldg(guide + min(max((int)(uc * (double)CGRB_NCHAN), 0), CGRB_NCHAN - 1));
+    int j = (int)__ldg(guide + min(max((int)(uc * (double)CGRB_BKG_GUIDE_N), 0), CGRB_BKG_GUIDE_N - 1));
     while (j < CGRB_NCHAN - 1 && !(uc < __ldg(cdf + j)))
         j++;
     return (uint8_t)j;
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(NT, BKG_CTAS) k_background(const double *__res
     const int64_t start = (int64_t)tl.k * BKG_TILE;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double *cdf = dtab + (size_t)tl.det * CGRB_DT_SIZE + CGRB_DT_BKG_CDF;
-    const double *guide = dtab + (size_t)tl.det * CGRB_DT_SIZE + CGRB_DT_BKG_GUIDE;
+    const uint8_t *guide = reinterpret_cast<const uint8_t *>(dtab + (size_t)tl.det * CGRB_DT_SIZE + CGRB_DT_BKG_GUIDE);
     // the previous tile's end time, asked for now and needed after the gaps (level-major order: it is there)
     unsigned long long prev = BKG_NOT_READY;
     if (threadIdx.x == 0 && tl.k > 0)
@@ -628,9 +630,10 @@ __global__ void __launch_bounds__(NT, BKG_CTAS) k_background(const double *__res
         double g0 = 0.0, g1 = 0.0;
         if (j0 < n) {
             PairDraw d = pair_draw(rng, tl.unit, tl.sid, ST_BKG, (start + j0) >> 1, 0);
-            g0 = -(inv_f * log(d.a));                        // time - (1/rate) * log(u)  background.py:33
+            // time - (1/rate) * log(u)  background.py:33
+            g0 = (rng.mode == 0) ? inv_f * neglog_fast(d.a) : -(inv_f * log(d.a));
             if (j0 + 1 < n)
-                g1 = -(inv_f * log(d.b));
+                g1 = (rng.mode == 0) ? inv_f * neglog_fast(d.b) : -(inv_f * log(d.b));
             exhausted |= d.exhausted;
         }
         const double incl = warp_incl_scan(g0 + g1, lane);

@@ -628,7 +628,9 @@ class Engine(object):
         self.launches += 1
         return False
 
-    def digitize_batch(self, b, rng):
+    def digitize_batch(self, b, rng, trials=None):
+        """``Response.digitize`` of every photon.  ``trials`` (the envelope sampler's per-photon trial counts, Philox
+        only) replays the fold fused into ``sample_energy(fold=True)``: same channel uniforms, same channels."""
         torch = _torch()
         w, dw, _ = self._work(b, 3, DIGITIZE_CHUNK)
         t = b.t
@@ -637,7 +639,8 @@ class Engine(object):
         _capi.check(
             self.lib.cgrb_digitize(
                 b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w), C.byref(desc),
-                t["energy_src"].data_ptr(), t["pha_src"].data_ptr(), b.d_counts.data_ptr(), self.stream),
+                t["energy_src"].data_ptr(), trials.data_ptr() if trials is not None else None,
+                t["pha_src"].data_ptr(), b.d_counts.data_ptr(), self.stream),
             "cgrb_digitize")
         self.launches += 1
 
@@ -874,8 +877,8 @@ class Engine(object):
             t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + _capi.NCHAN] = np.arange(1, _capi.NCHAN + 1) / _capi.NCHAN
             from .response.response import background_guide
 
-            t[_capi.DT_BKG_GUIDE:_capi.DT_BKG_GUIDE + _capi.NCHAN] = background_guide(
-                t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + _capi.NCHAN])
+            t[_capi.DT_BKG_GUIDE:_capi.DT_BKG_GUIDE + _capi.BKG_GUIDE_N // 8] = background_guide(
+                t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + _capi.NCHAN]).view("f8")
             self._utab = [t]
         return self._utab
 

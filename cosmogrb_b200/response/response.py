@@ -128,7 +128,8 @@ class Response(object):
             t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + nc] = cdf
         else:
             t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + nc] = np.arange(1, nc + 1) / nc
-        t[_capi.DT_BKG_GUIDE:_capi.DT_BKG_GUIDE + nc] = background_guide(t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + nc])
+        t[_capi.DT_BKG_GUIDE:_capi.DT_BKG_GUIDE + _capi.BKG_GUIDE_N // 8] = background_guide(
+            t[_capi.DT_BKG_CDF:_capi.DT_BKG_CDF + nc]).view("f8")
         # 10**linspace(log10 emin, log10 emax, n): cpl_functions.py:208,305
         for n, oe, oa in ((_capi.NE_LAMBDA, _capi.DT_G75_E, _capi.DT_G75_A),
                           (_capi.NE_ENVELOPE, _capi.DT_G500_E, _capi.DT_G500_A)):
@@ -228,11 +229,11 @@ Response.from_fits = classmethod(_response_from_fits)
 
 
 def background_guide(cdf):
-    """float64 [NCHAN] guide of the device background-channel draw (include/cosmogrb_b200.h, CGRB_DT_BKG_GUIDE):
-    guide[m] = min(searchsorted(cdf, m / NCHAN, 'right'), NCHAN - 1) -- a start at or before the channel of every
-    u in [m / NCHAN, (m + 1) / NCHAN); the device walks forward from it (numpy's legacy ``choice``, background.py:93)"""
-    nc = len(cdf)
-    return np.minimum(np.searchsorted(cdf, np.arange(nc) / float(nc), "right"), nc - 1).astype("f8")
+    """uint8 [BKG_GUIDE_N] guide of the device background-channel draw (include/cosmogrb_b200.h, CGRB_DT_BKG_GUIDE):
+    guide[m] = min(searchsorted(cdf, m / N, 'right'), NCHAN - 1) -- a start at or before the channel of every
+    u in [m / N, (m + 1) / N); the device walks forward from it (numpy's legacy ``choice``, background.py:93)"""
+    n = _capi.BKG_GUIDE_N
+    return np.minimum(np.searchsorted(cdf, np.arange(n) / float(n), "right"), len(cdf) - 1).astype(np.uint8)
 
 
 def channel_search_guide(cumulative_matrix):

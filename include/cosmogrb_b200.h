@@ -78,8 +78,9 @@ extern "C" {
 #define CGRB_DT_GUIDE (1720 + 140 * 128) /* [140*128] BYTES: guide[b][m] = searchsorted(cum[b], m/128, 'left')
                                            (0..128): the channel search for r starts at guide[b][floor(128 r)]
                                            and walks forward -- same result as a full search, ~2 probes    */
-#define CGRB_DT_BKG_GUIDE (1720 + 140 * 128 + 140 * 128 / 8) /* [128] guide of the background channel draw, stored as
-                                           doubles: guide[m] = min(searchsorted(bkg_cdf, m/128, 'right'), 127)      */
+#define CGRB_DT_BKG_GUIDE (1720 + 140 * 128 + 140 * 128 / 8) /* [1024] BYTES: guide of the background channel draw,
+                                           guide[m] = min(searchsorted(bkg_cdf, m/1024, 'right'), 127)               */
+#define CGRB_BKG_GUIDE_N 1024
 #define CGRB_DT_SIZE (1720 + 140 * 128 + 140 * 128 / 8 + 128) /* 22008 doubles = 176064 B per detector  */
 
 /* one (GRB, detector) work unit; 224 bytes, device array uploaded by the caller */
@@ -263,11 +264,14 @@ int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units
                                 int32_t *d_trials, cgrb_counts_t *d_counts, void *stream);
 
 /* Response.digitize (response.py:156-174; numba _digitize :10-25): nearest-CDF channel.
- * Work list as for cgrb_sample_energy. */
+ * Work list as for cgrb_sample_energy.  d_trials (may be NULL; Philox only): the per-photon trial counts written by
+ * cgrb_sample_energy_envelope -- a photon with a positive count takes its channel uniform from the Philox call of
+ * the trial that accepted it, which replays the fold fused into that kernel; otherwise photon i draws from its own
+ * counter. */
 int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                   const cgrb_work_t *d_work, int64_t n_work, const cgrb_rng_t *rng,
-                  const double *d_energy_src, uint8_t *d_pha_src, const cgrb_counts_t *d_counts,
-                  void *stream);
+                  const double *d_energy_src, const int32_t *d_trials, uint8_t *d_pha_src,
+                  const cgrb_counts_t *d_counts, void *stream);
 
 /* Background.sample_times + sample_channel (background.py:136-174; numba :13-44; numpy choice :93), one pass:
  * tiles of CGRB_BKG_TILE candidates, launched level-major over the units (no work list).  n_tiles: an upper bound

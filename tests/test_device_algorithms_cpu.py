@@ -223,25 +223,34 @@ def test_merge_path_tiles_equal_the_reference_combine():
 
 def test_background_channel_guide_equals_numpy_choice():
     """k_background: channel = searchsorted(cdf, u, 'right') clamped to the last channel (numpy's legacy choice,
-    background.py:93), found from a 128-entry guide (guide[m] = searchsorted(cdf, m / 128, 'right')) and a forward
-    walk"""
+    background.py:93), found from the detector table's 1024-entry guide (guide[m] = searchsorted(cdf, m / 1024,
+    'right')) and a forward walk"""
     from tests import helpers as h
+    from cosmogrb_b200 import _capi
+    from cosmogrb_b200.response.response import background_guide
 
     rs = np.random.RandomState(9)
+    N = _capi.BKG_GUIDE_N
     for det in ("n0", "b1"):
         w = np.asarray(h.bkg_weights(det)).astype("f8")
         cdf = w.cumsum()
         cdf /= cdf[-1]
-        guide = np.minimum(np.searchsorted(cdf, np.arange(128) / 128.0, "right"), 127)
-        u = np.concatenate((rs.random_sample(50000), cdf[:-1], np.nextafter(cdf[:-1], 0), [0.0, np.nextafter(1.0, 0)]))
+        guide = background_guide(cdf)
+        tab = h.response(det).device_table(h.bkg_weights(det), "linear")
+        assert np.array_equal(tab[_capi.DT_BKG_GUIDE:_capi.DT_BKG_GUIDE + N // 8].view(np.uint8), guide)
+        u = np.concatenate((rs.random_sample(50000), cdf[:-1], np.nextafter(cdf[:-1], 0), np.arange(N) / float(N),
+                            [0.0, np.nextafter(1.0, 0)]))
         want = np.minimum(np.searchsorted(cdf, u, "right"), 127)
         got = np.empty(len(u), dtype=int)
+        steps = 0
         for k, uc in enumerate(u):
-            j = int(guide[min(max(int(uc * 128.0), 0), 127)])
+            j = int(guide[min(max(int(uc * float(N)), 0), N - 1)])
             while j < 127 and not (uc < cdf[j]):
                 j += 1
+                steps += 1
             got[k] = j
         assert np.array_equal(got, want)
+        assert steps < 0.5 * len(u)            # the walk rarely moves at all
 
 
 # ---- k_merge_deadtime (round 2): chain elements mark their followers inside a tile with halo ------------------------------

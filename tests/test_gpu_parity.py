@@ -321,9 +321,10 @@ def test_combine_and_dead_time_pipeline(engine):
     e = b.view("energy_src", 0, "src")
     assert np.all((e >= rsp.emin) & (e <= rsp.emax))
     # the fold fused into the energy kernel == the standalone digitize kernel on the same energies
-    # (same Philox counters), which in turn is the oracle's _digitize given the uniforms (test above)
+    # (same channel uniforms: they ride in the Philox call of the accepting trial, replayed from the trial counts),
+    # which in turn is the oracle's _digitize given the uniforms (test above)
     fused = b.view("pha_src", 0, "src").copy()
-    engine.digitize_batch(b, Philox(1234))
+    engine.digitize_batch(b, Philox(1234), trials=b.t["trials"])
     assert np.array_equal(fused, b.view("pha_src", 0, "src"))
     # re-derive the source channels with the oracle from the same Philox uniforms is not possible
     # (device counters), so check determinism instead: same seed -> identical output
@@ -375,3 +376,59 @@ def test_squeeze_changes_no_decision(params):
     assert out[False][1] == out[False][0]                 # without the table every candidate is exact
     assert out[True][1] < 0.05 * out[True][0], f"squeeze left {out[True][1]} of {out[True][0]} exact"
     assert np.array_equal(out[True][2], out[False][2])
+
+
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al. 2011) on uint32 arrays: csrc/cgrb_device.cuh philox4x32_10"""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(x, dtype=np.uint64) for x in np.broadcast_arrays(c0, c1, c2, c3))
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(M0) * c0, np.uint64(M1) * c2
+        c0, c1, c2, c3 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & m32, p1 & m32, ((p0 >> np.uint64(32)) ^ c3 ^ k1) & m32, p0 & m32
+        k0, k1 = (k0 + np.uint64(W0)) & m32, (k1 + np.uint64(W1)) & m32
+    return c0, c1, c2, c3
+
+
+def _u53(a, b):
+    """cgrb_device.cuh u53: the top 52 of 64 random bits as the mantissa of a double in [1, 2), minus one"""
+    bits = (np.uint64(0x3FF0000000000000) | ((a >> np.uint64(12)) << np.uint64(32)) | ((a << np.uint64(20)) & np.uint64(0xFFFFFFFF))
+            | (b >> np.uint64(12)))
+    return bits.view("f8") - 1.0
+
+
+def test_background_under_philox_equals_a_host_replay_of_the_counters(engine):
+    """The production background (one pass, fast logarithm, guided channel draw) against a NumPy replay of its
+    Philox counters: candidate pair m -> counter (m, 0) gives the two gap uniforms, (m, 1) the two channel uniforms
+    (cgrb_common.cuh pair_draw); times = tstart + running sum of -log(u) / rate (background.py:13-44), channels =
+    searchsorted(cdf, u, 'right') (numpy's legacy choice, :93).  Times agree to 1e-13 relative (the device's
+    logarithm and summation order differ from NumPy's in the last bits), channels and the count exactly."""
+    seed, sid, rate, t0, t1 = 0x1234ABCD5678, 37, 500.0, -100.0, 300.0
+    rsp = h.response("n0")
+    w = h.bkg_weights("n0")
+    u = h.unit(stream_id=sid, bkg=(t0, t1, rate), flags=_capi.UNIT_NO_SOURCE, **h.README_DEMO)
+    b = engine.new_batch(u, [rsp.device_table(w, "linear")], compute_fmax=False)
+    engine.sample_background(b, Philox(seed))
+    c = engine.fetch_counts(b)
+    engine.check_status(b)
+    got_t, got_p = b.view("times_bkg", 0, "bkg"), b.view("pha_bkg", 0, "bkg")
+    n_pairs = (int(b.units["bkg_cap"][0]) + 1) // 2
+    m = np.arange(n_pairs, dtype=np.uint64)
+    k0, k1 = seed & 0xFFFFFFFF, seed >> 32
+    x, y, z, ww = _philox4x32_10(m, 0, sid, 4, k0, k1)              # ST_BKG = 4
+    ug = np.stack((_u53(x, y), _u53(z, ww)), axis=1).reshape(-1)
+    x, y, z, ww = _philox4x32_10(m, 1, sid, 4, k0, k1)
+    uc = np.stack((_u53(x, y), _u53(z, ww)), axis=1).reshape(-1)
+    times = t0 + np.cumsum(-np.log(ug) / rate)
+    n = int(np.searchsorted(times, t1, "right"))
+    assert abs(int(c["n_bkg"][0]) - (n + 1)) <= 1                  # a time within 1e-13 of tstop may fall either side
+    n = int(c["n_bkg"][0]) - 1
+    assert got_t[0] == t0 and np.all(np.diff(got_t) >= 0)
+    np.testing.assert_allclose(got_t[1:], times[:n], rtol=1e-13, atol=1e-11)
+    cdf = np.asarray(w).astype("f8").cumsum()
+    cdf /= cdf[-1]
+    want_p = np.minimum(np.searchsorted(cdf, uc[:n], "right"), 127)
+    assert np.array_equal(got_p[1:].astype(int), want_p)
+    x, y, _, _ = _philox4x32_10(np.uint64(0xFFFFFFFF), 1, sid, 4 | (0xFF << 8), k0, k1)      # event 0: index 0xFFFFFFFFFF
+    assert int(got_p[0]) == min(int(np.searchsorted(cdf, _u53(x, y), "right")), 127)
