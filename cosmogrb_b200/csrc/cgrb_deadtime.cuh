@@ -357,53 +357,112 @@ struct MergedGlobal {
     }
 };
 
-// the literal dead-time rule for merged event g (same walk as dt_keep) on the slow accessor
+// Sequential cursor over the merged order of the two global lists: O(1) per step (one load: only the side that
+// moved is refilled) instead of a merge-path search per access.  Position g: the merged prefix [0, g) consists of
+// A[0, ia) and B[0, ib); ties: background (A) first, so the LAST element of a prefix is B[ib-1] when B[ib-1] >= A[ia-1].
+struct MergedCursor {
+    const double *A, *B;
+    const uint8_t *pA, *pB;
+    int64_t nA, nB, ia, ib;
+    double a_prev, b_prev;      // A[ia-1], B[ib-1] (-inf when there is none)
+    double a_next, b_next;      // A[ia], B[ib] (+inf when there is none)
+    __device__ __forceinline__ void seek(const MergedGlobal &m, int64_t g)
+    {
+        A = m.A, B = m.B, pA = m.pA, pB = m.pB, nA = m.nA, nB = m.nB;
+        ia = merge_split(A, nA, B, nB, g);
+        ib = g - ia;
+        a_prev = ia > 0 ? A[ia - 1] : -INFINITY;
+        b_prev = ib > 0 ? B[ib - 1] : -INFINITY;
+        a_next = ia < nA ? A[ia] : INFINITY;
+        b_next = ib < nB ? B[ib] : INFINITY;
+    }
+    __device__ __forceinline__ int64_t pos() const { return ia + ib; }
+    // step back: returns merged event pos() - 1 and moves there (caller guarantees pos() > 0)
+    __device__ __forceinline__ void prev(double *t, uint8_t *p)
+    {
+        if (ib > 0 && (ia == 0 || b_prev >= a_prev)) {
+            ib--;
+            *t = b_prev;
+            *p = pB[ib];
+            b_next = b_prev;
+            b_prev = ib > 0 ? B[ib - 1] : -INFINITY;
+        } else {
+            ia--;
+            *t = a_prev;
+            *p = pA[ia];
+            a_next = a_prev;
+            a_prev = ia > 0 ? A[ia - 1] : -INFINITY;
+        }
+    }
+    // step forward: returns merged event pos() and moves past it (caller guarantees pos() < nA + nB)
+    __device__ __forceinline__ void next(double *t, uint8_t *p)
+    {
+        if (ia < nA && (ib >= nB || a_next <= b_next)) {
+            *t = a_next;
+            *p = pA[ia];
+            ia++;
+            a_prev = a_next;
+            a_next = ia < nA ? A[ia] : INFINITY;
+        } else {
+            *t = b_next;
+            *p = pB[ib];
+            ib++;
+            b_prev = b_next;
+            b_next = ib < nB ? B[ib] : INFINITY;
+        }
+    }
+};
+
+// the literal dead-time rule for merged event i (same walk as dt_keep) on the global lists: one backward pass to
+// the head of the chain -- the chain elements met on the way are exactly the overflow events between the head and
+// i, because every inner walk stops at the first one -- then one forward pass from the head
 __device__ __noinline__ bool dt_keep_slow(const MergedGlobal &m, int64_t i)
 {
     if (i == 0)
         return true;
-    double ti, tj;
-    uint8_t pi, pj;
-    m.get(i, &ti, &pi);
+    MergedCursor c;
+    c.seek(m, i + 1);
+    double ti, tj = 0.0;
+    uint8_t pi, pj = 0;
+    c.prev(&ti, &pi);                       // event i; the cursor now stands at i
     int64_t found = -1;
-    for (int64_t j = i - 1; j >= 0; j--) {
-        m.get(j, &tj, &pj);
+    while (c.pos() > 0) {
+        c.prev(&tj, &pj);
         if (tj + DT_TAU < ti)
             break;
-        if (pj == 127 || j == 0) {
-            found = j;
+        if (pj == 127 || c.pos() == 0) {
+            found = c.pos();
             break;
         }
     }
     if (found < 0)
         return true;
     int64_t head = found;
+    double th = tj;
+    uint8_t ph = pj;
     while (head > 0) {
-        double th;
-        uint8_t ph;
-        m.get(head, &th, &ph);
         int64_t q = -1;
         double tq = 0.0;
         uint8_t pq = 0;
-        for (int64_t j = head - 1; j >= 0; j--) {
-            m.get(j, &tq, &pq);
+        while (c.pos() > 0) {
+            c.prev(&tq, &pq);
             if (tq + DT_TAU < th)
                 break;
-            if (pq == 127 || j == 0) {
-                q = j;
+            if (pq == 127 || c.pos() == 0) {
+                q = c.pos();
                 break;
             }
         }
         if (q < 0 || tq + ((q == 0 && pq != 127) ? DT_NORMAL : DT_TAU) < th)
             break;
         head = q;
+        th = tq;
+        ph = pq;
     }
-    double th;
-    uint8_t ph;
-    m.get(head, &th, &ph);
     double t_end = th + ((head == 0 && ph != 127) ? DT_NORMAL : DT_TAU);
+    c.seek(m, head + 1);
     for (int64_t j = head + 1; j < i; j++) {
-        m.get(j, &tj, &pj);
+        c.next(&tj, &pj);
         if (pj == 127 && tj > t_end)
             t_end = tj + DT_TAU;
     }
@@ -472,7 +531,11 @@ __device__ __forceinline__ int dt_keep_local(const double *t, const uint8_t *p, 
 #ifndef MD_HALO
 #define MD_HALO 64              // look-back events staged in front of a tile (a multiple of 32)
 #endif
-#define MD_N (MD_TILE + MD_HALO)
+#ifndef MD_HALO_DENSE
+#define MD_HALO_DENSE 512       // the same for a tile whose events come more than MD_DENSE to the longest window
+#endif
+#define MD_DENSE 8
+#define MD_N (MD_TILE + MD_HALO_DENSE)
 
 // Per-tile records, one thread per ticket: the ~23 dependent probes of each merge-path search are hidden by the
 // other tiles' searches, and a CTA of the one-pass kernel gets everything about its tile from ONE 64-byte record.
@@ -485,7 +548,7 @@ struct MdTile {
     int32_t nt;                 // the tile's own events
     int32_t unit;
     uint32_t flags;             // MDT_*
-    int32_t pad;
+    int32_t l0;                 // look-back events staged in front of the tile (0, MD_HALO or MD_HALO_DENSE)
 };
 static_assert(sizeof(MdTile) == 64, "MdTile is one 64-byte record");
 #define MDT_LIVE 1u
@@ -503,7 +566,7 @@ __global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict
         return;
     MdTile t;
     t.a_off = t.b_off = t.wb = t.d0 = t.tot_off = 0;
-    t.na = t.nb = t.nt = t.unit = t.pad = 0;
+    t.na = t.nb = t.nt = t.unit = t.l0 = 0;
     t.flags = 0u;
     int unit, lo;
     if (level_ticket(o, T, &unit, &lo)) {
@@ -514,10 +577,23 @@ __global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict
         const double *A = times_bkg + u->bkg_off;
         const double *B = times_src + u->src_off;
         const int64_t d1 = min(d0 + (int64_t)MD_TILE, total);
-        const int64_t g0 = max((int64_t)0, d0 - MD_HALO);       // first merged rank held in shared memory
-        const int64_t i0 = merge_split(A, nA, B, nB, g0);
+        int64_t g0 = max((int64_t)0, d0 - MD_HALO);             // first merged rank held in shared memory
+        int64_t i0 = merge_split(A, nA, B, nB, g0);
         const int64_t i1 = (d1 == total) ? nA : merge_split(A, nA, B, nB, d1);
-        const int64_t j0 = g0 - i0;
+        int64_t j0 = g0 - i0;
+        if (d0 > MD_HALO) {
+            // A dense tile -- more than MD_DENSE events to the longest dead-time window, the peak of a very bright
+            // burst -- gets a longer halo: its chains of overflow events reach back hundreds of events, and a walk
+            // that leaves the halo goes to the global lists (exact, but slow).  Speed only: any halo is correct.
+            const int64_t j1 = d1 - i1;
+            const double t_first = fmin(i0 < nA ? A[i0] : INFINITY, j0 < nB ? B[j0] : INFINITY);
+            const double t_last = fmax(i1 > 0 ? A[i1 - 1] : -INFINITY, j1 > 0 ? B[j1 - 1] : -INFINITY);
+            if ((t_last - t_first) * (double)MD_DENSE < (double)(d1 - g0) * DT_TAU) {
+                g0 = max((int64_t)0, d0 - MD_HALO_DENSE);
+                i0 = merge_split(A, nA, B, nB, g0);
+                j0 = g0 - i0;
+            }
+        }
         t.a_off = u->bkg_off + i0;
         t.b_off = u->src_off + j0;
         t.wb = unit_work_begin[unit];
@@ -526,6 +602,7 @@ __global__ void __launch_bounds__(NT) k_merge_plan(const cgrb_unit_t *__restrict
         t.na = (int32_t)(i1 - i0);
         t.nb = (int32_t)((d1 - i1) - j0);
         t.nt = (int32_t)(d1 - d0);
+        t.l0 = (int32_t)(d0 - g0);
         t.unit = unit;
         t.flags = MDT_LIVE | (g0 == 0 ? MDT_HAS0 : 0u) | (d1 == total ? MDT_LAST : 0u);
     }
@@ -642,6 +719,8 @@ __device__ __noinline__ void md_merge_insertion(MdSmem &sm, int na, int nb, int 
     int mdest = 0;
 #pragma unroll
     for (int r = 0; r < MD_PER; r++) {
+        if (r * NT >= nj)                       // (uniform: the last round only exists under the long halo)
+            break;
         const int k = r * NT + tid;
         rt[r] = (k < nj) ? J[k] : 0.0;
         rp[r] = (k < nj) ? pJ[k] : 0;
@@ -676,6 +755,8 @@ __device__ __noinline__ void md_merge_insertion(MdSmem &sm, int na, int nb, int 
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < MD_PER; r++) {
+        if (r * NT >= nj)
+            break;
         const int k = r * NT + tid;
         if (k < nj) {
             const int c1 = sm.cblk[(k >> 5) + 1];
@@ -700,7 +781,8 @@ __device__ __noinline__ void md_merge_general(MdSmem &sm, int na, int nb, int ta
     // registers
     const double *a_ = sm.t + ta, *b_ = sm.t + tb;
     const uint8_t *pa_ = sm.p + qa, *pb_ = sm.p + qb;
-    const int q0 = min(tid * MD_PER, n);
+    const int per = (n + NT - 1) / NT;          // <= MD_PER; 9 under the short halo
+    const int q0 = min(tid * per, n);
     int lo = max(0, q0 - nb), hi = min(q0, na);
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -716,6 +798,8 @@ __device__ __noinline__ void md_merge_general(MdSmem &sm, int na, int nb, int ta
     for (int r = 0; r < MD_PER; r++) {
         rt[r] = 0.0;
         rp[r] = 0;
+        if (r >= per)
+            break;
         if (q0 + r < n) {
             const bool take_a = ia < na && (ib >= nb || a_[ia] <= b_[ib]);
             rt[r] = take_a ? a_[ia] : b_[ib];
@@ -727,7 +811,7 @@ __device__ __noinline__ void md_merge_general(MdSmem &sm, int na, int nb, int ta
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < MD_PER; r++)
-        if (q0 + r < n) {
+        if (r < per && q0 + r < n) {
             sm.t[q0 + r] = rt[r];
             sm.p[q0 + r] = rp[r];
         }
@@ -784,7 +868,7 @@ __global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_
     __syncthreads();
     const int na = tile.na, nb = tile.nb, n = na + nb;      // n = halo + tile <= MD_N
     const int64_t d0 = tile.d0;
-    const int l0 = (int)min(d0, (int64_t)MD_HALO), nt = tile.nt;     // l0 is 0 or MD_HALO
+    const int l0 = tile.l0, nt = tile.nt;                   // l0 is 0, MD_HALO or MD_HALO_DENSE
     const int unit = tile.unit;
     const bool has0 = (tile.flags & MDT_HAS0) != 0;
     // ---- 0. staging: slice A at t[ta + k] / p[qa + k], slice B at t[tb + k] / p[qb + k]; shared and global
@@ -853,13 +937,12 @@ __global__ void __launch_bounds__(NT, MD_CTAS) k_merge_deadtime(const cgrb_unit_
     const int e0 = wid * (32 * MD_R) + lane;    // tile element of round 0
     unsigned keep_bits = 0;                     // bit r: the event of round r survives
     if (MODE == 0) {
-        if (tid < l0) {
+        for (int h = tid; h < l0; h += NT) {
             // halo: its overflow events, and its first event in place of whatever lies before the halo
-            if (tid == 0 || P[tid] == 127) {
-                const double te = T[tid] + DT_TAU;
-                for (int k = tid + 1; k < n && !(te < T[k]); k++)
-                    if (k >= l0)
-                        atomicOr(&sm.rare[k >> 5], 1u << (k & 31));
+            if (h == 0 || P[h] == 127) {
+                const double te = T[h] + DT_TAU;
+                for (int k = max(h + 1, l0); k < n && !(te < T[k]); k++)
+                    atomicOr(&sm.rare[k >> 5], 1u << (k & 31));
             }
         }
         unsigned chain_bits = 0;                // bit r: the event of round r is a chain element

@@ -612,7 +612,7 @@ int64_t cgrb_gbm_trigger_workspace_bytes(int n_units, int64_t bins_per_unit)
     if (n_units <= 0 || bins_per_unit <= 0)
         return 0;
     const int64_t nu = n_units;
-    return nu * TRIG_NARR * bins_per_unit * 4 + nu * 4 * (bins_per_unit + 1) * 8 + nu * (bins_per_unit + 1) * 8 + 256;
+    return nu * TRIG_NARR * bins_per_unit * 4 + nu * 4 * (bins_per_unit + 1) * 4 + nu * (bins_per_unit + 1) * 8 + 768;
 }
 
 int cgrb_gbm_trigger(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
@@ -629,8 +629,8 @@ int cgrb_gbm_trigger(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t 
     const int64_t nu = n_units;
     int32_t *bins = (int32_t *)d_workspace;
     const size_t bins_bytes = (size_t)nu * TRIG_NARR * bins_per_unit * 4;
-    int64_t *csum = (int64_t *)((char *)d_workspace + ((bins_bytes + 255) / 256) * 256);
-    double *esum = (double *)(csum + nu * 4 * (bins_per_unit + 1));
+    int32_t *csum = (int32_t *)((char *)d_workspace + ((bins_bytes + 255) / 256) * 256);
+    double *esum = (double *)((char *)csum + (((size_t)nu * 4 * (bins_per_unit + 1) * 4 + 255) / 256) * 256);
     cudaError_t e = cudaMemsetAsync(bins, 0, bins_bytes, s);
     if (e != cudaSuccess)
         return fail(CGRB_E_CUDA, "cgrb_gbm_trigger: memset: %s", cudaGetErrorString(e));

@@ -48,7 +48,10 @@ __device__ __forceinline__ TrigGrid trig_grid(double tmin, double tmax, double d
 // Shared-memory histogram of a tile, three packed words per bin (a tile holds TRIG_TILE events, so every 16-bit
 // field stays below 2 x TRIG_TILE < 65536): word 0 = range a | range b << 16, word 1 = range c | range d << 16,
 // word 2 = events | overflow events << 16 (the two dead-time counters).
-__global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__ units,
+#ifndef TRIG_BIN_CTAS
+#define TRIG_BIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(NT, TRIG_BIN_CTAS) k_trig_bin(const cgrb_unit_t *__restrict__ units,
                                                  const cgrb_work_t *__restrict__ work, int64_t n_work,
                                                  const int32_t *__restrict__ chan_bounds, double dt,
                                                  const double *__restrict__ times_out,
@@ -196,24 +199,52 @@ __global__ void __launch_bounds__(NT) k_trig_bin(const cgrb_unit_t *__restrict__
     }
     }
     __syncthreads();
-    if (local)
-        for (int j = threadIdx.x; j < 3 * TRIG_LOCAL; j += NT) {
-            const int a = j / TRIG_LOCAL, l = j % TRIG_LOCAL;
-            const int v = s_h[a][l];
-            if (v && k0 + l < nb) {
-                const int lo = v & 0xffff, hi = (int)((unsigned)v >> 16);
-                if (lo)
-                    atomicAdd(ub + (2 * a) * bins_per_unit + k0 + l, lo);
-                if (hi)
-                    atomicAdd(ub + (2 * a + 1) * bins_per_unit + k0 + l, hi);
+    if (local) {
+        // The list is time-sorted, so the tile shares bins with its neighbours only at its two ends: the bin of its
+        // first event (and the one below it: the inclusive dead-time edge) with the tiles before it, every bin from
+        // the one below the NEXT tile's first event on with the tiles after it.  Those take atomics on the zeroed
+        // arrays; every bin strictly in between belongs to this tile alone and is stored plainly, zeros included
+        // (coalesced, one store per array and bin instead of up to six atomics).
+        const int ka_own = k0 + 2;                              // first bin no earlier tile can touch
+        int kb_own = nb;                                        // first bin a later tile can touch
+        if (end < n) {
+            const int kn = bin_of(t[end]);
+            kb_own = (kn < 0) ? nb : max(kn - 1, 0);
+        }
+        for (int l = threadIdx.x; l < TRIG_LOCAL; l += NT) {
+            const int k = k0 + l;
+            if (k >= nb)
+                break;
+            const int v0 = s_h[0][l], v1 = s_h[1][l], v2 = s_h[2][l];
+            if (k >= ka_own && k < kb_own) {
+                ub[0 * bins_per_unit + k] = v0 & 0xffff;
+                ub[1 * bins_per_unit + k] = (int)((unsigned)v0 >> 16);
+                ub[2 * bins_per_unit + k] = v1 & 0xffff;
+                ub[3 * bins_per_unit + k] = (int)((unsigned)v1 >> 16);
+                ub[4 * bins_per_unit + k] = v2 & 0xffff;
+                ub[5 * bins_per_unit + k] = (int)((unsigned)v2 >> 16);
+            } else if (v0 | v1 | v2) {
+                if (v0 & 0xffff)
+                    atomicAdd(ub + 0 * bins_per_unit + k, v0 & 0xffff);
+                if ((unsigned)v0 >> 16)
+                    atomicAdd(ub + 1 * bins_per_unit + k, (int)((unsigned)v0 >> 16));
+                if (v1 & 0xffff)
+                    atomicAdd(ub + 2 * bins_per_unit + k, v1 & 0xffff);
+                if ((unsigned)v1 >> 16)
+                    atomicAdd(ub + 3 * bins_per_unit + k, (int)((unsigned)v1 >> 16));
+                if (v2 & 0xffff)
+                    atomicAdd(ub + 4 * bins_per_unit + k, v2 & 0xffff);
+                if ((unsigned)v2 >> 16)
+                    atomicAdd(ub + 5 * bins_per_unit + k, (int)((unsigned)v2 >> 16));
             }
         }
+    }
 }
 
 // The exact significance test of one (window start i, gap) pair, from the 64-bit prefix sums in global memory
 // (rare: only windows the fp32 prefilter could not rule out).  sig = (S - a B) / sqrt(a B), a = ex / eb, decided
 // without the divisions when clear.  Returns 1 if sig >= thr; *razor is set when sig is within 1e-9 of thr.
-__device__ __noinline__ int trig_exact(const int64_t *__restrict__ cr, const double *__restrict__ es, int64_t i,
+__device__ __noinline__ int trig_exact(const int32_t *__restrict__ cr, const double *__restrict__ es, int64_t i,
                                        int64_t n_bkg, int64_t n_gap, int64_t n_src, double thr, int *razor)
 {
     const int64_t gs = i + n_bkg + n_gap;
@@ -234,6 +265,25 @@ __device__ __noinline__ int trig_exact(const int64_t *__restrict__ cr, const dou
     return sig >= thr ? 1 : 0;
 }
 
+// One (window start, time scale) pair that survived the source-window filter: the fp32 test on the staged prefix
+// sums (B from the global 32-bit prefix: the staged one has been turned into window sums by then), then the exact
+// one.  Out of line: a few windows per light curve come here.  Returns 1 on a hit.
+__device__ __noinline__ int trig_detail(const int32_t *__restrict__ cr, const double *__restrict__ es,
+                                        const float *s_ef, int li, int64_t i, int nbk, int nsr, int n_gap, float Sf,
+                                        bool use_pre, float min_eb, float min_ex, float thr2f, double thr, int *razor)
+{
+    const float *pe = s_ef + li + nbk;
+    const float ebf = pe[0] - s_ef[li];
+    const float Bf = (float)(cr[i + nbk] - cr[i]);
+    if (use_pre && Bf > 0.0f && ebf > min_eb) {
+        const float exf = pe[nsr + n_gap] - pe[n_gap];
+        const float d32 = Sf * ebf - Bf * exf;
+        if (exf > min_ex && (d32 <= 0.0f || d32 * d32 < 0.9f * thr2f * Bf * ebf * exf))
+            return 0;
+    }
+    return trig_exact(cr, es, i, nbk, n_gap, nsr, thr, razor);
+}
+
 #define TRIG_LOSS_N 4096
 #ifndef TRIG_PB
 #define TRIG_PB 4               // bins per thread and round in the prefix pass
@@ -246,7 +296,7 @@ __device__ __noinline__ int trig_exact(const int64_t *__restrict__ cr, const dou
 __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_unit_t *__restrict__ units, int n_units,
                                                   cgrb_trigger_par_t par, const double *__restrict__ times_out,
                                                   const cgrb_counts_t *__restrict__ counts, int64_t bins_per_unit,
-                                                  const int32_t *__restrict__ bins, int64_t *__restrict__ csum,
+                                                  const int32_t *__restrict__ bins, int32_t *__restrict__ csum,
                                                   double *__restrict__ esum, cgrb_trigger_t *__restrict__ out)
 {
     const int ui = blockIdx.x;
@@ -272,13 +322,16 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     const TrigGrid g = trig_grid(t[0], t[n - 1], dt);
     const int64_t nb = g.n_edges - 1;
     res.n_bins = (int32_t)max((int64_t)0, min(nb, (int64_t)0x7fffffff));
-    if (nb < 1 || nb >= 0x7fffffff) {
-        if (threadIdx.x == 0)
+    if (nb < 1 || nb >= 0x7fffffff || n > 0x7fffffff) {      // (the count prefix sums are 32-bit: <= n_kept)
+        if (threadIdx.x == 0) {
+            if (n > 0x7fffffff)
+                res.razor = 2;
             out[ui] = res;
+        }
         return;
     }
     const int32_t *ub = bins + (size_t)ui * TRIG_NARR * bins_per_unit;
-    int64_t *cs = csum + (size_t)ui * 4 * (bins_per_unit + 1);
+    int32_t *cs = csum + (size_t)ui * 4 * (bins_per_unit + 1);
     double *es = esum + (size_t)ui * (bins_per_unit + 1);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // prefix sums: counts after the reference's float round trip, exposures = (stop - start) - dead time.
@@ -297,7 +350,7 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         if ((int)(__dmul_rn(__ddiv_rn((double)c, dt), dt)) < c)
             atomicOr(&s_loss[c >> 5], 1u << (c & 31));
     __syncthreads();
-    long long carry_c[4] = {0, 0, 0, 0};
+    int carry_c[4] = {0, 0, 0, 0};
     double carry_e = 0.0;
     if (threadIdx.x == 0) {
         for (int r = 0; r < 4; r++)
@@ -373,7 +426,7 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
                 es[kf + j + 1] = off_e + e[j];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const long long off_c = carry_c[r] + (long long)(before_c[r] + ic[r] - c[r][TRIG_PB - 1]);
+            const int off_c = carry_c[r] + (before_c[r] + ic[r] - c[r][TRIG_PB - 1]);
 #pragma unroll
             for (int j = 0; j < TRIG_PB; j++)
                 if (kf + j < nb)
@@ -388,8 +441,10 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     // (+ the longest window span) are staged in shared memory as fp32 relative to the chunk start; all time
     // scales of a range share the background window of a given i.
     __shared__ float s_ef[TRIG_CH + TRIG_SPAN + 1];     // exposure prefix
-    __shared__ float s_cf[TRIG_CH + TRIG_SPAN + 1];     // count prefix (exact in fp32 below 2^24)
+    __shared__ float s_cf[TRIG_CH + TRIG_SPAN + 1];     // count prefix (exact in fp32 below 2^24), then window sums
+    __shared__ float s_need[TRIG_CH];                   // per window start: the source-window sum a hit needs at least
     __shared__ long long s_hit[10];
+    __shared__ float s_min[NW];
     const int n_scales[4] = {10, 10, 9, 4};
     const int64_t n_bkg = (int64_t)floor(par.background_duration / dt);
     const int64_t n_src = (int64_t)floor(par.pre_window / dt);          // the "source" window (swapped arguments)
@@ -400,10 +455,14 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     const bool staged_ok = (n_bkg + 512 + n_src <= TRIG_SPAN) && n_bkg > 0 && n_src > 0;
     const bool pre_params_ok = (thr >= 1.0) && (thr < 1e15) && (n_src <= n_bkg);
     const float thr2f = (float)(thr * thr);
+    const float thr_lo = 0.94f * (float)thr;                            // < sqrt(0.9) thr: the margin of the fp32 test
     const float min_eb = 0.25f * (float)((double)n_bkg * dt), min_ex = 0.25f * (float)((double)n_src * dt);
     const int nbk = (int)n_bkg, nsr = (int)n_src;
+    constexpr int TRIG_IPT = TRIG_CH / NT;                              // window starts per thread and chunk (8)
+    constexpr int TRIG_XPT = (TRIG_CH + TRIG_SPAN + NT) / NT;           // staged elements per thread (16)
+#pragma unroll 1
     for (int r = 0; r < 4 && !found && staged_ok; r++) {
-        const int64_t *cr = cs + r * (bins_per_unit + 1);
+        const int32_t *cr = cs + r * (bins_per_unit + 1);
         if (cr[nb] == 0)                                                  // `if sum(counts) == 0: continue`
             continue;
         const int ns = n_scales[r];
@@ -413,22 +472,22 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         for (int64_t c0 = 0; c0 < n_i_max; c0 += TRIG_CH) {
             __syncthreads();
             const int64_t hi = min(nb, c0 + TRIG_CH + TRIG_SPAN);
-            const long long cbase = cr[c0];
+            const int cbase = cr[c0];
             const double ebase = es[c0];
             // Nearly every window is far below the threshold: that is decided in fp32 (full rate, no 64-bit
             // conversions).  A hit needs d = S eb - B ex >= thr sqrt(B ex eb); the fp32 value of d is off by at
             // most ~3e-6 (S eb + B ex), i.e. by < 2.5 % of d for any window that could fire (counts < 2^24 so
             // that they are exact in fp32, thr >= 1, source window not longer than the background window), so
             // d^2 < 0.9 thr^2 B ex eb is a certain miss.  Everything else takes the exact path.
-            const bool use_pre = pre_params_ok && (cr[hi] - cbase) < (1ll << 24);
+            const bool use_pre = pre_params_ok && (cr[hi] - cbase) < (1 << 24);
+            const int n_st = (int)(hi - c0) + 1;
             {
                 // loads batched four deep: the staging is latency-bound otherwise
-                const int n_st = (int)(hi - c0) + 1;
                 const double *ep = es + c0;
-                const int64_t *cp = cr + c0;
+                const int32_t *cp = cr + c0;
                 for (int k = threadIdx.x; k < n_st; k += 4 * NT) {
                     double ev[4];
-                    long long cv[4];
+                    int cv[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const int kk = min(k + q * NT, n_st - 1);
@@ -440,7 +499,7 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
                         const int kk = k + q * NT;
                         if (kk < n_st) {
                             s_ef[kk] = (float)(ev[q] - ebase);
-                            s_cf[kk] = (float)(int)min(cv[q] - cbase, (long long)(1 << 24));
+                            s_cf[kk] = (float)min(cv[q] - cbase, 1 << 24);
                         }
                     }
                 }
@@ -449,28 +508,81 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
             const int i_end = (int)(min(c0 + (int64_t)TRIG_CH, n_i_max) - c0);
             // window i with gap n_gap exists iff i + n_bkg + n_gap + n_src < nb, i.e. n_gap < room(i)
             const int64_t room0 = nb - n_bkg - n_src - c0;
+            // Level 0 of the filter works on the source-window sums alone.  A hit needs
+            //     S >= a B + thr sqrt(a B),   a = ex / eb,
+            // and the right-hand side grows with a, so with ex_min = the smallest source-window exposure staged
+            // in this chunk no window starting at i can fire unless S >= S_min(i) = a_min B + 0.94 thr sqrt(a_min B),
+            // a_min = ex_min / eb(i) (0.94 < sqrt(0.9): the same margin as the fp32 test below, which every
+            // survivor still takes, and then the exact one).  One load and one compare per (window, time scale).
+            // (a) ex_min, and each thread's S_min for its TRIG_IPT window starts; (b) the count prefix becomes the
+            // array of source-window sums S(m) = C(m + n_src) - C(m), in place through registers.
+            float exm = INFINITY;
+            float sw[TRIG_XPT];
+#pragma unroll
+            for (int q = 0; q < TRIG_XPT; q++) {
+                const int m = threadIdx.x + q * NT;
+                sw[q] = 0.0f;
+                if (m + nsr < n_st) {
+                    sw[q] = s_cf[m + nsr] - s_cf[m];
+                    if (m >= nbk)
+                        exm = fminf(exm, s_ef[m + nsr] - s_ef[m]);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1)
+                exm = fminf(exm, __shfl_xor_sync(0xffffffffu, exm, d));
+            if (lane == 0)
+                s_min[wid] = exm;
+            float smin[TRIG_IPT];
+#pragma unroll
+            for (int q = 0; q < TRIG_IPT; q++) {
+                const int li = threadIdx.x + q * NT;
+                smin[q] = -INFINITY;
+                if (li < i_end) {
+                    const float Bf = s_cf[li + nbk] - s_cf[li];
+                    const float ebf = s_ef[li + nbk] - s_ef[li];
+                    if (use_pre && Bf > 0.0f && ebf > min_eb)
+                        smin[q] = Bf / ebf;             // times ex_min below
+                }
+            }
+            __syncthreads();
+            exm = s_min[0];
+#pragma unroll
+            for (int q = 1; q < NW; q++)
+                exm = fminf(exm, s_min[q]);
+            const bool lvl0 = exm > min_ex && exm < INFINITY;
+#pragma unroll
+            for (int q = 0; q < TRIG_XPT; q++) {
+                const int m = threadIdx.x + q * NT;
+                if (m + nsr < n_st)
+                    s_cf[m] = sw[q];
+            }
+#pragma unroll
+            for (int q = 0; q < TRIG_IPT; q++) {
+                float need = -INFINITY;
+                if (lvl0 && smin[q] > 0.0f) {
+                    const float ab = smin[q] * exm;     // a_min B
+                    need = ab * 0.99999f + thr_lo * sqrtf(ab);
+                }
+                s_need[threadIdx.x + q * NT] = need;
+            }
+            __syncthreads();
+#pragma unroll 1
             for (int li = threadIdx.x; li < i_end; li += NT) {
                 const int room = (int)min(room0 - li, (int64_t)1024);
-                const float Bf = s_cf[li + nbk] - s_cf[li];
-                const float ebf = s_ef[li + nbk] - s_ef[li];
-                const bool pre_i = use_pre && Bf > 0.0f && ebf > min_eb;
-                const float kf = 0.9f * thr2f * Bf * ebf;
-                const float *pc = s_cf + li + nbk, *pe = s_ef + li + nbk;
-                const float *pcs = pc + nsr, *pes = pe + nsr;
+                const float need = s_need[li];
+                const float *ps = s_cf + li + nbk;
 #pragma unroll
                 for (int gx = 9; gx >= 0; gx--) {
                     const int n_gap = 1 << gx;
                     if (gx >= ns || n_gap >= room)
                         continue;
-                    if (pre_i) {
-                        const float exf = pes[n_gap] - pe[n_gap];
-                        const float Sf = pcs[n_gap] - pc[n_gap];
-                        const float d32 = Sf * ebf - Bf * exf;
-                        if (exf > min_ex && (d32 <= 0.0f || d32 * d32 < kf * exf))
-                            continue;
-                    }
+                    const float Sf = ps[n_gap];
+                    if (Sf < need)
+                        continue;
                     const int64_t i = c0 + li;
-                    if (trig_exact(cr, es, i, n_bkg, n_gap, n_src, thr, &razor) && g.edge(i + n_bkg + n_gap) > -1.0)
+                    if (trig_detail(cr, es, s_ef, li, i, nbk, nsr, n_gap, Sf, use_pre, min_eb, min_ex, thr2f, thr, &razor) &&
+                        g.edge(i + n_bkg + n_gap) > -1.0)
                         atomicMin(&s_hit[ns - 1 - gx], (long long)i);
                 }
             }

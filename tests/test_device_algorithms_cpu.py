@@ -402,3 +402,136 @@ def test_tile_chain_marking_equals_the_serial_rule(rate, frac127, ties):
             assert n_rare < 0.01 * n           # GBM background: the rare list is (nearly) empty
         if rate >= 3e7:
             assert n_slow > 0                  # more than 64 events inside one window: the halo runs out
+
+
+# ---- k_merge_deadtime: the global walk (dt_keep_slow) on a sequential cursor over the two lists -----------------------
+class MergedCursor:
+    """csrc/cgrb_deadtime.cuh: MergedCursor -- position g: the merged prefix [0, g) is A[0, ia) + B[0, ib); ties:
+    background (A) first, so the last element of a prefix is B[ib-1] when B[ib-1] >= A[ia-1]"""
+
+    def __init__(self, A, pA, B, pB, g):
+        self.A, self.pA, self.B, self.pB = A, pA, B, pB
+        self.seek(g)
+
+    def seek(self, g):
+        self.ia = merge_split(self.A, self.B, g)
+        self.ib = g - self.ia
+
+    def pos(self):
+        return self.ia + self.ib
+
+    def prev(self):
+        a_prev = self.A[self.ia - 1] if self.ia > 0 else -np.inf
+        b_prev = self.B[self.ib - 1] if self.ib > 0 else -np.inf
+        if self.ib > 0 and (self.ia == 0 or b_prev >= a_prev):
+            self.ib -= 1
+            return self.B[self.ib], self.pB[self.ib]
+        self.ia -= 1
+        return self.A[self.ia], self.pA[self.ia]
+
+    def next(self):
+        a_next = self.A[self.ia] if self.ia < len(self.A) else np.inf
+        b_next = self.B[self.ib] if self.ib < len(self.B) else np.inf
+        if self.ia < len(self.A) and (self.ib >= len(self.B) or a_next <= b_next):
+            self.ia += 1
+            return self.A[self.ia - 1], self.pA[self.ia - 1]
+        self.ib += 1
+        return self.B[self.ib - 1], self.pB[self.ib - 1]
+
+
+def dt_keep_slow(A, pA, B, pB, i):
+    """csrc/cgrb_deadtime.cuh: dt_keep_slow -- one backward pass to the head of the chain, one forward pass from it"""
+    if i == 0:
+        return True
+    c = MergedCursor(A, pA, B, pB, i + 1)
+    ti, _ = c.prev()
+    found, tj, pj = -1, 0.0, 0
+    while c.pos() > 0:
+        tj, pj = c.prev()
+        if tj + TAU < ti:
+            break
+        if pj == 127 or c.pos() == 0:
+            found = c.pos()
+            break
+    if found < 0:
+        return True
+    head, th, ph = found, tj, pj
+    while head > 0:
+        q, tq, pq = -1, 0.0, 0
+        while c.pos() > 0:
+            tq, pq = c.prev()
+            if tq + TAU < th:
+                break
+            if pq == 127 or c.pos() == 0:
+                q = c.pos()
+                break
+        if q < 0 or tq + (NORMAL if (q == 0 and pq != 127) else TAU) < th:
+            break
+        head, th, ph = q, tq, pq
+    t_end = th + (NORMAL if (head == 0 and ph != 127) else TAU)
+    c.seek(head + 1)
+    for _ in range(head + 1, i):
+        tj, pj = c.next()
+        if pj == 127 and tj > t_end:
+            t_end = tj + TAU
+    return ti > t_end
+
+
+def test_merged_cursor_walks_the_reference_combine_both_ways():
+    rs = np.random.RandomState(12)
+    for nA, nB in ((300, 500), (0, 40), (40, 0), (1, 1), (700, 9)):
+        A, B = np.sort(rs.randint(0, 60, nA) * 0.25), np.sort(rs.randint(0, 60, nB) * 0.25)    # many exact ties
+        pA, pB = rs.randint(0, 128, nA), rs.randint(0, 128, nB)
+        want_t, want_p = orc.combine(A, pA, B, pB)
+        n = nA + nB
+        for g in sorted(set([0, 1, n // 3, n // 2, n - 1, n])):
+            c = MergedCursor(A, pA, B, pB, g)
+            fwd = [c.next() for _ in range(g, n)]
+            assert [x[0] for x in fwd] == list(want_t[g:]) and [x[1] for x in fwd] == list(want_p[g:])
+            c = MergedCursor(A, pA, B, pB, g)
+            back = [c.prev() for _ in range(g)]
+            assert [x[0] for x in back] == list(want_t[:g][::-1]) and [x[1] for x in back] == list(want_p[:g][::-1])
+            assert c.pos() == 0
+
+
+@pytest.mark.parametrize("rate,frac127,ties", [(2e5, 0.3, True), (3e6, 0.02, True), (3e7, 0.02, False), (5e6, 1.0, False)])
+def test_global_walk_on_the_cursor_equals_the_serial_rule(rate, frac127, ties):
+    """the walk an event takes when its chain leaves the tile's halo: exact for every event, on two lists with ties"""
+    rs = np.random.RandomState(int(rate) % 997 + 3)
+    n = 2500
+    for first127 in (False, True):
+        t, p = _events(rs, n, rate, frac127, ties)
+        p[0] = 127 if first127 else 5
+        is_a = rs.random_sample(n) < 0.3
+        # equal times: the reference's combine puts the background (A) events first
+        order = np.lexsort((~is_a, t))
+        t, p, is_a = t[order], p[order], is_a[order]
+        A, pA, B, pB = t[is_a], p[is_a], t[~is_a], p[~is_a]
+        ct, cp = orc.combine(A, pA, B, pB)
+        assert np.array_equal(ct, t) and np.array_equal(cp, p)
+        want = orc.gbm_dead_time(t, p)
+        got = np.array([dt_keep_slow(A, pA, B, pB, i) for i in range(n)])
+        assert np.array_equal(got, want)
+
+
+def test_dense_tiles_take_the_long_halo_and_stay_exact():
+    """k_merge_plan: a tile with more than MD_DENSE = 8 events to the longest window stages MD_HALO_DENSE = 512 events of
+    look-back instead of 64.  Any halo gives the same keep flags; the long one keeps dense tiles off the global walk."""
+    rs = np.random.RandomState(77)
+    n = 4 * 2048
+    t, p = _events(rs, n, 3e6, 0.02)            # ~32 events per window: the peak of a very bright burst
+    want = orc.gbm_dead_time(t, p)
+    slow = {}
+    for halo in (64, 512):
+        got, slow[halo] = [], 0
+        for d0 in range(0, n, 2048):
+            d1, g0 = min(d0 + 2048, n), max(0, d0 - 64)
+            dense = d0 > 64 and (t[d1 - 1] - t[g0]) * 8 < (d1 - g0) * TAU       # the rule of k_merge_plan
+            assert dense == (d0 > 0)
+            k, _, s_ = tile_keep_flags(t, p, d0, halo=halo)
+            got.append(k)
+            slow[halo] += s_
+        assert np.array_equal(np.concatenate(got), want)
+    assert slow[64] >= 5 and slow[512] == 0
+    tb, _ = _events(rs, n, 500.0, 0.05)         # GBM background: never dense
+    assert not any((tb[min(d0 + 2048, n) - 1] - tb[d0 - 64]) * 8 < (min(d0 + 2048, n) - d0 + 64) * TAU for d0 in range(2048, n, 2048))
