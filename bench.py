@@ -12,8 +12,9 @@ event counts are exchanged with one small NCCL all_gather (the event-offset gath
 ``e2e``    : the same through the host-facing call with HOST buffers: unit records + tables are
              copied H2D and all six event lists of every detector are copied D2H into pinned host
              memory inside the timed region.
-``--impl reference`` times the CPU oracle (port of the reference's numba path, oracle/) on all host
-cores on a bounded, stratified sample of the same workload.
+``--impl reference`` times the reference's own numba kernels and classes (staged under oracle/_ref by
+oracle/stage_ref.py; the C port of oracle/ if they are not at hand) on all host cores on a bounded,
+stratified sample of the same workload.
 """
 import argparse
 import json
@@ -147,31 +148,60 @@ def cpu_sample(n_windows, window_s, threads, seed=1):
     return sum(r[0] for r in res), dt, sum(r[1] for r in res), sum(r[2] for r in res)
 
 
+def reference_sampler():
+    """(kind, sample(n_windows, window_s, seed) -> (events, seconds, detail)) of the CPU arm: the reference's own numba
+    kernels and classes when its files are at hand (/root/reference, or the copy staged under oracle/_ref for the GPU
+    box: oracle/stage_ref.py, oracle/ref_numba.py), one forked process per host core; otherwise the C port of
+    oracle/, one thread per host core."""
+    threads = len(os.sched_getaffinity(0))
+    p = bright_params()
+    try:
+        from oracle import ref_numba
+
+        root, why = ref_numba.available()
+        if root is None or os.environ.get("CGRB_REFERENCE_ARM") == "port":
+            raise RuntimeError(why or "port forced")
+        ref_numba.setup(p)
+
+        def sample(n_windows, window_s, seed=1):
+            ev, n_src, dt = ref_numba.run_sample(n_windows, window_s, threads, p["duration"])
+            return ev, dt, f"{n_src} source events"
+
+        return "reference", threads, sample, f"numba kernels + classes of the reference ({root})"
+    except Exception as e:          # noqa: BLE001
+        from oracle import oracle as orc
+
+        orc.build()
+
+        def sample(n_windows, window_s, seed=1):
+            ev, dt, nc, ntr = cpu_sample(n_windows, window_s, threads, seed=seed)
+            return ev, dt, f"{nc} candidates, {ntr} rejection trials"
+
+        return "port", threads, sample, f"C port of the reference's numba path (oracle/); the reference itself: {e}"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle as orc
-
-    orc.build()
-    threads = len(os.sched_getaffinity(0))
-    n_windows, window_s = 4 * threads, 0.1          # ~15-25 s of CPU work per step
+    kind, threads, sample_fn, how = reference_sampler()
+    n_windows, window_s = 4 * threads, 0.1          # ~10-20 s of CPU work per step
     for _ in range(max(args.warmup, 0)):
-        cpu_sample(threads, 0.01, threads)
-    ev, secs = 0, 0.0
+        sample_fn(threads, 0.01)
+    ev, secs, detail = 0, 0.0, ""
     for k in range(args.steps):
-        e, dt, _, _ = cpu_sample(n_windows, window_s, threads, seed=k + 1)
+        e, dt, detail = sample_fn(n_windows, window_s, seed=k + 1)
         ev += e
         secs += dt
     value = ev / secs
-    sample = (f"{n_windows} windows x {window_s}s of detector n0 spread evenly over the 300 s burst "
-              f"(fraction {n_windows * window_s / 300:.4f} of one of the 14 units) per step")
+    sample = (f"{n_windows} windows x {window_s}s of detector n0 spread evenly over the 300 s burst, thinned with the whole "
+              f"burst's fmax (fraction {n_windows * window_s / 300:.4f} of one of the 14 units) per step; {how}; last step: {detail}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -537,16 +567,13 @@ def run_gpu(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import oracle as orc
-
-        orc.build()
-        threads = len(os.sched_getaffinity(0))
-        cpu_sample(threads, 0.01, threads)
-        n_w, w_s = 4 * threads, 0.1
-        e, dt, nc, ntr = cpu_sample(n_w, w_s, threads)
-        cpu_baseline = {"value": e / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{n_w} windows x {w_s}s of detector n0 spread evenly over the 300 s burst "
-                                  f"({e} events, {nc} candidates, {ntr} rejection trials, {dt:.1f}s wall)"}
+        # the CPU arm in a process of its own (it forks workers: not from a process that holds a CUDA context)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                               capture_output=True, text=True, timeout=900)
+            cpu_baseline = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:      # noqa: BLE001
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
     if rank == 0:
         line = {

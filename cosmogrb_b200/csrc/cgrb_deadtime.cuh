@@ -678,7 +678,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *s_bar, unsigned parity)
 #endif
 #define MD_SPARSE 64             // a tile whose minority list has at most this many events is merged by insertion
 #ifndef MD_CTAS
-#define MD_CTAS 6                // resident CTAs per SM the kernel is compiled for (register budget; ~20 KB of shared memory each)
+#define MD_CTAS 5                // resident CTAs per SM the kernel is compiled for (register budget; ~20 KB of shared memory each)
 #endif
 
 struct MdSmem {

@@ -637,7 +637,10 @@ int cgrb_gbm_trigger(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t 
     LAUNCH("k_trig_bin", s, k_trig_bin<<<(unsigned)n_work, NT, 0, s>>>(d_units, d_work, n_work, d_chan_bounds,
                                                                       par->base_timescale, d_times_out, d_pha_out,
                                                                       d_counts, bins_per_unit, bins));
-    LAUNCH("k_trig_eval", s, k_trig_eval<<<n_units, NT, 0, s>>>(d_units, n_units, *par, d_times_out, d_counts,
+    e = cudaFuncSetAttribute(k_trig_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, TRIG_EVAL_SMEM);     // > 48 KB: opt-in
+    if (e != cudaSuccess)
+        return fail(CGRB_E_CUDA, "cgrb_gbm_trigger: shared memory opt-in: %s", cudaGetErrorString(e));
+    LAUNCH("k_trig_eval", s, k_trig_eval<<<n_units, NT, TRIG_EVAL_SMEM, s>>>(d_units, n_units, *par, d_times_out, d_counts,
                                                                bins_per_unit, bins, csum, esum, d_out));
     return check_launch("cgrb_gbm_trigger");
 }

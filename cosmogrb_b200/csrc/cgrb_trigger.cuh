@@ -18,8 +18,10 @@
 #define TRIG_PASSES (TRIG_TILE / (TRIG_EPT * NT))
 #define TRIG_NCOMBO 33
 #define TRIG_NARR 6             // per-bin integer arrays: counts of the 4 ranges, events, overflow events
-#define TRIG_CH 2048            // windows per staged chunk of the search
+#define TRIG_CH 1792            // windows per staged chunk of the search (a multiple of NT)
 #define TRIG_SPAN 1832          // >= background (1062) + longest gap (512) + source (250) bins
+#define TRIG_ST (TRIG_CH + TRIG_SPAN + 4)       // staged prefix entries per chunk (+1, padded)
+#define TRIG_EVAL_SMEM ((3 * TRIG_ST + TRIG_CH) * 4)    // dynamic shared memory of k_trig_eval
 
 // exact (double)i for 0 <= i < 2^32 without the quarter-rate I2F.F64: 2^52 + i is representable, subtract 2^52
 __device__ __forceinline__ double trig_u2d(unsigned i)
@@ -49,7 +51,7 @@ __device__ __forceinline__ TrigGrid trig_grid(double tmin, double tmax, double d
 // field stays below 2 x TRIG_TILE < 65536): word 0 = range a | range b << 16, word 1 = range c | range d << 16,
 // word 2 = events | overflow events << 16 (the two dead-time counters).
 #ifndef TRIG_BIN_CTAS
-#define TRIG_BIN_CTAS 4
+#define TRIG_BIN_CTAS 6
 #endif
 __global__ void __launch_bounds__(NT, TRIG_BIN_CTAS) k_trig_bin(const cgrb_unit_t *__restrict__ units,
                                                  const cgrb_work_t *__restrict__ work, int64_t n_work,
@@ -437,20 +439,22 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     }
     __syncthreads();
     // the search: energy ranges a..d, time scales longest first; the first combination (in that order) with
-    // a window at or above the threshold wins, at its first window.  The prefix sums of a chunk of windows
-    // (+ the longest window span) are staged in shared memory as fp32 relative to the chunk start; all time
-    // scales of a range share the background window of a given i.
-    __shared__ float s_ef[TRIG_CH + TRIG_SPAN + 1];     // exposure prefix
-    __shared__ float s_cf[TRIG_CH + TRIG_SPAN + 1];     // count prefix (exact in fp32 below 2^24), then window sums
-    __shared__ float s_need[TRIG_CH];                   // per window start: the source-window sum a hit needs at least
-    __shared__ long long s_hit[10];
+    // a window at or above the threshold wins, at its first window.  Chunk by chunk of TRIG_CH window starts
+    // (+ the longest window span): the exposure prefix is staged once per chunk as fp32 relative to the chunk
+    // start and shared by the four ranges; the 32-bit count prefix of one range at a time arrives by cp.async
+    // while the previous range is being searched.
+    extern __shared__ __align__(16) unsigned char trig_dyn[];
+    float *s_ef = reinterpret_cast<float *>(trig_dyn);      // exposure prefix of the chunk
+    float *s_sw = s_ef + TRIG_ST;                           // source-window count sums S(m) = C(m + n_src) - C(m)
+    int *s_raw = reinterpret_cast<int *>(s_sw + TRIG_ST);   // count prefix of the range in flight
+    float *s_need = reinterpret_cast<float *>(s_raw + TRIG_ST);    // per window start: the S a hit needs at least
+    __shared__ int s_hit[4][10];            // first firing window start per combination (n_bins < 2^31)
     __shared__ float s_min[NW];
     const int n_scales[4] = {10, 10, 9, 4};
     const int64_t n_bkg = (int64_t)floor(par.background_duration / dt);
     const int64_t n_src = (int64_t)floor(par.pre_window / dt);          // the "source" window (swapped arguments)
     const double thr = par.threshold;
     int razor = 0;
-    bool found = false;
     // the staged layout needs n_bkg + longest gap + n_src <= TRIG_SPAN: true for the reference's constants
     const bool staged_ok = (n_bkg + 512 + n_src <= TRIG_SPAN) && n_bkg > 0 && n_src > 0;
     const bool pre_params_ok = (thr >= 1.0) && (thr < 1e15) && (n_src <= n_bkg);
@@ -458,152 +462,168 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     const float thr_lo = 0.94f * (float)thr;                            // < sqrt(0.9) thr: the margin of the fp32 test
     const float min_eb = 0.25f * (float)((double)n_bkg * dt), min_ex = 0.25f * (float)((double)n_src * dt);
     const int nbk = (int)n_bkg, nsr = (int)n_src;
-    constexpr int TRIG_IPT = TRIG_CH / NT;                              // window starts per thread and chunk (8)
-    constexpr int TRIG_XPT = (TRIG_CH + TRIG_SPAN + NT) / NT;           // staged elements per thread (16)
-#pragma unroll 1
-    for (int r = 0; r < 4 && !found && staged_ok; r++) {
+    constexpr int TRIG_IPT = TRIG_CH / NT;                              // window starts per thread and chunk
+    constexpr int TRIG_XPT = (TRIG_ST + NT - 1) / NT;                   // staged elements per thread
+    if (threadIdx.x < 40)
+        (&s_hit[0][0])[threadIdx.x] = INT_MAX;
+    unsigned range_ok = 0u;                                             // `if sum(counts) == 0: continue`
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        range_ok |= (cs[r * (bins_per_unit + 1) + nb] != 0) ? (1u << r) : 0u;
+    const int64_t n_i_max = nb - (n_bkg + 1 + n_src);                   // shortest gap: 1 bin
+    const int n_chunks = (staged_ok && n_i_max > 0) ? (int)((n_i_max + TRIG_CH - 1) / TRIG_CH) : 0;
+    // a combination is identified by key = 16 r + (index of the time scale, longest first): the smallest key with a
+    // hit wins.  Later chunks only hold later windows, so once a key has fired only smaller keys are still open.
+    int best_key = 64;
+    auto next_active = [&](int it) -> int {                             // iteration = 4 chunk + range
+        for (int nx = it + 1; nx < 4 * n_chunks; nx++) {
+            const int r = nx & 3;
+            if (((range_ok >> r) & 1u) && 16 * r < best_key)
+                return nx;
+        }
+        return -1;
+    };
+    auto prefetch = [&](int nx) {
+        const int64_t c0 = (int64_t)(nx >> 2) * TRIG_CH;
+        const int n_st = (int)(min(nb, c0 + TRIG_CH + TRIG_SPAN) - c0) + 1;
+        const int32_t *src = cs + (nx & 3) * (bins_per_unit + 1) + c0;
+        for (int k = threadIdx.x; k < n_st; k += NT) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_raw + k);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + k) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int it = next_active(-1);
+    if (it >= 0)
+        prefetch(it);
+    int staged_chunk = -1;
+    float exm = INFINITY;
+    while (it >= 0) {
+        const int r = it & 3;
+        const int64_t c0 = (int64_t)(it >> 2) * TRIG_CH;
+        const int64_t hi = min(nb, c0 + TRIG_CH + TRIG_SPAN);
+        const int n_st = (int)(hi - c0) + 1;
         const int32_t *cr = cs + r * (bins_per_unit + 1);
-        if (cr[nb] == 0)                                                  // `if sum(counts) == 0: continue`
-            continue;
         const int ns = n_scales[r];
-        if (threadIdx.x < 10)
-            s_hit[threadIdx.x] = LLONG_MAX;
-        const int64_t n_i_max = nb - (n_bkg + 1 + n_src);                 // shortest gap: 1 bin
-        for (int64_t c0 = 0; c0 < n_i_max; c0 += TRIG_CH) {
-            __syncthreads();
-            const int64_t hi = min(nb, c0 + TRIG_CH + TRIG_SPAN);
-            const int cbase = cr[c0];
+        if (staged_chunk != (it >> 2)) {
+            staged_chunk = it >> 2;
+            // exposure prefix of the chunk (nobody reads s_ef any more: the barrier that closed the last search)
             const double ebase = es[c0];
-            // Nearly every window is far below the threshold: that is decided in fp32 (full rate, no 64-bit
-            // conversions).  A hit needs d = S eb - B ex >= thr sqrt(B ex eb); the fp32 value of d is off by at
-            // most ~3e-6 (S eb + B ex), i.e. by < 2.5 % of d for any window that could fire (counts < 2^24 so
-            // that they are exact in fp32, thr >= 1, source window not longer than the background window), so
-            // d^2 < 0.9 thr^2 B ex eb is a certain miss.  Everything else takes the exact path.
-            const bool use_pre = pre_params_ok && (cr[hi] - cbase) < (1 << 24);
-            const int n_st = (int)(hi - c0) + 1;
-            {
-                // loads batched four deep: the staging is latency-bound otherwise
-                const double *ep = es + c0;
-                const int32_t *cp = cr + c0;
-                for (int k = threadIdx.x; k < n_st; k += 4 * NT) {
-                    double ev[4];
-                    int cv[4];
+            const double *ep = es + c0;
+            for (int k = threadIdx.x; k < n_st; k += 4 * NT) {
+                double ev[4];                           // loads batched four deep
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int kk = min(k + q * NT, n_st - 1);
-                        ev[q] = ep[kk];
-                        cv[q] = cp[kk];
-                    }
+                for (int q = 0; q < 4; q++)
+                    ev[q] = ep[min(k + q * NT, n_st - 1)];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int kk = k + q * NT;
-                        if (kk < n_st) {
-                            s_ef[kk] = (float)(ev[q] - ebase);
-                            s_cf[kk] = (float)min(cv[q] - cbase, 1 << 24);
-                        }
-                    }
-                }
+                for (int q = 0; q < 4; q++)
+                    if (k + q * NT < n_st)
+                        s_ef[k + q * NT] = (float)(ev[q] - ebase);
             }
             __syncthreads();
-            const int i_end = (int)(min(c0 + (int64_t)TRIG_CH, n_i_max) - c0);
-            // window i with gap n_gap exists iff i + n_bkg + n_gap + n_src < nb, i.e. n_gap < room(i)
-            const int64_t room0 = nb - n_bkg - n_src - c0;
-            // Level 0 of the filter works on the source-window sums alone.  A hit needs
-            //     S >= a B + thr sqrt(a B),   a = ex / eb,
-            // and the right-hand side grows with a, so with ex_min = the smallest source-window exposure staged
-            // in this chunk no window starting at i can fire unless S >= S_min(i) = a_min B + 0.94 thr sqrt(a_min B),
-            // a_min = ex_min / eb(i) (0.94 < sqrt(0.9): the same margin as the fp32 test below, which every
-            // survivor still takes, and then the exact one).  One load and one compare per (window, time scale).
-            // (a) ex_min, and each thread's S_min for its TRIG_IPT window starts; (b) the count prefix becomes the
-            // array of source-window sums S(m) = C(m + n_src) - C(m), in place through registers.
-            float exm = INFINITY;
-            float sw[TRIG_XPT];
+            // ex_min: the smallest source-window exposure staged in this chunk
+            float e_ = INFINITY;
 #pragma unroll
             for (int q = 0; q < TRIG_XPT; q++) {
                 const int m = threadIdx.x + q * NT;
-                sw[q] = 0.0f;
-                if (m + nsr < n_st) {
-                    sw[q] = s_cf[m + nsr] - s_cf[m];
-                    if (m >= nbk)
-                        exm = fminf(exm, s_ef[m + nsr] - s_ef[m]);
-                }
+                if (m >= nbk && m + nsr < n_st)
+                    e_ = fminf(e_, s_ef[m + nsr] - s_ef[m]);
             }
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1)
-                exm = fminf(exm, __shfl_xor_sync(0xffffffffu, exm, d));
+                e_ = fminf(e_, __shfl_xor_sync(0xffffffffu, e_, d));
             if (lane == 0)
-                s_min[wid] = exm;
-            float smin[TRIG_IPT];
-#pragma unroll
-            for (int q = 0; q < TRIG_IPT; q++) {
-                const int li = threadIdx.x + q * NT;
-                smin[q] = -INFINITY;
-                if (li < i_end) {
-                    const float Bf = s_cf[li + nbk] - s_cf[li];
-                    const float ebf = s_ef[li + nbk] - s_ef[li];
-                    if (use_pre && Bf > 0.0f && ebf > min_eb)
-                        smin[q] = Bf / ebf;             // times ex_min below
-                }
-            }
+                s_min[wid] = e_;
             __syncthreads();
             exm = s_min[0];
 #pragma unroll
             for (int q = 1; q < NW; q++)
                 exm = fminf(exm, s_min[q]);
-            const bool lvl0 = exm > min_ex && exm < INFINITY;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();                                // the count prefix of (chunk, range) has landed
+        const bool open = 16 * r < best_key;            // (a prefetch issued before the last hit may be moot)
+        const int i_end = (int)(min(c0 + (int64_t)TRIG_CH, n_i_max) - c0);
+        // Nearly every window is far below the threshold, which is decided in fp32 (full rate, no 64-bit
+        // conversions; counts below 2^24 are exact).  Level 0 works on the source-window sums alone: a hit needs
+        //     S >= a B + thr sqrt(a B),   a = ex / eb,
+        // and the right-hand side grows with a, so with ex_min as above no window starting at i can fire unless
+        // S >= S_min(i) = a_min B + 0.94 thr sqrt(a_min B), a_min = ex_min / eb(i) (0.94 < sqrt(0.9): the margin
+        // of the fp32 test in trig_detail, which every survivor takes next, and then the exact one).  One load
+        // and one compare per (window, time scale).
+        const bool use_pre = pre_params_ok && (s_raw[n_st - 1] - s_raw[0]) < (1 << 24);
+        const bool lvl0 = use_pre && exm > min_ex && exm < INFINITY;
+        if (open) {
 #pragma unroll
             for (int q = 0; q < TRIG_XPT; q++) {
                 const int m = threadIdx.x + q * NT;
                 if (m + nsr < n_st)
-                    s_cf[m] = sw[q];
+                    s_sw[m] = (float)min(s_raw[m + nsr] - s_raw[m], 1 << 24);
             }
 #pragma unroll
             for (int q = 0; q < TRIG_IPT; q++) {
+                const int li = threadIdx.x + q * NT;
                 float need = -INFINITY;
-                if (lvl0 && smin[q] > 0.0f) {
-                    const float ab = smin[q] * exm;     // a_min B
-                    need = ab * 0.99999f + thr_lo * sqrtf(ab);
+                if (lvl0 && li < i_end) {
+                    const float Bf = (float)(s_raw[li + nbk] - s_raw[li]);
+                    const float ebf = s_ef[li + nbk] - s_ef[li];
+                    if (Bf > 0.0f && ebf > min_eb) {
+                        const float ab = Bf / ebf * exm;        // a_min B
+                        need = ab * 0.99999f + thr_lo * sqrtf(ab);
+                    }
                 }
-                s_need[threadIdx.x + q * NT] = need;
+                s_need[li] = need;
             }
-            __syncthreads();
+        }
+        __syncthreads();                                // s_raw is free again
+        const int nx = next_active(it);
+        if (nx >= 0)
+            prefetch(nx);
+        if (open) {
+            // window i with gap n_gap exists iff i + n_bkg + n_gap + n_src < nb, i.e. n_gap < room(i)
+            const int64_t room0 = nb - n_bkg - n_src - c0;
+            const int s_lim = best_key - 16 * r;        // only time scales with an index below this are still open
 #pragma unroll 1
             for (int li = threadIdx.x; li < i_end; li += NT) {
                 const int room = (int)min(room0 - li, (int64_t)1024);
                 const float need = s_need[li];
-                const float *ps = s_cf + li + nbk;
+                const float *ps = s_sw + li + nbk;
 #pragma unroll
                 for (int gx = 9; gx >= 0; gx--) {
                     const int n_gap = 1 << gx;
-                    if (gx >= ns || n_gap >= room)
+                    if (gx >= ns || n_gap >= room || ns - 1 - gx >= s_lim)
                         continue;
                     const float Sf = ps[n_gap];
                     if (Sf < need)
                         continue;
                     const int64_t i = c0 + li;
+                    if (i >= (int64_t)((volatile int *)s_hit[r])[ns - 1 - gx])
+                        continue;                       // an earlier window of this combination has fired already
                     if (trig_detail(cr, es, s_ef, li, i, nbk, nsr, n_gap, Sf, use_pre, min_eb, min_ex, thr2f, thr, &razor) &&
                         g.edge(i + n_bkg + n_gap) > -1.0)
-                        atomicMin(&s_hit[ns - 1 - gx], (long long)i);
+                        atomicMin(&s_hit[r][ns - 1 - gx], (int)i);
                 }
             }
-            __syncthreads();
-            if (s_hit[0] != LLONG_MAX)
-                break;              // the first time scale fired: nothing later can overrule it
         }
         __syncthreads();
-        for (int sidx = 0; sidx < ns; sidx++) {
-            const long long first = s_hit[sidx];
-            if (first != LLONG_MAX) {
-                const int64_t n_gap = (int64_t)1 << (ns - 1 - sidx);
-                found = true;
-                res.detected = 1;
-                res.combo = r * 16 + sidx;
-                res.time = g.edge(first + n_bkg + n_gap);
-                res.time_scale = dt * (double)n_gap;
+        for (int key = 16 * r; key < min(best_key, 16 * r + ns); key++)
+            if (s_hit[r][key - 16 * r] != INT_MAX) {
+                best_key = key;
                 break;
             }
-        }
-        __syncthreads();
+        if (best_key == 0)
+            break;                  // the first combination fired: nothing later can overrule it
+        it = nx;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (best_key < 64) {
+        const int r = best_key >> 4, sidx = best_key & 15;
+        const int64_t n_gap = (int64_t)1 << (n_scales[r] - 1 - sidx);
+        res.detected = 1;
+        res.combo = best_key;
+        res.time = g.edge((int64_t)s_hit[r][sidx] + n_bkg + n_gap);
+        res.time_scale = dt * (double)n_gap;
     }
     __shared__ int s_razor;
     if (threadIdx.x == 0)

@@ -2,9 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY (never imported by the product package).  This module exists
 so that ``oracle/make_golden.py`` can execute the unmodified reference kernels in the
-authoring container and mint golden vectors under ``tests/golden/``.  It reads
-``/root/reference`` at run time, therefore it cannot (and must not) be used on the GPU
-box, by ``bench.py`` or by any ``-m gpu`` test.
+authoring container and mint golden vectors under ``tests/golden/``, and so that the CPU arm
+of ``bench.py`` (``--impl reference``, ``oracle/ref_numba.py``) can TIME them.  It reads the
+reference tree named by ``COSMOGRB_REFERENCE`` (default ``/root/reference``; on the GPU box
+the git-ignored copy staged under ``oracle/_ref`` by ``oracle/stage_ref.py``) at run time;
+no ``-m gpu`` test, ``smoke()`` or product code uses it.
 
 What is shimmed:
   * ``numba_scipy``   -> registers ``scipy.special.gammaincc`` / ``gamma`` for nopython

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 N_BKG, N_SRC, DT = 1062, 250, 0.016         # floor(17 / 0.016), floor(4 / 0.016)
-CH, SPAN = 2048, 1832                        # TRIG_CH, TRIG_SPAN
+CH, SPAN = 1792, 1832                        # TRIG_CH, TRIG_SPAN
 
 
 def _curve(rs, nb, rate, burst):
