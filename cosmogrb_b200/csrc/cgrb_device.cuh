@@ -85,6 +85,25 @@ __device__ __forceinline__ double u32d(uint32_t a)
 {
     return __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)(a << 20)) - 1.0;
 }
+// One Philox call carries a PAIR of background events: 40 bits for each exponential gap, 24 for each channel draw.
+// Gap uniforms are (k + 1/2) 2^-40, k < 2^40: never 0 (a zero would end the unit's list), resolution far below one
+// ulp of an arrival time; channel uniforms are k 2^-24.
+__device__ __forceinline__ double u40h(uint32_t a, uint32_t b8)
+{
+    return __hiloint2double((int)(0x3FF00000u | (a >> 12)), (int)((a << 20) | (b8 << 12) | 0x800u)) - 1.0;
+}
+__device__ __forceinline__ double u24d(uint32_t c)
+{
+    return __hiloint2double((int)(0x3FF00000u | (c >> 4)), (int)(c << 28)) - 1.0;
+}
+struct BkgDraw {
+    double ga, gb;      // gap uniforms of the pair's two events
+    uint32_t ca, cb;    // their channel draws, 24 bits each
+};
+__device__ __forceinline__ BkgDraw bkg_draw(const Philox4 p)
+{
+    return BkgDraw{u40h(p.x, p.y >> 24), u40h(p.z, (p.y >> 16) & 0xffu), p.w >> 8, ((p.w & 0xffu) << 16) | (p.y & 0xffffu)};
+}
 struct TrialDraw {
     double U, V, C;     // proposal, height, channel
 };
@@ -98,7 +117,7 @@ enum Stage : uint32_t {
     ST_SRC_TIME = 1,   // candidate k: xy -> gap uniform, zw -> acceptance uniform
     ST_SRC_ENERGY = 2, // photon i, trial j: literal sampler xy -> proposal, zw -> height; envelope sampler: trial_draw
     ST_SRC_CHAN = 3,   // photon i: xy -> channel uniform (stand-alone fold, photons of the literal loop)
-    ST_BKG = 4,        // candidate k: xy -> gap uniform, zw -> channel uniform of event k+1
+    ST_BKG = 4,        // candidate pair m: bkg_draw (two gap uniforms + two channel draws from one call); event 0: index 2^40 - 1
 };
 
 struct RngKey {

@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(NT) k_background_plan(const cgrb_unit_t *__res
 
 #define BKG_NOT_READY 0xFFFFFFFFFFFFFFFFull     // state words are set to this (a NaN no tile can publish) before the launch
 #ifndef BKG_CTAS
-#define BKG_CTAS 5
+#define BKG_CTAS 4
 #endif
 #define BKG_R (BKG_TILE / (2 * NT))             // rounds: a thread owns one candidate PAIR per round (4)
 
@@ -622,19 +622,30 @@ __global__ void __launch_bounds__(NT, BKG_CTAS) k_background(const double *__res
     // candidates from 256 w + 64 r, lane l the pair 2 l, 2 l + 1 of them.
     const double inv_f = tl.inv_rate;
     double p0[BKG_R], p1[BKG_R];
+    uint32_t ca[BKG_R], cb[BKG_R];  // channel draws of the pairs (Philox: they ride in the call that gave the gaps)
     bool exhausted = false;
     double rc = 0.0;                // running sum of the warp's earlier rounds
 #pragma unroll
     for (int r = 0; r < BKG_R; r++) {
         const int j0 = 256 * wid + 64 * r + 2 * lane;           // start and j0 are even
         double g0 = 0.0, g1 = 0.0;
+        ca[r] = cb[r] = 0u;
         if (j0 < n) {
-            PairDraw d = pair_draw(rng, tl.unit, tl.sid, ST_BKG, (start + j0) >> 1, 0);
             // time - (1/rate) * log(u)  background.py:33
-            g0 = (rng.mode == 0) ? inv_f * neglog_fast(d.a) : -(inv_f * log(d.a));
-            if (j0 + 1 < n)
-                g1 = (rng.mode == 0) ? inv_f * neglog_fast(d.b) : -(inv_f * log(d.b));
-            exhausted |= d.exhausted;
+            if (rng.mode == 0) {
+                const BkgDraw d = bkg_draw(philox_at(make_key(rng.seed), tl.sid, ST_BKG, (uint64_t)((start + j0) >> 1), 0u));
+                g0 = inv_f * neglog_fast(d.ga);
+                if (j0 + 1 < n)
+                    g1 = inv_f * neglog_fast(d.gb);
+                ca[r] = d.ca;
+                cb[r] = d.cb;
+            } else {
+                PairDraw d = pair_draw(rng, tl.unit, tl.sid, ST_BKG, (start + j0) >> 1, 0);
+                g0 = -(inv_f * log(d.a));
+                if (j0 + 1 < n)
+                    g1 = -(inv_f * log(d.b));
+                exhausted |= d.exhausted;
+            }
         }
         const double incl = warp_incl_scan(g0 + g1, lane);
         double excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -718,9 +729,8 @@ __global__ void __launch_bounds__(NT, BKG_CTAS) k_background(const double *__res
         if (va) {
             double ua, ub = 0.5;
             if (rng.mode == 0) {
-                PairDraw d = pair_draw(rng, tl.unit, tl.sid, ST_BKG, (start + j0) >> 1, 1);
-                ua = d.a;
-                ub = d.b;
+                ua = u24d(ca[r]);
+                ub = u24d(cb[r]);
             } else {
                 const int64_t o = rng_chan.d_off ? rng_chan.d_off[tl.unit] : 0;
                 const int64_t len = rng_chan.d_len ? rng_chan.d_len[tl.unit] : ((int64_t)1 << 62);

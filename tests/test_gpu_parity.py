@@ -400,10 +400,11 @@ def _u53(a, b):
 
 def test_background_under_philox_equals_a_host_replay_of_the_counters(engine):
     """The production background (one pass, fast logarithm, guided channel draw) against a NumPy replay of its
-    Philox counters: candidate pair m -> counter (m, 0) gives the two gap uniforms, (m, 1) the two channel uniforms
-    (cgrb_common.cuh pair_draw); times = tstart + running sum of -log(u) / rate (background.py:13-44), channels =
-    searchsorted(cdf, u, 'right') (numpy's legacy choice, :93).  Times agree to 1e-13 relative (the device's
-    logarithm and summation order differ from NumPy's in the last bits), channels and the count exactly."""
+    Philox counters: ONE call per candidate pair m, counter (m, 0), carries the pair's two gap uniforms (40 bits each,
+    (k + 1/2) 2^-40) and its two channel draws (24 bits each) -- cgrb_device.cuh bkg_draw; times = tstart + running
+    sum of -log(u) / rate (background.py:13-44), channels = searchsorted(cdf, u, 'right') (numpy's legacy choice,
+    :93).  Times agree to 1e-13 relative (the device's logarithm and summation order differ from NumPy's in the
+    last bits), channels and the count exactly."""
     seed, sid, rate, t0, t1 = 0x1234ABCD5678, 37, 500.0, -100.0, 300.0
     rsp = h.response("n0")
     w = h.bkg_weights("n0")
@@ -417,9 +418,13 @@ def test_background_under_philox_equals_a_host_replay_of_the_counters(engine):
     m = np.arange(n_pairs, dtype=np.uint64)
     k0, k1 = seed & 0xFFFFFFFF, seed >> 32
     x, y, z, ww = _philox4x32_10(m, 0, sid, 4, k0, k1)              # ST_BKG = 4
-    ug = np.stack((_u53(x, y), _u53(z, ww)), axis=1).reshape(-1)
-    x, y, z, ww = _philox4x32_10(m, 1, sid, 4, k0, k1)
-    uc = np.stack((_u53(x, y), _u53(z, ww)), axis=1).reshape(-1)
+    u64 = np.uint64
+    ga = ((x << u64(8)) | (y >> u64(24))).astype("f8")              # 40-bit integers: exact in a double
+    gb = ((z << u64(8)) | ((y >> u64(16)) & u64(0xFF))).astype("f8")
+    ug = np.stack(((ga + 0.5) * 2.0 ** -40, (gb + 0.5) * 2.0 ** -40), axis=1).reshape(-1)
+    ca, cb = ww >> u64(8), ((ww & u64(0xFF)) << u64(16)) | (y & u64(0xFFFF))
+    uc = np.stack((ca.astype("f8") * 2.0 ** -24, cb.astype("f8") * 2.0 ** -24), axis=1).reshape(-1)
+    assert ug.min() > 0.0 and ug.max() < 1.0
     times = t0 + np.cumsum(-np.log(ug) / rate)
     n = int(np.searchsorted(times, t1, "right"))
     assert abs(int(c["n_bkg"][0]) - (n + 1)) <= 1                  # a time within 1e-13 of tstop may fall either side
