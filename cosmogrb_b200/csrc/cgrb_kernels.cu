@@ -612,7 +612,8 @@ int64_t cgrb_gbm_trigger_workspace_bytes(int n_units, int64_t bins_per_unit)
     if (n_units <= 0 || bins_per_unit <= 0)
         return 0;
     const int64_t nu = n_units;
-    return nu * TRIG_NARR * bins_per_unit * 4 + nu * 4 * (bins_per_unit + 1) * 4 + nu * (bins_per_unit + 1) * 8 + 768;
+    const int64_t cstride = ((bins_per_unit + 4 + 3) / 4) * 4;       // prefix rows: 3 pad + (bins + 1) entries, a multiple of 4
+    return nu * TRIG_NARR * bins_per_unit * 4 + nu * 4 * cstride * 4 + nu * cstride * 8 + 768;
 }
 
 int cgrb_gbm_trigger(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work, int64_t n_work,
@@ -629,8 +630,9 @@ int cgrb_gbm_trigger(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t 
     const int64_t nu = n_units;
     int32_t *bins = (int32_t *)d_workspace;
     const size_t bins_bytes = (size_t)nu * TRIG_NARR * bins_per_unit * 4;
+    const int64_t cstride = ((bins_per_unit + 4 + 3) / 4) * 4;
     int32_t *csum = (int32_t *)((char *)d_workspace + ((bins_bytes + 255) / 256) * 256);
-    double *esum = (double *)((char *)csum + (((size_t)nu * 4 * (bins_per_unit + 1) * 4 + 255) / 256) * 256);
+    double *esum = (double *)((char *)csum + (((size_t)nu * 4 * cstride * 4 + 255) / 256) * 256);
     cudaError_t e = cudaMemsetAsync(bins, 0, bins_bytes, s);
     if (e != cudaSuccess)
         return fail(CGRB_E_CUDA, "cgrb_gbm_trigger: memset: %s", cudaGetErrorString(e));
@@ -641,7 +643,7 @@ int cgrb_gbm_trigger(const cgrb_unit_t *d_units, int n_units, const cgrb_work_t 
     if (e != cudaSuccess)
         return fail(CGRB_E_CUDA, "cgrb_gbm_trigger: shared memory opt-in: %s", cudaGetErrorString(e));
     LAUNCH("k_trig_eval", s, k_trig_eval<<<n_units, NT, TRIG_EVAL_SMEM, s>>>(d_units, n_units, *par, d_times_out, d_counts,
-                                                               bins_per_unit, bins, csum, esum, d_out));
+                                                               bins_per_unit, bins, cstride, csum, esum, d_out));
     return check_launch("cgrb_gbm_trigger");
 }
 

@@ -298,12 +298,19 @@ __device__ __noinline__ int trig_detail(const int32_t *__restrict__ cr, const do
 __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_unit_t *__restrict__ units, int n_units,
                                                   cgrb_trigger_par_t par, const double *__restrict__ times_out,
                                                   const cgrb_counts_t *__restrict__ counts, int64_t bins_per_unit,
-                                                  const int32_t *__restrict__ bins, int32_t *__restrict__ csum,
-                                                  double *__restrict__ esum, cgrb_trigger_t *__restrict__ out)
+                                                  const int32_t *__restrict__ bins, int64_t cstride,
+                                                  int32_t *__restrict__ csum, double *__restrict__ esum,
+                                                  cgrb_trigger_t *__restrict__ out)
 {
     const int ui = blockIdx.x;
     if (ui >= n_units)
         return;
+#ifdef TRIG_TIMING
+    long long tacc[8] = {0}, tlast = clock64();
+#define TT_MARK(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define TT_MARK(i)
+#endif
     const cgrb_unit_t *u = units + ui;
     const int64_t n = counts[ui].n_kept;
     cgrb_trigger_t res;
@@ -333,8 +340,11 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         return;
     }
     const int32_t *ub = bins + (size_t)ui * TRIG_NARR * bins_per_unit;
-    int32_t *cs = csum + (size_t)ui * 4 * (bins_per_unit + 1);
-    double *es = esum + (size_t)ui * (bins_per_unit + 1);
+    // prefix arrays: entry k = sum over the bins < k; entry 0 sits three elements into a 16-byte aligned row of
+    // `cstride` elements (a multiple of 4), so that entries k + 1 .. k + 4 of a thread's four bins are one aligned vector
+    int32_t *cs = csum + (size_t)ui * 4 * cstride + 3;
+    double *es = esum + (size_t)ui * cstride + 3;
+    const bool vec = (bins_per_unit & 3) == 0;          // the bin arrays of a unit are 16-byte aligned rows as well
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // prefix sums: counts after the reference's float round trip, exposures = (stop - start) - dead time.
     // Every thread owns TRIG_PB consecutive bins per round (serial prefix inside), the thread totals of all
@@ -352,11 +362,12 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         if ((int)(__dmul_rn(__ddiv_rn((double)c, dt), dt)) < c)
             atomicOr(&s_loss[c >> 5], 1u << (c & 31));
     __syncthreads();
+    TT_MARK(0);
     int carry_c[4] = {0, 0, 0, 0};
     double carry_e = 0.0;
     if (threadIdx.x == 0) {
         for (int r = 0; r < 4; r++)
-            cs[r * (bins_per_unit + 1)] = 0;
+            cs[r * cstride] = 0;
         es[0] = 0.0;
     }
     int par_ = 0;
@@ -364,11 +375,34 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         const int64_t kf = base + (int64_t)TRIG_PB * threadIdx.x;      // this thread's first bin
         int c[4][TRIG_PB];
         double e[TRIG_PB];
+        int na[TRIG_PB], no[TRIG_PB];
+        if (TRIG_PB == 4 && vec && kf + 3 < bins_per_unit) {
+            // bins at and beyond nb are zero (never written), so whole vectors can be read
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int4 v = *reinterpret_cast<const int4 *>(ub + r * bins_per_unit + kf);
+                c[r][0] = v.x, c[r][1] = v.y, c[r][2] = v.z, c[r][3] = v.w;
+            }
+            const int4 va = *reinterpret_cast<const int4 *>(ub + 4 * bins_per_unit + kf);
+            const int4 vo = *reinterpret_cast<const int4 *>(ub + 5 * bins_per_unit + kf);
+            na[0] = va.x, na[1] = va.y, na[2] = va.z, na[3] = va.w;
+            no[0] = vo.x, no[1] = vo.y, no[2] = vo.z, no[3] = vo.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < TRIG_PB; j++) {
+                const bool in = kf + j < nb;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    c[r][j] = in ? ub[r * bins_per_unit + kf + j] : 0;
+                na[j] = in ? ub[4 * bins_per_unit + kf + j] : 0;
+                no[j] = in ? ub[5 * bins_per_unit + kf + j] : 0;
+            }
+        }
 #pragma unroll
         for (int r = 0; r < 4; r++)
 #pragma unroll
             for (int j = 0; j < TRIG_PB; j++) {
-                const int raw = (kf + j < nb) ? ub[r * bins_per_unit + kf + j] : 0;
+                const int raw = c[r][j];
                 // (rate * dt).astype(int)
                 c[r][j] = ((unsigned)raw < TRIG_LOSS_N) ? raw - (int)((s_loss[raw >> 5] >> (raw & 31)) & 1u)
                                                        : (int)(__dmul_rn(__ddiv_rn((double)raw, dt), dt));
@@ -377,9 +411,8 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         for (int j = 0; j < TRIG_PB; j++) {
             e[j] = 0.0;
             if (kf + j < nb) {
-                const int na = ub[4 * bins_per_unit + kf + j], no = ub[5 * bins_per_unit + kf + j];
-                const double dead = __dadd_rn(__dmul_rn(trig_u2d((unsigned)(na - no)), 2.0e-6),
-                                              __dmul_rn(trig_u2d((unsigned)no), 10.0e-6));
+                const double dead = __dadd_rn(__dmul_rn(trig_u2d((unsigned)(na[j] - no[j])), 2.0e-6),
+                                              __dmul_rn(trig_u2d((unsigned)no[j]), 10.0e-6));
                 const int kk = (int)(kf + j);
                 e[j] = __dadd_rn(__dadd_rn(g.edge32(kk + 1), -g.edge32(kk)), -dead);
             }
@@ -422,22 +455,35 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
             }
         }
         const double off_e = carry_e + (before_e + (ie - te));
-#pragma unroll
-        for (int j = 0; j < TRIG_PB; j++)
-            if (kf + j < nb)
-                es[kf + j + 1] = off_e + e[j];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int off_c = carry_c[r] + (before_c[r] + ic[r] - c[r][TRIG_PB - 1]);
+        const bool whole = TRIG_PB == 4 && kf + 3 < nb;     // all four bins exist: aligned vector stores
+        if (whole) {
+            double2 *d = reinterpret_cast<double2 *>(es + kf + 1);
+            d[0] = make_double2(off_e + e[0], off_e + e[1]);
+            d[1] = make_double2(off_e + e[2], off_e + e[3]);
+        } else {
 #pragma unroll
             for (int j = 0; j < TRIG_PB; j++)
                 if (kf + j < nb)
-                    cs[r * (bins_per_unit + 1) + kf + j + 1] = off_c + c[r][j];
+                    es[kf + j + 1] = off_e + e[j];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int off_c = carry_c[r] + (before_c[r] + ic[r] - c[r][TRIG_PB - 1]);
+            if (whole)
+                *reinterpret_cast<int4 *>(cs + r * cstride + kf + 1) =
+                    make_int4(off_c + c[r][0], off_c + c[r][1], off_c + c[r][2], off_c + c[r][3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < TRIG_PB; j++)
+                    if (kf + j < nb)
+                        cs[r * cstride + kf + j + 1] = off_c + c[r][j];
+            }
             carry_c[r] += tot_c[r];
         }
         carry_e += tot_e;
     }
     __syncthreads();
+    TT_MARK(1);
     // the search: energy ranges a..d, time scales longest first; the first combination (in that order) with
     // a window at or above the threshold wins, at its first window.  Chunk by chunk of TRIG_CH window starts
     // (+ the longest window span): the exposure prefix is staged once per chunk as fp32 relative to the chunk
@@ -469,7 +515,7 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     unsigned range_ok = 0u;                                             // `if sum(counts) == 0: continue`
 #pragma unroll
     for (int r = 0; r < 4; r++)
-        range_ok |= (cs[r * (bins_per_unit + 1) + nb] != 0) ? (1u << r) : 0u;
+        range_ok |= (cs[r * cstride + nb] != 0) ? (1u << r) : 0u;
     const int64_t n_i_max = nb - (n_bkg + 1 + n_src);                   // shortest gap: 1 bin
     const int n_chunks = (staged_ok && n_i_max > 0) ? (int)((n_i_max + TRIG_CH - 1) / TRIG_CH) : 0;
     // a combination is identified by key = 16 r + (index of the time scale, longest first): the smallest key with a
@@ -486,7 +532,7 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
     auto prefetch = [&](int nx) {
         const int64_t c0 = (int64_t)(nx >> 2) * TRIG_CH;
         const int n_st = (int)(min(nb, c0 + TRIG_CH + TRIG_SPAN) - c0) + 1;
-        const int32_t *src = cs + (nx & 3) * (bins_per_unit + 1) + c0;
+        const int32_t *src = cs + (nx & 3) * cstride + c0;
         for (int k = threadIdx.x; k < n_st; k += NT) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(s_raw + k);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + k) : "memory");
@@ -503,7 +549,7 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         const int64_t c0 = (int64_t)(it >> 2) * TRIG_CH;
         const int64_t hi = min(nb, c0 + TRIG_CH + TRIG_SPAN);
         const int n_st = (int)(hi - c0) + 1;
-        const int32_t *cr = cs + r * (bins_per_unit + 1);
+        const int32_t *cr = cs + r * cstride;
         const int ns = n_scales[r];
         if (staged_chunk != (it >> 2)) {
             staged_chunk = it >> 2;
@@ -539,9 +585,11 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
 #pragma unroll
             for (int q = 1; q < NW; q++)
                 exm = fminf(exm, s_min[q]);
+            TT_MARK(2);
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();                                // the count prefix of (chunk, range) has landed
+        TT_MARK(3);
         const bool open = 16 * r < best_key;            // (a prefetch issued before the last hit may be moot)
         const int i_end = (int)(min(c0 + (int64_t)TRIG_CH, n_i_max) - c0);
         // Nearly every window is far below the threshold, which is decided in fp32 (full rate, no 64-bit
@@ -576,36 +624,45 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
             }
         }
         __syncthreads();                                // s_raw is free again
+        TT_MARK(4);
         const int nx = next_active(it);
         if (nx >= 0)
             prefetch(nx);
         if (open) {
-            // window i with gap n_gap exists iff i + n_bkg + n_gap + n_src < nb, i.e. n_gap < room(i)
+            // window i with gap n_gap = 2^gx exists iff i + n_bkg + n_gap + n_src < nb, i.e. n_gap < room(i); the time
+            // scales still open in this range are those with an index ns - 1 - gx below s_lim
             const int64_t room0 = nb - n_bkg - n_src - c0;
-            const int s_lim = best_key - 16 * r;        // only time scales with an index below this are still open
+            const int s_lim = best_key - 16 * r;
+            const unsigned open_gx = ((1u << ns) - 1u) & ~((1u << max(ns - s_lim, 0)) - 1u);
 #pragma unroll 1
             for (int li = threadIdx.x; li < i_end; li += NT) {
                 const int room = (int)min(room0 - li, (int64_t)1024);
+                // gaps that exist: 2^gx < room  <=>  gx < ceil(log2(room))
+                const unsigned fit = (room > 1) ? ((1u << (32 - __clz(room - 1))) - 1u) : 0u;
                 const float need = s_need[li];
                 const float *ps = s_sw + li + nbk;
+                // all ten source-window sums at once (in bounds of the staged array for every gap), one bit per
+                // time scale that could fire: no branch until something does
+                unsigned cand = 0u;
 #pragma unroll
-                for (int gx = 9; gx >= 0; gx--) {
+                for (int gx = 0; gx < 10; gx++)
+                    cand |= (ps[1 << gx] >= need) ? (1u << gx) : 0u;
+                cand &= open_gx & fit;
+                while (cand) {
+                    const int gx = 31 - __clz(cand);            // longest time scale first
+                    cand &= ~(1u << gx);
                     const int n_gap = 1 << gx;
-                    if (gx >= ns || n_gap >= room || ns - 1 - gx >= s_lim)
-                        continue;
-                    const float Sf = ps[n_gap];
-                    if (Sf < need)
-                        continue;
                     const int64_t i = c0 + li;
                     if (i >= (int64_t)((volatile int *)s_hit[r])[ns - 1 - gx])
                         continue;                       // an earlier window of this combination has fired already
-                    if (trig_detail(cr, es, s_ef, li, i, nbk, nsr, n_gap, Sf, use_pre, min_eb, min_ex, thr2f, thr, &razor) &&
+                    if (trig_detail(cr, es, s_ef, li, i, nbk, nsr, n_gap, ps[n_gap], use_pre, min_eb, min_ex, thr2f, thr, &razor) &&
                         g.edge(i + n_bkg + n_gap) > -1.0)
                         atomicMin(&s_hit[r][ns - 1 - gx], (int)i);
                 }
             }
         }
         __syncthreads();
+        TT_MARK(5);
         for (int key = 16 * r; key < min(best_key, 16 * r + ns); key++)
             if (s_hit[r][key - 16 * r] != INT_MAX) {
                 best_key = key;
@@ -625,6 +682,11 @@ __global__ void __launch_bounds__(NT, TRIG_EVAL_CTAS) k_trig_eval(const cgrb_uni
         res.time = g.edge((int64_t)s_hit[r][sidx] + n_bkg + n_gap);
         res.time_scale = dt * (double)n_gap;
     }
+#ifdef TRIG_TIMING
+    if (threadIdx.x == 0 && (blockIdx.x % 400) == 7)
+        printf("TT unit %d nb %d: setup %lld prefix %lld | ef-stage %lld wait-counts %lld convert %lld search %lld\n", ui, (int)nb,
+               tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5]);
+#endif
     __shared__ int s_razor;
     if (threadIdx.x == 0)
         s_razor = 0;

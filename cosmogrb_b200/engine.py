@@ -728,7 +728,7 @@ class Engine(object):
         w, dw, _ = self._work(b, 2, _capi.TRIG_TILE)
         u = b.units
         span = float(np.max(np.maximum(u["bkg_tstop"], u["src_tstop"]) - np.minimum(u["bkg_tstart"], u["src_tstart"])))
-        bins_per_unit = int(math.ceil(span / base_timescale)) + 4
+        bins_per_unit = (int(math.ceil(span / base_timescale)) + 4 + 3) // 4 * 4     # a multiple of 4: aligned rows
         cb = self.to_device(np.ascontiguousarray(chan_bounds, dtype=np.int32).reshape(-1, 8))
         ws = self.empty(self.lib.cgrb_gbm_trigger_workspace_bytes(b.n_units, bins_per_unit), torch.uint8)
         out = self.empty(b.n_units * _capi.TRIGGER_DTYPE.itemsize, torch.uint8)
