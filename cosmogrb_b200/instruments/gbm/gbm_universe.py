@@ -156,6 +156,7 @@ class _GBMBatchedUniverse(Universe):
             t3 = t_()
             tr = None
             if save:
+                ready.synchronize()         # the batch ran on its own stream: the copies below are issued on the caller's
                 arrays = eng.to_host(b, pinned)
                 c = arrays["counts"]
                 self._save_chunk(idx, b, arrays, ang)
@@ -192,6 +193,20 @@ class _GBMBatchedUniverse(Universe):
         # bytes of event buffers per batch (two batches are in flight); COSMOGRB_B200_BATCH_BYTES overrides it for
         # tuning runs without moving the skip threshold above
         budget = float(os.environ.get("COSMOGRB_B200_BATCH_BYTES", memory_budget / 2))
+        # The two batches in flight run on two compute streams (even / odd batches; each owns one pool slot, so
+        # buffer reuse stays stream-ordered): the last, partly filled wave of CTAs of one batch's kernels and its
+        # latency-bound stretches (trigger search, look-backs) are filled with the other batch's work.
+        # COSMOGRB_B200_STREAMS=1 puts everything back on the caller's stream.
+        caller_stream = torch.cuda.current_stream(eng.device)
+        n_streams = int(os.environ.get("COSMOGRB_B200_STREAMS", "2"))
+        if n_streams > 1:
+            if getattr(eng, "_batch_streams", None) is None:
+                eng._batch_streams = [torch.cuda.Stream(device=eng.device) for _ in range(2)]
+            batch_streams = eng._batch_streams
+            for bs in batch_streams:
+                bs.wait_stream(caller_stream)
+        else:
+            batch_streams = [caller_stream, caller_stream]
         pos, in_flight = 0, None
         while pos < len(todo):
             # grow the batch until the memory budget (or grbs_per_batch) is reached
@@ -208,15 +223,16 @@ class _GBMBatchedUniverse(Universe):
             t1 = t_()
             eng.use_pool(self.n_batches % 2)          # event buffers recycled from the slot used two batches ago
             try:
-                b = eng.new_batch(units, dtab, compute_fmax=False)
-                t2 = t_()
-                eng.process(b, Philox(seed))
-                if trigger:
-                    eng.gbm_trigger(b, chan_bounds, threshold=trigger_threshold, fetch=False)
+                with torch.cuda.stream(batch_streams[self.n_batches % 2]):
+                    b = eng.new_batch(units, dtab, compute_fmax=False)
+                    t2 = t_()
+                    eng.process(b, Philox(seed))
+                    if trigger:
+                        eng.gbm_trigger(b, chan_bounds, threshold=trigger_threshold, fetch=False)
+                    ready = torch.cuda.Event()
+                    ready.record(torch.cuda.current_stream(eng.device))
             finally:
                 eng.use_pool(None)
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(eng.device))
             t3 = t_()
             tm["build_units"] += t1 - t0
             tm["new_batch"] += t2 - t1
@@ -228,6 +244,9 @@ class _GBMBatchedUniverse(Universe):
             self.n_batches += 1
         if in_flight is not None:
             finish(in_flight)
+        if n_streams > 1:
+            for bs in batch_streams:
+                caller_stream.wait_stream(bs)
         # the one exchange of the population run: per-unit event counts of every rank
         t0 = t_()
         gathered = gather_event_counts(local_counts.reshape(-1, 3))

@@ -147,7 +147,9 @@ q = b.get("population")
 if q:
     out.append(f"| population C5 (`GBM_CPL_Universe.go(save=False, trigger=True)`, strong scaling) | {q['n_grbs']} bursts, {q['n_simulated']} simulated, "
                f"{q['n_skipped']} skipped: {q['grbs_per_s']:.0f} GRB/s, {q['events_per_s']:.4g} events/s in {q['ms'] / 1e3:.2f} s "
-               f"({q['kernel_ms_per_gpu'] / 1e3:.2f} s of kernels, {q['batches_per_gpu']} batches) |")
+               + (f"({q['kernel_ms_per_gpu'] / 1e3:.2f} s of kernels, " if "kernel_ms_per_gpu" in q else
+                  f"({q['kernel_ms_per_1000_bursts']:.1f} ms of kernels per 1000 bursts in the single-stream sample pass, ")
+               + f"{q['batches_per_gpu']} batches) |")
 cb = b.get("cpu_baseline")
 if cb:
     out.append(f"| cpu_baseline ({cb['kind']}, {cb['cores']} host threads) | {cb['value']:.4g} {cb['unit']} ({cb['sample']}) |")
@@ -174,7 +176,10 @@ if e:
                f"({b['config']['rejection_trials'] / b['config']['source_events']:.3f} trials per photon).")
 if q:
     nsim = q["n_simulated"]
-    out += ["", f"## Population kernels: live CUDA events of the {q['n_grbs']}-burst bench leg vs ncu on 256 bursts (ms per 1000 simulated bursts)",
+    if "kernels_ms_per_1000_bursts" in q:
+        q = dict(q, kernels={k: v * nsim / 1000.0 for k, v in q["kernels_ms_per_1000_bursts"].items()})
+        out += ["", q["kernel_sample"]]
+    out += ["", f"## Population kernels: live CUDA events of the bench leg vs ncu on 256 bursts (ms per 1000 simulated bursts)",
             "| kernel | live | ncu launch list | ncu DRAM B/event | ncu GB/s | issue % | warps active % | L1 hit % | L2 hit % | regs |", "|---|---|---|---|---|---|---|---|---|---|"]
     for n, v in q["kernels"].items():
         a = popagg.get(n)

@@ -18,9 +18,10 @@ for path in sys.argv[1:]:
     if d.get("population"):
         q = d["population"]
         print(f"   population: {q['n_grbs']} GRBs ({q.get('n_simulated')} simulated) {q['events']:.4g} events in {q['ms']:.1f} ms -> {q['grbs_per_s']:.1f} GRB/s "
-              f"{q['events_per_s']:.4g} ev/s; kernels {q['kernel_ms_per_gpu']:.1f} ms, batches {q['batches_per_gpu']}")
+              f"{q['events_per_s']:.4g} ev/s; kernels {q.get('kernel_ms_per_gpu', q.get('kernel_ms_per_1000_bursts', 0)):.1f} ms"
+              f"{' per 1000 bursts (sample pass)' if 'kernel_ms_per_1000_bursts' in q else ''}, batches {q['batches_per_gpu']}")
         print(f"      host seconds: {q.get('host_seconds')}  detail: {q.get('host_detail')}")
-        for k, v in q["kernels"].items():
+        for k, v in q.get("kernels", q.get("kernels_ms_per_1000_bursts", {})).items():
             print(f"      {k:26s} {v:9.3f} ms")
         for k, v in q["hbm_kernels"].items():
             print(f"      hbm {k:22s} {v['achieved_gbs']:.0f} GB/s frac {v['frac_of_measured_hbm']:.3f}")
