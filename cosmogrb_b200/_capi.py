@@ -139,6 +139,8 @@ EXPORTS = (
     "cgrb_sample_energy",
     "cgrb_energy_workspace_bytes",
     "cgrb_sample_energy_envelope",
+    "cgrb_energy_envelope_tables",
+    "cgrb_sample_energy_envelope_prepared",
     "cgrb_digitize",
     "cgrb_sample_background_workspace_bytes",
     "cgrb_sample_background",
@@ -188,6 +190,8 @@ def load():
     lib.cgrb_energy_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_energy_workspace_bytes.restype = i64
     lib.cgrb_sample_energy_envelope.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
+    lib.cgrb_energy_envelope_tables.argtypes = [vp, vp, i32, i32, vp, i64, vp]
+    lib.cgrb_sample_energy_envelope_prepared.argtypes = [vp, vp, i32, vp, i64, i32, rp, i64, vp, i64, vp, vp, vp, vp, vp, vp]
     lib.cgrb_digitize.argtypes = [vp, vp, i32, vp, i64, rp, vp, vp, vp, vp, vp]
     lib.cgrb_sample_background_workspace_bytes.argtypes = [i32, i64]
     lib.cgrb_sample_background_workspace_bytes.restype = i64

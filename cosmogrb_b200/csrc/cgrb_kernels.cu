@@ -340,30 +340,37 @@ int64_t cgrb_energy_workspace_bytes(int n_units, int64_t n_rows)
     return tabs + (int64_t)sizeof(double) * ENV_ROW * nr + (int64_t)CGRB_ENV_SEGS * nr;
 }
 
-int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+// what: bit 0 = build the per-unit tables + rows, bit 1 = sample
+static int energy_envelope_impl(int what, const char *who, const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                                 const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
                                 const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
                                 const double *d_times_src, double *d_energy_src, uint8_t *d_pha_src,
                                 int32_t *d_trials, cgrb_counts_t *d_counts, void *stream)
 {
-    if (!d_dtab || !d_units || n_units <= 0 || !d_work || n_work <= 0 || !d_times_src ||
-        (!d_energy_src && !d_pha_src) || !d_counts || !d_workspace || n_rows < n_units)
-        return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: bad argument%s");
+    if (!d_dtab || !d_units || n_units <= 0 || !d_workspace || n_rows < n_units)
+        return fail(CGRB_E_BADARG, "%s: bad argument", who);
     if (interp_extrap != 0 && interp_extrap != 1)
-        return fail(CGRB_E_BADARG, "cgrb_sample_energy_envelope: interp_extrap must be 0 (linear) or 1 (clamp)%s");
-    int rc = check_rng(rng, "cgrb_sample_energy_envelope");
-    if (rc)
-        return rc;
-    if (rng->mode != 0)
-        return fail(CGRB_E_UNSUPPORTED,
-                    "cgrb_sample_energy_envelope: injected uniforms replay the literal sampler; use cgrb_sample_energy%s");
+        return fail(CGRB_E_BADARG, "%s: interp_extrap must be 0 (linear) or 1 (clamp)", who);
+    if (what & 2) {
+        if (!d_work || n_work <= 0 || !d_times_src || (!d_energy_src && !d_pha_src) || !d_counts)
+            return fail(CGRB_E_BADARG, "%s: bad argument", who);
+        int rc = check_rng(rng, who);
+        if (rc)
+            return rc;
+        if (rng->mode != 0)
+            return fail(CGRB_E_UNSUPPORTED, "%s: injected uniforms replay the literal sampler; use cgrb_sample_energy", who);
+    }
     cudaStream_t s = (cudaStream_t)stream;
     EnergyUnitTab *etab = (EnergyUnitTab *)d_workspace;
     int64_t tabs = ((int64_t)sizeof(EnergyUnitTab) * n_units + 255) / 256 * 256;
     double *rows = (double *)((char *)d_workspace + tabs);
     uint8_t *row_guides = (uint8_t *)(rows + (size_t)ENV_ROW * n_rows);
+    if (what & 1) {
     LAUNCH("k_energy_tables", s, k_energy_tables<<<n_units, 256, 0, s>>>(d_dtab, d_units, n_units, interp_extrap, etab));
     LAUNCH("k_energy_rows", s, k_energy_rows<<<(unsigned)n_rows, NT, 0, s>>>(d_units, n_units, etab, rows, row_guides, n_rows));
+    }
+    if (!(what & 2))
+        return check_launch(who);
 #define ENV_LAUNCH(F, D, M)                                                                                       \
     LAUNCH("k_sample_energy_env", s, (k_sample_energy_env<F, D, M><<<(unsigned)n_work, NT, 0, s>>>(                \
         d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, rows, row_guides, d_times_src,    \
@@ -388,7 +395,35 @@ int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units
     } else
         ENV_LAUNCH(false, true, ENV_MIN_CTAS);
 #undef ENV_LAUNCH
-    return check_launch("cgrb_sample_energy_envelope");
+    return check_launch(who);
+}
+
+int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                                const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
+                                const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
+                                const double *d_times_src, double *d_energy_src, uint8_t *d_pha_src,
+                                int32_t *d_trials, cgrb_counts_t *d_counts, void *stream)
+{
+    return energy_envelope_impl(3, "cgrb_sample_energy_envelope", d_dtab, d_units, n_units, d_work, n_work, interp_extrap, rng,
+                                max_trials, d_workspace, n_rows, d_times_src, d_energy_src, d_pha_src, d_trials, d_counts, stream);
+}
+
+int cgrb_energy_envelope_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, int interp_extrap,
+                                void *d_workspace, int64_t n_rows, void *stream)
+{
+    return energy_envelope_impl(1, "cgrb_energy_envelope_tables", d_dtab, d_units, n_units, nullptr, 0, interp_extrap, nullptr, 0,
+                                d_workspace, n_rows, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int cgrb_sample_energy_envelope_prepared(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                                         const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
+                                         const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
+                                         const double *d_times_src, double *d_energy_src, uint8_t *d_pha_src,
+                                         int32_t *d_trials, cgrb_counts_t *d_counts, void *stream)
+{
+    return energy_envelope_impl(2, "cgrb_sample_energy_envelope_prepared", d_dtab, d_units, n_units, d_work, n_work, interp_extrap,
+                                rng, max_trials, d_workspace, n_rows, d_times_src, d_energy_src, d_pha_src, d_trials, d_counts,
+                                stream);
 }
 
 int cgrb_digitize(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work,

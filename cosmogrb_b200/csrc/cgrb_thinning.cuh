@@ -153,7 +153,12 @@ __global__ void __launch_bounds__(NT) k_gap_prefix(const cgrb_unit_t *__restrict
     const double inv_f = 1.0 / rate;
     const uint32_t stage = (WHICH == 0) ? ST_SRC_TIME : ST_BKG;
     const uint32_t sid = u->stream_id;
-    const int64_t n = min((int64_t)CGRB_SEG, cap - wk.start);
+    // a segment ends where the unit's next work entry starts (segments are at most CGRB_SEG candidates; small units
+    // are cut into shorter ones by the host so that their serial depth stays low)
+    int64_t seg_len = CGRB_SEG;
+    if (w + 1 < n_work && work[w + 1].unit == wk.unit)
+        seg_len = work[w + 1].start - wk.start;
+    const int64_t n = min(seg_len, cap - wk.start);
     double *out = prefix_out + ((WHICH == 0) ? u->src_off : u->bkg_off + 1) + wk.start;
     double carry = 0.0;
     bool exhausted = false;
@@ -371,7 +376,10 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
         s_last = t0;
     __syncthreads();
 
-    const int64_t n = min((int64_t)CGRB_SEG, u.src_cap - wk.start);
+    int64_t seg_len = CGRB_SEG;             // (as in k_gap_prefix: up to the unit's next work entry)
+    if (w + 1 < n_work && work[w + 1].unit == wk.unit)
+        seg_len = work[w + 1].start - wk.start;
+    const int64_t n = min(seg_len, u.src_cap - wk.start);
     // squeeze table of p(t) = lambda(t)/fmax (cgrb_thin_tables): decides most candidates without
     // evaluating lambda; the rest take the exact test, so decisions are those of the exact test
     const bool squeeze = thin_tab != nullptr && u.tab_n >= 4;

@@ -26,6 +26,12 @@ DEFAULT_SEED = 0x00C0560612B
 # photons per CTA work item of the energy kernels: amortises the 44 KB table prologue (measured on the bright
 # burst: 8192 -> 3.94 ms, 16384 -> 3.80, 32768 -> 3.82, 65536 -> 4.07); CGRB_ENERGY_CHUNK overrides for tuning
 ENERGY_CHUNK = int(os.environ.get("CGRB_ENERGY_CHUNK", 16384))
+BACKGROUND_SIDE_STREAM = os.environ.get("CGRB_BACKGROUND_SIDE_STREAM", "1") != "0"
+SIDE_STREAM_MAX_UNITS = int(os.environ.get("CGRB_SIDE_STREAM_MAX_UNITS", 64))     # a few bursts x 14 detectors
+# thinning: units with at most this many candidate slots are cut into short segments (a segment is processed by one
+# CTA, 512 candidates at a time: 16 serial rounds for a full 8192-candidate segment, which is what a single small
+# burst waits for); both numbers are even multiples of the kernels' 512-candidate tile
+SMALL_UNIT_SEGMENTS = (int(os.environ.get("CGRB_SMALL_UNIT_SLOTS", 65536)), int(os.environ.get("CGRB_SMALL_SEG", 1024)))
 DIGITIZE_CHUNK = 65536       # photons per CTA of the stand-alone digitize kernel (amortises staging the 18 KB guide)
 DEFAULT_MAX_TRIALS = 1 << 22
 
@@ -402,11 +408,26 @@ class Engine(object):
         torch = _torch()
         b.d_counts = torch.zeros(b.n_units * COUNTS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
 
-    def _work(self, b, which, chunk):
-        key = (which, chunk)
+    def _work(self, b, which, chunk, small=None):
+        """Work list of a batch: (unit, chunk) entries, ``chunk`` elements each.  ``small = (limit, chunk_small)``:
+        units whose capacity is at most ``limit`` are cut into chunks of ``chunk_small`` instead -- a function of
+        the unit alone, so results do not depend on what else is in the batch."""
+        key = (which, chunk, small)
         if key not in b.work:
             t0 = _now()
-            w = _capi.build_work(b.units, which, chunk)
+            if small is None:
+                w = _capi.build_work(b.units, which, chunk)
+            else:
+                assert which == 0
+                cap = b.units["src_cap"].astype(np.int64)
+                ch = np.where(cap <= small[0], small[1], chunk).astype(np.int64)
+                nseg = np.maximum((cap + ch - 1) // ch, 1)
+                w = np.zeros(int(nseg.sum()), dtype=_capi.WORK_DTYPE)
+                w["unit"] = np.repeat(np.arange(b.n_units, dtype=np.int32), nseg)
+                first = np.concatenate(([0], np.cumsum(nseg)[:-1]))
+                seg = np.arange(len(w), dtype=np.int64) - np.repeat(first, nseg)
+                w["seg"] = seg
+                w["start"] = seg * np.repeat(ch, nseg)
             wb = _unit_work_begin(w, b.n_units)
             t1 = _now()
             b.work[key] = (w, self.to_device(w), self.to_device(wb))
@@ -449,13 +470,22 @@ class Engine(object):
         without waiting for them -- the caller keeps launching the next batch on the compute stream and
         synchronises ``copy_stream`` before touching the arrays."""
         torch = _torch()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready_event)
+        # The counters size the copies, so the host has to see them first.  They come back on a stream of their own,
+        # ordered behind the batch's kernels only: on the copy stream they would queue behind the PREVIOUS batch's
+        # event lists (tens of ms), the host would enqueue this batch's copies only after those had finished, and the
+        # copy engine would idle for the host's enqueue latency once per batch.
+        if getattr(self, "_count_stream", None) is None:
+            self._count_stream = torch.cuda.Stream(device=self.device)
+        cnt = self._count_stream
+        with torch.cuda.stream(cnt):
+            cnt.wait_event(ready_event)
             cbuf = torch.empty(b.d_counts.numel(), dtype=torch.uint8, pin_memory=True)
             cbuf.copy_(b.d_counts, non_blocking=True)
-            copy_stream.synchronize()           # the counters size the copies
-            b.counts = cbuf.numpy().view(COUNTS_DTYPE).copy()
-            self.check_status(b)
+            cnt.synchronize()
+        b.counts = cbuf.numpy().view(COUNTS_DTYPE).copy()
+        self.check_status(b)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready_event)
             return self._enqueue_event_copies(b, None, extra)
 
     def fetch_results_after(self, b, ready_event, want_trigger=False):
@@ -521,7 +551,7 @@ class Engine(object):
     # -- stages ---------------------------------------------------------------------------------
     def sample_events(self, b, rng, want_candidates=False):
         torch = _torch()
-        w, dw, dwb = self._work(b, 0, _capi.SEG)
+        w, dw, dwb = self._work(b, 0, _capi.SEG, small=SMALL_UNIT_SEGMENTS)
         nw = len(w)
         t = b.t
         t["segsum"] = self.empty(nw, torch.float64)
@@ -576,8 +606,22 @@ class Engine(object):
             out[has] = L[torch.as_tensor(last.astype(np.int64), device=self.device)].cpu().numpy()
         return out
 
+    def energy_tables(self, b):
+        """The per-unit envelope tables of the tabulated-envelope energy sampler (they depend on the units only), on the
+        current stream; ``sample_energy(..., tables_ready=True)`` then samples with them (the caller orders the two)."""
+        torch = _torch()
+        t = b.t
+        if "etab" not in t:
+            t["etab"] = self.empty(self.lib.cgrb_energy_workspace_bytes(b.n_units, b.n_etab_rows), torch.uint8)
+        _capi.check(
+            self.lib.cgrb_energy_envelope_tables(b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units,
+                                                 self._extrap_code(b.interp_extrap), t["etab"].data_ptr(), b.n_etab_rows,
+                                                 self.stream),
+            "cgrb_energy_envelope_tables")
+        self.launches += 2
+
     def sample_energy(self, b, rng, max_trials=DEFAULT_MAX_TRIALS, want_trials=False, sampler=None,
-                      fold=False, want_energy=True):
+                      fold=False, want_energy=True, tables_ready=False):
         """``sampler``: "literal" (the reference's rejection loop, trial for trial; always used under
         injected uniforms) or "envelope" (same output distribution from a tabulated envelope, Philox
         only; the default under Philox).  ``fold=True`` (envelope sampler only) also folds every photon
@@ -608,15 +652,15 @@ class Engine(object):
             pha = None
             if fold:
                 t["pha_src"] = pha = self.empty(b.n_src_slots, torch.uint8)
+            fn = self.lib.cgrb_sample_energy_envelope_prepared if tables_ready else self.lib.cgrb_sample_energy_envelope
             _capi.check(
-                self.lib.cgrb_sample_energy_envelope(
-                    b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
-                    self._extrap_code(b.interp_extrap), C.byref(desc), int(max_trials), t["etab"].data_ptr(),
-                    b.n_etab_rows, t["times_src"].data_ptr(), en.data_ptr() if en is not None else None,
-                    pha.data_ptr() if pha is not None else None,
-                    tr.data_ptr() if want_trials else None, b.d_counts.data_ptr(), self.stream),
+                fn(b.dtab.data_ptr(), b.d_units.data_ptr(), b.n_units, dw.data_ptr(), len(w),
+                   self._extrap_code(b.interp_extrap), C.byref(desc), int(max_trials), t["etab"].data_ptr(),
+                   b.n_etab_rows, t["times_src"].data_ptr(), en.data_ptr() if en is not None else None,
+                   pha.data_ptr() if pha is not None else None,
+                   tr.data_ptr() if want_trials else None, b.d_counts.data_ptr(), self.stream),
                 "cgrb_sample_energy_envelope")
-            self.launches += 3
+            self.launches += 1 if tables_ready else 3
             return fold
         _capi.check(
             self.lib.cgrb_sample_energy(
@@ -775,12 +819,46 @@ class Engine(object):
                 keep_merged=False):
         """LightCurve.process() for every unit of the batch (lightcurve.py:167-200): source times,
         energies, channels; background times, channels; combine; dead time."""
+        # The background chain (order -> plan -> one-pass kernel) depends on nothing the source chain produces, so it
+        # runs on a side stream next to it and is joined before the merge: a single small burst is a chain of ~20
+        # dependent launches, each far too small to fill the GPU, and this takes three of them off the critical path
+        # Only for small batches: a population batch of thousands of units fills the GPU kernel by kernel, and there
+        # the extra streams cost more than they give (measured: 10,200 -> 6,500-8,600 GRB/s).
+        torch = _torch()
+        main = torch.cuda.current_stream(self.device)
+        side = tables_done = None
+        # (and never inside a pooled population run: the pool hands buffers out in call order, which the branches change)
+        if BACKGROUND_SIDE_STREAM and isinstance(rng, Philox) and b.n_units <= SIDE_STREAM_MAX_UNITS and self._pool is None:
+            sides = self.__dict__.setdefault("_side_streams", {})
+            side = sides.get(main.cuda_stream)
+            if side is None:
+                side = sides[main.cuda_stream] = torch.cuda.Stream(device=self.device)
+            side.wait_stream(main)          # the batch's uploads, and whatever used the pooled buffers before
+            with torch.cuda.stream(side):
+                self.sample_background(b, rng)
+                bkg_done = torch.cuda.Event()
+                bkg_done.record(side)
+            # the energy sampler's per-unit tables depend on the units only: a second branch
+            if (energy_sampler or self.energy_sampler) == "envelope":
+                side2 = sides.get((main.cuda_stream, 2))
+                if side2 is None:
+                    side2 = sides[(main.cuda_stream, 2)] = torch.cuda.Stream(device=self.device)
+                side2.wait_stream(main)
+                with torch.cuda.stream(side2):
+                    self.energy_tables(b)
+                    tables_done = torch.cuda.Event()
+                    tables_done.record(side2)
         self.sample_events(b, rng, want_candidates=diagnostics)
+        if tables_done is not None:
+            main.wait_event(tables_done)
         folded = self.sample_energy(b, rng, max_trials=max_trials, want_trials=diagnostics, sampler=energy_sampler,
-                                    fold=True, want_energy=diagnostics)
+                                    fold=True, want_energy=diagnostics, tables_ready=tables_done is not None)
         if not folded:
             self.digitize_batch(b, rng)
-        self.sample_background(b, rng)
+        if side is None:
+            self.sample_background(b, rng)
+        else:
+            main.wait_event(bkg_done)
         if diagnostics or keep_merged:      # keeps the merged pre-dead-time list (and the per-event selection)
             self.combine(b)
             self.dead_time(b, want_selection=diagnostics)

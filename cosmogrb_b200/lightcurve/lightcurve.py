@@ -94,7 +94,8 @@ class LightCurve(object):
 #: light curves of one call are cut into chunks of about this many event slots when the call is large:
 #: the device->host copy of chunk k then overlaps the kernels of chunk k+1
 PIPELINE_MIN_SLOTS = 8_000_000
-PIPELINE_CHUNKS = 7
+import os as _os
+PIPELINE_CHUNKS = int(_os.environ.get("CGRB_PIPELINE_CHUNKS", 7))      # chunks of a large call (device->host copies of chunk k overlap the kernels of k+1)
 
 
 def _chunks(units, eng):

@@ -262,6 +262,18 @@ int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units
                                 const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
                                 const double *d_times_src, double *d_energy_src, uint8_t *d_pha_src,
                                 int32_t *d_trials, cgrb_counts_t *d_counts, void *stream);
+/* The same in two steps.  The per-unit envelope tables and rows depend on the unit records and the detector tables
+ * only, not on the photons: cgrb_energy_envelope_tables builds them into d_workspace (on any stream, e.g. while the
+ * source times of SourceFunction.sample_events are still being drawn on another), and
+ * cgrb_sample_energy_envelope_prepared then samples with the tables of d_workspace taken as built (the caller orders
+ * the two calls: same stream, or an event).  Together they are cgrb_sample_energy_envelope. */
+int cgrb_energy_envelope_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, int interp_extrap,
+                                void *d_workspace, int64_t n_rows, void *stream);
+int cgrb_sample_energy_envelope_prepared(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
+                                         const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
+                                         const cgrb_rng_t *rng, int64_t max_trials, void *d_workspace, int64_t n_rows,
+                                         const double *d_times_src, double *d_energy_src, uint8_t *d_pha_src,
+                                         int32_t *d_trials, cgrb_counts_t *d_counts, void *stream);
 
 /* Response.digitize (response.py:156-174; numba _digitize :10-25): nearest-CDF channel.
  * Work list as for cgrb_sample_energy.  d_trials (may be NULL; Philox only): the per-photon trial counts written by

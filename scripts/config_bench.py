@@ -29,6 +29,9 @@ threads = len(os.sched_getaffinity(0))
 out = {"host_threads": threads}
 
 
+LAST_KERNELS = {}
+
+
 def gpu_events_per_s(units, reps=20):
     b = eng.new_batch(units, tabs)
     for k in range(3):
@@ -46,6 +49,15 @@ def gpu_events_per_s(units, reps=20):
     eng.check_status(b)
     ev = int(c["n_src"].sum() + c["n_bkg"].sum())
     ms = a.elapsed_time(z) / reps
+    # per-kernel durations of one more step (CUDA events around every launch)
+    _capi.profile_enable(True)
+    eng.reset_counts(b)
+    eng.process(b, Philox(999))
+    torch.cuda.synchronize()
+    LAST_KERNELS.clear()
+    for name, m in _capi.profile_read():
+        LAST_KERNELS[name] = round(LAST_KERNELS.get(name, 0.0) + m, 4)
+    _capi.profile_enable(False)
     return ev, ms, ev / (ms * 1e-3)
 
 
@@ -72,7 +84,8 @@ u1 = np.concatenate([h.unit(det_index=i, stream_id=i, **p1) for i in range(14)])
 ev, ms, rate = gpu_events_per_s(u1)
 n, dt, crate = cpu_events_per_s(p1, (-100.0, 300.0, 500.0))
 out["C1"] = {"gpu_events": ev, "gpu_ms_per_burst": ms, "gpu_events_per_s": rate, "gpu_grbs_per_s": 1e3 / ms,
-             "cpu_events": n, "cpu_s_per_burst": dt, "cpu_events_per_s": crate, "cpu_grbs_per_s": 1.0 / dt}
+             "cpu_events": n, "cpu_s_per_burst": dt, "cpu_events_per_s": crate, "cpu_grbs_per_s": 1.0 / dt,
+             "gpu_kernels_ms": dict(LAST_KERNELS), "gpu_kernels_ms_sum": round(sum(LAST_KERNELS.values()), 4)}
 
 # C3: background only, 1000 s, 14 detectors
 p3 = dict(h.README_DEMO, peak_flux=5e-20)
