@@ -214,7 +214,9 @@ int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_uni
                      int64_t n_nodes_total, void *stream);
 
 /* SourceFunction.sample_events (cpl_source.py:98-114; numba cpl_functions.py:134-188,
- * cpl_constant_functions.py:65-105).  Work list: which=0, chunk=CGRB_SEG.
+ * cpl_constant_functions.py:65-105).  Work list: which=0, chunk <= CGRB_SEG (an even multiple of 512): a segment
+ * ends where the unit's next entry starts, so a caller may cut small units into shorter segments (fewer serial
+ * rounds per CTA); the chunking must be a function of the unit alone if results are to be independent of the batch.
  *   d_segsum/d_segstart [n_work] doubles, d_segcount [n_work] int32: workspace
  *   d_stage   [sum src_cap] doubles: workspace (accepted times per segment)
  *   d_times_src [sum (src_cap+1)]: output, unit u at src_off; entry 0 is tstart

@@ -437,3 +437,51 @@ def test_background_under_philox_equals_a_host_replay_of_the_counters(engine):
     assert np.array_equal(got_p[1:].astype(int), want_p)
     x, y, _, _ = _philox4x32_10(np.uint64(0xFFFFFFFF), 1, sid, 4 | (0xFF << 8), k0, k1)      # event 0: index 0xFFFFFFFFFF
     assert int(got_p[0]) == min(int(np.searchsorted(cdf, _u53(x, y), "right")), 127)
+
+
+def test_side_stream_branches_change_nothing(engine, monkeypatch):
+    """Round 2: for small batches the background chain and the energy sampler's per-unit tables run on side streams
+    next to the source chain (cgrb_energy_envelope_tables + cgrb_sample_energy_envelope_prepared); the six lists
+    are the ones of the single-stream launch sequence, bit for bit."""
+    from cosmogrb_b200 import engine as eng_mod
+
+    dets = ("n0", "b0", "n5")
+    tabs = [h.response(d).device_table(h.bkg_weights(d), "linear") for d in dets]
+    units = np.concatenate([h.unit(det_index=i, stream_id=40 + i, **h.CONFTEST_BRIGHT) for i in range(len(dets))])
+    out = {}
+    for on in (False, True, True):
+        monkeypatch.setattr(eng_mod, "BACKGROUND_SIDE_STREAM", on)
+        b = engine.new_batch(units.copy(), tabs)
+        engine.process(b, Philox(4242))
+        c = engine.fetch_counts(b)
+        engine.check_status(b)
+        lists = [b.view(name, i, kind).copy() for i in range(len(dets))
+                 for name, kind in (("times_out", "kept"), ("pha_out", "kept"), ("times_src", "src"), ("pha_src", "src"),
+                                    ("times_bkg", "bkg"), ("pha_bkg", "bkg"))]
+        out.setdefault(on, []).append((c.copy(), lists))
+    (c0, l0), (c1, l1), (c2, l2) = out[False][0], out[True][0], out[True][1]
+    for k in ("n_src", "n_bkg", "n_kept", "n_candidates", "n_trials", "status"):
+        assert np.array_equal(c0[k], c1[k]) and np.array_equal(c0[k], c2[k]), k
+    assert all(np.array_equal(a, b_) for a, b_ in zip(l0, l1)) and all(np.array_equal(a, b_) for a, b_ in zip(l0, l2))
+
+
+def test_short_segments_of_small_units_are_the_same_process(engine, monkeypatch):
+    """Round 2: a unit with few candidate slots is thinned in 1024-candidate segments instead of 8192 (the kernels take
+    a segment's length from the work list).  The candidates and their uniforms are the same (Philox counters are
+    per candidate); only the association of the running gap sums changes, i.e. the last bits of the times."""
+    from cosmogrb_b200 import engine as eng_mod
+
+    tab = [h.response("n0").device_table(h.bkg_weights("n0"), "linear")]
+    got = {}
+    for small in ((0, 1024), (1 << 40, 1024), (1 << 40, 2048)):
+        monkeypatch.setattr(eng_mod, "SMALL_UNIT_SEGMENTS", small)
+        b = engine.new_batch(h.unit(stream_id=3, **dict(h.CONFTEST_BRIGHT, peak_flux=1e-4)), tab)
+        engine.sample_events(b, Philox(777))
+        c = engine.fetch_counts(b)
+        engine.check_status(b)
+        got[small] = (int(c["n_candidates"][0]), b.view("times_src", 0, "src").copy())
+    ref_n, ref_t = got[(0, 1024)]
+    assert ref_n > 8192                # more than one full-length segment in the reference chunking
+    for k in ((1 << 40, 1024), (1 << 40, 2048)):
+        assert got[k][0] == ref_n and len(got[k][1]) == len(ref_t)
+        np.testing.assert_allclose(got[k][1], ref_t, rtol=1e-13, atol=1e-13)
