@@ -73,7 +73,7 @@ class _GBMBatchedUniverse(Universe):
         return 2e5 * N_DET + 2e10 * pf * self._duration
 
     def _run_batched(self, grbs_per_batch=None, save=True, seed=None, memory_budget=64e9, trigger=False,
-                     trigger_threshold=4.5, simul_trigger_window=0.5, max_n_dets=12):
+                     trigger_threshold=4.5, simul_trigger_window=0.5, max_n_dets=12, runaway="skip"):
         """Batches of GRBs sized to ``memory_budget`` bytes of event buffers.  A burst whose candidate
         count (fmax x duration) does not fit the budget on its own is SKIPPED with a warning and listed in
         ``self.skipped`` (its event counts read -1): the reference's model makes lambda(t) explode for
@@ -142,6 +142,10 @@ class _GBMBatchedUniverse(Universe):
             local_det = np.zeros(len(mine), dtype=bool)
         tm["fmax_pass"] = t_() - t0
         too_big = (sizes > memory_budget) | ~np.isfinite(sizes)
+        if runaway == "raise" and np.any(too_big):
+            names = [self._name[int(mine[j])] for j in np.nonzero(too_big)[0][:8]]
+            raise _capi.EngineError(f"{int(too_big.sum())} burst(s) do not fit the memory budget ({memory_budget:.3g} B of "
+                                    f"event buffers; runaway lambda(t)): {', '.join(names)}{' ...' if too_big.sum() > 8 else ''}")
         for j in np.nonzero(too_big)[0]:
             g = int(mine[j])
             self.skipped.append(g)

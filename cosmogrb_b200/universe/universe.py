@@ -209,12 +209,20 @@ class Universe(object, metaclass=abc.ABCMeta):
             self._parameter_servers.append(ps)
 
     # -- dispatch ---------------------------------------------------------------------------------
-    def go(self, client=None, grbs_per_batch=None, save=True, seed=None, trigger=False):
+    def go(self, client=None, grbs_per_batch=None, save=True, seed=None, trigger=False, runaway="skip"):
         """Simulate the whole population (universe.py:123-149).  ``client`` is accepted for signature
         compatibility (the dask map is replaced by batched GPU launches + rank sharding).  ``trigger=True``
         also runs the GBM trigger (``Survey.process(GBMTrigger)``, survey.py:210-285) on the device while the
-        events are still in HBM: ``self.detected`` / ``self.trigger_results`` for the local bursts."""
+        events are still in HBM: ``self.detected`` / ``self.trigger_results`` for the local bursts.
+        ``runaway``: what to do with a burst whose candidate count does not fit the memory budget (the reference's
+        lambda(t) runs away for low Epeak at late times: 1e10-1e19 candidates, which its own loop would spend years
+        on) -- "skip" (default: warn, leave it out, counts -1, ``self.skipped``) or "raise" (EngineError naming the
+        bursts before anything is simulated)."""
+        if runaway not in ("skip", "raise"):
+            raise ValueError("runaway must be 'skip' or 'raise'")
         kw = dict(trigger=True) if trigger else {}
+        if runaway != "skip":
+            kw["runaway"] = runaway
         self._run_batched(grbs_per_batch=grbs_per_batch, save=save and self._save_path is not None, seed=seed, **kw)
         self._is_processed = True
 

@@ -246,6 +246,12 @@ def test_runaway_unit_is_refused_and_skipped(engine):
     uni.go(seed=3, save=False)
     assert uni.skipped == [1]
     assert np.all(uni.event_counts[1] == -1) and np.all(uni.event_counts[[0, 2], :, 1] > 1.8e5)
+    # the switch: runaway="raise" refuses the run before anything is simulated
+    uni2 = GBM_CPL_Universe(Population(**cols), save_path=None)
+    with pytest.raises(_capi.EngineError, match="do not fit the memory budget"):
+        uni2.go(seed=3, save=False, runaway="raise")
+    with pytest.raises(ValueError):
+        uni2.go(seed=3, save=False, runaway="truncate")
 
 
 def test_c1_readme_demo(engine):
