@@ -383,8 +383,23 @@ def run_gpu(args):
         # bare device->host yardstick of the e2e arm: ONE plain async copy of 1 GiB into pinned host memory, all
         # ranks at the same time (at N > 1 the GPUs of a box share the host's PCIe / memory side)
         pin = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+        pin.copy_(buf_a, non_blocking=True)
+        # SUSTAINED and barrier-synchronised: 4 x 1 GiB back to back on every rank at the same moment.  (A best-of-3
+        # of single copies, as in round 1, catches moments when the other ranks are idle: at 8 GPUs it read 18.9 GB/s
+        # per GPU where the box sustains 11.4 -- scripts/e2e_probe.py, 91 GB/s for the eight together.)
         sync_all()
-        peaks_live["d2h_pinned_gbs_per_gpu_all_ranks_concurrent"] = live_bw(lambda: pin.copy_(buf_a, non_blocking=True), 1 << 30, reps=3)
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(4):
+            pin.copy_(buf_a, non_blocking=True)
+        b_.record()
+        b_.synchronize()
+        d2h_rate = 4 * (1 << 30) / (a.elapsed_time(b_) * 1e-3) / 1e9
+        peaks_live["d2h_pinned_gbs_per_gpu_all_ranks_concurrent"] = d2h_rate
+        if dist is not None:
+            agg = torch.tensor([d2h_rate], dtype=torch.float64, device=dev)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            peaks_live["d2h_pinned_gbs_all_ranks_sum"] = float(agg.item())
         sync_all()
         del buf_a, buf_b, pin
     except Exception as e:          # noqa: BLE001
@@ -614,8 +629,9 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h // e2e_steps,
                     "steps": e2e_steps, "d2h_gbs_per_gpu": e2e_d2h_gbs, "d2h_yardstick_gbs_per_gpu": d2h_peak,
                     "frac_of_d2h_yardstick": (e2e_d2h_gbs / d2h_peak) if d2h_peak else None,
-                    "note": "bound by the device->host copy of the six event lists (18 B per event); the yardstick is one "
-                            "bare cudaMemcpyAsync of 1 GiB into pinned memory issued by all ranks at once"},
+                    "note": "bound by the device->host copy of the six event lists (18 B per event); the yardstick is a bare "
+                            "sustained copy into pinned memory (4 x 1 GiB back to back) issued by all ranks at the same moment: "
+                            "the host side of a box is shared by its GPUs"},
             "gpu_launches": int(launches),
             "rates": {"candidates_per_s": float(counts["n_candidates"].sum()) * world / (ms_max / args.steps * 1e-3),
                       "rejection_trials_per_s": float(counts["n_trials"].sum()) * world / (ms_max / args.steps * 1e-3)},
