@@ -296,7 +296,7 @@ __device__ __forceinline__ unsigned thin_accept(const LambdaTab *tab, const cgrb
 // cell's bound, or farther from the interpolation than the margin).
 __device__ __forceinline__ unsigned thin_accept_majorant(const LambdaTab *tab, const cgrb_unit_t &u,
                                                          const double2 *__restrict__ sq, const ThinCum tc, double gscale,
-                                                         double h, double tau, double u2, double *t_out,
+                                                         double h, double inv_fh, double tau, double u2, double *t_out,
                                                          long long *n_exact)
 {
     const int n = (int)u.tab_n;
@@ -308,8 +308,13 @@ __device__ __forceinline__ unsigned thin_accept_majorant(const LambdaTab *tab, c
         Lj1 = __ldg(tc.L + j + 1);
     }
     const double2 n0 = __ldg(sq + j), n1 = __ldg(sq + j + 1);
-    const double P = majorant_of(n0, n1);
     const double wdt = Lj1 - Lj;                    // = fmax h P_j: expected candidates of the cell
+    // the cell's majorant as the proposal actually realises it: candidates fall into the cell at the rate wdt / h, so
+    // the acceptance probability that leaves lambda(t) is p / (wdt / (fmax h)) -- one multiplication, and exact even
+    // where the rounding of the cumulative sums moved wdt by an ulp of Lambda (majorant_of(n0, n1) to ~1e-12)
+    // (a cell clamped at the reference's own ceiling P = 1 -- p may exceed 1 there -- must read exactly 1)
+    const double Pw = wdt * inv_fh;
+    const double P = (Pw > 1.0 - 1e-9) ? 1.0 : Pw;
     double fr = 0.0;
     if (wdt > 1e-30) {
         double r = (double)__frcp_rn((float)wdt);   // 1 / wdt by two Newton steps (monotone map inside the cell)
@@ -387,6 +392,7 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
     const double sq_inv_h = squeeze ? (double)(u.tab_n - 1) / (u.src_tstop - u.src_tstart) : 0.0;
     const double maj_h = maj ? (u.src_tstop - u.src_tstart) / (double)(u.tab_n - 1) : 0.0;
     const double maj_gscale = (maj && stop > 0.0) ? (double)(u.tab_n - 1) / stop : 0.0;
+    const double maj_inv_fh = (maj && maj_h > 0.0 && u.fmax > 0.0) ? 1.0 / (u.fmax * maj_h) : 0.0;
     unsigned vflags = 0u;                  // THIN_*_VIOLATED bits of the exact evaluations
     double *seg = stage + u.src_off + wk.start;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -421,9 +427,9 @@ __global__ void __launch_bounds__(NT, THIN_CTAS) k_source_thin(const double *__r
             PairDraw d = pair_draw(rng, wk.unit, u.stream_id, ST_SRC_TIME, (wk.start + j0) >> 1, 1);
             if (maj) {
                 const double tau_a = ta, tau_b = tb;
-                unsigned ra = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_a, d.a, &ta, &n_exact), rb = 0u;
+                unsigned ra = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, maj_inv_fh, tau_a, d.a, &ta, &n_exact), rb = 0u;
                 if (vb)
-                    rb = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, tau_b, d.b, &tb, &n_exact);
+                    rb = thin_accept_majorant(&tab, u, sq, tc, maj_gscale, maj_h, maj_inv_fh, tau_b, d.b, &tb, &n_exact);
                 aa = (ra & THIN_ACC) != 0u;
                 ab = (rb & THIN_ACC) != 0u;
                 vflags |= ra | rb;
