@@ -249,7 +249,7 @@ int cgrb_fmax(const double *d_dtab, cgrb_unit_t *d_units, int n_units, int inter
     return check_launch("cgrb_fmax");
 }
 
-int64_t cgrb_thin_cum_bytes(int64_t n_nodes_total) { return 12 * (n_nodes_total > 0 ? n_nodes_total : 0) + 8; }
+int64_t cgrb_thin_cum_bytes(int64_t n_nodes_total) { return 20 * (n_nodes_total > 0 ? n_nodes_total : 0) + 8; }
 
 int cgrb_thin_tables(const double *d_dtab, const cgrb_unit_t *d_units, int n_units, const cgrb_work_t *d_work,
                      int64_t n_work, double *d_thin_tab, void *d_thin_cum, int64_t n_nodes_total, void *stream)

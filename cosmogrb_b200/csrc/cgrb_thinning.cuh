@@ -18,18 +18,20 @@
 // unit-rate Poisson process in operational time tau = Lambda(t) = fmax * integral of P (the same stored
 // exponential gaps, with rate 1), mapped back through the piecewise-linear Lambda, and kept with probability
 // min(p, 1) / P_j: the accepted events are the same process, min(lambda, fmax), from Lambda_T candidates
-// instead of fmax * T.  `thin_cum`: per node the cumulative Lambda (double), then per node a search guide
-// (int32: the cell of tau = g * Lambda_T / (n - 1)).
+// instead of fmax * T.  `thin_cum`: per node the cumulative Lambda (double), then per cell the reciprocal of its
+// width in operational time (double), then per node a search guide (int32: the cell of tau = g * Lambda_T / (n - 1)).
 // ------------------------------------------------------------------------------------------
 struct ThinCum {
     const double *L;        // [tab_n] cumulative operational time at the nodes
+    const double *invw;     // [tab_n - 1] 1 / (L[j+1] - L[j]) of every cell (0 for an empty cell)
     const int32_t *guide;   // [tab_n - 1]
 };
 __device__ __forceinline__ ThinCum thin_cum_of(const double *thin_cum, int64_t n_nodes_total, const cgrb_unit_t &u)
 {
     ThinCum c;
     c.L = thin_cum + u.tab_off;
-    c.guide = reinterpret_cast<const int32_t *>(thin_cum + n_nodes_total) + u.tab_off;
+    c.invw = thin_cum + n_nodes_total + u.tab_off;
+    c.guide = reinterpret_cast<const int32_t *>(thin_cum + 2 * n_nodes_total) + u.tab_off;
     return c;
 }
 __device__ __forceinline__ bool unit_uses_majorant(const double *thin_cum, const cgrb_rng_t &rng, const cgrb_unit_t &u)
@@ -112,7 +114,11 @@ __global__ void __launch_bounds__(NT) k_thin_guide(const cgrb_unit_t *__restrict
     if (g >= n - 1)
         return;
     const double *L = thin_cum + u->tab_off;
-    int32_t *guide = reinterpret_cast<int32_t *>(thin_cum + n_nodes_total) + u->tab_off;
+    int32_t *guide = reinterpret_cast<int32_t *>(thin_cum + 2 * n_nodes_total) + u->tab_off;
+    {
+        const double wdt = L[g + 1] - L[g];         // cell g: the map tau -> t inside it is one multiplication
+        thin_cum[n_nodes_total + u->tab_off + g] = (wdt > 0.0) ? 1.0 / wdt : 0.0;
+    }
     const double target = (double)g * L[n - 1] / (double)(n - 1);
     int lo = 0, hi = n - 1;                     // largest j in [0, n-2] with L[j] <= target
     while (hi - lo > 1) {
@@ -315,14 +321,8 @@ __device__ __forceinline__ unsigned thin_accept_majorant(const LambdaTab *tab, c
     // (a cell clamped at the reference's own ceiling P = 1 -- p may exceed 1 there -- must read exactly 1)
     const double Pw = wdt * inv_fh;
     const double P = (Pw > 1.0 - 1e-9) ? 1.0 : Pw;
-    double fr = 0.0;
-    if (wdt > 1e-30) {
-        double r = (double)__frcp_rn((float)wdt);   // 1 / wdt by two Newton steps (monotone map inside the cell)
-        r = r * (2.0 - wdt * r);
-        r = r * (2.0 - wdt * r);
-        fr = fmin(fmax((tau - Lj) * r, 0.0), 1.0);
-    } else if (wdt > 0.0)
-        fr = fmin(fmax((tau - Lj) / wdt, 0.0), 1.0);
+    // position inside the cell: a monotone map (one multiplication by the cell's stored reciprocal width)
+    const double fr = fmin(fmax((tau - Lj) * __ldg(tc.invw + j), 0.0), 1.0);
     const double tj = u.src_tstart + (double)j * h;
     const double tj1 = (j == n - 2) ? u.src_tstop : u.src_tstart + (double)(j + 1) * h;
     const double t = fmin(fma(fr, h, tj), tj1);
