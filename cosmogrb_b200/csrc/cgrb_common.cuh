@@ -190,10 +190,14 @@ __device__ __forceinline__ double lambda_per_flux_at(const LambdaTab *tab, const
 // inclusive prefix is typically that far back.  Integer sums: the result does not depend on timing.
 // The state array must be zeroed before the launch.  Call with all 32 lanes of one warp.
 //
-// Forward progress: the caller takes its item index `w` from an atomic TICKET counter (zeroed with the state
-// array), not from blockIdx: every predecessor a warp can wait for was claimed by a CTA that is already running.
-// A warp only waits for the lanes at or before the nearest inclusive prefix, and a wait that outlasts
-// LB_WAIT_NS (20 s) gives up and reports it through *timed_out instead of hanging the device.
+// Forward progress: an item only ever waits for items with a SMALLER launch index of the same 1-D grid
+// (k_merge_deadtime: blockIdx.x is the tile's ticket in the level-major order, k_level_order), and CTAs of a 1-D
+// grid are dispatched in blockIdx order, so every predecessor is running or finished -- the assumption CUB's
+// decoupled look-back scan makes too.  (An atomic ticket counter claimed by persistent CTAs was built and measured:
+// CTAs holding claimed tiles behind the one they process form a convoy)  The assumption is not part of
+// the CUDA programming model, so no wait is unbounded: a warp only waits for the lanes at or before the nearest
+// inclusive prefix, and a wait that outlasts LB_WAIT_NS (20 s) gives up and reports it through *timed_out
+// (CGRB_ST_INTERNAL) instead of hanging the device.
 // ------------------------------------------------------------------------------------------
 #define LB_FLAG_AGG (1ull << 62)
 #define LB_FLAG_INC (2ull << 62)
