@@ -115,6 +115,23 @@ def capacity(rate, span):
     return cap.astype(np.int64)
 
 
+def source_work_list(src_cap, chunk, small):
+    """The thinning work list with per-unit segment lengths: unit u is cut into segments of ``small[1]`` candidates if
+    its capacity ``src_cap[u]`` is at most ``small[0]``, of ``chunk`` candidates otherwise (both even multiples of the
+    kernels' 512-candidate tile, at most CGRB_SEG); every unit owns at least one entry.  Same layout as
+    ``cgrb_build_work(which=0)``: entries ordered by unit, then by start."""
+    cap = np.asarray(src_cap, dtype=np.int64)
+    ch = np.where(cap <= small[0], small[1], chunk).astype(np.int64)
+    nseg = np.maximum((cap + ch - 1) // ch, 1)
+    w = np.zeros(int(nseg.sum()), dtype=_capi.WORK_DTYPE)
+    w["unit"] = np.repeat(np.arange(len(cap), dtype=np.int32), nseg)
+    first = np.concatenate(([0], np.cumsum(nseg)[:-1]))
+    seg = np.arange(len(w), dtype=np.int64) - np.repeat(first, nseg)
+    w["seg"] = seg
+    w["start"] = seg * np.repeat(ch, nseg)
+    return w
+
+
 def _unit_work_begin(work, n_units):
     return np.searchsorted(work["unit"], np.arange(n_units + 1), side="left").astype(np.int64)
 
@@ -419,15 +436,7 @@ class Engine(object):
                 w = _capi.build_work(b.units, which, chunk)
             else:
                 assert which == 0
-                cap = b.units["src_cap"].astype(np.int64)
-                ch = np.where(cap <= small[0], small[1], chunk).astype(np.int64)
-                nseg = np.maximum((cap + ch - 1) // ch, 1)
-                w = np.zeros(int(nseg.sum()), dtype=_capi.WORK_DTYPE)
-                w["unit"] = np.repeat(np.arange(b.n_units, dtype=np.int32), nseg)
-                first = np.concatenate(([0], np.cumsum(nseg)[:-1]))
-                seg = np.arange(len(w), dtype=np.int64) - np.repeat(first, nseg)
-                w["seg"] = seg
-                w["start"] = seg * np.repeat(ch, nseg)
+                w = source_work_list(b.units["src_cap"], chunk, small)
             wb = _unit_work_begin(w, b.n_units)
             t1 = _now()
             b.work[key] = (w, self.to_device(w), self.to_device(wb))

@@ -328,3 +328,32 @@ def test_h5_backend_string_datasets(tmp_path):
     r = store.open_tree(tmp_path / "s.h5")
     assert list(r.get("names")) == ["a", "bcd"] and list(r.get("extra_info/tags")) == ["x", "yz"]
     assert r.get("extra_info/note") == "hello"
+
+
+def test_source_work_list_per_unit_segments():
+    """engine.source_work_list: the thinning work list with short segments for small units.  With the rule off it is
+    cgrb_build_work(which=0); with it on every unit's candidates are covered once, by segments of its own length
+    (a function of the unit alone), starts even, segment lengths at most CGRB_SEG."""
+    from cosmogrb_b200 import _capi, engine
+
+    rs = np.random.RandomState(4)
+    caps = np.concatenate(([0, 1, 1023, 1024, 1025, 65536, 65537, 8192 * 3 + 1], rs.randint(1, 400000, 200)))
+    units = np.zeros(len(caps), dtype=_capi.UNIT_DTYPE)
+    units["src_cap"] = caps
+    ref = _capi.build_work(units, 0, _capi.SEG)
+    off = engine.source_work_list(caps, _capi.SEG, (-1, 1024))
+    assert np.array_equal(off, ref)
+    w = engine.source_work_list(caps, _capi.SEG, (65536, 1024))
+    assert np.all(np.diff(w["unit"]) >= 0) and set(w["unit"]) == set(range(len(caps)))
+    for u, cap in enumerate(caps):
+        mine = w[w["unit"] == u]
+        ch = 1024 if cap <= 65536 else _capi.SEG
+        assert np.array_equal(mine["seg"], np.arange(len(mine))) and np.array_equal(mine["start"], np.arange(len(mine)) * ch)
+        assert len(mine) == max(-(-int(cap) // ch), 1)
+        assert np.all(mine["start"] % 2 == 0) and ch <= _capi.SEG and ch % 512 == 0
+    # what the kernels derive from it: a segment ends where the unit's next entry starts, the last one at the capacity
+    nxt_same = np.concatenate((w["unit"][1:] == w["unit"][:-1], [False]))
+    seg_len = np.where(nxt_same, np.concatenate((w["start"][1:], [0])) - w["start"], _capi.SEG)
+    n = np.minimum(seg_len, caps[w["unit"]] - w["start"])
+    assert np.all(n <= _capi.SEG) and np.all(n[caps[w["unit"]] > 0] > 0)
+    assert np.array_equal(np.bincount(w["unit"], weights=np.maximum(n, 0), minlength=len(caps)).astype(np.int64), caps)
