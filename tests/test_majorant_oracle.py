@@ -170,3 +170,36 @@ def test_squeeze_margins_bound_the_interpolation_error(T, trise, tdecay, n):
         assert P[0] < 1e-6
     finite = np.isfinite(m[cell])
     assert np.max(err[finite] / m[cell][finite]) < 0.75         # measured worst case 0.45: head-room, not luck
+
+
+@pytest.mark.parametrize("name,params,det", _cases()[:4])
+def test_cell_bound_from_the_cell_width(name, params, det):
+    """Round 2: k_source_thin takes a cell's majorant from the cell's own width in operational time,
+    P = (L[j+1] - L[j]) / (fmax h) snapped to 1 above 1 - 1e-9, and the position inside the cell from the stored
+    reciprocal width.  The cumulative sums round, so P differs from the tabulated bound -- by far less than the 1e-9
+    tolerance of the kernel's self-check -- and a cell clamped at the reference's ceiling reads exactly 1."""
+    rsp = h.response(det)
+    s = h.oracle_source(rsp, **params)
+    ea = rsp.effective_area_packed
+    T = params["duration"]
+    fmax = orc.fmax(s, ea, 0.0, T)
+    tab = _table(s, ea, fmax, T)
+    if tab is None:
+        pytest.skip("no table for this unit")
+    t, p, m, P, L = tab
+    hh = T / (len(t) - 1)
+    wdt = np.diff(L)
+    Pw = wdt * (1.0 / (fmax * hh))
+    Pk = np.where(Pw > 1.0 - 1e-9, 1.0, Pw)
+    assert np.all(np.abs(Pk - P) <= 1e-10 * np.maximum(P, 1e-300) + 1e-13 * L[-1] / (fmax * hh))
+    assert np.all(Pk[P == 1.0] == 1.0)
+    # the map tau -> t inside a cell by the stored reciprocal: monotone, inside the cell, ends on the nodes
+    invw = np.where(wdt > 0.0, 1.0 / np.where(wdt > 0.0, wdt, 1.0), 0.0)
+    rs = np.random.RandomState(5)
+    j = rs.randint(0, len(wdt), 20000)
+    tau = L[j] + np.sort(rs.uniform(0.0, 1.0, 20000)) * wdt[j]
+    fr = np.clip((tau - L[j]) * invw[j], 0.0, 1.0)
+    tt = np.minimum(t[j] + fr * hh, t[j + 1])
+    assert np.all((tt >= t[j]) & (tt <= t[j + 1]))
+    exact = t[j] + np.where(wdt[j] > 0, (tau - L[j]) / np.where(wdt[j] > 0, wdt[j], 1.0), 0.0) * hh
+    assert np.all(np.abs(tt - exact) <= 4e-16 * (np.abs(exact) + hh))
