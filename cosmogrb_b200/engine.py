@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import sys
 import threading
 from dataclasses import dataclass, field
 from typing import Optional
@@ -274,7 +275,16 @@ class Engine(object):
         if i < len(bufs) and bufs[i].dtype == dtype and bufs[i].numel() >= n:
             return bufs[i]
         t0 = _now()
-        t = torch.empty(n + n // 4 + 1024, dtype=dtype, device=self.device)      # head-room: batches vary in size
+        if os.environ.get("CGRB_POOL_LOG"):
+            had = (str(bufs[i].dtype), bufs[i].numel()) if i < len(bufs) else None
+            print(f"[pool miss] slot {i}: want {dtype} x {n}, had {had}", file=sys.stderr, flush=True)
+        # head-room: batches vary in size.  Allocated in the DEFAULT stream's context whatever stream the batch runs
+        # on: torch's caching allocator keeps one block pool per stream, and with the two batch streams of a population
+        # run the outgrown buffers of one stream were no use to the other -- device memory filled up with cached
+        # blocks and every further growth went through the allocator's free-everything-and-retry path (0.6 s per
+        # 100,000 bursts).  Ordering is the pool's own: a slot is reused only after its previous batch was read back.
+        with torch.cuda.stream(torch.cuda.default_stream(self.device)):
+            t = torch.empty(n + n // 4 + 1024, dtype=dtype, device=self.device)
         self.host_times["alloc"] = self.host_times.get("alloc", 0.0) + (_now() - t0)
         if i < len(bufs):
             bufs[i] = t

@@ -53,6 +53,7 @@ for name, m in prof:
 nsim = n - len(uni.skipped)
 print(f"n={n} simulated={nsim} batches={uni.n_batches} batch_bytes={os.environ.get('COSMOGRB_B200_BATCH_BYTES')} "
       f"wall {1e3 * (t1 - t0):.1f} ms = {nsim / (t1 - t0):.0f} GRB/s; kernels {sum(pk.values()):.1f} ms; clocks {clk}")
+print(f"   host: {dict((k, round(v, 3)) for k, v in uni.timings.items())} {dict((k, round(v, 3)) for k, v in _eng.host_times.items())}")
 print("   per 1000 bursts: " + ", ".join(f"{k} {v * 1000 / nsim:.2f}" for k, v in sorted(pk.items(), key=lambda kv: -kv[1])[:10]))
 # per batch: events of each kind against the live time of the streaming kernels (is a slow kernel slow everywhere, or
 # on the few batches that hold the bright bursts?)
