@@ -85,7 +85,7 @@ class Tree(object):
                 n = q[len(prefix):].split("/")[0]
                 if n and n not in names:
                     names.append(n)
-        return names
+        return sorted(names)                    # h5py lists a group's members by name, whatever the backend
 
     def is_group(self, path):
         return _norm(path) in self._attrs

@@ -108,7 +108,7 @@ def test_grb_file_round_trip(tmp_path, backend):
     g = GRBSave.from_file(fn)
     assert (g.name, g.z, g.ra, g.dec, g.duration, g.T0) == ("SynthGRB_0", 1.0, 312.0, -62.0, 2.0, 0.1)
     assert g.source_params["alpha"] == -0.66 and g.extra_info["note"] == "x"
-    assert list(g.keys()) == ["n0", "n1", "b0"]
+    assert list(g.keys()) == ["b0", "n0", "n1"]          # name order, as h5py lists a group (either backend)
     for (lc, rsp) in pairs:
         got = g[lc.name]["lightcurve"]
         assert np.array_equal(got.times, lc.times) and np.array_equal(got.pha, lc.pha)
