@@ -286,8 +286,10 @@ __global__ void __launch_bounds__(NT) k_energy_rows(const cgrb_unit_t *__restric
     row_guides[r * CGRB_ENV_SEGS + j] = (uint8_t)seg;
 }
 
+// resident CTAs per SM the kernel is compiled for: 4 (64 registers) since the trial loop's carried state was cut to
+// what it needs (3.03 ms on C2 against 3.30 at 3 CTAs / 80 registers; before that cut 4 CTAs lost to their spills)
 #ifndef ENV_MIN_CTAS
-#define ENV_MIN_CTAS 3
+#define ENV_MIN_CTAS 4
 #endif
 struct EnvSmem {
     double xlo[CGRB_ENV_SEGS];
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
     __shared__ __align__(128) uint8_t s_guide[GUIDE_BYTES];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ cgrb_unit_t u;
-    __shared__ long long s_wl[NW];
+    __shared__ unsigned s_trials[NW];
     __shared__ double ck[16];
     const int64_t w = blockIdx.x;
     if (w >= n_work)
@@ -420,27 +422,41 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
 
     // Lane refill: every warp owns a contiguous slice of the chunk; a lane that accepted immediately takes
     // the warp's next photon, so no lane idles on a neighbour's geometric tail.
+    // The state a lane carries from trial to trial is kept to eleven 32-bit registers (the loop runs at the 80
+    // registers of three CTAs per SM: whatever does not fit is spilled and re-read every trial): photons are
+    // addressed relative to the work item's first one (32-bit), everything derived from (k, h, wq) -- the row total,
+    // the hull line's slope term -- is re-read or recomputed where it is used, trials are counted per warp (one
+    // per active lane and iteration), the status bits are raised where they occur.
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t per = (chunk_end - wk.start + NW - 1) / NW;
-    const int64_t wbeg = wk.start + (int64_t)wid * per, wend = min(wbeg + per, chunk_end);
-    int64_t next = wbeg;                 // warp-uniform
-    long long my_trials = 0;
-    bool capped = false, active = false, violated = false;
+    if (chunk_end - wk.start > 0x7fffffffll) {          // a work item is a few 10^4 photons; 2^31 is a caller's error
+        if (threadIdx.x == 0)
+            atomicOr(&counts[wk.unit].status, CGRB_ST_INTERNAL);
+        return;
+    }
+    const int len = (int)(chunk_end - wk.start);
+    const int per = (len + NW - 1) / NW;
+    const int wbeg = wid * per, wend = min(wbeg + per, len);    // the warp's slice, relative to wk.start
+    int next = wbeg;                     // warp-uniform
+    const int64_t item_off = u.src_off + wk.start;              // photon wk.start + di lives at item_off + di
+    if (lane == 0)
+        s_trials[wid] = 0;               // the warp's trial count (every active lane of an iteration is one trial)
+    bool active = false;
     // per-lane photon state; k (table row) and h (hull position) persist from photon to photon: a lane's
     // photons come in time order, so both usually advance by zero or one step
-    int64_t i = 0;
+    int di = 0;
     uint32_t j = 0;
     int k = -1, h = -1;
-    double wq = 0.0, s_idx = 0.0, t_clip = 0.0, total = 0.0;
+    double wq = 0.0;
+#define PHOTON_I (wk.start + (int64_t)di)
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, !active);
         if (need) {
-            const int64_t cand = next + __popc(need & ((1u << lane) - 1u));
+            const int cand = next + __popc(need & ((1u << lane) - 1u));
             next += __popc(need);
             if (!active && cand < wend) {
-                i = cand;
+                di = cand;
                 j = 0;
-                const double t = times_src[u.src_off + i];
+                const double t = times_src[item_off + di];
                 bool regular = (t > c_tlo) && (t < c_thi) && n_hull > 0;
                 wq = c_wa + c_wb * t;                           // (1+z) / ec(t)
                 {
@@ -482,9 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
                         hh = lo;
                     }
                     h = hh;
-                    s_idx = sm.hull_E[h] * wq;
-                    t_clip = sm.hull_lA5[h] - s_idx;
-                    total = __ldg(unit_rows + (size_t)k * ENV_ROW + CGRB_ENV_SEGS);
+                    const double total = __ldg(unit_rows + (size_t)k * ENV_ROW + CGRB_ENV_SEGS);
                     if (!(total > 0.0) || isinf(total))
                         regular = false;
                 }
@@ -493,30 +507,43 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
                 else {
                     // degenerate photon: the literal loop, right here (rare)
                     int64_t ntr = 0;
+                    bool cap1 = false;
                     EaGuess eg = make_ea_guess(sm.eax);
-                    const double x = literal_photon_serial(u, dt, sm.eax, sm.eay, eg, interp_extrap, rng.seed, i, t,
-                                                           max_trials, &ntr, &capped);
+                    const double x = literal_photon_serial(u, dt, sm.eax, sm.eay, eg, interp_extrap, rng.seed, PHOTON_I, t,
+                                                           max_trials, &ntr, &cap1);
+                    if (cap1)
+                        atomicOr(&counts[wk.unit].status, CGRB_ST_TRIAL_CAP);
                     if (DIAG && energy_src)
-                        energy_src[u.src_off + i] = x;
+                        energy_src[item_off + di] = x;
                     if (FOLD)
-                        pha_src[u.src_off + i] = (uint8_t)digitize_one(sm.edges, s_guide, cum, x, rng.seed, u.stream_id, i);
+                        pha_src[item_off + di] = (uint8_t)digitize_one(sm.edges, s_guide, cum, x, rng.seed, u.stream_id, PHOTON_I);
                     if (DIAG && trials_out)
-                        trials_out[u.src_off + i] = -(int32_t)ntr;      // negative: the literal loop (its channel comes from ST_SRC_CHAN)
-                    my_trials += ntr;
+                        trials_out[item_off + di] = -(int32_t)ntr;      // negative: the literal loop (its channel comes from ST_SRC_CHAN)
+                    if (ntr)                                            // rare path: straight to the unit's counter
+                        atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)ntr);
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, active)) {
+        const unsigned trying = __ballot_sync(0xffffffffu, active);
+        if (!trying) {
             if (next >= wend)
                 break;
             continue;
         }
+        if (lane == 0) {
+            unsigned v = s_trials[wid] + __popc(trying);
+            if (v & 0x80000000u) {          // never in practice: 2^31 trials in one warp's slice
+                atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)v);
+                v = 0;
+            }
+            s_trials[wid] = v;
+        }
         if (active) {
             const double *row = unit_rows + (size_t)k * ENV_ROW;
-            Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)i, j);
+            Philox4 p = philox_at(make_key(rng.seed), u.stream_id, ST_SRC_ENERGY, (uint64_t)PHOTON_I, j);
             const TrialDraw td = trial_draw(p);     // proposal, height and (if accepted) the channel from ONE call
             const double U = td.U, V = td.V;
-            const double y = U * total;
+            const double y = U * __ldg(row + CGRB_ENV_SEGS);    // the row's total: an L1 hit behind the Philox rounds
             // segment: row[lo] <= y < row[lo+1], walking forward from the row's guide
             int lo = unit_guides[k * CGRB_ENV_SEGS + min((int)(U * (double)CGRB_ENV_SEGS), CGRB_ENV_SEGS - 1)];
             double c0 = __ldg(row + lo), c1 = __ldg(row + lo + 1);
@@ -544,8 +571,9 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
                     A = sm.eay[CGRB_NBINS - 1];
             }
             A = fmax(A, 0.0);
-            if (sm.logAmax[lo] - xl * wq > t_clip)
-                A = fmin(A, exp(sm.hull_lA5[h] + s - s_idx));   // the literal envelope clips f here
+            const double s_idx = __dmul_rn(sm.hull_E[h], wq), lA5 = sm.hull_lA5[h];
+            if (sm.logAmax[lo] - xl * wq > lA5 - s_idx)
+                A = fmin(A, exp(lA5 + s - s_idx));   // the literal envelope clips f here
             // target / envelope = [A x^a / M_lo] exp(-d), decided from the bounds
             // 1 - d + d^2/2 - d^3/6 <= exp(-d) <= 1 - d + d^2/2 whenever they agree.  The envelope of row k is
             // M_j exp(-xlo_j w_k) exp(-emin (w - w_k)) >= M_j exp(-xlo_j w): the common factor in w - w_k costs
@@ -555,7 +583,8 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
             const double qhi = fma(d, fma(d, 0.5, -1.0), 1.0);
             const double qlo = qhi - d * d * d * (1.0 / 6.0);
             j++;
-            violated |= base * qlo > 1.000001;      // the envelope must dominate the target (self-check)
+            if (base * qlo > 1.000001)              // the envelope must dominate the target (self-check; never taken)
+                atomicOr(&counts[wk.unit].status, CGRB_ST_ENVELOPE);
             bool acc;
             if (V <= base * qlo)
                 acc = true;
@@ -566,7 +595,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
             const bool cap = !acc && j >= trial_cap;
             if (acc || cap) {
                 if (DIAG && energy_src)
-                    energy_src[u.src_off + i] = acc ? x : nan("");
+                    energy_src[item_off + di] = acc ? x : nan("");
                 if (FOLD) {
                     int pha;
                     if (acc) {
@@ -578,15 +607,15 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
                             b--;
                         if (b < 0)
                             b += CGRB_NBINS;                    // python negative index (x == emin)
-                        pha = nearest_cdf_guided(s_guide + b * CGRB_NCHAN, cum + (size_t)b * CGRB_NCHAN, td.C);
+                        pha = nearest_cdf_guided(s_guide + b * CGRB_NCHAN, cum + (size_t)b * CGRB_NCHAN, u32d(p.w));
                     } else
-                        pha = digitize_one(sm.edges, s_guide, cum, nan(""), rng.seed, u.stream_id, i);
-                    pha_src[u.src_off + i] = (uint8_t)pha;
+                        pha = digitize_one(sm.edges, s_guide, cum, nan(""), rng.seed, u.stream_id, PHOTON_I);
+                    pha_src[item_off + di] = (uint8_t)pha;
                 }
                 if (DIAG && trials_out)
-                    trials_out[u.src_off + i] = (int32_t)j;
-                my_trials += j;
-                capped |= cap;
+                    trials_out[item_off + di] = (int32_t)j;
+                if (cap)
+                    atomicOr(&counts[wk.unit].status, CGRB_ST_TRIAL_CAP);
                 active = false;
             }
         }
@@ -601,12 +630,8 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
 #undef c_tlo
 #undef c_thi
 #undef c_inv_opz
-    const long long tot = block_sum_ll(my_trials, s_wl);
-    if (threadIdx.x == 0 && tot)
-        atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)tot);
-    if (capped)
-        atomicOr(&counts[wk.unit].status, CGRB_ST_TRIAL_CAP);
-    if (violated)
-        atomicOr(&counts[wk.unit].status, CGRB_ST_ENVELOPE);
+#undef PHOTON_I
+    if (lane == 0 && s_trials[wid])
+        atomicAdd((unsigned long long *)&counts[wk.unit].n_trials, (unsigned long long)s_trials[wid]);
 }
 

@@ -376,12 +376,12 @@ static int energy_envelope_impl(int what, const char *who, const double *d_dtab,
         d_dtab, d_units, d_work, n_work, interp_extrap, *rng, max_trials, etab, rows, row_guides, d_times_src,    \
         d_energy_src, d_pha_src, d_trials, d_counts)))
     const bool diag = d_energy_src != nullptr || d_trials != nullptr;
-    // resident CTAs per SM the production variant is compiled for (register budget); CGRB_ENV_MIN_CTAS=2|3
+    // resident CTAs per SM the production variant is compiled for (register budget); CGRB_ENV_MIN_CTAS=2|3|4
     // switches it for tuning runs
     static int minb = 0;
     if (!minb) {
         const char *e = getenv("CGRB_ENV_MIN_CTAS");
-        minb = (e && e[0] == '2') ? 2 : (e && e[0] == '4') ? 4 : ENV_MIN_CTAS;
+        minb = (e && e[0] == '2') ? 2 : (e && e[0] == '3') ? 3 : (e && e[0] == '4') ? 4 : ENV_MIN_CTAS;
     }
     if (d_pha_src && diag)
         ENV_LAUNCH(true, true, ENV_MIN_CTAS);
