@@ -47,7 +47,7 @@ extern "C" {
 #define CGRB_ST_ENVELOPE 32u         /* energy envelope failed to dominate the target (bug)  */
 #define CGRB_ST_MAJORANT 128u        /* thinning majorant failed to dominate lambda(t) (bug)            */
 #define CGRB_ST_SQUEEZE 256u         /* squeeze margin failed to bound |p - interpolation| at an exact evaluation (bug) */
-#define CGRB_ST_INTERNAL 512u        /* a bounded wait inside a kernel gave up (look-back / bulk copy; never expected) */
+#define CGRB_ST_INTERNAL 512u        /* a bounded wait inside a kernel gave up (look-back / bulk copy; never expected), or a work item beyond a kernel's index range */
 #define CGRB_ST_DEADTIME_CHAIN 64u   /* physical dead time: unit handed to the serial fix-up (transient; cleared by it) */
 
 /* fixed GBM shape (instruments/gbm: 140 photon bins x 128 PHA channels) */
@@ -257,7 +257,10 @@ int cgrb_sample_energy(const double *d_dtab, const cgrb_unit_t *d_units, int n_u
  * reference's stream and therefore must use cgrb_sample_energy (returns CGRB_E_UNSUPPORTED).
  * Fused fold: with d_pha_src != NULL the kernel also performs Response.digitize on every accepted
  * energy (same Philox counters as cgrb_digitize, hence the same channels) and d_energy_src may then
- * be NULL, so photon energies never travel through HBM. */
+ * be NULL, so photon energies never travel through HBM.
+ * One work item (the photons from its start to the unit's next item) must hold fewer than 2^31 photons
+ * (the engine uses 16384); a longer one sets CGRB_ST_INTERNAL on the unit and is not sampled.
+ * n_trials counts one trial per active lane and loop iteration, the literal fall-back's trials added. */
 int64_t cgrb_energy_workspace_bytes(int n_units, int64_t n_rows);
 int cgrb_sample_energy_envelope(const double *d_dtab, const cgrb_unit_t *d_units, int n_units,
                                 const cgrb_work_t *d_work, int64_t n_work, int interp_extrap,
