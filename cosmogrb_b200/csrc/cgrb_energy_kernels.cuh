@@ -440,8 +440,8 @@ __global__ void __launch_bounds__(NT, MINB) k_sample_energy_env(const double *__
 
     // Lane refill: every warp owns a contiguous slice of the chunk; a lane that accepted immediately takes
     // the warp's next photon, so no lane idles on a neighbour's geometric tail.
-    // The state a lane carries from trial to trial is kept to eleven 32-bit registers (the loop runs at the 80
-    // registers of three CTAs per SM: whatever does not fit is spilled and re-read every trial): photons are
+    // The state a lane carries from trial to trial is kept small (the loop wants ~118 registers and runs in the 64
+    // of four CTAs per SM: whatever does not fit is spilled and re-read every trial): photons are
     // addressed relative to the work item's first one (32-bit), everything derived from (k, h, wq) -- the row total,
     // the hull line's slope term -- is re-read or recomputed where it is used, trials are counted per warp (one
     // per active lane and iteration), the status bits are raised where they occur.
