@@ -535,3 +535,65 @@ def test_dense_tiles_take_the_long_halo_and_stay_exact():
     assert slow[64] >= 5 and slow[512] == 0
     tb, _ = _events(rs, n, 500.0, 0.05)         # GBM background: never dense
     assert not any((tb[min(d0 + 2048, n) - 1] - tb[d0 - 64]) * 8 < (min(d0 + 2048, n) - d0 + 64) * TAU for d0 in range(2048, n, 2048))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# k_sample_energy_env: the lane-refill scheme (csrc/cgrb_energy_kernels.cuh).  A CTA owns the photons of one work item,
+# warp q the slice [q per, min((q + 1) per, len)) in 32-bit offsets from the item's first photon; a lane that finished a
+# photon takes the warp's next one, trial (photon, j) draws Philox counter (photon, j) whatever lane runs it, and the
+# trial counter of the unit is the number of active lanes summed over the loop's iterations.
+def _refill_warp(wbeg, wend, trials_of, cap):
+    """Python restatement of one warp's loop: returns {photon offset: trials spent}, and the warp's trial count."""
+    nxt = wbeg
+    active = [False] * 32
+    di = [0] * 32
+    j = [0] * 32
+    done, warp_trials = {}, 0
+    while True:
+        need = [not a for a in active]
+        if any(need):
+            before = 0
+            for lane in range(32):
+                if need[lane]:
+                    cand = nxt + before
+                    before += 1
+                    if cand < wend:
+                        di[lane], j[lane], active[lane] = cand, 0, True
+            nxt += before
+        if not any(active):
+            if nxt >= wend:
+                break
+            continue
+        warp_trials += sum(active)
+        for lane in range(32):
+            if active[lane]:
+                j[lane] += 1
+                acc = j[lane] >= trials_of(di[lane])          # the trial that accepts this photon
+                capped = (not acc) and j[lane] >= cap
+                if acc or capped:
+                    assert di[lane] not in done
+                    done[di[lane]] = j[lane]
+                    active[lane] = False
+    return done, warp_trials
+
+
+@pytest.mark.parametrize("length", [0, 1, 31, 32, 33, 255, 256, 257, 2049, 16384])
+def test_energy_kernel_lane_refill_covers_every_photon_once(length):
+    NW = 8
+    rng = np.random.RandomState(length)
+    need = rng.geometric(0.89, size=max(length, 1))            # trials a photon needs (1.12 on average, like C2)
+    need[::97] = 50                                            # a few photons beyond the cap
+    cap = 20
+    per = (length + NW - 1) // NW
+    seen, total = {}, 0
+    for wid in range(NW):
+        wbeg, wend = wid * per, min(wid * per + per, length)
+        done, wt = _refill_warp(wbeg, wend, lambda d: need[d], cap)
+        assert all(wbeg <= d < wend for d in done)
+        assert not (set(done) & set(seen))
+        seen.update(done)
+        total += wt
+    assert sorted(seen) == list(range(length))                 # every photon of the item, exactly once
+    want = np.minimum(need[:length], cap)
+    assert [seen[d] for d in range(length)] == list(want)      # trials per photon do not depend on the lane
+    assert total == int(want.sum())                            # per-warp popcount of active lanes == sum of trial counts
