@@ -61,7 +61,9 @@ def _format_value(value):
     if value is None:
         return " " * 20                         # undefined value (standard 4.2.1: blank value field)
     s = str(value).replace("'", "''").rstrip()
-    return f"'{s:<8s}'"
+    # closing quote not before column 20, value field filled to column 30 so that a comment starts in column 32:
+    # what astropy's Card and cfitsio both write (checked card by card against real GBM files, tests/test_fits_real_gbm.py)
+    return f"{chr(39)}{s:<8s}{chr(39)}".ljust(20)
 
 
 def format_card(key, value=None, comment=None):
