@@ -140,7 +140,10 @@ def open_tree(file_name):
         magic = fh.read(8)
     t = Tree()
     if magic.startswith(b"\x89HDF"):
-        import h5py
+        try:
+            import h5py
+        except ImportError:                      # a real HDF5 file and no h5py: the engine's own read-only decoder
+            from ..utils import hdf5_lite as h5py
 
         with h5py.File(file_name, "r") as f:
             t._attrs["/"] = dict(f.attrs)

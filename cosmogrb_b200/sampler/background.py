@@ -35,10 +35,10 @@ class BackgroundSpectrumTemplate(object):
     @classmethod
     def from_file(cls, file_name, start_at_one=False):
         try:
-            import h5py
-        except ImportError as e:        # pragma: no cover
-            raise ImportError("BackgroundSpectrumTemplate.from_file needs h5py") from e
-        with h5py.File(file_name, "r") as f:
+            import h5py as h5
+        except ImportError:             # the engine's own reader decodes the reference's template files
+            from ..utils import hdf5_lite as h5
+        with h5.File(file_name, "r") as f:
             counts = f["counts"][()]
         return cls(counts, start_at_one)
 

@@ -58,14 +58,38 @@ class Population(object):
                 return cls(**{k: z[k] for k in z.files})
         try:
             import popsynth
-        except ImportError as e:
-            raise ImportError(f"{file_name} is not an .npz population and popsynth is not installed") from e
+        except ImportError:
+            return cls._from_popsynth_hdf5(file_name)
         pop = popsynth.Population.from_file(file_name).to_sub_population()
         cols = dict(ra=pop.ra, dec=pop.dec, distances=pop.distances, duration=pop.duration)
         for k in ("ep", "alpha", "trise", "tdecay", "tau"):
             if hasattr(pop, k):
                 cols[k] = getattr(pop, k)
         cols["fluxes_latent"] = pop.fluxes.latent
+        return cls(**cols)
+
+    @classmethod
+    def _from_popsynth_hdf5(cls, file_name):
+        """A popsynth population file without popsynth (and without h5py: ``utils/hdf5_lite``).  The layout is the one
+        ``popsynth.Population.writeto`` produces -- ``distances``, ``fluxes`` (latent), ``theta`` / ``phi`` (sky
+        position in radians: ra = deg(phi), dec = 90 - deg(theta)), ``selection`` and one group per auxiliary quantity
+        under ``auxiliary_quantities`` with its ``true_values`` -- and, like ``to_sub_population()``
+        (universe/universe.py:45-47), only the selected objects are kept."""
+        from ..utils import hdf5_lite as h5
+
+        try:
+            f = h5.File(file_name)
+        except h5.HDF5Error as e:
+            raise ValueError(f"{file_name} is neither an .npz population nor a readable popsynth HDF5 file: {e}") from e
+        for need in ("distances", "fluxes", "theta", "phi", "selection", "auxiliary_quantities"):
+            if need not in f:
+                raise RuntimeError(f"{file_name}: not a popsynth population file (no {need!r})")
+        sel = np.asarray(f["selection"][()], dtype=bool)
+        cols = dict(ra=np.rad2deg(f["phi"][()])[sel], dec=(90.0 - np.rad2deg(f["theta"][()]))[sel],
+                    distances=f["distances"][()][sel], fluxes_latent=f["fluxes"][()][sel])
+        aux = f["auxiliary_quantities"]
+        for k in aux.keys():
+            cols[k] = aux[k]["true_values"][()][sel]
         return cls(**cols)
 
 
