@@ -13,6 +13,9 @@ installed (it is in the build image), so this module decodes the subset of the f
     filters deflate (zlib), shuffle, fletcher32 and LZF (h5py's filter 32000, decoded here);
   * attributes (message versions 1-3) of groups and datasets.
 
+Tested on real files (tests/test_hdf5_lite.py): everything h5py's default ``libver="earliest"`` writes -- version-0
+superblock, version-1 object headers, old-style groups -- which is what the reference's inputs are.  The version-2
+object header / link-message branch follows the format specification but no file of that kind was at hand.
 Anything else raises ``HDF5Error`` naming the unsupported feature -- nothing is guessed.  ``File`` mimics the few h5py
 idioms the callers use: ``f["a/b"]``, ``.keys()``, ``.attrs``, ``ds[()]``, ``ds.shape``, ``ds.dtype``, ``visititems``.
 """
@@ -107,7 +110,7 @@ class _Reader(object):
             tracked = bool(flags & 0x04)
             while blocks:
                 p, end = blocks.pop(0)
-                while p + 4 <= end - 4 + 4 and p + 4 <= end:
+                while p + 4 <= end:
                     mtype, msize, mflags = raw[p], self.u(p + 1, 2), raw[p + 3]
                     p += 4 + (2 if tracked else 0)
                     body = raw[p:p + msize]
