@@ -81,6 +81,8 @@ class _Reader(object):
             raise HDF5Error(f"offset / length sizes {self.O} / {self.L} are not supported")
         pos = 24 + (4 if ver == 1 else 0)
         self.base = self.u(pos, 8)
+        if self.base:
+            raise HDF5Error("a non-zero base address (user block) is not supported")
         pos += 4 * 8                                 # base, free-space info, end of file, driver info
         # root group symbol table entry
         self.root_header = self.u(pos + 8, 8)
